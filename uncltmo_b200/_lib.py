@@ -1,0 +1,80 @@
+"""ctypes binding of libuncltmo_b200.so, generated from the C-ABI header include/uncltmo_b200.h.
+
+There is no CPU or PyTorch fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libuncltmo_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "uncltmo_b200.h")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
+DTYPE_OF = {torch.float32: F32, torch.bfloat16: BF16}
+
+_lib = None
+_protos = None
+
+
+def _ctype(decl):
+    decl = decl.strip()
+    if "*" in decl or decl.startswith("uncl_stream_t"):
+        return ctypes.c_void_p
+    base = decl.split()[0] if not decl.startswith("unsigned") else "unsigned"
+    return {"int": ctypes.c_int, "long": ctypes.c_long, "float": ctypes.c_float, "double": ctypes.c_double,
+            "unsigned": ctypes.c_uint}[base]
+
+
+def prototypes():
+    """{name: (restype, [argtypes], takes_stream)} parsed from the header (single source of truth)."""
+    global _protos
+    if _protos is None:
+        src = re.sub(r"/\*.*?\*/", "", open(HEADER_PATH).read(), flags=re.S)
+        out = {}
+        for m in re.finditer(r"(const char\*|int)\s+(uncl_\w+)\s*\(([^)]*)\)\s*;", src):
+            ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+            arglist = [] if args in ("", "void") else [a for a in args.split(",")]
+            out[name] = (ctypes.c_char_p if "char" in ret else ctypes.c_int, [_ctype(a) for a in arglist],
+                         bool(arglist) and arglist[-1].strip().startswith("uncl_stream_t"))
+        _protos = out
+    return _protos
+
+
+def declared_symbols():
+    return sorted(prototypes())
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("uncltmo_b200: %s is missing - run `python -m uncltmo_b200.build` (or "
+                               "__graft_entry__.build()); there is no fallback path" % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (ret, args, _) in prototypes().items():
+            fn = getattr(l, name)  # AttributeError if the .so lacks a declared symbol
+            fn.restype = ret
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def ptr(t):
+    if isinstance(t, torch.Tensor):
+        if not t.is_cuda:
+            raise RuntimeError("uncltmo_b200 kernels need CUDA tensors (got %s); there is no CPU path" % t.device)
+        return t.data_ptr()
+    return t
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point on the current CUDA stream; raise RuntimeError on a non-zero return."""
+    l = lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = getattr(l, name)(*[ptr(a) for a in args], stream)
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, l.uncl_last_error().decode()))

@@ -1,0 +1,422 @@
+// 3x3 stride-1 convolution (and ConvTranspose 3x3 s1 as its padded/flipped twin) as an implicit GEMM on the
+// Blackwell tensor cores: tcgen05.mma (kind::f16, bf16 operands, fp32 accumulators in TMEM), operands staged by
+// TMA / bulk async copies, persistent warp-specialised CTAs (one per SM) with a double-buffered TMEM accumulator.
+//
+// Reference operator: models/unet_multi_filters/unet_parts.py:57-87 (double_conv), :126-141, :183-193
+// (ConvTranspose2d 3x3 s1 p0 == conv over a 2-px zero-padded input with flipped kernels; the zero padding is TMA
+// out-of-bounds fill), :319-322 (skip operators x^2 / sqrt(x+eps), emitted by the producing layer's epilogue),
+// :338-345 + Unet_singleFrame.py:207-209 (1x1 out conv + sigmoid, fused into the last conv's epilogue).
+//
+// How the conv becomes a GEMM without im2col and without re-loading the input once per tap:
+//   * activations are C8-blocked [N][C/8][H][W][8] bf16, so a TMA box {8ch, PW px, PH rows, 2 blocks} lands in
+//     shared memory as [2][PH*PW][8] - which IS the no-swizzle K-major UMMA operand layout (core matrix = 8
+//     consecutive pixels x 16 B, SBO = 128 B between 8-pixel groups, LBO = PH*PW*16 B between the two 8-channel
+//     halves of a K=16 step).
+//   * rows of the A operand are 128 CONSECUTIVE pixels of that halo tile.  A filter tap (ky,kx) is then just a
+//     different descriptor start address (+ (ky*PW+kx)*16 B) into the same tile: 9 MMAs per K-step reuse one
+//     halo tile, so shared memory is filled ~1.3x the input instead of 9x.
+//   * where 128 consecutive pixels wrap around the end of a tile row the accumulator row is garbage; every
+//     A row only feeds its own D row, so those rows are simply masked in the epilogue.
+// Weights are pre-packed per 16-channel K-chunk as [9 taps][2][NT][8] bf16 (K-major B operand, LBO = NT*16 B),
+// fetched with one cp.async.bulk per stage.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int kAccCols = 256;          // TMEM columns per accumulator stage (2 stages = 512 = all of TMEM)
+constexpr int kMaxStages = 6;
+
+struct TcParams {
+  const bf16* w;            // packed weights [NS][nchunk][ntaps][2][NT][8]
+  const float* bias;        // [C_out]
+  bf16* out;                // blocked output (may be null when fuse_outc)
+  long out_img_stride;
+  const float* outc_w;      // [C_out] (fuse_outc)
+  const float* outc_b;
+  float* out_img;           // [N][Ho][Wo] fp32 (fuse_outc)
+  float* out_logit;         // optional
+  int N, C_in, C_out, Ho, Wo, pad;
+  int NT, NS;               // N tile (<=128) and number of N splits
+  int MB;                   // M blocks (128 pixels each) per tile
+  int PW, PH;               // TMA box (halo tile) extent in pixels
+  int mode;                 // 0: row-aligned (tile = MB rows x 128 cols), 1: flattened (tile = MB*128 consecutive px)
+  int tiles_x, tiles_per_img, num_items;
+  int nchunk, ntaps, stages;
+  int a_box_bytes, a_stage_bytes, b_stage_bytes, stage_bytes;
+  int act, emit_skip, fuse_outc;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (sm_100 "version 1").
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);
+}
+
+// ---------------------------------------------------------------- tile geometry shared by the three roles
+struct Item {
+  int n, ns;          // image, N split
+  int bx, by;         // TMA box origin (input pixel coordinates, may be negative)
+  int moff0;          // start pixel (inside the box) of M block 0
+  int mb_act;         // active M blocks
+  int ty, tx, q0;     // row-aligned: tile row/col ; flattened: first flattened output index
+};
+
+__device__ __forceinline__ Item decode_item(const TcParams& p, int item) {
+  Item it;
+  const int tile = item / p.NS;
+  it.ns = item % p.NS;
+  it.n = tile / p.tiles_per_img;
+  const int t = tile % p.tiles_per_img;
+  if (p.mode == 0) {
+    it.ty = t / p.tiles_x;
+    it.tx = t % p.tiles_x;
+    it.bx = it.tx * 128 - p.pad;
+    it.by = it.ty * p.MB - p.pad;
+    it.moff0 = 0;
+    it.mb_act = min(p.MB, p.Ho - it.ty * p.MB);
+    it.q0 = 0;
+  } else {
+    const int pitch = p.Wo + 2;
+    it.q0 = t * 128 * p.MB;
+    const int y0 = it.q0 / pitch;
+    it.bx = -p.pad;
+    it.by = y0 - p.pad;
+    it.moff0 = it.q0 - y0 * pitch;
+    it.mb_act = min(p.MB, (p.Ho * pitch - it.q0 + 127) / 128);
+    it.ty = it.tx = 0;
+  }
+  return it;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  // carve: [stages x (A | B)] | barriers | tmem ptr | bias
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes + 128);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);  // [C_out] (+ [C_out] outc weights)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < p.C_out; i += kThreads) {
+    s_bias[i] = p.bias[i];
+    if (p.fuse_outc) s_bias[p.C_out + i] = p.outc_w[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)it.ns * p.nchunk * p.b_stage_bytes;
+        for (int ch = 0; ch < p.nchunk; ++ch) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = stage_base + (size_t)stage * p.stage_bytes;
+          mbar_expect_tx(&full[stage], (uint32_t)(p.a_box_bytes + p.b_stage_bytes));
+          tma_load_5d(sa, &tmap, &full[stage], 0, it.bx, it.by, ch * 2, it.n);
+          bulk_load(sa + p.a_stage_bytes, wsrc + (size_t)ch * p.b_stage_bytes, (uint32_t)p.b_stage_bytes, &full[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t lbo_a = (uint32_t)(p.PH * p.PW * 16), lbo_b = (uint32_t)(p.NT * 16);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const int mstep = (p.mode == 0) ? p.PW : 128;
+        for (int ch = 0; ch < p.nchunk; ++ch) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + (size_t)stage * p.stage_bytes);
+          const uint32_t sb = sa + (uint32_t)p.a_stage_bytes;
+          for (int t = 0; t < p.ntaps; ++t) {
+            const int tapoff = (p.ntaps == 9) ? (t / 3) * p.PW + (t % 3) : 0;
+            const uint64_t bdesc = make_desc(sb + (uint32_t)(t * 2 * p.NT * 16), lbo_b, 128);
+            const uint32_t accum = (ch > 0 || t > 0) ? 1u : 0u;
+            for (int b = 0; b < it.mb_act; ++b) {
+              const uint64_t adesc = make_desc(sa + (uint32_t)((it.moff0 + b * mstep + tapoff) * 16), lbo_a, 128);
+              tc_mma_bf16(tmem_base + (uint32_t)(acc * kAccCols + b * p.NT), adesc, bdesc, idesc, accum);
+            }
+          }
+          tc_commit(&empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue (4 warps = 128 TMEM lanes) ===============================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const long cb_stride = (long)p.Ho * p.Wo * 8;
+    const int Cb = p.C_out / 8;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const Item it = decode_item(p, item);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      for (int b = 0; b < it.mb_act; ++b) {
+        int oy, ox;
+        if (p.mode == 0) {
+          oy = it.ty * p.MB + b;
+          ox = it.tx * 128 + row;
+        } else {
+          const int q = it.q0 + b * 128 + row;
+          oy = q / (p.Wo + 2);
+          ox = q % (p.Wo + 2);
+        }
+        const bool valid = (oy < p.Ho) && (ox < p.Wo);
+        const long pix = (long)oy * p.Wo + ox;
+        float logit = 0.f;
+        for (int c0 = 0; c0 < p.NT; c0 += 32) {
+          uint32_t r[32];
+          tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccCols + b * p.NT + c0), r);
+          if (valid) {
+            const int cbase = it.ns * p.NT + c0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                v[j] = apply_act(__uint_as_float(r[g * 8 + j]) + s_bias[cbase + g * 8 + j], p.act);
+              if (p.out != nullptr) {
+                bf16* o = p.out + (long)it.n * p.out_img_stride + (long)(cbase / 8 + g) * cb_stride + pix * 8;
+                store8(o, v);
+                if (p.emit_skip) {
+                  float s[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) s[j] = v[j] * v[j];
+                  store8(o + (long)(2 * Cb) * cb_stride, s);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) s[j] = sqrtf(v[j] + 1e-8f);
+                  store8(o + (long)(3 * Cb) * cb_stride, s);
+                }
+              }
+              if (p.fuse_outc) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) logit = fmaf(v[j], s_bias[p.C_out + cbase + g * 8 + j], logit);
+              }
+            }
+          }
+        }
+        if (p.fuse_outc && valid) {
+          logit += __ldg(p.outc_b);
+          const long o = (long)it.n * p.Ho * p.Wo + pix;
+          if (p.out_logit) p.out_logit[o] = logit;
+          p.out_img[o] = 1.f / (1.f + expf(-logit));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                               long out_img_stride, int N, int C_in, int H, int W, int C_out, int pad, int act,
+                               int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b, float* out_img,
+                               float* out_logit, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && C_in % 16 == 0 && C_out % 32 == 0 && (pad == 0 || pad == 2),
+               "conv3x3_tc: unsupported C_in=%d C_out=%d pad=%d", C_in, C_out, pad);
+  TcParams p{};
+  p.NT = C_out < 128 ? C_out : 128;
+  UNCL_REQUIRE(C_out % p.NT == 0 && C_out <= 256, "conv3x3_tc: unsupported C_out=%d", C_out);
+  UNCL_REQUIRE(!fuse_outc || (C_out == p.NT && outc_w && outc_b && out_img), "conv3x3_tc: fuse_outc needs C_out<=128 and outc params");
+  UNCL_REQUIRE(out != nullptr || fuse_outc, "conv3x3_tc: no output requested");
+  UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "conv3x3_tc: input must be 16-byte aligned");
+  p.NS = C_out / p.NT;
+  p.w = reinterpret_cast<const bf16*>(w_packed);
+  p.bias = bias;
+  p.out = reinterpret_cast<bf16*>(out);
+  p.out_img_stride = out_img_stride;
+  p.outc_w = outc_w; p.outc_b = outc_b; p.out_img = out_img; p.out_logit = out_logit;
+  p.N = N; p.C_in = C_in; p.C_out = C_out; p.pad = pad;
+  p.Ho = H + 2 * pad - 2; p.Wo = W + 2 * pad - 2;
+  UNCL_REQUIRE(p.Ho > 0 && p.Wo > 0, "conv3x3_tc: empty output");
+  p.act = act; p.emit_skip = emit_skip; p.fuse_outc = fuse_outc;
+  p.ntaps = 9;
+  p.nchunk = C_in / 16;
+  const int mb_max = kAccCols / p.NT;
+  if (p.Wo >= 100) {
+    p.mode = 0;
+    p.MB = mb_max < p.Ho ? mb_max : p.Ho;
+    p.PW = 130; p.PH = p.MB + 2;
+    p.tiles_x = ceil_div(p.Wo, 128);
+    p.tiles_per_img = p.tiles_x * ceil_div(p.Ho, p.MB);
+  } else {
+    p.mode = 1;
+    const int pitch = p.Wo + 2, total = p.Ho * pitch;
+    p.MB = mb_max < ceil_div(total, 128) ? mb_max : ceil_div(total, 128);
+    p.PW = pitch;
+    p.PH = (pitch - 1 + 128 * p.MB - 1) / pitch + 1 + 2;
+    p.tiles_x = 1;
+    p.tiles_per_img = ceil_div(total, 128 * p.MB);
+  }
+  UNCL_REQUIRE(p.PW <= 256 && p.PH <= 256, "conv3x3_tc: halo tile too large (%d x %d)", p.PW, p.PH);
+  p.num_items = N * p.tiles_per_img * p.NS;
+  p.a_box_bytes = 2 * p.PH * p.PW * 16;
+  p.a_stage_bytes = (p.a_box_bytes + 127) & ~127;
+  p.b_stage_bytes = p.ntaps * 2 * p.NT * 16;
+  p.stage_bytes = p.a_stage_bytes + p.b_stage_bytes;  // both multiples of 128
+  const int tail = 128 + (2 * kMaxStages + 4) * 8 + 16 + 2 * C_out * 4 + 256;
+  const int budget = 227 * 1024 - tail;
+  p.stages = budget / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  UNCL_REQUIRE(p.stages >= 2, "conv3x3_tc: tile does not fit shared memory (%d B per stage)", p.stage_bytes);
+  int smem_bytes = p.stages * p.stage_bytes + tail;
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // force one CTA per SM (each CTA owns all 512 TMEM columns)
+
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return uncl_set_error(UNCL_ECUDA, "conv3x3_tc: cuTensorMapEncodeTiled unavailable");
+  CUtensorMap tmap;
+  const cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C_in / 8), (cuuint64_t)N};
+  const cuuint64_t gstr[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)in_img_stride * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)p.PW, (cuuint32_t)p.PH, 2, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "conv3x3_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "conv3x3_tc: smem attr: %s", cudaGetErrorString(e));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.num_items < sms ? p.num_items : sms;
+  conv3x3_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap, p);
+  return uncl_check_launch("conv3x3_tc");
+}

@@ -1,0 +1,214 @@
+// Bottleneck graph block of the generator (ViG Grapher + FFN on the 12x12 = 144-node grid).
+//
+// Reference: Unet_singleFrame.py:44-99 (GCNBlock), :20-42 (FFN); gcn_lib/torch_vertex.py:181-227 (Grapher_noBN),
+// :109-130 (DyGraphConv2d), :13-30 (MRConv2d); gcn_lib/torch_edge.py:135-159, 54-86, 9-20 (normalise, pairwise
+// distance + relative_pos, top-9); gcn_lib/torch_nn.py:81-102 (batched_index_select), :54-78 (BasicConv, groups=4).
+//
+// All internals are fp32 regardless of the conv precision: the KNN is a discrete choice (SURVEY.md "hard parts").
+// Tensors here are C8-blocked fp32 with HW = 144: [N][C/8][144][8].
+#include "common.cuh"
+
+constexpr int GN = 144;   // nodes
+constexpr int GK = 9;     // neighbours
+
+// x0 = in + pos_embed (pos_embed pre-blocked [C/8][144][8] fp32)
+template <typename T>
+__global__ void gcn_add_pos_kernel(const T* __restrict__ in, long in_img_stride, const float* __restrict__ pos,
+                                   float* __restrict__ out, int C, int N) {
+  const long per = (long)C * GN;
+  const long total = (long)N * per;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long n = i / per, o = i % per;
+    out[i] = to_f(in[n * in_img_stride + o]) + pos[o];
+  }
+}
+
+// Pointwise (1x1) conv on blocked fp32 tensors with groups, bias, activation, optional residual and per-sample
+// scale of the branch (DropPath: out = scale[n] * f(x) + res).  Weights packed [groups][Cin_g][Cout_g].
+// CTA: 64 pixels x 64 output channels; thread: 4 pixels x 4 channels.
+template <typename TOut>
+__global__ void __launch_bounds__(256) pw_conv_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, const float* __restrict__ res,
+                                                     const float* __restrict__ scale, TOut* __restrict__ out,
+                                                     long out_img_stride, int C_in, int C_out, int groups, int HW,
+                                                     int N, int act) {
+  __shared__ __align__(16) float s_a[32][64];  // [ci][pixel]
+  __shared__ __align__(16) float s_w[32][64];  // [ci][co]
+  const int cin_g = C_in / groups, cout_g = C_out / groups;
+  const int co0 = blockIdx.y * 64;
+  const int g = co0 / cout_g;
+  const int P = N * HW;
+  const int p0 = blockIdx.x * 64;
+  const int tp = (threadIdx.x & 15) * 4, tc = (threadIdx.x >> 4) * 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < cin_g; k0 += 32) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+      const int px = i & 63, ci = i >> 6;
+      const int p = p0 + px, c = g * cin_g + k0 + ci;
+      float v = 0.f;
+      if (p < P) {
+        const int n = p / HW, q = p % HW;
+        v = in[((long)n * (C_in / 8) + (c >> 3)) * HW * 8 + (long)q * 8 + (c & 7)];
+      }
+      s_a[ci][px] = v;
+    }
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+      const int co = i & 63, ci = i >> 6;
+      s_w[ci][co] = w[((long)g * cin_g + k0 + ci) * cout_g + (co0 - g * cout_g) + co];
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int ci = 0; ci < 32; ++ci) {
+      const float4 a = *reinterpret_cast<const float4*>(&s_a[ci][tp]);
+      const float4 b = *reinterpret_cast<const float4*>(&s_w[ci][tc]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = p0 + tp + i;
+    if (p >= P) continue;
+    const int n = p / HW, q = p % HW;
+    const float sc = scale ? scale[n] : 1.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = co0 + tc + j;
+      float v = apply_act(acc[i][j] + bias[c], act) * sc;
+      const long o = ((long)(c >> 3) * HW + q) * 8 + (c & 7);
+      if (res) v += res[(long)n * C_out * HW + o];
+      from_f(out[(long)n * out_img_stride + o], v);
+    }
+  }
+}
+
+// KNN graph + max-relative aggregation, one CTA per image (C = 256).
+//   yn = y / max(|y|_2, 1e-12) over channels; dist[i][j] = (|yn_i|^2 - 2 yn_i.yn_j) + |yn_j|^2 + relpos[i][j];
+//   idx[i] = 9 smallest; z = interleave(y, max_k(y[idx_k] - y_i)) -> [N][2C/8][144][8]
+template <int C>
+__global__ void __launch_bounds__(512) gcn_knn_agg_kernel(const float* __restrict__ y, const float* __restrict__ relpos,
+                                                         float* __restrict__ z, int* __restrict__ idx_out) {
+  extern __shared__ float smem[];
+  constexpr int LD = C + 1;
+  float* s_yn = smem;                 // [144][C+1]
+  float* s_sq = smem + GN * LD;       // [144]
+  int* s_idx = reinterpret_cast<int*>(s_sq + GN);  // [144][9]
+  const int n = blockIdx.x;
+  const float* yn_g = y + (long)n * C * GN;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+
+  for (int i = threadIdx.x; i < C * GN; i += blockDim.x) {
+    const int j = i & 7, node = (i >> 3) % GN, cb = i / (8 * GN);
+    s_yn[node * LD + cb * 8 + j] = yn_g[i];
+  }
+  __syncthreads();
+  for (int node = wid; node < GN; node += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) { const float v = s_yn[node * LD + c]; s = fmaf(v, v, s); }
+    s = warp_sum(s);
+    const float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);
+    float s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v = s_yn[node * LD + c] * inv;
+      s_yn[node * LD + c] = v;
+      s2 = fmaf(v, v, s2);
+    }
+    s2 = warp_sum(s2);
+    if (lane == 0) s_sq[node] = s2;
+  }
+  __syncthreads();
+  for (int i = wid; i < GN; i += nw) {
+    float d[5];
+    const float* yi = s_yn + i * LD;
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+      const int j = lane + 32 * t;
+      float dot = 0.f;
+      if (j < GN) {
+        const float* yj = s_yn + j * LD;
+#pragma unroll 8
+        for (int c = 0; c < C; ++c) dot = fmaf(yi[c], yj[c], dot);
+        d[t] = ((s_sq[i] + (-2.f * dot)) + s_sq[j]) + relpos[i * GN + j];
+      } else {
+        d[t] = INFINITY;
+      }
+    }
+    for (int k = 0; k < GK; ++k) {
+      float best = d[0];
+      int bj = lane;
+#pragma unroll
+      for (int t = 1; t < 5; ++t)
+        if (d[t] < best) { best = d[t]; bj = lane + 32 * t; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+      }
+      if ((bj & 31) == lane) d[bj >> 5] = INFINITY;
+      if (lane == 0) s_idx[i * GK + k] = bj;
+    }
+  }
+  __syncthreads();
+  if (idx_out)
+    for (int i = threadIdx.x; i < GN * GK; i += blockDim.x) idx_out[(long)n * GN * GK + i] = s_idx[i];
+  // aggregation on the raw (un-normalised) features, straight from global / L2
+  float* zn = z + (long)n * 2 * C * GN;
+  for (int i = wid; i < GN; i += nw) {
+    for (int cb = lane; cb < C / 8; cb += 32) {
+      float yi[8], m[8];
+      load8(yn_g + ((long)cb * GN + i) * 8, yi);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+      for (int k = 0; k < GK; ++k) {
+        float yj[8];
+        load8(yn_g + ((long)cb * GN + s_idx[i * GK + k]) * 8, yj);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], yj[j] - yi[j]);
+      }
+      const float lo[8] = {yi[0], m[0], yi[1], m[1], yi[2], m[2], yi[3], m[3]};
+      const float hi[8] = {yi[4], m[4], yi[5], m[5], yi[6], m[6], yi[7], m[7]};
+      store8(zn + ((long)(2 * cb) * GN + i) * 8, lo);
+      store8(zn + ((long)(2 * cb + 1) * GN + i) * 8, hi);
+    }
+  }
+}
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" int uncl_gcn_add_pos(const void* in, long in_img_stride, const float* pos, float* out, int N, int C,
+                                int dtype, cudaStream_t stream) {
+  UNCL_REQUIRE(C % 8 == 0 && N > 0, "gcn_add_pos: bad shape");
+  const long total = (long)N * C * GN;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  UNCL_DISPATCH_DTYPE(dtype, T, (gcn_add_pos_kernel<T><<<grid, 256, 0, stream>>>((const T*)in, in_img_stride, pos, out, C, N)));
+  return uncl_check_launch("gcn_add_pos");
+}
+
+// out dtype: fp32 or bf16 (the last FFN conv writes the generator's working dtype)
+extern "C" int uncl_pw_conv(const float* in, const float* w, const float* bias, const float* res, const float* scale,
+                            void* out, long out_img_stride, int N, int C_in, int C_out, int groups, int HW, int act,
+                            int out_dtype, cudaStream_t stream) {
+  UNCL_REQUIRE(groups > 0 && C_in % groups == 0 && C_out % groups == 0 && (C_in / groups) % 32 == 0 &&
+                   (C_out / groups) % 64 == 0 && N > 0,
+               "pw_conv: unsupported C_in=%d C_out=%d groups=%d", C_in, C_out, groups);
+  dim3 grid(ceil_div(N * HW, 64), C_out / 64);
+  UNCL_DISPATCH_DTYPE(out_dtype, T, (pw_conv_kernel<T><<<grid, 256, 0, stream>>>(in, w, bias, res, scale, (T*)out, out_img_stride, C_in, C_out, groups, HW, N, act)));
+  return uncl_check_launch("pw_conv");
+}
+
+extern "C" int uncl_gcn_knn_aggregate(const float* y, const float* relpos, float* z, int* idx_out, int N, int C,
+                                      cudaStream_t stream) {
+  UNCL_REQUIRE(C == 256 && N > 0, "gcn_knn_aggregate: only C=256 (shipped config) is built, got %d", C);
+  const size_t smem = (size_t)(GN * (C + 1) + GN) * sizeof(float) + (size_t)GN * GK * sizeof(int);
+  cudaError_t e = cudaFuncSetAttribute(gcn_knn_agg_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "gcn_knn_aggregate: smem attr: %s", cudaGetErrorString(e));
+  gcn_knn_agg_kernel<256><<<N, 512, smem, stream>>>(y, relpos, z, idx_out);
+  return uncl_check_launch("gcn_knn_aggregate");
+}

@@ -1,0 +1,351 @@
+"""Drop-in generator modules for the UnCLTMO `unet_multi_filters` U-Net (image and video variants).
+
+Same constructor / forward signatures and `state_dict` keys as the reference classes
+(models/unet_multi_filters/Unet_singleFrame.py:101-213, Unet.py:135-289), but
+every operator runs as an sm_100a kernel from libuncltmo_b200.so.  Only the shipped hyper-parameters are
+built (SURVEY.md §5 "config"); anything else raises at construction - there is no fallback.
+
+precision:
+  "fp32" - CUDA-core fp32 kernels (generator rel-L2 <= 1e-4 vs the reference).
+  "bf16" - bf16 activations; the 3x3 convolutions run on tcgen05 tensor cores (conv_tc.cu), fp32 accumulation;
+           the KNN graph of the bottleneck stays fp32 (rel-L2 <= 1e-2).
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib, packing
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, call
+
+SHIPPED = dict(n_channels=1, output_dim=1, last_layer="sigmoid", depth=4, layer_factor=4,
+               con_operator="square_and_square_root", filters=32, network="unet", unet_norm="none",
+               stretch_g="none", activation="relu", padding_mode="replicate", convtranspose_kernel=2)
+
+
+class _WB(nn.Module):
+    """weight (+bias) holder that contributes `<name>.weight` / `<name>.bias` to the state_dict."""
+
+    def __init__(self, wshape, bshape=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(wshape))
+        if bshape is not None:
+            self.bias = nn.Parameter(torch.zeros(bshape))
+
+
+class _Holder(nn.Module):
+    pass
+
+
+def _double(ci, co, second_transposed=False):
+    h = _Holder()
+    h.conv = _WB((co, ci, 3, 3), (co,))
+    h.conv1 = _WB((co, co, 3, 3), (co,))
+    h.second_transposed = second_transposed
+    return h
+
+
+class _GeneratorBase(nn.Module):
+    def __init__(self, n_channels, output_dim, last_layer, depth, layer_factor, con_operator, filters, bilinear,
+                 network, dilation, to_crop, unet_norm, stretch_g, activation, doubleConvTranspose, padding_mode,
+                 convtranspose_kernel, up_mode=True, recurrent_ch_ratio=1 / 32, precision="fp32"):
+        super().__init__()
+        got = dict(n_channels=n_channels, output_dim=output_dim, last_layer=last_layer, depth=depth,
+                   layer_factor=layer_factor, con_operator=con_operator, filters=filters, network=network,
+                   unet_norm=unet_norm, stretch_g=stretch_g, activation=activation, padding_mode=padding_mode,
+                   convtranspose_kernel=convtranspose_kernel)
+        bad = {k: v for k, v in got.items() if SHIPPED[k] != v}
+        if bad or bilinear or up_mode or not doubleConvTranspose:
+            raise NotImplementedError("uncltmo_b200 builds the shipped generator configuration only; unsupported: %r "
+                                      "(bilinear=%r up_mode=%r doubleConvTranspose=%r)"
+                                      % (bad, bilinear, up_mode, doubleConvTranspose))
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        self.to_crop = to_crop
+        self.depth = depth
+        self.recurrent_ch_ratio = recurrent_ch_ratio
+        f = filters
+        self.inc = _Holder()
+        self.inc.conv = _double(1, f)
+        self.inc.conv.conv = _WB((f, 1, 3, 3), (f,))
+        self.down_path = nn.ModuleList()
+        ch = f
+        for i in range(3):
+            d = _Holder()
+            d.mpconv = nn.ModuleList([nn.Identity(), _double(ch, 2 * ch)])
+            self.down_path.append(d)
+            ch *= 2
+        d = _Holder()
+        d.mpconv = nn.ModuleList([nn.Identity(), _double(ch, ch, second_transposed=True)])
+        self.down_path.append(d)
+        # bottleneck graph block
+        self.gcn = _Holder()
+        self.gcn.pos_embed = nn.Parameter(torch.zeros(1, ch, 12, 12))
+        grapher = _Holder()
+        grapher.relative_pos = nn.Parameter(torch.zeros(1, 144, 144), requires_grad=False)
+        grapher.fc1 = nn.ModuleList([_WB((ch, ch, 1, 1), (ch,))])
+        grapher.graph_conv = _Holder()
+        grapher.graph_conv.gconv = _Holder()
+        grapher.graph_conv.gconv.nn = nn.ModuleList([_WB((2 * ch, 2 * ch // 4, 1, 1), (2 * ch,))])
+        grapher.fc2 = nn.ModuleList([_WB((ch, 2 * ch, 1, 1), (ch,))])
+        ffn = _Holder()
+        ffn.fc1 = nn.ModuleList([_WB((ch, ch, 1, 1), (ch,))])
+        ffn.fc2 = nn.ModuleList([_WB((ch, ch, 1, 1), (ch,))])
+        self.gcn.module = nn.ModuleList([nn.ModuleList([grapher, ffn])])
+        self.drop_path_prob = 0.05  # GCNBlock: dpr = linspace(0.05, 0.1, 1)[0]  (Unet_singleFrame.py:63)
+        self.up_path = nn.ModuleList()
+        for i in range(4):
+            co = f if i >= 2 else ch // 2
+            u = _Holder()
+            u.up = _WB((ch, ch, 2, 2), (ch,))
+            u.conv = _Holder()
+            u.conv.conv = _WB((4 * ch, co, 3, 3), (co,))
+            u.conv.conv1 = _WB((co, co, 3, 3), (co,))
+            self.up_path.append(u)
+            ch //= 2
+        self.outc = _Holder()
+        self.outc.conv = _WB((1, f, 1, 1), (1,))
+        self._packed = None
+        self._packed_key = None
+        from .weights import relative_pos_table
+        with torch.no_grad():
+            grapher.relative_pos.copy_(relative_pos_table(8 * f, 12))
+
+    # ------------------------------------------------------------------ packing
+    def _pack_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + (self.precision,)
+
+    def packed(self):
+        key = self._pack_key()
+        if self._packed is None or key != self._packed_key:
+            self._packed = self._pack()
+            self._packed_key = key
+        return self._packed
+
+    def _pack(self):
+        tc = self.precision == "bf16"
+        P = {}
+
+        def conv(name, m, transposed):
+            w9 = packing.conv3x3_taps(m.weight.detach(), transposed)
+            P[name] = (packing.conv3x3_tc(w9) if tc else w9, m.bias.detach().float().contiguous())
+
+        with torch.no_grad():
+            P["inc0"] = (packing.conv_first(self.inc.conv.conv.weight.detach()), self.inc.conv.conv.bias.detach().float().contiguous())
+            conv("inc1", self.inc.conv.conv1, False)
+            for i in range(4):
+                blk = self.down_path[i].mpconv[1]
+                conv("d%d_0" % i, blk.conv, False)
+                conv("d%d_1" % i, blk.conv1, i == 3)
+            g, ffn = self.gcn.module[0][0], self.gcn.module[0][1]
+            P["pos"] = packing.blocked_param(self.gcn.pos_embed.detach())
+            P["relpos"] = g.relative_pos.detach().reshape(144, 144).float().contiguous()
+            for name, m, groups in (("g_fc1", g.fc1[0], 1), ("g_gconv", g.graph_conv.gconv.nn[0], 4),
+                                    ("g_fc2", g.fc2[0], 1), ("f_fc1", ffn.fc1[0], 1), ("f_fc2", ffn.fc2[0], 1)):
+                P[name] = (packing.pointwise(m.weight.detach(), groups), m.bias.detach().float().contiguous())
+            for i in range(4):
+                u = self.up_path[i]
+                P["u%d_up" % i] = (packing.convT2x2(u.up.weight.detach()), u.up.bias.detach().float().contiguous())
+                conv("u%d_0" % i, u.conv.conv, True)
+                conv("u%d_1" % i, u.conv.conv1, True)
+            P["outc"] = (self.outc.conv.weight.detach().reshape(-1).float().contiguous(),
+                         self.outc.conv.bias.detach().float().contiguous())
+        return P
+
+    # ------------------------------------------------------------------ one frame through the network
+    def _conv3(self, P, name, src, src_stride, dst, dst_stride, n, ci, h, w, co, pad, emit_skip=0, fuse=None):
+        wt, b = P[name]
+        if self.precision == "bf16":
+            if fuse is None:
+                call("uncl_conv3x3_tc", src, src_stride, wt, b, dst, dst_stride, n, ci, h, w, co, pad, ACT_RELU,
+                     emit_skip, 0, None, None, None, None)
+            else:
+                ow, ob, out_img, out_logit = fuse
+                call("uncl_conv3x3_tc", src, src_stride, wt, b, dst, dst_stride, n, ci, h, w, co, pad, ACT_RELU,
+                     emit_skip, 1, ow, ob, out_img, out_logit)
+        else:
+            call("uncl_conv3x3_simt", src, src_stride, wt, b, dst, dst_stride, n, ci, h, w, co, pad, ACT_RELU,
+                 emit_skip, _lib.F32)
+
+    def _run_frame(self, x, prev=None, droppath_scale=None, want_features=True, want_logit=False, keep=None):
+        """x: [N,1,H,W] fp32 CUDA contiguous with H=W=256.  prev: recurrent state of the previous frame (video).
+        Returns (out [N,1,256,256] fp32, up_x blocked tensor or None, logit or None, state list)."""
+        if x.dim() != 4 or x.shape[1] != 1 or x.shape[2] != 256 or x.shape[3] != 256:
+            raise ValueError("the generator only accepts [N,1,256,256] inputs (pos_embed is a fixed 12x12 grid, "
+                             "Unet_singleFrame.py:66,94); got %s" % (tuple(x.shape),))
+        if not x.is_cuda:
+            raise RuntimeError("uncltmo_b200 has no CPU path: move the input to a CUDA device")
+        P = self.packed()
+        x = x.contiguous().float()
+        n = x.shape[0]
+        dev = x.device
+        tdt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        dt = _lib.DTYPE_OF[tdt]
+
+        def buf(c, h, w):
+            return torch.empty((n, c // 8, h, w, 8), device=dev, dtype=tdt)
+
+        def st(t):
+            return t.stride(0)
+
+        f = 32
+        # encoder.  cat[i] is the concat buffer of up stage 3-i: [skip | upsampled | skip^2 | sqrt(skip)]
+        sizes = [(f, 252), (2 * f, 122), (4 * f, 57), (8 * f, 24)]
+        cat = [buf(4 * c, s, s) for c, s in sizes]
+        a0 = buf(f, 254, 254)
+        call("uncl_conv_first", x, P["inc0"][0], P["inc0"][1], a0, st(a0), n, 256, 256, f, ACT_RELU, dt)
+        self._conv3(P, "inc1", a0, st(a0), cat[0], st(cat[0]), n, f, 254, 254, f, 0, emit_skip=1)
+        state = [cat[0]]  # tensors whose first C/32 channels feed the next frame (Unet.py:229,251,264,272)
+        cur, cur_c, cur_s = cat[0], f, 252
+        for i in range(4):
+            ps = cur_s // 2
+            pooled = buf(cur_c, ps, ps)
+            pv = prev[i] if prev is not None else None
+            call("uncl_maxpool2", cur, st(cur), pv, st(pv) if pv is not None else 0, cur_c // 32 if pv is not None else 0,
+                 pooled, st(pooled), n, cur_c, cur_s, cur_s, dt)
+            co = cur_c * 2 if i < 3 else cur_c
+            mid = buf(co, ps - 2, ps - 2)
+            self._conv3(P, "d%d_0" % i, pooled, st(pooled), mid, st(mid), n, cur_c, ps, ps, co, 0)
+            if i < 3:
+                dst = cat[i + 1]
+                self._conv3(P, "d%d_1" % i, mid, st(mid), dst, st(dst), n, co, ps - 2, ps - 2, co, 0, emit_skip=1)
+                cur, cur_c, cur_s = dst, co, ps - 4
+            else:
+                x4 = buf(co, ps, ps)
+                self._conv3(P, "d3_1", mid, st(mid), x4, st(x4), n, co, ps - 2, ps - 2, co, 2)
+                cur, cur_c, cur_s = x4, co, ps
+            state.append(cur)
+        # bottleneck graph block (fp32 internals)
+        C = cur_c
+
+        def f32buf(c):
+            return torch.empty((n, c // 8, 144, 8), device=dev, dtype=torch.float32)
+
+        x0, y, z, z2, x1, f1 = f32buf(C), f32buf(C), f32buf(2 * C), f32buf(2 * C), f32buf(C), f32buf(C)
+        idx = torch.empty((n, 144, 9), device=dev, dtype=torch.int32) if keep is not None else None
+        call("uncl_gcn_add_pos", cur, st(cur), P["pos"], x0, n, C, dt)
+        call("uncl_pw_conv", x0, P["g_fc1"][0], P["g_fc1"][1], None, None, y, st(y), n, C, C, 1, 144, ACT_NONE, _lib.F32)
+        call("uncl_gcn_knn_aggregate", y, P["relpos"], z, idx, n, C)
+        call("uncl_pw_conv", z, P["g_gconv"][0], P["g_gconv"][1], None, None, z2, st(z2), n, 2 * C, 2 * C, 4, 144, ACT_GELU, _lib.F32)
+        s0 = droppath_scale[0] if droppath_scale is not None else None
+        s1 = droppath_scale[1] if droppath_scale is not None else None
+        call("uncl_pw_conv", z2, P["g_fc2"][0], P["g_fc2"][1], x0, s0, x1, st(x1), n, 2 * C, C, 1, 144, ACT_NONE, _lib.F32)
+        call("uncl_pw_conv", x1, P["f_fc1"][0], P["f_fc1"][1], None, None, f1, st(f1), n, C, C, 1, 144, ACT_GELU, _lib.F32)
+        gout = buf(C, 12, 12)
+        call("uncl_pw_conv", f1, P["f_fc2"][0], P["f_fc2"][1], x1, s1, gout, st(gout), n, C, C, 1, 144, ACT_NONE, dt)
+        state.append(gout)
+        if keep is not None:
+            keep.update(x0=x0, y=y, idx=idx, z=z, z2=z2, x1=x1, f1=f1, gcn=gout, skips=cat, x4=cur)
+        # decoder
+        up, up_c, up_s = gout, C, 12
+        out = torch.empty((n, 1, 256, 256), device=dev, dtype=torch.float32)
+        logit = torch.empty_like(out) if want_logit else None
+        fused = False
+        for i in range(4):
+            cb = cat[3 - i]
+            sk_c, sk_s = sizes[3 - i]
+            # ConvTranspose k2 s2 into the second channel group of the concat buffer
+            dst = cb[:, sk_c // 8:]
+            pv = prev[5 + i] if prev is not None else None
+            call("uncl_convT2x2", up, st(up), pv, st(pv) if pv is not None else 0, up_c // 32 if pv is not None else 0,
+                 P["u%d_up" % i][0], P["u%d_up" % i][1], dst, st(cb), n, up_c, up_s, up_s, sk_s, sk_s, dt)
+            co = f if i >= 2 else up_c // 2
+            mid = buf(co, sk_s + 2, sk_s + 2)
+            self._conv3(P, "u%d_0" % i, cb, st(cb), mid, st(mid), n, 4 * sk_c, sk_s, sk_s, co, 2)
+            last = i == 3
+            if last and self.precision == "bf16" and not want_features:
+                self._conv3(P, "u3_1", mid, st(mid), None, 0, n, co, sk_s + 2, sk_s + 2, co, 2,
+                            fuse=(P["outc"][0], P["outc"][1], out, logit))
+                fused, nxt = True, None
+            else:
+                nxt = buf(co, sk_s + 4, sk_s + 4)
+                self._conv3(P, "u%d_1" % i, mid, st(mid), nxt, st(nxt), n, co, sk_s + 2, sk_s + 2, co, 2)
+            up, up_c, up_s = nxt, co, sk_s + 4
+            state.append(up)
+            if keep is not None:
+                keep.setdefault("ups", []).append(up)
+        if not fused:
+            call("uncl_outc_sigmoid", up, st(up), P["outc"][0], P["outc"][1], out, logit, n, f, 256 * 256, dt)
+        return out, up, logit, state
+
+    def _features_nchw(self, up):
+        n = up.shape[0]
+        c, hw = up.shape[1] * 8, up.shape[2] * up.shape[3]
+        o = torch.empty((n, c, up.shape[2], up.shape[3]), device=up.device, dtype=torch.float32)
+        call("uncl_blocked_to_nchw", up, up.stride(0), o, n, c, hw, _lib.DTYPE_OF[up.dtype])
+        return o
+
+    def _droppath_scale(self, n, device):
+        """Per-sample DropPath factors (mask / keep_prob) for the two residual branches; None in eval."""
+        if not self.training or self.drop_path_prob <= 0:
+            return None
+        keep = 1.0 - self.drop_path_prob
+        return [torch.empty(n, device=device).bernoulli_(keep) / keep for _ in range(2)]
+
+    @staticmethod
+    def _crop(x_out, diffY, diffX):
+        # utils/data_loader_util.py:165-172 (crop_input_hdr_batch)
+        h, w = x_out.shape[-2], x_out.shape[-1]
+        th, tw = h - diffY, w - diffX
+        i, j = int(round((h - th) / 2.0)), int(round((w - tw) / 2.0))
+        return x_out[..., i:i + th, j:j + tw]
+
+
+def blocked_to_nchw(t):
+    """Debug/test helper: C8-blocked [N][C/8][H][W][8] (fp32 or bf16) -> NCHW fp32."""
+    n, cb, h, w, _ = t.shape
+    o = torch.empty((n, cb * 8, h, w), device=t.device, dtype=torch.float32)
+    call("uncl_blocked_to_nchw", t, t.stride(0), o, n, cb * 8, h * w, _lib.DTYPE_OF[t.dtype])
+    return o
+
+
+class UNet(_GeneratorBase):
+    """Image generator: forward(x[N,1,256,256]) -> (sigmoid map [N,1,256,256], up_x [N,32,256,256]).
+
+    Drop-in for models/unet_multi_filters/Unet_singleFrame.py:101-213.  Inference only in this build
+    (autograd through the kernels arrives with the backward kernels); call under torch.no_grad().
+    """
+
+    def forward(self, x, apply_crop=True, diffY=0, diffX=0):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("uncltmo_b200 generator backward is not built yet: call under torch.no_grad()")
+        out, up, _, _ = self._run_frame(x, droppath_scale=self._droppath_scale(x.shape[0], x.device))
+        feats = self._features_nchw(up)
+        if apply_crop and self.to_crop:
+            out = self._crop(out, diffY, diffX)
+        return out, feats
+
+    def tonemap_tiles(self, x, want_logit=False):
+        """Fast path for the frame pipeline: [N,1,256,256] -> [N,1,256,256] without materialising features."""
+        out, _, logit, _ = self._run_frame(x, want_features=False, want_logit=want_logit)
+        return (out, logit) if want_logit else out
+
+
+class UNetVideo(_GeneratorBase):
+    """Video generator: forward(x[N,T,1,256,256]) -> (frames [N,T,1,256,256], features [N,T,64,1,1]).
+
+    Drop-in for models/unet_multi_filters/Unet.py:135-289: frame k receives the first C/32 channels of its
+    eight stage inputs from frame k-1.
+    """
+
+    def forward(self, x, apply_crop=True, diffY=0, diffX=0):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("uncltmo_b200 generator backward is not built yet: call under torch.no_grad()")
+        from .features import contrast_features
+        outs, feats, prev = [], [], None
+        for k in range(x.shape[1]):
+            out, up, _, state = self._run_frame(x[:, k], prev=prev,
+                                                droppath_scale=self._droppath_scale(x.shape[0], x.device))
+            feats.append(contrast_features(up).unsqueeze(1))
+            if apply_crop and self.to_crop:
+                out = self._crop(out, diffY, diffX)
+            outs.append(out.unsqueeze(1))
+            prev = state
+        return torch.cat(outs, 1), torch.cat(feats, 1)
+
+    def tonemap_clip_tiles(self, x):
+        """[N,T,1,256,256] -> [N,T,1,256,256] (no feature extraction; inference path of run_model_on_video)."""
+        outs, prev = [], None
+        for k in range(x.shape[1]):
+            out, _, _, prev = self._run_frame(x[:, k], prev=prev, want_features=True)
+            outs.append(out.unsqueeze(1))
+        return torch.cat(outs, 1)

@@ -1,0 +1,49 @@
+"""One-time re-layout of reference-shaped parameters into the formats the kernels read.
+
+These run on the device with torch tensor ops when weights are (re)loaded - plumbing, not the hot path.
+Reference weight layouts: nn.Conv2d [C_out, C_in, kH, kW]; nn.ConvTranspose2d [C_in, C_out, kH, kW]
+(SURVEY.md Appendix B).
+"""
+import torch
+
+
+def conv3x3_taps(w, transposed):
+    """-> [9][C_in][C_out] fp32 (tap = ky*3+kx of the equivalent plain correlation).
+
+    transposed=True: ConvTranspose2d 3x3 s1 p0 == correlation over a 2-px zero-padded input with the kernel
+    flipped in both axes (unet_parts.py:114, 148-159)."""
+    if transposed:
+        return w.flip(2, 3).permute(2, 3, 0, 1).reshape(9, w.shape[0], w.shape[1]).contiguous().float()
+    return w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]).contiguous().float()
+
+
+def conv3x3_tc(w9):
+    """[9][C_in][C_out] fp32 -> bf16 [NS][C_in/16][9][2][NT][8], NT = min(C_out, 128) (conv_tc.cu B operand)."""
+    _, ci, co = w9.shape
+    nt = min(co, 128)
+    ns = co // nt
+    t = w9.reshape(9, ci // 16, 2, 8, ns, nt)          # tap, chunk, half, k8, ns, n
+    t = t.permute(4, 1, 0, 2, 5, 3).contiguous()       # ns, chunk, tap, half, n, k8
+    return t.to(torch.bfloat16)
+
+
+def convT2x2(w):
+    """ConvTranspose2d k2 s2 weight [C_in][C_out][2][2] -> [C_in][4][C_out] fp32 (pos = dy*2+dx)."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], 4, w.shape[1]).contiguous().float()
+
+
+def pointwise(w, groups=1):
+    """1x1 Conv2d weight [C_out][C_in/g][1][1] -> [g][C_in/g][C_out/g] fp32."""
+    co, cig = w.shape[0], w.shape[1]
+    return w.reshape(groups, co // groups, cig).permute(0, 2, 1).contiguous().float()
+
+
+def conv_first(w):
+    """Conv2d(1, C_out, 3) weight [C_out][1][3][3] -> [9][C_out] fp32."""
+    return w.reshape(w.shape[0], 9).t().contiguous().float()
+
+
+def blocked_param(t):
+    """[1][C][H][W] -> C8-blocked [C/8][H*W][8] fp32 (pos_embed)."""
+    _, c, h, w = t.shape
+    return t.reshape(c // 8, 8, h * w).permute(0, 2, 1).contiguous().float()
