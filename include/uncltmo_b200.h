@@ -96,6 +96,42 @@ int uncl_pw_conv(const float* in, const float* w, const float* bias, const float
 int uncl_gcn_knn_aggregate(const float* y, const float* relpos, float* z, int* idx_out, int N, int C,
                            uncl_stream_t stream);
 
+/* ---- frame path (utils/model_save_util.py, utils/hdr_image_util.py, utils/data_loader_util.py) ---- */
+
+/* bytes of the scratch buffer the frame-path calls below share (statistics, percentile state, histograms) */
+long uncl_frame_workspace_bytes(void);
+
+/* log-lambda normalisation fused with the replicate pad:  Y = .299R+.587G+.114B (after rgb -= min(rgb) if negative),
+ * Y -= min; out = log10(Y/max*f + 1) / max(...), written into the (H1 x W1) padded frame.
+ * model_save_util.py:232-239 (load_inference2), 255-262; hdr_image_util.py:76-82; data_loader_util.py:135-157, 175-179.
+ * rgb [3][H][W] fp32.  Leaves (min rgb, min Y, max Y) in the workspace for uncl_frame_postprocess. */
+int uncl_frame_normalise_pad(const float* rgb, int H, int W, float f_factor, float* gray_out, int H1, int W1,
+                             void* workspace, uncl_stream_t stream);
+
+/* gather T 256x256 tiles at origins[t] = (y, x) from the padded frame.  model_save_util.py:417-426, 438, 455-459, 470. */
+int uncl_tiles_gather(const float* frame, int H1, int W1, const int* origins, int T, float* tiles,
+                      uncl_stream_t stream);
+
+/* closed form of the sequential linear cross-fade of model_save_util.py:428-481: every pixel is a weighted sum of
+ * at most KxK tiles (K=3 at overlap 64); per-row / per-column [L][K] (tile index, weight) tables are built by the
+ * host mirror (uncltmo_b200/frame.py). */
+int uncl_tiles_blend(const float* tiles, const int* yidx, const float* yw, const int* ystart, const int* xidx,
+                     const float* xw, const int* xstart, int TX, int K, float* out, int H1, int W1,
+                     uncl_stream_t stream);
+
+/* numpy.percentile(clip(data, clamp_lo, clamp_hi), [p_lo, p_hi]) ('linear'), on device, no host sync.
+ * model_save_util.py:389-390 (99.5 / 0.5), hdr_image_util.py:93-102 (99.0 / 0.1).  pct_out[2]. */
+int uncl_percentile_pair(const float* data, long n, float clamp_lo, float clamp_hi, double p_lo, double p_hi,
+                         float* pct_out, void* workspace, uncl_stream_t stream);
+
+/* clamp to pct, min-max stretch, (rgb/(Y+1e-8))^0.5 * fake, crop the pad.  model_save_util.py:393-402,
+ * hdr_image_util.py:122-132.  fake [H1][W1]; rgb / out [3][H][W]. */
+int uncl_frame_postprocess(const float* fake, int H1, int W1, const float* rgb, int H, int W, const float* pct,
+                           float* out, void* workspace, uncl_stream_t stream);
+
+/* clamp(0,1), stretch between pct[0..1], clip, *255 -> uint8 HWC.  hdr_image_util.py:237-245, 93-102. */
+int uncl_frame_to_u8(const float* col, int H, int W, const float* pct, unsigned char* out, uncl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

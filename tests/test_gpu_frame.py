@@ -1,0 +1,129 @@
+"""GPU parity tests of the frame path (normalise, pad, tiling, blend, percentiles, post-process) via the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs as gi
+import oracle
+from uncltmo_b200 import synth
+from uncltmo_b200.frame import FramePipeline
+from uncltmo_b200.generator import UNet
+from uncltmo_b200.weights import make_generator_state_dict
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+G_ARGS = (1, 1, "sigmoid", 4, 4, "square_and_square_root", 32, 0, "unet", 0, 0, "none", "none", "relu", 1, "replicate", 2)
+
+
+def maxabs(a, b):
+    return (torch.as_tensor(a).double().cpu() - torch.as_tensor(b).double().cpu()).abs().max().item()
+
+
+class CheapG:
+    """Stand-in generator so the blend is tested without the network in the way."""
+
+    def tonemap_tiles(self, t):
+        return gi.cheap_model(t.cpu()).cuda()
+
+
+@pytest.fixture(scope="module")
+def net():
+    n = UNet(*G_ARGS, up_mode=0, precision="fp32").cuda().eval()
+    n.load_state_dict(make_generator_state_dict())
+    return n
+
+
+def test_normalise_and_pad(golden):
+    rgb = torch.from_numpy(gi.small_frame())
+    _, gray = oracle.log_lambda_normalise(rgb, gi.LAMBDA)
+    gp, dy, dx = oracle.resize_im(gray)
+    pipe = FramePipeline(CheapG())
+    got = pipe.normalise_pad(rgb.cuda(), gi.LAMBDA)
+    assert got.shape == gp.shape[1:]
+    assert maxabs(got, gp[0]) <= 2e-6
+    assert maxabs(got[dy // 2:dy // 2 + 268:2, dx // 2:dx // 2 + 300:2], golden["norm_gray_s2"][0]) <= 2e-6
+
+
+def test_normalise_negative_input_shift():
+    rgb = torch.from_numpy(gi.small_frame()) - 0.37  # exr-style negative values (model_save_util.py:233-234)
+    _, gray = oracle.log_lambda_normalise(rgb, 371.4)
+    gp, _, _ = oracle.resize_im(gray)
+    got = FramePipeline(CheapG()).normalise_pad(rgb.cuda(), 371.4)
+    assert maxabs(got, gp[0]) <= 5e-6
+
+
+@pytest.mark.parametrize("shape,overlap", [((272, 304), 64), ((464, 656), 64), ((784, 1040), 64), ((464, 464), 192)])
+def test_gather_and_blend(shape, overlap):
+    x = torch.from_numpy(gi.blend_field(*shape))
+    ref = oracle.tile_and_blend(x, gi.cheap_model, overlap=overlap)
+    pipe = FramePipeline(CheapG(), overlap=overlap)
+    pl = pipe.plan(shape[0] - 16, shape[1] - 16, torch.device("cuda"))
+    assert (pl.h1, pl.w1) == shape
+    tiles = pipe.gather_tiles(x[0, 0].cuda(), pl)
+    for t, (oy, ox) in enumerate(pl.origins.cpu().tolist()):
+        assert torch.equal(tiles[t, 0].cpu(), x[0, 0, oy:oy + 256, ox:ox + 256])
+    got = pipe.blend(pipe.run_generator(tiles), pl)
+    assert maxabs(got, ref[0, 0]) <= 2e-6
+
+
+def test_blend_of_constant_tiles_is_constant():
+    pipe = FramePipeline(CheapG())
+    pl = pipe.plan(1080, 1920, torch.device("cuda"))
+    assert pl.ntiles == 60
+    tiles = torch.full((60, 1, 256, 256), 0.625, device="cuda")
+    got = pipe.blend(tiles, pl)
+    assert maxabs(got, torch.full_like(got, 0.625)) <= 1e-6
+
+
+@pytest.mark.parametrize("n", [2, 1000, 331_776, 2_106_368])
+def test_percentiles_match_numpy(n):
+    rng = np.random.default_rng(n)
+    a = (rng.standard_normal(n) * 0.05 + 0.5).astype(np.float32)
+    a[: n // 7] = a[0]  # heavy ties
+    pipe = FramePipeline(CheapG())
+    for lo, hi in ((0.5, 99.5), (0.1, 99.0), (0.0, 100.0)):
+        got = pipe.percentiles(torch.from_numpy(a).cuda(), lo, hi).cpu().numpy()
+        ref = np.array([np.percentile(a, lo), np.percentile(a, hi)])
+        assert np.abs(got - ref).max() <= 1e-7 * max(1.0, np.abs(ref).max()) + 6e-8
+    neg = -a
+    got = pipe.percentiles(torch.from_numpy(neg).cuda(), 0.5, 99.5).cpu().numpy()
+    assert np.abs(got - np.array([np.percentile(neg, 0.5), np.percentile(neg, 99.5)])).max() <= 1e-7
+
+
+def test_frame_end_to_end_matches_reference_fixture(net, golden):
+    rgb = torch.from_numpy(gi.small_frame())
+    pipe = FramePipeline(net)
+    pl = pipe.plan(268, 300, torch.device("cuda"))
+    gray_p = pipe.normalise_pad(rgb.cuda(), gi.LAMBDA)
+    fake_p = pipe.blend(pipe.run_generator(pipe.gather_tiles(gray_p, pl)), pl)
+    assert maxabs(fake_p[::2, ::2], golden["frame_fake_s2"][0, 0]) <= 2e-6
+    pct = pipe.percentiles(fake_p, 0.5, 99.5).cpu().numpy()
+    assert np.abs(pct - golden["frame_percentiles"]).max() <= 5e-7
+    col = pipe.tonemap(rgb.cuda(), gi.LAMBDA)
+    assert col.shape == (3, 268, 300)
+    # stretch divides by (p99.5 - p0.5) ~ 1e-2 of a nearly flat random-init output: errors are amplified ~100x
+    assert maxabs(col[:, ::2, ::2], golden["frame_color_s2"]) <= 2e-4
+    u8 = pipe.tonemap(rgb.cuda(), gi.LAMBDA, uint8=True)
+    assert u8.shape == (268, 300, 3) and u8.dtype == torch.uint8
+    assert np.abs(u8.cpu().numpy()[::2, ::2].astype(int) - golden["frame_u8_s2"].astype(int)).max() <= 1
+
+
+def test_frame_1080p_properties(net):
+    """Full-size case through size-independent properties: shape, range, partition of unity, and equality of
+    the batched-tile path with tile-at-a-time execution (what the reference does)."""
+    rgb = torch.from_numpy(synth.hdr_frame(1080, 1920, seed=0)).cuda()
+    net_bf = UNet(*G_ARGS, up_mode=0, precision="bf16").cuda().eval()
+    net_bf.load_state_dict(make_generator_state_dict())
+    pipe = FramePipeline(net_bf)
+    pl = pipe.plan(1080, 1920, rgb.device)
+    assert (pl.h1, pl.w1, pl.ntiles) == (1088, 1936, 60)
+    gray_p = pipe.normalise_pad(rgb, 50.0)
+    assert gray_p.min().item() == 0.0 and abs(gray_p.max().item() - 1.0) < 1e-6
+    tiles = pipe.gather_tiles(gray_p, pl)
+    batched = pipe.run_generator(tiles)
+    single = torch.cat([net_bf.tonemap_tiles(tiles[i:i + 1]) for i in (0, 17, 59)])
+    assert torch.equal(batched[[0, 17, 59]], single)
+    col = pipe.tonemap(rgb, 50.0)
+    assert col.shape == (3, 1080, 1920) and torch.isfinite(col).all() and col.min().item() >= 0.0
+    u8 = pipe.tonemap(rgb, 50.0, uint8=True)
+    assert u8.shape == (1080, 1920, 3)

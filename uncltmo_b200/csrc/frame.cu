@@ -1,0 +1,374 @@
+// Frame path around the generator: log-lambda HDR normalisation fused with the replicate pad, tile gather,
+// closed-form cross-fade blend of the 256x256 tiles, on-device percentiles (radix select), post-process
+// (clamp / stretch / back-to-colour / crop) and the final 8-bit stretch.  All HBM-bound, vectorised where the
+// layout allows, no host synchronisation anywhere.
+//
+// Reference: utils/model_save_util.py:219-240, 242-263 (log-lambda normalise), :409-486, 488-565 (tiling + blend),
+// :389-402, 589-606 (post-process); utils/hdr_image_util.py:76-82 (to_gray), :122-132 (back_to_color_tensor),
+// :93-102, 237-245 (8-bit stretch); utils/data_loader_util.py:135-157, 175-179 (replicate pad).
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float gray_of(float r, float g, float b) { return 0.299f * r + 0.587f * g + 0.114f * b; }
+
+// ---- pass 1: per-block partial (min rgb, min Y, max Y) --------------------------------------------------------
+__global__ void __launch_bounds__(256) frame_stats_kernel(const float* __restrict__ rgb, long HW, const float* shift_src,
+                                                         float* __restrict__ partials) {
+  __shared__ float red[3][8];
+  // shift_src == nullptr: first pass (no shift).  Otherwise stats[0] holds min(rgb); if it is >= 0 nothing changes.
+  float shift = 0.f;
+  if (shift_src != nullptr) {
+    shift = fminf(shift_src[0], 0.f);
+    if (shift == 0.f) return;  // first-pass statistics stand
+  }
+  float mn = INFINITY, ymn = INFINITY, ymx = -INFINITY;
+  const long n4 = HW / 4;
+  const float4* r4 = reinterpret_cast<const float4*>(rgb);
+  const float4* g4 = reinterpret_cast<const float4*>(rgb + HW);
+  const float4* b4 = reinterpret_cast<const float4*>(rgb + 2 * HW);
+  const bool vec = (HW % 4 == 0);
+  if (vec) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+      const float4 r = __ldg(r4 + i), g = __ldg(g4 + i), b = __ldg(b4 + i);
+      const float rr[4] = {r.x, r.y, r.z, r.w}, gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        mn = fminf(mn, fminf(rr[k], fminf(gg[k], bb[k])));
+        const float y = gray_of(rr[k] - shift, gg[k] - shift, bb[k] - shift);
+        ymn = fminf(ymn, y);
+        ymx = fmaxf(ymx, y);
+      }
+    }
+  } else {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long)gridDim.x * blockDim.x) {
+      const float r = rgb[i], g = rgb[HW + i], b = rgb[2 * HW + i];
+      mn = fminf(mn, fminf(r, fminf(g, b)));
+      const float y = gray_of(r - shift, g - shift, b - shift);
+      ymn = fminf(ymn, y);
+      ymx = fmaxf(ymx, y);
+    }
+  }
+  mn = warp_min(mn); ymn = warp_min(ymn); ymx = warp_max(ymx);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { red[0][wid] = mn; red[1][wid] = ymn; red[2][wid] = ymx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { mn = fminf(mn, red[0][w]); ymn = fminf(ymn, red[1][w]); ymx = fmaxf(ymx, red[2][w]); }
+    partials[blockIdx.x * 3 + 0] = mn;
+    partials[blockIdx.x * 3 + 1] = ymn;
+    partials[blockIdx.x * 3 + 2] = ymx;
+  }
+}
+
+// reduce the per-block partials into stats[0..2] = (min rgb, min Y, max Y); on the second pass keeps min rgb
+__global__ void frame_stats_final_kernel(const float* __restrict__ partials, int nparts, float* __restrict__ stats,
+                                         int second_pass) {
+  __shared__ float red[3][32];
+  if (second_pass && fminf(stats[0], 0.f) == 0.f) return;
+  float mn = INFINITY, ymn = INFINITY, ymx = -INFINITY;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+    mn = fminf(mn, partials[3 * i]);
+    ymn = fminf(ymn, partials[3 * i + 1]);
+    ymx = fmaxf(ymx, partials[3 * i + 2]);
+  }
+  mn = warp_min(mn); ymn = warp_min(ymn); ymx = warp_max(ymx);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { red[0][wid] = mn; red[1][wid] = ymn; red[2][wid] = ymx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { mn = fminf(mn, red[0][w]); ymn = fminf(ymn, red[1][w]); ymx = fmaxf(ymx, red[2][w]); }
+    if (!second_pass) stats[0] = mn;
+    stats[1] = ymn;
+    stats[2] = ymx;
+  }
+}
+
+// ---- pass 2: gray_log = log10((Y - Ymin) / max(Y - Ymin) * f + 1) / max(...), written replicate-padded --------
+__global__ void __launch_bounds__(256) frame_normalise_pad_kernel(const float* __restrict__ rgb, int H, int W,
+                                                                 const float* __restrict__ stats, float f,
+                                                                 float* __restrict__ out, int H1, int W1, int padT,
+                                                                 int padL) {
+  const float shift = fminf(stats[0], 0.f), ymin = stats[1];
+  const float gmax = stats[2] - ymin;          // max of (gray - gray.min())
+  const float lmax = log10f((gmax / gmax) * f + 1.f);  // max of the log image is attained at gray == gmax
+  const long HW = (long)H * W;
+  const long total = (long)H1 * W1;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int x1 = i % W1, y1 = i / W1;
+    const int x = min(max(x1 - padL, 0), W - 1), y = min(max(y1 - padT, 0), H - 1);
+    const long s = (long)y * W + x;
+    const float g = gray_of(__ldg(rgb + s) - shift, __ldg(rgb + HW + s) - shift, __ldg(rgb + 2 * HW + s) - shift) - ymin;
+    out[i] = log10f((g / gmax) * f + 1.f) / lmax;
+  }
+}
+
+// ---- tiles: gather [T][256][256] from the padded frame, blend back ---------------------------------------------
+__global__ void __launch_bounds__(256) tiles_gather_kernel(const float* __restrict__ frame, int W1,
+                                                          const int* __restrict__ origins, float* __restrict__ tiles) {
+  const int t = blockIdx.y;
+  const int oy = origins[2 * t], ox = origins[2 * t + 1];
+  const float* src = frame + (long)oy * W1 + ox;
+  float* dst = tiles + (long)t * 65536;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 65536; i += gridDim.x * blockDim.x)
+    dst[i] = __ldg(src + (long)(i >> 8) * W1 + (i & 255));
+}
+
+// out(y,x) = sum_{a<K} sum_{b<K} wy[y][a] * wx[x][b] * tile[ty[y][a]][tx[x][b]](y - y0, x - x0)
+// (weights/indices are the closed form of the reference's sequential cross-fade; unused slots have weight 0)
+__global__ void __launch_bounds__(256) tiles_blend_kernel(const float* __restrict__ tiles, const int* __restrict__ yidx,
+                                                         const float* __restrict__ yw, const int* __restrict__ ystart,
+                                                         const int* __restrict__ xidx, const float* __restrict__ xw,
+                                                         const int* __restrict__ xstart, int TX, int K,
+                                                         float* __restrict__ out, int H1, int W1) {
+  const long total = (long)H1 * W1;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int x = i % W1, y = i / W1;
+    float acc = 0.f;
+    for (int a = 0; a < K; ++a) {
+      const float wa = yw[K * y + a];
+      if (wa == 0.f) continue;
+      const int ty = yidx[K * y + a];
+      const int ly = y - ystart[ty];
+      float row = 0.f;
+      for (int b = 0; b < K; ++b) {
+        const float wb = xw[K * x + b];
+        if (wb == 0.f) continue;
+        const int tx = xidx[K * x + b];
+        row = fmaf(wb, __ldg(tiles + ((long)(ty * TX + tx) << 16) + (ly << 8) + (x - xstart[tx])), row);
+      }
+      acc = fmaf(wa, row, acc);
+    }
+    out[i] = acc;
+  }
+}
+
+// ---- radix select: up to 4 order statistics of a float array in 3 histogram passes (11 + 11 + 10 bits) --------
+constexpr int kSelQ = 4;
+struct SelState {
+  unsigned prefix[kSelQ];
+  unsigned rank[kSelQ];
+};
+struct SelRanks {
+  unsigned r[kSelQ];
+};
+__device__ __forceinline__ unsigned order_key(float v) {
+  const unsigned b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_value(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(512) select_hist_kernel(const float* __restrict__ data, long n, float clamp_lo,
+                                                         float clamp_hi, const SelState* __restrict__ st,
+                                                         unsigned* __restrict__ hist) {
+  constexpr int BITS = PASS == 2 ? 10 : 11;
+  constexpr int SHIFT = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
+  constexpr int NQ = PASS == 0 ? 1 : kSelQ;
+  __shared__ unsigned s_hist[NQ << BITS];
+  for (int i = threadIdx.x; i < (NQ << BITS); i += blockDim.x) s_hist[i] = 0;
+  unsigned pre[kSelQ];
+#pragma unroll
+  for (int q = 0; q < kSelQ; ++q) pre[q] = PASS == 0 ? 0u : st->prefix[q];
+  __syncthreads();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = fminf(fmaxf(__ldg(data + i), clamp_lo), clamp_hi);
+    const unsigned k = order_key(v);
+    if (PASS == 0) {
+      atomicAdd(&s_hist[k >> SHIFT], 1u);
+    } else {
+      const unsigned hi = k >> (SHIFT + BITS), bin = (k >> SHIFT) & ((1u << BITS) - 1);
+#pragma unroll
+      for (int q = 0; q < kSelQ; ++q) {
+        // identical prefixes share a histogram slot (the lowest q) - the scan reads it from there
+        bool first = true;
+#pragma unroll
+        for (int q2 = 0; q2 < q; ++q2) first = first && (pre[q2] != pre[q]);
+        if (first && hi == pre[q]) atomicAdd(&s_hist[(q << BITS) + bin], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (NQ << BITS); i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+
+template <int PASS>
+__global__ void select_scan_kernel(SelState* st, unsigned* hist, const SelRanks ranks_in) {
+  constexpr int BITS = PASS == 2 ? 10 : 11;
+  const int q = threadIdx.x;
+  if (q < kSelQ) {
+    unsigned rank = PASS == 0 ? ranks_in.r[q] : st->rank[q];
+    const unsigned pre = PASS == 0 ? 0u : st->prefix[q];
+    int slot = 0;
+    if (PASS != 0) {
+      slot = q;
+      for (int q2 = q - 1; q2 >= 0; --q2)
+        if (st->prefix[q2] == pre) slot = q2;
+    }
+    const unsigned* h = hist + ((size_t)slot << BITS);
+    unsigned cum = 0;
+    int b = 0;
+    for (; b < (1 << BITS) - 1; ++b) {
+      const unsigned c = h[b];
+      if (rank < cum + c) break;
+      cum += c;
+    }
+    __syncwarp(__activemask());
+    // all readers of st->prefix are done before anyone overwrites it (single warp, lock-step after the loop)
+    st->rank[q] = rank - cum;
+    st->prefix[q] = (pre << BITS) | (unsigned)b;
+  }
+}
+
+// out[0] = lerp of order stats (ranks 0,1) with weight t0, out[1] = same for ranks 2,3 with t1 (numpy 'linear')
+__global__ void select_finish_kernel(const SelState* st, double t0, double t1, float* out) {
+  if (threadIdx.x == 0) {
+    const double a0 = key_value(st->prefix[0]), b0 = key_value(st->prefix[1]);
+    const double a1 = key_value(st->prefix[2]), b1 = key_value(st->prefix[3]);
+    out[0] = (float)(t0 < 0.5 ? a0 + (b0 - a0) * t0 : b0 - (b0 - a0) * (1.0 - t0));
+    out[1] = (float)(t1 < 0.5 ? a1 + (b1 - a1) * t1 : b1 - (b1 - a1) * (1.0 - t1));
+  }
+}
+
+// ---- post-process: clamp to percentiles, stretch, back to colour, crop --------------------------------------
+__global__ void __launch_bounds__(256) frame_postprocess_kernel(const float* __restrict__ fake, int W1, int padT,
+                                                               int padL, const float* __restrict__ rgb, int H, int W,
+                                                               const float* __restrict__ stats,
+                                                               const float* __restrict__ pct, float* __restrict__ out) {
+  const float shift = fminf(stats[0], 0.f);
+  const float lo = pct[0], hi = pct[1];
+  const float inv = 1.f / (hi - lo);
+  const long HW = (long)H * W;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long)gridDim.x * blockDim.x) {
+    const int x = i % W, y = i / W;
+    const float f = __ldg(fake + (long)(y + padT) * W1 + (x + padL));
+    const float s = (fminf(fmaxf(f, lo), hi) - lo) * inv;
+    const float r = __ldg(rgb + i) - shift, g = __ldg(rgb + HW + i) - shift, b = __ldg(rgb + 2 * HW + i) - shift;
+    const float d = gray_of(r, g, b) + 1e-8f;
+    out[i] = sqrtf(r / d) * s;
+    out[HW + i] = sqrtf(g / d) * s;
+    out[2 * HW + i] = sqrtf(b / d) * s;
+  }
+}
+
+// final 8-bit image, HWC: clip((clamp(c,0,1) - lo) / (hi - lo), 0, 1) * 255 truncated
+__global__ void __launch_bounds__(256) frame_to_u8_kernel(const float* __restrict__ col, long HW,
+                                                         const float* __restrict__ pct, unsigned char* __restrict__ out) {
+  const float lo = pct[0], hi = pct[1];
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = fminf(fmaxf(__ldg(col + c * HW + i), 0.f), 1.f);
+      v = fminf(fmaxf((v - lo) / (hi - lo), 0.f), 1.f);
+      out[3 * i + c] = (unsigned char)(v * 255.f);
+    }
+  }
+}
+
+inline int grid_for(long total, int block, int per_sm) {
+  long g = (total + block - 1) / block;
+  const long cap = 148L * per_sm;
+  return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+constexpr int kStatBlocks = 148 * 8;
+
+extern "C" long uncl_frame_workspace_bytes() {
+  // partials [kStatBlocks][3] floats | stats[4] | pct[4] | SelState | ranks[4] | hist [4][2048]
+  return (long)kStatBlocks * 3 * 4 + 16 + 16 + (long)sizeof(SelState) + 16 + 4L * 2048 * 4 + 256;
+}
+
+struct FrameWs {
+  float* partials; float* stats; float* pct; SelState* sel; unsigned* ranks; unsigned* hist;
+};
+static FrameWs carve(void* ws) {
+  FrameWs w;
+  char* p = reinterpret_cast<char*>(ws);
+  w.partials = reinterpret_cast<float*>(p); p += (size_t)kStatBlocks * 3 * 4;
+  w.stats = reinterpret_cast<float*>(p); p += 16;
+  w.pct = reinterpret_cast<float*>(p); p += 16;
+  w.sel = reinterpret_cast<SelState*>(p); p += sizeof(SelState);
+  w.ranks = reinterpret_cast<unsigned*>(p); p += 16;
+  w.hist = reinterpret_cast<unsigned*>(p);
+  return w;
+}
+
+extern "C" int uncl_frame_normalise_pad(const float* rgb, int H, int W, float f_factor, float* gray_out, int H1, int W1,
+                                        void* workspace, cudaStream_t stream) {
+  UNCL_REQUIRE(H > 0 && W > 0 && H1 >= H && W1 >= W && f_factor > 0.f, "frame_normalise_pad: bad arguments");
+  UNCL_REQUIRE((reinterpret_cast<uintptr_t>(rgb) & 15) == 0, "frame_normalise_pad: rgb must be 16-byte aligned");
+  FrameWs w = carve(workspace);
+  const long HW = (long)H * W;
+  const int nb = grid_for(HW / 4 + 1, 256, 8);
+  frame_stats_kernel<<<nb, 256, 0, stream>>>(rgb, HW, nullptr, w.partials);
+  frame_stats_final_kernel<<<1, 1024, 0, stream>>>(w.partials, nb, w.stats, 0);
+  // negative inputs (exr): shift by min(rgb) and recompute the luminance range; both kernels exit at once otherwise
+  frame_stats_kernel<<<nb, 256, 0, stream>>>(rgb, HW, w.stats, w.partials);
+  frame_stats_final_kernel<<<1, 1024, 0, stream>>>(w.partials, nb, w.stats, 1);
+  const int padT = (H1 - H) / 2, padL = (W1 - W) / 2;
+  frame_normalise_pad_kernel<<<grid_for((long)H1 * W1, 256, 8), 256, 0, stream>>>(rgb, H, W, w.stats, f_factor, gray_out, H1, W1, padT, padL);
+  return uncl_check_launch("frame_normalise_pad");
+}
+
+extern "C" int uncl_tiles_gather(const float* frame, int H1, int W1, const int* origins, int T, float* tiles,
+                                 cudaStream_t stream) {
+  UNCL_REQUIRE(T > 0 && H1 >= 256 && W1 >= 256, "tiles_gather: bad arguments");
+  tiles_gather_kernel<<<dim3(16, T), 256, 0, stream>>>(frame, W1, origins, tiles);
+  return uncl_check_launch("tiles_gather");
+}
+
+extern "C" int uncl_tiles_blend(const float* tiles, const int* yidx, const float* yw, const int* ystart,
+                                const int* xidx, const float* xw, const int* xstart, int TX, int K, float* out,
+                                int H1, int W1, cudaStream_t stream) {
+  UNCL_REQUIRE(TX > 0 && K > 0 && H1 >= 256 && W1 >= 256, "tiles_blend: bad arguments");
+  tiles_blend_kernel<<<grid_for((long)H1 * W1, 256, 8), 256, 0, stream>>>(tiles, yidx, yw, ystart, xidx, xw, xstart, TX, K, out, H1, W1);
+  return uncl_check_launch("tiles_blend");
+}
+
+// numpy.percentile(clamp(data, clamp_lo, clamp_hi), [p_lo, p_hi]) with the default 'linear' method -> pct_out[0..1]
+extern "C" int uncl_percentile_pair(const float* data, long n, float clamp_lo, float clamp_hi, double p_lo,
+                                    double p_hi, float* pct_out, void* workspace, cudaStream_t stream) {
+  UNCL_REQUIRE(n >= 2 && p_lo >= 0 && p_hi <= 100 && p_lo <= p_hi, "percentile_pair: bad arguments");
+  FrameWs w = carve(workspace);
+  const double v0 = p_lo / 100.0 * (double)(n - 1), v1 = p_hi / 100.0 * (double)(n - 1);
+  long k0 = (long)v0, k1 = (long)v1;
+  if (k0 > n - 2) k0 = n - 2;
+  if (k1 > n - 2) k1 = n - 2;
+  UNCL_REQUIRE(n < (1L << 32), "percentile_pair: n too large");
+  const SelRanks ranks = {{(unsigned)k0, (unsigned)(k0 + 1), (unsigned)k1, (unsigned)(k1 + 1)}};
+  const int nb = grid_for(n, 512, 4);
+  cudaMemsetAsync(w.hist, 0, 4 * 2048 * 4, stream);
+  select_hist_kernel<0><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist);
+  select_scan_kernel<0><<<1, 32, 0, stream>>>(w.sel, w.hist, ranks);
+  cudaMemsetAsync(w.hist, 0, 4 * 2048 * 4, stream);
+  select_hist_kernel<1><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist);
+  select_scan_kernel<1><<<1, 32, 0, stream>>>(w.sel, w.hist, ranks);
+  cudaMemsetAsync(w.hist, 0, 4 * 2048 * 4, stream);
+  select_hist_kernel<2><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist);
+  select_scan_kernel<2><<<1, 32, 0, stream>>>(w.sel, w.hist, ranks);
+  select_finish_kernel<<<1, 32, 0, stream>>>(w.sel, v0 - (double)k0, v1 - (double)k1, pct_out);
+  return uncl_check_launch("percentile_pair");
+}
+
+extern "C" int uncl_frame_postprocess(const float* fake, int H1, int W1, const float* rgb, int H, int W,
+                                      const float* pct, float* out, void* workspace, cudaStream_t stream) {
+  UNCL_REQUIRE(H > 0 && W > 0 && H1 >= H && W1 >= W, "frame_postprocess: bad arguments");
+  FrameWs w = carve(workspace);
+  frame_postprocess_kernel<<<grid_for((long)H * W, 256, 8), 256, 0, stream>>>(fake, W1, (H1 - H) / 2, (W1 - W) / 2, rgb, H, W, w.stats, pct, out);
+  return uncl_check_launch("frame_postprocess");
+}
+
+extern "C" int uncl_frame_to_u8(const float* col, int H, int W, const float* pct, unsigned char* out,
+                                cudaStream_t stream) {
+  UNCL_REQUIRE(H > 0 && W > 0, "frame_to_u8: bad arguments");
+  frame_to_u8_kernel<<<grid_for((long)H * W, 256, 8), 256, 0, stream>>>(col, (long)H * W, pct, out);
+  return uncl_check_launch("frame_to_u8");
+}

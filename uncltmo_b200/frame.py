@@ -1,0 +1,183 @@
+"""Frame path: HDR frame -> tone-mapped LDR frame, entirely on the GPU.
+
+Host-side mirror of the reference's inference driver (utils/model_save_util.py:293-407 run_model_on_single_image2,
+:409-486 test_big_size_image2, :567-614 run_model_on_video, :488-565 test_big_size_image) with every per-pixel
+operation done by kernels of libuncltmo_b200.so:  log-lambda normalise + replicate pad -> gather 256x256 tiles ->
+generator on ALL tiles in one batch -> closed-form cross-fade blend -> on-device percentiles -> clamp / stretch /
+back-to-colour / crop (-> optional 8-bit stretch).  No host synchronisation inside the path.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call
+
+PATCH = 256
+
+
+def padded_extent(n):
+    """data_loader_util.py:135-157 (resize_im): always pads to 16*floor(n/16)+16."""
+    return 16 * (n // 16) + 16
+
+
+def tile_starts(length, overlap=64, patch=PATCH):
+    """Tile start offsets along one axis (regular tiles, then one anchored at the far edge).
+    model_save_util.py:416-440: `while patch*i - overlap*(i-1) < L`."""
+    if length <= patch:
+        raise ValueError("tiling needs a padded extent > %d px (got %d): the reference fails on such inputs too "
+                         "(undersized edge tile, SURVEY.md §4)" % (patch, length))
+    starts, i = [], 1
+    while patch * i - overlap * (i - 1) < length:
+        starts.append((patch - overlap) * (i - 1))
+        i += 1
+    return starts + [length - patch]
+
+
+def axis_blend_table(length, overlap=64, patch=PATCH):
+    """Closed form of the sequential cross-fade along one axis.
+
+    Returns (starts, idx [L][K] int32, w [L][K] float32): position p of the blended result equals
+    sum_k w[p][k] * tile[idx[p][k]][p - starts[idx[p][k]]].  Derived by pushing unit weights through the
+    reference's update order (model_save_util.py:428-446 for columns, :448-481 for rows)."""
+    starts = tile_starts(length, overlap, patch)
+    nt = len(starts)
+    wt = np.zeros((nt, length), dtype=np.float64)
+    end = 0
+    for j, s in enumerate(starts[:-1]):
+        if j == 0:
+            wt[0, s:s + patch] = 1.0
+        else:
+            for i in range(overlap):
+                wt[:, s + i] *= (overlap - 1 - i) / (overlap - 1)
+                wt[j, s + i] += i / (overlap - 1)
+            wt[:, s + overlap:s + patch] = 0.0
+            wt[j, s + overlap:s + patch] = 1.0
+        end = s + patch
+    last = starts[-1]
+    rng = end - last
+    if rng <= 1:
+        raise ValueError("degenerate edge tile overlap (last_range=%d divides by zero in the reference, "
+                         "model_save_util.py:443)" % rng)
+    for i in range(rng):
+        wt[:, last + i] *= (rng - 1 - i) / (rng - 1)
+        wt[nt - 1, last + i] += i / (rng - 1)
+    wt[:, end:] = 0.0
+    wt[nt - 1, end:] = 1.0
+    k = int((wt != 0).sum(axis=0).max())
+    idx = np.zeros((length, k), dtype=np.int32)
+    w = np.zeros((length, k), dtype=np.float32)
+    for p in range(length):
+        nz = np.nonzero(wt[:, p])[0]
+        idx[p, :len(nz)] = nz
+        w[p, :len(nz)] = wt[nz, p]
+    return starts, idx, w
+
+
+class _Plan:
+    """Per-resolution constants: padded size, tile origins, blend tables (device resident)."""
+
+    def __init__(self, h, w, overlap, device):
+        self.h, self.w = h, w
+        self.h1, self.w1 = padded_extent(h), padded_extent(w)
+        ys, yidx, yw = axis_blend_table(self.h1, overlap)
+        xs, xidx, xw = axis_blend_table(self.w1, overlap)
+        k = max(yidx.shape[1], xidx.shape[1])
+
+        def widen(a):
+            out = np.zeros((a.shape[0], k), dtype=a.dtype)
+            out[:, :a.shape[1]] = a
+            return out
+
+        self.k = k
+        self.ty, self.tx = len(ys), len(xs)
+        self.ntiles = self.ty * self.tx
+        origins = np.array([(y, x) for y in ys for x in xs], dtype=np.int32)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
+        self.origins = dev(origins)
+        self.yidx, self.yw, self.ystart = dev(widen(yidx)), dev(widen(yw)), dev(np.array(ys, dtype=np.int32))
+        self.xidx, self.xw, self.xstart = dev(widen(xidx)), dev(widen(xw)), dev(np.array(xs, dtype=np.int32))
+
+
+class FramePipeline:
+    """HDR rgb frame [3,H,W] (fp32, CUDA) -> tone-mapped colour frame, through `generator` (uncltmo_b200 UNet)."""
+
+    def __init__(self, generator, factor_coeff=0.1, overlap=64, max_tiles_per_batch=256):
+        self.g = generator
+        self.factor_coeff = factor_coeff
+        self.overlap = overlap
+        self.max_tiles = max_tiles_per_batch
+        self._plans = {}
+        self._ws = None
+
+    def plan(self, h, w, device):
+        key = (h, w, self.overlap, str(device))
+        if key not in self._plans:
+            self._plans[key] = _Plan(h, w, self.overlap, device)
+        return self._plans[key]
+
+    def _workspace(self, device):
+        if self._ws is None or self._ws.device != device:
+            self._ws = torch.zeros(_lib.lib().uncl_frame_workspace_bytes(), dtype=torch.uint8, device=device)
+        return self._ws
+
+    # -- stages (each usable on its own; tests compare them one by one with the oracle) --
+    def normalise_pad(self, rgb, lam):
+        """-> gray_log padded [H1,W1] fp32.  model_save_util.py:232-239 + data_loader_util.resize_im."""
+        _, h, w = rgb.shape
+        pl = self.plan(h, w, rgb.device)
+        out = torch.empty((pl.h1, pl.w1), device=rgb.device, dtype=torch.float32)
+        call("uncl_frame_normalise_pad", rgb, h, w, float(lam * 255 * self.factor_coeff), out, pl.h1, pl.w1,
+             self._workspace(rgb.device))
+        return out
+
+    def gather_tiles(self, gray_p, pl):
+        tiles = torch.empty((pl.ntiles, 1, PATCH, PATCH), device=gray_p.device, dtype=torch.float32)
+        call("uncl_tiles_gather", gray_p, pl.h1, pl.w1, pl.origins, pl.ntiles, tiles)
+        return tiles
+
+    def blend(self, tiles, pl):
+        out = torch.empty((pl.h1, pl.w1), device=tiles.device, dtype=torch.float32)
+        call("uncl_tiles_blend", tiles, pl.yidx, pl.yw, pl.ystart, pl.xidx, pl.xw, pl.xstart, pl.tx, pl.k, out,
+             pl.h1, pl.w1)
+        return out
+
+    def run_generator(self, tiles):
+        if tiles.shape[0] <= self.max_tiles:
+            return self.g.tonemap_tiles(tiles)
+        return torch.cat([self.g.tonemap_tiles(tiles[i:i + self.max_tiles])
+                          for i in range(0, tiles.shape[0], self.max_tiles)])
+
+    def percentiles(self, x, p_lo, p_hi, clamp=(-3.0e38, 3.0e38)):
+        out = torch.empty(2, device=x.device, dtype=torch.float32)
+        call("uncl_percentile_pair", x, x.numel(), float(clamp[0]), float(clamp[1]), float(p_lo), float(p_hi), out,
+             self._workspace(x.device))
+        return out
+
+    def postprocess(self, fake_p, rgb, pl):
+        """percentile(0.5, 99.5) clamp -> stretch -> back to colour -> crop.  model_save_util.py:389-402.
+        Must follow normalise_pad() of the same frame (the luminance statistics live in the workspace)."""
+        pct = self.percentiles(fake_p, 0.5, 99.5)
+        out = torch.empty((3, pl.h, pl.w), device=rgb.device, dtype=torch.float32)
+        call("uncl_frame_postprocess", fake_p, pl.h1, pl.w1, rgb, pl.h, pl.w, pct, out, self._workspace(rgb.device))
+        return out
+
+    def to_uint8(self, col):
+        """hdr_image_util.save_gray_tensor_as_numpy_stretch without the file write: HWC uint8."""
+        _, h, w = col.shape
+        pct = self.percentiles(col, 0.1, 99.0, clamp=(0.0, 1.0))
+        out = torch.empty((h, w, 3), device=col.device, dtype=torch.uint8)
+        call("uncl_frame_to_u8", col, h, w, pct, out)
+        return out
+
+    # -- whole path --
+    def tonemap(self, rgb, lam, uint8=False):
+        """rgb [3,H,W] fp32 CUDA, lam = the image's lambda (f = lam*255*factor_coeff) -> [3,H,W] fp32 or HWC uint8."""
+        if not (rgb.is_cuda and rgb.dtype == torch.float32 and rgb.dim() == 3 and rgb.shape[0] == 3):
+            raise ValueError("tonemap expects a CUDA fp32 [3,H,W] tensor")
+        rgb = rgb.contiguous()
+        pl = self.plan(rgb.shape[1], rgb.shape[2], rgb.device)
+        gray_p = self.normalise_pad(rgb, lam)
+        tiles = self.gather_tiles(gray_p, pl)
+        fake_p = self.blend(self.run_generator(tiles), pl)
+        col = self.postprocess(fake_p, rgb, pl)
+        return self.to_uint8(col) if uint8 else col
