@@ -132,6 +132,47 @@ int uncl_frame_postprocess(const float* fake, int H1, int W1, const float* rgb, 
 /* clamp(0,1), stretch between pct[0..1], clip, *255 -> uint8 HWC.  hdr_image_util.py:237-245, 93-102. */
 int uncl_frame_to_u8(const float* col, int H, int W, const float* pct, unsigned char* out, uncl_stream_t stream);
 
+/* ---- discriminator and training losses, forward (dense fp32 planes [M][H][W]) ---- */
+
+/* per-plane mean and mean of the local variance under the 11x11 gaussian (sigma 1.5, valid):
+ * ContrastExtracter / compute_contrast + adaptive_avg_pool2d.  models/Discriminator.py:49-83, 121-125;
+ * Unet.py:101-133, 274-278; GanTrainerImg.py:24-56, 308-313.  scratch: 2*M floats.  Outputs may be NULL. */
+int uncl_plane_mean_contrast(const float* x, long plane_stride, int M, int H, int W, float* mean_out,
+                             float* cmean_out, float* scratch, uncl_stream_t stream);
+
+/* F.interpolate(scale_factor=0.5, mode='bicubic', align_corners=False).  models/struct_loss.py:52-53. */
+int uncl_bicubic_half(const float* in, float* out, int M, int H, int W, uncl_stream_t stream);
+
+/* StructLoss.forward: sum_l w[l] * MSE(z-normalised 5x5 windows of fake_l, of hdr_l), pyramid by bicubic x0.5.
+ * models/struct_loss.py:23-104.  weights_host: HOST array [levels].  loss_out: 1 float (device).
+ * scratch: >= 2*M*(H/2)*(W/2)*4/3 floats. */
+int uncl_struct_loss_fwd(const float* fake, const float* hdr, int M, int H, int W, int levels,
+                         const float* weights_host, float* loss_out, float* scratch, uncl_stream_t stream);
+
+/* SimpleDiscriminator.forward up to (fea map, logits): models/Discriminator.py:98-122.
+ * w1 [16][1][4][4], w2 [32][16][4][4], w3 [32], w_tail [62*62]; h_scratch N*16*127*127 floats;
+ * fea [N][62][62]; logits [N]. */
+int uncl_disc_forward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                      const float* w3, const float* b3, const float* w_tail, float* h_scratch, float* fea,
+                      float* logits, int N, int H, int W, uncl_stream_t stream);
+
+/* GanTrainer.contrastive_D_loss.  GanTrainerImg.py:219-229. */
+int uncl_contrastive_d_loss(const float* real_logits, const float* fake_logits, int B, float* out,
+                            uncl_stream_t stream);
+
+/* GanTrainer.nce with one positive and one negative, 'InfoNCE'.  GanTrainerImg.py:410-439.
+ * anchor [B][C][HW]; pos / neg likewise with image stride pos_stride / neg_stride in elements (0 = one sample
+ * broadcast, as infoNCE2 does :400-401).  logits_scratch: 2*B floats. */
+int uncl_nce_fwd(const float* anchor, const float* pos, long pos_stride, const float* neg, long neg_stride, int B,
+                 int C, int HW, float k, float constant, float* logits_scratch, float* loss_out,
+                 uncl_stream_t stream);
+
+/* nn.L1Loss of two vectors (per-image means).  GanTrainerImg.py:308-313. */
+int uncl_l1_mean(const float* a, const float* b, int n, float* out, uncl_stream_t stream);
+
+/* L_TV.  GanTrainer.py:669-682.  scratch: 2 floats. */
+int uncl_tv_loss(const float* x, int B, int C, int H, int W, float* scratch, float* out, uncl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
