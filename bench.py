@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Headline benchmark: 1080p tone-mapped frames/s through the B200 UnCLTMO hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16|fp32]
+
+One "step" = one synthetic 1080p HDR frame through the whole frame path: log-lambda normalise + pad ->
+60 tiles of 256x256 -> U-Net generator (incl. bottleneck graph block) on all tiles -> cross-fade blend ->
+percentile clamp / stretch / back-to-colour / crop -> 8-bit stretch.  N > 1 shards frames over ranks (one
+process per GPU, no data-path collective: image frames are independent - SURVEY.md §8e), weak scaling.
+
+Printed JSON (rank 0, one line):
+  value      frames/s with the HDR frame already resident in HBM (device-timed, max over ranks)
+  e2e        frames/s through the public API with HOST buffers: pinned H2D of the frame + D2H of the 8-bit result
+             inside the timed region
+  roofline   tensor-core roofline of the dominant kernel (conv3x3_tc, all 3x3 conv / ConvTranspose layers):
+             algorithmic FLOP per frame of those layers / device time spent in them, against the measured peak
+  cpu_baseline  the CPU oracle (PyTorch-on-CPU restatement of the reference, `oracle/`) on this box's host cores,
+             on a bounded sample of the same workload
+--impl reference times that CPU arm alone (the reference has no GPU-independent build to install: it IS the
+PyTorch code path the oracle restates).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 1080, 1920
+TILES = 60
+LAMBDA = 371.4          # median of lambda_data/input_images_lambdas.npy
+GFLOP_TILE = 18.2858    # generator forward per 256x256 tile
+# MACs per tile of the layers that run in conv3x3_tc: total 9.1429 GMAC minus inc.conv (0.0186), the four
+# ConvTranspose k2 s2 (0.0377+0.0514+0.0610+0.0650), the graph block (0.0566) and outc (0.0021)  
+GFLOP_TILE_TC = 2 * (9.1429 - 0.0186 - 0.2151 - 0.0566 - 0.0021)
+METRIC = "1080p tone-mapped frames/s (UNet fwd)"
+CONFIG = {"workload": "image TMO inference, one 1920x1080 HDR frame per step per GPU = 60 tiles of 256x256 "
+                      "(pad to 1088x1936, overlap 64), random-init weights, lambda 371.4",
+          "tiles_per_frame": TILES, "gflop_per_frame": TILES * GFLOP_TILE,
+          "l2": "3 frames rotate per rank and each step writes/reads >2 GB of activations (>> 126 MB L2), "
+                "so no input survives in L2 between steps",
+          "parallelism": "frames sharded over ranks, no collective",
+          "not_built_yet": "training step (backward kernels): 256^2 train steps/s is not reported this round"}
+G_ARGS = (1, 1, "sigmoid", 4, 4, "square_and_square_root", 32, 0, "unet", 0, 0, "none", "none", "relu", 1, "replicate", 2)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if "Active" in v and "Not" not in v:
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def cpu_reference_arm(steps, warmup, threads=None):
+    """The CPU oracle on the host cores.  One step = the generator on ONE 256x256 tile at batch 1 (the reference
+    runs tile by tile, utils/model_save_util.py:417-427); the rest of the frame path (normalise, pad, sequential
+    cross-fade, percentiles, back-to-colour) is timed once on the full 1080p frame with the generator stubbed out.
+    frame time = 60 * median(tile) + rest."""
+    import oracle
+    from uncltmo_b200 import synth
+    from uncltmo_b200.weights import make_generator_state_dict
+    torch.set_grad_enabled(False)
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = make_generator_state_dict()
+    rgb = torch.from_numpy(synth.hdr_frame(H, W, seed=0))
+    _, gray = oracle.log_lambda_normalise(rgb, LAMBDA)
+    gp, _, _ = oracle.resize_im(gray)
+    tiles = [gp[None, :, y:y + 256, x:x + 256].contiguous() for y in (0, 192, 384) for x in (0, 576, 1152, 1680)]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        oracle.unet_forward(sd, tiles[i % len(tiles)])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    t_tile = float(np.median(times))
+    t0 = time.perf_counter()
+    col = oracle.tonemap_frame(rgb, LAMBDA, lambda t: t * 0.5 + 0.25)
+    oracle.frame_path.to_uint8_stretch(col)
+    t_rest = time.perf_counter() - t0
+    t_frame = TILES * t_tile + t_rest
+    return {"value": 1.0 / t_frame, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": "%d generator tiles at batch 1 (median %.1f ms/tile, x60 tiles) + the rest of the 1080p frame path "
+                      "timed once with the generator stubbed (%.2f s)" % (len(times), t_tile * 1e3, t_rest),
+            "ms_per_tile": t_tile * 1e3, "rest_s": t_rest}, float(np.sum(times)) + t_rest
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, _ = cpu_reference_arm(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_tile"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": CONFIG,
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from uncltmo_b200 import _lib, synth
+    from uncltmo_b200.frame import FramePipeline
+    from uncltmo_b200.generator import UNet
+    from uncltmo_b200.weights import make_generator_state_dict
+    torch.set_grad_enabled(False)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    net = UNet(*G_ARGS, up_mode=0, precision=args.precision).to(dev).eval()
+    net.load_state_dict(make_generator_state_dict())
+    pipe = FramePipeline(net)
+    # a few distinct frames per rank so no step re-reads a frame that is still warm in L2 from the previous one
+    nframes = 3
+    host_frames = [torch.from_numpy(synth.hdr_frame(H, W, seed=100 * rank + i)).pin_memory() for i in range(nframes)]
+    dev_frames = [f.to(dev) for f in host_frames]
+    host_out = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        for i in range(args.warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    def step_resident(i):
+        pipe.tonemap(dev_frames[i % nframes], LAMBDA, uint8=True)
+
+    def step_e2e(i):
+        x = host_frames[i % nframes].to(dev, non_blocking=True)
+        y = pipe.tonemap(x, LAMBDA, uint8=True)
+        host_out.copy_(y, non_blocking=True)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    _lib.reset_launch_count()
+    ms_res = timed(step_resident, args.steps)
+    launches = _lib.launch_count() * args.steps // (args.steps + args.warmup)
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    # per-kernel device time (separate instrumented pass: an event pair around every C-ABI call)
+    roof = None
+    if rank == 0:
+        per_call = {}
+        reps = 3
+        for i in range(reps + 1):
+            _lib.start_call_timing()
+            step_resident(i)
+            torch.cuda.synchronize()
+            rec = _lib.stop_call_timing()
+            if i == 0:
+                continue
+            for name, ms in rec:
+                per_call.setdefault(name, []).append(ms)
+        tot = {k: sum(v) / reps for k, v in per_call.items()}
+        cnt = {k: len(v) // reps for k, v in per_call.items()}
+        tc_ms = tot.get("uncl_conv3x3_tc", None) if args.precision == "bf16" else tot.get("uncl_conv3x3_simt")
+        peak, hbm, how = measured_peaks()
+        if tc_ms:
+            name = "conv3x3_tc" if args.precision == "bf16" else "conv3x3_simt"
+            n_launch = cnt["uncl_" + name]
+            achieved = TILES * GFLOP_TILE_TC / tc_ms  # GFLOP/ms == TFLOP/s
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch_avg")
+            roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": how,
+                    "launches_per_step": n_launch, "avg_launch_ms": tc_ms / n_launch,
+                    "algorithmic_gflop_per_launch_avg": TILES * GFLOP_TILE_TC / n_launch,
+                    "share_of_step": tc_ms / sum(tot.values()),
+                    "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
+
+    if rank == 0:
+        base = None
+        if world == 1 and not args.no_cpu_baseline:
+            base, _ = cpu_reference_arm(steps=12, warmup=2)
+            base = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        fps = world * args.steps / (ms_res / 1e3)
+        line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": CONFIG,
+                "tflops_generator": world * args.steps * TILES * GFLOP_TILE / ms_res,
+                "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": "frames/s",
+                        "h2d_bytes_per_step": 3 * H * W * 4, "d2h_bytes_per_step": H * W * 3},
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": base, "clocks": clocks}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

