@@ -104,9 +104,9 @@ long uncl_frame_workspace_bytes(void);
 /* log-lambda normalisation fused with the replicate pad:  Y = .299R+.587G+.114B (after rgb -= min(rgb) if negative),
  * Y -= min; out = log10(Y/max*f + 1) / max(...), written into the (H1 x W1) padded frame.
  * model_save_util.py:232-239 (load_inference2), 255-262; hdr_image_util.py:76-82; data_loader_util.py:135-157, 175-179.
- * rgb [3][H][W] fp32.  Leaves (min rgb, min Y, max Y) in the workspace for uncl_frame_postprocess. */
+ * rgb [3][H][W] fp32.  stats_out[4] receives (min rgb, min Y, max Y, -) for uncl_frame_postprocess. */
 int uncl_frame_normalise_pad(const float* rgb, int H, int W, float f_factor, float* gray_out, int H1, int W1,
-                             void* workspace, uncl_stream_t stream);
+                             float* stats_out, void* workspace, uncl_stream_t stream);
 
 /* gather T 256x256 tiles at origins[t] = (y, x) from the padded frame.  model_save_util.py:417-426, 438, 455-459, 470. */
 int uncl_tiles_gather(const float* frame, int H1, int W1, const int* origins, int T, float* tiles,
@@ -125,9 +125,9 @@ int uncl_percentile_pair(const float* data, long n, float clamp_lo, float clamp_
                          float* pct_out, void* workspace, uncl_stream_t stream);
 
 /* clamp to pct, min-max stretch, (rgb/(Y+1e-8))^0.5 * fake, crop the pad.  model_save_util.py:393-402,
- * hdr_image_util.py:122-132.  fake [H1][W1]; rgb / out [3][H][W]. */
-int uncl_frame_postprocess(const float* fake, int H1, int W1, const float* rgb, int H, int W, const float* pct,
-                           float* out, void* workspace, uncl_stream_t stream);
+ * hdr_image_util.py:122-132.  fake [H1][W1]; rgb / out [3][H][W]; stats from uncl_frame_normalise_pad. */
+int uncl_frame_postprocess(const float* fake, int H1, int W1, const float* rgb, int H, int W, const float* stats,
+                           const float* pct, float* out, uncl_stream_t stream);
 
 /* clamp(0,1), stretch between pct[0..1], clip, *255 -> uint8 HWC.  hdr_image_util.py:237-245, 93-102. */
 int uncl_frame_to_u8(const float* col, int H, int W, const float* pct, unsigned char* out, uncl_stream_t stream);

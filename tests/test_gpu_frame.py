@@ -38,7 +38,7 @@ def test_normalise_and_pad(golden):
     _, gray = oracle.log_lambda_normalise(rgb, gi.LAMBDA)
     gp, dy, dx = oracle.resize_im(gray)
     pipe = FramePipeline(CheapG())
-    got = pipe.normalise_pad(rgb.cuda(), gi.LAMBDA)
+    got, _ = pipe.normalise_pad(rgb.cuda(), gi.LAMBDA)
     assert got.shape == gp.shape[1:]
     assert maxabs(got, gp[0]) <= 2e-6
     assert maxabs(got[dy // 2:dy // 2 + 268:2, dx // 2:dx // 2 + 300:2], golden["norm_gray_s2"][0]) <= 2e-6
@@ -48,7 +48,7 @@ def test_normalise_negative_input_shift():
     rgb = torch.from_numpy(gi.small_frame()) - 0.37  # exr-style negative values (model_save_util.py:233-234)
     _, gray = oracle.log_lambda_normalise(rgb, 371.4)
     gp, _, _ = oracle.resize_im(gray)
-    got = FramePipeline(CheapG()).normalise_pad(rgb.cuda(), 371.4)
+    got, _ = FramePipeline(CheapG()).normalise_pad(rgb.cuda(), 371.4)
     assert maxabs(got, gp[0]) <= 5e-6
 
 
@@ -94,7 +94,7 @@ def test_frame_end_to_end_matches_reference_fixture(net, golden):
     rgb = torch.from_numpy(gi.small_frame())
     pipe = FramePipeline(net)
     pl = pipe.plan(268, 300, torch.device("cuda"))
-    gray_p = pipe.normalise_pad(rgb.cuda(), gi.LAMBDA)
+    gray_p, _ = pipe.normalise_pad(rgb.cuda(), gi.LAMBDA)
     fake_p = pipe.blend(pipe.run_generator(pipe.gather_tiles(gray_p, pl)), pl)
     assert maxabs(fake_p[::2, ::2], golden["frame_fake_s2"][0, 0]) <= 2e-6
     pct = pipe.percentiles(fake_p, 0.5, 99.5).cpu().numpy()
@@ -117,7 +117,7 @@ def test_frame_1080p_properties(net):
     pipe = FramePipeline(net_bf)
     pl = pipe.plan(1080, 1920, rgb.device)
     assert (pl.h1, pl.w1, pl.ntiles) == (1088, 1936, 60)
-    gray_p = pipe.normalise_pad(rgb, 50.0)
+    gray_p, _ = pipe.normalise_pad(rgb, 50.0)
     assert gray_p.min().item() == 0.0 and abs(gray_p.max().item() - 1.0) < 1e-6
     tiles = pipe.gather_tiles(gray_p, pl)
     batched = pipe.run_generator(tiles)
@@ -127,3 +127,34 @@ def test_frame_1080p_properties(net):
     assert col.shape == (3, 1080, 1920) and torch.isfinite(col).all() and col.min().item() >= 0.0
     u8 = pipe.tonemap(rgb, 50.0, uint8=True)
     assert u8.shape == (1080, 1920, 3)
+
+
+def test_video_clip_path_matches_oracle():
+    """run_model_on_video on a 3-frame 268x300 clip: per-frame normalise, recurrent tile chains, per-frame blend and
+    post-process, against the oracle's sequential restatement (5-D tiling, model_save_util.py:488-565)."""
+    from uncltmo_b200.generator import UNetVideo
+    sd = make_generator_state_dict()
+    clip = synth.hdr_clip(3, 268, 300, seed=9)
+    lam = 371.4
+    vid = UNetVideo(*G_ARGS, up_mode=0, precision="fp32").cuda().eval()
+    vid.load_state_dict(sd)
+    got = FramePipeline(vid).tonemap_clip(torch.from_numpy(clip).cuda(), lam)
+    grays, rgbs = [], []
+    for t in range(3):
+        rgb, g = oracle.log_lambda_normalise(torch.from_numpy(clip[t]), lam)
+        gp, dy, dx = oracle.resize_im(g)
+        rgbs.append(oracle.resize_im(rgb)[0])
+        grays.append(gp[None, None])
+    x5 = torch.cat(grays, 1)  # [1,T,1,H1,W1]
+    fakes = oracle.tile_and_blend(x5, lambda tl: oracle.unet_video_forward(sd, tl)[0])
+    for t in range(3):
+        want = oracle.postprocess_frame(fakes[:, t], rgbs[t], dy, dx)
+        assert maxabs(got[t], want) <= 5e-4, t
+    indep = FramePipeline(net_fp32()).tonemap(torch.from_numpy(clip[2]).cuda(), lam)
+    assert maxabs(got[2], indep) > 1e-4  # the temporal recurrence is live
+
+
+def net_fp32():
+    n = UNet(*G_ARGS, up_mode=0, precision="fp32").cuda().eval()
+    n.load_state_dict(make_generator_state_dict())
+    return n

@@ -136,7 +136,7 @@ def test_video_generator_matches_oracle(golden):
     assert rel(feat, o_feat) <= 1e-3 and rel(feat, golden["g_vid_feat"]) <= 1e-3
     # the recurrence must matter: frame 1 differs from running it as an independent frame
     indep = make("fp32")(xv[:, 1].cuda())[0]
-    assert rel(out[:, 1], indep) > 1e-4
+    assert rel(out[:, 1], indep) > 2e-5  # ~8e-5 with these weights: 30 of 1500 channels are handed over
     bf = make("bf16", UNetVideo)(xv.cuda())[0]
     assert rel(bf, o_out) <= 1e-2
 
@@ -147,6 +147,9 @@ def test_droppath_masks_match_oracle():
     scale = [torch.tensor([0.0, 1 / 0.95]), torch.tensor([1 / 0.95, 0.0])]
     o_out, _ = oracle.unet_forward(sd, x, droppath_masks=scale)
     net = make("fp32")
-    out, _, _, _ = net._run_frame(x.cuda(), droppath_scale=[s.cuda() for s in scale])
+    keep = {}
+    out, _, _, _ = net._run_frame(x.cuda(), droppath_scale=[s.cuda() for s in scale], keep=keep)
     assert rel(out, o_out) <= 1e-4
-    assert rel(out, oracle.unet_forward(sd, x)[0]) > 1e-4
+    skips = oracle.unet_forward(sd, x, return_all=True)[2]["skips"]
+    assert rel(blocked_to_nchw(keep["gcn"]), oracle.gcn_block(sd, skips[4], scale)) <= 1e-5
+    assert rel(blocked_to_nchw(keep["gcn"]), oracle.gcn_block(sd, skips[4])) > 1e-2  # the masks are live

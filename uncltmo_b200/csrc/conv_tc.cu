@@ -93,15 +93,19 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
+// descriptors travel as (lo, hi) 32-bit halves: only `lo` (start address | LBO) changes between MMAs
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
       "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -116,6 +120,18 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // K-major, no-swizzle shared-memory matrix descriptor (sm_100 "version 1").
@@ -216,34 +232,68 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     __syncwarp();
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // the whole warp walks the (uniform) loop so that descriptors live in uniform registers; one elected lane issues
+    {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t lbo_a = (uint32_t)(p.PH * p.PW * 16), lbo_b = (uint32_t)(p.NT * 16);
+      // K-major no-swizzle descriptors: lo = (addr >> 4) | (LBO >> 4) << 16 ; hi = (SBO >> 4) | version 1 << 14
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+      const uint32_t a_lo_const = ((uint32_t)(p.PH * p.PW) & 0x3fffu) << 16;   // LBO_A = PH*PW*16 B
+      const uint32_t b_lo_const = ((uint32_t)p.NT & 0x3fffu) << 16;            // LBO_B = NT*16 B
+      const uint32_t stage0_16 = smem_u32(stage_base) >> 4, stage_16 = (uint32_t)p.stage_bytes >> 4;
+      const uint32_t a_bytes_16 = (uint32_t)p.a_stage_bytes >> 4, b_tap_16 = (uint32_t)(2 * p.NT);
+      const uint32_t mstep = (p.mode == 0) ? (uint32_t)p.PW : 128u;
+      const uint32_t pw = (uint32_t)p.PW, nt = (uint32_t)p.NT;
+      const bool taps9 = p.ntaps == 9;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const Item it = decode_item(p, item);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const int mstep = (p.mode == 0) ? p.PW : 128;
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * kAccCols);
+        const uint32_t mb = (uint32_t)it.mb_act;
         for (int ch = 0; ch < p.nchunk; ++ch) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + (size_t)stage * p.stage_bytes);
-          const uint32_t sb = sa + (uint32_t)p.a_stage_bytes;
-          for (int t = 0; t < p.ntaps; ++t) {
-            const int tapoff = (p.ntaps == 9) ? (t / 3) * p.PW + (t % 3) : 0;
-            const uint64_t bdesc = make_desc(sb + (uint32_t)(t * 2 * p.NT * 16), lbo_b, 128);
-            const uint32_t accum = (ch > 0 || t > 0) ? 1u : 0u;
-            for (int b = 0; b < it.mb_act; ++b) {
-              const uint64_t adesc = make_desc(sa + (uint32_t)((it.moff0 + b * mstep + tapoff) * 16), lbo_a, 128);
-              tc_mma_bf16(tmem_base + (uint32_t)(acc * kAccCols + b * p.NT), adesc, bdesc, idesc, accum);
+          const uint32_t sa16 = stage0_16 + (uint32_t)stage * stage_16;
+          uint32_t a_row = a_lo_const | (sa16 + (uint32_t)it.moff0);
+          uint32_t b_lo = b_lo_const | (sa16 + a_bytes_16);
+          if (taps9) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const uint32_t accum = (ky > 0 || kx > 0) ? 1u : (ch > 0 ? 1u : 0u);
+                uint32_t a_lo = a_row + (uint32_t)kx, d = d0;
+                if (elect_one()) {
+                  for (uint32_t b = 0; b < mb; ++b) {
+                    tc_mma_bf16(d, a_lo, desc_hi, b_lo, desc_hi, idesc, accum);
+                    a_lo += mstep;
+                    d += nt;
+                  }
+                }
+                __syncwarp();
+                b_lo += b_tap_16;
+              }
+              a_row += pw;
             }
+          } else {
+            uint32_t a_lo = a_row, d = d0;
+            if (elect_one()) {
+              for (uint32_t b = 0; b < mb; ++b) {
+                tc_mma_bf16(d, a_lo, desc_hi, b_lo, desc_hi, idesc, ch > 0 ? 1u : 0u);
+                a_lo += mstep;
+                d += nt;
+              }
+            }
+            __syncwarp();
           }
-          tc_commit(&empty[stage]);
+          if (elect_one()) tc_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull[acc]);
+        if (elect_one()) tc_commit(&tfull[acc]);
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

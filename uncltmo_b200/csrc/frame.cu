@@ -195,31 +195,44 @@ __global__ void __launch_bounds__(512) select_hist_kernel(const float* __restric
     if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
 }
 
+// one warp per query: lanes own contiguous slices of the histogram, warp prefix sum locates the bin holding `rank`
 template <int PASS>
-__global__ void select_scan_kernel(SelState* st, unsigned* hist, const SelRanks ranks_in) {
+__global__ void __launch_bounds__(32 * kSelQ) select_scan_kernel(SelState* st, unsigned* hist, const SelRanks ranks_in) {
   constexpr int BITS = PASS == 2 ? 10 : 11;
-  const int q = threadIdx.x;
-  if (q < kSelQ) {
-    unsigned rank = PASS == 0 ? ranks_in.r[q] : st->rank[q];
-    const unsigned pre = PASS == 0 ? 0u : st->prefix[q];
-    int slot = 0;
-    if (PASS != 0) {
-      slot = q;
-      for (int q2 = q - 1; q2 >= 0; --q2)
-        if (st->prefix[q2] == pre) slot = q2;
-    }
-    const unsigned* h = hist + ((size_t)slot << BITS);
-    unsigned cum = 0;
+  constexpr int PER = (1 << BITS) / 32;
+  const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned rank = PASS == 0 ? ranks_in.r[q] : st->rank[q];
+  const unsigned pre = PASS == 0 ? 0u : st->prefix[q];
+  int slot = 0;
+  if (PASS != 0) {
+    slot = q;
+    for (int q2 = q - 1; q2 >= 0; --q2)
+      if (st->prefix[q2] == pre) slot = q2;
+  }
+  __syncthreads();  // every warp has read the old prefixes / ranks before anyone overwrites them
+  const unsigned* h = hist + ((size_t)slot << BITS) + lane * PER;
+  unsigned mine = 0;
+  for (int i = 0; i < PER; ++i) mine += h[i];
+  unsigned incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const unsigned excl = incl - mine;
+  // the owner lane is the first one whose inclusive count exceeds rank (the last lane if counts fall short)
+  const unsigned ballot = __ballot_sync(0xffffffffu, rank < incl);
+  const int owner = ballot ? __ffs(ballot) - 1 : 31;
+  if (lane == owner) {
+    unsigned cum = excl;
     int b = 0;
-    for (; b < (1 << BITS) - 1; ++b) {
+    for (; b < PER - 1; ++b) {
       const unsigned c = h[b];
       if (rank < cum + c) break;
       cum += c;
     }
-    __syncwarp(__activemask());
-    // all readers of st->prefix are done before anyone overwrites it (single warp, lock-step after the loop)
     st->rank[q] = rank - cum;
-    st->prefix[q] = (pre << BITS) | (unsigned)b;
+    st->prefix[q] = (pre << BITS) | (unsigned)(lane * PER + b);
   }
 }
 
@@ -302,19 +315,19 @@ static FrameWs carve(void* ws) {
 }
 
 extern "C" int uncl_frame_normalise_pad(const float* rgb, int H, int W, float f_factor, float* gray_out, int H1, int W1,
-                                        void* workspace, cudaStream_t stream) {
+                                        float* stats_out, void* workspace, cudaStream_t stream) {
   UNCL_REQUIRE(H > 0 && W > 0 && H1 >= H && W1 >= W && f_factor > 0.f, "frame_normalise_pad: bad arguments");
   UNCL_REQUIRE((reinterpret_cast<uintptr_t>(rgb) & 15) == 0, "frame_normalise_pad: rgb must be 16-byte aligned");
   FrameWs w = carve(workspace);
   const long HW = (long)H * W;
   const int nb = grid_for(HW / 4 + 1, 256, 8);
   frame_stats_kernel<<<nb, 256, 0, stream>>>(rgb, HW, nullptr, w.partials);
-  frame_stats_final_kernel<<<1, 1024, 0, stream>>>(w.partials, nb, w.stats, 0);
+  frame_stats_final_kernel<<<1, 1024, 0, stream>>>(w.partials, nb, stats_out, 0);
   // negative inputs (exr): shift by min(rgb) and recompute the luminance range; both kernels exit at once otherwise
-  frame_stats_kernel<<<nb, 256, 0, stream>>>(rgb, HW, w.stats, w.partials);
-  frame_stats_final_kernel<<<1, 1024, 0, stream>>>(w.partials, nb, w.stats, 1);
+  frame_stats_kernel<<<nb, 256, 0, stream>>>(rgb, HW, stats_out, w.partials);
+  frame_stats_final_kernel<<<1, 1024, 0, stream>>>(w.partials, nb, stats_out, 1);
   const int padT = (H1 - H) / 2, padL = (W1 - W) / 2;
-  frame_normalise_pad_kernel<<<grid_for((long)H1 * W1, 256, 8), 256, 0, stream>>>(rgb, H, W, w.stats, f_factor, gray_out, H1, W1, padT, padL);
+  frame_normalise_pad_kernel<<<grid_for((long)H1 * W1, 256, 8), 256, 0, stream>>>(rgb, H, W, stats_out, f_factor, gray_out, H1, W1, padT, padL);
   return uncl_check_launch("frame_normalise_pad");
 }
 
@@ -347,22 +360,21 @@ extern "C" int uncl_percentile_pair(const float* data, long n, float clamp_lo, f
   const int nb = grid_for(n, 512, 4);
   cudaMemsetAsync(w.hist, 0, 4 * 2048 * 4, stream);
   select_hist_kernel<0><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist);
-  select_scan_kernel<0><<<1, 32, 0, stream>>>(w.sel, w.hist, ranks);
+  select_scan_kernel<0><<<1, 32 * kSelQ, 0, stream>>>(w.sel, w.hist, ranks);
   cudaMemsetAsync(w.hist, 0, 4 * 2048 * 4, stream);
   select_hist_kernel<1><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist);
-  select_scan_kernel<1><<<1, 32, 0, stream>>>(w.sel, w.hist, ranks);
+  select_scan_kernel<1><<<1, 32 * kSelQ, 0, stream>>>(w.sel, w.hist, ranks);
   cudaMemsetAsync(w.hist, 0, 4 * 2048 * 4, stream);
   select_hist_kernel<2><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist);
-  select_scan_kernel<2><<<1, 32, 0, stream>>>(w.sel, w.hist, ranks);
+  select_scan_kernel<2><<<1, 32 * kSelQ, 0, stream>>>(w.sel, w.hist, ranks);
   select_finish_kernel<<<1, 32, 0, stream>>>(w.sel, v0 - (double)k0, v1 - (double)k1, pct_out);
   return uncl_check_launch("percentile_pair");
 }
 
 extern "C" int uncl_frame_postprocess(const float* fake, int H1, int W1, const float* rgb, int H, int W,
-                                      const float* pct, float* out, void* workspace, cudaStream_t stream) {
+                                      const float* stats, const float* pct, float* out, cudaStream_t stream) {
   UNCL_REQUIRE(H > 0 && W > 0 && H1 >= H && W1 >= W, "frame_postprocess: bad arguments");
-  FrameWs w = carve(workspace);
-  frame_postprocess_kernel<<<grid_for((long)H * W, 256, 8), 256, 0, stream>>>(fake, W1, (H1 - H) / 2, (W1 - W) / 2, rgb, H, W, w.stats, pct, out);
+  frame_postprocess_kernel<<<grid_for((long)H * W, 256, 8), 256, 0, stream>>>(fake, W1, (H1 - H) / 2, (W1 - W) / 2, rgb, H, W, stats, pct, out);
   return uncl_check_launch("frame_postprocess");
 }
 

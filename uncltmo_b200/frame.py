@@ -122,13 +122,15 @@ class FramePipeline:
 
     # -- stages (each usable on its own; tests compare them one by one with the oracle) --
     def normalise_pad(self, rgb, lam):
-        """-> gray_log padded [H1,W1] fp32.  model_save_util.py:232-239 + data_loader_util.resize_im."""
+        """-> (gray_log padded [H1,W1] fp32, stats [4] = (min rgb, min Y, max Y, -)).
+        model_save_util.py:232-239 + data_loader_util.resize_im."""
         _, h, w = rgb.shape
         pl = self.plan(h, w, rgb.device)
         out = torch.empty((pl.h1, pl.w1), device=rgb.device, dtype=torch.float32)
-        call("uncl_frame_normalise_pad", rgb, h, w, float(lam * 255 * self.factor_coeff), out, pl.h1, pl.w1,
+        stats = torch.empty(4, device=rgb.device, dtype=torch.float32)
+        call("uncl_frame_normalise_pad", rgb, h, w, float(lam * 255 * self.factor_coeff), out, pl.h1, pl.w1, stats,
              self._workspace(rgb.device))
-        return out
+        return out, stats
 
     def gather_tiles(self, gray_p, pl):
         tiles = torch.empty((pl.ntiles, 1, PATCH, PATCH), device=gray_p.device, dtype=torch.float32)
@@ -153,12 +155,11 @@ class FramePipeline:
              self._workspace(x.device))
         return out
 
-    def postprocess(self, fake_p, rgb, pl):
-        """percentile(0.5, 99.5) clamp -> stretch -> back to colour -> crop.  model_save_util.py:389-402.
-        Must follow normalise_pad() of the same frame (the luminance statistics live in the workspace)."""
+    def postprocess(self, fake_p, rgb, stats, pl):
+        """percentile(0.5, 99.5) clamp -> stretch -> back to colour -> crop.  model_save_util.py:389-402."""
         pct = self.percentiles(fake_p, 0.5, 99.5)
         out = torch.empty((3, pl.h, pl.w), device=rgb.device, dtype=torch.float32)
-        call("uncl_frame_postprocess", fake_p, pl.h1, pl.w1, rgb, pl.h, pl.w, pct, out, self._workspace(rgb.device))
+        call("uncl_frame_postprocess", fake_p, pl.h1, pl.w1, rgb, pl.h, pl.w, stats, pct, out)
         return out
 
     def to_uint8(self, col):
@@ -176,8 +177,31 @@ class FramePipeline:
             raise ValueError("tonemap expects a CUDA fp32 [3,H,W] tensor")
         rgb = rgb.contiguous()
         pl = self.plan(rgb.shape[1], rgb.shape[2], rgb.device)
-        gray_p = self.normalise_pad(rgb, lam)
+        gray_p, stats = self.normalise_pad(rgb, lam)
         tiles = self.gather_tiles(gray_p, pl)
         fake_p = self.blend(self.run_generator(tiles), pl)
-        col = self.postprocess(fake_p, rgb, pl)
+        col = self.postprocess(fake_p, rgb, stats, pl)
         return self.to_uint8(col) if uint8 else col
+
+    def tonemap_clip(self, frames, lam, uint8=False):
+        """Video path (run_model_on_video, model_save_util.py:567-614): frames [T,3,H,W] fp32 CUDA of ONE scene, one
+        lambda per scene.  `self.g` must be the video generator (UNetVideo): every tile is a chain over the T frames
+        that hands its recurrent channel slices from frame to frame; tiles are independent of each other."""
+        if not (frames.is_cuda and frames.dtype == torch.float32 and frames.dim() == 4 and frames.shape[1] == 3):
+            raise ValueError("tonemap_clip expects a CUDA fp32 [T,3,H,W] tensor")
+        frames = frames.contiguous()
+        t_len = frames.shape[0]
+        pl = self.plan(frames.shape[2], frames.shape[3], frames.device)
+        norm = [self.normalise_pad(frames[t], lam) for t in range(t_len)]
+        tiles = [self.gather_tiles(g, pl) for g, _ in norm]
+        outs = [[] for _ in range(t_len)]
+        for i in range(0, pl.ntiles, self.max_tiles):
+            chain = self.g.tonemap_clip_tiles([tl[i:i + self.max_tiles] for tl in tiles])
+            for t in range(t_len):
+                outs[t].append(chain[t])
+        res = []
+        for t in range(t_len):
+            fake_p = self.blend(torch.cat(outs[t]) if len(outs[t]) > 1 else outs[t][0], pl)
+            col = self.postprocess(fake_p, frames[t], norm[t][1], pl)
+            res.append(self.to_uint8(col) if uint8 else col)
+        return torch.stack(res)

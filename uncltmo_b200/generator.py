@@ -342,10 +342,11 @@ class UNetVideo(_GeneratorBase):
             prev = state
         return torch.cat(outs, 1), torch.cat(feats, 1)
 
-    def tonemap_clip_tiles(self, x):
-        """[N,T,1,256,256] -> [N,T,1,256,256] (no feature extraction; inference path of run_model_on_video)."""
+    def tonemap_clip_tiles(self, frames):
+        """frames: list over T of [N,1,256,256] tile batches (same tiles, consecutive frames) -> list of [N,1,256,256].
+        No feature extraction (inference path of run_model_on_video)."""
         outs, prev = [], None
-        for k in range(x.shape[1]):
-            out, _, _, prev = self._run_frame(x[:, k], prev=prev, want_features=True)
-            outs.append(out.unsqueeze(1))
-        return torch.cat(outs, 1)
+        for x in frames:
+            out, _, _, prev = self._run_frame(x, prev=prev, want_features=True)
+            outs.append(out)
+        return outs
