@@ -1,0 +1,46 @@
+"""Runs a few tcgen05 conv launches at the generator's 60-tile shapes (for `ncu --set full -k regex:conv3x3_tc`)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from uncltmo_b200 import _lib, packing  # noqa: E402
+
+CASES = {  # name: (C_in, C_out, H, pad, emit_skip, fuse_outc)
+    "inc1": (32, 32, 254, 0, 1, 0), "d0_1": (64, 64, 124, 0, 1, 0), "d1_1": (128, 128, 59, 0, 1, 0),
+    "u1_0": (512, 64, 57, 2, 0, 0), "u3_0": (128, 32, 252, 2, 0, 0), "u3_1": (32, 32, 254, 2, 0, 1),
+}
+
+
+def run(name, n=60, reps=1):
+    ci, co, h, pad, emit, fuse = CASES[name]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn((n, ci // 8, h, h, 8), device="cuda", generator=g).to(torch.bfloat16)
+    w9 = torch.randn((9, ci, co), device="cuda", generator=g) / (9 * ci) ** 0.5
+    b = torch.zeros(co, device="cuda")
+    ho = h + 2 * pad - 2
+    out = torch.empty((n, (4 if emit else 1) * co // 8, ho, ho, 8), device="cuda", dtype=torch.bfloat16)
+    wp = packing.conv3x3_tc(w9)
+    ow, ob = torch.randn(co, device="cuda"), torch.zeros(1, device="cuda")
+    img = torch.empty((n, ho, ho), device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(reps + 1):
+        if i == 1:
+            e0.record()
+        _lib.call("uncl_conv3x3_tc", x, x.stride(0), wp, b, None if fuse else out, out.stride(0), n, ci, h, h, co, pad, 1,
+                  emit, fuse, ow if fuse else None, ob if fuse else None, img if fuse else None, None)
+    e1.record()
+    torch.cuda.synchronize()
+    if reps:
+        ms = e0.elapsed_time(e1) / reps
+        fl = 2.0 * 9 * ci * co * ho * ho * n
+        print("%-5s %8.1f us  %7.1f TFLOP/s" % (name, ms * 1e3, fl / ms / 1e9), flush=True)
+
+
+if __name__ == "__main__":
+    names = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CASES)
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    for nm in names:
+        run(nm, reps=reps)

@@ -41,9 +41,10 @@ struct TcParams {
   int N, C_in, C_out, Ho, Wo, pad;
   int NT, NS;               // N tile (<=128) and number of N splits
   int MB;                   // M blocks (128 pixels each) per tile
-  int PW, PH;               // TMA box (halo tile) extent in pixels
-  int mode;                 // 0: row-aligned (tile = MB rows x 128 cols), 1: flattened (tile = MB*128 consecutive px)
-  int tiles_x, tiles_per_img, num_items;
+  int PW, PH;               // TMA box (halo tile) extent in pixels; PW is also the flattening pitch of a band
+  int BW, nbands;           // output columns per band (PW = BW + 2), bands per image row
+  int band_total;           // Ho * PW: flattened (pitch PW) output positions of one band
+  int tiles_per_band, tiles_per_img, num_items;
   int nchunk, ntaps, stages;
   int a_box_bytes, a_stage_bytes, b_stage_bytes, stage_bytes;
   int act, emit_skip, fuse_outc;
@@ -74,11 +75,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -141,46 +142,43 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // ---------------------------------------------------------------- tile geometry shared by the three roles
+// A tile is MB*128 CONSECUTIVE positions of one band, flattened with pitch PW (= BW + 2): position q -> output
+// (q / PW, band*BW + q % PW); the last two positions of every pitch row are the wrap-around garbage columns.
 struct Item {
   int n, ns;          // image, N split
-  int bx, by;         // TMA box origin (input pixel coordinates, may be negative)
+  int band;           // column band
+  int bx, by;         // TMA box origin (input pixel coordinates, may be negative: zero fill)
   int moff0;          // start pixel (inside the box) of M block 0
   int mb_act;         // active M blocks
-  int ty, tx, q0;     // row-aligned: tile row/col ; flattened: first flattened output index
+  int q0;             // first flattened position
 };
 
-__device__ __forceinline__ Item decode_item(const TcParams& p, int item) {
+struct Geo {  // hot scalars of TcParams, hoisted into registers
+  int NS, tiles_per_img, tiles_per_band, MB, PW, BW, pad, band_total;
+};
+
+__device__ __forceinline__ Item decode_item(const Geo& g, int item) {
   Item it;
-  const int tile = item / p.NS;
-  it.ns = item % p.NS;
-  it.n = tile / p.tiles_per_img;
-  const int t = tile % p.tiles_per_img;
-  if (p.mode == 0) {
-    it.ty = t / p.tiles_x;
-    it.tx = t % p.tiles_x;
-    it.bx = it.tx * 128 - p.pad;
-    it.by = it.ty * p.MB - p.pad;
-    it.moff0 = 0;
-    it.mb_act = min(p.MB, p.Ho - it.ty * p.MB);
-    it.q0 = 0;
-  } else {
-    const int pitch = p.Wo + 2;
-    it.q0 = t * 128 * p.MB;
-    const int y0 = it.q0 / pitch;
-    it.bx = -p.pad;
-    it.by = y0 - p.pad;
-    it.moff0 = it.q0 - y0 * pitch;
-    it.mb_act = min(p.MB, (p.Ho * pitch - it.q0 + 127) / 128);
-    it.ty = it.tx = 0;
-  }
+  const int tile = item / g.NS;
+  it.ns = item - tile * g.NS;
+  it.n = tile / g.tiles_per_img;
+  const int t = tile - it.n * g.tiles_per_img;
+  it.band = t / g.tiles_per_band;
+  const int tb = t - it.band * g.tiles_per_band;
+  it.q0 = tb * 128 * g.MB;
+  const int y0 = it.q0 / g.PW;
+  it.bx = it.band * g.BW - g.pad;
+  it.by = y0 - g.pad;
+  it.moff0 = it.q0 - y0 * g.PW;
+  it.mb_act = min(g.MB, (g.band_total - it.q0 + 127) / 128);
   return it;
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // carve: [stages x (A | B)] | barriers | tmem ptr | bias
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // keeps the shared address space
   uint8_t* stage_base = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes + 128);
   uint64_t* full = bars;
@@ -191,10 +189,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);  // [C_out] (+ [C_out] outc weights)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Geo geo = {p.NS, p.tiles_per_img, p.tiles_per_band, p.MB, p.PW, p.BW, p.pad, p.band_total};
+  const int num_items = p.num_items, nchunk = p.nchunk, stages = p.stages, stage_bytes = p.stage_bytes;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -216,16 +216,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const Item it = decode_item(p, item);
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)it.ns * p.nchunk * p.b_stage_bytes;
-        for (int ch = 0; ch < p.nchunk; ++ch) {
+      const uint32_t tx_bytes = (uint32_t)(p.a_box_bytes + p.b_stage_bytes), b_bytes = (uint32_t)p.b_stage_bytes;
+      const int a_stage_bytes = p.a_stage_bytes;
+      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const Item it = decode_item(geo, item);
+        const uint8_t* wsrc = wbase + (size_t)it.ns * nchunk * b_bytes;
+        for (int ch = 0; ch < nchunk; ++ch) {
           mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = stage_base + (size_t)stage * p.stage_bytes;
-          mbar_expect_tx(&full[stage], (uint32_t)(p.a_box_bytes + p.b_stage_bytes));
-          tma_load_5d(sa, &tmap, &full[stage], 0, it.bx, it.by, ch * 2, it.n);
-          bulk_load(sa + p.a_stage_bytes, wsrc + (size_t)ch * p.b_stage_bytes, (uint32_t)p.b_stage_bytes, &full[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          uint8_t* sa = stage_base + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full[stage], tx_bytes);
+          tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, ch * 2, it.n);
+          bulk_load(sa + a_stage_bytes, wsrc + (size_t)ch * b_bytes, b_bytes, &full[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -239,20 +242,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       const uint32_t desc_hi = (128u >> 4) | (1u << 14);
       const uint32_t a_lo_const = ((uint32_t)(p.PH * p.PW) & 0x3fffu) << 16;   // LBO_A = PH*PW*16 B
       const uint32_t b_lo_const = ((uint32_t)p.NT & 0x3fffu) << 16;            // LBO_B = NT*16 B
-      const uint32_t stage0_16 = smem_u32(stage_base) >> 4, stage_16 = (uint32_t)p.stage_bytes >> 4;
+      const uint32_t stage0_16 = smem_u32(stage_base) >> 4, stage_16 = (uint32_t)stage_bytes >> 4;
       const uint32_t a_bytes_16 = (uint32_t)p.a_stage_bytes >> 4, b_tap_16 = (uint32_t)(2 * p.NT);
-      const uint32_t mstep = (p.mode == 0) ? (uint32_t)p.PW : 128u;
+      const uint32_t mstep = 128u;
       const uint32_t pw = (uint32_t)p.PW, nt = (uint32_t)p.NT;
       const bool taps9 = p.ntaps == 9;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const Item it = decode_item(p, item);
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const Item it = decode_item(geo, item);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * kAccCols);
         const uint32_t mb = (uint32_t)it.mb_act;
-        for (int ch = 0; ch < p.nchunk; ++ch) {
+        for (int ch = 0; ch < nchunk; ++ch) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa16 = stage0_16 + (uint32_t)stage * stage_16;
@@ -290,7 +293,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           }
           if (elect_one()) tc_commit(&empty[stage]);
           __syncwarp();
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         if (elect_one()) tc_commit(&tfull[acc]);
         __syncwarp();
@@ -302,63 +305,68 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     // =============================== epilogue (4 warps = 128 TMEM lanes) ===============================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const long cb_stride = (long)p.Ho * p.Wo * 8;
-    const int Cb = p.C_out / 8;
+    const int Ho = p.Ho, Wo = p.Wo, NT = p.NT, C_out = p.C_out;
+    const long cb_stride = (long)Ho * Wo * 8;
+    const long skip2 = (long)(2 * (C_out / 8)) * cb_stride, skip3 = (long)(3 * (C_out / 8)) * cb_stride;
+    const float act_floor = (p.act == UNCL_ACT_RELU) ? 0.f : -INFINITY;   // ReLU or identity, branch-free
+    const bool emit_skip = p.emit_skip != 0, fuse_outc = p.fuse_outc != 0;
+    bf16* const out = p.out;
+    const long out_img_stride = p.out_img_stride;
+    float* const out_img = p.out_img;
+    float* const out_logit = p.out_logit;
+    const float outc_b = fuse_outc ? __ldg(p.outc_b) : 0.f;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const Item it = decode_item(p, item);
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const Item it = decode_item(geo, item);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      const int cbase0 = it.ns * NT;
+      bf16* const out_n = out + (long)it.n * out_img_stride + (long)(cbase0 / 8) * cb_stride;
       for (int b = 0; b < it.mb_act; ++b) {
-        int oy, ox;
-        if (p.mode == 0) {
-          oy = it.ty * p.MB + b;
-          ox = it.tx * 128 + row;
-        } else {
-          const int q = it.q0 + b * 128 + row;
-          oy = q / (p.Wo + 2);
-          ox = q % (p.Wo + 2);
-        }
-        const bool valid = (oy < p.Ho) && (ox < p.Wo);
-        const long pix = (long)oy * p.Wo + ox;
+        const int q = it.q0 + b * 128 + row;
+        const int oy = q / geo.PW, xl = q - oy * geo.PW;
+        const int ox = it.band * geo.BW + xl;
+        const bool valid = (oy < Ho) && (xl < geo.BW) && (ox < Wo);
+        const long pix = (long)oy * Wo + ox;
         float logit = 0.f;
-        for (int c0 = 0; c0 < p.NT; c0 += 32) {
+        for (int c0 = 0; c0 < NT; c0 += 32) {
           uint32_t r[32];
-          tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccCols + b * p.NT + c0), r);
+          tc_ld32(tmem_base + lane_base + (uint32_t)(acc * kAccCols + b * NT + c0), r);
           if (valid) {
-            const int cbase = it.ns * p.NT + c0;
+            const float* bias = s_bias + cbase0 + c0;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float v[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                v[j] = apply_act(__uint_as_float(r[g * 8 + j]) + s_bias[cbase + g * 8 + j], p.act);
-              if (p.out != nullptr) {
-                bf16* o = p.out + (long)it.n * p.out_img_stride + (long)(cbase / 8 + g) * cb_stride + pix * 8;
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[g * 8 + j]) + bias[g * 8 + j], act_floor);
+              if (out != nullptr) {
+                bf16* o = out_n + (long)(c0 / 8 + g) * cb_stride + pix * 8;
                 store8(o, v);
-                if (p.emit_skip) {
-                  float s[8];
+                if (emit_skip) {
+                  float s2[8];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) s[j] = v[j] * v[j];
-                  store8(o + (long)(2 * Cb) * cb_stride, s);
+                  for (int j = 0; j < 8; ++j) s2[j] = v[j] * v[j];
+                  store8(o + skip2, s2);
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) s[j] = sqrtf(v[j] + 1e-8f);
-                  store8(o + (long)(3 * Cb) * cb_stride, s);
+                  for (int j = 0; j < 8; ++j) s2[j] = sqrtf(v[j] + 1e-8f);
+                  store8(o + skip3, s2);
                 }
               }
-              if (p.fuse_outc) {
+              if (fuse_outc) {
+                const float* ow = s_bias + C_out + cbase0 + c0 + g * 8;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) logit = fmaf(v[j], s_bias[p.C_out + cbase + g * 8 + j], logit);
+                for (int j = 0; j < 8; ++j) logit = fmaf(v[j], ow[j], logit);
               }
             }
           }
         }
-        if (p.fuse_outc && valid) {
-          logit += __ldg(p.outc_b);
-          const long o = (long)it.n * p.Ho * p.Wo + pix;
-          if (p.out_logit) p.out_logit[o] = logit;
-          p.out_img[o] = 1.f / (1.f + expf(-logit));
+        if (fuse_outc && valid) {
+          logit += outc_b;
+          const long o = (long)it.n * Ho * Wo + pix;
+          if (out_logit) out_logit[o] = logit;
+          out_img[o] = 1.f / (1.f + __expf(-logit));
         }
       }
       tc_fence_before();
@@ -419,23 +427,18 @@ extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w
   p.act = act; p.emit_skip = emit_skip; p.fuse_outc = fuse_outc;
   p.ntaps = 9;
   p.nchunk = C_in / 16;
+  UNCL_REQUIRE(act == UNCL_ACT_RELU || act == UNCL_ACT_NONE, "conv3x3_tc: only ReLU / identity epilogues are built");
   const int mb_max = kAccCols / p.NT;
-  if (p.Wo >= 100) {
-    p.mode = 0;
-    p.MB = mb_max < p.Ho ? mb_max : p.Ho;
-    p.PW = 130; p.PH = p.MB + 2;
-    p.tiles_x = ceil_div(p.Wo, 128);
-    p.tiles_per_img = p.tiles_x * ceil_div(p.Ho, p.MB);
-  } else {
-    p.mode = 1;
-    const int pitch = p.Wo + 2, total = p.Ho * pitch;
-    p.MB = mb_max < ceil_div(total, 128) ? mb_max : ceil_div(total, 128);
-    p.PW = pitch;
-    p.PH = (pitch - 1 + 128 * p.MB - 1) / pitch + 1 + 2;
-    p.tiles_x = 1;
-    p.tiles_per_img = ceil_div(total, 128 * p.MB);
-  }
-  UNCL_REQUIRE(p.PW <= 256 && p.PH <= 256, "conv3x3_tc: halo tile too large (%d x %d)", p.PW, p.PH);
+  // column bands: the TMA box row is PW pixels = 2*PW 8-byte elements and a box dimension holds <= 256 elements
+  p.nbands = ceil_div(p.Wo, 126);
+  p.BW = ceil_div(p.Wo, p.nbands);
+  p.PW = p.BW + 2;
+  p.band_total = p.Ho * p.PW;
+  p.MB = mb_max < ceil_div(p.band_total, 128) ? mb_max : ceil_div(p.band_total, 128);
+  p.PH = (p.PW - 1 + 128 * p.MB - 1) / p.PW + 1 + 2;
+  p.tiles_per_band = ceil_div(p.band_total, 128 * p.MB);
+  p.tiles_per_img = p.nbands * p.tiles_per_band;
+  UNCL_REQUIRE(p.PW <= 128 && p.PH <= 256, "conv3x3_tc: halo tile too large (%d x %d)", p.PW, p.PH);
   p.num_items = N * p.tiles_per_img * p.NS;
   p.a_box_bytes = 2 * p.PH * p.PW * 16;
   p.a_stage_bytes = (p.a_box_bytes + 127) & ~127;
@@ -452,11 +455,13 @@ extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w
   EncodeTiledFn encode = get_encode();
   if (!encode) return uncl_set_error(UNCL_ECUDA, "conv3x3_tc: cuTensorMapEncodeTiled unavailable");
   CUtensorMap tmap;
-  const cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C_in / 8), (cuuint64_t)N};
-  const cuuint64_t gstr[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)in_img_stride * 2};
-  const cuuint32_t box[5] = {8, (cuuint32_t)p.PW, (cuuint32_t)p.PH, 2, 1};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), gdim, gstr, box, estr,
+  // 4-D map over 8-byte elements: (x*2 + half, y, channel block, image); one pixel's 8 bf16 channels = 2 elements,
+  // so a box row is PW*16 contiguous bytes in global memory (full 32-byte sectors) and lands pixel-major in smem.
+  const cuuint64_t gdim[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)(C_in / 8), (cuuint64_t)N};
+  const cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)in_img_stride * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)p.PW * 2, (cuuint32_t)p.PH, 2, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(in), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "conv3x3_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
