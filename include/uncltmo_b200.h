@@ -62,6 +62,15 @@ int uncl_convT2x2(const void* in, long in_img_stride, const void* prev, long pre
                   const float* bias, void* out, long out_img_stride, int N, int C, int H, int W, int H2, int W2,
                   int dtype, uncl_stream_t stream);
 
+/* The same ConvTranspose k2 s2 as a tcgen05 GEMM [pixels x C].[C x 4C] with a pixel-shuffle epilogue (bf16).
+ * w_packed: bf16 [NS][C/16][1][2][NT][8], column j = (dy*2+dx)*C + co, NT = min(4C, 128) (packing.convT2x2_tc). */
+int uncl_convT2x2_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                     long out_img_stride, int N, int C, int H, int W, int H2, int W2, uncl_stream_t stream);
+
+/* Video recurrence for kernels without a `prev` input: dst[:, :r] = src[:, :r] (r <= 8).  Unet.py:244, 270. */
+int uncl_splice_channels(void* dst, long dst_img_stride, const void* src, long src_img_stride, int r, int N, int HW,
+                         int dtype, uncl_stream_t stream);
+
 /* down.mpconv[0]: nn.MaxPool2d(2).  unet_parts.py:210-213.  prev/r as above (Unet.py:244). */
 int uncl_maxpool2(const void* in, long in_img_stride, const void* prev, long prev_img_stride, int r, void* out,
                   long out_img_stride, int N, int C, int H, int W, int dtype, uncl_stream_t stream);

@@ -290,6 +290,26 @@ __global__ void nchw_to_blocked_kernel(const float* __restrict__ in, T* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// video recurrence for kernels that have no `prev` input: overwrite the first r (<= 8) channels of `dst`
+// with those of `src` (both blocked; only channel block 0 is touched).  Unet.py:244, 270.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void splice_channels_kernel(T* __restrict__ dst, long dst_img_stride, const T* __restrict__ src,
+                                       long src_img_stride, int r, int HW, int N) {
+  const long total = (long)N * HW;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int p = i % HW, n = i / HW;
+    float d[8], s[8];
+    load8(dst + (long)n * dst_img_stride + (long)p * 8, d);
+    load8(src + (long)n * src_img_stride + (long)p * 8, s);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < r) d[c] = s[c];
+    store8(dst + (long)n * dst_img_stride + (long)p * 8, d);
+  }
+}
+
 // ================================================================================================
 // C ABI
 // ================================================================================================
@@ -357,4 +377,11 @@ extern "C" int uncl_nchw_to_blocked(const float* in, void* out, long out_img_str
   const long total = (long)N * ((C + 7) & ~7) * HW;
   UNCL_DISPATCH_DTYPE(dtype, T, (nchw_to_blocked_kernel<T><<<grid1d(total), 256, 0, stream>>>(in, (T*)out, out_img_stride, C, HW, N)));
   return uncl_check_launch("nchw_to_blocked");
+}
+
+extern "C" int uncl_splice_channels(void* dst, long dst_img_stride, const void* src, long src_img_stride, int r, int N,
+                                    int HW, int dtype, cudaStream_t stream) {
+  UNCL_REQUIRE(r >= 1 && r <= 8 && N > 0 && HW > 0, "splice_channels: r must be in 1..8");
+  UNCL_DISPATCH_DTYPE(dtype, T, (splice_channels_kernel<T><<<grid1d((long)N * HW), 256, 0, stream>>>((T*)dst, dst_img_stride, (const T*)src, src_img_stride, r, HW, N)));
+  return uncl_check_launch("splice_channels");
 }

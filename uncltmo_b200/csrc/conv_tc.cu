@@ -48,6 +48,7 @@ struct TcParams {
   int nchunk, ntaps, stages;
   int a_box_bytes, a_stage_bytes, b_stage_bytes, stage_bytes;
   int act, emit_skip, fuse_outc;
+  int sh_C, sh_H2, sh_W2;   // pixel-shuffle epilogue (ConvTranspose k2 s2): channels, target extent (replicate pad)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -174,6 +175,9 @@ __device__ __forceinline__ Item decode_item(const Geo& g, int item) {
   return it;
 }
 
+// EPI 0: conv epilogue (bias, ReLU, optional skip emission / fused 1x1 out conv + sigmoid)
+// EPI 1: pixel-shuffle epilogue of ConvTranspose k2 s2 (columns = (dy, dx, co)), replicate pad into (H2 x W2)
+template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -322,51 +326,84 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       const Item it = decode_item(geo, item);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int cbase0 = it.ns * NT;
-      bf16* const out_n = out + (long)it.n * out_img_stride + (long)(cbase0 / 8) * cb_stride;
-      for (int b = 0; b < it.mb_act; ++b) {
-        const int q = it.q0 + b * 128 + row;
-        const int oy = q / geo.PW, xl = q - oy * geo.PW;
-        const int ox = it.band * geo.BW + xl;
-        const bool valid = (oy < Ho) && (xl < geo.BW) && (ox < Wo);
-        const long pix = (long)oy * Wo + ox;
-        float logit = 0.f;
-        for (int c0 = 0; c0 < NT; c0 += 32) {
-          uint32_t r[32];
-          tc_ld32(tmem_base + lane_base + (uint32_t)(acc * kAccCols + b * NT + c0), r);
-          if (valid) {
-            const float* bias = s_bias + cbase0 + c0;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[g * 8 + j]) + bias[g * 8 + j], act_floor);
-              if (out != nullptr) {
-                bf16* o = out_n + (long)(c0 / 8 + g) * cb_stride + pix * 8;
-                store8(o, v);
-                if (emit_skip) {
-                  float s2[8];
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) s2[j] = v[j] * v[j];
-                  store8(o + skip2, s2);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) s2[j] = sqrtf(v[j] + 1e-8f);
-                  store8(o + skip3, s2);
+      if constexpr (EPI == 0) {
+        const int cbase0 = it.ns * NT;
+        bf16* const out_n = out + (long)it.n * out_img_stride + (long)(cbase0 / 8) * cb_stride;
+        for (int b = 0; b < it.mb_act; ++b) {
+          const int q = it.q0 + b * 128 + row;
+          const int oy = q / geo.PW, xl = q - oy * geo.PW;
+          const int ox = it.band * geo.BW + xl;
+          const bool valid = (oy < Ho) && (xl < geo.BW) && (ox < Wo);
+          const long pix = (long)oy * Wo + ox;
+          float logit = 0.f;
+          for (int c0 = 0; c0 < NT; c0 += 32) {
+            uint32_t r[32];
+            tc_ld32(tmem_base + lane_base + (uint32_t)(acc * kAccCols + b * NT + c0), r);
+            if (valid) {
+              const float* bias = s_bias + cbase0 + c0;
+  #pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float v[8];
+  #pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[g * 8 + j]) + bias[g * 8 + j], act_floor);
+                if (out != nullptr) {
+                  bf16* o = out_n + (long)(c0 / 8 + g) * cb_stride + pix * 8;
+                  store8(o, v);
+                  if (emit_skip) {
+                    float s2[8];
+  #pragma unroll
+                    for (int j = 0; j < 8; ++j) s2[j] = v[j] * v[j];
+                    store8(o + skip2, s2);
+  #pragma unroll
+                    for (int j = 0; j < 8; ++j) s2[j] = sqrtf(v[j] + 1e-8f);
+                    store8(o + skip3, s2);
+                  }
                 }
-              }
-              if (fuse_outc) {
-                const float* ow = s_bias + C_out + cbase0 + c0 + g * 8;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) logit = fmaf(v[j], ow[j], logit);
+                if (fuse_outc) {
+                  const float* ow = s_bias + C_out + cbase0 + c0 + g * 8;
+  #pragma unroll
+                  for (int j = 0; j < 8; ++j) logit = fmaf(v[j], ow[j], logit);
+                }
               }
             }
           }
+          if (fuse_outc && valid) {
+            logit += outc_b;
+            const long o = (long)it.n * Ho * Wo + pix;
+            if (out_logit) out_logit[o] = logit;
+            out_img[o] = 1.f / (1.f + __expf(-logit));
+          }
         }
-        if (fuse_outc && valid) {
-          logit += outc_b;
-          const long o = (long)it.n * Ho * Wo + pix;
-          if (out_logit) out_logit[o] = logit;
-          out_img[o] = 1.f / (1.f + __expf(-logit));
+      } else {
+        // ConvTranspose k2 s2: column j = pos * C + co, pos = dy * 2 + dx; out pixel (2y+dy, 2x+dx) (+ replicate pad)
+        const int C = p.sh_C, H2 = p.sh_H2, W2 = p.sh_W2, Hi = Ho, Wi = Wo;
+        const int padT = (H2 - 2 * Hi) / 2, padL = (W2 - 2 * Wi) / 2;
+        const long cb2 = (long)H2 * W2 * 8;
+        bf16* const out_img_n = out + (long)it.n * out_img_stride;
+        for (int b = 0; b < it.mb_act; ++b) {
+          const int q = it.q0 + b * 128 + row;
+          const int y = q / geo.PW, x = q - y * geo.PW;
+          const bool valid = y < Hi;
+          for (int c0 = 0; c0 < NT; c0 += 32) {
+            uint32_t r[32];
+            tc_ld32(tmem_base + lane_base + (uint32_t)(acc * kAccCols + b * NT + c0), r);
+            if (valid) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int j0 = it.ns * NT + c0 + g * 8;
+                const int pos = j0 / C, co0 = j0 - pos * C;
+                const int Y = 2 * y + (pos >> 1), X = 2 * x + (pos & 1);
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) + s_bias[co0 + j];
+                const int y_lo = (Y == 0) ? 0 : Y + padT, y_hi = (Y == 2 * Hi - 1) ? H2 - 1 : Y + padT;
+                const int x_lo = (X == 0) ? 0 : X + padL, x_hi = (X == 2 * Wi - 1) ? W2 - 1 : X + padL;
+                bf16* o = out_img_n + (long)(co0 / 8) * cb2;
+                for (int yy = y_lo; yy <= y_hi; ++yy)
+                  for (int xx = x_lo; xx <= x_hi; ++xx) store8(o + ((long)yy * W2 + xx) * 8, v);
+              }
+            }
+          }
         }
       }
       tc_fence_before();
@@ -403,6 +440,65 @@ EncodeTiledFn get_encode() {
 
 }  // namespace
 
+namespace {
+
+// fills the tile geometry for an (ntaps = 9: 3x3 with halo | ntaps = 1: pointwise GEMM) problem and launches
+int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, int H, int W, int epi, int bias_floats,
+              const char* what, cudaStream_t stream) {
+  UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "%s: input must be 16-byte aligned", what);
+  const int halo = p.ntaps == 9 ? 2 : 0;
+  p.nchunk = C_in / 16;
+  const int mb_max = kAccCols / p.NT;
+  // column bands: the TMA box row is PW pixels = 2*PW 8-byte elements and a box dimension holds <= 256 elements
+  p.nbands = ceil_div(p.Wo, 128 - halo);
+  p.BW = ceil_div(p.Wo, p.nbands);
+  p.PW = p.BW + halo;
+  p.band_total = p.Ho * p.PW;
+  p.MB = mb_max < ceil_div(p.band_total, 128) ? mb_max : ceil_div(p.band_total, 128);
+  p.PH = (p.PW - 1 + 128 * p.MB - 1) / p.PW + 1 + halo;
+  p.tiles_per_band = ceil_div(p.band_total, 128 * p.MB);
+  p.tiles_per_img = p.nbands * p.tiles_per_band;
+  UNCL_REQUIRE(p.PW <= 128 && p.PH <= 256, "%s: halo tile too large (%d x %d)", what, p.PW, p.PH);
+  p.num_items = N * p.tiles_per_img * p.NS;
+  p.a_box_bytes = 2 * p.PH * p.PW * 16;
+  p.a_stage_bytes = (p.a_box_bytes + 127) & ~127;
+  p.b_stage_bytes = p.ntaps * 2 * p.NT * 16;
+  p.stage_bytes = p.a_stage_bytes + p.b_stage_bytes;  // both multiples of 128
+  const int tail = 128 + (2 * kMaxStages + 4) * 8 + 16 + bias_floats * 4 + 256;
+  const int budget = 227 * 1024 - tail;
+  p.stages = budget / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  UNCL_REQUIRE(p.stages >= 2, "%s: tile does not fit shared memory (%d B per stage)", what, p.stage_bytes);
+  int smem_bytes = p.stages * p.stage_bytes + tail;
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // force one CTA per SM (each CTA owns all 512 TMEM columns)
+
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled unavailable", what);
+  CUtensorMap tmap;
+  // 4-D map over 8-byte elements: (x*2 + half, y, channel block, image); one pixel's 8 bf16 channels = 2 elements,
+  // so a box row is PW*16 contiguous bytes in global memory (full 32-byte sectors) and lands pixel-major in smem.
+  const cuuint64_t gdim[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)(C_in / 8), (cuuint64_t)N};
+  const cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)in_img_stride * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)p.PW * 2, (cuuint32_t)p.PH, 2, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(in), gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
+
+  auto kern = epi == 0 ? conv3x3_tc_kernel<0> : conv3x3_tc_kernel<1>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.num_items < sms ? p.num_items : sms;
+  kern<<<grid, kThreads, smem_bytes, stream>>>(tmap, p);
+  return uncl_check_launch(what);
+}
+
+}  // namespace
+
 extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
                                long out_img_stride, int N, int C_in, int H, int W, int C_out, int pad, int act,
                                int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b, float* out_img,
@@ -414,7 +510,7 @@ extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w
   UNCL_REQUIRE(C_out % p.NT == 0 && C_out <= 256, "conv3x3_tc: unsupported C_out=%d", C_out);
   UNCL_REQUIRE(!fuse_outc || (C_out == p.NT && outc_w && outc_b && out_img), "conv3x3_tc: fuse_outc needs C_out<=128 and outc params");
   UNCL_REQUIRE(out != nullptr || fuse_outc, "conv3x3_tc: no output requested");
-  UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "conv3x3_tc: input must be 16-byte aligned");
+  UNCL_REQUIRE(act == UNCL_ACT_RELU || act == UNCL_ACT_NONE, "conv3x3_tc: only ReLU / identity epilogues are built");
   p.NS = C_out / p.NT;
   p.w = reinterpret_cast<const bf16*>(w_packed);
   p.bias = bias;
@@ -426,52 +522,26 @@ extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w
   UNCL_REQUIRE(p.Ho > 0 && p.Wo > 0, "conv3x3_tc: empty output");
   p.act = act; p.emit_skip = emit_skip; p.fuse_outc = fuse_outc;
   p.ntaps = 9;
-  p.nchunk = C_in / 16;
-  UNCL_REQUIRE(act == UNCL_ACT_RELU || act == UNCL_ACT_NONE, "conv3x3_tc: only ReLU / identity epilogues are built");
-  const int mb_max = kAccCols / p.NT;
-  // column bands: the TMA box row is PW pixels = 2*PW 8-byte elements and a box dimension holds <= 256 elements
-  p.nbands = ceil_div(p.Wo, 126);
-  p.BW = ceil_div(p.Wo, p.nbands);
-  p.PW = p.BW + 2;
-  p.band_total = p.Ho * p.PW;
-  p.MB = mb_max < ceil_div(p.band_total, 128) ? mb_max : ceil_div(p.band_total, 128);
-  p.PH = (p.PW - 1 + 128 * p.MB - 1) / p.PW + 1 + 2;
-  p.tiles_per_band = ceil_div(p.band_total, 128 * p.MB);
-  p.tiles_per_img = p.nbands * p.tiles_per_band;
-  UNCL_REQUIRE(p.PW <= 128 && p.PH <= 256, "conv3x3_tc: halo tile too large (%d x %d)", p.PW, p.PH);
-  p.num_items = N * p.tiles_per_img * p.NS;
-  p.a_box_bytes = 2 * p.PH * p.PW * 16;
-  p.a_stage_bytes = (p.a_box_bytes + 127) & ~127;
-  p.b_stage_bytes = p.ntaps * 2 * p.NT * 16;
-  p.stage_bytes = p.a_stage_bytes + p.b_stage_bytes;  // both multiples of 128
-  const int tail = 128 + (2 * kMaxStages + 4) * 8 + 16 + 2 * C_out * 4 + 256;
-  const int budget = 227 * 1024 - tail;
-  p.stages = budget / p.stage_bytes;
-  if (p.stages > kMaxStages) p.stages = kMaxStages;
-  UNCL_REQUIRE(p.stages >= 2, "conv3x3_tc: tile does not fit shared memory (%d B per stage)", p.stage_bytes);
-  int smem_bytes = p.stages * p.stage_bytes + tail;
-  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // force one CTA per SM (each CTA owns all 512 TMEM columns)
+  return launch_tc(p, in, in_img_stride, N, C_in, H, W, 0, 2 * C_out, "conv3x3_tc", stream);
+}
 
-  EncodeTiledFn encode = get_encode();
-  if (!encode) return uncl_set_error(UNCL_ECUDA, "conv3x3_tc: cuTensorMapEncodeTiled unavailable");
-  CUtensorMap tmap;
-  // 4-D map over 8-byte elements: (x*2 + half, y, channel block, image); one pixel's 8 bf16 channels = 2 elements,
-  // so a box row is PW*16 contiguous bytes in global memory (full 32-byte sectors) and lands pixel-major in smem.
-  const cuuint64_t gdim[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)(C_in / 8), (cuuint64_t)N};
-  const cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)in_img_stride * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)p.PW * 2, (cuuint32_t)p.PH, 2, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(in), gdim, gstr, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "conv3x3_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
-
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "conv3x3_tc: smem attr: %s", cudaGetErrorString(e));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = p.num_items < sms ? p.num_items : sms;
-  conv3x3_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap, p);
-  return uncl_check_launch("conv3x3_tc");
+// ConvTranspose2d(C, C, 2, stride=2) as a GEMM [pixels x C] . [C x 4C] with a pixel-shuffle epilogue.
+// w_packed: bf16 [NS][C/16][1][2][NT][8], column j = (dy*2+dx)*C + co, NT = min(4C, 128).
+extern "C" int uncl_convT2x2_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                                long out_img_stride, int N, int C, int H, int W, int H2, int W2, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && C % 32 == 0 && H2 >= 2 * H && W2 >= 2 * W && W <= 128, "convT2x2_tc: unsupported C=%d W=%d", C, W);
+  TcParams p{};
+  const int n_total = 4 * C;
+  p.NT = n_total < 128 ? n_total : 128;
+  p.NS = n_total / p.NT;
+  p.w = reinterpret_cast<const bf16*>(w_packed);
+  p.bias = bias;
+  p.out = reinterpret_cast<bf16*>(out);
+  p.out_img_stride = out_img_stride;
+  p.N = N; p.C_in = C; p.C_out = C; p.pad = 0;
+  p.Ho = H; p.Wo = W;
+  p.act = UNCL_ACT_NONE;
+  p.ntaps = 1;
+  p.sh_C = C; p.sh_H2 = H2; p.sh_W2 = W2;
+  return launch_tc(p, in, in_img_stride, N, C, H, W, 1, 2 * C, "convT2x2_tc", stream);
 }

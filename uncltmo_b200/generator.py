@@ -144,7 +144,8 @@ class _GeneratorBase(nn.Module):
                 P[name] = (packing.pointwise(m.weight.detach(), groups), m.bias.detach().float().contiguous())
             for i in range(4):
                 u = self.up_path[i]
-                P["u%d_up" % i] = (packing.convT2x2(u.up.weight.detach()), u.up.bias.detach().float().contiguous())
+                P["u%d_up" % i] = (packing.convT2x2_tc(u.up.weight.detach()) if tc else packing.convT2x2(u.up.weight.detach()),
+                                   u.up.bias.detach().float().contiguous())
                 conv("u%d_0" % i, u.conv.conv, True)
                 conv("u%d_1" % i, u.conv.conv1, True)
             P["outc"] = (self.outc.conv.weight.detach().reshape(-1).float().contiguous(),
@@ -246,8 +247,17 @@ class _GeneratorBase(nn.Module):
             # ConvTranspose k2 s2 into the second channel group of the concat buffer
             dst = cb[:, sk_c // 8:]
             pv = prev[5 + i] if prev is not None else None
-            call("uncl_convT2x2", up, st(up), pv, st(pv) if pv is not None else 0, up_c // 32 if pv is not None else 0,
-                 P["u%d_up" % i][0], P["u%d_up" % i][1], dst, st(cb), n, up_c, up_s, up_s, sk_s, sk_s, dt)
+            if self.precision == "bf16":
+                if pv is not None:
+                    # the up-conv GEMM has no `prev` input: keep this frame's hand-over slice, then splice in place
+                    state[5 + i] = up[:, :1].clone()
+                    call("uncl_splice_channels", up, st(up), pv, st(pv), up_c // 32, n, up_s * up_s, dt)
+                call("uncl_convT2x2_tc", up, st(up), P["u%d_up" % i][0], P["u%d_up" % i][1], dst, st(cb), n, up_c,
+                     up_s, up_s, sk_s, sk_s)
+            else:
+                call("uncl_convT2x2", up, st(up), pv, st(pv) if pv is not None else 0,
+                     up_c // 32 if pv is not None else 0, P["u%d_up" % i][0], P["u%d_up" % i][1], dst, st(cb), n, up_c,
+                     up_s, up_s, sk_s, sk_s, dt)
             co = f if i >= 2 else up_c // 2
             mid = buf(co, sk_s + 2, sk_s + 2)
             self._conv3(P, "u%d_0" % i, cb, st(cb), mid, st(mid), n, 4 * sk_c, sk_s, sk_s, co, 2)

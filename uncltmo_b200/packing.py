@@ -32,6 +32,17 @@ def convT2x2(w):
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], 4, w.shape[1]).contiguous().float()
 
 
+def convT2x2_tc(w):
+    """ConvTranspose2d k2 s2 weight [C_in][C_out][2][2] -> bf16 [NS][C_in/16][2][NT][8] (GEMM B operand, K-major):
+    column j = (dy*2+dx)*C_out + co, NT = min(4*C_out, 128)."""
+    ci, co = w.shape[0], w.shape[1]
+    n_total = 4 * co
+    nt = min(n_total, 128)
+    b = w.permute(2, 3, 1, 0).reshape(n_total, ci)             # [j][ci]
+    b = b.reshape(n_total // nt, nt, ci // 16, 2, 8).permute(0, 2, 3, 1, 4).contiguous()
+    return b.to(torch.bfloat16)
+
+
 def pointwise(w, groups=1):
     """1x1 Conv2d weight [C_out][C_in/g][1][1] -> [g][C_in/g][C_out/g] fp32."""
     co, cig = w.shape[0], w.shape[1]
