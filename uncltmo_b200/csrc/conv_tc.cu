@@ -25,7 +25,8 @@
 
 namespace {
 
-constexpr int kThreads = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int kThreads = 320;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
+constexpr int kEpiWarps = 8;           // two warps per TMEM lane quarter, M blocks interleaved between them
 constexpr int kAccCols = 256;          // TMEM columns per accumulator stage (2 stages = 512 = all of TMEM)
 constexpr int kMaxStages = 6;
 
@@ -199,7 +200,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -306,8 +307,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     }
     __syncwarp();
   } else {
-    // =============================== epilogue (4 warps = 128 TMEM lanes) ===============================
+    // =============================== epilogue (8 warps: 4 TMEM lane quarters x 2 M-block parities) ========
     const int quarter = warp & 3;
+    const int bpar = (warp - 2) >> 2;   // this warp takes M blocks b with (b & 1) == bpar
     const int row = quarter * 32 + lane;
     const int Ho = p.Ho, Wo = p.Wo, NT = p.NT, C_out = p.C_out;
     const long cb_stride = (long)Ho * Wo * 8;
@@ -329,7 +331,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       if constexpr (EPI == 0) {
         const int cbase0 = it.ns * NT;
         bf16* const out_n = out + (long)it.n * out_img_stride + (long)(cbase0 / 8) * cb_stride;
-        for (int b = 0; b < it.mb_act; ++b) {
+        for (int b = bpar; b < it.mb_act; b += 2) {
           const int q = it.q0 + b * 128 + row;
           const int oy = q / geo.PW, xl = q - oy * geo.PW;
           const int ox = it.band * geo.BW + xl;
@@ -380,7 +382,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const int padT = (H2 - 2 * Hi) / 2, padL = (W2 - 2 * Wi) / 2;
         const long cb2 = (long)H2 * W2 * 8;
         bf16* const out_img_n = out + (long)it.n * out_img_stride;
-        for (int b = 0; b < it.mb_act; ++b) {
+        for (int b = bpar; b < it.mb_act; b += 2) {
           const int q = it.q0 + b * 128 + row;
           const int y = q / geo.PW, x = q - y * geo.PW;
           const bool valid = y < Hi;

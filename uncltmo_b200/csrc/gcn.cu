@@ -25,79 +25,100 @@ __global__ void gcn_add_pos_kernel(const T* __restrict__ in, long in_img_stride,
 
 // Pointwise (1x1) conv on blocked fp32 tensors with groups, bias, activation, optional residual and per-sample
 // scale of the branch (DropPath: out = scale[n] * f(x) + res).  Weights packed [groups][Cin_g][Cout_g].
-// CTA: 64 pixels x 64 output channels; thread: 4 pixels x 4 channels.
-template <typename TOut>
+// CTA: 128 pixels x PW_CO output channels, K step 16; thread: 8 pixels x (PW_CO/16) channels.
+constexpr int PW_PX = 128, PW_K = 16;
+
+template <typename TOut, int PW_CO>
 __global__ void __launch_bounds__(256) pw_conv_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                      const float* __restrict__ bias, const float* __restrict__ res,
                                                      const float* __restrict__ scale, TOut* __restrict__ out,
                                                      long out_img_stride, int C_in, int C_out, int groups, int HW,
                                                      int N, int act) {
-  __shared__ __align__(16) float s_a[32][64];  // [ci][pixel]
-  __shared__ __align__(16) float s_w[32][64];  // [ci][co]
+  constexpr int TC = PW_CO / 16;  // channels per thread (8 or 4)
+  __shared__ __align__(16) float s_a[PW_K][PW_PX];  // [ci][pixel]
+  __shared__ __align__(16) float s_w[PW_K][PW_CO];  // [ci][co]
   const int cin_g = C_in / groups, cout_g = C_out / groups;
-  const int co0 = blockIdx.y * 64;
+  const int co0 = blockIdx.y * PW_CO;
   const int g = co0 / cout_g;
   const int P = N * HW;
-  const int p0 = blockIdx.x * 64;
-  const int tp = (threadIdx.x & 15) * 4, tc = (threadIdx.x >> 4) * 4;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < cin_g; k0 += 32) {
+  const int p0 = blockIdx.x * PW_PX;
+  const int tp = (threadIdx.x & 15) * 8, tc = (threadIdx.x >> 4) * TC;
+  float acc[8][TC];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TC; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < cin_g; k0 += PW_K) {
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
-      const int px = i & 63, ci = i >> 6;
-      const int p = p0 + px, c = g * cin_g + k0 + ci;
-      float v = 0.f;
+    // A tile: 16 ci x 128 px = two 8-channel blocks; each thread moves one pixel of one block (32 B)
+    {
+      const int px = threadIdx.x & 127, blk = threadIdx.x >> 7;
+      const int p = p0 + px, c = g * cin_g + k0 + blk * 8;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (p < P) {
-        const int n = p / HW, q = p % HW;
-        v = in[((long)n * (C_in / 8) + (c >> 3)) * HW * 8 + (long)q * 8 + (c & 7)];
+        const int n = p / HW, q = p - n * HW;
+        load8(in + ((long)n * (C_in / 8) + (c >> 3)) * HW * 8 + (long)q * 8, v);
       }
-      s_a[ci][px] = v;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_a[blk * 8 + j][px] = v[j];
     }
-    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
-      const int co = i & 63, ci = i >> 6;
+    for (int i = threadIdx.x; i < PW_K * PW_CO; i += 256) {
+      const int co = i % PW_CO, ci = i / PW_CO;
       s_w[ci][co] = w[((long)g * cin_g + k0 + ci) * cout_g + (co0 - g * cout_g) + co];
     }
     __syncthreads();
-#pragma unroll 8
-    for (int ci = 0; ci < 32; ++ci) {
-      const float4 a = *reinterpret_cast<const float4*>(&s_a[ci][tp]);
-      const float4 b = *reinterpret_cast<const float4*>(&s_w[ci][tc]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+    for (int ci = 0; ci < PW_K; ++ci) {
+      float av[8], bv[TC];
+      *reinterpret_cast<float4*>(av) = *reinterpret_cast<const float4*>(&s_a[ci][tp]);
+      *reinterpret_cast<float4*>(av + 4) = *reinterpret_cast<const float4*>(&s_a[ci][tp + 4]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int j = 0; j < TC; j += 4) *reinterpret_cast<float4*>(bv + j) = *reinterpret_cast<const float4*>(&s_w[ci][tc + j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TC; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     const int p = p0 + tp + i;
     if (p >= P) continue;
-    const int n = p / HW, q = p % HW;
+    const int n = p / HW, q = p - n * HW;
     const float sc = scale ? scale[n] : 1.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = co0 + tc + j;
-      float v = apply_act(acc[i][j] + bias[c], act) * sc;
+    for (int j0 = 0; j0 < TC; j0 += 4) {  // TC is 4 or 8 and tc is a multiple of 4: one half channel block at a time
+      const int c = co0 + tc + j0;
       const long o = ((long)(c >> 3) * HW + q) * 8 + (c & 7);
-      if (res) v += res[(long)n * C_out * HW + o];
-      from_f(out[(long)n * out_img_stride + o], v);
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = apply_act(acc[i][j0 + j] + bias[c + j], act) * sc;
+        if (res) v[j] += res[(long)n * C_out * HW + o + j];
+        from_f(out[(long)n * out_img_stride + o + j], v[j]);
+      }
     }
   }
 }
 
-// KNN graph + max-relative aggregation, one CTA per image (C = 256).
+// KNN graph + max-relative aggregation (C = 256).  KNN_SPLIT CTAs per image, each owning a contiguous range of nodes.
 //   yn = y / max(|y|_2, 1e-12) over channels; dist[i][j] = (|yn_i|^2 - 2 yn_i.yn_j) + |yn_j|^2 + relpos[i][j];
 //   idx[i] = 9 smallest; z = interleave(y, max_k(y[idx_k] - y_i)) -> [N][2C/8][144][8]
+// Distances: a warp takes two rows i at a time; each lane keeps 5 columns j (lane + 32 t) x 2 rows in registers and
+// streams the channel axis with 128-bit shared loads (row stride C+4 floats keeps them conflict-free).
+constexpr int KNN_SPLIT = 2;
+
 template <int C>
 __global__ void __launch_bounds__(512) gcn_knn_agg_kernel(const float* __restrict__ y, const float* __restrict__ relpos,
                                                          float* __restrict__ z, int* __restrict__ idx_out) {
-  extern __shared__ float smem[];
-  constexpr int LD = C + 1;
-  float* s_yn = smem;                 // [144][C+1]
+  extern __shared__ __align__(16) float smem[];
+  constexpr int LD = C + 4;
+  constexpr int ROWS = GN / KNN_SPLIT;
+  float* s_yn = smem;                 // [144][C+4]
   float* s_sq = smem + GN * LD;       // [144]
-  int* s_idx = reinterpret_cast<int*>(s_sq + GN);  // [144][9]
-  const int n = blockIdx.x;
+  int* s_idx = reinterpret_cast<int*>(s_sq + GN);  // [ROWS][9]
+  const int n = blockIdx.x / KNN_SPLIT, part = blockIdx.x % KNN_SPLIT;
+  const int i_begin = part * ROWS;
   const float* yn_g = y + (long)n * C * GN;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
@@ -121,54 +142,76 @@ __global__ void __launch_bounds__(512) gcn_knn_agg_kernel(const float* __restric
     if (lane == 0) s_sq[node] = s2;
   }
   __syncthreads();
-  for (int i = wid; i < GN; i += nw) {
-    float d[5];
-    const float* yi = s_yn + i * LD;
+  for (int ip = wid; ip < ROWS / 2; ip += nw) {
+    const int i0 = i_begin + 2 * ip;
+    float dot[2][5];
 #pragma unroll
-    for (int t = 0; t < 5; ++t) {
-      const int j = lane + 32 * t;
-      float dot = 0.f;
-      if (j < GN) {
-        const float* yj = s_yn + j * LD;
-#pragma unroll 8
-        for (int c = 0; c < C; ++c) dot = fmaf(yi[c], yj[c], dot);
-        d[t] = ((s_sq[i] + (-2.f * dot)) + s_sq[j]) + relpos[i * GN + j];
-      } else {
-        d[t] = INFINITY;
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int t = 0; t < 5; ++t) dot[r][t] = 0.f;
+    const float* yi0 = s_yn + i0 * LD;
+    const float* yi1 = yi0 + LD;
+    const float* yj[5];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) yj[t] = s_yn + min(lane + 32 * t, GN - 1) * LD;
+#pragma unroll 2
+    for (int c = 0; c < C; c += 4) {
+      const float4 a0 = *reinterpret_cast<const float4*>(yi0 + c);
+      const float4 a1 = *reinterpret_cast<const float4*>(yi1 + c);
+#pragma unroll
+      for (int t = 0; t < 5; ++t) {
+        const float4 b = *reinterpret_cast<const float4*>(yj[t] + c);
+        dot[0][t] = fmaf(a0.x, b.x, dot[0][t]); dot[0][t] = fmaf(a0.y, b.y, dot[0][t]);
+        dot[0][t] = fmaf(a0.z, b.z, dot[0][t]); dot[0][t] = fmaf(a0.w, b.w, dot[0][t]);
+        dot[1][t] = fmaf(a1.x, b.x, dot[1][t]); dot[1][t] = fmaf(a1.y, b.y, dot[1][t]);
+        dot[1][t] = fmaf(a1.z, b.z, dot[1][t]); dot[1][t] = fmaf(a1.w, b.w, dot[1][t]);
       }
     }
-    for (int k = 0; k < GK; ++k) {
-      float best = d[0];
-      int bj = lane;
 #pragma unroll
-      for (int t = 1; t < 5; ++t)
-        if (d[t] < best) { best = d[t]; bj = lane + 32 * t; }
+    for (int r = 0; r < 2; ++r) {
+      const int i = i0 + r;
+      float d[5];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-        if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+      for (int t = 0; t < 5; ++t) {
+        const int j = lane + 32 * t;
+        d[t] = j < GN ? ((s_sq[i] + (-2.f * dot[r][t])) + s_sq[j]) + relpos[i * GN + j] : INFINITY;
       }
-      if ((bj & 31) == lane) d[bj >> 5] = INFINITY;
-      if (lane == 0) s_idx[i * GK + k] = bj;
+      for (int k = 0; k < GK; ++k) {
+        float best = d[0];
+        int bj = lane;
+#pragma unroll
+        for (int t = 1; t < 5; ++t)
+          if (d[t] < best) { best = d[t]; bj = lane + 32 * t; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+          if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+        }
+#pragma unroll
+        for (int t = 0; t < 5; ++t)
+          if (bj == lane + 32 * t) d[t] = INFINITY;
+        if (lane == 0) s_idx[(i - i_begin) * GK + k] = bj;
+      }
     }
   }
   __syncthreads();
   if (idx_out)
-    for (int i = threadIdx.x; i < GN * GK; i += blockDim.x) idx_out[(long)n * GN * GK + i] = s_idx[i];
+    for (int i = threadIdx.x; i < ROWS * GK; i += blockDim.x) idx_out[((long)n * GN + i_begin) * GK + i] = s_idx[i];
   // aggregation on the raw (un-normalised) features, straight from global / L2
   float* zn = z + (long)n * 2 * C * GN;
-  for (int i = wid; i < GN; i += nw) {
+  for (int il = wid; il < ROWS; il += nw) {
+    const int i = i_begin + il;
     for (int cb = lane; cb < C / 8; cb += 32) {
       float yi[8], m[8];
       load8(yn_g + ((long)cb * GN + i) * 8, yi);
 #pragma unroll
       for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
       for (int k = 0; k < GK; ++k) {
-        float yj[8];
-        load8(yn_g + ((long)cb * GN + s_idx[i * GK + k]) * 8, yj);
+        float yj8[8];
+        load8(yn_g + ((long)cb * GN + s_idx[il * GK + k]) * 8, yj8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], yj[j] - yi[j]);
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], yj8[j] - yi[j]);
       }
       const float lo[8] = {yi[0], m[0], yi[1], m[1], yi[2], m[2], yi[3], m[3]};
       const float hi[8] = {yi[4], m[4], yi[5], m[5], yi[6], m[6], yi[7], m[7]};
@@ -195,20 +238,28 @@ extern "C" int uncl_gcn_add_pos(const void* in, long in_img_stride, const float*
 extern "C" int uncl_pw_conv(const float* in, const float* w, const float* bias, const float* res, const float* scale,
                             void* out, long out_img_stride, int N, int C_in, int C_out, int groups, int HW, int act,
                             int out_dtype, cudaStream_t stream) {
-  UNCL_REQUIRE(groups > 0 && C_in % groups == 0 && C_out % groups == 0 && (C_in / groups) % 32 == 0 &&
+  UNCL_REQUIRE(groups > 0 && C_in % groups == 0 && C_out % groups == 0 && (C_in / groups) % 16 == 0 &&
                    (C_out / groups) % 64 == 0 && N > 0,
                "pw_conv: unsupported C_in=%d C_out=%d groups=%d", C_in, C_out, groups);
-  dim3 grid(ceil_div(N * HW, 64), C_out / 64);
-  UNCL_DISPATCH_DTYPE(out_dtype, T, (pw_conv_kernel<T><<<grid, 256, 0, stream>>>(in, w, bias, res, scale, (T*)out, out_img_stride, C_in, C_out, groups, HW, N, act)));
+  // 128-wide channel tiles when that still fills the machine, else 64-wide (twice the CTAs)
+  const int px_tiles = ceil_div(N * HW, PW_PX);
+  const bool wide = (C_out / groups) % 128 == 0 && px_tiles * (C_out / 128) >= 120;
+  if (wide) {
+    dim3 grid(px_tiles, C_out / 128);
+    UNCL_DISPATCH_DTYPE(out_dtype, T, (pw_conv_kernel<T, 128><<<grid, 256, 0, stream>>>(in, w, bias, res, scale, (T*)out, out_img_stride, C_in, C_out, groups, HW, N, act)));
+  } else {
+    dim3 grid(px_tiles, C_out / 64);
+    UNCL_DISPATCH_DTYPE(out_dtype, T, (pw_conv_kernel<T, 64><<<grid, 256, 0, stream>>>(in, w, bias, res, scale, (T*)out, out_img_stride, C_in, C_out, groups, HW, N, act)));
+  }
   return uncl_check_launch("pw_conv");
 }
 
 extern "C" int uncl_gcn_knn_aggregate(const float* y, const float* relpos, float* z, int* idx_out, int N, int C,
                                       cudaStream_t stream) {
   UNCL_REQUIRE(C == 256 && N > 0, "gcn_knn_aggregate: only C=256 (shipped config) is built, got %d", C);
-  const size_t smem = (size_t)(GN * (C + 1) + GN) * sizeof(float) + (size_t)GN * GK * sizeof(int);
+  const size_t smem = (size_t)(GN * (C + 4) + GN) * sizeof(float) + (size_t)GN * GK * sizeof(int);
   cudaError_t e = cudaFuncSetAttribute(gcn_knn_agg_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "gcn_knn_aggregate: smem attr: %s", cudaGetErrorString(e));
-  gcn_knn_agg_kernel<256><<<N, 512, smem, stream>>>(y, relpos, z, idx_out);
+  gcn_knn_agg_kernel<256><<<N * KNN_SPLIT, 512, smem, stream>>>(y, relpos, z, idx_out);
   return uncl_check_launch("gcn_knn_aggregate");
 }
