@@ -182,6 +182,38 @@ int uncl_l1_mean(const float* a, const float* b, int n, float* out, uncl_stream_
 /* L_TV.  GanTrainer.py:669-682.  scratch: 2 floats. */
 int uncl_tv_loss(const float* x, int B, int C, int H, int W, float* scratch, float* out, uncl_stream_t stream);
 
+/* ---- backward building blocks of the generator (fp32, C8-blocked; dense tensors unless a stride is given) ----
+ * Data gradients of the 3x3 convs / pointwise convs reuse uncl_conv3x3_simt / uncl_pw_conv with transposed weights. */
+
+/* dY *= (Y > 0) in place (apply_relu) and db[c] += sum dY (db may be NULL).  ReLU of unet_parts.py:70-86. */
+int uncl_relu_bwd_bias(float* dY, const float* Y, long y_img_stride, float* db, int N, int C, int HW, int apply_relu,
+                       uncl_stream_t stream);
+/* dW9[t][ci][co] += sum X[.., y+ky-pad, x+kx-pad, ci] * dZ[.., y, x, co]   (dW9 zeroed by the caller) */
+int uncl_conv3x3_wgrad(const float* X, long x_img_stride, const float* dZ, float* dW9, int N, int C_in, int H, int W,
+                       int C_out, int pad, uncl_stream_t stream);
+int uncl_conv_first_wgrad(const float* x, const float* dZ, float* dW, int N, int H, int W, int C, uncl_stream_t stream);
+int uncl_maxpool2_bwd(const float* X, long x_img_stride, const float* dP, float* dX, int N, int C, int H, int W,
+                      uncl_stream_t stream);
+/* cat = [x2 | x1 | x2^2 | sqrt(x2+1e-8)] (unet_parts.py:319-322) and its backward */
+int uncl_skip_concat_fwd(const float* x2, long x2_img_stride, const float* x1, float* cat, int N, int C, int HW,
+                         uncl_stream_t stream);
+int uncl_skip_concat_bwd(const float* dcat, const float* x2, long x2_img_stride, float* dx2, float* dx1, int N, int C,
+                         int HW, uncl_stream_t stream);
+/* ConvTranspose k2 s2 backward helper: fold the replicate pad and move (dy,dx) into channels: [N][4C/8][H][W][8] */
+int uncl_convT2x2_s2d(const float* dY, float* out, int N, int C, int H, int W, int H2, int W2, uncl_stream_t stream);
+/* dW[g][ci][co] += sum_pix X[pix,ci] * dZ[pix,co]   (dW zeroed by the caller) */
+int uncl_pw_wgrad(const float* X, const float* dZ, float* dW, int N, int C_in, int C_out, int groups, int HW,
+                  uncl_stream_t stream);
+int uncl_gelu_fwd(const float* u, float* g, long n, uncl_stream_t stream);
+int uncl_gelu_bwd(const float* u, const float* dg, float* du, long n, uncl_stream_t stream);
+int uncl_scale_rows(float* x, const float* scale, int N, long per_image, uncl_stream_t stream);
+int uncl_batch_sum(const float* x, float* out, int N, long M, uncl_stream_t stream);
+/* MRConv2d aggregation backward (gcn_lib/torch_vertex.py:21-30); dy zeroed by the caller */
+int uncl_gcn_agg_bwd(const float* dz, const float* y, const int* idx, float* dy, int N, int C, uncl_stream_t stream);
+/* outconv + sigmoid backward; dw / db zeroed by the caller */
+int uncl_outc_sigmoid_bwd(const float* d_out, const float* out, const float* up, long up_img_stride, const float* w,
+                          float* d_up, float* dw, float* db, int N, int C, int HW, uncl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

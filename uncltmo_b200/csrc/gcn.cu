@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) pw_conv_kernel(const float* __restrict__ 
       *reinterpret_cast<float4*>(av) = *reinterpret_cast<const float4*>(&s_a[ci][tp]);
       *reinterpret_cast<float4*>(av + 4) = *reinterpret_cast<const float4*>(&s_a[ci][tp + 4]);
 #pragma unroll
-      for (int j = 0; j < TC; j += 4) *reinterpret_cast<float4*>(bv + j) = *reinterpret_cast<const float4*>(&s_w[ci][tc + j]);
+      for (int j = 0; j < TC; ++j) bv[j] = s_w[ci][tc + j];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -87,16 +87,12 @@ __global__ void __launch_bounds__(256) pw_conv_kernel(const float* __restrict__ 
     const int n = p / HW, q = p - n * HW;
     const float sc = scale ? scale[n] : 1.f;
 #pragma unroll
-    for (int j0 = 0; j0 < TC; j0 += 4) {  // TC is 4 or 8 and tc is a multiple of 4: one half channel block at a time
-      const int c = co0 + tc + j0;
+    for (int j = 0; j < TC; ++j) {
+      const int c = co0 + tc + j;
       const long o = ((long)(c >> 3) * HW + q) * 8 + (c & 7);
-      float v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[j] = apply_act(acc[i][j0 + j] + bias[c + j], act) * sc;
-        if (res) v[j] += res[(long)n * C_out * HW + o + j];
-        from_f(out[(long)n * out_img_stride + o + j], v[j]);
-      }
+      float v = apply_act(acc[i][j] + (bias ? bias[c] : 0.f), act) * sc;
+      if (res) v += res[(long)n * C_out * HW + o];
+      from_f(out[(long)n * out_img_stride + o], v);
     }
   }
 }
@@ -239,7 +235,7 @@ extern "C" int uncl_pw_conv(const float* in, const float* w, const float* bias, 
                             void* out, long out_img_stride, int N, int C_in, int C_out, int groups, int HW, int act,
                             int out_dtype, cudaStream_t stream) {
   UNCL_REQUIRE(groups > 0 && C_in % groups == 0 && C_out % groups == 0 && (C_in / groups) % 16 == 0 &&
-                   (C_out / groups) % 64 == 0 && N > 0,
+                   (C_out / groups) % 32 == 0 && N > 0,
                "pw_conv: unsupported C_in=%d C_out=%d groups=%d", C_in, C_out, groups);
   // 128-wide channel tiles when that still fills the machine, else 64-wide (twice the CTAs)
   const int px_tiles = ceil_div(N * HW, PW_PX);
@@ -247,9 +243,12 @@ extern "C" int uncl_pw_conv(const float* in, const float* w, const float* bias, 
   if (wide) {
     dim3 grid(px_tiles, C_out / 128);
     UNCL_DISPATCH_DTYPE(out_dtype, T, (pw_conv_kernel<T, 128><<<grid, 256, 0, stream>>>(in, w, bias, res, scale, (T*)out, out_img_stride, C_in, C_out, groups, HW, N, act)));
-  } else {
+  } else if ((C_out / groups) % 64 == 0) {
     dim3 grid(px_tiles, C_out / 64);
     UNCL_DISPATCH_DTYPE(out_dtype, T, (pw_conv_kernel<T, 64><<<grid, 256, 0, stream>>>(in, w, bias, res, scale, (T*)out, out_img_stride, C_in, C_out, groups, HW, N, act)));
+  } else {
+    dim3 grid(px_tiles, C_out / 32);
+    UNCL_DISPATCH_DTYPE(out_dtype, T, (pw_conv_kernel<T, 32><<<grid, 256, 0, stream>>>(in, w, bias, res, scale, (T*)out, out_img_stride, C_in, C_out, groups, HW, N, act)));
   }
   return uncl_check_launch("pw_conv");
 }

@@ -311,18 +311,59 @@ def blocked_to_nchw(t):
 class UNet(_GeneratorBase):
     """Image generator: forward(x[N,1,256,256]) -> (sigmoid map [N,1,256,256], up_x [N,32,256,256]).
 
-    Drop-in for models/unet_multi_filters/Unet_singleFrame.py:101-213.  Inference only in this build
-    (autograd through the kernels arrives with the backward kernels); call under torch.no_grad().
+    Drop-in for models/unet_multi_filters/Unet_singleFrame.py:101-213.  With autograd enabled the forward is built
+    from `uncltmo_b200.autograd` Functions (fp32 path), so `loss.backward()` runs the library's backward kernels.
     """
 
     def forward(self, x, apply_crop=True, diffY=0, diffX=0):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("uncltmo_b200 generator backward is not built yet: call under torch.no_grad()")
-        out, up, _, _ = self._run_frame(x, droppath_scale=self._droppath_scale(x.shape[0], x.device))
-        feats = self._features_nchw(up)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            out, feats = self._forward_train(x, self._droppath_scale(x.shape[0], x.device))
+        else:
+            out, up, _, _ = self._run_frame(x, droppath_scale=self._droppath_scale(x.shape[0], x.device))
+            feats = self._features_nchw(up)
         if apply_crop and self.to_crop:
             out = self._crop(out, diffY, diffX)
         return out, feats
+
+    def _forward_train(self, x, droppath_scale=None):
+        """Same network as _run_frame, built from autograd Functions whose forward and backward are library kernels.
+        fp32 path only this round (the tensor-core backward is next)."""
+        from . import autograd as A
+        if self.precision != "fp32":
+            raise NotImplementedError("training (autograd) runs on the fp32 path this round: construct the generator "
+                                      "with precision='fp32'")
+        if x.dim() != 4 or tuple(x.shape[1:]) != (1, 256, 256) or not x.is_cuda:
+            raise ValueError("the generator expects CUDA [N,1,256,256] inputs")
+        n = x.shape[0]
+        c = self.inc.conv
+        a0 = A.ConvFirst.apply(x, c.conv.weight, c.conv.bias)
+        cur = A.Conv3x3.apply(a0, c.conv1.weight, c.conv1.bias, False, True)
+        skips = [cur]
+        for i in range(4):
+            blk = self.down_path[i].mpconv[1]
+            m = A.Conv3x3.apply(A.MaxPool2.apply(cur), blk.conv.weight, blk.conv.bias, False, True)
+            cur = A.Conv3x3.apply(m, blk.conv1.weight, blk.conv1.bias, i == 3, True)
+            skips.append(cur)
+        g, ffn = self.gcn.module[0][0], self.gcn.module[0][1]
+        s0 = droppath_scale[0] if droppath_scale is not None else None
+        s1 = droppath_scale[1] if droppath_scale is not None else None
+        x0 = A.AddPos.apply(cur, self.gcn.pos_embed)
+        y = A.PwConv.apply(x0, g.fc1[0].weight, g.fc1[0].bias, None, None, 1, False)
+        z = A.KnnAggregate.apply(y, g.relative_pos.detach().reshape(144, 144).float().contiguous())
+        gc = g.graph_conv.gconv.nn[0]
+        z2 = A.PwConv.apply(z, gc.weight, gc.bias, None, None, 4, True)
+        x1 = A.PwConv.apply(z2, g.fc2[0].weight, g.fc2[0].bias, x0, s0, 1, False)
+        f1 = A.PwConv.apply(x1, ffn.fc1[0].weight, ffn.fc1[0].bias, None, None, 1, True)
+        up = A.PwConv.apply(f1, ffn.fc2[0].weight, ffn.fc2[0].bias, x1, s1, 1, False).reshape(n, -1, 12, 12, 8)
+        for i in range(4):
+            u = self.up_path[i]
+            sk = skips[3 - i]
+            x1u = A.ConvT2x2.apply(up, u.up.weight, u.up.bias, sk.shape[2], sk.shape[3])
+            cat = A.SkipConcat.apply(sk, x1u)
+            m = A.Conv3x3.apply(cat, u.conv.conv.weight, u.conv.conv.bias, True, True)
+            up = A.Conv3x3.apply(m, u.conv.conv1.weight, u.conv.conv1.bias, True, True)
+        out = A.OutcSigmoid.apply(up, self.outc.conv.weight, self.outc.conv.bias)
+        return out, A.BlockedToNCHW.apply(up)
 
     def tonemap_tiles(self, x, want_logit=False):
         """Fast path for the frame pipeline: [N,1,256,256] -> [N,1,256,256] without materialising features."""
