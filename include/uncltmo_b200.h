@@ -159,11 +159,12 @@ int uncl_struct_loss_fwd(const float* fake, const float* hdr, int M, int H, int 
                          const float* weights_host, float* loss_out, float* scratch, uncl_stream_t stream);
 
 /* SimpleDiscriminator.forward up to (fea map, logits): models/Discriminator.py:98-122.
- * w1 [16][1][4][4], w2 [32][16][4][4], w3 [32], w_tail [62*62]; h_scratch N*16*127*127 floats;
+ * w1 [16][1][4][4], w2 [32][16][4][4], w3 [32], w_tail [62*62]; h_scratch N*16*127*127 floats (the post-LeakyReLU
+ * first activation, kept for the backward); a2_out N*32*62*62 floats or NULL (second activation, for the backward);
  * fea [N][62][62]; logits [N]. */
 int uncl_disc_forward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
-                      const float* w3, const float* b3, const float* w_tail, float* h_scratch, float* fea,
-                      float* logits, int N, int H, int W, uncl_stream_t stream);
+                      const float* w3, const float* b3, const float* w_tail, float* h_scratch, float* a2_out,
+                      float* fea, float* logits, int N, int H, int W, uncl_stream_t stream);
 
 /* GanTrainer.contrastive_D_loss.  GanTrainerImg.py:219-229. */
 int uncl_contrastive_d_loss(const float* real_logits, const float* fake_logits, int B, float* out,
@@ -175,6 +176,10 @@ int uncl_contrastive_d_loss(const float* real_logits, const float* fake_logits, 
 int uncl_nce_fwd(const float* anchor, const float* pos, long pos_stride, const float* neg, long neg_stride, int B,
                  int C, int HW, float k, float constant, float* logits_scratch, float* loss_out,
                  uncl_stream_t stream);
+
+/* TMQI statistical naturalness N of M images in [0,1] (TMQI.py:210-242, `original` block mode): the score that picks
+ * the positives / negatives of infoNCE2 and the pseudo label (GanTrainerImg.py:341-408).  scratch: 2*M floats. */
+int uncl_tmqi_naturalness(const float* x, int M, int H, int W, float* scratch, float* out, uncl_stream_t stream);
 
 /* nn.L1Loss of two vectors (per-image means).  GanTrainerImg.py:308-313. */
 int uncl_l1_mean(const float* a, const float* b, int n, float* out, uncl_stream_t stream);
@@ -213,6 +218,33 @@ int uncl_gcn_agg_bwd(const float* dz, const float* y, const int* idx, float* dy,
 /* outconv + sigmoid backward; dw / db zeroed by the caller */
 int uncl_outc_sigmoid_bwd(const float* d_out, const float* out, const float* up, long up_img_stride, const float* w,
                           float* d_up, float* dw, float* db, int N, int C, int HW, uncl_stream_t stream);
+
+/* ---- loss / discriminator backward.  `g_up` is the upstream gradient as a DEVICE scalar (no host sync). ---- */
+
+/* d StructLoss / d fake.  scratch: >= 6.5*M*H*W + 64 floats.  weights_host: HOST array [levels]. */
+int uncl_struct_loss_bwd(const float* fake, const float* hdr, int M, int H, int W, int levels,
+                         const float* weights_host, const float* g_up, float* d_fake, float* scratch,
+                         uncl_stream_t stream);
+/* logits: the 2*B similarities uncl_nce_fwd left in its scratch.  d_pos / d_neg may be NULL. */
+int uncl_nce_bwd(const float* anchor, const float* pos, long pos_stride, const float* neg, long neg_stride, int B,
+                 int C, int HW, float k, float constant, const float* logits, const float* g_up, float* d_anchor,
+                 float* d_pos, float* d_neg, uncl_stream_t stream);
+int uncl_contrastive_d_bwd(const float* real_logits, const float* fake_logits, int B, const float* g_up, float* d_real,
+                           float* d_fake, uncl_stream_t stream);
+/* d_mean / d_cmean: [M] upstream gradients of uncl_plane_mean_contrast's outputs (either may be NULL);
+ * mu_scratch: M*(H-10)*(W-10) floats. */
+int uncl_plane_mean_contrast_bwd(const float* x, int M, int H, int W, const float* d_mean, const float* d_cmean,
+                                 float* dx, float* mu_scratch, uncl_stream_t stream);
+int uncl_l1_mean_bwd(const float* a, const float* b, int n, const float* g_up, float* da, float* db,
+                     uncl_stream_t stream);
+int uncl_tv_bwd(const float* x, int B, int C, int H, int W, const float* g_up, float* dx, uncl_stream_t stream);
+/* SimpleDiscriminator backward (models/Discriminator.py:98-126).  d_fea [N][62][62] holds the gradient arriving
+ * through the feature branch on entry (zeros if none); the tail's contribution is added.  dx may be NULL.
+ * dw3 / db3 must be zeroed by the caller.  scratch: N*(32*62*62 + 16*127*127) floats. */
+int uncl_disc_backward(const float* x, const float* h1, const float* a2, const float* fea, const float* w1,
+                       const float* w2, const float* w3, const float* w_tail, const float* d_logits, float* d_fea,
+                       float* dx, float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3,
+                       float* dw_tail, float* scratch, int N, uncl_stream_t stream);
 
 #ifdef __cplusplus
 }

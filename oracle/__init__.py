@@ -15,3 +15,4 @@ from .discriminator import simple_discriminator_forward, contrast_map, gauss_win
 from .losses import (struct_loss, contrastive_d_loss, nce, l1_mean_terms, tv_loss)  # noqa: F401
 from .frame_path import (log_lambda_normalise, to_gray, resize_im, tile_and_blend, tile_grid,  # noqa: F401
                          back_to_color, postprocess_frame, tonemap_frame)
+from .train_step import tmqi_naturalness, train_step_losses  # noqa: F401

@@ -112,6 +112,17 @@ def main():
     out["l1_mean"] = np.array(l1(fake.mean(dim=[-1, -2]), ld[:2].mean(dim=[-1, -2])).item())
     out["l1_contrast"] = np.array(l1(ce(fake).mean(dim=[-1, -2]), ce(ld[:2]).mean(dim=[-1, -2])).item())
     out["tv"] = np.array(GT.L_TV()(ld).item())
+    # TMQI statistical naturalness, the score behind infoNCE2 / pseudo_label_loss (TMQI.py:210-242)
+    from TMQI import TMQI
+    tm = TMQI()
+    nat = [tm(hdr[i, 0].numpy().astype(np.float64), (fake[i, 0].numpy() * 255).astype(np.float64))[2] for i in range(2)]
+    nat += [tm(ld[i, 0].numpy().astype(np.float64) + 1e-3, (ld[i, 0].numpy() * 255).astype(np.float64))[2] for i in range(3)]
+    q = ld[0, 0].numpy()
+    nat += [tm(q[j * 128:(j + 1) * 128, k * 128:(k + 1) * 128].astype(np.float64) + 1e-3,
+               (q[j * 128:(j + 1) * 128, k * 128:(k + 1) * 128] * 255).astype(np.float64))[2] for j in range(2) for k in range(2)]
+    out["tmqi_naturalness"] = np.array(nat)
+    out["pseudo_label_loss"] = np.array(t.pseudo_label_loss(ld[:2], ld[:2] + 1e-3).item())
+    out["infoNCE2"] = np.array(t.infoNCE2(g1[:3], ld, ld + 1e-3, "InfoNCE", 1, 1e-2).item())
 
     # ---- frame path: normalise, pad, tile+blend, post-process ----
     rgb = torch.from_numpy(gi.small_frame())

@@ -11,8 +11,14 @@ from uncltmo_b200.generator import UNet
 from uncltmo_b200.weights import make_generator_state_dict
 
 pytestmark = pytest.mark.gpu
-torch.set_grad_enabled(False)
 G_ARGS = (1, 1, "sigmoid", 4, 4, "square_and_square_root", 32, 0, "unet", 0, 0, "none", "none", "relu", 1, "replicate", 2)
+
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    """Inference tests run without autograd; tests that need it re-enable it locally."""
+    with torch.no_grad():
+        yield
 
 
 def maxabs(a, b):

@@ -10,11 +10,17 @@ from uncltmo_b200.generator import UNet, UNetVideo, blocked_to_nchw
 from uncltmo_b200.weights import make_generator_state_dict
 
 pytestmark = pytest.mark.gpu
-torch.set_grad_enabled(False)
 G_ARGS = (1, 1, "sigmoid", 4, 4, "square_and_square_root", 32, 0, "unet", 0, 0, "none", "none", "relu", 1, "replicate", 2)
 
 # tolerances stated by BASELINE.json north_star: generator output rel-L2 <= 1e-4 (fp32 path), <= 1e-2 (bf16 path)
 TOL = {"fp32": 1e-4, "bf16": 1e-2}
+
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    """Inference tests run without autograd; tests that need it re-enable it locally."""
+    with torch.no_grad():
+        yield
 
 
 def rel(a, b):
@@ -74,8 +80,6 @@ def test_module_forward_surface(oracle_run):
     out, feats = net(x.cuda(), apply_crop=True, diffY=0, diffX=0)
     assert out.shape == (2, 1, 256, 256) and feats.shape == (2, 32, 256, 256)
     assert rel(out, o_out) <= 1e-4 and rel(feats, o_up) <= 1e-5
-    with torch.enable_grad(), pytest.raises(NotImplementedError):
-        net(x.cuda())
 
 
 def test_fused_outc_path(oracle_run):

@@ -13,8 +13,14 @@ from uncltmo_b200.struct_loss import StructLoss
 from uncltmo_b200.weights import make_discriminator_state_dict, make_generator_state_dict
 
 pytestmark = pytest.mark.gpu
-torch.set_grad_enabled(False)
 RTOL = 1e-3
+
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    """Inference tests run without autograd; tests that need it re-enable it locally."""
+    with torch.no_grad():
+        yield
 
 
 def relerr(a, b):
@@ -95,3 +101,100 @@ def test_mean_contrast_l1_and_tv(golden):
     mean, con = plane_mean_contrast(ld.cuda())
     assert torch.allclose(mean.cpu(), ld.mean(dim=(-1, -2)), rtol=1e-5)
     assert torch.allclose(con.cpu(), oracle.contrast_map(ld).mean(dim=(-1, -2)), rtol=1e-3, atol=1e-7)
+
+
+# ----------------------------------------------------------------------------------------------- backward parity
+def _leaf(t, dev=None):
+    t = t.clone().to(dev) if dev else t.clone().double()
+    return t.requires_grad_(True)
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def test_tmqi_naturalness_on_device(golden):
+    from uncltmo_b200.autograd_losses import tmqi_naturalness
+    sd = make_generator_state_dict()
+    fake, _ = oracle.unet_forward(sd, gi.generator_input())
+    ld = gi.ldr_input()
+    q = ld[0:1, :, :, :].reshape(1, 1, 2, 128, 2, 128).permute(0, 2, 4, 1, 3, 5).reshape(4, 1, 128, 128)
+    got = torch.cat([tmqi_naturalness(fake.cuda()), tmqi_naturalness(ld.cuda()), tmqi_naturalness(q.cuda())]).cpu().numpy()
+    assert np.abs(got - golden["tmqi_naturalness"]).max() <= 1e-4 * golden["tmqi_naturalness"].max()
+    assert relerr(losses.pseudo_label_loss(ld[:2].cuda(), None).item(), golden["pseudo_label_loss"]) <= RTOL
+    g1, _, _ = gi.nce_features_map()
+    assert relerr(losses.infoNCE2(g1[:3].cuda(), ld.cuda(), None, "InfoNCE", 1, 1e-2).item(), golden["infoNCE2"]) <= RTOL
+
+
+@torch.enable_grad()
+def test_struct_loss_backward():
+    rng = np.random.default_rng(7)
+    a = torch.from_numpy((rng.random((2, 1, 64, 80)) * 0.2 + 0.4).astype(np.float32))
+    b = torch.from_numpy(rng.random((2, 1, 64, 80)).astype(np.float32))
+    ar = _leaf(a)
+    (oracle.struct_loss(ar, b.double(), (1.0, 2.0, 0.5)) * 3.0).backward()
+    ac = _leaf(a, "cuda")
+    (StructLoss([1.0, 2.0, 0.5])(ac, None, b.cuda(), [1.0, 2.0, 0.5]) * 3.0).backward()
+    assert _rel(ac.grad, ar.grad) <= 1e-4
+    flat = torch.full((1, 1, 32, 32), 0.5)   # flat windows: variance exactly 0
+    fr, fc = _leaf(flat), _leaf(flat, "cuda")
+    oracle.struct_loss(fr, b[:1, :, :32, :32].double(), (1.0,)).backward()
+    StructLoss([1.0])(fc, None, b[:1, :, :32, :32].cuda(), [1.0]).backward()
+    assert (fc.grad.cpu().double() - fr.grad).abs().max().item() <= 1e-3 * fr.grad.abs().max().item()
+
+
+@torch.enable_grad()
+def test_contrastive_nce_l1_tv_backward():
+    a, b = gi.logits_pair()
+    ar, br = _leaf(a), _leaf(b)
+    oracle.contrastive_d_loss(ar, br).backward()
+    ac, bc = _leaf(a, "cuda"), _leaf(b, "cuda")
+    losses.contrastive_D_loss(ac, bc).backward()
+    assert _rel(ac.grad, ar.grad) <= 1e-5 and _rel(bc.grad, br.grad) <= 1e-5
+    g1, g2, g3 = gi.nce_features_map()
+    r1, r2, r3 = _leaf(g1), _leaf(g2), _leaf(g3)
+    oracle.nce(r1, r2, r3, 1, 1e-2).backward()
+    c1, c2, c3 = _leaf(g1, "cuda"), _leaf(g2, "cuda"), _leaf(g3, "cuda")
+    losses.nce(c1, [c2], [c3], "InfoNCE", 1, 1e-2).backward()
+    assert _rel(c1.grad, r1.grad) <= 1e-4 and _rel(c2.grad, r2.grad) <= 1e-4 and _rel(c3.grad, r3.grad) <= 1e-4
+    # broadcast positive / negative taken from the anchor batch itself (infoNCE2): gradients add up on those samples
+    r1 = _leaf(g1)
+    oracle.nce(r1, r1[2:3].expand_as(r1), r1[0:1].expand_as(r1), 1, 1e-2).backward()
+    c1 = _leaf(g1, "cuda")
+    losses.nce_from_indices(c1, torch.tensor(2, device="cuda"), torch.tensor(0, device="cuda"), "InfoNCE", 1, 1e-2).backward()
+    assert _rel(c1.grad, r1.grad) <= 1e-4
+    ld = gi.ldr_input()
+    x = gi.generator_input()
+    fr = _leaf(x)
+    lm, lc = oracle.l1_mean_terms(fr, ld[:2].double())
+    (2.0 * lm + 3.0 * lc).backward()
+    fc = _leaf(x, "cuda")
+    lm, lc = losses.l1_mean_terms(fc, ld[:2].cuda())
+    (2.0 * lm + 3.0 * lc).backward()
+    assert _rel(fc.grad, fr.grad) <= 1e-4
+    tr, tc = _leaf(ld), _leaf(ld, "cuda")
+    oracle.tv_loss(tr).backward()
+    losses.L_TV()(tc).backward()
+    assert _rel(tc.grad, tr.grad) <= 1e-5
+
+
+@torch.enable_grad()
+def test_discriminator_backward():
+    sd = make_discriminator_state_dict()
+    x = gi.ldr_input()
+    params = {k: _leaf(v) for k, v in sd.items()}
+    xr = _leaf(x)
+    logit, fea = oracle.simple_discriminator_forward(params, xr)
+    rng = np.random.default_rng(9)
+    pl = torch.from_numpy(rng.standard_normal((3, 1)).astype(np.float32))
+    pf = torch.from_numpy(rng.standard_normal((3, 2, 1, 1)).astype(np.float32))
+    ((logit * pl.double()).sum() + (fea * pf.double()).sum() * 10).backward()
+    d = SimpleDiscriminator(256, 1, 16, "none", "none", 0, 0).cuda()
+    d.load_state_dict(sd)
+    xc = _leaf(x, "cuda")
+    logit, fea = d(xc)
+    ((logit * pl.cuda()).sum() + (fea * pf.cuda()).sum() * 10).backward()
+    assert _rel(xc.grad, xr.grad) <= 1e-4
+    for k, p in d.named_parameters():
+        assert _rel(p.grad, params[k].grad) <= 1e-4, k

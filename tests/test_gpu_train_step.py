@@ -1,0 +1,89 @@
+"""One GAN training step (train_D + train_G of GanTrainerImg) on the B200 path against the CPU oracle's step:
+loss values within 1e-3 relative (BASELINE.json), gradients of the well-conditioned parameter groups within 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from uncltmo_b200 import synth
+from uncltmo_b200.discriminator import SimpleDiscriminator
+from uncltmo_b200.generator import UNet
+from uncltmo_b200.trainer import GanTrainerStep
+from uncltmo_b200.weights import make_discriminator_state_dict, make_generator_state_dict
+
+pytestmark = pytest.mark.gpu
+G_ARGS = (1, 1, "sigmoid", 4, 4, "square_and_square_root", 32, 0, "unet", 0, 0, "none", "none", "relu", 1, "replicate", 2)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+class RecordingSGD(torch.optim.SGD):
+    """lr = 0 optimizer that keeps a copy of the gradients it was handed (zero_grad follows immediately in the trainer)."""
+
+    def step(self):
+        self.seen = {id(p): p.grad.detach().clone() for g in self.param_groups for p in g["params"] if p.grad is not None}
+
+
+@pytest.mark.parametrize("epoch", [0, 7, 10])
+def test_train_step_matches_oracle(epoch):
+    g_sd, d_sd = make_generator_state_dict(), make_discriminator_state_dict()
+    hdr = torch.from_numpy(synth.normalised_batch(2, seed=4)).reshape(1, 2, 1, 256, 256)
+    pos = torch.from_numpy(synth.ldr_batch(2, seed=5)).reshape(1, 2, 1, 256, 256)
+    neg = torch.from_numpy(synth.ldr_batch(2, seed=6)).reshape(1, 2, 1, 256, 256)
+    # float64 oracle: several gradients (e.g. the out-conv bias = a signed sum over 131072 pixels) cancel heavily, and an
+    # fp32 reference would carry as much rounding noise as the path under test
+    ref = oracle.train_step_losses({k: v.double() for k, v in g_sd.items()}, {k: v.double() for k, v in d_sd.items()},
+                                   hdr[0].double(), pos[0].double(), neg[0].double(), epoch)
+
+    netG = UNet(*G_ARGS, up_mode=0, precision="fp32").cuda().train()
+    netG.load_state_dict(g_sd)
+    netG.drop_path_prob = 0.0
+    netD = SimpleDiscriminator(256, 1, 16, "none", "none", 0, 0).cuda().train()
+    netD.load_state_dict(d_sd)
+    optG = RecordingSGD([p for p in netG.parameters() if p.requires_grad], lr=0.0)
+    optD = RecordingSGD(netD.parameters(), lr=0.0)
+    tr = GanTrainerStep(netG, netD, optG, optD)
+    err_g, err_s = tr.step(hdr.cuda(), None, pos.cuda(), neg.cuda(), epoch)
+    assert abs(tr.errD.item() - ref["errD"]) <= 1e-3 * abs(ref["errD"])
+    assert abs(err_g.item() - ref["errG_d"]) <= 1e-3 * abs(ref["errG_d"])
+    assert abs(err_s.item() - ref["errG_struct"]) <= 1e-3 * abs(ref["errG_struct"])
+    biggest = max(g.double().norm().item() for g in ref["grads_D"].values())
+    for k, p in netD.named_parameters():
+        # model.4.bias shifts every logit alike and the contrastive loss only sees differences: its exact gradient
+        # is 0 and both sides hold rounding noise there, hence the floor relative to the largest gradient
+        got, want = optD.seen[id(p)].double().cpu(), ref["grads_D"][k].double()
+        assert (got - want).norm().item() <= 1e-3 * want.norm().item() + 1e-6 * biggest, k
+    # decoder / graph block / deepest encoder stage are well conditioned (tests/test_gpu_backward.py explains why the
+    # shallow encoder stages are not, in the reference itself)
+    bad = {}
+    for k, p in netG.named_parameters():
+        if k in ref["grads_G"] and not (k.startswith("inc.") or k[:11] in ("down_path.0", "down_path.1", "down_path.2")):
+            e = rel(optG.seen[id(p)], ref["grads_G"][k])
+            # outc.conv.bias = sum over all pixels of d(logit): the struct-loss part of that sum cancels to ~0 window by
+            # window while its terms are ~1e4 larger, so fp32 leaves ~1e-2 of noise on the small remainder
+            if e > (5e-2 if k == "outc.conv.bias" else 2e-3):
+                bad[k] = e
+    assert not bad, bad
+
+
+def test_adam_training_reduces_struct_loss():
+    """A few real optimizer steps (Adam, the reference's lr 1e-5 x100 to see movement): losses stay finite, G changes."""
+    torch.manual_seed(0)
+    netG = UNet(*G_ARGS, up_mode=0, precision="fp32").cuda().train()
+    netG.load_state_dict(make_generator_state_dict())
+    netD = SimpleDiscriminator(256, 1, 16, "none", "none", 0, 0).cuda().train()
+    netD.load_state_dict(make_discriminator_state_dict())
+    optG = torch.optim.Adam([p for p in netG.parameters() if p.requires_grad], lr=1e-3, betas=(0.5, 0.999))
+    optD = torch.optim.Adam(netD.parameters(), lr=1.5e-5, betas=(0.5, 0.999))
+    tr = GanTrainerStep(netG, netD, optG, optD)
+    hdr = torch.from_numpy(synth.normalised_batch(4, seed=4)).reshape(2, 2, 1, 256, 256).cuda()
+    pos = torch.from_numpy(synth.ldr_batch(4, seed=5)).reshape(2, 2, 1, 256, 256).cuda()
+    neg = torch.from_numpy(synth.ldr_batch(4, seed=6)).reshape(2, 2, 1, 256, 256).cuda()
+    hist = []
+    for _ in range(6):
+        _, s = tr.step(hdr, None, pos, neg, 0)
+        hist.append(s.item())
+    assert all(np.isfinite(hist)) and hist[-1] < hist[0]

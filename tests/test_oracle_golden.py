@@ -1,12 +1,19 @@
 """Pins the CPU oracle against fixtures produced by the reference itself (tests/golden/make_golden.py)."""
 import numpy as np
+import pytest
 import torch
 
 import golden_inputs as gi
 import oracle
 from uncltmo_b200.weights import make_generator_state_dict, make_discriminator_state_dict
 
-torch.set_grad_enabled(False)
+
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    """Inference tests run without autograd; tests that need it re-enable it locally."""
+    with torch.no_grad():
+        yield
 
 
 def close(a, b, tol=1e-6):
@@ -103,3 +110,20 @@ def test_frame_end_to_end(golden):
     assert np.abs(u8.astype(int) - golden["frame_u8_s2"].astype(int)).max() <= 1
     assert close(oracle.tonemap_frame(rgb, gi.LAMBDA, lambda t: oracle.unet_forward(sd, t)[0])[:, ::2, ::2],
                  golden["frame_color_s2"], 1e-5)
+
+
+def test_tmqi_naturalness_and_selection_losses(golden):
+    """The score that drives infoNCE2 / pseudo_label_loss (TMQI.py:210-242) and the two losses built on it."""
+    from oracle import train_step as ts
+    sd = make_generator_state_dict()
+    x = gi.generator_input()
+    fake, _ = oracle.unet_forward(sd, x)
+    ld = gi.ldr_input()
+    nat = [oracle.tmqi_naturalness(fake[i, 0].numpy() * 255) for i in range(2)]
+    nat += [oracle.tmqi_naturalness(ld[i, 0].numpy() * 255) for i in range(3)]
+    q = ld[0, 0].numpy()
+    nat += [oracle.tmqi_naturalness(q[j * 128:(j + 1) * 128, k * 128:(k + 1) * 128] * 255) for j in range(2) for k in range(2)]
+    assert close(np.array(nat), golden["tmqi_naturalness"], 1e-5)
+    assert close(ts.pseudo_label_loss(ld[:2]), golden["pseudo_label_loss"], 1e-5)
+    g1, _, _ = gi.nce_features_map()
+    assert close(ts.info_nce2(g1[:3], ld, 1, 1e-2), golden["infoNCE2"], 1e-5)

@@ -188,8 +188,9 @@ __global__ void __launch_bounds__(256) disc_conv1_kernel(const float* __restrict
 // h [N][16][Hi][Wi] -> fea [N][Ho][Wo];  w2 [32][16][4][4], w3 [32]
 __global__ void __launch_bounds__(128) disc_conv2_kernel(const float* __restrict__ h, const float* __restrict__ w2,
                                                         const float* __restrict__ b2, const float* __restrict__ w3,
-                                                        const float* __restrict__ b3, float* __restrict__ fea, int Hi,
-                                                        int Wi, int Ho, int Wo, long total) {
+                                                        const float* __restrict__ b3, float* __restrict__ fea,
+                                                        float* __restrict__ a2_out, int Hi, int Wi, int Ho, int Wo,
+                                                        long total) {
   extern __shared__ float s_w2[];  // 32*256 + 32 + 32
   for (int i = threadIdx.x; i < 32 * 256; i += blockDim.x) s_w2[i] = w2[i];
   if (threadIdx.x < 32) { s_w2[8192 + threadIdx.x] = b2[threadIdx.x]; s_w2[8224 + threadIdx.x] = w3[threadIdx.x]; }
@@ -214,7 +215,11 @@ __global__ void __launch_bounds__(128) disc_conv2_kernel(const float* __restrict
     }
     float o = __ldg(b3);
 #pragma unroll
-    for (int c = 0; c < 32; ++c) o = fmaf(acc[c] > 0.f ? acc[c] : 0.2f * acc[c], s_w2[8224 + c], o);
+    for (int c = 0; c < 32; ++c) {
+      const float av = acc[c] > 0.f ? acc[c] : 0.2f * acc[c];
+      if (a2_out) a2_out[((n * 32 + c) * Ho + oy) * Wo + ox] = av;
+      o = fmaf(av, s_w2[8224 + c], o);
+    }
     fea[i] = o;
   }
 }
@@ -338,6 +343,54 @@ __global__ void tv_final_kernel(const float* __restrict__ acc, int B, int C, int
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TMQI statistical naturalness (TMQI.py:210-242, original=True): u = mean(L), sig = mean over zero-padded 11x11
+// blocks of the block standard deviation, N = normpdf(u)/normpdf(mode) * betapdf(sig/64.29)/betapdf(mode).
+// L = 255 * x.  One thread per block; sums[2m] += sum L, sums[2m+1] += sum block std.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) tmqi_blocks_kernel(const float* __restrict__ x, int H, int W, int nby, int nbx,
+                                                         float* __restrict__ sums) {
+  __shared__ float red[33];
+  const int m = blockIdx.y;
+  const float* xp = x + (long)m * H * W;
+  float spix = 0.f, sstd = 0.f;
+  for (int b = blockIdx.x * 128 + threadIdx.x; b < nby * nbx; b += gridDim.x * 128) {
+    const int y0 = (b / nbx) * 11, x0 = (b % nbx) * 11;
+    float s = 0.f;
+    for (int dy = 0; dy < 11; ++dy)
+      for (int dx = 0; dx < 11; ++dx) {
+        const int yy = y0 + dy, xx = x0 + dx;
+        if (yy < H && xx < W) s += 255.f * __ldg(xp + (long)yy * W + xx);
+      }
+    const float mean = s / 121.f;
+    float v = 0.f;
+    for (int dy = 0; dy < 11; ++dy)
+      for (int dx = 0; dx < 11; ++dx) {
+        const int yy = y0 + dy, xx = x0 + dx;
+        const float val = (yy < H && xx < W) ? 255.f * __ldg(xp + (long)yy * W + xx) : 0.f;
+        v = fmaf(val - mean, val - mean, v);
+      }
+    spix += s;
+    sstd += sqrtf(v / 121.f);
+  }
+  atomic_add_block(spix, sums + 2 * m, red);
+  atomic_add_block(sstd, sums + 2 * m + 1, red);
+}
+__global__ void tmqi_final_kernel(const float* __restrict__ sums, int M, int H, int W, int nblocks, float* __restrict__ out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float phat1 = 4.4f, phat2 = 10.1f, muhat = 115.94f, sigmahat = 27.99f;
+  const float u = sums[2 * m] / (float)((long)H * W);
+  const float sig = sums[2 * m + 1] / (float)nblocks;
+  const float mode = (phat1 - 1.f) / (phat1 + phat2 - 2.f);
+  const float xq = sig / 64.29f;
+  float pc = 0.f;
+  if (xq > 0.f && xq < 1.f)
+    pc = expf((phat1 - 1.f) * (logf(xq) - logf(mode)) + (phat2 - 1.f) * (logf(1.f - xq) - logf(1.f - mode)));
+  const float z = (u - muhat) / sigmahat;
+  out[m] = expf(-0.5f * z * z) * pc;
+}
+
 inline int cap_grid(long total, int block, int per_sm) {
   long g = (total + block - 1) / block;
   const long cap = 148L * per_sm;
@@ -409,8 +462,8 @@ extern "C" int uncl_struct_loss_fwd(const float* fake, const float* hdr, int M, 
 // SimpleDiscriminator forward (input 256x256, dim 16, no padding).  h_scratch: N*16*127*127 floats.
 // fea [N][62][62], logits [N].
 extern "C" int uncl_disc_forward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
-                                 const float* w3, const float* b3, const float* w_tail, float* h_scratch, float* fea,
-                                 float* logits, int N, int H, int W, cudaStream_t stream) {
+                                 const float* w3, const float* b3, const float* w_tail, float* h_scratch, float* a2_out,
+                                 float* fea, float* logits, int N, int H, int W, cudaStream_t stream) {
   UNCL_REQUIRE(N > 0 && H >= 10 && W >= 10, "disc_forward: bad shape");
   const int H1 = (H - 4) / 2 + 1, W1 = (W - 4) / 2 + 1, H2 = (H1 - 4) / 2 + 1, W2 = (W1 - 4) / 2 + 1;
   const long t1 = (long)N * H1 * W1, t2 = (long)N * H2 * W2;
@@ -418,7 +471,7 @@ extern "C" int uncl_disc_forward(const float* x, const float* w1, const float* b
   const size_t smem = (32 * 256 + 64) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(disc_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "disc_forward: %s", cudaGetErrorString(e));
-  disc_conv2_kernel<<<cap_grid(t2, 128, 4), 128, smem, stream>>>(h_scratch, w2, b2, w3, b3, fea, H1, W1, H2, W2, t2);
+  disc_conv2_kernel<<<cap_grid(t2, 128, 4), 128, smem, stream>>>(h_scratch, w2, b2, w3, b3, fea, a2_out, H1, W1, H2, W2, t2);
   rowdot_kernel<<<N, 256, 0, stream>>>(fea, w_tail, H2 * W2, logits);
   return uncl_check_launch("disc_forward");
 }
@@ -459,4 +512,17 @@ extern "C" int uncl_tv_loss(const float* x, int B, int C, int H, int W, float* s
   tv_kernel<<<cap_grid(total, 256, 8), 256, 0, stream>>>(x, H, W, total, scratch);
   tv_final_kernel<<<1, 32, 0, stream>>>(scratch, B, C, H, W, out);
   return uncl_check_launch("tv_loss");
+}
+
+// TMQI naturalness score of M images in [0,1] (scaled by 255 inside).  scratch: 2*M floats.
+extern "C" int uncl_tmqi_naturalness(const float* x, int M, int H, int W, float* scratch, float* out,
+                                     cudaStream_t stream) {
+  UNCL_REQUIRE(M > 0 && H > 10 && W > 10, "tmqi_naturalness: bad shape");
+  const int nby = (H + (11 - H % 11)) / 11, nbx = (W + (11 - W % 11)) / 11;
+  cudaMemsetAsync(scratch, 0, (size_t)2 * M * sizeof(float), stream);
+  int gx = ceil_div(nby * nbx, 128);
+  if (gx > 16) gx = 16;
+  tmqi_blocks_kernel<<<dim3(gx, M), 128, 0, stream>>>(x, H, W, nby, nbx, scratch);
+  tmqi_final_kernel<<<ceil_div(M, 128), 128, 0, stream>>>(scratch, M, H, W, nby * nbx, out);
+  return uncl_check_launch("tmqi_naturalness");
 }

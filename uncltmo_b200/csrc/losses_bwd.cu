@@ -1,0 +1,541 @@
+// Backward kernels of the training losses and of the SimpleDiscriminator (dense fp32 planes [M][H][W]).
+// Every kernel takes the upstream gradient as a DEVICE scalar pointer so that no host synchronisation is needed.
+//
+// Reference: autograd of models/struct_loss.py:46-104, GanTrainerImg.py:219-229 (contrastive_D_loss), :410-439 (nce),
+// :24-56 / models/Discriminator.py:61-83 (ContrastExtracter), GanTrainer.py:669-682 (L_TV), Discriminator.py:87-126.
+#include "common.cuh"
+
+namespace {
+
+inline int cap_grid(long total, int block, int per_sm) {
+  long g = (total + block - 1) / block;
+  const long cap = 148L * per_sm;
+  return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+__constant__ float c_g11[11];
+bool g_ready = false;
+int ensure_gauss() {
+  if (g_ready) return 0;
+  double g[11], s = 0;
+  for (int i = 0; i < 11; ++i) { g[i] = exp(-((i - 5) * (i - 5)) / (2.0 * 1.5 * 1.5)); s += g[i]; }
+  float gf[11];
+  for (int i = 0; i < 11; ++i) gf[i] = (float)(g[i] / s);
+  if (cudaMemcpyToSymbol(c_g11, gf, sizeof(gf)) != cudaSuccess) return -1;
+  g_ready = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// structural loss, one level.  Per 5x5 window w (u = a - mu_a, v = b - mu_b, S = centred sums, d = std + e):
+//   L_w = S_aa/d_a^2 + S_bb/d_b^2 - 2 S_ab/(d_a d_b)
+//   dL_w/da_k = P_w u_k - Q_w v_k,  P_w = 2/d_a^2 - 2 S_aa/(25 std_a d_a^3) + 2 S_ab/(25 std_a d_a^2 d_b),
+//                                   Q_w = 2/(d_a d_b)
+// coef[0..3] = scale * (P, P mu_a, Q, Q mu_b); the pixel gradient sums them over the <=25 windows that cover it.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) struct_coef_kernel(const float* __restrict__ a, const float* __restrict__ b, int H,
+                                                         int W, float scale, const float* __restrict__ g_up,
+                                                         float* __restrict__ coef, long plane) {
+  __shared__ float s_a[20][37];
+  __shared__ float s_b[20][37];
+  const long m = blockIdx.z;
+  const float* ap = a + m * H * W;
+  const float* bp = b + m * H * W;
+  const int Ho = H - 4, Wo = W - 4;
+  const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * 16;
+  for (int i = threadIdx.x; i < 20 * 36; i += 256) {
+    const int ly = i / 36, lx = i % 36;
+    const int gy = oy0 + ly, gx = ox0 + lx;
+    const bool in = gy < H && gx < W;
+    s_a[ly][lx] = in ? __ldg(ap + (long)gy * W + gx) : 0.f;
+    s_b[ly][lx] = in ? __ldg(bp + (long)gy * W + gx) : 0.f;
+  }
+  __syncthreads();
+  const float sc = scale * __ldg(g_up);
+  for (int i = threadIdx.x; i < 16 * 32; i += 256) {
+    const int ly = i / 32, lx = i % 32;
+    if (oy0 + ly < Ho && ox0 + lx < Wo) {
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) { sa += s_a[ly + dy][lx + dx]; sb += s_b[ly + dy][lx + dx]; }
+      const float ma = sa * 0.04f, mb = sb * 0.04f;
+      float saa = 0.f, sbb = 0.f, sab = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+          const float da = s_a[ly + dy][lx + dx] - ma, db = s_b[ly + dy][lx + dx] - mb;
+          saa = fmaf(da, da, saa); sbb = fmaf(db, db, sbb); sab = fmaf(da, db, sab);
+        }
+      const float e = 1e-5f;
+      const float std_a = sqrtf(saa * 0.04f + e), std_b = sqrtf(sbb * 0.04f + e);
+      const float d_a = std_a + e, d_b = std_b + e;
+      // d std_a / d a_k = u_k / (25 std_a) while the variance is positive (max(var, 0) in the reference)
+      const float dstd = saa > 0.f ? 1.f / (25.f * std_a) : 0.f;
+      const float P = sc * (2.f / (d_a * d_a) - 2.f * saa / (d_a * d_a * d_a) * dstd + 2.f * sab / (d_a * d_a * d_b) * dstd);
+      const float Q = sc * 2.f / (d_a * d_b);
+      const long o = m * Ho * Wo + (long)(oy0 + ly) * Wo + ox0 + lx;
+      coef[o] = P;
+      coef[plane + o] = P * ma;
+      coef[2 * plane + o] = Q;
+      coef[3 * plane + o] = Q * mb;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) struct_grad_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                         const float* __restrict__ coef, long plane, int H, int W,
+                                                         long total, float* __restrict__ grad) {
+  const int Ho = H - 4, Wo = W - 4;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int x = i % W, y = (i / W) % H;
+    const long m = i / ((long)W * H);
+    const int y0 = max(0, y - 4), y1 = min(y, Ho - 1), x0 = max(0, x - 4), x1 = min(x, Wo - 1);
+    float sp = 0.f, spm = 0.f, sq = 0.f, sqm = 0.f;
+    for (int wy = y0; wy <= y1; ++wy)
+      for (int wx = x0; wx <= x1; ++wx) {
+        const long o = m * Ho * Wo + (long)wy * Wo + wx;
+        sp += __ldg(coef + o);
+        spm += __ldg(coef + plane + o);
+        sq += __ldg(coef + 2 * plane + o);
+        sqm += __ldg(coef + 3 * plane + o);
+      }
+    grad[i] = a[i] * sp - spm - b[i] * sq + sqm;
+  }
+}
+
+// transpose of the bicubic x0.5 down-sampler: d_in += taps * d_out (d_in already holds the level's own gradient)
+__global__ void __launch_bounds__(256) bicubic_half_bwd_kernel(const float* __restrict__ d_out, float* __restrict__ d_in,
+                                                              int H, int W, long total) {
+  const int Ho = H / 2, Wo = W / 2;
+  const float t[4] = {-0.09375f, 0.59375f, 0.59375f, -0.09375f};
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int x = i % Wo, y = (i / Wo) % Ho;
+    const long m = i / ((long)Wo * Ho);
+    const float g = d_out[i];
+    float* p = d_in + m * H * W;
+#pragma unroll
+    for (int aa = 0; aa < 4; ++aa) {
+      const int yy = min(max(2 * y - 1 + aa, 0), H - 1);
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        const int xx = min(max(2 * x - 1 + bb, 0), W - 1);
+        atomicAdd(p + (long)yy * W + xx, t[aa] * t[bb] * g);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// nce backward.  loss = mean_b [lse(l0,l1) - l0];  dl0 = g (p0 - 1)/B, dl1 = g (1 - p0)/B
+//   sim(a,p) = (1/HW) sum a p / (c0 + k|a-p|):  d/da = (p den - a p k sgn(a-p)) / den^2,  d/dp = (a den + a p k sgn(a-p)) / den^2
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nce_pair_grad(float a, float p, float k, float c0, float& da, float& dp) {
+  const float diff = a - p;
+  const float den = c0 + k * fabsf(diff);
+  const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+  const float inv2 = 1.f / (den * den);
+  da = (p * den - a * p * k * sg) * inv2;
+  dp = (a * den + a * p * k * sg) * inv2;
+}
+
+// d_anchor for every sample (+ d_pos / d_neg when they are per-sample tensors)
+__global__ void __launch_bounds__(256) nce_bwd_kernel(const float* __restrict__ a, const float* __restrict__ p, long ps,
+                                                     const float* __restrict__ n, long ns, long CHW, float k, float c0,
+                                                     float inv_hw, const float* __restrict__ logits, int B,
+                                                     const float* __restrict__ g_up, float* __restrict__ da,
+                                                     float* __restrict__ dp, float* __restrict__ dn) {
+  const int b = blockIdx.y;
+  const float l0 = logits[2 * b], l1 = logits[2 * b + 1];
+  const float mx = fmaxf(l0, l1);
+  const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+  const float p0 = e0 / (e0 + e1);
+  const float g = __ldg(g_up) / (float)B * inv_hw;
+  const float dl0 = g * (p0 - 1.f), dl1 = g * (1.f - p0);
+  const float* ab = a + (long)b * CHW;
+  const float* pb = p + (long)b * ps;
+  const float* nb = n + (long)b * ns;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < CHW; i += (long)gridDim.x * 256) {
+    const float av = ab[i];
+    float da_p, dp_p, da_n, dn_n;
+    nce_pair_grad(av, pb[i], k, c0, da_p, dp_p);
+    nce_pair_grad(av, nb[i], k, c0, da_n, dn_n);
+    da[(long)b * CHW + i] = dl0 * da_p + dl1 * da_n;
+    if (dp && ps) dp[(long)b * CHW + i] = dl0 * dp_p;
+    if (dn && ns) dn[(long)b * CHW + i] = dl1 * dn_n;
+  }
+}
+// broadcast positive / negative (stride 0): their gradient sums over the batch
+__global__ void __launch_bounds__(256) nce_bwd_bcast_kernel(const float* __restrict__ a, const float* __restrict__ q,
+                                                           long CHW, float k, float c0, float inv_hw,
+                                                           const float* __restrict__ logits, int B, int which,
+                                                           const float* __restrict__ g_up, float* __restrict__ dq) {
+  extern __shared__ float s_dl[];  // [B]
+  for (int b = threadIdx.x; b < B; b += 256) {
+    const float l0 = logits[2 * b], l1 = logits[2 * b + 1];
+    const float mx = fmaxf(l0, l1);
+    const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+    const float p0 = e0 / (e0 + e1);
+    const float g = __ldg(g_up) / (float)B * inv_hw;
+    s_dl[b] = which == 0 ? g * (p0 - 1.f) : g * (1.f - p0);
+  }
+  __syncthreads();
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < CHW; i += (long)gridDim.x * 256) {
+    const float qv = q[i];
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+      float da_, dq_;
+      nce_pair_grad(a[(long)b * CHW + i], qv, k, c0, da_, dq_);
+      acc = fmaf(s_dl[b], dq_, acc);
+    }
+    dq[i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// contrastive D loss backward (one block, O(B^2))
+// ---------------------------------------------------------------------------------------------------------
+__global__ void contrastive_d_bwd_kernel(const float* __restrict__ r, const float* __restrict__ f, int B,
+                                         const float* __restrict__ g_up, float* __restrict__ dr, float* __restrict__ df) {
+  extern __shared__ float s[];  // lse1[B], lse2[B]
+  float* lse1 = s;
+  float* lse2 = s + B;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    float mx = r[i];
+    for (int j = 0; j < B; ++j) mx = fmaxf(mx, f[j]);
+    float sum = expf(r[i] - mx);
+    for (int j = 0; j < B; ++j) sum += expf(f[j] - mx);
+    lse1[i] = mx + logf(sum);
+    mx = -f[i];
+    for (int j = 0; j < B; ++j) mx = fmaxf(mx, -r[j]);
+    sum = expf(-f[i] - mx);
+    for (int j = 0; j < B; ++j) sum += expf(-r[j] - mx);
+    lse2[i] = mx + logf(sum);
+  }
+  __syncthreads();
+  const float g = __ldg(g_up) / (float)B;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    // half 1 rows: [r_i, f_0..f_{B-1}] ; half 2 rows: [-f_i, -r_0..-r_{B-1}]
+    float gr = expf(r[i] - lse1[i]) - 1.f;          // own row of half 1
+    float gf = 1.f - expf(-f[i] - lse2[i]);         // own row of half 2 (d(-f_i)/df_i = -1)
+    for (int j = 0; j < B; ++j) {
+      gf += expf(f[i] - lse1[j]);                   // f_i appears in every row j of half 1
+      gr -= expf(-r[i] - lse2[j]);                  // -r_i appears in every row j of half 2
+    }
+    dr[i] = g * gr;
+    df[i] = g * gf;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-plane mean / mean-local-variance backward
+//   mean = sum x / HW ; cmean = (1/No) sum_o [ (g*x^2)_o - (g*x)_o^2 ]
+//   dx_p = d_mean/HW + d_cmean/No * ( 2 x_p A_p - 2 B_p ),  A_p = sum_{o covers p} g2(p-o),  B_p = sum g2(p-o) mu_o
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) plane_mu_kernel(const float* __restrict__ x, int H, int W, long total,
+                                                      float* __restrict__ mu) {
+  const int Ho = H - 10, Wo = W - 10;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int ox = i % Wo, oy = (i / Wo) % Ho;
+    const long m = i / ((long)Wo * Ho);
+    const float* p = x + m * H * W + (long)oy * W + ox;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 11; ++ky) {
+      float row = 0.f;
+#pragma unroll
+      for (int kx = 0; kx < 11; ++kx) row = fmaf(c_g11[kx], __ldg(p + ky * W + kx), row);
+      acc = fmaf(c_g11[ky], row, acc);
+    }
+    mu[i] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) plane_mean_contrast_bwd_kernel(const float* __restrict__ x, const float* __restrict__ mu,
+                                                                     const float* __restrict__ d_mean,
+                                                                     const float* __restrict__ d_cmean, int H, int W,
+                                                                     long total, float* __restrict__ dx) {
+  const int Ho = H - 10, Wo = W - 10;
+  const float inv_hw = 1.f / (float)((long)H * W), inv_no = 1.f / (float)((long)Ho * Wo);
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int px = i % W, py = (i / W) % H;
+    const long m = i / ((long)W * H);
+    float g = d_mean ? d_mean[m] * inv_hw : 0.f;
+    if (d_cmean) {
+      const float dc = d_cmean[m] * inv_no;
+      float A = 0.f, Bv = 0.f;
+      const float* mp = mu + m * Ho * Wo;
+      for (int ky = 0; ky < 11; ++ky) {
+        const int oy = py - ky;
+        if (oy < 0 || oy >= Ho) continue;
+        float ra = 0.f, rb = 0.f;
+        for (int kx = 0; kx < 11; ++kx) {
+          const int ox = px - kx;
+          if (ox < 0 || ox >= Wo) continue;
+          ra += c_g11[kx];
+          rb = fmaf(c_g11[kx], __ldg(mp + (long)oy * Wo + ox), rb);
+        }
+        A = fmaf(c_g11[ky], ra, A);
+        Bv = fmaf(c_g11[ky], rb, Bv);
+      }
+      g += dc * (2.f * x[i] * A - 2.f * Bv);
+    }
+    dx[i] = g;
+  }
+}
+
+// L1 of two vectors: out = mean |a - b| ; da = g sign(a-b)/n, db = -da
+__global__ void l1_mean_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int n,
+                                   const float* __restrict__ g_up, float* __restrict__ da, float* __restrict__ db) {
+  const float g = __ldg(g_up) / (float)n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float d = a[i] - b[i];
+    const float s = d > 0.f ? g : (d < 0.f ? -g : 0.f);
+    if (da) da[i] = s;
+    if (db) db[i] = -s;
+  }
+}
+
+// TV backward: loss = 2 (sum dh^2 / count_h + sum dw^2 / count_w) / B
+__global__ void __launch_bounds__(256) tv_bwd_kernel(const float* __restrict__ x, int H, int W, long total, float ch,
+                                                    float cw, const float* __restrict__ g_up, float* __restrict__ dx) {
+  const float g = __ldg(g_up);
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int xx = i % W, yy = (i / W) % H;
+    const float v = x[i];
+    float acc = 0.f;
+    if (yy > 0) acc += ch * 2.f * (v - x[i - W]);
+    if (yy + 1 < H) acc -= ch * 2.f * (x[i + W] - v);
+    if (xx > 0) acc += cw * 2.f * (v - x[i - 1]);
+    if (xx + 1 < W) acc -= cw * 2.f * (x[i + 1] - v);
+    dx[i] = g * acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SimpleDiscriminator backward
+// ---------------------------------------------------------------------------------------------------------
+// fea = conv3(a2) + b3, logits = fea . w_tail.  d_fea (in/out): adds d_logits[n] * w_tail[p]; d_w_tail[p] += sum_n d_logits fea
+__global__ void __launch_bounds__(256) disc_tail_bwd_kernel(const float* __restrict__ d_logits, const float* __restrict__ w_tail,
+                                                           const float* __restrict__ fea, float* __restrict__ d_fea,
+                                                           float* __restrict__ d_w_tail, int P, int N) {
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < P; p += gridDim.x * 256) {
+    float acc = 0.f;
+    const float wt = w_tail[p];
+    for (int n = 0; n < N; ++n) {
+      const float dl = d_logits ? d_logits[n] : 0.f;
+      d_fea[(long)n * P + p] += dl * wt;
+      acc = fmaf(dl, fea[(long)n * P + p], acc);
+    }
+    if (d_w_tail) d_w_tail[p] = acc;
+  }
+}
+// d_z2[n][c][p] = d_fea[n][p] * w3[c] * lrelu'(a2) ; dw3[c] += sum d_fea a2[c] ; db3 += sum d_fea
+__global__ void __launch_bounds__(256) disc_top_bwd_kernel(const float* __restrict__ d_fea, const float* __restrict__ a2,
+                                                          const float* __restrict__ w3, float* __restrict__ d_z2,
+                                                          float* __restrict__ dw3, float* __restrict__ db3, int P, int N) {
+  __shared__ float s_acc[33];
+  if (threadIdx.x < 33) s_acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  const long total = (long)N * P;
+  for (long base = (long)blockIdx.x * 256; base < total; base += (long)gridDim.x * 256) {
+    const long i = base + threadIdx.x;
+    const bool valid = i < total;
+    const int p = valid ? (int)(i % P) : 0, n = valid ? (int)(i / P) : 0;
+    const float df = valid ? d_fea[i] : 0.f;
+    float sb = warp_sum(df);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[32], sb);
+    for (int c = 0; c < 32; ++c) {
+      const float av = valid ? a2[((long)n * 32 + c) * P + p] : 0.f;
+      if (valid) d_z2[((long)n * 32 + c) * P + p] = df * __ldg(w3 + c) * (av > 0.f ? 1.f : 0.2f);
+      const float sw = warp_sum(df * av);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[c], sw);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) atomicAdd(dw3 + threadIdx.x, s_acc[threadIdx.x]);
+  if (threadIdx.x == 32) atomicAdd(db3, s_acc[32]);
+}
+// generic 4x4 stride-2 conv weight gradient: dW[co][ci][k] += sum in[n][ci][2oy+ky][2ox+kx] * dz[n][co][oy][ox]; db[co] += sum dz
+// grid (Cout, Cin), block 256
+__global__ void __launch_bounds__(256) conv4s2_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dz,
+                                                           float* __restrict__ dW, float* __restrict__ db, int Cin,
+                                                           int Cout, int Hi, int Wi, int Ho, int Wo, int N) {
+  __shared__ float red[8][17];
+  const int co = blockIdx.x, ci = blockIdx.y;
+  float acc[17];
+#pragma unroll
+  for (int k = 0; k < 17; ++k) acc[k] = 0.f;
+  const long total = (long)N * Ho * Wo;
+  for (long i = threadIdx.x; i < total; i += 256) {
+    const int ox = i % Wo, oy = (i / Wo) % Ho;
+    const long n = i / ((long)Wo * Ho);
+    const float g = dz[((n * Cout + co) * Ho + oy) * Wo + ox];
+    const float* p = in + ((n * Cin + ci) * Hi + 2 * oy) * Wi + 2 * ox;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = fmaf(__ldg(p + (k >> 2) * Wi + (k & 3)), g, acc[k]);
+    acc[16] += g;
+  }
+#pragma unroll
+  for (int k = 0; k < 17; ++k) acc[k] = warp_sum(acc[k]);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < 17; ++k) red[wid][k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < 17) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    if (threadIdx.x < 16) dW[((long)co * Cin + ci) * 16 + threadIdx.x] = s;
+    else if (ci == 0 && db) db[co] = s;
+  }
+}
+// generic 4x4 stride-2 conv data gradient: d_in[n][ci][y][x] = sum_{co,k} dz[n][co][(y-ky)/2][(x-kx)/2] * w[co][ci][k]
+// optionally times lrelu'(act_in) (act_in = the post-LeakyReLU tensor that fed the conv)
+__global__ void __launch_bounds__(256) conv4s2_dgrad_kernel(const float* __restrict__ dz, const float* __restrict__ w,
+                                                           const float* __restrict__ act_in, float* __restrict__ d_in,
+                                                           int Cin, int Cout, int Hi, int Wi, int Ho, int Wo, long total) {
+  extern __shared__ float s_w[];  // [Cout][Cin][16]
+  for (int i = threadIdx.x; i < Cout * Cin * 16; i += 256) s_w[i] = w[i];
+  __syncthreads();
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int x = i % Wi, y = (i / Wi) % Hi, ci = (i / ((long)Wi * Hi)) % Cin;
+    const long n = i / ((long)Wi * Hi * Cin);
+    float acc = 0.f;
+    for (int ky = (y & 1); ky < 4; ky += 2) {
+      const int oy = (y - ky) >> 1;
+      if (y - ky < 0 || oy >= Ho) continue;
+      for (int kx = (x & 1); kx < 4; kx += 2) {
+        const int ox = (x - kx) >> 1;
+        if (x - kx < 0 || ox >= Wo) continue;
+        const float* dp = dz + (n * Cout * Ho + oy) * Wo + ox;
+        for (int co = 0; co < Cout; ++co)
+          acc = fmaf(__ldg(dp + (long)co * Ho * Wo), s_w[(co * Cin + ci) * 16 + ky * 4 + kx], acc);
+      }
+    }
+    if (act_in) acc *= act_in[i] > 0.f ? 1.f : 0.2f;
+    d_in[i] = acc;
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+// d_fake [M][H][W] (written).  scratch floats: >= 6.5 * M*H*W + 64
+extern "C" int uncl_struct_loss_bwd(const float* fake, const float* hdr, int M, int H, int W, int levels,
+                                    const float* weights_host, const float* g_up, float* d_fake, float* scratch,
+                                    cudaStream_t stream) {
+  UNCL_REQUIRE(M > 0 && levels >= 1 && levels <= 4 && (H >> (levels - 1)) >= 5 && (W >> (levels - 1)) >= 5,
+               "struct_loss_bwd: bad arguments");
+  const float* a[4];
+  const float* b[4];
+  float* g[4];
+  int hs[4], ws[4];
+  a[0] = fake; b[0] = hdr; g[0] = d_fake; hs[0] = H; ws[0] = W;
+  float* next = scratch;
+  float* coef = next; next += 4L * M * H * W;
+  for (int l = 1; l < levels; ++l) {
+    hs[l] = hs[l - 1] / 2; ws[l] = ws[l - 1] / 2;
+    const long n = (long)M * hs[l] * ws[l];
+    float* al = next; float* bl = next + n; g[l] = next + 2 * n; next += 3 * n;
+    a[l] = al; b[l] = bl;
+    int rc = uncl_bicubic_half(a[l - 1], al, M, hs[l - 1], ws[l - 1], stream);
+    if (rc) return rc;
+    rc = uncl_bicubic_half(b[l - 1], bl, M, hs[l - 1], ws[l - 1], stream);
+    if (rc) return rc;
+  }
+  for (int l = 0; l < levels; ++l) {
+    const int h = hs[l], w = ws[l];
+    const long plane = (long)M * (h - 4) * (w - 4);
+    const float scale = weights_host[l] / (25.f * (float)plane);
+    struct_coef_kernel<<<dim3(ceil_div(w - 4, 32), ceil_div(h - 4, 16), M), 256, 0, stream>>>(a[l], b[l], h, w, scale, g_up, coef, plane);
+    const long total = (long)M * h * w;
+    struct_grad_kernel<<<cap_grid(total, 256, 8), 256, 0, stream>>>(a[l], b[l], coef, plane, h, w, total, g[l]);
+  }
+  for (int l = levels - 1; l >= 1; --l) {
+    const long total = (long)M * hs[l] * ws[l];
+    bicubic_half_bwd_kernel<<<cap_grid(total, 256, 8), 256, 0, stream>>>(g[l], g[l - 1], hs[l - 1], ws[l - 1], total);
+  }
+  return uncl_check_launch("struct_loss_bwd");
+}
+
+extern "C" int uncl_nce_bwd(const float* anchor, const float* pos, long pos_stride, const float* neg, long neg_stride,
+                            int B, int C, int HW, float k, float constant, const float* logits, const float* g_up,
+                            float* d_anchor, float* d_pos, float* d_neg, cudaStream_t stream) {
+  UNCL_REQUIRE(B > 0 && C > 0 && HW > 0 && d_anchor, "nce_bwd: bad arguments");
+  const long CHW = (long)C * HW;
+  int gx = cap_grid(CHW, 256, 8) / B;
+  if (gx < 1) gx = 1;
+  nce_bwd_kernel<<<dim3(gx, B), 256, 0, stream>>>(anchor, pos, pos_stride, neg, neg_stride, CHW, k, constant, 1.f / (float)HW, logits, B, g_up, d_anchor, d_pos, d_neg);
+  if (d_pos && pos_stride == 0)
+    nce_bwd_bcast_kernel<<<cap_grid(CHW, 256, 8), 256, B * sizeof(float), stream>>>(anchor, pos, CHW, k, constant, 1.f / (float)HW, logits, B, 0, g_up, d_pos);
+  if (d_neg && neg_stride == 0)
+    nce_bwd_bcast_kernel<<<cap_grid(CHW, 256, 8), 256, B * sizeof(float), stream>>>(anchor, neg, CHW, k, constant, 1.f / (float)HW, logits, B, 1, g_up, d_neg);
+  return uncl_check_launch("nce_bwd");
+}
+
+extern "C" int uncl_contrastive_d_bwd(const float* real_logits, const float* fake_logits, int B, const float* g_up,
+                                      float* d_real, float* d_fake, cudaStream_t stream) {
+  UNCL_REQUIRE(B > 0 && B <= 4096, "contrastive_d_bwd: bad batch");
+  contrastive_d_bwd_kernel<<<1, 128, 2 * B * sizeof(float), stream>>>(real_logits, fake_logits, B, g_up, d_real, d_fake);
+  return uncl_check_launch("contrastive_d_bwd");
+}
+
+// mu_scratch: M*(H-10)*(W-10) floats.  d_mean / d_cmean may be NULL.
+extern "C" int uncl_plane_mean_contrast_bwd(const float* x, int M, int H, int W, const float* d_mean, const float* d_cmean,
+                                            float* dx, float* mu_scratch, cudaStream_t stream) {
+  UNCL_REQUIRE(M > 0 && H > 10 && W > 10, "plane_mean_contrast_bwd: bad shape");
+  if (ensure_gauss() != 0) return uncl_set_error(UNCL_ECUDA, "plane_mean_contrast_bwd: constant upload failed");
+  if (d_cmean) {
+    const long to = (long)M * (H - 10) * (W - 10);
+    plane_mu_kernel<<<cap_grid(to, 256, 8), 256, 0, stream>>>(x, H, W, to, mu_scratch);
+  }
+  const long total = (long)M * H * W;
+  plane_mean_contrast_bwd_kernel<<<cap_grid(total, 256, 8), 256, 0, stream>>>(x, mu_scratch, d_mean, d_cmean, H, W, total, dx);
+  return uncl_check_launch("plane_mean_contrast_bwd");
+}
+
+extern "C" int uncl_l1_mean_bwd(const float* a, const float* b, int n, const float* g_up, float* da, float* db,
+                                cudaStream_t stream) {
+  UNCL_REQUIRE(n > 0, "l1_mean_bwd: empty");
+  l1_mean_bwd_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(a, b, n, g_up, da, db);
+  return uncl_check_launch("l1_mean_bwd");
+}
+
+extern "C" int uncl_tv_bwd(const float* x, int B, int C, int H, int W, const float* g_up, float* dx, cudaStream_t stream) {
+  UNCL_REQUIRE(B > 0 && C > 0 && H > 1 && W > 1, "tv_bwd: bad shape");
+  const long total = (long)B * C * H * W;
+  const float ch = 2.f / ((float)((long)(H - 1) * W) * (float)B), cw = 2.f / ((float)((long)H * (W - 1)) * (float)B);
+  tv_bwd_kernel<<<cap_grid(total, 256, 8), 256, 0, stream>>>(x, H, W, total, ch, cw, g_up, dx);
+  return uncl_check_launch("tv_bwd");
+}
+
+// SimpleDiscriminator backward.  Inputs of the forward: x [N][256][256], h1 [N][16][127][127] (post-LReLU),
+// a2 [N][32][62][62] (post-LReLU), fea [N][62][62].  d_fea (in/out): gradient from the feature branch, the tail
+// contribution is added here.  Outputs: dx (NULL to skip) and parameter gradients (dw*, db* zeroed by the caller
+// where accumulated: dw3, db3).  scratch: N*32*62*62 + N*16*127*127 floats.
+extern "C" int uncl_disc_backward(const float* x, const float* h1, const float* a2, const float* fea, const float* w1,
+                                  const float* w2, const float* w3, const float* w_tail, const float* d_logits,
+                                  float* d_fea, float* dx, float* dw1, float* db1, float* dw2, float* db2, float* dw3,
+                                  float* db3, float* dw_tail, float* scratch, int N, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0, "disc_backward: empty batch");
+  const int H = 256, H1 = 127, H2 = 62, P = H2 * H2;
+  float* d_z2 = scratch;
+  float* d_z1 = scratch + (long)N * 32 * P;
+  disc_tail_bwd_kernel<<<ceil_div(P, 256), 256, 0, stream>>>(d_logits, w_tail, fea, d_fea, dw_tail, P, N);
+  disc_top_bwd_kernel<<<cap_grid((long)N * P, 256, 2), 256, 0, stream>>>(d_fea, a2, w3, d_z2, dw3, db3, P, N);
+  conv4s2_wgrad_kernel<<<dim3(32, 16), 256, 0, stream>>>(h1, d_z2, dw2, db2, 16, 32, H1, H1, H2, H2, N);
+  const long t1 = (long)N * 16 * H1 * H1;
+  cudaError_t e = cudaFuncSetAttribute(conv4s2_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 16 * 16 * 4);
+  if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "disc_backward: %s", cudaGetErrorString(e));
+  conv4s2_dgrad_kernel<<<cap_grid(t1, 256, 8), 256, 32 * 16 * 16 * 4, stream>>>(d_z2, w2, h1, d_z1, 16, 32, H1, H1, H2, H2, t1);
+  conv4s2_wgrad_kernel<<<dim3(16, 1), 256, 0, stream>>>(x, d_z1, dw1, db1, 1, 16, H, H, H1, H1, N);
+  if (dx) {
+    const long t0 = (long)N * H * H;
+    conv4s2_dgrad_kernel<<<cap_grid(t0, 256, 8), 256, 16 * 16 * 4, stream>>>(d_z1, w1, nullptr, dx, 1, 16, H, H, H1, H1, t0);
+  }
+  return uncl_check_launch("disc_backward");
+}

@@ -1,4 +1,4 @@
-"""Drop-in SimpleDiscriminator (models/Discriminator.py:87-126), forward on sm_100a kernels.
+"""Drop-in SimpleDiscriminator (models/Discriminator.py:87-126) on sm_100a kernels, forward and backward.
 
 Same constructor signature, `forward(x) -> (output [N,1], fea_final [N,2,1,1])` and state_dict keys
 (`model.0/2/4.{weight,bias}`, `tail.1.weight`).  Only the shipped configuration is built
@@ -7,8 +7,7 @@ Same constructor signature, `forward(x) -> (output [N,1], fea_final [N,2,1,1])` 
 import torch
 import torch.nn as nn
 
-from ._lib import call
-from .features import plane_mean_contrast
+from .autograd_losses import DiscFn, PlaneMeanContrastFn
 
 
 class SimpleDiscriminator(nn.Module):
@@ -21,18 +20,12 @@ class SimpleDiscriminator(nn.Module):
         self.tail = nn.ModuleList([nn.Identity(), nn.Linear(62 * 62, 1, bias=False)])
 
     def forward(self, x):
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("uncltmo_b200 discriminator backward is not built yet: call under torch.no_grad()")
         if x.dim() != 4 or tuple(x.shape[1:]) != (1, 256, 256):
             raise ValueError("SimpleDiscriminator expects [N,1,256,256]")
-        x = x.contiguous().float()
-        n = x.shape[0]
-        h = torch.empty((n, 16, 127, 127), device=x.device, dtype=torch.float32)
-        fea = torch.empty((n, 1, 62, 62), device=x.device, dtype=torch.float32)
-        logits = torch.empty((n, 1), device=x.device, dtype=torch.float32)
+        if not x.is_cuda:
+            raise RuntimeError("uncltmo_b200 has no CPU path: move the input to a CUDA device")
         m = self.model
-        call("uncl_disc_forward", x, m[0].weight.detach().contiguous(), m[0].bias.detach(), m[2].weight.detach().contiguous(),
-             m[2].bias.detach(), m[4].weight.detach().contiguous(), m[4].bias.detach(),
-             self.tail[1].weight.detach().contiguous(), h, fea, logits, n, 256, 256)
-        mean, con = plane_mean_contrast(fea)
+        logits, fea = DiscFn.apply(x, m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias,
+                                   self.tail[1].weight)
+        mean, con = PlaneMeanContrastFn.apply(fea)
         return logits, torch.cat([mean, con], dim=1)[:, :, None, None]

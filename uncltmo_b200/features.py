@@ -8,14 +8,8 @@ def plane_mean_contrast(x, want_mean=True, want_contrast=True):
     """x [..., H, W] fp32 CUDA (dense planes) -> (mean [...], mean local variance [...]).
 
     ContrastExtracter + adaptive_avg_pool2d: models/Discriminator.py:61-83,121-125; Unet.py:112-133,274-278."""
-    x = x.contiguous().float()
-    h, w = x.shape[-2], x.shape[-1]
-    m = x.numel() // (h * w)
-    mean = torch.empty(x.shape[:-2], device=x.device, dtype=torch.float32) if want_mean else None
-    con = torch.empty(x.shape[:-2], device=x.device, dtype=torch.float32) if want_contrast else None
-    scratch = torch.empty(2 * m, device=x.device, dtype=torch.float32)
-    call("uncl_plane_mean_contrast", x, h * w, m, h, w, mean, con, scratch)
-    return mean, con
+    from .autograd_losses import PlaneMeanContrastFn
+    return PlaneMeanContrastFn.apply(x)
 
 
 def contrast_features(up_blocked):

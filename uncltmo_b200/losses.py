@@ -1,45 +1,23 @@
-"""Loss methods of GanTrainer / GanTrainerImg with the reference call signatures, forward on sm_100a kernels.
+"""Loss methods of GanTrainer / GanTrainerImg with the reference call signatures, on sm_100a kernels (fwd + bwd).
 
-Reference: GanTrainerImg.py:219-229 (contrastive_D_loss), :410-439 (nce), :370-382 (infoNCE), :308-313 (mean /
-contrast L1 terms), GanTrainer.py:669-682 (L_TV).  `infoNCE2` / `pseudo_label_loss` choose their positives with a
-host TMQI score (GanTrainerImg.py:341-408); here the selection is passed in as indices (`nce_from_indices`) - the
-on-device TMQI-naturalness score is the next row of SURVEY.md §8(f2).
+Reference: GanTrainerImg.py:219-229 (contrastive_D_loss), :410-439 (nce), :370-382 (infoNCE), :384-408 (infoNCE2),
+:341-368 (pseudo_label_loss), :308-313 (mean / contrast L1 terms), GanTrainer.py:669-682 (L_TV).
+The reference picks the positives / negatives of infoNCE2 and the pseudo label with a HOST numpy TMQI call per image
+(80 calls and a device->host copy per step); here the naturalness score is a kernel and the arg-max stays on the device.
 """
 import torch
 
-from ._lib import call
-from .features import plane_mean_contrast
-
-
-def _scalar(dev):
-    return torch.empty(1, device=dev, dtype=torch.float32)
+from .autograd_losses import (ContrastiveDFn, L1MeanFn, NceFn, PlaneMeanContrastFn, TVFn, tmqi_naturalness)
 
 
 def contrastive_D_loss(real_logits, fake_logits):
-    r = real_logits.reshape(-1).contiguous().float()
-    f = fake_logits.reshape(-1).contiguous().float()
-    out = _scalar(r.device)
-    call("uncl_contrastive_d_loss", r, f, r.numel(), out)
-    return out[0]
+    return ContrastiveDFn.apply(real_logits, fake_logits)
 
 
 def nce(fea_anchor, feas_positive, feas_negative, cl_loss_type, k, constant):
     if cl_loss_type != "InfoNCE" or len(feas_positive) != 1 or len(feas_negative) != 1:
         raise NotImplementedError("only the shipped call pattern (InfoNCE, one positive, one negative) is built")
-    a = fea_anchor.contiguous().float()
-    b, c, h, w = a.shape
-
-    def prep(t):
-        if t.shape[0] == 1 or (t.stride(0) == 0):
-            return t[:1].contiguous().float(), 0
-        return t.contiguous().float(), c * h * w
-
-    p, ps = prep(feas_positive[0])
-    n, ns = prep(feas_negative[0])
-    logits = torch.empty(2 * b, device=a.device, dtype=torch.float32)
-    out = _scalar(a.device)
-    call("uncl_nce_fwd", a, p, ps, n, ns, b, c, h * w, float(k), float(constant), logits, out)
-    return out[0]
+    return NceFn.apply(fea_anchor, feas_positive[0], feas_negative[0], k, constant)
 
 
 def infoNCE(fea_fake, fea_real, fea_neg, fake, hdr_input, cl_loss_type, k, constant):
@@ -47,18 +25,43 @@ def infoNCE(fea_fake, fea_real, fea_neg, fake, hdr_input, cl_loss_type, k, const
 
 
 def nce_from_indices(fea_fake, pos_index, neg_index, cl_loss_type, k, constant):
-    """infoNCE2 after the selection: positive / negative = one sample of the batch, broadcast (GanTrainerImg.py:400-405)."""
-    return nce(fea_fake, [fea_fake[pos_index:pos_index + 1]], [fea_fake[neg_index:neg_index + 1]], cl_loss_type, k, constant)
+    """infoNCE2 after the selection: positive / negative = one sample of the batch, broadcast (GanTrainerImg.py:400-405).
+    pos_index / neg_index: python ints or 0-dim / 1-element device tensors (no host sync in the latter case)."""
+    def pick(i):
+        if torch.is_tensor(i):
+            return fea_fake.index_select(0, i.reshape(1))
+        return fea_fake[i:i + 1]
+    return nce(fea_fake, [pick(pos_index)], [pick(neg_index)], cl_loss_type, k, constant)
+
+
+def infoNCE2(fea_fake, fake, hdr_input, cl_loss_type, k, constant):
+    """GanTrainerImg.py:384-408: positive / negative = the batch samples with the highest / lowest TMQI naturalness."""
+    n = tmqi_naturalness(fake)
+    return nce_from_indices(fea_fake, torch.argmax(n), torch.argmin(n), cl_loss_type, k, constant)
+
+
+def plane_mean_contrast(x):
+    return PlaneMeanContrastFn.apply(x)
 
 
 def l1_mean_terms(fake, ldr):
     """(L1 of per-image means, L1 of per-image mean local variance): GanTrainerImg.py:308-313."""
-    fm, fc = plane_mean_contrast(fake)
-    lm, lc = plane_mean_contrast(ldr)
-    o1, o2 = _scalar(fake.device), _scalar(fake.device)
-    call("uncl_l1_mean", fm.reshape(-1), lm.reshape(-1), fm.numel(), o1)
-    call("uncl_l1_mean", fc.reshape(-1), lc.reshape(-1), fc.numel(), o2)
-    return o1[0], o2[0]
+    fm, fc = PlaneMeanContrastFn.apply(fake)
+    lm, lc = PlaneMeanContrastFn.apply(ldr)
+    return L1MeanFn.apply(fm, lm), L1MeanFn.apply(fc, lc)
+
+
+def pseudo_label_loss(fake, hdr_input):
+    """GanTrainerImg.py:341-368: split every fake into 2x2 quadrants, take the quadrant with the best naturalness as
+    the pseudo label, L1 between all quadrants and the label in mean and in mean local variance."""
+    b = fake.shape[0]
+    ps = fake.shape[-1] // 2
+    patches = fake.reshape(b, 1, 2, ps, 2, ps).permute(0, 2, 4, 1, 3, 5).reshape(b * 4, 1, ps, ps).contiguous()
+    best = torch.argmax(tmqi_naturalness(patches))
+    label = patches.index_select(0, best.reshape(1))
+    pm, pc = PlaneMeanContrastFn.apply(patches)
+    lm, lc = PlaneMeanContrastFn.apply(label)
+    return L1MeanFn.apply(pm, lm.expand_as(pm)) + L1MeanFn.apply(pc, lc.expand_as(pc))
 
 
 class L_TV(torch.nn.Module):
@@ -67,9 +70,4 @@ class L_TV(torch.nn.Module):
         self.TVLoss_weight = TVLoss_weight
 
     def forward(self, x):
-        x = x.contiguous().float()
-        b, c, h, w = x.shape
-        scratch = torch.empty(2, device=x.device, dtype=torch.float32)
-        out = _scalar(x.device)
-        call("uncl_tv_loss", x, b, c, h, w, scratch, out)
-        return self.TVLoss_weight * out[0]
+        return self.TVLoss_weight * TVFn.apply(x)

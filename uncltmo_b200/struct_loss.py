@@ -1,8 +1,8 @@
-"""Drop-in StructLoss (models/struct_loss.py:7-40): pyramid structural loss, forward on an sm_100a stencil kernel."""
+"""Drop-in StructLoss (models/struct_loss.py:7-40): pyramid structural loss on sm_100a stencil kernels (fwd + bwd)."""
 import torch
 import torch.nn as nn
 
-from ._lib import call
+from .autograd_losses import StructLossFn
 
 
 class StructLoss(nn.Module):
@@ -13,20 +13,20 @@ class StructLoss(nn.Module):
             raise NotImplementedError("uncltmo_b200 builds the shipped StructLoss (5x5 window, no frame) only")
         self.pyramid_weight_list = pyramid_weight_list
         self.window_size = window_size
+        self._w_cache = None
+
+    def _weights(self, pyramid_weight_list):
+        # the reference keeps the weights as a (device) tensor; read it once instead of once per step
+        key = id(pyramid_weight_list)
+        if self._w_cache is None or self._w_cache[0] != key:
+            w = pyramid_weight_list.tolist() if torch.is_tensor(pyramid_weight_list) else list(pyramid_weight_list)
+            self._w_cache = (key, [float(v) for v in w])
+        return self._w_cache[1]
 
     def forward(self, fake, hdr_input_original_gray_norm, hdr_input, pyramid_weight_list):
         """The second argument is ignored, as in the reference (struct_loss.py:23,39)."""
-        if torch.is_grad_enabled() and fake.requires_grad:
-            raise NotImplementedError("uncltmo_b200 struct-loss backward is not built yet: call under torch.no_grad()")
         if fake.shape != hdr_input.shape or fake.dim() != 4 or fake.shape[1] != 1:
             raise ValueError("StructLoss expects two [N,1,H,W] tensors of equal shape")
-        w = [float(v) for v in (pyramid_weight_list.tolist() if torch.is_tensor(pyramid_weight_list) else pyramid_weight_list)]
-        n, _, h, wd = fake.shape
-        fake = fake.contiguous().float()
-        hdr = hdr_input.contiguous().float()
-        import ctypes
-        wh = (ctypes.c_float * len(w))(*w)
-        scratch = torch.empty(2 * n * (h // 2) * (wd // 2) * 4 // 3 + 64, device=fake.device, dtype=torch.float32)
-        out = torch.empty(1, device=fake.device, dtype=torch.float32)
-        call("uncl_struct_loss_fwd", fake, hdr, n, h, wd, len(w), ctypes.cast(wh, ctypes.c_void_p).value, out, scratch)
-        return out[0]
+        if not fake.is_cuda:
+            raise RuntimeError("uncltmo_b200 has no CPU path: move the inputs to a CUDA device")
+        return StructLossFn.apply(fake, hdr_input.detach(), self._weights(pyramid_weight_list))

@@ -1,0 +1,97 @@
+"""The training step of GanTrainerImg (image TMO), mirrored on the B200 path.
+
+Reference: GanTrainerImg.py:200-217 (train_D), :231-260 (D_real_fake_pass), :262-292 (train_G), :302-339
+(update_g_d_loss, the epoch-dependent loss schedule), :452-461 (update_struct_loss).  Differences, none of which
+changes a gradient that reaches an optimizer:
+  * the D-step generator forward and the discriminator passes over real images run without an autograd graph
+    (the reference builds the graphs and throws them away; `D(real_neg)` of the D step is computed and never used
+    there - GanTrainerImg.py:237 - and is skipped here);
+  * errG_d and errG_struct are summed and back-propagated once instead of twice with retain_graph=True;
+  * the TMQI naturalness that picks positives / negatives / the pseudo label is computed on the device
+    (the reference makes 80 host numpy calls per step), so a step has no host synchronisation;
+  * the `epoch > epoch_step2` branch uses L_TV from GanTrainer.py:669-682 (the image trainer references an undefined
+    name there).
+"""
+import torch
+
+from . import losses
+from .struct_loss import StructLoss
+
+
+class GanTrainerStep:
+    def __init__(self, netG, netD, optimizerG, optimizerD, loss_g_d_factor=0.1, struct_loss_factor=1.0,
+                 adv_weight_list=(0.2, 0.2, 0.2), pyramid_weight_list=(1.0, 1.0, 1.0), epoch_step1=6, epoch_step2=9):
+        self.netG, self.netD = netG, netD
+        self.optimizerG, self.optimizerD = optimizerG, optimizerD
+        self.loss_g_d_factor = loss_g_d_factor
+        self.struct_loss_factor = struct_loss_factor
+        self.adv_weight_list = [float(a) for a in adv_weight_list]
+        self.pyramid_weight_list = [float(p) for p in pyramid_weight_list]
+        self.epoch_step1, self.epoch_step2 = epoch_step1, epoch_step2
+        self.struct_loss = StructLoss(self.pyramid_weight_list)
+        self.errD = self.errG_d = self.errG_struct = None
+
+    @staticmethod
+    def _flat(t):
+        return t.reshape(-1, t.shape[-3], t.shape[-2], t.shape[-1]).float()
+
+    # ------------------------------------------------------------------ D step
+    def train_D(self, hdr_input, real_ldr_pos, real_ldr_neg, epoch):
+        self.netD.zero_grad(set_to_none=True)
+        d_real_pos, _ = self.netD(self._flat(real_ldr_pos))
+        with torch.no_grad():
+            fake, _ = self.netG(self._flat(hdr_input))
+        d_fake, _ = self.netD(fake.detach())
+        w = self.adv_weight_list[0] * (1.0 if epoch <= self.epoch_step1 else 1e-6)
+        self.errD = w * losses.contrastive_D_loss(d_real_pos, d_fake)
+        self.errD.backward()
+        self.optimizerD.step()
+        return self.errD
+
+    # ------------------------------------------------------------------ G step
+    def g_d_loss(self, d_fake_bp, d_real_pos_bp, d_fea_fake, d_fea_real_pos, d_fea_real_neg, d_fea_input, fea_fake, fake,
+                 hdr_input, ldr_pos, epoch):
+        """update_g_d_loss (GanTrainerImg.py:302-339) without the backward call."""
+        f = self.loss_g_d_factor
+        if epoch <= self.epoch_step2:
+            first = epoch <= self.epoch_step1
+            err = f * (1.0 if first else 1e-6) * losses.contrastive_D_loss(d_fake_bp, d_real_pos_bp)
+            err = err + f * 0.5 * losses.infoNCE(d_fea_fake, d_fea_real_pos, d_fea_input, fake, hdr_input, "InfoNCE", 1, 1e-2)
+            err = err + f * 0.5 * 0.2 * losses.infoNCE(d_fea_fake, d_fea_real_pos, d_fea_real_neg, fake, hdr_input, "InfoNCE", 1e3, 2)
+            err = err + f * (1e-6 if first else 0.5) * losses.infoNCE2(fea_fake, fake, hdr_input, "InfoNCE", 1, 1e-2)
+            l_mean, l_con = losses.l1_mean_terms(fake, ldr_pos)
+            err = err + f * (1e-6 if first else 0.5 * 1e2) * l_mean
+            err = err + f * (1e-6 if first else 0.5 * 2) * l_con
+            err = err + f * 1e-6 * losses.pseudo_label_loss(fake, hdr_input)
+        else:
+            err = f * 1e-6 * losses.contrastive_D_loss(d_fake_bp, d_real_pos_bp)
+            l_mean, _ = losses.l1_mean_terms(fake, ldr_pos)
+            err = err + f * 0.5 * 1e2 * l_mean
+            err = err + f * 0.5 * 1e2 * losses.pseudo_label_loss(fake, hdr_input)
+            err = err + f * 0.2 * 1e5 * losses.L_TV()(fake)
+        return err
+
+    def train_G(self, hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch):
+        self.netG.zero_grad(set_to_none=True)
+        hdr = self._flat(hdr_input)
+        pos, neg = self._flat(real_ldr_pos), self._flat(real_ldr_neg)
+        fake, fea_fake = self.netG(hdr)
+        d_fake_bp, d_fea_fake = self.netD(fake)
+        with torch.no_grad():
+            d_real_pos_bp, d_fea_real_pos = self.netD(pos)
+            _, d_fea_real_neg = self.netD(neg)
+            _, d_fea_input = self.netD(hdr)
+        self.errG_d = self.g_d_loss(d_fake_bp, d_real_pos_bp, d_fea_fake, d_fea_real_pos, d_fea_real_neg, d_fea_input,
+                                    fea_fake, fake, hdr, pos, epoch)
+        total = self.errG_d
+        if self.struct_loss_factor:
+            self.errG_struct = self.struct_loss_factor * self.struct_loss(fake, None, hdr, self.pyramid_weight_list)
+            total = total + self.errG_struct
+        total.backward()
+        self.optimizerG.step()
+        return self.errG_d, self.errG_struct
+
+    def step(self, hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch):
+        """One iteration of GanTrainer.train_epoch's loop body (GanTrainerImg.py:178-186)."""
+        self.train_D(hdr_input, real_ldr_pos, real_ldr_neg, epoch)
+        return self.train_G(hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch)
