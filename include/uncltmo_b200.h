@@ -49,11 +49,13 @@ int uncl_conv3x3_simt(const void* in, long in_img_stride, const float* w, const 
  * w_packed: bf16 [C_in/16][9][2][C_out][8] (see uncltmo_b200/packing.py); bias fp32.
  * fuse_outc=1: apply the 1x1 out conv (outc_w [C_out], outc_b [1]) + sigmoid in the epilogue and write
  * out_img [N][Ho][Wo] fp32 (unet_parts.py:338-345 + nn.Sigmoid, Unet_singleFrame.py:207-209); `out` may then be
- * NULL to skip storing the feature map. */
+ * NULL to skip storing the feature map.  The input is always bf16; `out_dtype` selects bf16 or fp32 stores (the
+ * training path keeps fp32 tensors between the tensor-core convolutions).  The data gradient of a conv is this same
+ * call on the output gradient with the taps reversed / transposed and pad 2 - pad. */
 int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
-                    long out_img_stride, int N, int C_in, int H, int W, int C_out, int pad, int act, int emit_skip,
-                    int fuse_outc, const float* outc_w, const float* outc_b, float* out_img, float* out_logit,
-                    uncl_stream_t stream);
+                    long out_img_stride, int out_dtype, int N, int C_in, int H, int W, int C_out, int pad, int act,
+                    int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b, float* out_img,
+                    float* out_logit, uncl_stream_t stream);
 
 /* up.up: nn.ConvTranspose2d(C, C, 2, stride=2) + bias, written into an (H2 x W2) channel slice of the skip
  * concat buffer with F.pad(..., mode='replicate') semantics.  unet_parts.py:283-299.  w [C][4][C] fp32.
@@ -79,6 +81,9 @@ int uncl_maxpool2(const void* in, long in_img_stride, const void* prev, long pre
  * out / logit: [N][HW] fp32 (logit may be NULL). */
 int uncl_outc_sigmoid(const void* in, long in_img_stride, const float* w, const float* b, float* out, float* logit,
                       int N, int C, int HW, int dtype, uncl_stream_t stream);
+
+/* dense fp32 <-> bf16 conversion of a blocked tensor (n elements, multiple of 8) */
+int uncl_convert(const void* in, int in_dtype, void* out, int out_dtype, long n, uncl_stream_t stream);
 
 /* layout transforms at the module boundary (NCHW fp32 <-> blocked) */
 int uncl_blocked_to_nchw(const void* in, long in_img_stride, float* out, int N, int C, int HW, int dtype,

@@ -1,0 +1,58 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: sharding, gradient buckets, gathered logits."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from uncltmo_b200 import dist as udist
+
+
+def test_shard_range_partitions():
+    for n in (1, 7, 60, 61, 1798):
+        for world in (1, 2, 4, 8):
+            spans = [udist.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert udist.shard_tiles(60, 3, 8) == list(range(24, 32)) and udist.shard_tiles(60, 7, 8) == list(range(53, 60))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(s)) for s in ((300,), (17, 9), (5,), (64, 64))]
+    params[2].requires_grad_(False)
+    for i, p in enumerate(params):
+        if p.requires_grad and i != 1:
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    buckets = udist.GradientBuckets(params, bucket_bytes=1024)   # params[1] has no grad yet: must be treated as zeros
+    buckets.allreduce()
+    ok = all(torch.allclose(params[i].grad, torch.full_like(params[i], 3.0 * (i + 1))) for i in (0, 3))
+    ok = ok and torch.count_nonzero(params[1].grad) == 0 and params[2].grad is None
+    # gathered logits: global loss, local gradient
+    t = torch.tensor([[float(rank)], [float(rank) + 0.5]], requires_grad=True)
+    g = udist.all_gather_cat(t)
+    (g * torch.arange(1, 5.0).view(4, 1)).sum().backward()
+    ok = ok and g.shape == (4, 1) and torch.equal(g.detach().flatten(), torch.tensor([0.0, 0.5, 1.0, 1.5]))
+    ok = ok and torch.equal(t.grad.flatten(), torch.tensor([1.0, 2.0]) + 2.0 * rank)
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_gradient_buckets_and_gather_world2():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert out[0] and out[1]

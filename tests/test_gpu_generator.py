@@ -116,7 +116,7 @@ def test_tcgen05_conv_against_cuda_core_conv(ci, co, h, pad, n):
     ref = torch.empty((n, 4 * co // 8, ho, ho, 8), device="cuda", dtype=torch.bfloat16)
     out = torch.full((n, 4 * co // 8, ho, ho, 8), float("nan"), device="cuda", dtype=torch.bfloat16)
     _lib.call("uncl_conv3x3_simt", x, x.stride(0), w9, b, ref, ref.stride(0), n, ci, h, h, co, pad, 1, 1, _lib.BF16)
-    _lib.call("uncl_conv3x3_tc", x, x.stride(0), packing.conv3x3_tc(w9), b, out, out.stride(0), n, ci, h, h, co, pad,
+    _lib.call("uncl_conv3x3_tc", x, x.stride(0), packing.conv3x3_tc(w9), b, out, out.stride(0), _lib.BF16, n, ci, h, h, co, pad,
               1, 1, 0, None, None, None, None)
     torch.cuda.synchronize()
     used = [0, 2, 3]  # y, y^2, sqrt(y): channel groups written by emit_skip (group 1 belongs to the up-conv)

@@ -40,7 +40,7 @@ def conv_unit_tests():
         ref = torch.empty((n, co // 8, ho, ho, 8), device="cuda", dtype=torch.bfloat16)
         out = torch.full((n, co // 8, ho, ho, 8), float("nan"), device="cuda", dtype=torch.bfloat16)
         _lib.call("uncl_conv3x3_simt", x, x.stride(0), w9, b, ref, ref.stride(0), n, ci, h, h, co, pad, 1, 0, _lib.BF16)
-        _lib.call("uncl_conv3x3_tc", x, x.stride(0), packing.conv3x3_tc(w9), b, out, out.stride(0), n, ci, h, h, co, pad,
+        _lib.call("uncl_conv3x3_tc", x, x.stride(0), packing.conv3x3_tc(w9), b, out, out.stride(0), _lib.BF16, n, ci, h, h, co, pad,
                   1, 0, 0, None, None, None, None)
         torch.cuda.synchronize()
         nan = torch.isnan(out.float()).sum().item()

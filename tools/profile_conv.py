@@ -29,7 +29,7 @@ def run(name, n=60, reps=1):
     for i in range(reps + 1):
         if i == 1:
             e0.record()
-        _lib.call("uncl_conv3x3_tc", x, x.stride(0), wp, b, None if fuse else out, out.stride(0), n, ci, h, h, co, pad, 1,
+        _lib.call("uncl_conv3x3_tc", x, x.stride(0), wp, b, None if fuse else out, out.stride(0), _lib.BF16, n, ci, h, h, co, pad, 1,
                   emit, fuse, ow if fuse else None, ob if fuse else None, img if fuse else None, None)
     e1.record()
     torch.cuda.synchronize()

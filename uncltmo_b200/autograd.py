@@ -47,11 +47,20 @@ class ConvFirst(Function):
         return None, dw.t().reshape(c, 1, 3, 3), db
 
 
+def _to_bf16(t):
+    o = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
+    call("uncl_convert", t, F32, o, _lib.BF16, t.numel())
+    return o
+
+
 class Conv3x3(Function):
-    """nn.Conv2d(k=3, valid) or nn.ConvTranspose2d(k=3, s=1, p=0) (+ReLU).  unet_parts.py:57-87, 126-141, 183-193."""
+    """nn.Conv2d(k=3, valid) or nn.ConvTranspose2d(k=3, s=1, p=0) (+ReLU).  unet_parts.py:57-87, 126-141, 183-193.
+
+    tc=False: fp32 CUDA-core kernels.  tc=True ("mixed" training): forward and data gradient run on the tcgen05
+    kernel with bf16-rounded operands and fp32 accumulation / fp32 outputs; the weight gradient stays fp32."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, transposed, relu):
+    def forward(ctx, x, weight, bias, transposed, relu, tc=False):
         w9 = packing.conv3x3_taps(weight.detach(), transposed)  # [9][C_in][C_out]
         n, cb, h, w, _ = x.shape
         ci, co = w9.shape[1], w9.shape[2]
@@ -59,16 +68,22 @@ class Conv3x3(Function):
         ho, wo = h + 2 * pad - 2, w + 2 * pad - 2
         x = x.contiguous()
         y = _empty((n, co // 8, ho, wo, 8), x)
-        call("uncl_conv3x3_simt", x, x.stride(0), w9, bias.detach().float().contiguous(), y, y.stride(0), n, ci, h, w, co,
-             pad, ACT_RELU if relu else ACT_NONE, 0, F32)
+        b = bias.detach().float().contiguous()
+        act = ACT_RELU if relu else ACT_NONE
+        if tc:
+            xb = _to_bf16(x)
+            call("uncl_conv3x3_tc", xb, xb.stride(0), packing.conv3x3_tc(w9), b, y, y.stride(0), F32, n, ci, h, w, co, pad,
+                 act, 0, 0, None, None, None, None)
+        else:
+            call("uncl_conv3x3_simt", x, x.stride(0), w9, b, y, y.stride(0), n, ci, h, w, co, pad, act, 0, F32)
         ctx.save_for_backward(x, y, w9)
-        ctx.cfg = (transposed, relu, pad)
+        ctx.cfg = (transposed, relu, pad, tc)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, y, w9 = ctx.saved_tensors
-        transposed, relu, pad = ctx.cfg
+        transposed, relu, pad, tc = ctx.cfg
         n, _, h, w, _ = x.shape
         ci, co = w9.shape[1], w9.shape[2]
         ho, wo = y.shape[2], y.shape[3]
@@ -80,15 +95,20 @@ class Conv3x3(Function):
             # dgrad of a correlation with pad p = correlation of dz with pad 2-p and the taps reversed / transposed
             wt = w9.flip(0).transpose(1, 2).contiguous()
             dx = _empty(x.shape, x)
-            call("uncl_conv3x3_simt", dz, dz.stride(0), wt, _zeros(ci, x), dx, dx.stride(0), n, co, ho, wo, ci, 2 - pad,
-                 ACT_NONE, 0, F32)
+            if tc:
+                dzb = _to_bf16(dz)
+                call("uncl_conv3x3_tc", dzb, dzb.stride(0), packing.conv3x3_tc(wt), _zeros(ci, x), dx, dx.stride(0), F32, n,
+                     co, ho, wo, ci, 2 - pad, ACT_NONE, 0, 0, None, None, None, None)
+            else:
+                call("uncl_conv3x3_simt", dz, dz.stride(0), wt, _zeros(ci, x), dx, dx.stride(0), n, co, ho, wo, ci, 2 - pad,
+                     ACT_NONE, 0, F32)
         dw9 = _zeros((9, ci, co), x)
         call("uncl_conv3x3_wgrad", x, x.stride(0), dz, dw9, n, ci, h, w, co, pad)
         if transposed:   # w9[t] = W[:, :, 2-ky, 2-kx]  (W is [C_in, C_out, 3, 3])
             dw = dw9.reshape(3, 3, ci, co).permute(2, 3, 0, 1).flip(2, 3)
         else:            # w9[t] = W[co, ci, ky, kx]
             dw = dw9.reshape(3, 3, ci, co).permute(3, 2, 0, 1)
-        return dx, dw.contiguous(), db, None, None
+        return dx, dw.contiguous(), db, None, None, None
 
 
 class MaxPool2(Function):

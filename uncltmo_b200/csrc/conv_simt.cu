@@ -310,6 +310,16 @@ __global__ void splice_channels_kernel(T* __restrict__ dst, long dst_img_stride,
   }
 }
 
+// dense element-wise dtype conversion (fp32 <-> bf16); n must be a multiple of 8 (blocked tensors always are)
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, long n8) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    float v[8];
+    load8(in + i * 8, v);
+    store8(out + i * 8, v);
+  }
+}
+
 // ================================================================================================
 // C ABI
 // ================================================================================================
@@ -384,4 +394,16 @@ extern "C" int uncl_splice_channels(void* dst, long dst_img_stride, const void* 
   UNCL_REQUIRE(r >= 1 && r <= 8 && N > 0 && HW > 0, "splice_channels: r must be in 1..8");
   UNCL_DISPATCH_DTYPE(dtype, T, (splice_channels_kernel<T><<<grid1d((long)N * HW), 256, 0, stream>>>((T*)dst, dst_img_stride, (const T*)src, src_img_stride, r, HW, N)));
   return uncl_check_launch("splice_channels");
+}
+
+extern "C" int uncl_convert(const void* in, int in_dtype, void* out, int out_dtype, long n, cudaStream_t stream) {
+  UNCL_REQUIRE(n > 0 && n % 8 == 0, "convert: element count must be a positive multiple of 8");
+  const long n8 = n / 8;
+  if (in_dtype == UNCL_F32 && out_dtype == UNCL_BF16)
+    convert_kernel<float, bf16><<<grid1d(n8), 256, 0, stream>>>((const float*)in, (bf16*)out, n8);
+  else if (in_dtype == UNCL_BF16 && out_dtype == UNCL_F32)
+    convert_kernel<bf16, float><<<grid1d(n8), 256, 0, stream>>>((const bf16*)in, (float*)out, n8);
+  else
+    return uncl_set_error(UNCL_EINVAL, "convert: unsupported dtype pair %d -> %d", in_dtype, out_dtype);
+  return uncl_check_launch("convert");
 }

@@ -33,7 +33,8 @@ constexpr int kMaxStages = 6;
 struct TcParams {
   const bf16* w;            // packed weights [NS][nchunk][ntaps][2][NT][8]
   const float* bias;        // [C_out]
-  bf16* out;                // blocked output (may be null when fuse_outc)
+  void* out;                // blocked output, bf16 or fp32 (may be null when fuse_outc)
+  int out_f32;              // 1: `out` is fp32 (training path: fp32 tensors between the tensor-core convs)
   long out_img_stride;
   const float* outc_w;      // [C_out] (fuse_outc)
   const float* outc_b;
@@ -316,7 +317,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const long skip2 = (long)(2 * (C_out / 8)) * cb_stride, skip3 = (long)(3 * (C_out / 8)) * cb_stride;
     const float act_floor = (p.act == UNCL_ACT_RELU) ? 0.f : -INFINITY;   // ReLU or identity, branch-free
     const bool emit_skip = p.emit_skip != 0, fuse_outc = p.fuse_outc != 0;
-    bf16* const out = p.out;
+    bf16* const out = reinterpret_cast<bf16*>(p.out);
+    float* const outf = reinterpret_cast<float*>(p.out);
+    const bool out_f32 = p.out_f32 != 0;
     const long out_img_stride = p.out_img_stride;
     float* const out_img = p.out_img;
     float* const out_logit = p.out_logit;
@@ -330,7 +333,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       tc_fence_after();
       if constexpr (EPI == 0) {
         const int cbase0 = it.ns * NT;
-        bf16* const out_n = out + (long)it.n * out_img_stride + (long)(cbase0 / 8) * cb_stride;
         for (int b = bpar; b < it.mb_act; b += 2) {
           const int q = it.q0 + b * 128 + row;
           const int oy = q / geo.PW, xl = q - oy * geo.PW;
@@ -349,16 +351,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[g * 8 + j]) + bias[g * 8 + j], act_floor);
                 if (out != nullptr) {
-                  bf16* o = out_n + (long)(c0 / 8 + g) * cb_stride + pix * 8;
-                  store8(o, v);
+                  const long off = (long)it.n * out_img_stride + (long)(cbase0 / 8 + c0 / 8 + g) * cb_stride + pix * 8;
+                  float s2[8], s3[8];
                   if (emit_skip) {
-                    float s2[8];
-  #pragma unroll
-                    for (int j = 0; j < 8; ++j) s2[j] = v[j] * v[j];
-                    store8(o + skip2, s2);
-  #pragma unroll
-                    for (int j = 0; j < 8; ++j) s2[j] = sqrtf(v[j] + 1e-8f);
-                    store8(o + skip3, s2);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { s2[j] = v[j] * v[j]; s3[j] = sqrtf(v[j] + 1e-8f); }
+                  }
+                  if (out_f32) {
+                    store8(outf + off, v);
+                    if (emit_skip) { store8(outf + off + skip2, s2); store8(outf + off + skip3, s3); }
+                  } else {
+                    store8(out + off, v);
+                    if (emit_skip) { store8(out + off + skip2, s2); store8(out + off + skip3, s3); }
                   }
                 }
                 if (fuse_outc) {
@@ -502,21 +506,23 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
 }  // namespace
 
 extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
-                               long out_img_stride, int N, int C_in, int H, int W, int C_out, int pad, int act,
-                               int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b, float* out_img,
-                               float* out_logit, cudaStream_t stream) {
+                               long out_img_stride, int out_dtype, int N, int C_in, int H, int W, int C_out, int pad,
+                               int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
+                               float* out_img, float* out_logit, cudaStream_t stream) {
   UNCL_REQUIRE(N > 0 && C_in % 16 == 0 && C_out % 32 == 0 && (pad == 0 || pad == 2),
                "conv3x3_tc: unsupported C_in=%d C_out=%d pad=%d", C_in, C_out, pad);
   TcParams p{};
   p.NT = C_out < 128 ? C_out : 128;
-  UNCL_REQUIRE(C_out % p.NT == 0 && C_out <= 256, "conv3x3_tc: unsupported C_out=%d", C_out);
+  UNCL_REQUIRE(C_out % p.NT == 0 && C_out <= 1024, "conv3x3_tc: unsupported C_out=%d", C_out);
+  UNCL_REQUIRE(out_dtype == UNCL_F32 || out_dtype == UNCL_BF16, "conv3x3_tc: bad out_dtype");
   UNCL_REQUIRE(!fuse_outc || (C_out == p.NT && outc_w && outc_b && out_img), "conv3x3_tc: fuse_outc needs C_out<=128 and outc params");
   UNCL_REQUIRE(out != nullptr || fuse_outc, "conv3x3_tc: no output requested");
   UNCL_REQUIRE(act == UNCL_ACT_RELU || act == UNCL_ACT_NONE, "conv3x3_tc: only ReLU / identity epilogues are built");
   p.NS = C_out / p.NT;
   p.w = reinterpret_cast<const bf16*>(w_packed);
   p.bias = bias;
-  p.out = reinterpret_cast<bf16*>(out);
+  p.out = out;
+  p.out_f32 = out_dtype == UNCL_F32;
   p.out_img_stride = out_img_stride;
   p.outc_w = outc_w; p.outc_b = outc_b; p.out_img = out_img; p.out_logit = out_logit;
   p.N = N; p.C_in = C_in; p.C_out = C_out; p.pad = pad;
@@ -538,7 +544,7 @@ extern "C" int uncl_convT2x2_tc(const void* in, long in_img_stride, const void* 
   p.NS = n_total / p.NT;
   p.w = reinterpret_cast<const bf16*>(w_packed);
   p.bias = bias;
-  p.out = reinterpret_cast<bf16*>(out);
+  p.out = out;
   p.out_img_stride = out_img_stride;
   p.N = N; p.C_in = C; p.C_out = C; p.pad = 0;
   p.Ho = H; p.Wo = W;

@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(256) disc_top_bwd_kernel(const float* __restri
   if (threadIdx.x == 32) atomicAdd(db3, s_acc[32]);
 }
 // generic 4x4 stride-2 conv weight gradient: dW[co][ci][k] += sum in[n][ci][2oy+ky][2ox+kx] * dz[n][co][oy][ox]; db[co] += sum dz
-// grid (Cout, Cin), block 256
+// grid (Cout, Cin, pixel split), block 256; dW / db are accumulated with atomics (zeroed by the caller)
 __global__ void __launch_bounds__(256) conv4s2_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dz,
                                                            float* __restrict__ dW, float* __restrict__ db, int Cin,
                                                            int Cout, int Hi, int Wi, int Ho, int Wo, int N) {
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(256) conv4s2_wgrad_kernel(const float* __restr
 #pragma unroll
   for (int k = 0; k < 17; ++k) acc[k] = 0.f;
   const long total = (long)N * Ho * Wo;
-  for (long i = threadIdx.x; i < total; i += 256) {
+  for (long i = (long)blockIdx.z * 256 + threadIdx.x; i < total; i += (long)gridDim.z * 256) {
     const int ox = i % Wo, oy = (i / Wo) % Ho;
     const long n = i / ((long)Wo * Ho);
     const float g = dz[((n * Cout + co) * Ho + oy) * Wo + ox];
@@ -387,8 +387,8 @@ __global__ void __launch_bounds__(256) conv4s2_wgrad_kernel(const float* __restr
   if (threadIdx.x < 17) {
     float s = 0.f;
     for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    if (threadIdx.x < 16) dW[((long)co * Cin + ci) * 16 + threadIdx.x] = s;
-    else if (ci == 0 && db) db[co] = s;
+    if (threadIdx.x < 16) atomicAdd(dW + ((long)co * Cin + ci) * 16 + threadIdx.x, s);
+    else if (ci == 0 && db) atomicAdd(db + co, s);
   }
 }
 // generic 4x4 stride-2 conv data gradient: d_in[n][ci][y][x] = sum_{co,k} dz[n][co][(y-ky)/2][(x-kx)/2] * w[co][ci][k]
@@ -527,12 +527,12 @@ extern "C" int uncl_disc_backward(const float* x, const float* h1, const float* 
   float* d_z1 = scratch + (long)N * 32 * P;
   disc_tail_bwd_kernel<<<ceil_div(P, 256), 256, 0, stream>>>(d_logits, w_tail, fea, d_fea, dw_tail, P, N);
   disc_top_bwd_kernel<<<cap_grid((long)N * P, 256, 2), 256, 0, stream>>>(d_fea, a2, w3, d_z2, dw3, db3, P, N);
-  conv4s2_wgrad_kernel<<<dim3(32, 16), 256, 0, stream>>>(h1, d_z2, dw2, db2, 16, 32, H1, H1, H2, H2, N);
+  conv4s2_wgrad_kernel<<<dim3(32, 16, 4), 256, 0, stream>>>(h1, d_z2, dw2, db2, 16, 32, H1, H1, H2, H2, N);
   const long t1 = (long)N * 16 * H1 * H1;
   cudaError_t e = cudaFuncSetAttribute(conv4s2_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 16 * 16 * 4);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "disc_backward: %s", cudaGetErrorString(e));
   conv4s2_dgrad_kernel<<<cap_grid(t1, 256, 8), 256, 32 * 16 * 16 * 4, stream>>>(d_z2, w2, h1, d_z1, 16, 32, H1, H1, H2, H2, t1);
-  conv4s2_wgrad_kernel<<<dim3(16, 1), 256, 0, stream>>>(x, d_z1, dw1, db1, 1, 16, H, H, H1, H1, N);
+  conv4s2_wgrad_kernel<<<dim3(16, 1, 64), 256, 0, stream>>>(x, d_z1, dw1, db1, 1, 16, H, H, H1, H1, N);
   if (dx) {
     const long t0 = (long)N * H * H;
     conv4s2_dgrad_kernel<<<cap_grid(t0, 256, 8), 256, 16 * 16 * 4, stream>>>(d_z1, w1, nullptr, dx, 1, 16, H, H, H1, H1, t0);

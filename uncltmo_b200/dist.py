@@ -1,0 +1,80 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), NCCL over NVLink for the only collective the path needs.
+
+* Inference: image frames (and tiles) are independent - ranks take disjoint frames, no collective.
+  Video scenes shard by TILE CHAIN, not by frame: the generator hands channel slices from frame k-1 to frame k of the
+  same tile (Unet.py:229-286), so a rank owns a subset of the tiles for all frames of the scene.
+* Training: data parallel over the batch; gradients are summed with bucketed all-reduces.  The reference's
+  counterpart is nn.DataParallel (utils/model_save_util.py:50-54), i.e. scatter / replicate / gather every step.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world):
+    """Contiguous, balanced [begin, end) of n items for `rank` (the first n % world ranks get one extra)."""
+    base, extra = divmod(n, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def shard_tiles(ntiles, rank, world):
+    """Tile-chain ownership for a video scene."""
+    return list(range(*shard_range(ntiles, rank, world)))
+
+
+class GradientBuckets:
+    """Flat fp32 buckets over a parameter list, built in REVERSE registration order (decoder first: the order
+    in which backward produces gradients), all-reduced (sum) with one collective per bucket."""
+
+    def __init__(self, params, bucket_bytes=8 << 20):
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets, cur, size = [], [], 0
+        for p in reversed(self.params):
+            cur.append(p)
+            size += p.numel() * 4
+            if size >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self._flat = None
+
+    def allreduce(self, group=None, average=False, async_op=False):
+        """Sum (or average) .grad over the process group.  Returns the list of work handles if async_op."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return []
+        world = dist.get_world_size(group)
+        works, flats = [], []
+        for bucket in self.buckets:
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True))
+            flats.append((flat, bucket))
+        for w in works:
+            w.wait()
+        for flat, bucket in flats:
+            if average:
+                flat /= world
+            off = 0
+            for p in bucket:
+                n = p.numel()
+                g = flat[off:off + n].view_as(p)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+                off += n
+        return works
+
+
+def all_gather_cat(t, group=None):
+    """Concatenate a small per-rank tensor over ranks along dim 0 (logits / naturalness scores of the global batch).
+    The local slice keeps its autograd history; the remote slices are constants - each rank differentiates the global
+    loss with respect to its own samples and the gradient all-reduce adds the pieces up."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return t
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t.detach().contiguous(), group=group)
+    parts[rank] = t
+    return torch.cat(parts, dim=0)

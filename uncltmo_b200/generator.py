@@ -157,11 +157,11 @@ class _GeneratorBase(nn.Module):
         wt, b = P[name]
         if self.precision == "bf16":
             if fuse is None:
-                call("uncl_conv3x3_tc", src, src_stride, wt, b, dst, dst_stride, n, ci, h, w, co, pad, ACT_RELU,
+                call("uncl_conv3x3_tc", src, src_stride, wt, b, dst, dst_stride, _lib.BF16, n, ci, h, w, co, pad, ACT_RELU,
                      emit_skip, 0, None, None, None, None)
             else:
                 ow, ob, out_img, out_logit = fuse
-                call("uncl_conv3x3_tc", src, src_stride, wt, b, dst, dst_stride, n, ci, h, w, co, pad, ACT_RELU,
+                call("uncl_conv3x3_tc", src, src_stride, wt, b, dst, dst_stride, _lib.BF16, n, ci, h, w, co, pad, ACT_RELU,
                      emit_skip, 1, ow, ob, out_img, out_logit)
         else:
             call("uncl_conv3x3_simt", src, src_stride, wt, b, dst, dst_stride, n, ci, h, w, co, pad, ACT_RELU,
@@ -327,22 +327,22 @@ class UNet(_GeneratorBase):
 
     def _forward_train(self, x, droppath_scale=None):
         """Same network as _run_frame, built from autograd Functions whose forward and backward are library kernels.
-        fp32 path only this round (the tensor-core backward is next)."""
+        precision 'fp32': CUDA-core kernels throughout (gradient parity 1e-3 vs the float64 oracle).
+        precision 'bf16': "mixed" - the 3x3 convolutions (forward and data gradient) run on the tcgen05 kernel with
+        bf16-rounded operands and fp32 accumulation; every tensor between kernels and every weight gradient is fp32."""
         from . import autograd as A
-        if self.precision != "fp32":
-            raise NotImplementedError("training (autograd) runs on the fp32 path this round: construct the generator "
-                                      "with precision='fp32'")
+        tc = self.precision == "bf16"   # mixed: tensor-core conv forward / data gradient, fp32 tensors and weight gradients
         if x.dim() != 4 or tuple(x.shape[1:]) != (1, 256, 256) or not x.is_cuda:
             raise ValueError("the generator expects CUDA [N,1,256,256] inputs")
         n = x.shape[0]
         c = self.inc.conv
         a0 = A.ConvFirst.apply(x, c.conv.weight, c.conv.bias)
-        cur = A.Conv3x3.apply(a0, c.conv1.weight, c.conv1.bias, False, True)
+        cur = A.Conv3x3.apply(a0, c.conv1.weight, c.conv1.bias, False, True, tc)
         skips = [cur]
         for i in range(4):
             blk = self.down_path[i].mpconv[1]
-            m = A.Conv3x3.apply(A.MaxPool2.apply(cur), blk.conv.weight, blk.conv.bias, False, True)
-            cur = A.Conv3x3.apply(m, blk.conv1.weight, blk.conv1.bias, i == 3, True)
+            m = A.Conv3x3.apply(A.MaxPool2.apply(cur), blk.conv.weight, blk.conv.bias, False, True, tc)
+            cur = A.Conv3x3.apply(m, blk.conv1.weight, blk.conv1.bias, i == 3, True, tc)
             skips.append(cur)
         g, ffn = self.gcn.module[0][0], self.gcn.module[0][1]
         s0 = droppath_scale[0] if droppath_scale is not None else None
@@ -360,8 +360,8 @@ class UNet(_GeneratorBase):
             sk = skips[3 - i]
             x1u = A.ConvT2x2.apply(up, u.up.weight, u.up.bias, sk.shape[2], sk.shape[3])
             cat = A.SkipConcat.apply(sk, x1u)
-            m = A.Conv3x3.apply(cat, u.conv.conv.weight, u.conv.conv.bias, True, True)
-            up = A.Conv3x3.apply(m, u.conv.conv1.weight, u.conv.conv1.bias, True, True)
+            m = A.Conv3x3.apply(cat, u.conv.conv.weight, u.conv.conv.bias, True, True, tc)
+            up = A.Conv3x3.apply(m, u.conv.conv1.weight, u.conv.conv1.bias, True, True, tc)
         out = A.OutcSigmoid.apply(up, self.outc.conv.weight, self.outc.conv.bias)
         return out, A.BlockedToNCHW.apply(up)
 

@@ -11,10 +11,18 @@ changes a gradient that reaches an optimizer:
     (the reference makes 80 host numpy calls per step), so a step has no host synchronisation;
   * the `epoch > epoch_step2` branch uses L_TV from GanTrainer.py:669-682 (the image trainer references an undefined
     name there).
+
+Multi-GPU (one process per GPU, torch.distributed initialised): every rank takes an equal slice of the global batch.
+Per-sample-mean losses are scaled by 1/world and gradients are SUMMED over ranks with bucketed NCCL all-reduces
+(uncltmo_b200.dist.GradientBuckets) - the reference's counterpart is nn.DataParallel.  The all-pairs contrastive loss
+sees the all-gathered logits of the global batch.  The TMQI selections of infoNCE2 / pseudo_label_loss are made within
+a rank's slice when world > 1 (their loss weight is 1e-7 for epoch <= 6): a stated deviation from global-batch semantics.
 """
 import torch
+import torch.distributed as dist
 
 from . import losses
+from .dist import GradientBuckets, all_gather_cat
 from .struct_loss import StructLoss
 
 
@@ -30,6 +38,9 @@ class GanTrainerStep:
         self.epoch_step1, self.epoch_step2 = epoch_step1, epoch_step2
         self.struct_loss = StructLoss(self.pyramid_weight_list)
         self.errD = self.errG_d = self.errG_struct = None
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.buckets_G = GradientBuckets(netG.parameters()) if self.world > 1 else None
+        self.buckets_D = GradientBuckets(netD.parameters()) if self.world > 1 else None
 
     @staticmethod
     def _flat(t):
@@ -43,8 +54,10 @@ class GanTrainerStep:
             fake, _ = self.netG(self._flat(hdr_input))
         d_fake, _ = self.netD(fake.detach())
         w = self.adv_weight_list[0] * (1.0 if epoch <= self.epoch_step1 else 1e-6)
-        self.errD = w * losses.contrastive_D_loss(d_real_pos, d_fake)
+        self.errD = w * losses.contrastive_D_loss(all_gather_cat(d_real_pos), all_gather_cat(d_fake))
         self.errD.backward()
+        if self.buckets_D is not None:
+            self.buckets_D.allreduce()
         self.optimizerD.step()
         return self.errD
 
@@ -53,9 +66,12 @@ class GanTrainerStep:
                  hdr_input, ldr_pos, epoch):
         """update_g_d_loss (GanTrainerImg.py:302-339) without the backward call."""
         f = self.loss_g_d_factor
+        s = 1.0 / self.world   # per-sample-mean terms: local mean * (local / global batch)
+        gathered = losses.contrastive_D_loss(all_gather_cat(d_fake_bp), all_gather_cat(d_real_pos_bp))
         if epoch <= self.epoch_step2:
             first = epoch <= self.epoch_step1
-            err = f * (1.0 if first else 1e-6) * losses.contrastive_D_loss(d_fake_bp, d_real_pos_bp)
+            err = f * (1.0 if first else 1e-6) * gathered
+            f = f * s
             err = err + f * 0.5 * losses.infoNCE(d_fea_fake, d_fea_real_pos, d_fea_input, fake, hdr_input, "InfoNCE", 1, 1e-2)
             err = err + f * 0.5 * 0.2 * losses.infoNCE(d_fea_fake, d_fea_real_pos, d_fea_real_neg, fake, hdr_input, "InfoNCE", 1e3, 2)
             err = err + f * (1e-6 if first else 0.5) * losses.infoNCE2(fea_fake, fake, hdr_input, "InfoNCE", 1, 1e-2)
@@ -64,7 +80,8 @@ class GanTrainerStep:
             err = err + f * (1e-6 if first else 0.5 * 2) * l_con
             err = err + f * 1e-6 * losses.pseudo_label_loss(fake, hdr_input)
         else:
-            err = f * 1e-6 * losses.contrastive_D_loss(d_fake_bp, d_real_pos_bp)
+            err = f * 1e-6 * gathered
+            f = f * s
             l_mean, _ = losses.l1_mean_terms(fake, ldr_pos)
             err = err + f * 0.5 * 1e2 * l_mean
             err = err + f * 0.5 * 1e2 * losses.pseudo_label_loss(fake, hdr_input)
@@ -85,9 +102,11 @@ class GanTrainerStep:
                                     fea_fake, fake, hdr, pos, epoch)
         total = self.errG_d
         if self.struct_loss_factor:
-            self.errG_struct = self.struct_loss_factor * self.struct_loss(fake, None, hdr, self.pyramid_weight_list)
+            self.errG_struct = (self.struct_loss_factor / self.world) * self.struct_loss(fake, None, hdr, self.pyramid_weight_list)
             total = total + self.errG_struct
         total.backward()
+        if self.buckets_G is not None:
+            self.buckets_G.allreduce()
         self.optimizerG.step()
         return self.errG_d, self.errG_struct
 
