@@ -47,7 +47,7 @@ CONFIG = {"workload": "image TMO inference, one 1920x1080 HDR frame per step per
           "l2": "3 frames rotate per rank and each step writes/reads >2 GB of activations (>> 126 MB L2), "
                 "so no input survives in L2 between steps",
           "parallelism": "frames sharded over ranks, no collective",
-          "not_built_yet": "training step (backward kernels): 256^2 train steps/s is not reported this round"}
+          "second_metric": "256^2 train steps/s is reported in the `train` object of the same line"}
 G_ARGS = (1, 1, "sigmoid", 4, 4, "square_and_square_root", 32, 0, "unet", 0, 0, "none", "none", "relu", 1, "replicate", 2)
 
 
@@ -135,6 +135,98 @@ def cpu_reference_arm(steps, warmup, threads=None):
             "ms_per_tile": t_tile * 1e3, "rest_s": t_rest}, float(np.sum(times)) + t_rest
 
 
+TRAIN_GFLOP_STEP = 4 * GFLOP_TILE * 16   # G fwd (D step) + G fwd (G step) + one merged backward, 16 images
+
+
+def train_workload(dev, precision, steps, warmup, world=1, rank=0):
+    """256x256 image-TMO training step, global batch 8x2 = 16 images (GanTrainerImg.train_D + train_G, epoch-0 loss
+    schedule, Adam as main_train_image.py builds it).  Strong scaling: ranks split the 16 images."""
+    from uncltmo_b200 import _lib, synth
+    from uncltmo_b200.discriminator import SimpleDiscriminator
+    from uncltmo_b200.generator import UNet
+    from uncltmo_b200.trainer import GanTrainerStep
+    from uncltmo_b200.weights import make_discriminator_state_dict, make_generator_state_dict
+    import torch.distributed as dist
+    netG = UNet(*G_ARGS, up_mode=0, precision=precision).to(dev).train()
+    netG.load_state_dict(make_generator_state_dict())
+    netD = SimpleDiscriminator(256, 1, 16, "none", "none", 0, 0).to(dev).train()
+    netD.load_state_dict(make_discriminator_state_dict())
+    optG = torch.optim.Adam([p for p in netG.parameters() if p.requires_grad], lr=1e-5, betas=(0.5, 0.999))
+    optD = torch.optim.Adam(netD.parameters(), lr=1.5e-5, betas=(0.5, 0.999))
+    tr = GanTrainerStep(netG, netD, optG, optD)
+    b_local = max(1, 8 // world)
+    mk = lambda a: torch.from_numpy(a).reshape(b_local, 2, 1, 256, 256)  # noqa: E731
+    host = [(mk(synth.normalised_batch(2 * b_local, seed=40 + 10 * rank + i)).pin_memory(),
+             mk(synth.ldr_batch(2 * b_local, seed=50 + 10 * rank + i)).pin_memory(),
+             mk(synth.ldr_batch(2 * b_local, seed=60 + 10 * rank + i)).pin_memory()) for i in range(2)]
+    devb = [tuple(t.to(dev) for t in h) for h in host]
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(fn):
+        for i in range(warmup):
+            fn(i)
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    def resident(i):
+        h, p, n = devb[i % 2]
+        tr.step(h, None, p, n, 0)
+
+    loss_host = torch.empty(2).pin_memory()
+
+    def e2e(i):
+        h, p, n = (t.to(dev, non_blocking=True) for t in host[i % 2])
+        g, s = tr.step(h, None, p, n, 0)
+        loss_host.copy_(torch.stack([g.detach(), s.detach()]), non_blocking=True)
+
+    _lib.reset_launch_count()
+    ms = run(resident)
+    launches = _lib.launch_count() * steps // (steps + warmup)
+    ms_e2e = run(e2e)
+    bytes_in = 3 * b_local * 2 * 256 * 256 * 4
+    return {"metric": "256^2 train steps/s (16 images/step: train_D + train_G)", "value": steps / (ms / 1e3), "unit": "steps/s",
+            "ms_per_step": ms / steps, "scaling": "strong", "dtype": "f32" if precision == "fp32" else "bf16 operands / f32 tensors (mixed)",
+            "tflops_algorithmic": steps * TRAIN_GFLOP_STEP / ms, "gpu_launches": launches,
+            "e2e": {"value": steps / (ms_e2e / 1e3), "unit": "steps/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 8},
+            "config": {"global_batch": "8 x 2 crops = 16 images of 256x256", "per_gpu_images": 2 * b_local, "loss_schedule": "epoch 0",
+                       "optimizer": "Adam(lr 1e-5 / 1.5e-5, betas (0.5, 0.999))", "parallelism": "dp%d, NCCL gradient all-reduce" % world}}
+
+
+def cpu_train_arm(threads=None):
+    """The CPU oracle's training step (same schedule, torch autograd on the host cores) on a 2-image sample, x8."""
+    import oracle
+    from uncltmo_b200 import synth
+    from uncltmo_b200.weights import make_discriminator_state_dict, make_generator_state_dict
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    g_sd, d_sd = make_generator_state_dict(), make_discriminator_state_dict()
+    hdr = torch.from_numpy(synth.normalised_batch(2, seed=4))
+    pos, neg = torch.from_numpy(synth.ldr_batch(2, seed=5)), torch.from_numpy(synth.ldr_batch(2, seed=6))
+    with torch.enable_grad():
+        oracle.train_step_losses(g_sd, d_sd, hdr, pos, neg, 0)
+        t0 = time.perf_counter()
+        oracle.train_step_losses(g_sd, d_sd, hdr, pos, neg, 0)
+        dt = time.perf_counter() - t0
+    return {"value": 1.0 / (8 * dt), "unit": "steps/s", "cores": threads, "kind": "port",
+            "sample": "one D+G step of the oracle on 2 of the 16 images (%.2f s), x8" % dt}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -158,6 +250,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
+    ap.add_argument("--train-precision", default="bf16", choices=["bf16", "fp32"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -261,6 +355,19 @@ def main():
                     "share_of_step": tc_ms / sum(tot.values()),
                     "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
 
+    train = None
+    if not args.no_train:
+        net = pipe = None
+        dev_frames = None
+        torch.cuda.empty_cache()
+        with torch.enable_grad():
+            train = train_workload(dev, args.train_precision, max(5, args.steps // 2), args.warmup, world, rank)
+            exact = train_workload(dev, "fp32", 5, 3, 1, 0) if world == 1 else None
+        if exact is not None:
+            train["fp32_exact_path"] = {"value": exact["value"], "unit": "steps/s", "ms_per_step": exact["ms_per_step"]}
+            if not args.no_cpu_baseline:
+                train["cpu_baseline"] = cpu_train_arm()
+
     if rank == 0:
         base = None
         if world == 1 and not args.no_cpu_baseline:
@@ -274,7 +381,7 @@ def main():
                 "tflops_generator": world * args.steps * TILES * GFLOP_TILE / ms_res,
                 "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": "frames/s",
                         "h2d_bytes_per_step": 3 * H * W * 4, "d2h_bytes_per_step": H * W * 3},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": base, "clocks": clocks}
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": base, "clocks": clocks, "train": train}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
