@@ -251,6 +251,18 @@ int uncl_disc_backward(const float* x, const float* h1, const float* a2, const f
                        float* dx, float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3,
                        float* dw_tail, float* scratch, int N, uncl_stream_t stream);
 
+/* ---- off-default-path operators ---- */
+
+/* adaptive_lambda.cross_entropy (utils/adaptive_lambda.py:7-21) for a population of L candidate lambdas at once:
+ * log10(g*lambda+1)/max -> `bins`-bin density histogram over [0,1] -> cross entropy against `targets`.
+ * lambdas: L doubles on the device.  workspace: (L*bins + 4)*4 bytes. */
+int uncl_lambda_cross_entropy(const float* gray, long n, const double* lambdas, int L, const float* targets, int bins,
+                              float* ce_out, void* workspace, uncl_stream_t stream);
+/* models/Blocks.py:77-138 on a dense [N][per] tensor.  mode: 0 Exp, 1 MySig(param), 2 Clip, 3 MaxNormalization,
+ * 4 MaxNormalizationEpsilon, 5 BatchMaxNormalization, 6 MinMaxNormalization.  scratch: 2*N floats. */
+int uncl_blocks_apply(const float* x, float* out, int N, long per, int mode, float param, float* scratch,
+                      uncl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

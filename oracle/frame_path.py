@@ -139,3 +139,11 @@ def tonemap_frame(rgb, lam, model_fn, factor_coeff=0.1):
     g_p, _, _ = resize_im(g)
     fake = tile_and_blend(g_p[None], model_fn)
     return postprocess_frame(fake, rgb_p, dy, dx)
+
+
+def lambda_cross_entropy(factor, gray_im, targets, bins_):
+    """utils/adaptive_lambda.py:7-21 (numpy)."""
+    g = np.log10(np.asarray(gray_im) * factor + 1)
+    g = g / g.max()
+    pred, _ = np.histogram(g.reshape(-1), bins=bins_, density=True, range=(0, 1))
+    return -np.sum(np.asarray(targets) * np.log(pred + 1e-9)) / pred.shape[0]
