@@ -201,6 +201,10 @@ int uncl_relu_bwd_bias(float* dY, const float* Y, long y_img_stride, float* db, 
 /* dW9[t][ci][co] += sum X[.., y+ky-pad, x+kx-pad, ci] * dZ[.., y, x, co]   (dW9 zeroed by the caller) */
 int uncl_conv3x3_wgrad(const float* X, long x_img_stride, const float* dZ, float* dW9, int N, int C_in, int H, int W,
                        int C_out, int pad, uncl_stream_t stream);
+/* The same weight gradient on the tcgen05 tensor cores (bf16 X and dZ, fp32 accumulation in TMEM, fp32 atomics into
+ * dW9): a GEMM with K = pixels whose operands are read MN-major straight from the C8-blocked TMA tiles. */
+int uncl_conv3x3_wgrad_tc(const void* X, long x_img_stride, const void* dZ, float* dW9, int N, int C_in, int H, int W,
+                          int C_out, int pad, uncl_stream_t stream);
 int uncl_conv_first_wgrad(const float* x, const float* dZ, float* dW, int N, int H, int W, int C, uncl_stream_t stream);
 int uncl_maxpool2_bwd(const float* X, long x_img_stride, const float* dP, float* dX, int N, int C, int H, int W,
                       uncl_stream_t stream);

@@ -53,6 +53,29 @@ def test_conv3x3(ci, co, h, transposed, relu):
     assert rel(wc.grad, wr.grad) < 1e-5 and rel(bc.grad, br.grad) < 1e-5
 
 
+@pytest.mark.parametrize("ci,co,h,transposed", [(32, 32, 70, False), (32, 64, 37, False), (64, 128, 30, False),
+                                               (128, 32, 66, True), (256, 256, 12, False), (256, 256, 10, True),
+                                               (1024, 128, 24, True), (512, 64, 57, True), (128, 128, 59, False)])
+def test_conv3x3_tensor_core_path(ci, co, h, transposed):
+    """tc=True: tcgen05 forward, data gradient and weight gradient (bf16 operands, fp32 accumulation) against float64.
+    Inputs are pre-rounded to bf16 so that only the accumulation order differs."""
+    x = rnd(2, ci, h, h + 2, seed=1).to(torch.bfloat16).float()
+    w = rnd(*((ci, co, 3, 3) if transposed else (co, ci, 3, 3)), seed=2, scale=(9 * ci) ** -0.5).to(torch.bfloat16).float()
+    b = rnd(co, seed=3, scale=0.1)
+    xr, wr, br = leaf(x), leaf(w), leaf(b)
+    # no ReLU here: a pre-activation within fp32 rounding of 0 would flip its mask between the two sides and change the
+    # 3x3 neighbourhood of that one pixel (the mask itself is covered by test_conv3x3)
+    yr = F.conv_transpose2d(xr, wr, br) if transposed else F.conv2d(xr, wr, br)
+    g = rnd(*yr.shape, seed=4).to(torch.bfloat16).float()
+    yr.backward(g.double())
+    xb, wc, bc = leaf(to_blocked(x), "cuda"), leaf(w, "cuda"), leaf(b, "cuda")
+    y = A.Conv3x3.apply(xb, wc, bc, transposed, False, True)
+    y.backward(to_blocked(g).cuda())
+    assert rel(from_blocked(y), yr) < 1e-5
+    assert rel(from_blocked(xb.grad), xr.grad) < 1e-5      # dz is exactly representable (g * mask), weights bf16
+    assert rel(wc.grad, wr.grad) < 1e-5 and rel(bc.grad, br.grad) < 1e-5
+
+
 def test_conv_first():
     x = rnd(2, 1, 40, 52, seed=1)
     w, b = rnd(32, 1, 3, 3, seed=2, scale=0.3), rnd(32, seed=3, scale=0.1)

@@ -74,6 +74,7 @@ class Conv3x3(Function):
             xb = _to_bf16(x)
             call("uncl_conv3x3_tc", xb, xb.stride(0), packing.conv3x3_tc(w9), b, y, y.stride(0), F32, n, ci, h, w, co, pad,
                  act, 0, 0, None, None, None, None)
+            x = xb   # the backward only needs the bf16 copy (weight gradient on the tensor cores)
         else:
             call("uncl_conv3x3_simt", x, x.stride(0), w9, b, y, y.stride(0), n, ci, h, w, co, pad, act, 0, F32)
         ctx.save_for_backward(x, y, w9)
@@ -88,22 +89,25 @@ class Conv3x3(Function):
         ci, co = w9.shape[1], w9.shape[2]
         ho, wo = y.shape[2], y.shape[3]
         dz = dy.contiguous().clone()
-        db = _zeros(co, x)
+        db = _zeros(co, dz)
         call("uncl_relu_bwd_bias", dz, y, y.stride(0), db, n, co, ho * wo, 1 if relu else 0)
         dx = None
+        dzb = _to_bf16(dz) if tc else None
         if ctx.needs_input_grad[0]:
             # dgrad of a correlation with pad p = correlation of dz with pad 2-p and the taps reversed / transposed
             wt = w9.flip(0).transpose(1, 2).contiguous()
-            dx = _empty(x.shape, x)
+            dx = _empty(x.shape, dz)
             if tc:
-                dzb = _to_bf16(dz)
-                call("uncl_conv3x3_tc", dzb, dzb.stride(0), packing.conv3x3_tc(wt), _zeros(ci, x), dx, dx.stride(0), F32, n,
+                call("uncl_conv3x3_tc", dzb, dzb.stride(0), packing.conv3x3_tc(wt), _zeros(ci, dz), dx, dx.stride(0), F32, n,
                      co, ho, wo, ci, 2 - pad, ACT_NONE, 0, 0, None, None, None, None)
             else:
-                call("uncl_conv3x3_simt", dz, dz.stride(0), wt, _zeros(ci, x), dx, dx.stride(0), n, co, ho, wo, ci, 2 - pad,
+                call("uncl_conv3x3_simt", dz, dz.stride(0), wt, _zeros(ci, dz), dx, dx.stride(0), n, co, ho, wo, ci, 2 - pad,
                      ACT_NONE, 0, F32)
-        dw9 = _zeros((9, ci, co), x)
-        call("uncl_conv3x3_wgrad", x, x.stride(0), dz, dw9, n, ci, h, w, co, pad)
+        dw9 = _zeros((9, ci, co), dz)
+        if tc:
+            call("uncl_conv3x3_wgrad_tc", x, x.stride(0), dzb, dw9, n, ci, h, w, co, pad)
+        else:
+            call("uncl_conv3x3_wgrad", x, x.stride(0), dz, dw9, n, ci, h, w, co, pad)
         if transposed:   # w9[t] = W[:, :, 2-ky, 2-kx]  (W is [C_in, C_out, 3, 3])
             dw = dw9.reshape(3, 3, ci, co).permute(2, 3, 0, 1).flip(2, 3)
         else:            # w9[t] = W[co, ci, ky, kx]
