@@ -160,12 +160,14 @@ def _contrast_features(up_x):
     return torch.cat([up_x.mean(dim=(2, 3), keepdim=True), var.mean(dim=(2, 3), keepdim=True)], dim=1)
 
 
-def unet_video_forward(sd, x, droppath_masks=None):
+def unet_video_forward(sd, x, droppath_masks=None, detach_state=False):
     """Video generator forward, Unet.py:213-289.
 
     x: [N,T,1,256,256] -> (frames [N,T,1,256,256], features [N,T,64,1,1]).  Frame k feeds the first
     C/32 channels of its 8 stage inputs from frame k-1 (not detached).
     droppath_masks: optional list (per frame) of mask pairs.
+    detach_state: NOT the reference behaviour - cuts the gradient through the hand-over, so that tests can measure how
+    much of a gradient travels through the recurrence.
     """
     outs, feats, prev = [], [], None
     for k in range(x.shape[1]):
@@ -183,7 +185,7 @@ def unet_video_forward(sd, x, droppath_masks=None):
         feats.append(_contrast_features(up_x).unsqueeze(1))
         out = torch.sigmoid(F.conv2d(up_x, sd["outc.conv.weight"], sd["outc.conv.bias"]))
         outs.append(out.unsqueeze(1))
-        prev = cur
+        prev = [c.detach() for c in cur] if detach_state else cur
     return torch.cat(outs, 1), torch.cat(feats, 1)
 
 

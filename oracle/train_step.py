@@ -7,7 +7,7 @@ import torch
 import torch.nn.functional as F
 
 from .discriminator import simple_discriminator_forward
-from .generator import unet_forward
+from .generator import unet_forward, unet_video_forward
 from .losses import contrastive_d_loss, l1_mean_terms, nce, struct_loss, tv_loss
 
 
@@ -65,18 +65,28 @@ def g_d_loss(d_fake, d_pos, fea_fake_d, fea_pos_d, fea_neg_d, fea_in_d, fea_fake
     return err
 
 
+def _generate(gp, hdr, droppath):
+    """Image step: hdr [B,1,256,256].  Video step (GanTrainer.py:241-243, 274-276): hdr [B,T,1,256,256] through the
+    recurrent generator, outputs flattened to [B*T, ...]."""
+    if hdr.dim() == 5:
+        fake, fea = unet_video_forward(gp, hdr, droppath)
+        return fake.reshape(-1, *fake.shape[2:]), fea.reshape(-1, *fea.shape[2:])
+    return unet_forward(gp, hdr, droppath)
+
+
 def train_step_losses(g_sd, d_sd, hdr, pos, neg, epoch, droppath=None):
     """Loss values and gradients of one D step and one G step at fixed parameters (no optimizer update).
-    Returns dict(errD, errG_d, errG_struct, grads_D, grads_G)."""
+    Returns dict(errD, errG_d, errG_struct, grads_D, grads_G).  A 5-D hdr selects the video trainer's step."""
     gp = {k: v.clone().requires_grad_(k != "gcn.module.0.0.relative_pos") for k, v in g_sd.items()}
     dp = {k: v.clone().requires_grad_(True) for k, v in d_sd.items()}
     d_pos, _ = simple_discriminator_forward(dp, pos)
     with torch.no_grad():
-        fake0, _ = unet_forward(gp, hdr, droppath)
+        fake0, _ = _generate(gp, hdr, droppath)
     d_fake, _ = simple_discriminator_forward(dp, fake0)
     err_d = 0.2 * (1.0 if epoch <= 6 else 1e-6) * contrastive_d_loss(d_pos, d_fake)
     grads_d = dict(zip(dp, torch.autograd.grad(err_d, list(dp.values()))))
-    fake, fea_fake = unet_forward(gp, hdr, droppath)
+    fake, fea_fake = _generate(gp, hdr, droppath)
+    hdr = hdr.reshape(-1, *hdr.shape[-3:])
     dd = {k: v.detach() for k, v in dp.items()}
     d_fake_bp, fea_fake_d = simple_discriminator_forward(dd, fake)
     d_pos_bp, fea_pos_d = simple_discriminator_forward(dd, pos)

@@ -206,3 +206,19 @@ def test_outc_sigmoid_and_layout():
     assert rel(out, outr) < 1e-6 and rel(feats, up) == 0.0
     assert rel(from_blocked(ub.grad), ur.grad) < 1e-6
     assert rel(wc.grad, wr.grad) < 1e-5 and rel(bc.grad, br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("c,h,r", [(32, 20, 1), (64, 13, 2), (128, 7, 4), (256, 12, 8)])
+def test_splice_channels(c, h, r):
+    """Video hand-over cat(prev[:, :r], cur[:, r:]) (Unet.py:244, 270): exact copy forward, gradient split backward."""
+    cur, prev = rnd(2, c, h, h, seed=1), rnd(2, c, h, h, seed=2)
+    cr, pr = leaf(cur), leaf(prev)
+    yr = torch.cat((pr[:, :r], cr[:, r:]), 1)
+    g = rnd(*yr.shape, seed=3)
+    yr.backward(g.double())
+    cb, pb = leaf(to_blocked(cur), "cuda"), leaf(to_blocked(prev), "cuda")
+    y = A.SpliceChannels.apply(cb, pb, r)
+    y.backward(to_blocked(g).cuda())
+    assert torch.equal(from_blocked(y).cpu().double(), yr.detach())
+    assert torch.equal(from_blocked(cb.grad).cpu().double(), cr.grad)
+    assert torch.equal(from_blocked(pb.grad).cpu().double(), pr.grad)

@@ -164,3 +164,13 @@ def net_fp32():
     n = UNet(*G_ARGS, up_mode=0, precision="fp32").cuda().eval()
     n.load_state_dict(make_generator_state_dict())
     return n
+
+
+def test_streaming_host_api_matches_single_frame_calls(net):
+    frames = [torch.from_numpy(synth.hdr_frame(268, 300, seed=20 + i)).pin_memory() for i in range(5)]
+    pipe = FramePipeline(net)
+    got = pipe.tonemap_host_frames(frames, 50.0)
+    torch.cuda.synchronize()
+    for f, g in zip(frames, got):
+        want = pipe.tonemap(f.cuda(), 50.0, uint8=True).cpu()
+        assert torch.equal(g, want)

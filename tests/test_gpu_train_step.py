@@ -87,3 +87,35 @@ def test_adam_training_reduces_struct_loss():
         _, s = tr.step(hdr, None, pos, neg, 0)
         hist.append(s.item())
     assert all(np.isfinite(hist)) and hist[-1] < hist[0]
+
+
+@pytest.mark.parametrize("epoch", [0, 10])
+def test_video_train_step_matches_oracle(epoch):
+    """GanTrainer (video): 5-D clips through the recurrent generator, features [B*T,64,1,1] into infoNCE2."""
+    from uncltmo_b200.generator import UNetVideo
+    g_sd, d_sd = make_generator_state_dict(), make_discriminator_state_dict()
+    hdr = torch.from_numpy(synth.normalised_batch(2, seed=4)).reshape(1, 2, 1, 256, 256)
+    pos = torch.from_numpy(synth.ldr_batch(2, seed=5)).reshape(1, 2, 1, 256, 256)
+    neg = torch.from_numpy(synth.ldr_batch(2, seed=6)).reshape(1, 2, 1, 256, 256)
+    ref = oracle.train_step_losses({k: v.double() for k, v in g_sd.items()}, {k: v.double() for k, v in d_sd.items()},
+                                   hdr.double(), pos[0].double(), neg[0].double(), epoch)
+    netG = UNetVideo(*G_ARGS, up_mode=0, precision="fp32").cuda().train()
+    netG.load_state_dict(g_sd)
+    netG.drop_path_prob = 0.0
+    netD = SimpleDiscriminator(256, 1, 16, "none", "none", 0, 0).cuda().train()
+    netD.load_state_dict(d_sd)
+    optG = RecordingSGD([p for p in netG.parameters() if p.requires_grad], lr=0.0)
+    optD = RecordingSGD(netD.parameters(), lr=0.0)
+    tr = GanTrainerStep(netG, netD, optG, optD)
+    assert tr.video
+    err_g, err_s = tr.step(hdr.cuda(), None, pos.cuda(), neg.cuda(), epoch)
+    assert abs(tr.errD.item() - ref["errD"]) <= 1e-3 * abs(ref["errD"])
+    assert abs(err_g.item() - ref["errG_d"]) <= 1e-3 * abs(ref["errG_d"])
+    assert abs(err_s.item() - ref["errG_struct"]) <= 1e-3 * abs(ref["errG_struct"])
+    bad = {}
+    for k, p in netG.named_parameters():
+        if k in ref["grads_G"] and not (k.startswith("inc.") or k[:11] in ("down_path.0", "down_path.1", "down_path.2")):
+            e = rel(optG.seen[id(p)], ref["grads_G"][k])
+            if e > (5e-2 if k == "outc.conv.bias" else 2e-3):
+                bad[k] = e
+    assert not bad, bad

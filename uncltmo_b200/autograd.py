@@ -115,6 +115,33 @@ class Conv3x3(Function):
         return dx, dw.contiguous(), db, None, None, None
 
 
+class SpliceChannels(Function):
+    """Video recurrence: cat(prev[:, :r], cur[:, r:]) (Unet.py:244, 270); the gradient flows to both (prev is not
+    detached in the reference)."""
+
+    @staticmethod
+    def forward(ctx, cur, prev, r):
+        out = cur.contiguous().clone()
+        prev = prev.contiguous()
+        n = out.shape[0]
+        hw = out.numel() // (n * out.shape[1] * 8)
+        call("uncl_splice_channels", out, out.stride(0), prev, prev.stride(0), r, n, hw, F32)
+        ctx.r = r
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        n = dout.shape[0]
+        hw = dout.numel() // (n * dout.shape[1] * 8)
+        d_cur = dout.clone()
+        zero = torch.zeros((n, 1) + tuple(dout.shape[2:]), device=dout.device, dtype=torch.float32)
+        call("uncl_splice_channels", d_cur, d_cur.stride(0), zero, zero.stride(0), ctx.r, n, hw, F32)
+        d_prev = torch.zeros_like(dout)
+        call("uncl_splice_channels", d_prev, d_prev.stride(0), dout, dout.stride(0), ctx.r, n, hw, F32)
+        return d_cur, d_prev, None
+
+
 class MaxPool2(Function):
     """nn.MaxPool2d(2).  unet_parts.py:210-213."""
 

@@ -183,6 +183,48 @@ class FramePipeline:
         col = self.postprocess(fake_p, rgb, stats, pl)
         return self.to_uint8(col) if uint8 else col
 
+    def tonemap_host_frames(self, host_frames, lam, out=None):
+        """Stream pinned HOST frames through the path: [3,H,W] fp32 each -> HWC uint8 host tensors.
+
+        The host->device copy of frame i+1 and the device->host copy of result i-1 run on their own streams while
+        frame i computes (double-buffered device staging), so a long sequence costs max(copy, compute) per frame.
+        Every frame's input and output still cross PCIe inside the call."""
+        if not host_frames:
+            return []
+        dev = next(self.g.parameters()).device
+        compute = torch.cuda.current_stream(dev)
+        h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        stage = [torch.empty(host_frames[0].shape, device=dev, dtype=torch.float32) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]     # staging buffer i holds a fresh frame
+        free = [torch.cuda.Event() for _ in range(2)]      # staging buffer i has been consumed
+        results = []
+        if out is None:
+            h, w = host_frames[0].shape[1], host_frames[0].shape[2]
+            out = [torch.empty((h, w, 3), dtype=torch.uint8).pin_memory() for _ in host_frames]
+        with torch.cuda.stream(h2d):
+            stage[0].copy_(host_frames[0], non_blocking=True)
+            ready[0].record(h2d)
+        for i, _ in enumerate(host_frames):
+            b = i & 1
+            if i + 1 < len(host_frames):
+                with torch.cuda.stream(h2d):
+                    if i >= 1:
+                        h2d.wait_event(free[1 - b])
+                    stage[1 - b].copy_(host_frames[i + 1], non_blocking=True)
+                    ready[1 - b].record(h2d)
+            compute.wait_event(ready[b])
+            u8 = self.tonemap(stage[b], lam, uint8=True)
+            free[b].record(compute)
+            done = torch.cuda.Event()
+            done.record(compute)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done)
+                out[i].copy_(u8, non_blocking=True)
+                u8.record_stream(d2h)
+            results.append(out[i])
+        compute.wait_stream(d2h)
+        return results
+
     def tonemap_clip(self, frames, lam, uint8=False):
         """Video path (run_model_on_video, model_save_util.py:567-614): frames [T,3,H,W] fp32 CUDA of ONE scene, one
         lambda per scene.  `self.g` must be the video generator (UNetVideo): every tile is a chain over the T frames

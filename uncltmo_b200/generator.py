@@ -284,6 +284,54 @@ class _GeneratorBase(nn.Module):
         call("uncl_blocked_to_nchw", up, up.stride(0), o, n, c, hw, _lib.DTYPE_OF[up.dtype])
         return o
 
+    def _forward_train(self, x, droppath_scale=None, prev=None, want_state=False):
+        """Same network as _run_frame, built from autograd Functions whose forward and backward are library kernels.
+        precision 'fp32': CUDA-core kernels throughout (gradient parity 1e-3 vs the float64 oracle).
+        precision 'bf16': "mixed" - the 3x3 convolutions (forward, data and weight gradients) run on the tcgen05
+        kernels with bf16-rounded operands and fp32 accumulation; every tensor between kernels is fp32.
+        prev / want_state: recurrent channel hand-over of the video generator (Unet.py:229-286)."""
+        from . import autograd as A
+        tc = self.precision == "bf16"
+        if x.dim() != 4 or tuple(x.shape[1:]) != (1, 256, 256) or not x.is_cuda:
+            raise ValueError("the generator expects CUDA [N,1,256,256] inputs")
+        n = x.shape[0]
+        c = self.inc.conv
+        a0 = A.ConvFirst.apply(x, c.conv.weight, c.conv.bias)
+        cur = A.Conv3x3.apply(a0, c.conv1.weight, c.conv1.bias, False, True, tc)
+        skips, state = [cur], [cur]
+        for i in range(4):
+            blk = self.down_path[i].mpconv[1]
+            fea = cur if prev is None else A.SpliceChannels.apply(cur, prev[i], cur.shape[1] * 8 // 32)
+            m = A.Conv3x3.apply(A.MaxPool2.apply(fea), blk.conv.weight, blk.conv.bias, False, True, tc)
+            cur = A.Conv3x3.apply(m, blk.conv1.weight, blk.conv1.bias, i == 3, True, tc)
+            skips.append(cur)
+            state.append(cur)
+        g, ffn = self.gcn.module[0][0], self.gcn.module[0][1]
+        s0 = droppath_scale[0] if droppath_scale is not None else None
+        s1 = droppath_scale[1] if droppath_scale is not None else None
+        x0 = A.AddPos.apply(cur, self.gcn.pos_embed)
+        y = A.PwConv.apply(x0, g.fc1[0].weight, g.fc1[0].bias, None, None, 1, False)
+        z = A.KnnAggregate.apply(y, g.relative_pos.detach().reshape(144, 144).float().contiguous())
+        gc = g.graph_conv.gconv.nn[0]
+        z2 = A.PwConv.apply(z, gc.weight, gc.bias, None, None, 4, True)
+        x1 = A.PwConv.apply(z2, g.fc2[0].weight, g.fc2[0].bias, x0, s0, 1, False)
+        f1 = A.PwConv.apply(x1, ffn.fc1[0].weight, ffn.fc1[0].bias, None, None, 1, True)
+        up = A.PwConv.apply(f1, ffn.fc2[0].weight, ffn.fc2[0].bias, x1, s1, 1, False).reshape(n, -1, 12, 12, 8)
+        state.append(up)
+        for i in range(4):
+            u = self.up_path[i]
+            sk = skips[3 - i]
+            fea = up if prev is None else A.SpliceChannels.apply(up, prev[5 + i], up.shape[1] * 8 // 32)
+            x1u = A.ConvT2x2.apply(fea, u.up.weight, u.up.bias, sk.shape[2], sk.shape[3])
+            cat = A.SkipConcat.apply(sk, x1u)
+            m = A.Conv3x3.apply(cat, u.conv.conv.weight, u.conv.conv.bias, True, True, tc)
+            up = A.Conv3x3.apply(m, u.conv.conv1.weight, u.conv.conv1.bias, True, True, tc)
+            state.append(up)
+        if want_state:
+            return A.OutcSigmoid.apply(up, self.outc.conv.weight, self.outc.conv.bias), A.BlockedToNCHW.apply(up), state
+        out = A.OutcSigmoid.apply(up, self.outc.conv.weight, self.outc.conv.bias)
+        return out, A.BlockedToNCHW.apply(up)
+
     def _droppath_scale(self, n, device):
         """Per-sample DropPath factors (mask / keep_prob) for the two residual branches; None in eval."""
         if not self.training or self.drop_path_prob <= 0:
@@ -325,46 +373,6 @@ class UNet(_GeneratorBase):
             out = self._crop(out, diffY, diffX)
         return out, feats
 
-    def _forward_train(self, x, droppath_scale=None):
-        """Same network as _run_frame, built from autograd Functions whose forward and backward are library kernels.
-        precision 'fp32': CUDA-core kernels throughout (gradient parity 1e-3 vs the float64 oracle).
-        precision 'bf16': "mixed" - the 3x3 convolutions (forward and data gradient) run on the tcgen05 kernel with
-        bf16-rounded operands and fp32 accumulation; every tensor between kernels and every weight gradient is fp32."""
-        from . import autograd as A
-        tc = self.precision == "bf16"   # mixed: tensor-core conv forward / data gradient, fp32 tensors and weight gradients
-        if x.dim() != 4 or tuple(x.shape[1:]) != (1, 256, 256) or not x.is_cuda:
-            raise ValueError("the generator expects CUDA [N,1,256,256] inputs")
-        n = x.shape[0]
-        c = self.inc.conv
-        a0 = A.ConvFirst.apply(x, c.conv.weight, c.conv.bias)
-        cur = A.Conv3x3.apply(a0, c.conv1.weight, c.conv1.bias, False, True, tc)
-        skips = [cur]
-        for i in range(4):
-            blk = self.down_path[i].mpconv[1]
-            m = A.Conv3x3.apply(A.MaxPool2.apply(cur), blk.conv.weight, blk.conv.bias, False, True, tc)
-            cur = A.Conv3x3.apply(m, blk.conv1.weight, blk.conv1.bias, i == 3, True, tc)
-            skips.append(cur)
-        g, ffn = self.gcn.module[0][0], self.gcn.module[0][1]
-        s0 = droppath_scale[0] if droppath_scale is not None else None
-        s1 = droppath_scale[1] if droppath_scale is not None else None
-        x0 = A.AddPos.apply(cur, self.gcn.pos_embed)
-        y = A.PwConv.apply(x0, g.fc1[0].weight, g.fc1[0].bias, None, None, 1, False)
-        z = A.KnnAggregate.apply(y, g.relative_pos.detach().reshape(144, 144).float().contiguous())
-        gc = g.graph_conv.gconv.nn[0]
-        z2 = A.PwConv.apply(z, gc.weight, gc.bias, None, None, 4, True)
-        x1 = A.PwConv.apply(z2, g.fc2[0].weight, g.fc2[0].bias, x0, s0, 1, False)
-        f1 = A.PwConv.apply(x1, ffn.fc1[0].weight, ffn.fc1[0].bias, None, None, 1, True)
-        up = A.PwConv.apply(f1, ffn.fc2[0].weight, ffn.fc2[0].bias, x1, s1, 1, False).reshape(n, -1, 12, 12, 8)
-        for i in range(4):
-            u = self.up_path[i]
-            sk = skips[3 - i]
-            x1u = A.ConvT2x2.apply(up, u.up.weight, u.up.bias, sk.shape[2], sk.shape[3])
-            cat = A.SkipConcat.apply(sk, x1u)
-            m = A.Conv3x3.apply(cat, u.conv.conv.weight, u.conv.conv.bias, True, True, tc)
-            up = A.Conv3x3.apply(m, u.conv.conv1.weight, u.conv.conv1.bias, True, True, tc)
-        out = A.OutcSigmoid.apply(up, self.outc.conv.weight, self.outc.conv.bias)
-        return out, A.BlockedToNCHW.apply(up)
-
     def tonemap_tiles(self, x, want_logit=False):
         """Fast path for the frame pipeline: [N,1,256,256] -> [N,1,256,256] without materialising features."""
         out, _, logit, _ = self._run_frame(x, want_features=False, want_logit=want_logit)
@@ -379,18 +387,21 @@ class UNetVideo(_GeneratorBase):
     """
 
     def forward(self, x, apply_crop=True, diffY=0, diffX=0):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("uncltmo_b200 generator backward is not built yet: call under torch.no_grad()")
-        from .features import contrast_features
+        from .features import contrast_features, plane_mean_contrast
+        train = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         outs, feats, prev = [], [], None
         for k in range(x.shape[1]):
-            out, up, _, state = self._run_frame(x[:, k], prev=prev,
-                                                droppath_scale=self._droppath_scale(x.shape[0], x.device))
-            feats.append(contrast_features(up).unsqueeze(1))
+            scale = self._droppath_scale(x.shape[0], x.device)
+            if train:
+                out, up_nchw, prev = self._forward_train(x[:, k].contiguous(), scale, prev=prev, want_state=True)
+                mean, con = plane_mean_contrast(up_nchw)
+                feats.append(torch.cat([mean, con], dim=1)[:, None, :, None, None])
+            else:
+                out, up, _, prev = self._run_frame(x[:, k], prev=prev, droppath_scale=scale)
+                feats.append(contrast_features(up).unsqueeze(1))
             if apply_crop and self.to_crop:
                 out = self._crop(out, diffY, diffX)
             outs.append(out.unsqueeze(1))
-            prev = state
         return torch.cat(outs, 1), torch.cat(feats, 1)
 
     def tonemap_clip_tiles(self, frames):

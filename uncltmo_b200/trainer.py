@@ -1,7 +1,9 @@
-"""The training step of GanTrainerImg (image TMO), mirrored on the B200 path.
+"""The training step of GanTrainerImg (image TMO) and GanTrainer (video TMO), mirrored on the B200 path.
 
 Reference: GanTrainerImg.py:200-217 (train_D), :231-260 (D_real_fake_pass), :262-292 (train_G), :302-339
-(update_g_d_loss, the epoch-dependent loss schedule), :452-461 (update_struct_loss).  Differences, none of which
+(update_g_d_loss, the epoch-dependent loss schedule), :452-461 (update_struct_loss); the video trainer
+GanTrainer.py:233-262, :264-300, :310-349 is the same step with 5-D clip batches and the recurrent generator (pass
+hdr_input as [B,T,1,256,256] and a UNetVideo).  Differences, none of which
 changes a gradient that reaches an optimizer:
   * the D-step generator forward and the discriminator passes over real images run without an autograd graph
     (the reference builds the graphs and throws them away; `D(real_neg)` of the D step is computed and never used
@@ -29,7 +31,9 @@ from .struct_loss import StructLoss
 class GanTrainerStep:
     def __init__(self, netG, netD, optimizerG, optimizerD, loss_g_d_factor=0.1, struct_loss_factor=1.0,
                  adv_weight_list=(0.2, 0.2, 0.2), pyramid_weight_list=(1.0, 1.0, 1.0), epoch_step1=6, epoch_step2=9):
+        from .generator import UNetVideo
         self.netG, self.netD = netG, netD
+        self.video = isinstance(netG, UNetVideo)
         self.optimizerG, self.optimizerD = optimizerG, optimizerD
         self.loss_g_d_factor = loss_g_d_factor
         self.struct_loss_factor = struct_loss_factor
@@ -46,12 +50,22 @@ class GanTrainerStep:
     def _flat(t):
         return t.reshape(-1, t.shape[-3], t.shape[-2], t.shape[-1]).float()
 
+    def _generate(self, hdr_input):
+        """Image trainer: G on [B,1,256,256].  Video trainer (GanTrainer.py:241-243, 274-276): G on the 5-D clip batch
+        [B,T,1,256,256] (frames of a clip are chained through the recurrent hand-over), outputs flattened to B*T."""
+        if self.video:
+            if hdr_input.dim() != 5:
+                raise ValueError("the video trainer expects [B,T,1,256,256] clips")
+            fake, fea = self.netG(hdr_input.float())
+            return self._flat(fake), self._flat(fea)
+        return self.netG(self._flat(hdr_input))
+
     # ------------------------------------------------------------------ D step
     def train_D(self, hdr_input, real_ldr_pos, real_ldr_neg, epoch):
         self.netD.zero_grad(set_to_none=True)
         d_real_pos, _ = self.netD(self._flat(real_ldr_pos))
         with torch.no_grad():
-            fake, _ = self.netG(self._flat(hdr_input))
+            fake, _ = self._generate(hdr_input)
         d_fake, _ = self.netD(fake.detach())
         w = self.adv_weight_list[0] * (1.0 if epoch <= self.epoch_step1 else 1e-6)
         self.errD = w * losses.contrastive_D_loss(all_gather_cat(d_real_pos), all_gather_cat(d_fake))
@@ -92,7 +106,7 @@ class GanTrainerStep:
         self.netG.zero_grad(set_to_none=True)
         hdr = self._flat(hdr_input)
         pos, neg = self._flat(real_ldr_pos), self._flat(real_ldr_neg)
-        fake, fea_fake = self.netG(hdr)
+        fake, fea_fake = self._generate(hdr_input)
         d_fake_bp, d_fea_fake = self.netD(fake)
         with torch.no_grad():
             d_real_pos_bp, d_fea_real_pos = self.netD(pos)
