@@ -67,7 +67,8 @@ int uncl_convT2x2(const void* in, long in_img_stride, const void* prev, long pre
 /* The same ConvTranspose k2 s2 as a tcgen05 GEMM [pixels x C].[C x 4C] with a pixel-shuffle epilogue (bf16).
  * w_packed: bf16 [NS][C/16][1][2][NT][8], column j = (dy*2+dx)*C + co, NT = min(4C, 128) (packing.convT2x2_tc). */
 int uncl_convT2x2_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
-                     long out_img_stride, int N, int C, int H, int W, int H2, int W2, uncl_stream_t stream);
+                     long out_img_stride, int out_dtype, int N, int C, int H, int W, int H2, int W2,
+                     uncl_stream_t stream);
 
 /* Video recurrence for kernels without a `prev` input: dst[:, :r] = src[:, :r] (r <= 8).  Unet.py:244, 270. */
 int uncl_splice_channels(void* dst, long dst_img_stride, const void* src, long src_img_stride, int r, int N, int HW,
@@ -106,9 +107,19 @@ int uncl_pw_conv(const float* in, const float* w, const float* bias, const float
 
 /* DenseDilatedKnnGraph (k=9, dilation 1, relative_pos) + MRConv2d aggregation + channel interleave.
  * gcn_lib/torch_edge.py:135-159, 54-86, 9-20; gcn_lib/torch_vertex.py:21-30.
- * y [N][C/8][144][8]; relpos [144][144]; z [N][2C/8][144][8]; idx_out [N][144][9] int32 or NULL. */
-int uncl_gcn_knn_aggregate(const float* y, const float* relpos, float* z, int* idx_out, int N, int C,
+ * y [N][C/8][144][8]; relpos [144][144]; z [N][2C/8][144][8] (fp32 or bf16); idx_out [N][144][9] int32 or NULL. */
+int uncl_gcn_knn_aggregate(const float* y, const float* relpos, void* z, int z_dtype, int* idx_out, int N, int C,
                            uncl_stream_t stream);
+
+/* The same 1x1 (grouped) conv as a tcgen05 GEMM per group, bf16 operands / fp32 accumulation:
+ * out = scale[n] * act(W x + b) + res, act in {none, ReLU, GELU}.  Also the data gradient of the k2 s2 up-convolution
+ * (4C -> C over the space-to-depth gradient).  in: bf16 blocked [N][C_in/8][H][W][8], W <= 128;
+ * w_packed: bf16 [NS][C_in/g/16][2][NT][8], NT = min(C_out/g, 128) (packing.pointwise_tc); bias / res / scale may be
+ * NULL; res and out are blocked with C_out channels, fp32 or bf16 each. */
+int uncl_pw_conv_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, const void* res,
+                    long res_img_stride, int res_dtype, const float* scale, void* out, long out_img_stride,
+                    int out_dtype, int N, int C_in, int C_out, int groups, int H, int W, int act,
+                    uncl_stream_t stream);
 
 /* ---- frame path (utils/model_save_util.py, utils/hdr_image_util.py, utils/data_loader_util.py) ---- */
 

@@ -31,3 +31,12 @@ agg = {}
 for n, ms in rec: agg[n] = agg.get(n, 0) + ms
 for n, ms in sorted(agg.items(), key=lambda kv: -kv[1])[:14]: print("  %-32s %8.3f ms" % (n, ms))
 print("  total kernels", sum(agg.values()))
+print("  top-level count", len(rec))
+try:
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        tr.step(hdr, None, pos, neg, 0)
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+except Exception as e:  # CUPTI may be unavailable on the box
+    print("profiler unavailable:", e)

@@ -303,7 +303,7 @@ class KnnAggregate(Function):
         n, cb = y.shape[0], y.shape[1]
         z = _empty((n, 2 * cb, 144, 8), y)
         idx = torch.empty((n, 144, 9), device=y.device, dtype=torch.int32)
-        call("uncl_gcn_knn_aggregate", y, relpos, z, idx, n, cb * 8)
+        call("uncl_gcn_knn_aggregate", y, relpos, z, F32, idx, n, cb * 8)
         ctx.save_for_backward(y, idx)
         return z
 

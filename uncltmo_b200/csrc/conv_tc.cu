@@ -51,6 +51,12 @@ struct TcParams {
   int a_box_bytes, a_stage_bytes, b_stage_bytes, stage_bytes;
   int act, emit_skip, fuse_outc;
   int sh_C, sh_H2, sh_W2;   // pixel-shuffle epilogue (ConvTranspose k2 s2): channels, target extent (replicate pad)
+  // pointwise epilogue (EPI 2): out = scale[n] * act(acc + bias) + res
+  const void* res;          // blocked, C_out channels, fp32 or bf16 (null: none)
+  long res_img_stride;
+  int res_f32;
+  const float* scale;       // per-image factor (DropPath) or null
+  int ns_per_group;         // grouped 1x1 conv: N splits per group (K range of a split = its group's input channels)
 };
 
 // ---------------------------------------------------------------- tile geometry shared by the three roles
@@ -88,6 +94,7 @@ __device__ __forceinline__ Item decode_item(const Geo& g, int item) {
 
 // EPI 0: conv epilogue (bias, ReLU, optional skip emission / fused 1x1 out conv + sigmoid)
 // EPI 1: pixel-shuffle epilogue of ConvTranspose k2 s2 (columns = (dy, dx, co)), replicate pad into (H2 x W2)
+// EPI 2: pointwise (1x1, optionally grouped) conv epilogue: bias, ReLU / GELU / identity, per-image scale, residual
 template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
@@ -118,7 +125,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   for (int i = threadIdx.x; i < p.C_out; i += kThreads) {
-    s_bias[i] = p.bias[i];
+    s_bias[i] = p.bias ? p.bias[i] : 0.f;
     if (p.fuse_outc) s_bias[p.C_out + i] = p.outc_w[i];
   }
   tc_fence_before();
@@ -134,14 +141,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       const uint32_t tx_bytes = (uint32_t)(p.a_box_bytes + p.b_stage_bytes), b_bytes = (uint32_t)p.b_stage_bytes;
       const int a_stage_bytes = p.a_stage_bytes;
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
+      const int ns_per_group = p.ns_per_group;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const Item it = decode_item(geo, item);
         const uint8_t* wsrc = wbase + (size_t)it.ns * nchunk * b_bytes;
+        const int kblk0 = (it.ns / ns_per_group) * nchunk * 2;   // first input channel block of this split's group
         for (int ch = 0; ch < nchunk; ++ch) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = stage_base + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full[stage], tx_bytes);
-          tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, ch * 2, it.n);
+          tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, kblk0 + ch * 2, it.n);
           bulk_load(sa + a_stage_bytes, wsrc + (size_t)ch * b_bytes, b_bytes, &full[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -289,12 +298,52 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             out_img[o] = 1.f / (1.f + __expf(-logit));
           }
         }
+      } else if constexpr (EPI == 2) {
+        const int cbase0 = it.ns * NT;
+        const int act = p.act;
+        const float sc = p.scale ? __ldg(p.scale + it.n) : 1.f;
+        const bf16* const resb = reinterpret_cast<const bf16*>(p.res);
+        const float* const resf = reinterpret_cast<const float*>(p.res);
+        const bool res_f32 = p.res_f32 != 0;
+        const long res_img_stride = p.res_img_stride;
+        for (int b = bpar; b < it.mb_act; b += 2) {
+          const int q = it.q0 + b * 128 + row;
+          const int oy = q / geo.PW, xl = q - oy * geo.PW;
+          const int ox = it.band * geo.BW + xl;
+          const bool valid = (oy < Ho) && (xl < geo.BW) && (ox < Wo);
+          const long pix = (long)oy * Wo + ox;
+          for (int c0 = 0; c0 < NT; c0 += 32) {
+            uint32_t r[32];
+            tc_ld32(tmem_base + lane_base + (uint32_t)(acc * kAccCols + b * NT + c0), r);
+            if (valid) {
+              const float* bias = s_bias + cbase0 + c0;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = sc * apply_act(__uint_as_float(r[g * 8 + j]) + bias[g * 8 + j], act);
+                const long cpix = (long)(cbase0 / 8 + c0 / 8 + g) * cb_stride + pix * 8;
+                if (resf != nullptr) {
+                  float rr[8];
+                  if (res_f32) load8(resf + (long)it.n * res_img_stride + cpix, rr);
+                  else load8(resb + (long)it.n * res_img_stride + cpix, rr);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] += rr[j];
+                }
+                const long off = (long)it.n * out_img_stride + cpix;
+                if (out_f32) store8(outf + off, v);
+                else store8(out + off, v);
+              }
+            }
+          }
+        }
       } else {
         // ConvTranspose k2 s2: column j = pos * C + co, pos = dy * 2 + dx; out pixel (2y+dy, 2x+dx) (+ replicate pad)
         const int C = p.sh_C, H2 = p.sh_H2, W2 = p.sh_W2, Hi = Ho, Wi = Wo;
         const int padT = (H2 - 2 * Hi) / 2, padL = (W2 - 2 * Wi) / 2;
         const long cb2 = (long)H2 * W2 * 8;
         bf16* const out_img_n = out + (long)it.n * out_img_stride;
+        float* const outf_img_n = outf + (long)it.n * out_img_stride;
         for (int b = bpar; b < it.mb_act; b += 2) {
           const int q = it.q0 + b * 128 + row;
           const int y = q / geo.PW, x = q - y * geo.PW;
@@ -313,9 +362,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) + s_bias[co0 + j];
                 const int y_lo = (Y == 0) ? 0 : Y + padT, y_hi = (Y == 2 * Hi - 1) ? H2 - 1 : Y + padT;
                 const int x_lo = (X == 0) ? 0 : X + padL, x_hi = (X == 2 * Wi - 1) ? W2 - 1 : X + padL;
-                bf16* o = out_img_n + (long)(co0 / 8) * cb2;
+                const long o = (long)(co0 / 8) * cb2;
                 for (int yy = y_lo; yy <= y_hi; ++yy)
-                  for (int xx = x_lo; xx <= x_hi; ++xx) store8(o + ((long)yy * W2 + xx) * 8, v);
+                  for (int xx = x_lo; xx <= x_hi; ++xx) {
+                    if (out_f32) store8(outf_img_n + o + ((long)yy * W2 + xx) * 8, v);
+                    else store8(out_img_n + o + ((long)yy * W2 + xx) * 8, v);
+                  }
               }
             }
           }
@@ -346,7 +398,7 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
               const char* what, cudaStream_t stream) {
   UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "%s: input must be 16-byte aligned", what);
   const int halo = p.ntaps == 9 ? 2 : 0;
-  p.nchunk = C_in / 16;
+  if (p.nchunk <= 0) p.nchunk = C_in / 16;
   const int mb_max = kAccCols / p.NT;
   // column bands: the TMA box row is PW pixels = 2*PW 8-byte elements and a box dimension holds <= 256 elements
   p.nbands = ceil_div(p.Wo, 128 - halo);
@@ -385,7 +437,8 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
 
-  auto kern = epi == 0 ? conv3x3_tc_kernel<0> : conv3x3_tc_kernel<1>;
+  if (p.ns_per_group <= 0) p.ns_per_group = p.NS;
+  auto kern = epi == 0 ? conv3x3_tc_kernel<0> : (epi == 1 ? conv3x3_tc_kernel<1> : conv3x3_tc_kernel<2>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));
   int dev = 0, sms = 148;
@@ -429,8 +482,10 @@ extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w
 // ConvTranspose2d(C, C, 2, stride=2) as a GEMM [pixels x C] . [C x 4C] with a pixel-shuffle epilogue.
 // w_packed: bf16 [NS][C/16][1][2][NT][8], column j = (dy*2+dx)*C + co, NT = min(4C, 128).
 extern "C" int uncl_convT2x2_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
-                                long out_img_stride, int N, int C, int H, int W, int H2, int W2, cudaStream_t stream) {
+                                long out_img_stride, int out_dtype, int N, int C, int H, int W, int H2, int W2,
+                                cudaStream_t stream) {
   UNCL_REQUIRE(N > 0 && C % 32 == 0 && H2 >= 2 * H && W2 >= 2 * W && W <= 128, "convT2x2_tc: unsupported C=%d W=%d", C, W);
+  UNCL_REQUIRE(out_dtype == UNCL_F32 || out_dtype == UNCL_BF16, "convT2x2_tc: bad out_dtype");
   TcParams p{};
   const int n_total = 4 * C;
   p.NT = n_total < 128 ? n_total : 128;
@@ -438,6 +493,7 @@ extern "C" int uncl_convT2x2_tc(const void* in, long in_img_stride, const void* 
   p.w = reinterpret_cast<const bf16*>(w_packed);
   p.bias = bias;
   p.out = out;
+  p.out_f32 = out_dtype == UNCL_F32;
   p.out_img_stride = out_img_stride;
   p.N = N; p.C_in = C; p.C_out = C; p.pad = 0;
   p.Ho = H; p.Wo = W;
@@ -445,4 +501,37 @@ extern "C" int uncl_convT2x2_tc(const void* in, long in_img_stride, const void* 
   p.ntaps = 1;
   p.sh_C = C; p.sh_H2 = H2; p.sh_W2 = W2;
   return launch_tc(p, in, in_img_stride, N, C, H, W, 1, 2 * C, "convT2x2_tc", stream);
+}
+
+// 1x1 (optionally grouped) convolution as a tensor-core GEMM [pixels x C_in/g] . [C_in/g x C_out/g] per group:
+// out = scale[n] * act(W x + b) + res.  gcn_lib/torch_nn.py:54-78 (BasicConv), torch_vertex.py:219-227, Unet_singleFrame.py:36-42;
+// also the data gradient of the k2 s2 up-convolution (a 4C -> C pointwise GEMM over the space-to-depth gradient).
+// in: bf16 blocked [N][C_in/8][H][W][8], W <= 128.  w_packed: bf16 [NS][C_in/g/16][2][NT][8], NT = min(C_out/g, 128).
+extern "C" int uncl_pw_conv_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, const void* res,
+                               long res_img_stride, int res_dtype, const float* scale, void* out, long out_img_stride,
+                               int out_dtype, int N, int C_in, int C_out, int groups, int H, int W, int act,
+                               cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && groups > 0 && C_in % (16 * groups) == 0 && C_out % (32 * groups) == 0 && W <= 128 && H > 0,
+               "pw_conv_tc: unsupported C_in=%d C_out=%d groups=%d W=%d", C_in, C_out, groups, W);
+  UNCL_REQUIRE((out_dtype == UNCL_F32 || out_dtype == UNCL_BF16) && out != nullptr, "pw_conv_tc: bad output");
+  UNCL_REQUIRE(res == nullptr || res_dtype == UNCL_F32 || res_dtype == UNCL_BF16, "pw_conv_tc: bad res_dtype");
+  UNCL_REQUIRE(act == UNCL_ACT_NONE || act == UNCL_ACT_RELU || act == UNCL_ACT_GELU, "pw_conv_tc: unsupported activation");
+  TcParams p{};
+  const int cout_g = C_out / groups;
+  p.NT = cout_g < 128 ? cout_g : 128;
+  UNCL_REQUIRE(cout_g % p.NT == 0 && C_out <= 2048, "pw_conv_tc: unsupported C_out/groups=%d", cout_g);
+  p.NS = C_out / p.NT;
+  p.ns_per_group = cout_g / p.NT;
+  p.nchunk = C_in / groups / 16;
+  p.w = reinterpret_cast<const bf16*>(w_packed);
+  p.bias = bias;
+  p.out = out;
+  p.out_f32 = out_dtype == UNCL_F32;
+  p.out_img_stride = out_img_stride;
+  p.res = res; p.res_img_stride = res_img_stride; p.res_f32 = res_dtype == UNCL_F32; p.scale = scale;
+  p.N = N; p.C_in = C_in; p.C_out = C_out; p.pad = 0;
+  p.Ho = H; p.Wo = W;
+  p.act = act;
+  p.ntaps = 1;
+  return launch_tc(p, in, in_img_stride, N, C_in, H, W, 2, 2 * C_out, "pw_conv_tc", stream);
 }

@@ -104,9 +104,9 @@ __global__ void __launch_bounds__(256) pw_conv_kernel(const float* __restrict__ 
 // streams the channel axis with 128-bit shared loads (row stride C+4 floats keeps them conflict-free).
 constexpr int KNN_SPLIT = 2;
 
-template <int C>
+template <int C, typename TZ>
 __global__ void __launch_bounds__(512) gcn_knn_agg_kernel(const float* __restrict__ y, const float* __restrict__ relpos,
-                                                         float* __restrict__ z, int* __restrict__ idx_out) {
+                                                         TZ* __restrict__ z, int* __restrict__ idx_out) {
   extern __shared__ __align__(16) float smem[];
   constexpr int LD = C + 4;
   constexpr int ROWS = GN / KNN_SPLIT;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(512) gcn_knn_agg_kernel(const float* __restric
   if (idx_out)
     for (int i = threadIdx.x; i < ROWS * GK; i += blockDim.x) idx_out[((long)n * GN + i_begin) * GK + i] = s_idx[i];
   // aggregation on the raw (un-normalised) features, straight from global / L2
-  float* zn = z + (long)n * 2 * C * GN;
+  TZ* zn = z + (long)n * 2 * C * GN;
   for (int il = wid; il < ROWS; il += nw) {
     const int i = i_begin + il;
     for (int cb = lane; cb < C / 8; cb += 32) {
@@ -253,12 +253,13 @@ extern "C" int uncl_pw_conv(const float* in, const float* w, const float* bias, 
   return uncl_check_launch("pw_conv");
 }
 
-extern "C" int uncl_gcn_knn_aggregate(const float* y, const float* relpos, float* z, int* idx_out, int N, int C,
+extern "C" int uncl_gcn_knn_aggregate(const float* y, const float* relpos, void* z, int z_dtype, int* idx_out, int N, int C,
                                       cudaStream_t stream) {
   UNCL_REQUIRE(C == 256 && N > 0, "gcn_knn_aggregate: only C=256 (shipped config) is built, got %d", C);
   const size_t smem = (size_t)(GN * (C + 4) + GN) * sizeof(float) + (size_t)GN * GK * sizeof(int);
-  cudaError_t e = cudaFuncSetAttribute(gcn_knn_agg_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(gcn_knn_agg_kernel<256, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gcn_knn_agg_kernel<256, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "gcn_knn_aggregate: smem attr: %s", cudaGetErrorString(e));
-  gcn_knn_agg_kernel<256><<<N * KNN_SPLIT, 512, smem, stream>>>(y, relpos, z, idx_out);
+  UNCL_DISPATCH_DTYPE(z_dtype, T, (gcn_knn_agg_kernel<256, T><<<N * KNN_SPLIT, 512, smem, stream>>>(y, relpos, (T*)z, idx_out)));
   return uncl_check_launch("gcn_knn_aggregate");
 }

@@ -141,7 +141,8 @@ class _GeneratorBase(nn.Module):
             P["relpos"] = g.relative_pos.detach().reshape(144, 144).float().contiguous()
             for name, m, groups in (("g_fc1", g.fc1[0], 1), ("g_gconv", g.graph_conv.gconv.nn[0], 4),
                                     ("g_fc2", g.fc2[0], 1), ("f_fc1", ffn.fc1[0], 1), ("f_fc2", ffn.fc2[0], 1)):
-                P[name] = (packing.pointwise(m.weight.detach(), groups), m.bias.detach().float().contiguous())
+                pack = packing.pointwise_tc if tc and name != "g_fc1" else packing.pointwise
+                P[name] = (pack(m.weight.detach(), groups), m.bias.detach().float().contiguous())
             for i in range(4):
                 u = self.up_path[i]
                 P["u%d_up" % i] = (packing.convT2x2_tc(u.up.weight.detach()) if tc else packing.convT2x2(u.up.weight.detach()),
@@ -221,18 +222,37 @@ class _GeneratorBase(nn.Module):
         def f32buf(c):
             return torch.empty((n, c // 8, 144, 8), device=dev, dtype=torch.float32)
 
-        x0, y, z, z2, x1, f1 = f32buf(C), f32buf(C), f32buf(2 * C), f32buf(2 * C), f32buf(C), f32buf(C)
-        idx = torch.empty((n, 144, 9), device=dev, dtype=torch.int32) if keep is not None else None
-        call("uncl_gcn_add_pos", cur, st(cur), P["pos"], x0, n, C, dt)
-        call("uncl_pw_conv", x0, P["g_fc1"][0], P["g_fc1"][1], None, None, y, st(y), n, C, C, 1, 144, ACT_NONE, _lib.F32)
-        call("uncl_gcn_knn_aggregate", y, P["relpos"], z, idx, n, C)
-        call("uncl_pw_conv", z, P["g_gconv"][0], P["g_gconv"][1], None, None, z2, st(z2), n, 2 * C, 2 * C, 4, 144, ACT_GELU, _lib.F32)
         s0 = droppath_scale[0] if droppath_scale is not None else None
         s1 = droppath_scale[1] if droppath_scale is not None else None
-        call("uncl_pw_conv", z2, P["g_fc2"][0], P["g_fc2"][1], x0, s0, x1, st(x1), n, 2 * C, C, 1, 144, ACT_NONE, _lib.F32)
-        call("uncl_pw_conv", x1, P["f_fc1"][0], P["f_fc1"][1], None, None, f1, st(f1), n, C, C, 1, 144, ACT_GELU, _lib.F32)
+        idx = torch.empty((n, 144, 9), device=dev, dtype=torch.int32) if keep is not None else None
+        x0, y = f32buf(C), f32buf(C)
         gout = buf(C, 12, 12)
-        call("uncl_pw_conv", f1, P["f_fc2"][0], P["f_fc2"][1], x1, s1, gout, st(gout), n, C, C, 1, 144, ACT_NONE, dt)
+        call("uncl_gcn_add_pos", cur, st(cur), P["pos"], x0, n, C, dt)
+        # fc1 feeds the KNN selection: kept in fp32 on the CUDA cores in both precisions
+        call("uncl_pw_conv", x0, P["g_fc1"][0], P["g_fc1"][1], None, None, y, st(y), n, C, C, 1, 144, ACT_NONE, _lib.F32)
+        if self.precision == "bf16":
+            # the other four 1x1 convs (92 % of the block's MACs) run as tensor-core GEMMs on bf16 tensors
+            def b16buf(c):
+                return torch.empty((n, c // 8, 144, 8), device=dev, dtype=torch.bfloat16)
+
+            z, z2, x1, f1 = b16buf(2 * C), b16buf(2 * C), b16buf(C), b16buf(C)
+            BF, F32 = _lib.BF16, _lib.F32
+            call("uncl_gcn_knn_aggregate", y, P["relpos"], z, BF, idx, n, C)
+            call("uncl_pw_conv_tc", z, st(z), P["g_gconv"][0], P["g_gconv"][1], None, 0, BF, None, z2, st(z2), BF, n,
+                 2 * C, 2 * C, 4, 12, 12, ACT_GELU)
+            call("uncl_pw_conv_tc", z2, st(z2), P["g_fc2"][0], P["g_fc2"][1], x0, st(x0), F32, s0, x1, st(x1), BF, n,
+                 2 * C, C, 1, 12, 12, ACT_NONE)
+            call("uncl_pw_conv_tc", x1, st(x1), P["f_fc1"][0], P["f_fc1"][1], None, 0, BF, None, f1, st(f1), BF, n,
+                 C, C, 1, 12, 12, ACT_GELU)
+            call("uncl_pw_conv_tc", f1, st(f1), P["f_fc2"][0], P["f_fc2"][1], x1, st(x1), BF, s1, gout, st(gout), BF, n,
+                 C, C, 1, 12, 12, ACT_NONE)
+        else:
+            z, z2, x1, f1 = f32buf(2 * C), f32buf(2 * C), f32buf(C), f32buf(C)
+            call("uncl_gcn_knn_aggregate", y, P["relpos"], z, _lib.F32, idx, n, C)
+            call("uncl_pw_conv", z, P["g_gconv"][0], P["g_gconv"][1], None, None, z2, st(z2), n, 2 * C, 2 * C, 4, 144, ACT_GELU, _lib.F32)
+            call("uncl_pw_conv", z2, P["g_fc2"][0], P["g_fc2"][1], x0, s0, x1, st(x1), n, 2 * C, C, 1, 144, ACT_NONE, _lib.F32)
+            call("uncl_pw_conv", x1, P["f_fc1"][0], P["f_fc1"][1], None, None, f1, st(f1), n, C, C, 1, 144, ACT_GELU, _lib.F32)
+            call("uncl_pw_conv", f1, P["f_fc2"][0], P["f_fc2"][1], x1, s1, gout, st(gout), n, C, C, 1, 144, ACT_NONE, dt)
         state.append(gout)
         if keep is not None:
             keep.update(x0=x0, y=y, idx=idx, z=z, z2=z2, x1=x1, f1=f1, gcn=gout, skips=cat, x4=cur)
@@ -252,8 +272,8 @@ class _GeneratorBase(nn.Module):
                     # the up-conv GEMM has no `prev` input: keep this frame's hand-over slice, then splice in place
                     state[5 + i] = up[:, :1].clone()
                     call("uncl_splice_channels", up, st(up), pv, st(pv), up_c // 32, n, up_s * up_s, dt)
-                call("uncl_convT2x2_tc", up, st(up), P["u%d_up" % i][0], P["u%d_up" % i][1], dst, st(cb), n, up_c,
-                     up_s, up_s, sk_s, sk_s)
+                call("uncl_convT2x2_tc", up, st(up), P["u%d_up" % i][0], P["u%d_up" % i][1], dst, st(cb), _lib.BF16, n,
+                     up_c, up_s, up_s, sk_s, sk_s)
             else:
                 call("uncl_convT2x2", up, st(up), pv, st(pv) if pv is not None else 0,
                      up_c // 32 if pv is not None else 0, P["u%d_up" % i][0], P["u%d_up" % i][1], dst, st(cb), n, up_c,

@@ -49,6 +49,15 @@ def pointwise(w, groups=1):
     return w.reshape(groups, co // groups, cig).permute(0, 2, 1).contiguous().float()
 
 
+def pointwise_tc(w, groups=1):
+    """1x1 Conv2d weight [C_out][C_in/g][1][1] -> bf16 [NS][C_in/g/16][2][NT][8] (conv_tc.cu pointwise B operand, K-major):
+    N split ns covers output channels ns*NT .. ns*NT+NT-1 (inside one group), NT = min(C_out/g, 128)."""
+    co, cig = w.shape[0], w.shape[1]
+    nt = min(co // groups, 128)
+    b = w.reshape(co // nt, nt, cig // 16, 2, 8).permute(0, 2, 3, 1, 4).contiguous()
+    return b.to(torch.bfloat16)
+
+
 def conv_first(w):
     """Conv2d(1, C_out, 3) weight [C_out][1][3][3] -> [9][C_out] fp32."""
     return w.reshape(w.shape[0], 9).t().contiguous().float()
