@@ -209,6 +209,9 @@ int uncl_tv_loss(const float* x, int B, int C, int H, int W, float* scratch, flo
 /* dY *= (Y > 0) in place (apply_relu) and db[c] += sum dY (db may be NULL).  ReLU of unet_parts.py:70-86. */
 int uncl_relu_bwd_bias(float* dY, const float* Y, long y_img_stride, float* db, int N, int C, int HW, int apply_relu,
                        uncl_stream_t stream);
+/* Out-of-place form: dZ = dY * (Y > 0) as fp32 or bf16 (the tensor-core gradient operand), db[c] += sum dZ. */
+int uncl_relu_bwd_bias_out(const float* dY, const float* Y, long y_img_stride, void* dZ, int dz_dtype, float* db, int N,
+                           int C, int HW, int apply_relu, uncl_stream_t stream);
 /* dW9[t][ci][co] += sum X[.., y+ky-pad, x+kx-pad, ci] * dZ[.., y, x, co]   (dW9 zeroed by the caller) */
 int uncl_conv3x3_wgrad(const float* X, long x_img_stride, const float* dZ, float* dW9, int N, int C_in, int H, int W,
                        int C_out, int pad, uncl_stream_t stream);
@@ -224,8 +227,10 @@ int uncl_skip_concat_fwd(const float* x2, long x2_img_stride, const float* x1, f
                          uncl_stream_t stream);
 int uncl_skip_concat_bwd(const float* dcat, const float* x2, long x2_img_stride, float* dx2, float* dx1, int N, int C,
                          int HW, uncl_stream_t stream);
-/* ConvTranspose k2 s2 backward helper: fold the replicate pad and move (dy,dx) into channels: [N][4C/8][H][W][8] */
-int uncl_convT2x2_s2d(const float* dY, float* out, int N, int C, int H, int W, int H2, int W2, uncl_stream_t stream);
+/* ConvTranspose k2 s2 backward helper: fold the replicate pad and move (dy,dx) into channels: [N][4C/8][H][W][8];
+ * out_bf16 (may be NULL): a bf16 copy of the same tensor, the operand of the tensor-core data-gradient GEMM. */
+int uncl_convT2x2_s2d(const float* dY, float* out, void* out_bf16, int N, int C, int H, int W, int H2, int W2,
+                      uncl_stream_t stream);
 /* dW[g][ci][co] += sum_pix X[pix,ci] * dZ[pix,co]   (dW zeroed by the caller) */
 int uncl_pw_wgrad(const float* X, const float* dZ, float* dW, int N, int C_in, int C_out, int groups, int HW,
                   uncl_stream_t stream);

@@ -8,7 +8,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib, packing
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, F32, call
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32, call
 
 
 def _zeros(shape, like):
@@ -88,22 +88,24 @@ class Conv3x3(Function):
         n, _, h, w, _ = x.shape
         ci, co = w9.shape[1], w9.shape[2]
         ho, wo = y.shape[2], y.shape[3]
-        dz = dy.contiguous().clone()
-        db = _zeros(co, dz)
-        call("uncl_relu_bwd_bias", dz, y, y.stride(0), db, n, co, ho * wo, 1 if relu else 0)
+        dy = dy.contiguous()
+        db = _zeros(co, dy)
+        # one pass: ReLU mask + bias gradient + the operand the gradient GEMMs read (bf16 on the tensor-core path)
+        dz = torch.empty(dy.shape, device=dy.device, dtype=torch.bfloat16 if tc else torch.float32)
+        call("uncl_relu_bwd_bias_out", dy, y, y.stride(0), dz, BF16 if tc else F32, db, n, co, ho * wo, 1 if relu else 0)
         dx = None
-        dzb = _to_bf16(dz) if tc else None
+        dzb = dz
         if ctx.needs_input_grad[0]:
             # dgrad of a correlation with pad p = correlation of dz with pad 2-p and the taps reversed / transposed
             wt = w9.flip(0).transpose(1, 2).contiguous()
-            dx = _empty(x.shape, dz)
+            dx = _empty(x.shape, dy)
             if tc:
-                call("uncl_conv3x3_tc", dzb, dzb.stride(0), packing.conv3x3_tc(wt), _zeros(ci, dz), dx, dx.stride(0), F32, n,
+                call("uncl_conv3x3_tc", dzb, dzb.stride(0), packing.conv3x3_tc(wt), _zeros(ci, dy), dx, dx.stride(0), F32, n,
                      co, ho, wo, ci, 2 - pad, ACT_NONE, 0, 0, None, None, None, None)
             else:
-                call("uncl_conv3x3_simt", dz, dz.stride(0), wt, _zeros(ci, dz), dx, dx.stride(0), n, co, ho, wo, ci, 2 - pad,
+                call("uncl_conv3x3_simt", dz, dz.stride(0), wt, _zeros(ci, dy), dx, dx.stride(0), n, co, ho, wo, ci, 2 - pad,
                      ACT_NONE, 0, F32)
-        dw9 = _zeros((9, ci, co), dz)
+        dw9 = _zeros((9, ci, co), dy)
         if tc:
             call("uncl_conv3x3_wgrad_tc", x, x.stride(0), dzb, dw9, n, ci, h, w, co, pad)
         else:
@@ -164,38 +166,51 @@ class MaxPool2(Function):
 
 
 class ConvT2x2(Function):
-    """up.up: nn.ConvTranspose2d(C, C, 2, stride=2) + replicate pad to the skip size.  unet_parts.py:283-299."""
+    """up.up: nn.ConvTranspose2d(C, C, 2, stride=2) + replicate pad to the skip size.  unet_parts.py:283-299.
+    tc=True: forward and data gradient are tensor-core GEMMs on bf16-rounded operands (fp32 accumulation / outputs)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, h2, w2):
+    def forward(ctx, x, weight, bias, h2, w2, tc=False):
         x = x.contiguous()
         n, cb, h, w, _ = x.shape
         c = cb * 8
         y = _empty((n, cb, h2, w2, 8), x)
-        call("uncl_convT2x2", x, x.stride(0), None, 0, 0, packing.convT2x2(weight.detach()),
-             bias.detach().float().contiguous(), y, y.stride(0), n, c, h, w, h2, w2, F32)
+        b = bias.detach().float().contiguous()
+        if tc:
+            xb = _to_bf16(x)
+            call("uncl_convT2x2_tc", xb, xb.stride(0), packing.convT2x2_tc(weight.detach()), b, y, y.stride(0), F32, n, c,
+                 h, w, h2, w2)
+        else:
+            call("uncl_convT2x2", x, x.stride(0), None, 0, 0, packing.convT2x2(weight.detach()), b, y, y.stride(0), n, c,
+                 h, w, h2, w2, F32)
         ctx.save_for_backward(x, weight)
-        ctx.hw2 = (h2, w2)
+        ctx.cfg = (h2, w2, tc)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
-        h2, w2 = ctx.hw2
+        h2, w2, tc = ctx.cfg
         n, cb, h, w, _ = x.shape
         c = cb * 8
         s2d = _empty((n, 4 * cb, h, w, 8), x)
-        call("uncl_convT2x2_s2d", dy.contiguous(), s2d, n, c, h, w, h2, w2)
-        # columns of the GEMM are j = pos*C + co
-        wt = weight.detach().permute(2, 3, 1, 0).reshape(1, 4 * c, c).contiguous().float()   # [1][4C][C]
+        s2d_b = torch.empty(s2d.shape, device=x.device, dtype=torch.bfloat16) if tc else None
+        call("uncl_convT2x2_s2d", dy.contiguous(), s2d, s2d_b, n, c, h, w, h2, w2)
         dx = _empty(x.shape, x)
-        call("uncl_pw_conv", s2d, wt, None, None, None, dx, dx.stride(0), n, 4 * c, c, 1, h * w, ACT_NONE, F32)
+        # columns of the GEMM are j = pos*C + co:  dx[p, ci] = sum_j s2d[p, j] * W[ci, co, dy, dx]
+        if tc:
+            wt = packing.pointwise_tc(weight.detach().permute(0, 2, 3, 1).reshape(c, 4 * c, 1, 1))
+            call("uncl_pw_conv_tc", s2d_b, s2d_b.stride(0), wt, None, None, 0, F32, None, dx, dx.stride(0), F32, n, 4 * c,
+                 c, 1, h, w, ACT_NONE)
+        else:
+            wt = weight.detach().permute(2, 3, 1, 0).reshape(1, 4 * c, c).contiguous().float()   # [1][4C][C]
+            call("uncl_pw_conv", s2d, wt, None, None, None, dx, dx.stride(0), n, 4 * c, c, 1, h * w, ACT_NONE, F32)
         dwp = _zeros((1, c, 4 * c), x)
         call("uncl_pw_wgrad", x, s2d, dwp, n, c, 4 * c, 1, h * w)
         dw = dwp.reshape(c, 2, 2, c).permute(0, 3, 1, 2).contiguous()
         db4 = _zeros(4 * c, x)
         call("uncl_relu_bwd_bias", s2d, None, 0, db4, n, 4 * c, h * w, 0)
-        return dx, dw, db4.reshape(4, c).sum(0), None, None
+        return dx, dw, db4.reshape(4, c).sum(0), None, None, None
 
 
 class SkipConcat(Function):
@@ -243,35 +258,42 @@ class AddPos(Function):
 
 class PwConv(Function):
     """1x1 conv (+groups) with optional GELU, residual and per-sample DropPath scale:
-    out = scale[n] * act(W x + b) + res.  gcn_lib/torch_vertex.py:219-227, torch_nn.py:54-78, Unet_singleFrame.py:36-42."""
+    out = scale[n] * act(W x + b) + res.  gcn_lib/torch_vertex.py:219-227, torch_nn.py:54-78, Unet_singleFrame.py:36-42.
+    tc=True: forward and data gradient are tensor-core GEMMs on bf16-rounded operands (fp32 accumulation / outputs)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, res, scale, groups, gelu):
+    def forward(ctx, x, weight, bias, res, scale, groups, gelu, tc=False):
         x = x.contiguous()
         n, cbi, hw, _ = x.shape
         ci, co = cbi * 8, weight.shape[0]
-        wp = packing.pointwise(weight.detach(), groups)
         b = bias.detach().float().contiguous()
         out = _empty((n, co // 8, hw, 8), x)
         u = None
         if gelu:
             assert res is None and scale is None
             u = _empty(out.shape, x)
-            call("uncl_pw_conv", x, wp, b, None, None, u, u.stride(0), n, ci, co, groups, hw, ACT_NONE, F32)
-            call("uncl_gelu_fwd", u, out, u.numel())
+        r = res.contiguous() if res is not None else None
+        if tc:
+            assert hw == 144
+            xb = _to_bf16(x)
+            wq = packing.pointwise_tc(weight.detach(), groups)
+            call("uncl_pw_conv_tc", xb, xb.stride(0), wq, b, r, r.stride(0) if r is not None else 0, F32, scale,
+                 u if gelu else out, out.stride(0), F32, n, ci, co, groups, 12, 12, ACT_NONE)
         else:
-            call("uncl_pw_conv", x, wp, b, res.contiguous() if res is not None else None, scale, out, out.stride(0), n, ci,
-                 co, groups, hw, ACT_NONE, F32)
-        ctx.save_for_backward(x, wp, u, scale)
-        ctx.cfg = (groups, gelu, res is not None)
+            wq = packing.pointwise(weight.detach(), groups)
+            call("uncl_pw_conv", x, wq, b, r, scale, u if gelu else out, out.stride(0), n, ci, co, groups, hw, ACT_NONE, F32)
+        if gelu:
+            call("uncl_gelu_fwd", u, out, u.numel())
+        ctx.save_for_backward(x, weight, u, scale)
+        ctx.cfg = (groups, gelu, res is not None, tc)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, wp, u, scale = ctx.saved_tensors
-        groups, gelu, has_res = ctx.cfg
+        x, weight, u, scale = ctx.saved_tensors
+        groups, gelu, has_res, tc = ctx.cfg
         n, cbi, hw, _ = x.shape
-        ci, co = cbi * 8, wp.shape[0] * wp.shape[2]
+        ci, co = cbi * 8, weight.shape[0]
         dout = dout.contiguous()
         d = dout
         if scale is not None:
@@ -283,15 +305,22 @@ class PwConv(Function):
             d = du
         dx = None
         if ctx.needs_input_grad[0]:
-            wt = wp.transpose(1, 2).contiguous()   # [g][Cout_g][Cin_g]
             dx = _empty(x.shape, x)
-            call("uncl_pw_conv", d, wt, None, None, None, dx, dx.stride(0), n, co, ci, groups, hw, ACT_NONE, F32)
-        dwp = _zeros(wp.shape, x)
+            if tc:
+                # transposed 1x1 conv: per group [C_out/g -> C_in/g], i.e. a conv with weight [C_in][C_out/g]
+                wt = weight.detach().reshape(groups, co // groups, ci // groups).transpose(1, 2).reshape(ci, co // groups, 1, 1)
+                db16 = _to_bf16(d)
+                call("uncl_pw_conv_tc", db16, db16.stride(0), packing.pointwise_tc(wt, groups), None, None, 0, F32, None, dx,
+                     dx.stride(0), F32, n, co, ci, groups, 12, 12, ACT_NONE)
+            else:
+                wt = packing.pointwise(weight.detach(), groups).transpose(1, 2).contiguous()   # [g][Cout_g][Cin_g]
+                call("uncl_pw_conv", d, wt, None, None, None, dx, dx.stride(0), n, co, ci, groups, hw, ACT_NONE, F32)
+        dwp = _zeros((groups, ci // groups, co // groups), x)
         call("uncl_pw_wgrad", x, d, dwp, n, ci, co, groups, hw)
         dw = dwp.permute(0, 2, 1).reshape(co, ci // groups, 1, 1).contiguous()
         db = _zeros(co, x)
         call("uncl_relu_bwd_bias", d, None, 0, db, n, co, hw, 0)
-        return dx, dw, db, (dout if has_res else None), None, None, None
+        return dx, dw, db, (dout if has_res else None), None, None, None, None
 
 
 class KnnAggregate(Function):

@@ -55,6 +55,44 @@ __global__ void __launch_bounds__(256) relu_bwd_bias_kernel(float* __restrict__ 
   }
 }
 
+// out-of-place variant: dZ = dY * (Y > 0) written as fp32 or bf16 (the tensor-core dgrad / wgrad operand), db += sum dZ
+template <typename TO>
+__global__ void __launch_bounds__(256) relu_bwd_bias_out_kernel(const float* __restrict__ dY, const float* __restrict__ Y,
+                                                               long y_img_stride, TO* __restrict__ dZ,
+                                                               float* __restrict__ db, int C, int HW, int apply_relu) {
+  __shared__ float red[8][8];
+  const int cb = blockIdx.y, n = blockIdx.z;
+  const long base = ((long)n * (C / 8) + cb) * HW * 8;
+  const float* y = Y ? Y + (long)n * y_img_stride + (long)cb * HW * 8 : nullptr;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < HW; p += gridDim.x * 256) {
+    float g[8];
+    load8(dY + base + (long)p * 8, g);
+    if (apply_relu) {
+      float v[8];
+      load8(y + (long)p * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = v[j] > 0.f ? g[j] : 0.f;
+    }
+    store8(dZ + base + (long)p * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += g[j];
+  }
+  if (db == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = warp_sum(s[j]);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[wid][j] = s[j];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(db + cb * 8 + threadIdx.x, t);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // 3x3 weight gradient: dW9[t][ci][co] += sum_{n,y,x} X[n, ci, y+ky-pad, x+kx-pad] * dZ[n, co, y, x]
 // CTA: one input channel block (8 ci) x CO_T output channels x 9 taps, over a strided subset of 8x32 pixel tiles.
@@ -257,8 +295,9 @@ __global__ void __launch_bounds__(256) skip_concat_bwd_kernel(const float* __res
 //   out[n, pos*C + co, y, x] = sum over the padded copies of dY[n, co, 2y+dy, 2x+dx]   (pos = dy*2+dx)
 // after which dX = pointwise conv with W^T, dW = pointwise weight gradient, db = column sums.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) convT2x2_s2d_kernel(const float* __restrict__ dY, float* __restrict__ out, int C,
-                                                          int H, int W, int H2, int W2, int N) {
+__global__ void __launch_bounds__(256) convT2x2_s2d_kernel(const float* __restrict__ dY, float* __restrict__ out,
+                                                          bf16* __restrict__ out_b, int C, int H, int W, int H2, int W2,
+                                                          int N) {
   const int Cb = C / 8;
   const long total = (long)N * 4 * Cb * H * W;
   const int padT = (H2 - 2 * H) / 2, padL = (W2 - 2 * W) / 2;
@@ -278,7 +317,9 @@ __global__ void __launch_bounds__(256) convT2x2_s2d_kernel(const float* __restri
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[j] += v[j];
       }
-    store8(out + (((long)n * 4 * Cb + cb4) * H * W + (long)y * W + x) * 8, s);
+    const long o = (((long)n * 4 * Cb + cb4) * H * W + (long)y * W + x) * 8;
+    store8(out + o, s);
+    if (out_b != nullptr) store8(out_b + o, s);
   }
 }
 
@@ -452,6 +493,15 @@ extern "C" int uncl_relu_bwd_bias(float* dY, const float* Y, long y_img_stride, 
   return uncl_check_launch("relu_bwd_bias");
 }
 
+extern "C" int uncl_relu_bwd_bias_out(const float* dY, const float* Y, long y_img_stride, void* dZ, int dz_dtype, float* db,
+                                      int N, int C, int HW, int apply_relu, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && C % 8 == 0 && HW > 0 && (!apply_relu || Y) && dZ, "relu_bwd_bias_out: bad arguments");
+  int gx = (HW + 255) / 256;
+  if (gx > 64) gx = 64;
+  UNCL_DISPATCH_DTYPE(dz_dtype, T, (relu_bwd_bias_out_kernel<T><<<dim3(gx, C / 8, N), 256, 0, stream>>>(dY, Y, y_img_stride, (T*)dZ, db, C, HW, apply_relu)));
+  return uncl_check_launch("relu_bwd_bias_out");
+}
+
 extern "C" int uncl_conv3x3_wgrad(const float* X, long x_img_stride, const float* dZ, float* dW9, int N, int C_in,
                                   int H, int W, int C_out, int pad, cudaStream_t stream) {
   UNCL_REQUIRE(N > 0 && C_in % 8 == 0 && C_out % 32 == 0 && (pad == 0 || pad == 2), "conv3x3_wgrad: unsupported shape");
@@ -497,10 +547,10 @@ extern "C" int uncl_skip_concat_bwd(const float* dcat, const float* x2, long x2_
   return uncl_check_launch("skip_concat_bwd");
 }
 
-extern "C" int uncl_convT2x2_s2d(const float* dY, float* out, int N, int C, int H, int W, int H2, int W2,
+extern "C" int uncl_convT2x2_s2d(const float* dY, float* out, void* out_bf16, int N, int C, int H, int W, int H2, int W2,
                                  cudaStream_t stream) {
   UNCL_REQUIRE(N > 0 && C % 8 == 0 && H2 >= 2 * H && W2 >= 2 * W, "convT2x2_s2d: bad shape");
-  convT2x2_s2d_kernel<<<cap_grid((long)N * 4 * (C / 8) * H * W, 256, 8), 256, 0, stream>>>(dY, out, C, H, W, H2, W2, N);
+  convT2x2_s2d_kernel<<<cap_grid((long)N * 4 * (C / 8) * H * W, 256, 8), 256, 0, stream>>>(dY, out, (bf16*)out_bf16, C, H, W, H2, W2, N);
   return uncl_check_launch("convT2x2_s2d");
 }
 

@@ -330,19 +330,19 @@ class _GeneratorBase(nn.Module):
         s0 = droppath_scale[0] if droppath_scale is not None else None
         s1 = droppath_scale[1] if droppath_scale is not None else None
         x0 = A.AddPos.apply(cur, self.gcn.pos_embed)
-        y = A.PwConv.apply(x0, g.fc1[0].weight, g.fc1[0].bias, None, None, 1, False)
+        y = A.PwConv.apply(x0, g.fc1[0].weight, g.fc1[0].bias, None, None, 1, False, False)   # feeds KNN: fp32
         z = A.KnnAggregate.apply(y, g.relative_pos.detach().reshape(144, 144).float().contiguous())
         gc = g.graph_conv.gconv.nn[0]
-        z2 = A.PwConv.apply(z, gc.weight, gc.bias, None, None, 4, True)
-        x1 = A.PwConv.apply(z2, g.fc2[0].weight, g.fc2[0].bias, x0, s0, 1, False)
-        f1 = A.PwConv.apply(x1, ffn.fc1[0].weight, ffn.fc1[0].bias, None, None, 1, True)
-        up = A.PwConv.apply(f1, ffn.fc2[0].weight, ffn.fc2[0].bias, x1, s1, 1, False).reshape(n, -1, 12, 12, 8)
+        z2 = A.PwConv.apply(z, gc.weight, gc.bias, None, None, 4, True, tc)
+        x1 = A.PwConv.apply(z2, g.fc2[0].weight, g.fc2[0].bias, x0, s0, 1, False, tc)
+        f1 = A.PwConv.apply(x1, ffn.fc1[0].weight, ffn.fc1[0].bias, None, None, 1, True, tc)
+        up = A.PwConv.apply(f1, ffn.fc2[0].weight, ffn.fc2[0].bias, x1, s1, 1, False, tc).reshape(n, -1, 12, 12, 8)
         state.append(up)
         for i in range(4):
             u = self.up_path[i]
             sk = skips[3 - i]
             fea = up if prev is None else A.SpliceChannels.apply(up, prev[5 + i], up.shape[1] * 8 // 32)
-            x1u = A.ConvT2x2.apply(fea, u.up.weight, u.up.bias, sk.shape[2], sk.shape[3])
+            x1u = A.ConvT2x2.apply(fea, u.up.weight, u.up.bias, sk.shape[2], sk.shape[3], tc)
             cat = A.SkipConcat.apply(sk, x1u)
             m = A.Conv3x3.apply(cat, u.conv.conv.weight, u.conv.conv.bias, True, True, tc)
             up = A.Conv3x3.apply(m, u.conv.conv1.weight, u.conv.conv1.bias, True, True, tc)

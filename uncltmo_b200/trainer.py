@@ -70,6 +70,7 @@ class GanTrainerStep:
         w = self.adv_weight_list[0] * (1.0 if epoch <= self.epoch_step1 else 1e-6)
         self.errD = w * losses.contrastive_D_loss(all_gather_cat(d_real_pos), all_gather_cat(d_fake))
         self.errD.backward()
+        self.errD = self.errD.detach()   # keep the value, let the graph (and its AccumulateGrad nodes) go
         if self.buckets_D is not None:
             self.buckets_D.allreduce()
         self.optimizerD.step()
@@ -119,6 +120,10 @@ class GanTrainerStep:
             self.errG_struct = (self.struct_loss_factor / self.world) * self.struct_loss(fake, None, hdr, self.pyramid_weight_list)
             total = total + self.errG_struct
         total.backward()
+        del total
+        self.errG_d = self.errG_d.detach()
+        if self.errG_struct is not None:
+            self.errG_struct = self.errG_struct.detach()
         if self.buckets_G is not None:
             self.buckets_G.allreduce()
         self.optimizerG.step()
@@ -128,3 +133,48 @@ class GanTrainerStep:
         """One iteration of GanTrainer.train_epoch's loop body (GanTrainerImg.py:178-186)."""
         self.train_D(hdr_input, real_ldr_pos, real_ldr_neg, epoch)
         return self.train_G(hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch)
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole iteration
+    def _branch(self, epoch):
+        return 0 if epoch <= self.epoch_step1 else (1 if epoch <= self.epoch_step2 else 2)
+
+    def capture(self, hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch, warmup=3):
+        """Capture one whole iteration - train_D, train_G, both optimizer steps and (multi-GPU) the gradient
+        all-reduces - into a CUDA graph for the loss schedule `epoch` falls in.  The step makes ~1000 kernel launches of
+        10 us each and has no host synchronisation, so a replay removes the launch-bound floor (it matters most when the
+        batch is split over several GPUs).  `warmup` REAL iterations run on the given batch first (lazy optimizer state
+        and lazily initialised kernels must exist before the capture).  Optimizers must be built with capturable=True.
+        Input shapes are frozen; `replay` copies new batches into the captured buffers."""
+        for opt in (self.optimizerG, self.optimizerD):
+            if not all(g.get("capturable", False) for g in opt.param_groups):
+                raise ValueError("GanTrainerStep.capture needs optimizers constructed with capturable=True")
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        static = [hdr_input.clone(), real_ldr_pos.clone(), real_ldr_neg.clone()]
+        self.errD = self.errG_d = self.errG_struct = None
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self.step(static[0], None, static[1], static[2], epoch)
+        torch.cuda.current_stream().wait_stream(side)
+        self.netG.zero_grad(set_to_none=True)
+        self.netD.zero_grad(set_to_none=True)
+        self.netG._packed = None      # the weight re-layout of the D-step generator pass must be part of the graph
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            err_g, err_s = self.step(static[0], None, static[1], static[2], epoch)
+        self.netG._packed = None
+        self._graphs[self._branch(epoch)] = (graph, static, (self.errD, err_g, err_s))
+        return graph
+
+    def replay(self, hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch):
+        """`step` through the captured graph: returns (errG_d, errG_struct); `self.errD` as after `step`."""
+        graph, static, (err_d, err_g, err_s) = self._graphs[self._branch(epoch)]
+        for dst, src in zip(static, (hdr_input, real_ldr_pos, real_ldr_neg)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        graph.replay()
+        self.netG._packed = None      # parameters changed behind the version counters the packing cache keys on
+        self.errD, self.errG_d, self.errG_struct = err_d, err_g, err_s
+        return err_g, err_s
