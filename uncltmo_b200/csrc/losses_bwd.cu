@@ -357,65 +357,140 @@ __global__ void __launch_bounds__(256) disc_top_bwd_kernel(const float* __restri
   if (threadIdx.x < 32) atomicAdd(dw3 + threadIdx.x, s_acc[threadIdx.x]);
   if (threadIdx.x == 32) atomicAdd(db3, s_acc[32]);
 }
-// generic 4x4 stride-2 conv weight gradient: dW[co][ci][k] += sum in[n][ci][2oy+ky][2ox+kx] * dz[n][co][oy][ox]; db[co] += sum dz
-// grid (Cout, Cin, pixel split), block 256; dW / db are accumulated with atomics (zeroed by the caller)
+// 4x4 stride-2 conv weight gradient: dW[co][ci][k] += sum in[n][ci][2oy+ky][2ox+kx] * dz[n][co][oy][ox]; db[co] += sum dz
+// A CTA takes a contiguous slice of the N*Ho*Wo output pixels.  Thread = (patch element pi = ci*16 + k, pixel group pg),
+// COUT accumulators in registers; the dz row of a pixel (COUT values) is broadcast from shared memory, the input value
+// is read once per (pixel, patch element) - the previous version re-read the patch once per output channel.
+// Partial sums are combined in shared memory, then one global atomic per (co, ci, k) per CTA (dW / db zeroed by caller).
+template <int CIN, int COUT>
 __global__ void __launch_bounds__(256) conv4s2_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dz,
-                                                           float* __restrict__ dW, float* __restrict__ db, int Cin,
-                                                           int Cout, int Hi, int Wi, int Ho, int Wo, int N) {
-  __shared__ float red[8][17];
-  const int co = blockIdx.x, ci = blockIdx.y;
-  float acc[17];
+                                                           float* __restrict__ dW, float* __restrict__ db, int Hi, int Wi,
+                                                           int Ho, int Wo, long total, long per_cta) {
+  constexpr int PL = CIN * 16;        // patch lanes
+  constexpr int G = 256 / PL;         // pixel groups
+  constexpr int CH = 32;              // pixels staged per chunk
+  __shared__ __align__(16) float s_dz[CH][COUT];
+  __shared__ long s_off[CH];
+  __shared__ float s_acc[COUT][PL + 1];
+  __shared__ float s_db[COUT];
+  const int pi = threadIdx.x % PL, pg = threadIdx.x / PL;
+  const int ci = pi >> 4, k = pi & 15;
+  const long poff = (long)ci * Hi * Wi + (k >> 2) * Wi + (k & 3);
+  const long HWo = (long)Ho * Wo;
+  float acc[COUT];
 #pragma unroll
-  for (int k = 0; k < 17; ++k) acc[k] = 0.f;
-  const long total = (long)N * Ho * Wo;
-  for (long i = (long)blockIdx.z * 256 + threadIdx.x; i < total; i += (long)gridDim.z * 256) {
-    const int ox = i % Wo, oy = (i / Wo) % Ho;
-    const long n = i / ((long)Wo * Ho);
-    const float g = dz[((n * Cout + co) * Ho + oy) * Wo + ox];
-    const float* p = in + ((n * Cin + ci) * Hi + 2 * oy) * Wi + 2 * ox;
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+  float accb = 0.f;
+  for (int i = threadIdx.x; i < COUT * (PL + 1); i += 256) (&s_acc[0][0])[i] = 0.f;
+  if (threadIdx.x < COUT) s_db[threadIdx.x] = 0.f;
+  const long p_begin = (long)blockIdx.x * per_cta;
+  const long p_end = p_begin + per_cta < total ? p_begin + per_cta : total;
+  for (long p0 = p_begin; p0 < p_end; p0 += CH) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < CH * COUT; i += 256) {
+      const int px = i % CH, co = i / CH;
+      const long p = p0 + px;
+      float v = 0.f;
+      if (p < p_end) {
+        const long n = p / HWo, r = p - n * HWo;
+        v = dz[(n * COUT + co) * HWo + r];
+        if (co == 0) {
+          const int oy = (int)(r / Wo), ox = (int)(r - (long)oy * Wo);
+          s_off[px] = (n * CIN * Hi + 2 * oy) * (long)Wi + 2 * ox;
+        }
+      } else if (co == 0) {
+        s_off[px] = -1;
+      }
+      s_dz[px][co] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < COUT) {
+      float t = 0.f;
+#pragma unroll 8
+      for (int px = 0; px < CH; ++px) t += s_dz[px][threadIdx.x];
+      accb += t;
+    }
+    for (int px = pg; px < CH; px += G) {
+      const long off = s_off[px];
+      if (off < 0) break;
+      const float v = __ldg(in + off + poff);
+      const float4* d4 = reinterpret_cast<const float4*>(&s_dz[px][0]);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = fmaf(__ldg(p + (k >> 2) * Wi + (k & 3)), g, acc[k]);
-    acc[16] += g;
-  }
-#pragma unroll
-  for (int k = 0; k < 17; ++k) acc[k] = warp_sum(acc[k]);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0)
-#pragma unroll
-    for (int k = 0; k < 17; ++k) red[wid][k] = acc[k];
-  __syncthreads();
-  if (threadIdx.x < 17) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    if (threadIdx.x < 16) atomicAdd(dW + ((long)co * Cin + ci) * 16 + threadIdx.x, s);
-    else if (ci == 0 && db) atomicAdd(db + co, s);
-  }
-}
-// generic 4x4 stride-2 conv data gradient: d_in[n][ci][y][x] = sum_{co,k} dz[n][co][(y-ky)/2][(x-kx)/2] * w[co][ci][k]
-// optionally times lrelu'(act_in) (act_in = the post-LeakyReLU tensor that fed the conv)
-__global__ void __launch_bounds__(256) conv4s2_dgrad_kernel(const float* __restrict__ dz, const float* __restrict__ w,
-                                                           const float* __restrict__ act_in, float* __restrict__ d_in,
-                                                           int Cin, int Cout, int Hi, int Wi, int Ho, int Wo, long total) {
-  extern __shared__ float s_w[];  // [Cout][Cin][16]
-  for (int i = threadIdx.x; i < Cout * Cin * 16; i += 256) s_w[i] = w[i];
-  __syncthreads();
-  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
-    const int x = i % Wi, y = (i / Wi) % Hi, ci = (i / ((long)Wi * Hi)) % Cin;
-    const long n = i / ((long)Wi * Hi * Cin);
-    float acc = 0.f;
-    for (int ky = (y & 1); ky < 4; ky += 2) {
-      const int oy = (y - ky) >> 1;
-      if (y - ky < 0 || oy >= Ho) continue;
-      for (int kx = (x & 1); kx < 4; kx += 2) {
-        const int ox = (x - kx) >> 1;
-        if (x - kx < 0 || ox >= Wo) continue;
-        const float* dp = dz + (n * Cout * Ho + oy) * Wo + ox;
-        for (int co = 0; co < Cout; ++co)
-          acc = fmaf(__ldg(dp + (long)co * Ho * Wo), s_w[(co * Cin + ci) * 16 + ky * 4 + kx], acc);
+      for (int c4 = 0; c4 < COUT / 4; ++c4) {
+        const float4 d = d4[c4];
+        acc[c4 * 4 + 0] = fmaf(v, d.x, acc[c4 * 4 + 0]);
+        acc[c4 * 4 + 1] = fmaf(v, d.y, acc[c4 * 4 + 1]);
+        acc[c4 * 4 + 2] = fmaf(v, d.z, acc[c4 * 4 + 2]);
+        acc[c4 * 4 + 3] = fmaf(v, d.w, acc[c4 * 4 + 3]);
       }
     }
-    if (act_in) acc *= act_in[i] > 0.f ? 1.f : 0.2f;
-    d_in[i] = acc;
+  }
+  __syncthreads();
+  if (G == 1) {
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) s_acc[c][pi] = acc[c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) atomicAdd(&s_acc[c][pi], acc[c]);
+  }
+  if (threadIdx.x < COUT) s_db[threadIdx.x] = accb;
+  __syncthreads();
+  for (int i = threadIdx.x; i < COUT * PL; i += 256) {
+    const int co = i / PL, q = i - co * PL;   // q = ci*16 + k: dW is [co][ci][16]
+    atomicAdd(dW + (long)co * PL + q, s_acc[co][q]);
+  }
+  if (db && threadIdx.x < COUT) atomicAdd(db + threadIdx.x, s_db[threadIdx.x]);
+}
+
+// 4x4 stride-2 conv data gradient: d_in[n][ci][y][x] = sum_{co,k} dz[n][co][(y-ky)/2][(x-kx)/2] * w[co][ci][k],
+// optionally times lrelu'(act_in) (act_in = the post-LeakyReLU tensor that fed the conv).
+// blockIdx.y = parity class (y&1, x&1): all threads of a CTA use the same (ky, kx) taps, so the weights are shared-memory
+// broadcasts; a thread owns one pixel and all CIN input channels, each dz value is loaded once for CIN FMAs.
+template <int CIN>
+__global__ void __launch_bounds__(256) conv4s2_dgrad_kernel(const float* __restrict__ dz, const float* __restrict__ w,
+                                                           const float* __restrict__ act_in, float* __restrict__ d_in,
+                                                           int Cout, int Hi, int Wi, int Ho, int Wo, int N) {
+  extern __shared__ __align__(16) float s_w[];  // [16 k][Cout][CIN]
+  for (int i = threadIdx.x; i < Cout * CIN * 16; i += 256) {
+    const int k = i & 15, ci = (i >> 4) % CIN, co = i / (16 * CIN);
+    s_w[(k * Cout + co) * CIN + ci] = w[i];   // w is [co][ci][k]
+  }
+  __syncthreads();
+  const int py = blockIdx.y >> 1, px = blockIdx.y & 1;
+  const int Hh = (Hi - py + 1) / 2, Wh = (Wi - px + 1) / 2;
+  const long total = (long)N * Hh * Wh;
+  const long HWo = (long)Ho * Wo, HWi = (long)Hi * Wi;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int x2 = (int)(i % Wh), y2 = (int)((i / Wh) % Hh);
+    const long n = i / ((long)Wh * Hh);
+    const int y = 2 * y2 + py, x = 2 * x2 + px;
+    float acc[CIN];
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int oy = y2 - a, ky = py + 2 * a;
+      if (oy < 0 || oy >= Ho) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ox = x2 - b, kx = px + 2 * b;
+        if (ox < 0 || ox >= Wo) continue;
+        const float* dp = dz + n * Cout * HWo + (long)oy * Wo + ox;
+        const float* wk = s_w + (size_t)(ky * 4 + kx) * Cout * CIN;
+        for (int co = 0; co < Cout; ++co) {
+          const float g = __ldg(dp + co * HWo);
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) acc[c] = fmaf(g, wk[co * CIN + c], acc[c]);
+        }
+      }
+    }
+    const long o = n * CIN * HWi + (long)y * Wi + x;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      float v = acc[c];
+      if (act_in) v *= act_in[o + c * HWi] > 0.f ? 1.f : 0.2f;
+      d_in[o + c * HWi] = v;
+    }
   }
 }
 
@@ -527,15 +602,18 @@ extern "C" int uncl_disc_backward(const float* x, const float* h1, const float* 
   float* d_z1 = scratch + (long)N * 32 * P;
   disc_tail_bwd_kernel<<<ceil_div(P, 256), 256, 0, stream>>>(d_logits, w_tail, fea, d_fea, dw_tail, P, N);
   disc_top_bwd_kernel<<<cap_grid((long)N * P, 256, 2), 256, 0, stream>>>(d_fea, a2, w3, d_z2, dw3, db3, P, N);
-  conv4s2_wgrad_kernel<<<dim3(32, 16, 4), 256, 0, stream>>>(h1, d_z2, dw2, db2, 16, 32, H1, H1, H2, H2, N);
-  const long t1 = (long)N * 16 * H1 * H1;
-  cudaError_t e = cudaFuncSetAttribute(conv4s2_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 16 * 16 * 4);
+  const int ctas = 148 * 2;
+  const long t2 = (long)N * H2 * H2;
+  conv4s2_wgrad_kernel<16, 32><<<ctas, 256, 0, stream>>>(h1, d_z2, dw2, db2, H1, H1, H2, H2, t2, (t2 + ctas - 1) / ctas);
+  cudaError_t e = cudaFuncSetAttribute(conv4s2_dgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 16 * 16 * 4);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "disc_backward: %s", cudaGetErrorString(e));
-  conv4s2_dgrad_kernel<<<cap_grid(t1, 256, 8), 256, 32 * 16 * 16 * 4, stream>>>(d_z2, w2, h1, d_z1, 16, 32, H1, H1, H2, H2, t1);
-  conv4s2_wgrad_kernel<<<dim3(16, 1, 64), 256, 0, stream>>>(x, d_z1, dw1, db1, 1, 16, H, H, H1, H1, N);
+  const long q1 = (long)N * 64 * 64;   // pixels per parity class (upper bound)
+  conv4s2_dgrad_kernel<16><<<dim3(cap_grid(q1, 256, 2), 4), 256, 32 * 16 * 16 * 4, stream>>>(d_z2, w2, h1, d_z1, 32, H1, H1, H2, H2, N);
+  const long t1 = (long)N * H1 * H1;
+  conv4s2_wgrad_kernel<1, 16><<<ctas, 256, 0, stream>>>(x, d_z1, dw1, db1, H, H, H1, H1, t1, (t1 + ctas - 1) / ctas);
   if (dx) {
-    const long t0 = (long)N * H * H;
-    conv4s2_dgrad_kernel<<<cap_grid(t0, 256, 8), 256, 16 * 16 * 4, stream>>>(d_z1, w1, nullptr, dx, 1, 16, H, H, H1, H1, t0);
+    const long q0 = (long)N * 128 * 128;
+    conv4s2_dgrad_kernel<1><<<dim3(cap_grid(q0, 256, 4), 4), 256, 16 * 16 * 4, stream>>>(d_z1, w1, nullptr, dx, 16, H, H, H1, H1, N);
   }
   return uncl_check_launch("disc_backward");
 }
