@@ -111,6 +111,10 @@ int uncl_pw_conv(const float* in, const float* w, const float* bias, const float
 int uncl_gcn_knn_aggregate(const float* y, const float* relpos, void* z, int z_dtype, int* idx_out, int N, int C,
                            uncl_stream_t stream);
 
+/* Diagnostics for profiling only: per-role cycle counters of the tensor-core conv kernels (8 uint64 on the device,
+ * zeroed by the caller; NULL switches off).  See conv_tc.cu. */
+int uncl_conv_tc_set_debug(void* counters);
+
 /* The same 1x1 (grouped) conv as a tcgen05 GEMM per group, bf16 operands / fp32 accumulation:
  * out = scale[n] * act(W x + b) + res, act in {none, ReLU, GELU}.  Also the data gradient of the k2 s2 up-convolution
  * (4C -> C over the space-to-depth gradient).  in: bf16 blocked [N][C_in/8][H][W][8], W <= 128;

@@ -19,6 +19,7 @@
 //     A row only feeds its own D row, so those rows are simply masked in the epilogue.
 // Weights are pre-packed per 16-channel K-chunk as [9 taps][2][NT][8] bf16 (K-major B operand, LBO = NT*16 B),
 // fetched with one cp.async.bulk per stage.
+#include <cstdlib>
 #include "tc_ptx.cuh"
 
 namespace {
@@ -57,6 +58,8 @@ struct TcParams {
   int res_f32;
   const float* scale;       // per-image factor (DropPath) or null
   int ns_per_group;         // grouped 1x1 conv: N splits per group (K range of a split = its group's input channels)
+  int dbg_align;            // diagnostics: issue every tap from a 128-byte aligned address (WRONG results, timing probe)
+  unsigned long long* dbg;  // diagnostics (uncl_conv_tc_set_debug): cycle counters of the three roles, or null
 };
 
 // ---------------------------------------------------------------- tile geometry shared by the three roles
@@ -142,18 +145,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       const int a_stage_bytes = p.a_stage_bytes;
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
       const int ns_per_group = p.ns_per_group;
+      unsigned long long* const dbg = p.dbg;
+      long long w_empty = 0;
+      const long long t_begin = dbg ? clock64() : 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const Item it = decode_item(geo, item);
         const uint8_t* wsrc = wbase + (size_t)it.ns * nchunk * b_bytes;
         const int kblk0 = (it.ns / ns_per_group) * nchunk * 2;   // first input channel block of this split's group
         for (int ch = 0; ch < nchunk; ++ch) {
+          const long long tw0 = dbg ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1);
+          if (dbg) w_empty += clock64() - tw0;
           uint8_t* sa = stage_base + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full[stage], tx_bytes);
           tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, kblk0 + ch * 2, it.n);
           bulk_load(sa + a_stage_bytes, wsrc + (size_t)ch * b_bytes, b_bytes, &full[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
+      }
+      if (dbg) {
+        atomicAdd(dbg + 0, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(dbg + 1, (unsigned long long)w_empty);
       }
     }
     __syncwarp();
@@ -171,19 +183,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       const uint32_t mstep = 128u;
       const uint32_t pw = (uint32_t)p.PW, nt = (uint32_t)p.NT;
       const bool taps9 = p.ntaps == 9;
+      const bool dbg_align = p.dbg_align != 0;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      unsigned long long* const dbg = p.dbg;
+      long long w_full = 0, w_tempty = 0;
+      const long long t_begin = dbg ? clock64() : 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const Item it = decode_item(geo, item);
+        const long long tw0 = dbg ? clock64() : 0;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
+        if (dbg) w_tempty += clock64() - tw0;
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * kAccCols);
         const uint32_t mb = (uint32_t)it.mb_act;
         for (int ch = 0; ch < nchunk; ++ch) {
+          const long long tw1 = dbg ? clock64() : 0;
           mbar_wait(&full[stage], phase);
+          if (dbg) w_full += clock64() - tw1;
           tc_fence_after();
           const uint32_t sa16 = stage0_16 + (uint32_t)stage * stage_16;
-          uint32_t a_row = a_lo_const | (sa16 + (uint32_t)it.moff0);
+          uint32_t a_row = a_lo_const | (sa16 + (uint32_t)(dbg_align ? (it.moff0 & ~7) : it.moff0));
           uint32_t b_lo = b_lo_const | (sa16 + a_bytes_16);
           if (taps9) {
 #pragma unroll
@@ -191,7 +211,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 #pragma unroll
               for (int kx = 0; kx < 3; ++kx) {
                 const uint32_t accum = (ky > 0 || kx > 0) ? 1u : (ch > 0 ? 1u : 0u);
-                uint32_t a_lo = a_row + (uint32_t)kx, d = d0;
+                uint32_t a_lo = a_row + (dbg_align ? 0u : (uint32_t)kx), d = d0;
                 if (elect_one()) {
                   for (uint32_t b = 0; b < mb; ++b) {
                     tc_mma_bf16(d, a_lo, desc_hi, b_lo, desc_hi, idesc, accum);
@@ -202,7 +222,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 __syncwarp();
                 b_lo += b_tap_16;
               }
-              a_row += pw;
+              a_row += dbg_align ? (pw & ~7u) : pw;
             }
           } else {
             uint32_t a_lo = a_row, d = d0;
@@ -222,6 +242,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         if (elect_one()) tc_commit(&tfull[acc]);
         __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (dbg && lane == 0) {
+        atomicAdd(dbg + 2, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(dbg + 3, (unsigned long long)w_full);
+        atomicAdd(dbg + 4, (unsigned long long)w_tempty);
       }
     }
     __syncwarp();
@@ -245,9 +270,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     int acc = 0;
     uint32_t acc_phase = 0;
+    unsigned long long* const dbg = (warp == 2 && lane == 0) ? p.dbg : nullptr;
+    long long w_tfull = 0;
+    const long long t_begin = dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const Item it = decode_item(geo, item);
+      const long long tw0 = dbg ? clock64() : 0;
       mbar_wait(&tfull[acc], acc_phase);
+      if (dbg) w_tfull += clock64() - tw0;
       tc_fence_after();
       if constexpr (EPI == 0) {
         const int cbase0 = it.ns * NT;
@@ -339,8 +369,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         }
       } else {
         // ConvTranspose k2 s2: column j = pos * C + co, pos = dy * 2 + dx; out pixel (2y+dy, 2x+dx) (+ replicate pad)
+        // C % 32 == 0, so a 32-column chunk lies inside one pos: all index arithmetic is per chunk, not per store
         const int C = p.sh_C, H2 = p.sh_H2, W2 = p.sh_W2, Hi = Ho, Wi = Wo;
         const int padT = (H2 - 2 * Hi) / 2, padL = (W2 - 2 * Wi) / 2;
+        const bool padded = (H2 != 2 * Hi) || (W2 != 2 * Wi);
         const long cb2 = (long)H2 * W2 * 8;
         bf16* const out_img_n = out + (long)it.n * out_img_stride;
         float* const outf_img_n = outf + (long)it.n * out_img_stride;
@@ -352,22 +384,36 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             uint32_t r[32];
             tc_ld32(tmem_base + lane_base + (uint32_t)(acc * kAccCols + b * NT + c0), r);
             if (valid) {
+              const int j0 = it.ns * NT + c0;
+              const int pos = j0 / C, co0 = j0 - pos * C;
+              const int Y = 2 * y + (pos >> 1), X = 2 * x + (pos & 1);
+              const float* bias = s_bias + co0;
+              const long o0 = (long)(co0 / 8) * cb2;
+              if (!padded) {
+                const long o = o0 + ((long)Y * W2 + X) * 8;
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int j0 = it.ns * NT + c0 + g * 8;
-                const int pos = j0 / C, co0 = j0 - pos * C;
-                const int Y = 2 * y + (pos >> 1), X = 2 * x + (pos & 1);
-                float v[8];
+                for (int g = 0; g < 4; ++g) {
+                  float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) + s_bias[co0 + j];
+                  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) + bias[g * 8 + j];
+                  if (out_f32) store8(outf_img_n + o + g * cb2, v);
+                  else store8(out_img_n + o + g * cb2, v);
+                }
+              } else {
                 const int y_lo = (Y == 0) ? 0 : Y + padT, y_hi = (Y == 2 * Hi - 1) ? H2 - 1 : Y + padT;
                 const int x_lo = (X == 0) ? 0 : X + padL, x_hi = (X == 2 * Wi - 1) ? W2 - 1 : X + padL;
-                const long o = (long)(co0 / 8) * cb2;
-                for (int yy = y_lo; yy <= y_hi; ++yy)
-                  for (int xx = x_lo; xx <= x_hi; ++xx) {
-                    if (out_f32) store8(outf_img_n + o + ((long)yy * W2 + xx) * 8, v);
-                    else store8(out_img_n + o + ((long)yy * W2 + xx) * 8, v);
-                  }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  float v[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) + bias[g * 8 + j];
+                  for (int yy = y_lo; yy <= y_hi; ++yy)
+                    for (int xx = x_lo; xx <= x_hi; ++xx) {
+                      const long o = o0 + g * cb2 + ((long)yy * W2 + xx) * 8;
+                      if (out_f32) store8(outf_img_n + o, v);
+                      else store8(out_img_n + o, v);
+                    }
+                }
               }
             }
           }
@@ -377,6 +423,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (dbg) {
+      atomicAdd(dbg + 5, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(dbg + 6, (unsigned long long)w_tfull);
+      atomicAdd(dbg + 7, 1ull);
     }
   }
 
@@ -392,6 +443,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 }  // namespace
 
 namespace {
+
+unsigned long long* g_dbg = nullptr;   // diagnostics only, see uncl_conv_tc_set_debug
+int g_dbg_align = 0;
 
 // fills the tile geometry for an (ntaps = 9: 3x3 with halo | ntaps = 1: pointwise GEMM) problem and launches
 int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, int H, int W, int epi, int bias_floats,
@@ -438,6 +492,8 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
   if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
 
   if (p.ns_per_group <= 0) p.ns_per_group = p.NS;
+  p.dbg = g_dbg;
+  p.dbg_align = g_dbg_align;
   auto kern = epi == 0 ? conv3x3_tc_kernel<0> : (epi == 1 ? conv3x3_tc_kernel<1> : conv3x3_tc_kernel<2>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));
@@ -534,4 +590,14 @@ extern "C" int uncl_pw_conv_tc(const void* in, long in_img_stride, const void* w
   p.act = act;
   p.ntaps = 1;
   return launch_tc(p, in, in_img_stride, N, C_in, H, W, 2, 2 * C_out, "pw_conv_tc", stream);
+}
+
+// Diagnostics: when set (device pointer to 8 zeroed uint64), every tensor-core conv launch adds, summed over its CTAs,
+// [0] producer cycles, [1] producer wait-for-empty-stage, [2] MMA-issuer cycles, [3] its wait-for-full-stage,
+// [4] its wait-for-free-accumulator, [5] epilogue-warp cycles, [6] its wait-for-accumulator, [7] CTA count.
+// Not thread-safe, not for production use (the only mutable global of the library); pass NULL to switch off.
+extern "C" int uncl_conv_tc_set_debug(void* counters) {
+  g_dbg_align = getenv("UNCL_PROBE_ALIGNED_TAPS") != nullptr;
+  g_dbg = reinterpret_cast<unsigned long long*>(counters);
+  return UNCL_OK;
 }
