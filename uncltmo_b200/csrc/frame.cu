@@ -160,44 +160,10 @@ __device__ __forceinline__ float key_value(unsigned k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// one warp per query: lanes own contiguous slices of the histogram, warp prefix sum locates the bin holding `rank`.
+// Runs in the first 4 warps of the LAST histogram CTA to finish (see select_pass_kernel).
 template <int PASS>
-__global__ void __launch_bounds__(512) select_hist_kernel(const float* __restrict__ data, long n, float clamp_lo,
-                                                         float clamp_hi, const SelState* __restrict__ st,
-                                                         unsigned* __restrict__ hist) {
-  constexpr int BITS = PASS == 2 ? 10 : 11;
-  constexpr int SHIFT = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
-  constexpr int NQ = PASS == 0 ? 1 : kSelQ;
-  __shared__ unsigned s_hist[NQ << BITS];
-  for (int i = threadIdx.x; i < (NQ << BITS); i += blockDim.x) s_hist[i] = 0;
-  unsigned pre[kSelQ];
-#pragma unroll
-  for (int q = 0; q < kSelQ; ++q) pre[q] = PASS == 0 ? 0u : st->prefix[q];
-  __syncthreads();
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const float v = fminf(fmaxf(__ldg(data + i), clamp_lo), clamp_hi);
-    const unsigned k = order_key(v);
-    if (PASS == 0) {
-      atomicAdd(&s_hist[k >> SHIFT], 1u);
-    } else {
-      const unsigned hi = k >> (SHIFT + BITS), bin = (k >> SHIFT) & ((1u << BITS) - 1);
-#pragma unroll
-      for (int q = 0; q < kSelQ; ++q) {
-        // identical prefixes share a histogram slot (the lowest q) - the scan reads it from there
-        bool first = true;
-#pragma unroll
-        for (int q2 = 0; q2 < q; ++q2) first = first && (pre[q2] != pre[q]);
-        if (first && hi == pre[q]) atomicAdd(&s_hist[(q << BITS) + bin], 1u);
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < (NQ << BITS); i += blockDim.x)
-    if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
-}
-
-// one warp per query: lanes own contiguous slices of the histogram, warp prefix sum locates the bin holding `rank`
-template <int PASS>
-__global__ void __launch_bounds__(32 * kSelQ) select_scan_kernel(SelState* st, unsigned* hist, const SelRanks ranks_in) {
+__device__ __forceinline__ void select_scan(SelState* st, const unsigned* hist, const SelRanks& ranks_in) {
   constexpr int BITS = PASS == 2 ? 10 : 11;
   constexpr int PER = (1 << BITS) / 32;
   const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -209,7 +175,7 @@ __global__ void __launch_bounds__(32 * kSelQ) select_scan_kernel(SelState* st, u
     for (int q2 = q - 1; q2 >= 0; --q2)
       if (st->prefix[q2] == pre) slot = q2;
   }
-  __syncthreads();  // every warp has read the old prefixes / ranks before anyone overwrites them
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // every warp has read the old prefixes / ranks before anyone overwrites them
   const unsigned* h = hist + ((size_t)slot << BITS) + lane * PER;
   unsigned mine = 0;
   for (int i = 0; i < PER; ++i) mine += h[i];
@@ -236,13 +202,69 @@ __global__ void __launch_bounds__(32 * kSelQ) select_scan_kernel(SelState* st, u
   }
 }
 
-// out[0] = lerp of order stats (ranks 0,1) with weight t0, out[1] = same for ranks 2,3 with t1 (numpy 'linear')
-__global__ void select_finish_kernel(const SelState* st, double t0, double t1, float* out) {
+// One radix pass: per-CTA shared histograms of the digit (restricted to the prefixes found so far), merged with global
+// atomics; the last CTA to arrive scans the merged histogram for the 4 ranks, clears it for the next pass and, after the
+// third pass, interpolates the two percentiles (numpy 'linear').  `done` and `hist` must be zero on entry of pass 0.
+template <int PASS>
+__global__ void __launch_bounds__(512) select_pass_kernel(const float* __restrict__ data, long n, float clamp_lo,
+                                                         float clamp_hi, SelState* st, unsigned* __restrict__ hist,
+                                                         unsigned* done, const SelRanks ranks, double t0, double t1,
+                                                         float* out) {
+  constexpr int BITS = PASS == 2 ? 10 : 11;
+  constexpr int SHIFT = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);
+  constexpr int NQ = PASS == 0 ? 1 : kSelQ;
+  __shared__ unsigned s_hist[NQ << BITS];
+  __shared__ bool s_last;
+  for (int i = threadIdx.x; i < (NQ << BITS); i += blockDim.x) s_hist[i] = 0;
+  unsigned pre[kSelQ];
+#pragma unroll
+  for (int q = 0; q < kSelQ; ++q) pre[q] = PASS == 0 ? 0u : st->prefix[q];
+  __syncthreads();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = fminf(fmaxf(__ldg(data + i), clamp_lo), clamp_hi);
+    const unsigned k = order_key(v);
+    if (PASS == 0) {
+      // tone-mapped values cluster in a few exponent bins: aggregate equal digits inside the warp, one atomic per group
+      const unsigned bin = k >> SHIFT;
+      const unsigned active = __activemask();
+      const unsigned peers = __match_any_sync(active, bin);
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (unsigned)__popc(peers));
+    } else {
+      const unsigned hi = k >> (SHIFT + BITS), bin = (k >> SHIFT) & ((1u << BITS) - 1);
+#pragma unroll
+      for (int q = 0; q < kSelQ; ++q) {
+        // identical prefixes share a histogram slot (the lowest q) - the scan reads it from there
+        bool first = true;
+#pragma unroll
+        for (int q2 = 0; q2 < q; ++q2) first = first && (pre[q2] != pre[q]);
+        if (first && hi == pre[q]) atomicAdd(&s_hist[(q << BITS) + bin], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (NQ << BITS); i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // the merged histogram comes back into shared memory in one parallel sweep (L2 reads, bypassing L1); the scan's
+  // dependent look-ups then run at shared-memory latency
+  for (int i = threadIdx.x; i < (NQ << BITS); i += blockDim.x) s_hist[i] = __ldcg(hist + i);
+  __syncthreads();
+  if (threadIdx.x < 32 * kSelQ) select_scan<PASS>(st, s_hist, ranks);
+  __syncthreads();
+  for (int i = threadIdx.x; i < (kSelQ << 11); i += blockDim.x) hist[i] = 0;
   if (threadIdx.x == 0) {
-    const double a0 = key_value(st->prefix[0]), b0 = key_value(st->prefix[1]);
-    const double a1 = key_value(st->prefix[2]), b1 = key_value(st->prefix[3]);
-    out[0] = (float)(t0 < 0.5 ? a0 + (b0 - a0) * t0 : b0 - (b0 - a0) * (1.0 - t0));
-    out[1] = (float)(t1 < 0.5 ? a1 + (b1 - a1) * t1 : b1 - (b1 - a1) * (1.0 - t1));
+    *done = 0;
+    if (PASS == 2) {
+      const double a0 = key_value(st->prefix[0]), b0 = key_value(st->prefix[1]);
+      const double a1 = key_value(st->prefix[2]), b1 = key_value(st->prefix[3]);
+      out[0] = (float)(t0 < 0.5 ? a0 + (b0 - a0) * t0 : b0 - (b0 - a0) * (1.0 - t0));
+      out[1] = (float)(t1 < 0.5 ? a1 + (b1 - a1) * t1 : b1 - (b1 - a1) * (1.0 - t1));
+    }
   }
 }
 
@@ -358,16 +380,11 @@ extern "C" int uncl_percentile_pair(const float* data, long n, float clamp_lo, f
   UNCL_REQUIRE(n < (1L << 32), "percentile_pair: n too large");
   const SelRanks ranks = {{(unsigned)k0, (unsigned)(k0 + 1), (unsigned)k1, (unsigned)(k1 + 1)}};
   const int nb = grid_for(n, 512, 4);
-  cudaMemsetAsync(w.hist, 0, 4 * 2048 * 4, stream);
-  select_hist_kernel<0><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist);
-  select_scan_kernel<0><<<1, 32 * kSelQ, 0, stream>>>(w.sel, w.hist, ranks);
-  cudaMemsetAsync(w.hist, 0, 4 * 2048 * 4, stream);
-  select_hist_kernel<1><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist);
-  select_scan_kernel<1><<<1, 32 * kSelQ, 0, stream>>>(w.sel, w.hist, ranks);
-  cudaMemsetAsync(w.hist, 0, 4 * 2048 * 4, stream);
-  select_hist_kernel<2><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist);
-  select_scan_kernel<2><<<1, 32 * kSelQ, 0, stream>>>(w.sel, w.hist, ranks);
-  select_finish_kernel<<<1, 32, 0, stream>>>(w.sel, v0 - (double)k0, v1 - (double)k1, pct_out);
+  const double t0 = v0 - (double)k0, t1 = v1 - (double)k1;
+  cudaMemsetAsync(w.ranks, 0, 16 + 4 * 2048 * 4, stream);   // arrival counter (w.ranks[0]) + histograms, contiguous
+  select_pass_kernel<0><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist, w.ranks, ranks, t0, t1, pct_out);
+  select_pass_kernel<1><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist, w.ranks, ranks, t0, t1, pct_out);
+  select_pass_kernel<2><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist, w.ranks, ranks, t0, t1, pct_out);
   return uncl_check_launch("percentile_pair");
 }
 
