@@ -287,6 +287,21 @@ int uncl_lambda_cross_entropy(const float* gray, long n, const double* lambdas, 
 int uncl_blocks_apply(const float* x, float* out, int N, long per, int mode, float param, float* scratch,
                       uncl_stream_t stream);
 
+/* ---- training-sample preparation on the device ----
+ * utils/ProcessedDatasetFolderImg.py:44-168, utils/ProcessedDatasetFolder.py:43-215 (npy_loader), :13-22 (get_ldr_im). */
+
+/* cv2.resize (INTER_LINEAR, float32) of an HWC image to RH x RW followed by the P x P crop at (xx, yy), written CHW.
+ * src_base / src_off: the batch's source images packed in one device buffer, per-crop offsets in floats;
+ * meta: int32 [S][8] = {H, W, RH, RW, xx, yy, 0, 0} (RH == H and RW == W: no resize); color [S][3][P][P]. */
+int uncl_sample_crop_resize(const float* src_base, const long* src_off, const int* meta, float* color, int S, int P,
+                            uncl_stream_t stream);
+/* Y = .299R + .587G + .114B and the loader's normalisation.  mode 0 (HDR): input = log10((Y-min)/max(Y-min)*f+1) /
+ * max(...), gray_norm = Y/max, gray_shift = Y-min (either may be NULL); mode 1: Y/max; mode 2: Y/255;
+ * mode 3: clip(((Y-min)/max)*max_stretch - min_stretch, 0, 1).  f_per_sample: S floats (mode 0).  stats_scratch: 2*S. */
+int uncl_sample_normalise(const float* color, int S, int P, int mode, const float* f_per_sample, float max_stretch,
+                          float min_stretch, float* input, float* gray_norm, float* gray_shift, float* stats_scratch,
+                          uncl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
