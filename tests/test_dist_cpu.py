@@ -47,6 +47,16 @@ def _worker(rank, world, port, out):
     (g * torch.arange(1, 5.0).view(4, 1)).sum().backward()
     ok = ok and g.shape == (4, 1) and torch.equal(g.detach().flatten(), torch.tensor([0.0, 0.5, 1.0, 1.5]))
     ok = ok and torch.equal(t.grad.flatten(), torch.tensor([1.0, 2.0]) + 2.0 * rank)
+    # video scene sharded by tile chain: 7 tiles over 2 ranks (4 + 3), T = 3 frames
+    full = torch.arange(3 * 7 * 2, dtype=torch.float32).reshape(3, 7, 2)
+    lo, hi = udist.shard_range(7, rank, world)
+    got = udist.gather_tile_chains(full[:, lo:hi].clone(), 7)
+    ok = ok and torch.equal(got, full)
+    try:
+        udist.gather_tile_chains(full[:, :1].clone(), 7)
+        ok = False
+    except ValueError:
+        pass
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

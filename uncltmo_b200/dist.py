@@ -22,6 +22,29 @@ def shard_tiles(ntiles, rank, world):
     return list(range(*shard_range(ntiles, rank, world)))
 
 
+def gather_tile_chains(local, ntiles, group=None):
+    """Video scene sharded by tile chain: every rank computed `local` = [T, n_local, ...] outputs for its contiguous
+    `shard_range` of the `ntiles` tiles (all T frames); returns the full [T, ntiles, ...] on every rank.
+    One all-gather of equal-sized (zero-padded) blocks - the only collective of the inference path."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_range(ntiles, rank, world)
+    if local.shape[1] != hi - lo:
+        raise ValueError("rank %d owns tiles [%d, %d) but holds %d" % (rank, lo, hi, local.shape[1]))
+    per = (ntiles + world - 1) // world
+    block = local.new_zeros((local.shape[0], per) + tuple(local.shape[2:]))
+    block[:, :hi - lo] = local
+    block = block.contiguous()
+    out = [torch.empty_like(block) for _ in range(world)]
+    dist.all_gather(out, block, group=group)
+    parts = []
+    for r in range(world):
+        b, e = shard_range(ntiles, r, world)
+        parts.append(out[r][:, :e - b])
+    return torch.cat(parts, dim=1)
+
+
 class GradientBuckets:
     """Flat fp32 buckets over a parameter list, built in REVERSE registration order (decoder first: the order
     in which backward produces gradients), all-reduced (sum) with one collective per bucket."""

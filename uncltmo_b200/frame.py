@@ -225,25 +225,41 @@ class FramePipeline:
         compute.wait_stream(d2h)
         return results
 
-    def tonemap_clip(self, frames, lam, uint8=False):
+    def tonemap_clip(self, frames, lam, uint8=False, shard_tiles=False):
         """Video path (run_model_on_video, model_save_util.py:567-614): frames [T,3,H,W] fp32 CUDA of ONE scene, one
         lambda per scene.  `self.g` must be the video generator (UNetVideo): every tile is a chain over the T frames
-        that hands its recurrent channel slices from frame to frame; tiles are independent of each other."""
+        that hands its recurrent channel slices from frame to frame; tiles are independent of each other.
+
+        shard_tiles=True (torch.distributed initialised, every rank holding the same frames): the scene is split by tile
+        chain - a rank runs its contiguous share of the tiles through all T frames, one all-gather returns every rank
+        the full set (splitting by frame would change the results), blend / post-process follow."""
         if not (frames.is_cuda and frames.dtype == torch.float32 and frames.dim() == 4 and frames.shape[1] == 3):
             raise ValueError("tonemap_clip expects a CUDA fp32 [T,3,H,W] tensor")
+        import torch.distributed as tdist
+        from .dist import gather_tile_chains, shard_range
         frames = frames.contiguous()
         t_len = frames.shape[0]
         pl = self.plan(frames.shape[2], frames.shape[3], frames.device)
         norm = [self.normalise_pad(frames[t], lam) for t in range(t_len)]
         tiles = [self.gather_tiles(g, pl) for g, _ in norm]
+        lo, hi = 0, pl.ntiles
+        sharded = shard_tiles and tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1
+        if sharded:
+            lo, hi = shard_range(pl.ntiles, tdist.get_rank(), tdist.get_world_size())
         outs = [[] for _ in range(t_len)]
-        for i in range(0, pl.ntiles, self.max_tiles):
-            chain = self.g.tonemap_clip_tiles([tl[i:i + self.max_tiles] for tl in tiles])
+        for i in range(lo, hi, self.max_tiles):
+            j = min(i + self.max_tiles, hi)
+            chain = self.g.tonemap_clip_tiles([tl[i:j] for tl in tiles])
             for t in range(t_len):
                 outs[t].append(chain[t])
+        per_frame = [torch.cat(o) if len(o) > 1 else o[0] for o in outs] if hi > lo else \
+            [tiles[0].new_empty((0, 1, 256, 256)) for _ in range(t_len)]
+        if sharded:
+            full = gather_tile_chains(torch.stack(per_frame), pl.ntiles)
+            per_frame = [full[t] for t in range(t_len)]
         res = []
         for t in range(t_len):
-            fake_p = self.blend(torch.cat(outs[t]) if len(outs[t]) > 1 else outs[t][0], pl)
+            fake_p = self.blend(per_frame[t], pl)
             col = self.postprocess(fake_p, frames[t], norm[t][1], pl)
             res.append(self.to_uint8(col) if uint8 else col)
         return torch.stack(res)
