@@ -138,16 +138,51 @@ def cpu_reference_arm(steps, warmup, threads=None):
 TRAIN_GFLOP_STEP = 4 * GFLOP_TILE * 16   # G fwd (D step) + G fwd (G step) + one merged backward, 16 images
 
 
-def train_workload(dev, precision, steps, warmup, world=1, rank=0):
+def video_inference_workload(dev, precision, world, rank, frames=8, iters=2):
+    """BASELINE.json configs[3]: video TMO on a synthetic 1080p clip (frame k = frame 0 translated + 1 % noise, SURVEY.md
+    section 8d).  The recurrent generator couples the frames of a scene, not its tiles: with N GPUs the scene is split
+    by tile chain (one all-gather per scene), so this is STRONG scaling of one scene."""
+    from uncltmo_b200 import synth
+    from uncltmo_b200.frame import FramePipeline
+    from uncltmo_b200.generator import UNetVideo
+    from uncltmo_b200.weights import make_generator_state_dict
+    import torch.distributed as dist
+    net = UNetVideo(*G_ARGS, up_mode=0, precision=precision).to(dev).eval()
+    net.load_state_dict(make_generator_state_dict())
+    pipe = FramePipeline(net)
+    clip = torch.from_numpy(synth.hdr_clip(frames, H, W, seed=0)).to(dev)
+    with torch.no_grad():
+        pipe.tonemap_clip(clip, LAMBDA, uint8=True, shard_tiles=world > 1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            pipe.tonemap_clip(clip, LAMBDA, uint8=True, shard_tiles=world > 1)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return {"metric": "1080p video tone-mapped frames/s (recurrent UNet fwd, one scene)", "value": frames * iters / (ms / 1e3),
+            "unit": "frames/s", "ms_per_frame": ms / (frames * iters), "scaling": "strong", "dtype": precision,
+            "config": {"clip": "%d frames of 1920x1080, 60 tile chains" % frames,
+                       "parallelism": "tile chains sharded over %d rank(s), one NCCL all-gather per scene" % world}}
+
+
+def train_workload(dev, precision, steps, warmup, world=1, rank=0, video=False):
     """256x256 image-TMO training step, global batch 8x2 = 16 images (GanTrainerImg.train_D + train_G, epoch-0 loss
     schedule, Adam as main_train_image.py builds it).  Strong scaling: ranks split the 16 images."""
     from uncltmo_b200 import _lib, synth
     from uncltmo_b200.discriminator import SimpleDiscriminator
-    from uncltmo_b200.generator import UNet
+    from uncltmo_b200.generator import UNet, UNetVideo
     from uncltmo_b200.trainer import GanTrainerStep
     from uncltmo_b200.weights import make_discriminator_state_dict, make_generator_state_dict
     import torch.distributed as dist
-    netG = UNet(*G_ARGS, up_mode=0, precision=precision).to(dev).train()
+    netG = (UNetVideo if video else UNet)(*G_ARGS, up_mode=0, precision=precision).to(dev).train()
     netG.load_state_dict(make_generator_state_dict())
     netD = SimpleDiscriminator(256, 1, 16, "none", "none", 0, 0).to(dev).train()
     netD.load_state_dict(make_discriminator_state_dict())
@@ -213,7 +248,9 @@ def train_workload(dev, precision, steps, warmup, world=1, rank=0):
     ms = run(resident)
     ms_e2e = run(e2e)
     bytes_in = 3 * b_local * 2 * 256 * 256 * 4
-    return {"metric": "256^2 train steps/s (16 images/step: train_D + train_G)", "value": steps / (ms / 1e3), "unit": "steps/s",
+    what = "video TMO, 8 clips x 2 consecutive frames (recurrent generator, GanTrainer.py)" if video else \
+        "16 images/step: train_D + train_G"
+    return {"metric": "256^2 train steps/s (%s)" % what, "value": steps / (ms / 1e3), "unit": "steps/s",
             "ms_per_step": ms / steps, "scaling": "strong", "execution": "CUDA graph replay of the whole iteration",
             "eager_launch_path": {"value": steps / (ms_eager / 1e3), "unit": "steps/s", "ms_per_step": ms_eager / steps}, "dtype": "f32" if precision == "fp32" else "bf16 operands / f32 tensors (mixed)",
             "tflops_algorithmic": steps * TRAIN_GFLOP_STEP / ms, "gpu_launches": launches,
@@ -388,7 +425,7 @@ def main():
                     "share_of_step": tc_ms / sum(tot.values()),
                     "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
 
-    train = None
+    train = video = None
     if not args.no_train:
         net = pipe = None
         dev_frames = None
@@ -400,6 +437,11 @@ def main():
             train["fp32_exact_path"] = {"value": exact["value"], "unit": "steps/s", "ms_per_step": exact["ms_per_step"]}
             if not args.no_cpu_baseline:
                 train["cpu_baseline"] = cpu_train_arm()
+        # BASELINE.json configs[3] / configs[4]: the video generator (inference on a 1080p clip, 256^2 training step)
+        video = {"inference": video_inference_workload(dev, args.precision, world, rank)}
+        torch.cuda.empty_cache()
+        with torch.enable_grad():
+            video["train"] = train_workload(dev, args.train_precision, 5, args.warmup, world, rank, video=True)
 
     if rank == 0:
         base = None
@@ -414,7 +456,8 @@ def main():
                 "tflops_generator": world * args.steps * TILES * GFLOP_TILE / ms_res,
                 "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": "frames/s",
                         "h2d_bytes_per_step": 3 * H * W * 4, "d2h_bytes_per_step": H * W * 3},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": base, "clocks": clocks, "train": train}
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": base, "clocks": clocks, "train": train,
+                "video": video}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

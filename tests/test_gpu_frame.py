@@ -114,25 +114,37 @@ def test_frame_end_to_end_matches_reference_fixture(net, golden):
     assert np.abs(u8.cpu().numpy()[::2, ::2].astype(int) - golden["frame_u8_s2"].astype(int)).max() <= 1
 
 
-def test_frame_1080p_properties(net):
-    """Full-size case through size-independent properties: shape, range, partition of unity, and equality of
-    the batched-tile path with tile-at-a-time execution (what the reference does)."""
-    rgb = torch.from_numpy(synth.hdr_frame(1080, 1920, seed=0)).cuda()
+@pytest.mark.parametrize("h,w,padded,ntiles", [(769, 1025, (784, 1040), 24), (1080, 1920, (1088, 1936), 60),
+                                               (2160, 3840, (2176, 3856), 220)])
+def test_frame_full_sizes_properties(h, w, padded, ntiles):
+    """BASELINE.json's full sizes (HDR-Survey 1/4 resolution, 1080p, 4K) through size-independent properties: tile
+    count of SURVEY.md section 8d, range of the normalisation, equality of the batched-tile path with tile-at-a-time
+    execution (what the reference does), blend as a partition of unity, finite non-negative colour output, and the 8-bit
+    stretch reaching both ends of the range."""
+    rgb = torch.from_numpy(synth.hdr_frame(h, w, seed=0)).cuda()
     net_bf = UNet(*G_ARGS, up_mode=0, precision="bf16").cuda().eval()
     net_bf.load_state_dict(make_generator_state_dict())
     pipe = FramePipeline(net_bf)
-    pl = pipe.plan(1080, 1920, rgb.device)
-    assert (pl.h1, pl.w1, pl.ntiles) == (1088, 1936, 60)
+    pl = pipe.plan(h, w, rgb.device)
+    assert (pl.h1, pl.w1, pl.ntiles) == (padded[0], padded[1], ntiles)
     gray_p, _ = pipe.normalise_pad(rgb, 50.0)
     assert gray_p.min().item() == 0.0 and abs(gray_p.max().item() - 1.0) < 1e-6
     tiles = pipe.gather_tiles(gray_p, pl)
     batched = pipe.run_generator(tiles)
-    single = torch.cat([net_bf.tonemap_tiles(tiles[i:i + 1]) for i in (0, 17, 59)])
-    assert torch.equal(batched[[0, 17, 59]], single)
+    probe = [0, ntiles // 3, ntiles - 1]
+    single = torch.cat([net_bf.tonemap_tiles(tiles[i:i + 1]) for i in probe])
+    assert torch.equal(batched[probe], single)
+    ones = pipe.blend(torch.ones_like(batched), pl)
+    assert (ones - 1.0).abs().max().item() <= 2e-6
+    lo, hi = batched.min().item(), batched.max().item()
+    blended = pipe.blend(batched, pl)
+    assert lo - 1e-6 <= blended.min().item() and blended.max().item() <= hi + 1e-6     # a convex combination of tile values
     col = pipe.tonemap(rgb, 50.0)
-    assert col.shape == (3, 1080, 1920) and torch.isfinite(col).all() and col.min().item() >= 0.0
+    assert col.shape == (3, h, w) and torch.isfinite(col).all() and col.min().item() >= 0.0
     u8 = pipe.tonemap(rgb, 50.0, uint8=True)
-    assert u8.shape == (1080, 1920, 3)
+    assert u8.shape == (h, w, 3) and u8.min().item() == 0 and u8.max().item() == 255
+    del batched, tiles, blended, col, u8
+    torch.cuda.empty_cache()
 
 
 def test_video_clip_path_matches_oracle():
