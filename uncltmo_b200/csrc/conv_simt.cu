@@ -10,12 +10,14 @@
 // ------------------------------------------------------------------------------------------------
 // 3x3 conv, C_in = 1 (inc.conv): x [N][H][W] fp32 -> blocked [N][C_out/8][H-2][W-2][8], bias + ReLU
 // ------------------------------------------------------------------------------------------------
+// thread = one output column, two output rows (they share 6 of their 12 input values); the weights of 4 output
+// channels travel as one 128-bit shared-memory broadcast, so the kernel is FMA-bound (288 per pixel), not LDS-bound
 template <typename T>
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, T* __restrict__ out,
                                                         long out_img_stride, int H, int W, int C_out, int act) {
   // w: [9][C_out]
-  extern __shared__ float s_w[];  // 9*C_out + C_out
+  extern __shared__ __align__(16) float s_w[];  // 9*C_out + C_out
   float* s_b = s_w + 9 * C_out;
   for (int i = threadIdx.x; i < 9 * C_out; i += blockDim.x) s_w[i] = w[i];
   for (int i = threadIdx.x; i < C_out; i += blockDim.x) s_b[i] = bias[i];
@@ -23,26 +25,44 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
   const int Ho = H - 2, Wo = W - 2;
   const int n = blockIdx.z;
   const int ox = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int oy = blockIdx.y * 16 + 2 * (threadIdx.x >> 5);
   if (ox >= Wo || oy >= Ho) return;
+  const bool two = oy + 1 < Ho;
   const float* xi = x + (long)n * H * W + (long)oy * W + ox;
-  float a[9];
+  float a[12];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
+  for (int ky = 0; ky < 4; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) a[ky * 3 + kx] = __ldg(xi + ky * W + kx);
+    for (int kx = 0; kx < 3; ++kx) a[ky * 3 + kx] = (ky < 3 || two) ? __ldg(xi + ky * W + kx) : 0.f;
   T* o = out + (long)n * out_img_stride + ((long)oy * Wo + ox) * 8;
   const long cb_stride = (long)Ho * Wo * 8;
+  const float4* w4 = reinterpret_cast<const float4*>(s_w);
+  const float4* b4 = reinterpret_cast<const float4*>(s_b);
+  const int c4 = C_out / 4;
   for (int cb = 0; cb < C_out / 8; ++cb) {
-    float v[8];
+    float v0[8], v1[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float acc = s_b[cb * 8 + j];
+    for (int h = 0; h < 2; ++h) {
+      const float4 bb = b4[cb * 2 + h];
+      float p0[4] = {bb.x, bb.y, bb.z, bb.w}, p1[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-      for (int t = 0; t < 9; ++t) acc = fmaf(a[t], s_w[t * C_out + cb * 8 + j], acc);
-      v[j] = apply_act(acc, act);
+      for (int t = 0; t < 9; ++t) {
+        const float4 ww = w4[t * c4 + cb * 2 + h];
+        const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          p0[j] = fmaf(a[t], wv[j], p0[j]);
+          p1[j] = fmaf(a[t + 3], wv[j], p1[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v0[h * 4 + j] = apply_act(p0[j], act);
+        v1[h * 4 + j] = apply_act(p1[j], act);
+      }
     }
-    store8(o + cb * cb_stride, v);
+    store8(o + cb * cb_stride, v0);
+    if (two) store8(o + cb * cb_stride + (long)Wo * 8, v1);
   }
 }
 
@@ -331,7 +351,7 @@ static inline int grid1d(long total, int block = 256) {
 extern "C" int uncl_conv_first(const float* x, const float* w, const float* bias, void* out, long out_img_stride,
                                int N, int H, int W, int C_out, int act, int dtype, cudaStream_t stream) {
   UNCL_REQUIRE(C_out % 8 == 0 && H > 2 && W > 2 && N > 0, "conv_first: bad shape N=%d H=%d W=%d C_out=%d", N, H, W, C_out);
-  dim3 grid(ceil_div(W - 2, 32), ceil_div(H - 2, 8), N);
+  dim3 grid(ceil_div(W - 2, 32), ceil_div(H - 2, 16), N);
   size_t smem = (size_t)10 * C_out * sizeof(float);
   UNCL_DISPATCH_DTYPE(dtype, T, (conv_first_kernel<T><<<grid, 256, smem, stream>>>(x, w, bias, (T*)out, out_img_stride, H, W, C_out, act)));
   return uncl_check_launch("conv_first");
