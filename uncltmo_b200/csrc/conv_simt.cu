@@ -233,10 +233,14 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const T* __restrict__ in,
                                                       const T* __restrict__ prev, long prev_img_stride, int r,
                                                       T* __restrict__ out, long out_img_stride, int C, int H, int W,
                                                       int N) {
+  // one CTA per output row (n, channel block, y): the index arithmetic is per CTA, threads stride over x
   const int Ho = H / 2, Wo = W / 2, Cb = C / 8;
-  const long total = (long)N * Cb * Ho * Wo;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int x = i % Wo, y = (i / Wo) % Ho, cb = (i / ((long)Wo * Ho)) % Cb, n = i / ((long)Wo * Ho * Cb);
+  const int row = blockIdx.x;
+  const int y = row % Ho, cb = (row / Ho) % Cb, n = row / (Ho * Cb);
+  const T* in_row = in + (long)n * in_img_stride + ((long)cb * H + 2 * y) * W * 8;
+  const T* pv_row = (prev != nullptr && cb * 8 < r) ? prev + (long)n * prev_img_stride + ((long)cb * H + 2 * y) * W * 8 : nullptr;
+  T* out_row = out + (long)n * out_img_stride + ((long)cb * Ho + y) * Wo * 8;
+  for (int x = threadIdx.x; x < Wo; x += blockDim.x) {
     float m[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
@@ -244,12 +248,12 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const T* __restrict__ in,
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
-        const long off = (((long)cb * H + 2 * y + dy) * W + 2 * x + dx) * 8;
+        const long off = ((long)dy * W + 2 * x + dx) * 8;
         float v[8];
-        load8(in + (long)n * in_img_stride + off, v);
-        if (prev != nullptr && cb * 8 < r) {
+        load8(in_row + off, v);
+        if (pv_row != nullptr) {
           float pv[8];
-          load8(prev + (long)n * prev_img_stride + off, pv);
+          load8(pv_row + off, pv);
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             if (cb * 8 + c < r) v[c] = pv[c];
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const T* __restrict__ in,
 #pragma unroll
         for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
       }
-    store8(out + (long)n * out_img_stride + (((long)cb * Ho + y) * Wo + x) * 8, m);
+    store8(out_row + (long)x * 8, m);
   }
 }
 
@@ -382,8 +386,10 @@ extern "C" int uncl_maxpool2(const void* in, long in_img_stride, const void* pre
                              void* out, long out_img_stride, int N, int C, int H, int W, int dtype,
                              cudaStream_t stream) {
   UNCL_REQUIRE(C % 8 == 0 && H >= 2 && W >= 2 && N > 0, "maxpool2: bad shape");
-  const long total = (long)N * (C / 8) * (H / 2) * (W / 2);
-  UNCL_DISPATCH_DTYPE(dtype, T, (maxpool2_kernel<T><<<grid1d(total), 256, 0, stream>>>((const T*)in, in_img_stride, (const T*)prev, prev_img_stride, r, (T*)out, out_img_stride, C, H, W, N)));
+  const long rows = (long)N * (C / 8) * (H / 2);
+  UNCL_REQUIRE(rows < (1L << 31), "maxpool2: too many rows");
+  const int threads = (W / 2) <= 32 ? 32 : ((W / 2) <= 64 ? 64 : 128);
+  UNCL_DISPATCH_DTYPE(dtype, T, (maxpool2_kernel<T><<<(unsigned)rows, threads, 0, stream>>>((const T*)in, in_img_stride, (const T*)prev, prev_img_stride, r, (T*)out, out_img_stride, C, H, W, N)));
   return uncl_check_launch("maxpool2");
 }
 
