@@ -252,7 +252,8 @@ def train_workload(dev, precision, steps, warmup, world=1, rank=0, video=False):
         "16 images/step: train_D + train_G"
     return {"metric": "256^2 train steps/s (%s)" % what, "value": steps / (ms / 1e3), "unit": "steps/s",
             "ms_per_step": ms / steps, "scaling": "strong", "execution": "CUDA graph replay of the whole iteration",
-            "eager_launch_path": {"value": steps / (ms_eager / 1e3), "unit": "steps/s", "ms_per_step": ms_eager / steps}, "dtype": "f32" if precision == "fp32" else "bf16 operands / f32 tensors (mixed)",
+            "eager_launch_path": {"value": steps / (ms_eager / 1e3), "unit": "steps/s", "ms_per_step": ms_eager / steps,
+                                  "note": "same trainer without capture; launch-bound, and Adam(capturable=True) is slower eagerly"}, "dtype": "f32" if precision == "fp32" else "bf16 operands / f32 tensors (mixed)",
             "tflops_algorithmic": steps * TRAIN_GFLOP_STEP / ms, "gpu_launches": launches,
             "e2e": {"value": steps / (ms_e2e / 1e3), "unit": "steps/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 8},
             "config": {"global_batch": "8 x 2 crops = 16 images of 256x256", "per_gpu_images": 2 * b_local, "loss_schedule": "epoch 0",

