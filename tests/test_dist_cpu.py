@@ -41,6 +41,26 @@ def _worker(rank, world, port, out):
     buckets.allreduce()
     ok = all(torch.allclose(params[i].grad, torch.full_like(params[i], 3.0 * (i + 1))) for i in (0, 3))
     ok = ok and torch.count_nonzero(params[1].grad) == 0 and params[2].grad is None
+    # the same sums through the backward hooks (buckets launched as soon as their gradients exist)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3), torch.nn.Linear(3, 1))
+    for i, p in enumerate(net.parameters()):
+        torch.manual_seed(100 + i)
+        p.data.normal_()
+    net[2].bias.requires_grad_(False)
+    hooked = udist.GradientBuckets(net.parameters(), bucket_bytes=64).install_hooks()
+    xs = torch.arange(12.0).reshape(2, 6) / 10 + rank
+    hooked.arm()
+    net(xs).sum().backward()
+    launched_early = len(hooked._inflight)
+    hooked.finish()
+    got = [p.grad.clone() for p in net.parameters() if p.requires_grad]
+    for p in net.parameters():
+        p.grad = None
+    all_x = torch.cat([torch.arange(12.0).reshape(2, 6) / 10 + r for r in range(world)])
+    net(all_x).sum().backward()
+    want = [p.grad for p in net.parameters() if p.requires_grad]
+    ok = ok and launched_early == len(hooked.buckets) and len(hooked.buckets) >= 2
+    ok = ok and all(torch.allclose(a, b, atol=1e-5) for a, b in zip(got, want)) and net[2].bias.grad is None
     # gathered logits: global loss, local gradient
     t = torch.tensor([[float(rank)], [float(rank) + 0.5]], requires_grad=True)
     g = udist.all_gather_cat(t)

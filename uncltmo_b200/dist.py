@@ -61,6 +61,87 @@ class GradientBuckets:
         if cur:
             self.buckets.append(cur)
         self._flat = None
+        self._bucket_of = {id(p): bi for bi, b in enumerate(self.buckets) for p in b}
+        self._hooks, self._pending, self._inflight, self._comm = [], None, {}, None
+
+    # ---------------------------------------------------------------- overlap with backward
+    def install_hooks(self, group=None):
+        """Launch a bucket's all-reduce as soon as backward has produced all of its gradients (buckets are in backward
+        order), on a communication stream next to the remaining backward kernels.  Use `arm()` before backward() and
+        `finish()` after it instead of `allreduce()`.  Works inside a CUDA-graph capture (NCCL branches are captured)."""
+        if self._hooks:
+            return self
+        self._group = group
+        for b in self.buckets:
+            for p in b:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        return self
+
+    def arm(self):
+        self._pending = [len(b) for b in self.buckets]
+        self._inflight = {}
+
+    def _on_grad(self, p):
+        if self._pending is None or not (dist.is_available() and dist.is_initialized()):
+            return
+        bi = self._bucket_of[id(p)]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._launch(bi)
+
+    def _launch(self, bi):
+        bucket = self.buckets[bi]
+        cuda = bucket[0].is_cuda
+        if cuda:
+            if self._comm is None:
+                self._comm = torch.cuda.Stream(bucket[0].device)
+            main = torch.cuda.current_stream(bucket[0].device)
+            self._comm.wait_stream(main)
+            ctx = torch.cuda.stream(self._comm)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self._group, async_op=True)
+        self._inflight[bi] = (flat, work)
+
+    def finish(self, average=False):
+        """Wait for the in-flight buckets, reduce the ones backward never completed (parameters without a gradient this
+        step count as zeros) and write the sums back into .grad."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self._group) == 1:
+            self._pending = None
+            return
+        world = dist.get_world_size(self._group)
+        for bi in range(len(self.buckets)):
+            if bi not in self._inflight:
+                self._launch(bi)
+        cuda = self.buckets[0][0].is_cuda
+        main = torch.cuda.current_stream(self.buckets[0][0].device) if cuda else None
+        for bi, (flat, work) in sorted(self._inflight.items()):
+            if cuda:
+                with torch.cuda.stream(self._comm):
+                    work.wait()
+            else:
+                work.wait()
+        if cuda:
+            main.wait_stream(self._comm)
+        for bi, (flat, work) in sorted(self._inflight.items()):
+            if cuda:
+                flat.record_stream(main)
+            if average:
+                flat /= world
+            off = 0
+            for p in self.buckets[bi]:
+                n = p.numel()
+                g = flat[off:off + n].view_as(p)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+                off += n
+        self._pending, self._inflight = None, {}
 
     def allreduce(self, group=None, average=False, async_op=False):
         """Sum (or average) .grad over the process group.  Returns the list of work handles if async_op."""

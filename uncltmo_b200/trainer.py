@@ -44,7 +44,8 @@ class GanTrainerStep:
         self.errD = self.errG_d = self.errG_struct = None
         self._side = None
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        self.buckets_G = GradientBuckets(netG.parameters()) if self.world > 1 else None
+        # generator gradients (19.7 MB) are reduced bucket by bucket WHILE backward is still running (hooks)
+        self.buckets_G = GradientBuckets(netG.parameters()).install_hooks() if self.world > 1 else None
         self.buckets_D = GradientBuckets(netD.parameters()) if self.world > 1 else None
 
     @staticmethod
@@ -134,13 +135,15 @@ class GanTrainerStep:
         if self.struct_loss_factor:
             self.errG_struct = (self.struct_loss_factor / self.world) * self.struct_loss(fake, None, hdr, self.pyramid_weight_list)
             total = total + self.errG_struct
+        if self.buckets_G is not None:
+            self.buckets_G.arm()
         total.backward()
         del total
         self.errG_d = self.errG_d.detach()
         if self.errG_struct is not None:
             self.errG_struct = self.errG_struct.detach()
         if self.buckets_G is not None:
-            self.buckets_G.allreduce()
+            self.buckets_G.finish()
         self.optimizerG.step()
         return self.errG_d, self.errG_struct
 
