@@ -6,9 +6,9 @@ from uncltmo_b200 import _lib, packing
 cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
 n, ci, h = 60, 128, 252
 x = torch.randn((n, ci // 8, h, h, 8), device="cuda").bfloat16()
-for co in (32, 64, 96, 128):
+for co in (32, 64, 96, 128) + ((256,) if os.environ.get('UNCL_PROBE_NT256') else ()):
     w9 = torch.randn((9, ci, co), device="cuda") * 0.03
-    wp = packing.conv3x3_tc(w9)
+    wp = packing.conv3x3_tc(w9) if co != 256 else torch.randn((1, ci // 16, 9, 2, 256, 8), device='cuda').bfloat16() * 0.03
     b = torch.zeros(co, device="cuda")
     out = torch.empty((n, co // 8, h + 2, h + 2, 8), device="cuda", dtype=torch.bfloat16)
     for it in range(2):
@@ -22,7 +22,7 @@ for co in (32, 64, 96, 128):
         torch.cuda.synchronize()
     _lib.lib().uncl_conv_tc_set_debug(None)
     c = cnt.tolist()
-    NT = min(co, 128)
+    NT = min(co, 128) if co != 256 else 256
     PW = 86  # 254 / 3 bands + 2
     mmas_total = n * 254 * 254 / 128 * 1.05 * (ci // 16) * 9
     print("C_out %3d: %.1f us, mma-warp cycles/cta %.0f, wait-full %.1f%% wait-acc %.1f%%, ~%.1f cycles per MMA (floor %d)" % (

@@ -515,6 +515,7 @@ extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w
                "conv3x3_tc: unsupported C_in=%d C_out=%d pad=%d", C_in, C_out, pad);
   TcParams p{};
   p.NT = C_out < 128 ? C_out : 128;
+  if (C_out == 256 && getenv("UNCL_PROBE_NT256") != nullptr) p.NT = 256;   // timing probe (weights packed by the caller)
   UNCL_REQUIRE(C_out % p.NT == 0 && C_out <= 1024, "conv3x3_tc: unsupported C_out=%d", C_out);
   UNCL_REQUIRE(out_dtype == UNCL_F32 || out_dtype == UNCL_BF16, "conv3x3_tc: bad out_dtype");
   UNCL_REQUIRE(!fuse_outc || (C_out == p.NT && outc_w && outc_b && out_img), "conv3x3_tc: fuse_outc needs C_out<=128 and outc params");
