@@ -116,30 +116,44 @@ __global__ void __launch_bounds__(256) tiles_gather_kernel(const float* __restri
 
 // out(y,x) = sum_{a<K} sum_{b<K} wy[y][a] * wx[x][b] * tile[ty[y][a]][tx[x][b]](y - y0, x - x0)
 // (weights/indices are the closed form of the reference's sequential cross-fade; unused slots have weight 0)
+template <int KMAX>
 __global__ void __launch_bounds__(256) tiles_blend_kernel(const float* __restrict__ tiles, const int* __restrict__ yidx,
                                                          const float* __restrict__ yw, const int* __restrict__ ystart,
                                                          const int* __restrict__ xidx, const float* __restrict__ xw,
                                                          const int* __restrict__ xstart, int TX, int K,
                                                          float* __restrict__ out, int H1, int W1) {
-  const long total = (long)H1 * W1;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int x = i % W1, y = i / W1;
-    float acc = 0.f;
-    for (int a = 0; a < K; ++a) {
-      const float wa = yw[K * y + a];
-      if (wa == 0.f) continue;
-      const int ty = yidx[K * y + a];
-      const int ly = y - ystart[ty];
-      float row = 0.f;
-      for (int b = 0; b < K; ++b) {
-        const float wb = xw[K * x + b];
-        if (wb == 0.f) continue;
-        const int tx = xidx[K * x + b];
-        row = fmaf(wb, __ldg(tiles + ((long)(ty * TX + tx) << 16) + (ly << 8) + (x - xstart[tx])), row);
-      }
-      acc = fmaf(wa, row, acc);
+  // one CTA row per output row: the row's tile indices / weights are CTA-uniform, no per-pixel division
+  const int y = blockIdx.y;
+  float wa_[KMAX];
+  int ty_[KMAX], ly_[KMAX];
+#pragma unroll
+  for (int a = 0; a < KMAX; ++a) {
+    wa_[a] = a < K ? yw[K * y + a] : 0.f;
+    ty_[a] = a < K ? yidx[K * y + a] : 0;
+    ly_[a] = y - ystart[ty_[a]];
+  }
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W1; x += gridDim.x * blockDim.x) {
+    float wb_[KMAX];
+    long off_[KMAX];
+#pragma unroll
+    for (int b = 0; b < KMAX; ++b) {
+      wb_[b] = b < K ? xw[K * x + b] : 0.f;
+      const int tx = b < K ? xidx[K * x + b] : 0;
+      off_[b] = ((long)tx << 16) + (x - xstart[tx]);
     }
-    out[i] = acc;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < KMAX; ++a) {
+      if (wa_[a] == 0.f) continue;
+      float row = 0.f;
+#pragma unroll
+      for (int b = 0; b < KMAX; ++b) {
+        if (wb_[b] == 0.f) continue;
+        row = fmaf(wb_[b], __ldg(tiles + ((long)(ty_[a] * TX) << 16) + off_[b] + (ly_[a] << 8)), row);
+      }
+      acc = fmaf(wa_[a], row, acc);
+    }
+    out[(long)y * W1 + x] = acc;
   }
 }
 
@@ -220,8 +234,8 @@ __global__ void __launch_bounds__(512) select_pass_kernel(const float* __restric
 #pragma unroll
   for (int q = 0; q < kSelQ; ++q) pre[q] = PASS == 0 ? 0u : st->prefix[q];
   __syncthreads();
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const float v = fminf(fmaxf(__ldg(data + i), clamp_lo), clamp_hi);
+  auto visit = [&](float raw) {
+    const float v = fminf(fmaxf(raw, clamp_lo), clamp_hi);
     const unsigned k = order_key(v);
     if (PASS == 0) {
       // tone-mapped values cluster in a few exponent bins: aggregate equal digits inside the warp, one atomic per group
@@ -240,6 +254,25 @@ __global__ void __launch_bounds__(512) select_pass_kernel(const float* __restric
         if (first && hi == pre[q]) atomicAdd(&s_hist[(q << BITS) + bin], 1u);
       }
     }
+  };
+  // 128-bit loads, two in flight per thread: the pass is a pure stream and would otherwise be latency-bound
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(data) & 15) == 0) {
+    const float4* d4 = reinterpret_cast<const float4*>(data);
+    const long n4 = n >> 2;
+    long i = tid;
+    for (; i + nthreads < n4; i += 2 * nthreads) {
+      const float4 a = __ldg(d4 + i), b = __ldg(d4 + i + nthreads);
+      visit(a.x); visit(a.y); visit(a.z); visit(a.w);
+      visit(b.x); visit(b.y); visit(b.z); visit(b.w);
+    }
+    if (i < n4) {
+      const float4 a = __ldg(d4 + i);
+      visit(a.x); visit(a.y); visit(a.z); visit(a.w);
+    }
+    for (long j = (n4 << 2) + tid; j < n; j += nthreads) visit(__ldg(data + j));
+  } else {
+    for (long i = tid; i < n; i += nthreads) visit(__ldg(data + i));
   }
   __syncthreads();
   for (int i = threadIdx.x; i < (NQ << BITS); i += blockDim.x)
@@ -363,8 +396,10 @@ extern "C" int uncl_tiles_gather(const float* frame, int H1, int W1, const int* 
 extern "C" int uncl_tiles_blend(const float* tiles, const int* yidx, const float* yw, const int* ystart,
                                 const int* xidx, const float* xw, const int* xstart, int TX, int K, float* out,
                                 int H1, int W1, cudaStream_t stream) {
-  UNCL_REQUIRE(TX > 0 && K > 0 && H1 >= 256 && W1 >= 256, "tiles_blend: bad arguments");
-  tiles_blend_kernel<<<grid_for((long)H1 * W1, 256, 8), 256, 0, stream>>>(tiles, yidx, yw, ystart, xidx, xw, xstart, TX, K, out, H1, W1);
+  UNCL_REQUIRE(TX > 0 && K > 0 && K <= 8 && H1 >= 256 && W1 >= 256, "tiles_blend: bad arguments (K=%d)", K);
+  const dim3 grid((W1 + 255) / 256, H1);
+  if (K <= 3) tiles_blend_kernel<3><<<grid, 256, 0, stream>>>(tiles, yidx, yw, ystart, xidx, xw, xstart, TX, K, out, H1, W1);
+  else tiles_blend_kernel<8><<<grid, 256, 0, stream>>>(tiles, yidx, yw, ystart, xidx, xw, xstart, TX, K, out, H1, W1);
   return uncl_check_launch("tiles_blend");
 }
 
