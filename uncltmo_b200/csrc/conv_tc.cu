@@ -28,7 +28,7 @@ using namespace tcptx;
 
 constexpr int kThreads = 320;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
 constexpr int kEpiWarps = 8;           // two warps per TMEM lane quarter, M blocks interleaved between them
-constexpr int kAccCols = 256;          // TMEM columns per accumulator stage (2 stages = 512 = all of TMEM)
+constexpr int kAccCols = 256;          // TMEM columns per accumulator stage when double-buffered (2 stages = 512 = all of TMEM)
 constexpr int kMaxStages = 6;
 
 struct TcParams {
@@ -49,6 +49,7 @@ struct TcParams {
   int band_total;           // Ho * PW: flattened (pitch PW) output positions of one band
   int tiles_per_band, tiles_per_img, num_items;
   int nchunk, ntaps, stages;
+  int nacc, acc_cols;       // accumulator stages (2 x 256 columns, or 1 x 512 for K-heavy layers: see launch_tc)
   int a_box_bytes, a_stage_bytes, b_stage_bytes, stage_bytes;
   int act, emit_skip, fuse_outc;
   int sh_C, sh_H2, sh_W2;   // pixel-shuffle epilogue (ConvTranspose k2 s2): channels, target extent (replicate pad)
@@ -58,7 +59,6 @@ struct TcParams {
   int res_f32;
   const float* scale;       // per-image factor (DropPath) or null
   int ns_per_group;         // grouped 1x1 conv: N splits per group (K range of a split = its group's input channels)
-  int dbg_align;            // diagnostics: issue every tap from a 128-byte aligned address (WRONG results, timing probe)
   unsigned long long* dbg;  // diagnostics (uncl_conv_tc_set_debug): cycle counters of the three roles, or null
 };
 
@@ -183,7 +183,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       const uint32_t mstep = 128u;
       const uint32_t pw = (uint32_t)p.PW, nt = (uint32_t)p.NT;
       const bool taps9 = p.ntaps == 9;
-      const bool dbg_align = p.dbg_align != 0;
+      const int nacc = p.nacc, acc_cols = p.acc_cols;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       unsigned long long* const dbg = p.dbg;
@@ -195,7 +195,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         if (dbg) w_tempty += clock64() - tw0;
         tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(acc * kAccCols);
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * acc_cols);
         const uint32_t mb = (uint32_t)it.mb_act;
         for (int ch = 0; ch < nchunk; ++ch) {
           const long long tw1 = dbg ? clock64() : 0;
@@ -203,27 +203,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           if (dbg) w_full += clock64() - tw1;
           tc_fence_after();
           const uint32_t sa16 = stage0_16 + (uint32_t)stage * stage_16;
-          uint32_t a_row = a_lo_const | (sa16 + (uint32_t)(dbg_align ? (it.moff0 & ~7) : it.moff0));
+          uint32_t a_row = a_lo_const | (sa16 + (uint32_t)it.moff0);
           uint32_t b_lo = b_lo_const | (sa16 + a_bytes_16);
           if (taps9) {
+            // one elected region per K chunk: 9 taps x MB MMAs issued back to back by the same thread
+            if (elect_one()) {
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
+              for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                const uint32_t accum = (ky > 0 || kx > 0) ? 1u : (ch > 0 ? 1u : 0u);
-                uint32_t a_lo = a_row + (dbg_align ? 0u : (uint32_t)kx), d = d0;
-                if (elect_one()) {
+                for (int kx = 0; kx < 3; ++kx) {
+                  const uint32_t accum = (ky > 0 || kx > 0) ? 1u : (ch > 0 ? 1u : 0u);
+                  uint32_t a_lo = a_row + (uint32_t)kx, d = d0;
                   for (uint32_t b = 0; b < mb; ++b) {
                     tc_mma_bf16(d, a_lo, desc_hi, b_lo, desc_hi, idesc, accum);
                     a_lo += mstep;
                     d += nt;
                   }
+                  b_lo += b_tap_16;
                 }
-                __syncwarp();
-                b_lo += b_tap_16;
+                a_row += pw;
               }
-              a_row += dbg_align ? (pw & ~7u) : pw;
             }
+            __syncwarp();
           } else {
             uint32_t a_lo = a_row, d = d0;
             if (elect_one()) {
@@ -241,7 +242,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         }
         if (elect_one()) tc_commit(&tfull[acc]);
         __syncwarp();
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
       }
       if (dbg && lane == 0) {
         atomicAdd(dbg + 2, (unsigned long long)(clock64() - t_begin));
@@ -268,6 +269,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     float* const out_logit = p.out_logit;
     const float outc_b = fuse_outc ? __ldg(p.outc_b) : 0.f;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int nacc = p.nacc, acc_cols = p.acc_cols;
     int acc = 0;
     uint32_t acc_phase = 0;
     unsigned long long* const dbg = (warp == 2 && lane == 0) ? p.dbg : nullptr;
@@ -290,7 +292,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           float logit = 0.f;
           for (int c0 = 0; c0 < NT; c0 += 32) {
             uint32_t r[32];
-            tc_ld32(tmem_base + lane_base + (uint32_t)(acc * kAccCols + b * NT + c0), r);
+            tc_ld32(tmem_base + lane_base + (uint32_t)(acc * acc_cols + b * NT + c0), r);
             if (valid) {
               const float* bias = s_bias + cbase0 + c0;
   #pragma unroll
@@ -344,7 +346,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           const long pix = (long)oy * Wo + ox;
           for (int c0 = 0; c0 < NT; c0 += 32) {
             uint32_t r[32];
-            tc_ld32(tmem_base + lane_base + (uint32_t)(acc * kAccCols + b * NT + c0), r);
+            tc_ld32(tmem_base + lane_base + (uint32_t)(acc * acc_cols + b * NT + c0), r);
             if (valid) {
               const float* bias = s_bias + cbase0 + c0;
 #pragma unroll
@@ -382,7 +384,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           const bool valid = y < Hi;
           for (int c0 = 0; c0 < NT; c0 += 32) {
             uint32_t r[32];
-            tc_ld32(tmem_base + lane_base + (uint32_t)(acc * kAccCols + b * NT + c0), r);
+            tc_ld32(tmem_base + lane_base + (uint32_t)(acc * acc_cols + b * NT + c0), r);
             if (valid) {
               const int j0 = it.ns * NT + c0;
               const int pos = j0 / C, co0 = j0 - pos * C;
@@ -422,7 +424,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
     }
     if (dbg) {
       atomicAdd(dbg + 5, (unsigned long long)(clock64() - t_begin));
@@ -445,7 +447,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 namespace {
 
 unsigned long long* g_dbg = nullptr;   // diagnostics only, see uncl_conv_tc_set_debug
-int g_dbg_align = 0;
 
 // fills the tile geometry for an (ntaps = 9: 3x3 with halo | ntaps = 1: pointwise GEMM) problem and launches
 int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, int H, int W, int epi, int bias_floats,
@@ -453,13 +454,31 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
   UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "%s: input must be 16-byte aligned", what);
   const int halo = p.ntaps == 9 ? 2 : 0;
   if (p.nchunk <= 0) p.nchunk = C_in / 16;
-  const int mb_max = kAccCols / p.NT;
+  // Accumulator staging.  The tensor core keeps the B tile (weights of one tap / K chunk) stationary and streams the A
+  // rows through it; measured cost per tap = ~60-90 cycles to switch B + MB x (stream 128 rows).  More M blocks per
+  // tile amortise the switch, so K-heavy layers take all 512 TMEM columns for ONE accumulator stage (twice the M
+  // blocks; the exposed epilogue is < 3 % of such a tile), short-K layers keep two stages so that the epilogue of
+  // tile i overlaps the MMAs of tile i+1.  Measured per layer (profiles/README.md): the single stage pays off for
+  // N = 128 with K >= 512*9 (up0.conv: 167 -> 129 us); for narrower N the exposed epilogue and the coarser tiles cost
+  // more than the amortisation gains.
+  p.nacc = (p.NT == 128 && C_in >= 512 && p.ntaps == 9 && getenv("UNCL_PROBE_DOUBLE_ACC") == nullptr) ? 1 : 2;
+  p.acc_cols = p.nacc == 1 ? 512 : kAccCols;
+  const int mb_max = p.acc_cols / p.NT;
   // column bands: the TMA box row is PW pixels = 2*PW 8-byte elements and a box dimension holds <= 256 elements
   p.nbands = ceil_div(p.Wo, 128 - halo);
   p.BW = ceil_div(p.Wo, p.nbands);
   p.PW = p.BW + halo;
   p.band_total = p.Ho * p.PW;
-  p.MB = mb_max < ceil_div(p.band_total, 128) ? mb_max : ceil_div(p.band_total, 128);
+  {
+    // equal-sized tiles: the band's M blocks are spread evenly over the smallest number of tiles that fit TMEM
+    const int blocks = ceil_div(p.band_total, 128);
+    const int tiles = ceil_div(blocks, mb_max);
+    p.MB = ceil_div(blocks, tiles);
+  }
+  if (const char* e = getenv("UNCL_PROBE_MB")) {   // timing probe: force the M blocks per tile
+    const int want = atoi(e);
+    if (want >= 1 && want < p.MB) p.MB = want;
+  }
   p.PH = (p.PW - 1 + 128 * p.MB - 1) / p.PW + 1 + halo;
   p.tiles_per_band = ceil_div(p.band_total, 128 * p.MB);
   p.tiles_per_img = p.nbands * p.tiles_per_band;
@@ -493,7 +512,6 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
 
   if (p.ns_per_group <= 0) p.ns_per_group = p.NS;
   p.dbg = g_dbg;
-  p.dbg_align = g_dbg_align;
   auto kern = epi == 0 ? conv3x3_tc_kernel<0> : (epi == 1 ? conv3x3_tc_kernel<1> : conv3x3_tc_kernel<2>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));
@@ -598,7 +616,6 @@ extern "C" int uncl_pw_conv_tc(const void* in, long in_img_stride, const void* w
 // [4] its wait-for-free-accumulator, [5] epilogue-warp cycles, [6] its wait-for-accumulator, [7] CTA count.
 // Not thread-safe, not for production use (the only mutable global of the library); pass NULL to switch off.
 extern "C" int uncl_conv_tc_set_debug(void* counters) {
-  g_dbg_align = getenv("UNCL_PROBE_ALIGNED_TAPS") != nullptr;
   g_dbg = reinterpret_cast<unsigned long long*>(counters);
   return UNCL_OK;
 }
