@@ -46,7 +46,8 @@ int uncl_conv3x3_simt(const void* in, long in_img_stride, const float* w, const 
                       int dtype, uncl_stream_t stream);
 
 /* Same operator on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM, TMA-fed).
- * w_packed: bf16 [C_in/16][9][2][C_out][8] (see uncltmo_b200/packing.py); bias fp32.
+ * w_packed: bf16, the B-operand layout uncltmo_b200/packing.py:conv3x3_tc produces for this (C_in, C_out):
+ * [NS][C_in/16][9][2][NT][8], or [NS][C_in/16][3][2][3*NT][8] for the kx-merged kernel (C_out <= 64, C_in >= 64); bias fp32.
  * fuse_outc=1: apply the 1x1 out conv (outc_w [C_out], outc_b [1]) + sigmoid in the epilogue and write
  * out_img [N][Ho][Wo] fp32 (unet_parts.py:338-345 + nn.Sigmoid, Unet_singleFrame.py:207-209); `out` may then be
  * NULL to skip storing the feature map.  The input is always bf16; `out_dtype` selects bf16 or fp32 stores (the

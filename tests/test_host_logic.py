@@ -95,6 +95,16 @@ def test_tc_weight_packing_layout():
     assert p[ns, ch, tap, half, n, k].float() == w9[tap, ch * 16 + half * 8 + k, ns * 128 + n]
 
 
+def test_tc_weight_packing_layout_merged_kx():
+    """C_out <= 64, C_in >= 64: the three kx taps of a filter row sit side by side in N (conv_tc_merged.cu)."""
+    for co in (32, 64):
+        w9 = torch.arange(9 * 64 * co, dtype=torch.float32).reshape(9, 64, co) % 251
+        p = packing.conv3x3_tc(w9)
+        assert p.shape == (1, 4, 3, 2, 3 * co, 8) and p.dtype == torch.bfloat16
+        ch, ky, half, kx, n, k = 2, 1, 1, 2, co - 3, 5
+        assert p[0, ch, ky, half, kx * co + n, k].float() == w9[ky * 3 + kx, ch * 16 + half * 8 + k, n]
+
+
 def test_convT2x2_and_pointwise_packing():
     g = torch.Generator().manual_seed(4)
     w = torch.randn(32, 32, 2, 2, generator=g)

@@ -525,12 +525,36 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
 
 }  // namespace
 
+int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                                  long out_img_stride, int out_f32, int N, int C_in, int H, int W, int C_out, int pad,
+                                  int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
+                                  float* out_img, float* out_logit, unsigned long long* dbg, cudaStream_t stream);
+
+// Which 3x3 layers run in the kx-merged kernel (conv_tc_merged.cu); packing.conv3x3_tc packs the weights to match.
+// Measured per layer of the 1080p frame (profiles/README.md): with C_out <= 64 the merged formulation wins when the
+// K loop is long enough to hide its heavier epilogue (C_in >= 64: 500 -> 327 us, 253 -> 155 us, 184 -> 113 us) and loses
+// on the C_in = 32 layers, which are epilogue-bound either way.
+static bool use_merged(int C_in, int C_out) {
+  const char* e = getenv("UNCL_MERGED_MIN_CI");
+  return C_out <= 64 && C_in >= (e ? atoi(e) : 64);
+}
+
 extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
                                long out_img_stride, int out_dtype, int N, int C_in, int H, int W, int C_out, int pad,
                                int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
                                float* out_img, float* out_logit, cudaStream_t stream) {
   UNCL_REQUIRE(N > 0 && C_in % 16 == 0 && C_out % 32 == 0 && (pad == 0 || pad == 2),
                "conv3x3_tc: unsupported C_in=%d C_out=%d pad=%d", C_in, C_out, pad);
+  if (use_merged(C_in, C_out)) {
+    UNCL_REQUIRE(out_dtype == UNCL_F32 || out_dtype == UNCL_BF16, "conv3x3_tc: bad out_dtype");
+    UNCL_REQUIRE(!fuse_outc || (outc_w && outc_b && out_img), "conv3x3_tc: fuse_outc needs outc params");
+    UNCL_REQUIRE(out != nullptr || fuse_outc, "conv3x3_tc: no output requested");
+    UNCL_REQUIRE(act == UNCL_ACT_RELU || act == UNCL_ACT_NONE, "conv3x3_tc: only ReLU / identity epilogues are built");
+    UNCL_REQUIRE(H + 2 * pad - 2 > 0 && W + 2 * pad - 2 > 0, "conv3x3_tc: empty output");
+    return uncl_launch_conv3x3_tc_merged(in, in_img_stride, w_packed, bias, out, out_img_stride, out_dtype == UNCL_F32, N, C_in,
+                                         H, W, C_out, pad, act, emit_skip, fuse_outc, outc_w, outc_b, out_img, out_logit,
+                                         g_dbg, stream);
+  }
   TcParams p{};
   p.NT = C_out < 128 ? C_out : 128;
   if (C_out == 256 && getenv("UNCL_PROBE_NT256") != nullptr) p.NT = 256;   // timing probe (weights packed by the caller)

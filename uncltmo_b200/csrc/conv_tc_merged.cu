@@ -1,0 +1,457 @@
+// 3x3 stride-1 convolution / ConvTranspose 3x3 for NARROW outputs (C_out <= 64) on the tensor cores with the three
+// kx taps of a kernel row merged into the N dimension of one tcgen05.mma.
+//
+// Why (profiles/r1_mma_probe.csv): a kind::f16 M=128 K=16 instruction with both operands in shared memory costs
+// max(N/2, (4096 + 32 N) / 128) cycles - it reads its 4 KB A tile (128 pixels x 16 channels) and its B tile at
+// 128 B/cycle every time, whatever the previous instruction used.  With N = C_out = 32 (52 % of the generator's FLOPs)
+// the A read alone is twice the math.  Merging the three kx taps makes N' = 3 C_out columns share one A read:
+//     D[p][kx*C + co] = sum_{ky, ci} X[p + ky*PW][ci] * W[ky][kx][ci][co]        (3 MMAs per K chunk instead of 9)
+//     out[q][co]      = D[q][co] + D[q+1][C + co] + D[q+2][2C + co]              (epilogue)
+// N' = 96 costs 56 cycles for what took 3 x 40, N' = 192 runs at the math floor (96 cycles).
+// The price is the epilogue's cross-row sum: accumulator rows are TMEM lanes, a warp only reaches its own 32 lanes, so
+// the kx = 1, 2 column groups come from the neighbouring lanes by warp shuffle and, for the last two lanes of a warp,
+// from the next warp through a small shared-memory exchange.  Tiles overlap by two positions so that no exchange
+// crosses a tile.
+//
+// Everything else follows conv_tc.cu: C8-blocked bf16 activations, one TMA halo box per K chunk whose shared-memory
+// image is the no-swizzle K-major operand, a filter ROW (ky) is a descriptor start-address shift of ky*PW pixels,
+// persistent warp-specialised CTAs, double-buffered TMEM accumulator.
+// Reference operator: models/unet_multi_filters/unet_parts.py:57-87, :126-141, :183-193, :319-322, :338-345.
+// Weights: bf16 [NS][C_in/16][3 ky][2][3*NT (kx, n)][8], NT = min(C_out, 64) (packing.conv3x3_tc).
+#include <cstdlib>
+#include "tc_ptx.cuh"
+
+namespace {
+
+using namespace tcptx;
+
+constexpr int kThreads = 576;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2-17: epilogue
+constexpr int kEpiWarps = 16;     // 4 TMEM lane quarters x 2 work units x 2 halves of 16 channels
+constexpr int kMaxStages = 8;
+constexpr int kUnits = 2;         // (M block, 32-channel chunk) pairs per tile: 2 blocks x 32 ch or 1 block x 64 ch
+constexpr int kXSlot = 96;        // floats per exchange slot: lane 0's kx=1 and kx=2 groups, lane 1's kx=2 group
+
+struct MgParams {
+  const bf16* w;
+  const float* bias;
+  void* out;
+  int out_f32;
+  long out_img_stride;
+  const float* outc_w;
+  const float* outc_b;
+  float* out_img;
+  float* out_logit;
+  int C_out, Ho, Wo, pad;
+  int NT, NS, NP;           // channels per N split, N splits, MMA N = 3 * NT
+  int MB, ADV;              // M blocks per tile, tile advance in positions (128 * MB - 2)
+  int PW, PH, BW;
+  int band_total, tiles_per_band, tiles_per_img, num_items;
+  int nchunk, stages, nacc, acc_cols;
+  int a_box_bytes, a_stage_bytes, b_stage_bytes, stage_bytes;
+  int act, emit_skip, fuse_outc;
+  unsigned long long m_NS, m_tpi, m_tpb, m_PW;   // 2^40 / d + 1: exact x / d for x < 2^20, d < 2^12 ... (see fastdiv)
+  unsigned long long* dbg;
+};
+
+// x / d with the host-computed magic m = 2^40 / d + 1 (exact for x < 2^24 and d <= 2^16: x * (m - 2^40/d) < 2^40 / d)
+__device__ __forceinline__ int fastdiv(int x, unsigned long long m) {
+  return (int)(((unsigned long long)(uint32_t)x * m) >> 40);
+}
+
+struct MgItem {
+  int n, ns, band, bx, by, moff0, q0;
+};
+
+__device__ __forceinline__ MgItem mg_decode(const MgParams& p, int item) {
+  MgItem it;
+  const int tile = fastdiv(item, p.m_NS);
+  it.ns = item - tile * p.NS;
+  it.n = fastdiv(tile, p.m_tpi);
+  const int t = tile - it.n * p.tiles_per_img;
+  it.band = fastdiv(t, p.m_tpb);
+  const int tb = t - it.band * p.tiles_per_band;
+  it.q0 = tb * p.ADV;
+  const int y0 = fastdiv(it.q0, p.m_PW);
+  it.bx = it.band * p.BW - p.pad;
+  it.by = y0 - p.pad;
+  it.moff0 = it.q0 - y0 * p.PW;
+  return it;
+}
+
+__device__ __forceinline__ void tc_ld32_nw(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16_nw(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// MMA issuer: 3 filter rows x MB blocks per K chunk, straight-line (MB is a compile-time constant), every block of
+// the tile is always issued (blocks past the end of a band read zero-filled / stale rows and are masked later).
+template <int MB>
+__device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_base, uint64_t* full, uint64_t* empty,
+                                            uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base, int lane) {
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NP >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+  const uint32_t a_lo_const = ((uint32_t)(p.PH * p.PW) & 0x3fffu) << 16;   // LBO_A = PH*PW*16 B
+  const uint32_t b_lo_const = ((uint32_t)p.NP & 0x3fffu) << 16;            // LBO_B = NP*16 B
+  const uint32_t stage0_16 = smem_u32(stage_base) >> 4, stage_16 = (uint32_t)p.stage_bytes >> 4;
+  const uint32_t a_bytes_16 = (uint32_t)p.a_stage_bytes >> 4, b_row_16 = (uint32_t)(2 * p.NP);
+  const uint32_t pw = (uint32_t)p.PW, np = (uint32_t)p.NP;
+  const int nacc = p.nacc, acc_cols = p.acc_cols, nchunk = p.nchunk, stages = p.stages, num_items = p.num_items;
+  int stage = 0, acc = 0;
+  uint32_t phase = 0, acc_phase = 0;
+  unsigned long long* const dbg = p.dbg;
+  long long w_full = 0, w_tempty = 0;
+  const long long t_begin = dbg ? clock64() : 0;
+  for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    const MgItem it = mg_decode(p, item);
+    const long long tw0 = dbg ? clock64() : 0;
+    mbar_wait(&tempty[acc], acc_phase ^ 1);
+    if (dbg) w_tempty += clock64() - tw0;
+    tc_fence_after();
+    const uint32_t d0 = tmem_base + (uint32_t)(acc * acc_cols);
+    for (int ch = 0; ch < nchunk; ++ch) {
+      const long long tw1 = dbg ? clock64() : 0;
+      mbar_wait(&full[stage], phase);
+      if (dbg) w_full += clock64() - tw1;
+      tc_fence_after();
+      const uint32_t sa16 = stage0_16 + (uint32_t)stage * stage_16;
+      const uint32_t a_row = a_lo_const | (sa16 + (uint32_t)it.moff0);
+      const uint32_t b_lo = b_lo_const | (sa16 + a_bytes_16);
+      if (elect_one()) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+          for (int b = 0; b < MB; ++b) {
+            tc_mma_bf16(d0 + (uint32_t)b * np, a_row + (uint32_t)ky * pw + (uint32_t)b * 128u, desc_hi,
+                        b_lo + (uint32_t)ky * b_row_16, desc_hi, idesc, ky > 0 ? 1u : (ch > 0 ? 1u : 0u));
+          }
+        }
+        tc_commit(&empty[stage]);
+      }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) tc_commit(&tfull[acc]);
+    __syncwarp();
+    if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+  }
+  if (dbg && lane == 0) {
+    atomicAdd(dbg + 2, (unsigned long long)(clock64() - t_begin));
+    atomicAdd(dbg + 3, (unsigned long long)w_full);
+    atomicAdd(dbg + 4, (unsigned long long)w_tempty);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MgParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint8_t* stage_base = smem;
+  float* xbuf = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes);   // [2][kUnits][4][kXSlot]
+  float* lbuf = xbuf + 2 * kUnits * 4 * kXSlot;                                       // [2][kUnits][128] partial logits
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lbuf + 2 * kUnits * 128);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [C_out] (+ [C_out] outc weights)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_items = p.num_items, nchunk = p.nchunk, stages = p.stages, stage_bytes = p.stage_bytes;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < p.C_out; i += kThreads) {
+    s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    if (p.fuse_outc) s_bias[p.C_out + i] = p.outc_w[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = (uint32_t)(p.a_box_bytes + p.b_stage_bytes), b_bytes = (uint32_t)p.b_stage_bytes;
+      const int a_stage_bytes = p.a_stage_bytes;
+      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
+      unsigned long long* const dbg = p.dbg;
+      long long w_empty = 0;
+      const long long t_begin = dbg ? clock64() : 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const MgItem it = mg_decode(p, item);
+        const uint8_t* wsrc = wbase + (size_t)it.ns * nchunk * b_bytes;
+        for (int ch = 0; ch < nchunk; ++ch) {
+          const long long tw0 = dbg ? clock64() : 0;
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (dbg) w_empty += clock64() - tw0;
+          uint8_t* sa = stage_base + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full[stage], tx_bytes);
+          tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, ch * 2, it.n);
+          bulk_load(sa + a_stage_bytes, wsrc + (size_t)ch * b_bytes, b_bytes, &full[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (dbg) {
+        atomicAdd(dbg + 0, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(dbg + 1, (unsigned long long)w_empty);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (p.MB == 1) mg_mma_role<1>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
+    else mg_mma_role<2>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
+    __syncwarp();
+  } else {
+    // =============================== epilogue ===============================
+    // A tile has two work units (M block b, 32-channel chunk c): 2 x 32 channels (NT = 32) or 1 x 64 channels (NT = 64).
+    // Each unit is handled, per TMEM lane quarter, by two warps that take 16 channels each: 4 x 2 x 2 = 16 warps.
+    const int quarter = warp & 3;                 // a warp reaches TMEM lanes 32 * (warp % 4) ..
+    const int k = (warp - 2) >> 2;                // 0..3
+    const int u = k & 1, h = k >> 1;
+    const int row = quarter * 32 + lane;
+    const int Ho = p.Ho, Wo = p.Wo, NT = p.NT, NP = p.NP, C_out = p.C_out, ADV = p.ADV, PW = p.PW, BW = p.BW;
+    const int b = NT == 32 ? u : 0, c = NT == 32 ? 0 : u;
+    const uint32_t col = (uint32_t)(b * NP + c * 32 + h * 16);
+    const long cb_stride = (long)Ho * Wo * 8;
+    const long skip2 = (long)(2 * (C_out / 8)) * cb_stride, skip3 = (long)(3 * (C_out / 8)) * cb_stride;
+    const float act_floor = (p.act == UNCL_ACT_RELU) ? 0.f : -INFINITY;
+    const bool emit_skip = p.emit_skip != 0, fuse_outc = p.fuse_outc != 0;
+    bf16* const out = reinterpret_cast<bf16*>(p.out);
+    float* const outf = reinterpret_cast<float*>(p.out);
+    const bool out_f32 = p.out_f32 != 0;
+    const long out_img_stride = p.out_img_stride;
+    float* const out_img = p.out_img;
+    float* const out_logit = p.out_logit;
+    const float outc_b = fuse_outc ? __ldg(p.outc_b) : 0.f;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int nacc = p.nacc, acc_cols = p.acc_cols;
+    // rows q+1, q+2 of lanes 30 / 31 live in the next warp: next quarter, or quarter 0 of the next M block
+    const bool has_next = quarter < 3 || (NT == 32 && u == 0);
+    const int nu = quarter < 3 ? u : 1, nq = quarter < 3 ? quarter + 1 : 0;
+    const int my_slot = (u * 4 + quarter) * kXSlot + h * 16, next_slot = (nu * 4 + nq) * kXSlot + h * 16;
+    const int src1 = (lane + 1) & 31, src2 = (lane + 2) & 31;
+    const int l = b * 128 + row;
+    const int cb0 = c * 32 + h * 16;   // first channel of this warp inside the N split
+    int acc = 0, par = 0;
+    uint32_t acc_phase = 0;
+    unsigned long long* const dbg = (warp == 2 && lane == 0) ? p.dbg : nullptr;
+    long long w_tfull = 0;
+    const long long t_begin = dbg ? clock64() : 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const MgItem it = mg_decode(p, item);
+      const long long tw0 = dbg ? clock64() : 0;
+      mbar_wait(&tfull[acc], acc_phase);
+      if (dbg) w_tfull += clock64() - tw0;
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + lane_base + (uint32_t)(acc * acc_cols) + col;
+      uint32_t r0[16], r1[16], r2[16];
+      tc_ld16_nw(tacc, r0);
+      tc_ld16_nw(tacc + (uint32_t)NT, r1);
+      tc_ld16_nw(tacc + (uint32_t)(2 * NT), r2);
+      tc_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);   // everything this warp needs is in registers: release the accumulator
+      float* const xpar = xbuf + par * (kUnits * 4 * kXSlot);
+      // lanes 0 and 1 publish what the previous warp's lanes 30 / 31 need ...
+      if (lane < 2) {
+        float4* s = reinterpret_cast<float4*>(xpar + my_slot + (lane == 0 ? 32 : 64));
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            s[j - 8] = make_float4(__uint_as_float(r1[4 * j]), __uint_as_float(r1[4 * j + 1]), __uint_as_float(r1[4 * j + 2]),
+                                   __uint_as_float(r1[4 * j + 3]));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          s[j] = make_float4(__uint_as_float(r2[4 * j]), __uint_as_float(r2[4 * j + 1]), __uint_as_float(r2[4 * j + 2]),
+                             __uint_as_float(r2[4 * j + 3]));
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      // ... and take over the next warp's first rows: nobody in this warp reads lane 0's kx=1 group or lanes 0/1's kx=2
+      // groups, so they become the sources the rotating shuffles deliver to lanes 31 / 30, 31
+      if (lane < 2 && has_next) {
+        const float4* s = reinterpret_cast<const float4*>(xpar + next_slot + (lane == 0 ? 32 : 64));
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 f = s[j - 8];
+            r1[4 * j] = __float_as_uint(f.x); r1[4 * j + 1] = __float_as_uint(f.y);
+            r1[4 * j + 2] = __float_as_uint(f.z); r1[4 * j + 3] = __float_as_uint(f.w);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 f = s[j];
+          r2[4 * j] = __float_as_uint(f.x); r2[4 * j + 1] = __float_as_uint(f.y);
+          r2[4 * j + 2] = __float_as_uint(f.z); r2[4 * j + 3] = __float_as_uint(f.w);
+        }
+      }
+      __syncwarp();
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        v[j] = __uint_as_float(r0[j]) + __shfl_sync(0xffffffffu, __uint_as_float(r1[j]), src1) +
+               __shfl_sync(0xffffffffu, __uint_as_float(r2[j]), src2);
+      const int q = it.q0 + l;
+      const int oy = fastdiv(q, p.m_PW), xl = q - oy * PW;
+      const int ox = it.band * BW + xl;
+      const bool valid = (l < ADV) && (oy < Ho) && (xl < BW) && (ox < Wo);
+      const long pix = (long)oy * Wo + ox;
+      const int cbase = it.ns * NT + cb0;
+      float logit = 0.f;
+      if (valid) {
+        const float* bias = s_bias + cbase;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[g * 8 + j] + bias[g * 8 + j], act_floor);
+          if (out != nullptr) {
+            const long off = (long)it.n * out_img_stride + (long)(cbase / 8 + g) * cb_stride + pix * 8;
+            float s2[8], s3[8];
+            if (emit_skip) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { s2[j] = o[j] * o[j]; s3[j] = sqrtf(o[j] + 1e-8f); }
+            }
+            if (out_f32) {
+              store8(outf + off, o);
+              if (emit_skip) { store8(outf + off + skip2, s2); store8(outf + off + skip3, s3); }
+            } else {
+              store8(out + off, o);
+              if (emit_skip) { store8(out + off + skip2, s2); store8(out + off + skip3, s3); }
+            }
+          }
+          if (fuse_outc) {
+            const float* ow = s_bias + C_out + cbase + g * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) logit = fmaf(o[j], ow[j], logit);
+          }
+        }
+      }
+      if (fuse_outc) {   // the two 16-channel halves of a pixel sit in different warps: combine through shared memory
+        float* lp = lbuf + (par * kUnits + u) * 128 + row;
+        if (h == 1) *lp = logit;
+        asm volatile("bar.sync 2, 512;" ::: "memory");
+        if (h == 0 && valid) {
+          logit += *lp + outc_b;
+          const long o1 = (long)it.n * Ho * Wo + pix;
+          if (out_logit) out_logit[o1] = logit;
+          out_img[o1] = 1.f / (1.f + __expf(-logit));
+        }
+      }
+      par ^= 1;
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+    }
+    if (dbg) {
+      atomicAdd(dbg + 5, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(dbg + 6, (unsigned long long)w_tfull);
+      atomicAdd(dbg + 7, 1ull);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+}  // namespace
+
+// Called by uncl_conv3x3_tc (conv_tc.cu) for C_out <= 64; arguments already validated there.
+int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                                  long out_img_stride, int out_f32, int N, int C_in, int H, int W, int C_out, int pad,
+                                  int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
+                                  float* out_img, float* out_logit, unsigned long long* dbg, cudaStream_t stream) {
+  const char* what = "conv3x3_tc(merged)";
+  UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "%s: input must be 16-byte aligned", what);
+  MgParams p{};
+  p.NT = C_out < 64 ? C_out : 64;
+  UNCL_REQUIRE(p.NT % 32 == 0 && C_out % p.NT == 0, "%s: unsupported C_out=%d", what, C_out);
+  UNCL_REQUIRE(!fuse_outc || C_out == 32, "%s: the fused out conv needs C_out == 32", what);
+  p.NS = C_out / p.NT;
+  p.NP = 3 * p.NT;
+  p.w = reinterpret_cast<const bf16*>(w_packed);
+  p.bias = bias; p.out = out; p.out_f32 = out_f32; p.out_img_stride = out_img_stride;
+  p.outc_w = outc_w; p.outc_b = outc_b; p.out_img = out_img; p.out_logit = out_logit;
+  p.C_out = C_out; p.pad = pad;
+  p.Ho = H + 2 * pad - 2; p.Wo = W + 2 * pad - 2;
+  p.act = act; p.emit_skip = emit_skip; p.fuse_outc = fuse_outc;
+  p.nchunk = C_in / 16;
+  // accumulator staging: two stages of 256 TMEM columns (epilogue of tile i overlaps the MMAs of tile i+1)
+  p.nacc = 2;
+  p.acc_cols = 256;
+  p.MB = p.acc_cols / p.NP;   // 2 blocks of 96 columns or 1 block of 192: always two 32-channel work units per tile
+  p.ADV = 128 * p.MB - 2;
+  const int nbands = ceil_div(p.Wo, 126);
+  p.BW = ceil_div(p.Wo, nbands);
+  p.PW = p.BW + 2;
+  p.band_total = p.Ho * p.PW;
+  p.tiles_per_band = ceil_div(p.band_total - 2, p.ADV);
+  if (p.tiles_per_band < 1) p.tiles_per_band = 1;
+  p.tiles_per_img = nbands * p.tiles_per_band;
+  p.PH = (p.PW - 1 + 128 * p.MB - 1) / p.PW + 1 + 2;
+  UNCL_REQUIRE(p.PW <= 128 && p.PH <= 256, "%s: halo tile too large (%d x %d)", what, p.PW, p.PH);
+  p.num_items = N * p.tiles_per_img * p.NS;
+  UNCL_REQUIRE(p.num_items < (1 << 24), "%s: too many tiles (%d)", what, p.num_items);
+  p.m_NS = (1ull << 40) / (unsigned)p.NS + 1; p.m_tpi = (1ull << 40) / (unsigned)p.tiles_per_img + 1;
+  p.m_tpb = (1ull << 40) / (unsigned)p.tiles_per_band + 1; p.m_PW = (1ull << 40) / (unsigned)p.PW + 1;
+  p.a_box_bytes = 2 * p.PH * p.PW * 16;
+  p.a_stage_bytes = (p.a_box_bytes + 127) & ~127;
+  p.b_stage_bytes = 3 * 2 * p.NP * 16;
+  p.stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  const int tail = 128 + 2 * kUnits * 4 * kXSlot * 4 + 2 * kUnits * 128 * 4 + (2 * kMaxStages + 4) * 8 + 16 + 2 * C_out * 4 + 256;
+  const int budget = 227 * 1024 - tail;
+  p.stages = budget / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  if (const char* e = getenv("UNCL_MG_STAGES")) { const int want = atoi(e); if (want >= 2 && want < p.stages) p.stages = want; }
+  UNCL_REQUIRE(p.stages >= 2, "%s: tile does not fit shared memory (%d B per stage)", what, p.stage_bytes);
+  int smem_bytes = p.stages * p.stage_bytes + tail;
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM (each owns all 512 TMEM columns)
+
+  CUtensorMap tmap;
+  CUresult r = encode_blocked_bf16(&tmap, in, W, H, C_in / 8, N, in_img_stride, p.PW, p.PH, 2);
+  if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
+  p.dbg = dbg;
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_merged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.num_items < sms ? p.num_items : sms;
+  conv3x3_tc_merged_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap, p);
+  return uncl_check_launch(what);
+}

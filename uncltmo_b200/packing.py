@@ -4,6 +4,8 @@ These run on the device with torch tensor ops when weights are (re)loaded - plum
 Reference weight layouts: nn.Conv2d [C_out, C_in, kH, kW]; nn.ConvTranspose2d [C_in, C_out, kH, kW]
 (SURVEY.md Appendix B).
 """
+import os
+
 import torch
 
 
@@ -17,9 +19,22 @@ def conv3x3_taps(w, transposed):
     return w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]).contiguous().float()
 
 
+MERGED_MIN_CI = int(os.environ.get("UNCL_MERGED_MIN_CI", "64"))   # must match conv_tc.cu:use_merged()
+
+
 def conv3x3_tc(w9):
-    """[9][C_in][C_out] fp32 -> bf16 [NS][C_in/16][9][2][NT][8], NT = min(C_out, 128) (conv_tc.cu B operand)."""
+    """[9][C_in][C_out] fp32 -> the tensor-core B operand of uncl_conv3x3_tc (bf16, K-major core matrices of 8 x 16 B).
+
+    C_out <= 64 and C_in >= 64 (conv_tc_merged.cu, the three kx taps of a filter row merged into N):
+        [NS][C_in/16][3 ky][2][3*NT (kx, n)][8], NT = min(C_out, 64)
+    wider layers (conv_tc.cu, one tap per MMA): [NS][C_in/16][9][2][NT][8], NT = min(C_out, 128)."""
     _, ci, co = w9.shape
+    if co <= 64 and ci >= MERGED_MIN_CI:
+        nt = min(co, 64)
+        ns = co // nt
+        t = w9.reshape(3, 3, ci // 16, 2, 8, ns, nt)       # ky, kx, chunk, half, k8, ns, n
+        t = t.permute(5, 2, 0, 3, 1, 6, 4).contiguous()    # ns, chunk, ky, half, kx, n, k8
+        return t.reshape(ns, ci // 16, 3, 2, 3 * nt, 8).to(torch.bfloat16)
     nt = min(co, 128)
     ns = co // nt
     t = w9.reshape(9, ci // 16, 2, 8, ns, nt)          # tap, chunk, half, k8, ns, n
