@@ -8,9 +8,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from uncltmo_b200 import _lib, packing  # noqa: E402
 
-CASES = {  # name: (C_in, C_out, H, pad, emit_skip, fuse_outc)
-    "inc1": (32, 32, 254, 0, 1, 0), "d0_1": (64, 64, 124, 0, 1, 0), "d1_1": (128, 128, 59, 0, 1, 0),
-    "u1_0": (512, 64, 57, 2, 0, 0), "u3_0": (128, 32, 252, 2, 0, 0), "u3_1": (32, 32, 254, 2, 0, 1),
+CASES = {  # name: (C_in, C_out, H, pad, emit_skip, fuse_outc) - the 17 tensor-core 3x3 layers of the generator
+    "inc1": (32, 32, 254, 0, 1, 0), "d0_0": (32, 64, 126, 0, 0, 0), "d0_1": (64, 64, 124, 0, 1, 0),
+    "d1_0": (64, 128, 61, 0, 0, 0), "d1_1": (128, 128, 59, 0, 1, 0), "d2_0": (128, 256, 28, 0, 0, 0),
+    "d2_1": (256, 256, 26, 0, 1, 0), "d3_0": (256, 256, 12, 0, 0, 0), "bott": (256, 256, 10, 2, 0, 0),
+    "u0_0": (1024, 128, 24, 2, 0, 0), "u0_1": (128, 128, 26, 2, 0, 0), "u1_0": (512, 64, 57, 2, 0, 0),
+    "u1_1": (64, 64, 59, 2, 0, 0), "u2_0": (256, 32, 122, 2, 0, 0), "u2_1": (32, 32, 124, 2, 0, 0),
+    "u3_0": (128, 32, 252, 2, 0, 0), "u3_1": (32, 32, 254, 2, 0, 1),
 }
 
 
@@ -40,7 +44,7 @@ def run(name, n=60, reps=1):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CASES)
+    names = sys.argv[1].split(",") if len(sys.argv) > 1 and sys.argv[1] != "all" else list(CASES)
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     for nm in names:
         run(nm, reps=reps)

@@ -61,6 +61,14 @@ __device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
 __device__ __forceinline__ void from_f(float& d, float x) { d = x; }
 __device__ __forceinline__ void from_f(bf16& d, float x) { d = __float2bfloat16_rn(x); }
 
+// MUFU.SQRT: max relative error 2^-23 (PTX ISA, sqrt.approx.f32) - one instruction instead of the ~10 of the IEEE sqrtf;
+// used where the result is an activation that is rounded to bf16 or feeds further fp32 arithmetic with looser tolerances
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
     case UNCL_ACT_RELU: return fmaxf(x, 0.f);

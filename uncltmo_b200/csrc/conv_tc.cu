@@ -26,8 +26,9 @@ namespace {
 
 using namespace tcptx;
 
-constexpr int kThreads = 320;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
-constexpr int kEpiWarps = 8;           // two warps per TMEM lane quarter, M blocks interleaved between them
+constexpr int kThreads = 576;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-17: epilogue
+constexpr int kEpiWarps = 16;          // four warps per TMEM lane quarter; (M block, 32-column chunk) units dealt round-robin
+constexpr int kEpiPerQuarter = kEpiWarps / 4;
 constexpr int kAccCols = 256;          // TMEM columns per accumulator stage when double-buffered (2 stages = 512 = all of TMEM)
 constexpr int kMaxStages = 6;
 
@@ -60,6 +61,8 @@ struct TcParams {
   const float* scale;       // per-image factor (DropPath) or null
   int ns_per_group;         // grouped 1x1 conv: N splits per group (K range of a split = its group's input channels)
   unsigned long long* dbg;  // diagnostics (uncl_conv_tc_set_debug): cycle counters of the three roles, or null
+  unsigned long long m_PW;  // 2^40 / PW + 1 (fastdiv_pw)
+  int probe_noload;         // timing probe: the producer only loads the first `stages` chunks, then re-signals stale stages
 };
 
 // ---------------------------------------------------------------- tile geometry shared by the three roles
@@ -78,6 +81,11 @@ struct Geo {  // hot scalars of TcParams, hoisted into registers
   int NS, tiles_per_img, tiles_per_band, MB, PW, BW, pad, band_total;
 };
 
+// q / PW with the host-computed magic m = 2^40 / PW + 1 (exact for q < 2^24, PW <= 128)
+__device__ __forceinline__ int fastdiv_pw(int q, unsigned long long m) {
+  return (int)(((unsigned long long)(uint32_t)q * m) >> 40);
+}
+
 __device__ __forceinline__ Item decode_item(const Geo& g, int item) {
   Item it;
   const int tile = item / g.NS;
@@ -93,6 +101,23 @@ __device__ __forceinline__ Item decode_item(const Geo& g, int item) {
   it.moff0 = it.q0 - y0 * g.PW;
   it.mb_act = min(g.MB, (g.band_total - it.q0 + 127) / 128);
   return it;
+}
+
+// 9 taps x MB blocks of one K chunk, fully unrolled: descriptor low words are base + compile-time-shaped offsets
+template <int MB>
+__device__ __forceinline__ void issue_taps9(uint32_t d0, uint32_t a_row, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                            uint32_t pw, uint32_t nt, uint32_t b_tap_16, uint32_t first) {
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+      for (int b = 0; b < MB; ++b) {
+        tc_mma_bf16(d0 + (uint32_t)b * nt, a_row + (uint32_t)ky * pw + (uint32_t)(kx + b * 128), desc_hi,
+                    b_lo + (uint32_t)(ky * 3 + kx) * b_tap_16, desc_hi, idesc, (ky > 0 || kx > 0) ? 1u : first);
+      }
+    }
+  }
 }
 
 // EPI 0: conv epilogue (bias, ReLU, optional skip emission / fused 1x1 out conv + sigmoid)
@@ -153,13 +178,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const uint8_t* wsrc = wbase + (size_t)it.ns * nchunk * b_bytes;
         const int kblk0 = (it.ns / ns_per_group) * nchunk * 2;   // first input channel block of this split's group
         for (int ch = 0; ch < nchunk; ++ch) {
+          if (p.probe_noload & 4) continue;
           const long long tw0 = dbg ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1);
           if (dbg) w_empty += clock64() - tw0;
           uint8_t* sa = stage_base + (size_t)stage * stage_bytes;
+          if ((p.probe_noload & 1) && (item != (int)blockIdx.x || ch >= stages)) { mbar_arrive(&full[stage]); }
+          else {
           mbar_expect_tx(&full[stage], tx_bytes);
           tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, kblk0 + ch * 2, it.n);
           bulk_load(sa + a_stage_bytes, wsrc + (size_t)ch * b_bytes, b_bytes, &full[stage]);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -199,29 +228,43 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const uint32_t mb = (uint32_t)it.mb_act;
         for (int ch = 0; ch < nchunk; ++ch) {
           const long long tw1 = dbg ? clock64() : 0;
-          mbar_wait(&full[stage], phase);
+          if (!(p.probe_noload & 4)) mbar_wait(&full[stage], phase);
           if (dbg) w_full += clock64() - tw1;
           tc_fence_after();
           const uint32_t sa16 = stage0_16 + (uint32_t)stage * stage_16;
           uint32_t a_row = a_lo_const | (sa16 + (uint32_t)it.moff0);
           uint32_t b_lo = b_lo_const | (sa16 + a_bytes_16);
           if (taps9) {
-            // one elected region per K chunk: 9 taps x MB MMAs issued back to back by the same thread
+            // one elected region per K chunk: 9 taps x MB MMAs issued back to back by the same thread.  For the tile
+            // heights the generator uses the region is straight-line code (issue_taps9<MB>): the issuing warp is a
+            // serial, latency-bound instruction stream and the remainder path of a runtime `mb` loop (R2UR / LDCU per
+            // tap) cost ~240 cycles per tap at MB = 2 - twice the 128 cycles its two N = 128 MMAs execute in.
+            // Every block of the tile is issued; blocks past the end of a band read zero-filled rows of the halo box
+            // and are skipped by the epilogue.
             if (elect_one()) {
+              const uint32_t first = ch > 0 ? 1u : 0u;
+              switch (p.MB) {
+                case 1: issue_taps9<1>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
+                case 2: issue_taps9<2>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
+                case 3: issue_taps9<3>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
+                case 4: issue_taps9<4>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
+                case 8: issue_taps9<8>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
+                default:
 #pragma unroll
-              for (int ky = 0; ky < 3; ++ky) {
+                  for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                  const uint32_t accum = (ky > 0 || kx > 0) ? 1u : (ch > 0 ? 1u : 0u);
-                  uint32_t a_lo = a_row + (uint32_t)kx, d = d0;
-                  for (uint32_t b = 0; b < mb; ++b) {
-                    tc_mma_bf16(d, a_lo, desc_hi, b_lo, desc_hi, idesc, accum);
-                    a_lo += mstep;
-                    d += nt;
+                    for (int kx = 0; kx < 3; ++kx) {
+                      const uint32_t accum = (ky > 0 || kx > 0) ? 1u : first;
+                      uint32_t a_lo = a_row + (uint32_t)kx, d = d0;
+                      for (uint32_t b = 0; b < mb; ++b) {
+                        tc_mma_bf16(d, a_lo, desc_hi, b_lo, desc_hi, idesc, accum);
+                        a_lo += mstep;
+                        d += nt;
+                      }
+                      b_lo += b_tap_16;
+                    }
+                    a_row += pw;
                   }
-                  b_lo += b_tap_16;
-                }
-                a_row += pw;
               }
             }
             __syncwarp();
@@ -236,7 +279,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             }
             __syncwarp();
           }
-          if (elect_one()) tc_commit(&empty[stage]);
+          if (!(p.probe_noload & 4) && elect_one()) tc_commit(&empty[stage]);
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -254,7 +297,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   } else {
     // =============================== epilogue (8 warps: 4 TMEM lane quarters x 2 M-block parities) ========
     const int quarter = warp & 3;
-    const int bpar = (warp - 2) >> 2;   // this warp takes M blocks b with (b & 1) == bpar
+    const int k4 = (warp - 2) >> 2;     // this warp takes the units u = (block, 32-column chunk) with u % 4 == k4
+    const int cpb = p.NT >> 5;          // 32-column chunks per M block
     const int row = quarter * 32 + lane;
     const int Ho = p.Ho, Wo = p.Wo, NT = p.NT, C_out = p.C_out;
     const long cb_stride = (long)Ho * Wo * 8;
@@ -283,14 +327,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       tc_fence_after();
       if constexpr (EPI == 0) {
         const int cbase0 = it.ns * NT;
-        for (int b = bpar; b < it.mb_act; b += 2) {
+        const int units = ((p.probe_noload & 2) ? 0 : it.mb_act) * cpb;
+        for (int u = k4, b = 0, cc = k4; u < units; u += kEpiPerQuarter, cc += kEpiPerQuarter) {
+          while (cc >= cpb) { cc -= cpb; ++b; }
+          const int c0 = cc * 32;
           const int q = it.q0 + b * 128 + row;
-          const int oy = q / geo.PW, xl = q - oy * geo.PW;
+          const int oy = fastdiv_pw(q, p.m_PW), xl = q - oy * geo.PW;
           const int ox = it.band * geo.BW + xl;
           const bool valid = (oy < Ho) && (xl < geo.BW) && (ox < Wo);
           const long pix = (long)oy * Wo + ox;
           float logit = 0.f;
-          for (int c0 = 0; c0 < NT; c0 += 32) {
+          {
             uint32_t r[32];
             tc_ld32(tmem_base + lane_base + (uint32_t)(acc * acc_cols + b * NT + c0), r);
             if (valid) {
@@ -305,7 +352,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                   float s2[8], s3[8];
                   if (emit_skip) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { s2[j] = v[j] * v[j]; s3[j] = sqrtf(v[j] + 1e-8f); }
+                    for (int j = 0; j < 8; ++j) { s2[j] = v[j] * v[j]; s3[j] = fast_sqrt(v[j] + 1e-8f); }
                   }
                   if (out_f32) {
                     store8(outf + off, v);
@@ -323,7 +370,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
               }
             }
           }
-          if (fuse_outc && valid) {
+          if (fuse_outc && valid) {   // C_out == 32: the unit holds all channels of its pixels
             logit += outc_b;
             const long o = (long)it.n * Ho * Wo + pix;
             if (out_logit) out_logit[o] = logit;
@@ -338,13 +385,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const float* const resf = reinterpret_cast<const float*>(p.res);
         const bool res_f32 = p.res_f32 != 0;
         const long res_img_stride = p.res_img_stride;
-        for (int b = bpar; b < it.mb_act; b += 2) {
+        const int units = it.mb_act * cpb;
+        for (int u = k4, b = 0, cc = k4; u < units; u += kEpiPerQuarter, cc += kEpiPerQuarter) {
+          while (cc >= cpb) { cc -= cpb; ++b; }
+          const int c0 = cc * 32;
           const int q = it.q0 + b * 128 + row;
-          const int oy = q / geo.PW, xl = q - oy * geo.PW;
+          const int oy = fastdiv_pw(q, p.m_PW), xl = q - oy * geo.PW;
           const int ox = it.band * geo.BW + xl;
           const bool valid = (oy < Ho) && (xl < geo.BW) && (ox < Wo);
           const long pix = (long)oy * Wo + ox;
-          for (int c0 = 0; c0 < NT; c0 += 32) {
+          {
             uint32_t r[32];
             tc_ld32(tmem_base + lane_base + (uint32_t)(acc * acc_cols + b * NT + c0), r);
             if (valid) {
@@ -378,11 +428,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const long cb2 = (long)H2 * W2 * 8;
         bf16* const out_img_n = out + (long)it.n * out_img_stride;
         float* const outf_img_n = outf + (long)it.n * out_img_stride;
-        for (int b = bpar; b < it.mb_act; b += 2) {
+        const int units = it.mb_act * cpb;
+        for (int u = k4, b = 0, cc = k4; u < units; u += kEpiPerQuarter, cc += kEpiPerQuarter) {
+          while (cc >= cpb) { cc -= cpb; ++b; }
+          const int c0 = cc * 32;
           const int q = it.q0 + b * 128 + row;
-          const int y = q / geo.PW, x = q - y * geo.PW;
+          const int y = fastdiv_pw(q, p.m_PW), x = q - y * geo.PW;
           const bool valid = y < Hi;
-          for (int c0 = 0; c0 < NT; c0 += 32) {
+          {
             uint32_t r[32];
             tc_ld32(tmem_base + lane_base + (uint32_t)(acc * acc_cols + b * NT + c0), r);
             if (valid) {
@@ -484,6 +537,7 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
   p.tiles_per_img = p.nbands * p.tiles_per_band;
   UNCL_REQUIRE(p.PW <= 128 && p.PH <= 256, "%s: halo tile too large (%d x %d)", what, p.PW, p.PH);
   p.num_items = N * p.tiles_per_img * p.NS;
+  p.m_PW = (1ull << 40) / (unsigned)p.PW + 1;
   p.a_box_bytes = 2 * p.PH * p.PW * 16;
   p.a_stage_bytes = (p.a_box_bytes + 127) & ~127;
   p.b_stage_bytes = p.ntaps * 2 * p.NT * 16;
@@ -512,6 +566,8 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
 
   if (p.ns_per_group <= 0) p.ns_per_group = p.NS;
   p.dbg = g_dbg;
+  p.probe_noload = getenv("UNCL_PROBE_NOLOAD") != nullptr ? 1 : 0;
+  if (const char* e = getenv("UNCL_PROBE_FLAGS")) p.probe_noload = atoi(e);
   auto kern = epi == 0 ? conv3x3_tc_kernel<0> : (epi == 1 ? conv3x3_tc_kernel<1> : conv3x3_tc_kernel<2>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));
@@ -560,7 +616,7 @@ extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w
   if (C_out == 256 && getenv("UNCL_PROBE_NT256") != nullptr) p.NT = 256;   // timing probe (weights packed by the caller)
   UNCL_REQUIRE(C_out % p.NT == 0 && C_out <= 1024, "conv3x3_tc: unsupported C_out=%d", C_out);
   UNCL_REQUIRE(out_dtype == UNCL_F32 || out_dtype == UNCL_BF16, "conv3x3_tc: bad out_dtype");
-  UNCL_REQUIRE(!fuse_outc || (C_out == p.NT && outc_w && outc_b && out_img), "conv3x3_tc: fuse_outc needs C_out<=128 and outc params");
+  UNCL_REQUIRE(!fuse_outc || (C_out == 32 && outc_w && outc_b && out_img), "conv3x3_tc: fuse_outc needs C_out == 32 and outc params");
   UNCL_REQUIRE(out != nullptr || fuse_outc, "conv3x3_tc: no output requested");
   UNCL_REQUIRE(act == UNCL_ACT_RELU || act == UNCL_ACT_NONE, "conv3x3_tc: only ReLU / identity epilogues are built");
   p.NS = C_out / p.NT;

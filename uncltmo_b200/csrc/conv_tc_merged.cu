@@ -46,9 +46,10 @@ struct MgParams {
   int MB, ADV;              // M blocks per tile, tile advance in positions (128 * MB - 2)
   int PW, PH, BW;
   int band_total, tiles_per_band, tiles_per_img, num_items;
-  int nchunk, stages, nacc, acc_cols;
+  int nchunk, ksteps, stages, nacc, acc_cols;   // ksteps: K = 16 steps (16 input channels each) per pipeline stage
   int a_box_bytes, a_stage_bytes, b_stage_bytes, stage_bytes;
   int act, emit_skip, fuse_outc;
+  int probe_noload;         // timing probe: the producer only loads the first `stages` chunks, then re-signals stale stages
   unsigned long long m_NS, m_tpi, m_tpb, m_PW;   // 2^40 / d + 1: exact x / d for x < 2^20, d < 2^12 ... (see fastdiv)
   unsigned long long* dbg;
 };
@@ -103,7 +104,7 @@ __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 
 // MMA issuer: 3 filter rows x MB blocks per K chunk, straight-line (MB is a compile-time constant), every block of
 // the tile is always issued (blocks past the end of a band read zero-filled / stale rows and are masked later).
-template <int MB>
+template <int MB, int kKSteps>
 __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_base, uint64_t* full, uint64_t* empty,
                                             uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base, int lane) {
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NP >> 3) << 17) | ((128u >> 4) << 24);
@@ -113,6 +114,7 @@ __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_ba
   const uint32_t stage0_16 = smem_u32(stage_base) >> 4, stage_16 = (uint32_t)p.stage_bytes >> 4;
   const uint32_t a_bytes_16 = (uint32_t)p.a_stage_bytes >> 4, b_row_16 = (uint32_t)(2 * p.NP);
   const uint32_t pw = (uint32_t)p.PW, np = (uint32_t)p.NP;
+  const uint32_t a_kstep_16 = (uint32_t)(2 * p.PH * p.PW);   // the next two channel blocks of the halo box
   const int nacc = p.nacc, acc_cols = p.acc_cols, nchunk = p.nchunk, stages = p.stages, num_items = p.num_items;
   int stage = 0, acc = 0;
   uint32_t phase = 0, acc_phase = 0;
@@ -128,22 +130,27 @@ __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_ba
     const uint32_t d0 = tmem_base + (uint32_t)(acc * acc_cols);
     for (int ch = 0; ch < nchunk; ++ch) {
       const long long tw1 = dbg ? clock64() : 0;
-      mbar_wait(&full[stage], phase);
+      if (!(p.probe_noload & 4)) mbar_wait(&full[stage], phase);
       if (dbg) w_full += clock64() - tw1;
       tc_fence_after();
       const uint32_t sa16 = stage0_16 + (uint32_t)stage * stage_16;
       const uint32_t a_row = a_lo_const | (sa16 + (uint32_t)it.moff0);
       const uint32_t b_lo = b_lo_const | (sa16 + a_bytes_16);
       if (elect_one()) {
+        // a stage holds kKSteps K=16 steps (32 input channels): kKSteps x 3 filter rows x MB blocks, straight-line
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
+        for (int kc = 0; kc < kKSteps; ++kc) {
 #pragma unroll
-          for (int b = 0; b < MB; ++b) {
-            tc_mma_bf16(d0 + (uint32_t)b * np, a_row + (uint32_t)ky * pw + (uint32_t)b * 128u, desc_hi,
-                        b_lo + (uint32_t)ky * b_row_16, desc_hi, idesc, ky > 0 ? 1u : (ch > 0 ? 1u : 0u));
+          for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int b = 0; b < MB; ++b) {
+              tc_mma_bf16(d0 + (uint32_t)b * np, a_row + (uint32_t)kc * a_kstep_16 + (uint32_t)ky * pw + (uint32_t)b * 128u,
+                          desc_hi, b_lo + (uint32_t)(kc * 3 + ky) * b_row_16, desc_hi, idesc,
+                          (kc > 0 || ky > 0) ? 1u : (ch > 0 ? 1u : 0u));
+            }
           }
         }
-        tc_commit(&empty[stage]);
+        if (!(p.probe_noload & 4)) tc_commit(&empty[stage]);
       }
       __syncwarp();
       if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -211,13 +218,17 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         const MgItem it = mg_decode(p, item);
         const uint8_t* wsrc = wbase + (size_t)it.ns * nchunk * b_bytes;
         for (int ch = 0; ch < nchunk; ++ch) {
+          if (p.probe_noload & 4) continue;
           const long long tw0 = dbg ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1);
           if (dbg) w_empty += clock64() - tw0;
           uint8_t* sa = stage_base + (size_t)stage * stage_bytes;
+          if ((p.probe_noload & 1) && (item != (int)blockIdx.x || ch >= stages)) { mbar_arrive(&full[stage]); }
+          else {
           mbar_expect_tx(&full[stage], tx_bytes);
-          tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, ch * 2, it.n);
+          tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, ch * 2 * p.ksteps, it.n);
           bulk_load(sa + a_stage_bytes, wsrc + (size_t)ch * b_bytes, b_bytes, &full[stage]);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -229,8 +240,11 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     __syncwarp();
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (p.MB == 1) mg_mma_role<1>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
-    else mg_mma_role<2>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
+    // N' = 96: two M blocks, 32 input channels per stage (halves the barrier round trips of the latency-bound issuing
+    // warp: 329 -> 302 us on up3.conv); N' = 192: one M block, 16 channels per stage (the 18 KB weight stage would
+    // leave only 3 pipeline stages otherwise: 101 -> 108 us on up1.conv)
+    if (p.MB == 1) mg_mma_role<1, 1>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
+    else mg_mma_role<2, 2>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
     __syncwarp();
   } else {
     // =============================== epilogue ===============================
@@ -283,6 +297,7 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);   // everything this warp needs is in registers: release the accumulator
+      if (p.probe_noload & 2) { par ^= 1; if (++acc == nacc) { acc = 0; acc_phase ^= 1; } continue; }
       float* const xpar = xbuf + par * (kUnits * 4 * kXSlot);
       // lanes 0 and 1 publish what the previous warp's lanes 30 / 31 need ...
       if (lane < 2) {
@@ -343,7 +358,7 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             float s2[8], s3[8];
             if (emit_skip) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { s2[j] = o[j] * o[j]; s3[j] = sqrtf(o[j] + 1e-8f); }
+              for (int j = 0; j < 8; ++j) { s2[j] = o[j] * o[j]; s3[j] = fast_sqrt(o[j] + 1e-8f); }
             }
             if (out_f32) {
               store8(outf + off, o);
@@ -410,13 +425,18 @@ int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void
   p.C_out = C_out; p.pad = pad;
   p.Ho = H + 2 * pad - 2; p.Wo = W + 2 * pad - 2;
   p.act = act; p.emit_skip = emit_skip; p.fuse_outc = fuse_outc;
-  p.nchunk = C_in / 16;
+  const int kKSteps = p.NT == 32 ? 2 : 1;   // must match the mg_mma_role instantiation chosen by MB
+  p.ksteps = kKSteps;
+  UNCL_REQUIRE(C_in % (16 * kKSteps) == 0, "%s: C_in must be a multiple of %d", what, 16 * kKSteps);
+  p.nchunk = C_in / (16 * kKSteps);
   // accumulator staging: two stages of 256 TMEM columns (epilogue of tile i overlaps the MMAs of tile i+1)
   p.nacc = 2;
   p.acc_cols = 256;
   p.MB = p.acc_cols / p.NP;   // 2 blocks of 96 columns or 1 block of 192: always two 32-channel work units per tile
   p.ADV = 128 * p.MB - 2;
-  const int nbands = ceil_div(p.Wo, 126);
+  int bw_max = 126;
+  if (const char* e = getenv("UNCL_MG_BW")) { const int want = atoi(e); if (want >= 8 && want < bw_max) bw_max = want; }
+  const int nbands = ceil_div(p.Wo, bw_max);
   p.BW = ceil_div(p.Wo, nbands);
   p.PW = p.BW + 2;
   p.band_total = p.Ho * p.PW;
@@ -429,9 +449,9 @@ int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void
   UNCL_REQUIRE(p.num_items < (1 << 24), "%s: too many tiles (%d)", what, p.num_items);
   p.m_NS = (1ull << 40) / (unsigned)p.NS + 1; p.m_tpi = (1ull << 40) / (unsigned)p.tiles_per_img + 1;
   p.m_tpb = (1ull << 40) / (unsigned)p.tiles_per_band + 1; p.m_PW = (1ull << 40) / (unsigned)p.PW + 1;
-  p.a_box_bytes = 2 * p.PH * p.PW * 16;
+  p.a_box_bytes = 2 * kKSteps * p.PH * p.PW * 16;
   p.a_stage_bytes = (p.a_box_bytes + 127) & ~127;
-  p.b_stage_bytes = 3 * 2 * p.NP * 16;
+  p.b_stage_bytes = kKSteps * 3 * 2 * p.NP * 16;
   p.stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   const int tail = 128 + 2 * kUnits * 4 * kXSlot * 4 + 2 * kUnits * 128 * 4 + (2 * kMaxStages + 4) * 8 + 16 + 2 * C_out * 4 + 256;
   const int budget = 227 * 1024 - tail;
@@ -443,9 +463,11 @@ int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM (each owns all 512 TMEM columns)
 
   CUtensorMap tmap;
-  CUresult r = encode_blocked_bf16(&tmap, in, W, H, C_in / 8, N, in_img_stride, p.PW, p.PH, 2);
+  CUresult r = encode_blocked_bf16(&tmap, in, W, H, C_in / 8, N, in_img_stride, p.PW, p.PH, 2 * kKSteps);
   if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
   p.dbg = dbg;
+  p.probe_noload = getenv("UNCL_PROBE_NOLOAD") != nullptr ? 1 : 0;   // bit 0: no loads, 1: no epilogue work, 2: MMA free-runs
+  if (const char* e = getenv("UNCL_PROBE_FLAGS")) p.probe_noload = atoi(e);
   cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_merged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));
   int dev = 0, sms = 148;
