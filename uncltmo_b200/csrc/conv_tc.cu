@@ -1,6 +1,8 @@
 // 3x3 stride-1 convolution (and ConvTranspose 3x3 s1 as its padded/flipped twin) as an implicit GEMM on the
 // Blackwell tensor cores: tcgen05.mma (kind::f16, bf16 operands, fp32 accumulators in TMEM), operands staged by
-// TMA / bulk async copies, persistent warp-specialised CTAs (one per SM) with a double-buffered TMEM accumulator.
+// TMA / bulk async copies, persistent warp-specialised CTAs (one per SM: 1 TMA producer warp, 1 MMA-issuing warp,
+// 16 epilogue warps) with a double-buffered TMEM accumulator.  Narrow layers with a long K loop (C_out <= 64,
+// C_in >= 64) are routed to the kx-merged variant in conv_tc_merged.cu.
 //
 // Reference operator: models/unet_multi_filters/unet_parts.py:57-87 (double_conv), :126-141, :183-193
 // (ConvTranspose2d 3x3 s1 p0 == conv over a 2-px zero-padded input with flipped kernels; the zero padding is TMA
@@ -428,7 +430,42 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const long cb2 = (long)H2 * W2 * 8;
         bf16* const out_img_n = out + (long)it.n * out_img_stride;
         float* const outf_img_n = outf + (long)it.n * out_img_stride;
-        const int units = it.mb_act * cpb;
+        // Paired mode (bf16, no replicate pad, both dx of a dy inside one N split, even W2): a thread takes the dx = 0 and
+        // dx = 1 columns of the same 32 channels, whose outputs are neighbouring pixels = 32 contiguous bytes per channel
+        // block -> one 256-bit store per lane, a warp writes 1 KB contiguous (the 16-byte stores at a 32-byte stride of
+        // the unpaired path half-fill every sector they touch).
+        const bool paired = !out_f32 && !padded && 2 * C <= NT && NT == 128 && (W2 & 1) == 0;
+        const int units = paired ? it.mb_act * 2 : it.mb_act * cpb;
+        if (paired) {
+          for (int u = k4; u < units; u += kEpiPerQuarter) {
+            const int b = u >> 1, pu = u & 1;
+            const int colA = C == 32 ? pu * 64 : pu * 32;   // dx = 0 columns; dx = 1 is C columns further
+            const int q = it.q0 + b * 128 + row;
+            const int y = fastdiv_pw(q, p.m_PW), x = q - y * geo.PW;
+            uint32_t ra[32], rb[32];
+            tc_ld32_nowait(tmem_base + lane_base + (uint32_t)(acc * acc_cols + b * NT + colA), ra);
+            tc_ld32(tmem_base + lane_base + (uint32_t)(acc * acc_cols + b * NT + colA + C), rb);
+            if (y < Hi) {
+              const int j0 = it.ns * NT + colA;
+              const int pos = j0 / C, co0 = j0 - pos * C;   // pos = 2 * dy
+              const int Y = 2 * y + (pos >> 1), X = 2 * x;
+              const float* bias = s_bias + co0;
+              bf16* o = out_img_n + (long)(co0 / 8) * cb2 + ((long)Y * W2 + X) * 8;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float b0 = bias[g * 8 + 2 * j], b1 = bias[g * 8 + 2 * j + 1];
+                  w[j] = pack_bf16x2(__uint_as_float(ra[g * 8 + 2 * j]) + b0, __uint_as_float(ra[g * 8 + 2 * j + 1]) + b1);
+                  w[4 + j] = pack_bf16x2(__uint_as_float(rb[g * 8 + 2 * j]) + b0, __uint_as_float(rb[g * 8 + 2 * j + 1]) + b1);
+                }
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + g * cb2), "r"(w[0]), "r"(w[1]),
+                             "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+              }
+            }
+          }
+        } else
         for (int u = k4, b = 0, cc = k4; u < units; u += kEpiPerQuarter, cc += kEpiPerQuarter) {
           while (cc >= cpb) { cc -= cpb; ++b; }
           const int c0 = cc * 32;
@@ -507,13 +544,14 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
   UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "%s: input must be 16-byte aligned", what);
   const int halo = p.ntaps == 9 ? 2 : 0;
   if (p.nchunk <= 0) p.nchunk = C_in / 16;
-  // Accumulator staging.  The tensor core keeps the B tile (weights of one tap / K chunk) stationary and streams the A
-  // rows through it; measured cost per tap = ~60-90 cycles to switch B + MB x (stream 128 rows).  More M blocks per
-  // tile amortise the switch, so K-heavy layers take all 512 TMEM columns for ONE accumulator stage (twice the M
-  // blocks; the exposed epilogue is < 3 % of such a tile), short-K layers keep two stages so that the epilogue of
-  // tile i overlaps the MMAs of tile i+1.  Measured per layer (profiles/README.md): the single stage pays off for
-  // N = 128 with K >= 512*9 (up0.conv: 167 -> 129 us); for narrower N the exposed epilogue and the coarser tiles cost
-  // more than the amortisation gains.
+  // Accumulator staging.  An SS-mode MMA costs max(N/2, (4096 + 32 N)/128) cycles whatever the previous one used
+  // (tools/mma_probe.cu); what the tile height buys is issue-side: the MMA-issuing warp is one serial, latency-bound
+  // instruction stream and every K chunk costs it a barrier round trip (wait full, fence, elect, commit: ~300+ cycles).
+  // More M blocks per tile put more MMAs behind each round trip, so K-heavy layers take all 512 TMEM columns for ONE
+  // accumulator stage (twice the M blocks; the exposed epilogue is < 3 % of such a tile), short-K layers keep two
+  // stages so that the epilogue of tile i overlaps the MMAs of tile i+1.  Measured per layer (profiles/README.md): the
+  // single stage pays off for N = 128 with K >= 512*9 (up0.conv: 167 -> 129 us); for narrower N the exposed epilogue
+  // and the coarser tiles cost more than the amortisation gains.
   p.nacc = (p.NT == 128 && C_in >= 512 && p.ntaps == 9 && getenv("UNCL_PROBE_DOUBLE_ACC") == nullptr) ? 1 : 2;
   p.acc_cols = p.nacc == 1 ? 512 : kAccCols;
   const int mb_max = p.acc_cols / p.NT;

@@ -8,6 +8,8 @@
 //     D[p][kx*C + co] = sum_{ky, ci} X[p + ky*PW][ci] * W[ky][kx][ci][co]        (3 MMAs per K chunk instead of 9)
 //     out[q][co]      = D[q][co] + D[q+1][C + co] + D[q+2][2C + co]              (epilogue)
 // N' = 96 costs 56 cycles for what took 3 x 40, N' = 192 runs at the math floor (96 cycles).
+// Used for C_out <= 64 with C_in >= 64 (uncl_conv3x3_tc decides): with only 32 input channels the K loop is too short
+// to hide this kernel's heavier epilogue (~7500 warp instructions per 256-position tile, ncu) and conv_tc.cu stays ahead.
 // The price is the epilogue's cross-row sum: accumulator rows are TMEM lanes, a warp only reaches its own 32 lanes, so
 // the kx = 1, 2 column groups come from the neighbouring lanes by warp shuffle and, for the last two lanes of a warp,
 // from the next warp through a small shared-memory exchange.  Tiles overlap by two positions so that no exchange
@@ -15,7 +17,8 @@
 //
 // Everything else follows conv_tc.cu: C8-blocked bf16 activations, one TMA halo box per K chunk whose shared-memory
 // image is the no-swizzle K-major operand, a filter ROW (ky) is a descriptor start-address shift of ky*PW pixels,
-// persistent warp-specialised CTAs, double-buffered TMEM accumulator.
+// persistent warp-specialised CTAs (1 TMA producer warp, 1 MMA-issuing warp, 16 epilogue warps), double-buffered TMEM
+// accumulator (2 x 256 columns: two M blocks of N' = 96 or one of N' = 192 per stage).
 // Reference operator: models/unet_multi_filters/unet_parts.py:57-87, :126-141, :183-193, :319-322, :338-345.
 // Weights: bf16 [NS][C_in/16][3 ky][2][3*NT (kx, n)][8], NT = min(C_out, 64) (packing.conv3x3_tc).
 #include <cstdlib>
@@ -79,18 +82,6 @@ __device__ __forceinline__ MgItem mg_decode(const MgParams& p, int item) {
   return it;
 }
 
-__device__ __forceinline__ void tc_ld32_nw(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
 __device__ __forceinline__ void tc_ld16_nw(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "

@@ -414,7 +414,8 @@ extern "C" int uncl_percentile_pair(const float* data, long n, float clamp_lo, f
   if (k1 > n - 2) k1 = n - 2;
   UNCL_REQUIRE(n < (1L << 32), "percentile_pair: n too large");
   const SelRanks ranks = {{(unsigned)k0, (unsigned)(k0 + 1), (unsigned)k1, (unsigned)(k1 + 1)}};
-  const int nb = grid_for(n, 512, 4);
+  // two CTAs per SM: every CTA clears and merges up to 4 x 2048 shared-memory bins, so few fat CTAs beat many thin ones
+  const int nb = grid_for(n, 512 * 16, 2);
   const double t0 = v0 - (double)k0, t1 = v1 - (double)k1;
   cudaMemsetAsync(w.ranks, 0, 16 + 4 * 2048 * 4, stream);   // arrival counter (w.ranks[0]) + histograms, contiguous
   select_pass_kernel<0><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist, w.ranks, ranks, t0, t1, pct_out);
