@@ -101,7 +101,10 @@ CONV_CASES = [(32, 32, 254, 0, 2), (32, 64, 126, 0, 1), (64, 64, 124, 0, 1), (64
               (128, 256, 28, 0, 2), (256, 256, 26, 0, 1), (256, 256, 12, 0, 3), (256, 256, 10, 2, 3),
               (1024, 128, 24, 2, 1), (128, 128, 26, 2, 1), (512, 64, 57, 2, 1), (64, 64, 59, 2, 2),
               (256, 32, 122, 2, 1), (32, 32, 124, 2, 2), (128, 32, 252, 2, 1), (32, 32, 254, 2, 1),
-              (16, 32, 3, 0, 1), (32, 32, 130, 0, 1), (32, 96, 40, 2, 1)]
+              (16, 32, 3, 0, 1), (32, 32, 130, 0, 1), (32, 96, 40, 2, 1),
+              # kx-merged kernel (C_out <= 64, C_in >= 64, C_in % 32 == 0): tiny, ragged and two-band extras; 80 -> one-tap
+              (64, 32, 3, 0, 1), (64, 64, 5, 2, 2), (96, 32, 40, 2, 1), (80, 32, 20, 0, 1), (128, 64, 130, 0, 1),
+              (64, 32, 129, 2, 1)]
 
 
 @pytest.mark.parametrize("ci,co,h,pad,n", CONV_CASES)
@@ -127,6 +130,35 @@ def test_tcgen05_conv_against_cuda_core_conv(ci, co, h, pad, n):
         assert (a - r).abs().max().item() <= 2.0 ** -7 * max(1.0, r.abs().max().item())
         assert rel(a, r) <= 2e-3
     assert torch.isnan(out[:, co // 8:2 * co // 8].float()).all()  # untouched slice stays untouched
+
+
+@pytest.mark.parametrize("ci,h,pad", [(64, 37, 0), (128, 20, 2)])
+def test_merged_conv_fused_out_conv_and_fp32_output(ci, h, pad):
+    """kx-merged kernel: fp32 feature-map output, and the fused 1x1 out conv + sigmoid (two 16-channel halves of a pixel
+    live in different warps) against the same feature map pushed through the out conv in torch."""
+    co, n = 32, 2
+    g = torch.Generator(device="cuda").manual_seed(ci + h)
+    x = torch.randn((n, ci // 8, h, h, 8), device="cuda", generator=g).to(torch.bfloat16)
+    w9 = (torch.randn((9, ci, co), device="cuda", generator=g) / (9 * ci) ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(co, device="cuda", generator=g) * 0.1
+    ow, ob = torch.randn(co, device="cuda", generator=g) * 0.3, torch.randn(1, device="cuda", generator=g)
+    ho = h + 2 * pad - 2
+    feat = torch.full((n, co // 8, ho, ho, 8), float("nan"), device="cuda", dtype=torch.float32)
+    ref = torch.empty_like(feat)
+    wp = packing.conv3x3_tc(w9)
+    assert wp.shape[2] == 3  # merged layout
+    _lib.call("uncl_conv3x3_simt", x.float(), x.stride(0), w9, b, ref, ref.stride(0), n, ci, h, h, co, pad, 1, 0, _lib.F32)
+    _lib.call("uncl_conv3x3_tc", x, x.stride(0), wp, b, feat, feat.stride(0), _lib.F32, n, ci, h, h, co, pad, 1, 0, 0,
+              None, None, None, None)
+    img = torch.full((n, ho, ho), float("nan"), device="cuda")
+    logit = torch.full((n, ho, ho), float("nan"), device="cuda")
+    _lib.call("uncl_conv3x3_tc", x, x.stride(0), wp, b, None, feat.stride(0), _lib.BF16, n, ci, h, h, co, pad, 1, 0, 1,
+              ow, ob, img, logit)
+    torch.cuda.synchronize()
+    assert not torch.isnan(feat).any() and rel(feat, ref) <= 1e-5
+    want = (feat.permute(0, 2, 3, 1, 4).reshape(n, ho, ho, co) * ow).sum(-1) + ob
+    assert not torch.isnan(logit).any() and (logit - want).abs().max().item() <= 1e-4 * max(1.0, want.abs().max().item())
+    assert (img - torch.sigmoid(want)).abs().max().item() <= 1e-5
 
 
 def test_video_generator_matches_oracle(golden):

@@ -103,6 +103,9 @@ def test_tc_weight_packing_layout_merged_kx():
         assert p.shape == (1, 4, 3, 2, 3 * co, 8) and p.dtype == torch.bfloat16
         ch, ky, half, kx, n, k = 2, 1, 1, 2, co - 3, 5
         assert p[0, ch, ky, half, kx * co + n, k].float() == w9[ky * 3 + kx, ch * 16 + half * 8 + k, n]
+    # the one-tap layout everywhere else: short K, K not a multiple of 32, wide outputs
+    for ci, co in ((32, 32), (80, 32), (64, 128)):
+        assert packing.conv3x3_tc(torch.zeros(9, ci, co)).shape == (1, ci // 16, 9, 2, min(co, 128), 8)
 
 
 def test_convT2x2_and_pointwise_packing():

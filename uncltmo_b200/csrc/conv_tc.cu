@@ -630,7 +630,7 @@ int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void
 // on the C_in = 32 layers, which are epilogue-bound either way.
 static bool use_merged(int C_in, int C_out) {
   const char* e = getenv("UNCL_MERGED_MIN_CI");
-  return C_out <= 64 && C_in >= (e ? atoi(e) : 64);
+  return C_out <= 64 && C_in % 32 == 0 && C_in >= (e ? atoi(e) : 64);
 }
 
 extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,

@@ -220,7 +220,7 @@ __device__ __forceinline__ void select_scan(SelState* st, const unsigned* hist, 
 // atomics; the last CTA to arrive scans the merged histogram for the 4 ranks, clears it for the next pass and, after the
 // third pass, interpolates the two percentiles (numpy 'linear').  `done` and `hist` must be zero on entry of pass 0.
 template <int PASS>
-__global__ void __launch_bounds__(512) select_pass_kernel(const float* __restrict__ data, long n, float clamp_lo,
+__global__ void __launch_bounds__(1024) select_pass_kernel(const float* __restrict__ data, long n, float clamp_lo,
                                                          float clamp_hi, SelState* st, unsigned* __restrict__ hist,
                                                          unsigned* done, const SelRanks ranks, double t0, double t1,
                                                          float* out) {
@@ -414,13 +414,14 @@ extern "C" int uncl_percentile_pair(const float* data, long n, float clamp_lo, f
   if (k1 > n - 2) k1 = n - 2;
   UNCL_REQUIRE(n < (1L << 32), "percentile_pair: n too large");
   const SelRanks ranks = {{(unsigned)k0, (unsigned)(k0 + 1), (unsigned)k1, (unsigned)(k1 + 1)}};
-  // two CTAs per SM: every CTA clears and merges up to 4 x 2048 shared-memory bins, so few fat CTAs beat many thin ones
-  const int nb = grid_for(n, 512 * 16, 2);
+  // one 1024-thread CTA per SM: every CTA merges up to 4 x 2048 shared-memory bins into the global histogram with
+  // atomics, and those (CTAs x non-empty bins per pass) - not the data stream - set the pass time
+  const int nb = grid_for(n, 1024 * 8, 1);
   const double t0 = v0 - (double)k0, t1 = v1 - (double)k1;
   cudaMemsetAsync(w.ranks, 0, 16 + 4 * 2048 * 4, stream);   // arrival counter (w.ranks[0]) + histograms, contiguous
-  select_pass_kernel<0><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist, w.ranks, ranks, t0, t1, pct_out);
-  select_pass_kernel<1><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist, w.ranks, ranks, t0, t1, pct_out);
-  select_pass_kernel<2><<<nb, 512, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist, w.ranks, ranks, t0, t1, pct_out);
+  select_pass_kernel<0><<<nb, 1024, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist, w.ranks, ranks, t0, t1, pct_out);
+  select_pass_kernel<1><<<nb, 1024, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist, w.ranks, ranks, t0, t1, pct_out);
+  select_pass_kernel<2><<<nb, 1024, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist, w.ranks, ranks, t0, t1, pct_out);
   return uncl_check_launch("percentile_pair");
 }
 

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) pw_conv_kernel(const float* __restrict__ 
 // KNN graph + max-relative aggregation (C = 256).  KNN_SPLIT CTAs per image, each owning a contiguous range of nodes.
 //   yn = y / max(|y|_2, 1e-12) over channels; dist[i][j] = (|yn_i|^2 - 2 yn_i.yn_j) + |yn_j|^2 + relpos[i][j];
 //   idx[i] = 9 smallest; z = interleave(y, max_k(y[idx_k] - y_i)) -> [N][2C/8][144][8]
-// Distances: a warp takes two rows i at a time; each lane keeps 5 columns j (lane + 32 t) x 2 rows in registers and
+// Distances: a warp takes six rows i at a time; each lane keeps 5 columns j (lane + 32 t) x 6 rows in registers and
 // streams the channel axis with 128-bit shared loads (row stride C+4 floats keeps them conflict-free).
 constexpr int KNN_SPLIT = 2;
 
@@ -118,9 +118,12 @@ __global__ void __launch_bounds__(512) gcn_knn_agg_kernel(const float* __restric
   const float* yn_g = y + (long)n * C * GN;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
-  for (int i = threadIdx.x; i < C * GN; i += blockDim.x) {
-    const int j = i & 7, node = (i >> 3) % GN, cb = i / (8 * GN);
-    s_yn[node * LD + cb * 8 + j] = yn_g[i];
+  {
+    const float4* y4 = reinterpret_cast<const float4*>(yn_g);   // 128-bit loads: half a pixel block each
+    for (int i = threadIdx.x; i < C * GN / 4; i += blockDim.x) {
+      const int half = i & 1, node = (i >> 1) % GN, cb = i / (2 * GN);
+      *reinterpret_cast<float4*>(&s_yn[node * LD + cb * 8 + half * 4]) = __ldg(y4 + i);
+    }
   }
   __syncthreads();
   for (int node = wid; node < GN; node += nw) {
@@ -138,33 +141,38 @@ __global__ void __launch_bounds__(512) gcn_knn_agg_kernel(const float* __restric
     if (lane == 0) s_sq[node] = s2;
   }
   __syncthreads();
-  for (int ip = wid; ip < ROWS / 2; ip += nw) {
-    const int i0 = i_begin + 2 * ip;
-    float dot[2][5];
+  // KR rows per warp: the B rows (5 x 128-bit loads per lane and K step) are what saturates shared memory, so every
+  // extra row held in registers divides that traffic; 72 rows / 6 = 12 warps take one group each
+  constexpr int KR = 6;
+  static_assert(ROWS % KR == 0, "row groups");
+  for (int ip = wid; ip < ROWS / KR; ip += nw) {
+    const int i0 = i_begin + KR * ip;
+    float dot[KR][5];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int r = 0; r < KR; ++r)
 #pragma unroll
       for (int t = 0; t < 5; ++t) dot[r][t] = 0.f;
     const float* yi0 = s_yn + i0 * LD;
-    const float* yi1 = yi0 + LD;
     const float* yj[5];
 #pragma unroll
     for (int t = 0; t < 5; ++t) yj[t] = s_yn + min(lane + 32 * t, GN - 1) * LD;
 #pragma unroll 2
     for (int c = 0; c < C; c += 4) {
-      const float4 a0 = *reinterpret_cast<const float4*>(yi0 + c);
-      const float4 a1 = *reinterpret_cast<const float4*>(yi1 + c);
+      float4 a[KR];
+#pragma unroll
+      for (int r = 0; r < KR; ++r) a[r] = *reinterpret_cast<const float4*>(yi0 + r * LD + c);
 #pragma unroll
       for (int t = 0; t < 5; ++t) {
         const float4 b = *reinterpret_cast<const float4*>(yj[t] + c);
-        dot[0][t] = fmaf(a0.x, b.x, dot[0][t]); dot[0][t] = fmaf(a0.y, b.y, dot[0][t]);
-        dot[0][t] = fmaf(a0.z, b.z, dot[0][t]); dot[0][t] = fmaf(a0.w, b.w, dot[0][t]);
-        dot[1][t] = fmaf(a1.x, b.x, dot[1][t]); dot[1][t] = fmaf(a1.y, b.y, dot[1][t]);
-        dot[1][t] = fmaf(a1.z, b.z, dot[1][t]); dot[1][t] = fmaf(a1.w, b.w, dot[1][t]);
+#pragma unroll
+        for (int r = 0; r < KR; ++r) {
+          dot[r][t] = fmaf(a[r].x, b.x, dot[r][t]); dot[r][t] = fmaf(a[r].y, b.y, dot[r][t]);
+          dot[r][t] = fmaf(a[r].z, b.z, dot[r][t]); dot[r][t] = fmaf(a[r].w, b.w, dot[r][t]);
+        }
       }
     }
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
+    for (int r = 0; r < KR; ++r) {
       const int i = i0 + r;
       float d[5];
 #pragma unroll
@@ -239,7 +247,7 @@ extern "C" int uncl_pw_conv(const float* in, const float* w, const float* bias, 
                "pw_conv: unsupported C_in=%d C_out=%d groups=%d", C_in, C_out, groups);
   // 128-wide channel tiles when that still fills the machine, else 64-wide (twice the CTAs)
   const int px_tiles = ceil_div(N * HW, PW_PX);
-  const bool wide = (C_out / groups) % 128 == 0 && px_tiles * (C_out / 128) >= 120;
+  const bool wide = (C_out / groups) % 128 == 0 && px_tiles * (C_out / 128) >= 120;   // (64-wide tiles measured slower: 72 -> 77 us on fc1)
   if (wide) {
     dim3 grid(px_tiles, C_out / 128);
     UNCL_DISPATCH_DTYPE(out_dtype, T, (pw_conv_kernel<T, 128><<<grid, 256, 0, stream>>>(in, w, bias, res, scale, (T*)out, out_img_stride, C_in, C_out, groups, HW, N, act)));

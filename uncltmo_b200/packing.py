@@ -25,11 +25,11 @@ MERGED_MIN_CI = int(os.environ.get("UNCL_MERGED_MIN_CI", "64"))   # must match c
 def conv3x3_tc(w9):
     """[9][C_in][C_out] fp32 -> the tensor-core B operand of uncl_conv3x3_tc (bf16, K-major core matrices of 8 x 16 B).
 
-    C_out <= 64 and C_in >= 64 (conv_tc_merged.cu, the three kx taps of a filter row merged into N):
+    C_out <= 64, C_in >= 64 and C_in % 32 == 0 (conv_tc_merged.cu, the three kx taps of a filter row merged into N):
         [NS][C_in/16][3 ky][2][3*NT (kx, n)][8], NT = min(C_out, 64)
     wider layers (conv_tc.cu, one tap per MMA): [NS][C_in/16][9][2][NT][8], NT = min(C_out, 128)."""
     _, ci, co = w9.shape
-    if co <= 64 and ci >= MERGED_MIN_CI:
+    if co <= 64 and ci % 32 == 0 and ci >= MERGED_MIN_CI:
         nt = min(co, 64)
         ns = co // nt
         t = w9.reshape(3, 3, ci // 16, 2, 8, ns, nt)       # ky, kx, chunk, half, k8, ns, n
