@@ -186,8 +186,8 @@ def train_workload(dev, precision, steps, warmup, world=1, rank=0, video=False):
     netG.load_state_dict(make_generator_state_dict())
     netD = SimpleDiscriminator(256, 1, 16, "none", "none", 0, 0).to(dev).train()
     netD.load_state_dict(make_discriminator_state_dict())
-    optG = torch.optim.Adam([p for p in netG.parameters() if p.requires_grad], lr=1e-5, betas=(0.5, 0.999), capturable=True)
-    optD = torch.optim.Adam(netD.parameters(), lr=1.5e-5, betas=(0.5, 0.999), capturable=True)
+    optG = torch.optim.Adam([p for p in netG.parameters() if p.requires_grad], lr=1e-5, betas=(0.5, 0.999), capturable=True, fused=True)
+    optD = torch.optim.Adam(netD.parameters(), lr=1.5e-5, betas=(0.5, 0.999), capturable=True, fused=True)
     tr = GanTrainerStep(netG, netD, optG, optD)
     b_local = max(1, 8 // world)
     mk = lambda a: torch.from_numpy(a).reshape(b_local, 2, 1, 256, 256)  # noqa: E731
@@ -257,7 +257,7 @@ def train_workload(dev, precision, steps, warmup, world=1, rank=0, video=False):
             "tflops_algorithmic": steps * TRAIN_GFLOP_STEP / ms, "gpu_launches": launches,
             "e2e": {"value": steps / (ms_e2e / 1e3), "unit": "steps/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 8},
             "config": {"global_batch": "8 x 2 crops = 16 images of 256x256", "per_gpu_images": 2 * b_local, "loss_schedule": "epoch 0",
-                       "optimizer": "Adam(lr 1e-5 / 1.5e-5, betas (0.5, 0.999))", "parallelism": "dp%d, NCCL gradient all-reduce" % world}}
+                       "optimizer": "torch.optim.Adam(lr 1e-5 / 1.5e-5, betas (0.5, 0.999), fused=True, capturable=True)", "parallelism": "dp%d, NCCL gradient all-reduce" % world}}
 
 
 def cpu_train_arm(threads=None):

@@ -6,6 +6,7 @@
 // Reference: utils/model_save_util.py:219-240, 242-263 (log-lambda normalise), :409-486, 488-565 (tiling + blend),
 // :389-402, 589-606 (post-process); utils/hdr_image_util.py:76-82 (to_gray), :122-132 (back_to_color_tensor),
 // :93-102, 237-245 (8-bit stretch); utils/data_loader_util.py:135-157, 175-179 (replicate pad).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -301,6 +302,166 @@ __global__ void __launch_bounds__(1024) select_pass_kernel(const float* __restri
   }
 }
 
+
+// ---- fused select: the three radix passes in ONE cooperative kernel, keys resident in shared memory ----------
+// One CTA per SM owns a contiguous slice of the data and keeps its order keys in shared memory (<= 46 K keys per CTA:
+// planes up to ~6.8 M values, i.e. both percentile calls of a 1080p frame); passes 1 and 2 then never touch global
+// memory again, and the passes are separated by a grid barrier instead of a kernel boundary plus a last-CTA tail.
+// Every CTA scans the merged histogram itself (identical result everywhere), so one barrier per pass is enough; the
+// three passes use three separate, pre-zeroed global histograms.  Same digits, ranks and interpolation as
+// select_pass_kernel: the results are bit-identical.
+constexpr int kFusedThreads = 1024;
+constexpr int kFusedMaxKeys = 46 * 1024;
+
+__device__ __forceinline__ void select_grid_barrier(unsigned* ctr, unsigned target) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(ctr, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// scan of one pass on shared-memory state (s_pre / s_rank are this CTA's copies of SelState), by the whole CTA:
+// 256 threads per query, 8 (pass 2: 4) consecutive bins per thread, warp scan + 8 warp totals.  Same owner rule as
+// select_scan: the first position whose inclusive count exceeds the rank, the last bin if the counts fall short.
+template <int PASS>
+__device__ __forceinline__ void select_scan_block(unsigned* s_pre, unsigned* s_rank, const unsigned* hist,
+                                                  const SelRanks& ranks_in, unsigned* s_wtot /* [4][8] */) {
+  constexpr int BITS = PASS == 2 ? 10 : 11;
+  constexpr int PER = (1 << BITS) / 256;
+  const int q = threadIdx.x >> 8, t = threadIdx.x & 255, lane = threadIdx.x & 31, w = t >> 5;
+  const unsigned rank = PASS == 0 ? ranks_in.r[q] : s_rank[q];
+  const unsigned pre = PASS == 0 ? 0u : s_pre[q];
+  int slot = 0;
+  if (PASS != 0) {
+    slot = q;
+    for (int q2 = q - 1; q2 >= 0; --q2)
+      if (s_pre[q2] == pre) slot = q2;
+  }
+  const unsigned* h = hist + ((size_t)slot << BITS) + t * PER;
+  unsigned c[PER], mine = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { c[i] = h[i]; mine += c[i]; }
+  unsigned incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_wtot[q * 8 + w] = incl;
+  __syncthreads();   // also: every thread has read the old prefixes / ranks before anyone overwrites them
+  unsigned base = 0;
+  for (int i = 0; i < w; ++i) base += s_wtot[q * 8 + i];
+  incl += base;
+  const unsigned excl = incl - mine;
+  // owner: rank in [excl, incl), or the very last thread of the query when the counts fall short
+  const bool owner = (rank >= excl && rank < incl) || (t == 255 && rank >= incl);
+  if (owner) {
+    unsigned cum = excl;
+    int b = 0;
+#pragma unroll
+    for (; b < PER - 1; ++b) {
+      if (rank < cum + c[b]) break;
+      cum += c[b];
+    }
+    s_rank[q] = rank - cum;
+    s_pre[q] = (pre << BITS) | (unsigned)(t * PER + b);
+  }
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+select_fused_kernel(const float* __restrict__ data, long n, long per_cta, float clamp_lo, float clamp_hi,
+                    unsigned* __restrict__ hist3, unsigned* barrier, const SelRanks ranks, double t0, double t1,
+                    float* out) {
+  extern __shared__ __align__(16) unsigned s_dyn[];
+  unsigned* s_hist = s_dyn;                       // [4][2048]
+  unsigned* s_keys = s_dyn + (kSelQ << 11);       // [per_cta]
+  __shared__ unsigned s_pre[kSelQ], s_rank[kSelQ], s_wtot[kSelQ * 8];
+  const long begin = (long)blockIdx.x * per_cta;
+  const int cnt = (int)max(0L, min(per_cta, n - begin));
+  for (int i = threadIdx.x; i < (kSelQ << 11); i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  // ---- load + pass 0 (top 11 bits)
+  {
+    auto visit0 = [&](float raw, int idx) {
+      const unsigned k = order_key(fminf(fmaxf(raw, clamp_lo), clamp_hi));
+      s_keys[idx] = k;
+      const unsigned bin = k >> 21;
+      const unsigned peers = __match_any_sync(__activemask(), bin);
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (unsigned)__popc(peers));
+    };
+    const float* d = data + begin;   // begin is a multiple of 4 and data is 16-byte aligned (checked by the host)
+    const int c4 = cnt >> 2;
+    const float4* d4 = reinterpret_cast<const float4*>(d);
+    int i = threadIdx.x;
+    for (; i + kFusedThreads < c4; i += 2 * kFusedThreads) {
+      const float4 a = __ldg(d4 + i), b = __ldg(d4 + i + kFusedThreads);
+      visit0(a.x, 4 * i); visit0(a.y, 4 * i + 1); visit0(a.z, 4 * i + 2); visit0(a.w, 4 * i + 3);
+      const int j = i + kFusedThreads;
+      visit0(b.x, 4 * j); visit0(b.y, 4 * j + 1); visit0(b.z, 4 * j + 2); visit0(b.w, 4 * j + 3);
+    }
+    if (i < c4) {
+      const float4 a = __ldg(d4 + i);
+      visit0(a.x, 4 * i); visit0(a.y, 4 * i + 1); visit0(a.z, 4 * i + 2); visit0(a.w, 4 * i + 3);
+    }
+    for (int t = (c4 << 2) + threadIdx.x; t < cnt; t += kFusedThreads) visit0(__ldg(d + t), t);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist3[i], s_hist[i]);
+  select_grid_barrier(barrier, gridDim.x);
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = __ldcg(hist3 + i);
+  __syncthreads();
+  select_scan_block<0>(s_pre, s_rank, s_hist, ranks, s_wtot);
+  __syncthreads();
+  // ---- passes 1 (next 11 bits) and 2 (last 10 bits) from the shared-memory keys
+#pragma unroll
+  for (int pass = 1; pass <= 2; ++pass) {
+    const int BITS = pass == 2 ? 10 : 11, SHIFT = pass == 1 ? 10 : 0;
+    unsigned pre[kSelQ];
+    bool first[kSelQ];
+#pragma unroll
+    for (int q = 0; q < kSelQ; ++q) {
+      pre[q] = s_pre[q];
+      first[q] = true;
+#pragma unroll
+      for (int q2 = 0; q2 < q; ++q2) first[q] = first[q] && (s_pre[q2] != pre[q]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (kSelQ << 11); i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const unsigned k = s_keys[i];
+      const unsigned hi = k >> (SHIFT + BITS), bin = (k >> SHIFT) & ((1u << BITS) - 1);
+#pragma unroll
+      for (int q = 0; q < kSelQ; ++q)
+        if (first[q] && hi == pre[q]) atomicAdd(&s_hist[(q << BITS) + bin], 1u);
+    }
+    __syncthreads();
+    unsigned* gh = hist3 + pass * (kSelQ << 11);
+    for (int i = threadIdx.x; i < (kSelQ << BITS); i += blockDim.x)
+      if (s_hist[i]) atomicAdd(&gh[i], s_hist[i]);
+    select_grid_barrier(barrier, gridDim.x * (unsigned)(pass + 1));
+    for (int i = threadIdx.x; i < (kSelQ << BITS); i += blockDim.x) s_hist[i] = __ldcg(gh + i);
+    __syncthreads();
+    if (pass == 1) select_scan_block<1>(s_pre, s_rank, s_hist, ranks, s_wtot);
+    else select_scan_block<2>(s_pre, s_rank, s_hist, ranks, s_wtot);
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double a0 = key_value(s_pre[0]), b0 = key_value(s_pre[1]);
+    const double a1 = key_value(s_pre[2]), b1 = key_value(s_pre[3]);
+    out[0] = (float)(t0 < 0.5 ? a0 + (b0 - a0) * t0 : b0 - (b0 - a0) * (1.0 - t0));
+    out[1] = (float)(t1 < 0.5 ? a1 + (b1 - a1) * t1 : b1 - (b1 - a1) * (1.0 - t1));
+  }
+}
+
 // ---- post-process: clamp to percentiles, stretch, back to colour, crop --------------------------------------
 __global__ void __launch_bounds__(256) frame_postprocess_kernel(const float* __restrict__ fake, int W1, int padT,
                                                                int padL, const float* __restrict__ rgb, int H, int W,
@@ -350,12 +511,13 @@ inline int grid_for(long total, int block, int per_sm) {
 constexpr int kStatBlocks = 148 * 8;
 
 extern "C" long uncl_frame_workspace_bytes() {
-  // partials [kStatBlocks][3] floats | stats[4] | pct[4] | SelState | ranks[4] | hist [4][2048]
-  return (long)kStatBlocks * 3 * 4 + 16 + 16 + (long)sizeof(SelState) + 16 + 4L * 2048 * 4 + 256;
+  // partials [kStatBlocks][3] floats | stats[4] | pct[4] | SelState | ranks[4] | hist [4][2048] | fused: barrier[4] + hist [3][4][2048]
+  return (long)kStatBlocks * 3 * 4 + 16 + 16 + (long)sizeof(SelState) + 16 + 4L * 2048 * 4 + 16 + 3L * 4 * 2048 * 4 + 256;
 }
 
 struct FrameWs {
   float* partials; float* stats; float* pct; SelState* sel; unsigned* ranks; unsigned* hist;
+  unsigned* fused_barrier; unsigned* fused_hist;
 };
 static FrameWs carve(void* ws) {
   FrameWs w;
@@ -365,7 +527,9 @@ static FrameWs carve(void* ws) {
   w.pct = reinterpret_cast<float*>(p); p += 16;
   w.sel = reinterpret_cast<SelState*>(p); p += sizeof(SelState);
   w.ranks = reinterpret_cast<unsigned*>(p); p += 16;
-  w.hist = reinterpret_cast<unsigned*>(p);
+  w.hist = reinterpret_cast<unsigned*>(p); p += 4 * 2048 * 4;
+  w.fused_barrier = reinterpret_cast<unsigned*>(p); p += 16;
+  w.fused_hist = reinterpret_cast<unsigned*>(p);
   return w;
 }
 
@@ -414,10 +578,31 @@ extern "C" int uncl_percentile_pair(const float* data, long n, float clamp_lo, f
   if (k1 > n - 2) k1 = n - 2;
   UNCL_REQUIRE(n < (1L << 32), "percentile_pair: n too large");
   const SelRanks ranks = {{(unsigned)k0, (unsigned)(k0 + 1), (unsigned)k1, (unsigned)(k1 + 1)}};
-  // one 1024-thread CTA per SM: every CTA merges up to 4 x 2048 shared-memory bins into the global histogram with
-  // atomics, and those (CTAs x non-empty bins per pass) - not the data stream - set the pass time
-  const int nb = grid_for(n, 1024 * 8, 1);
   const double t0 = v0 - (double)k0, t1 = v1 - (double)k1;
+  // fused path: one cooperative launch when every CTA's slice of keys fits in its shared memory
+  {
+    int dev = 0, sms = 148, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    long per_cta = ((n + sms - 1) / sms + 3) & ~3L;
+    if (coop && per_cta <= kFusedMaxKeys && (reinterpret_cast<uintptr_t>(data) & 15) == 0 && getenv("UNCL_SELECT_3PASS") == nullptr) {
+      const size_t smem = (size_t)((kSelQ << 11) + per_cta) * sizeof(unsigned);
+      cudaError_t e = cudaFuncSetAttribute(select_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "percentile_pair: smem attr: %s", cudaGetErrorString(e));
+      cudaMemsetAsync(w.fused_barrier, 0, 16 + 3 * 4 * 2048 * 4, stream);
+      unsigned* hist3 = w.fused_hist;
+      unsigned* bar = w.fused_barrier;
+      void* args[] = {(void*)&data, (void*)&n, (void*)&per_cta, (void*)&clamp_lo, (void*)&clamp_hi, (void*)&hist3, (void*)&bar,
+                      (void*)&ranks, (void*)&t0, (void*)&t1, (void*)&pct_out};
+      e = cudaLaunchCooperativeKernel((const void*)select_fused_kernel, dim3(sms), dim3(kFusedThreads), args, smem, stream);
+      if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "percentile_pair: cooperative launch: %s", cudaGetErrorString(e));
+      return uncl_check_launch("percentile_pair");
+    }
+  }
+  // three-pass path (large planes).  One 1024-thread CTA per SM: every CTA merges up to 4 x 2048 shared-memory bins
+  // into the global histogram with atomics
+  const int nb = grid_for(n, 1024 * 8, 1);
   cudaMemsetAsync(w.ranks, 0, 16 + 4 * 2048 * 4, stream);   // arrival counter (w.ranks[0]) + histograms, contiguous
   select_pass_kernel<0><<<nb, 1024, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist, w.ranks, ranks, t0, t1, pct_out);
   select_pass_kernel<1><<<nb, 1024, 0, stream>>>(data, n, clamp_lo, clamp_hi, w.sel, w.hist, w.ranks, ranks, t0, t1, pct_out);
