@@ -52,6 +52,7 @@ struct TcParams {
   int band_total;           // Ho * PW: flattened (pitch PW) output positions of one band
   int tiles_per_band, tiles_per_img, num_items;
   int nchunk, ntaps, stages;
+  int ksteps;               // K = 16 steps per pipeline stage (pointwise GEMMs: up to 4 = 64 input channels per barrier round trip)
   int nacc, acc_cols;       // accumulator stages (2 x 256 columns, or 1 x 512 for K-heavy layers: see launch_tc)
   int a_box_bytes, a_stage_bytes, b_stage_bytes, stage_bytes;
   int act, emit_skip, fuse_outc;
@@ -178,7 +179,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const Item it = decode_item(geo, item);
         const uint8_t* wsrc = wbase + (size_t)it.ns * nchunk * b_bytes;
-        const int kblk0 = (it.ns / ns_per_group) * nchunk * 2;   // first input channel block of this split's group
+        const int kblk0 = (it.ns / ns_per_group) * nchunk * 2 * p.ksteps;   // first input channel block of this split's group
         for (int ch = 0; ch < nchunk; ++ch) {
           if (p.probe_noload & 4) continue;
           const long long tw0 = dbg ? clock64() : 0;
@@ -188,7 +189,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           if ((p.probe_noload & 1) && (item != (int)blockIdx.x || ch >= stages)) { mbar_arrive(&full[stage]); }
           else {
           mbar_expect_tx(&full[stage], tx_bytes);
-          tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, kblk0 + ch * 2, it.n);
+          tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, kblk0 + ch * 2 * p.ksteps, it.n);
           bulk_load(sa + a_stage_bytes, wsrc + (size_t)ch * b_bytes, b_bytes, &full[stage]);
           }
           if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -271,12 +272,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             }
             __syncwarp();
           } else {
-            uint32_t a_lo = a_row, d = d0;
+            // pointwise GEMM: a stage holds `ksteps` K = 16 steps (their A halves / B tiles follow each other in the stage)
             if (elect_one()) {
-              for (uint32_t b = 0; b < mb; ++b) {
-                tc_mma_bf16(d, a_lo, desc_hi, b_lo, desc_hi, idesc, ch > 0 ? 1u : 0u);
-                a_lo += mstep;
-                d += nt;
+              const uint32_t a_kstep_16 = (uint32_t)(2 * p.PH * p.PW), ksteps = (uint32_t)p.ksteps;
+              for (uint32_t kc = 0; kc < ksteps; ++kc) {
+                uint32_t a_lo = a_row + kc * a_kstep_16, d = d0;
+                const uint32_t accum = (ch > 0 || kc > 0) ? 1u : 0u;
+                for (uint32_t b = 0; b < mb; ++b) {
+                  tc_mma_bf16(d, a_lo, desc_hi, b_lo + kc * b_tap_16, desc_hi, idesc, accum);
+                  a_lo += mstep;
+                  d += nt;
+                }
               }
             }
             __syncwarp();
@@ -544,6 +550,7 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
   UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "%s: input must be 16-byte aligned", what);
   const int halo = p.ntaps == 9 ? 2 : 0;
   if (p.nchunk <= 0) p.nchunk = C_in / 16;
+  p.ksteps = 1;
   // Accumulator staging.  An SS-mode MMA costs max(N/2, (4096 + 32 N)/128) cycles whatever the previous one used
   // (tools/mma_probe.cu); what the tile height buys is issue-side: the MMA-issuing warp is one serial, latency-bound
   // instruction stream and every K chunk costs it a barrier round trip (wait full, fence, elect, commit: ~300+ cycles).
@@ -576,12 +583,21 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
   UNCL_REQUIRE(p.PW <= 128 && p.PH <= 256, "%s: halo tile too large (%d x %d)", what, p.PW, p.PH);
   p.num_items = N * p.tiles_per_img * p.NS;
   p.m_PW = (1ull << 40) / (unsigned)p.PW + 1;
-  p.a_box_bytes = 2 * p.PH * p.PW * 16;
-  p.a_stage_bytes = (p.a_box_bytes + 127) & ~127;
-  p.b_stage_bytes = p.ntaps * 2 * p.NT * 16;
-  p.stage_bytes = p.a_stage_bytes + p.b_stage_bytes;  // both multiples of 128
   const int tail = 128 + (2 * kMaxStages + 4) * 8 + 16 + bias_floats * 4 + 256;
   const int budget = 227 * 1024 - tail;
+  // pointwise GEMMs are short, latency-bound launches: fewer, fatter pipeline stages (up to 64 input channels) cut the
+  // issuing warp's barrier round trips - as long as four stages still fit
+  if (p.ntaps == 1 && getenv("UNCL_PROBE_PW_KSTEPS1") == nullptr) {
+    for (int ks = 4; ks > 1; ks >>= 1) {
+      const int sb = ((2 * ks * p.PH * p.PW * 16 + 127) & ~127) + ks * 2 * p.NT * 16;
+      if (p.nchunk % ks == 0 && 4 * sb <= budget) { p.ksteps = ks; break; }
+    }
+    p.nchunk /= p.ksteps;
+  }
+  p.a_box_bytes = 2 * p.ksteps * p.PH * p.PW * 16;
+  p.a_stage_bytes = (p.a_box_bytes + 127) & ~127;
+  p.b_stage_bytes = p.ksteps * p.ntaps * 2 * p.NT * 16;
+  p.stage_bytes = p.a_stage_bytes + p.b_stage_bytes;  // both multiples of 128
   p.stages = budget / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   UNCL_REQUIRE(p.stages >= 2, "%s: tile does not fit shared memory (%d B per stage)", what, p.stage_bytes);
@@ -595,7 +611,7 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
   // so a box row is PW*16 contiguous bytes in global memory (full 32-byte sectors) and lands pixel-major in smem.
   const cuuint64_t gdim[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)(C_in / 8), (cuuint64_t)N};
   const cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)in_img_stride * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)p.PW * 2, (cuuint32_t)p.PH, 2, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)p.PW * 2, (cuuint32_t)p.PH, (cuuint32_t)(2 * p.ksteps), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(in), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
