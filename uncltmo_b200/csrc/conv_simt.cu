@@ -232,15 +232,17 @@ template <typename T>
 __global__ void __launch_bounds__(256) maxpool2_kernel(const T* __restrict__ in, long in_img_stride,
                                                       const T* __restrict__ prev, long prev_img_stride, int r,
                                                       T* __restrict__ out, long out_img_stride, int C, int H, int W,
-                                                      int N) {
-  // one CTA per output row (n, channel block, y): the index arithmetic is per CTA, threads stride over x
+                                                      int total_rows, int tpr, int rows_per_cta) {
+  // a CTA covers `rows_per_cta` output rows (n, channel block, y) with `tpr` threads each (tpr = 16..128, a power of two
+  // >= Wo where possible): narrow deep layers get full 128-thread CTAs instead of 12-of-32-lane ones
   const int Ho = H / 2, Wo = W / 2, Cb = C / 8;
-  const int row = blockIdx.x;
+  const int row = blockIdx.x * rows_per_cta + (int)(threadIdx.x / tpr);
+  if (row >= total_rows) return;
   const int y = row % Ho, cb = (row / Ho) % Cb, n = row / (Ho * Cb);
   const T* in_row = in + (long)n * in_img_stride + ((long)cb * H + 2 * y) * W * 8;
   const T* pv_row = (prev != nullptr && cb * 8 < r) ? prev + (long)n * prev_img_stride + ((long)cb * H + 2 * y) * W * 8 : nullptr;
   T* out_row = out + (long)n * out_img_stride + ((long)cb * Ho + y) * Wo * 8;
-  for (int x = threadIdx.x; x < Wo; x += blockDim.x) {
+  for (int x = threadIdx.x % tpr; x < Wo; x += tpr) {
     float m[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
@@ -388,8 +390,11 @@ extern "C" int uncl_maxpool2(const void* in, long in_img_stride, const void* pre
   UNCL_REQUIRE(C % 8 == 0 && H >= 2 && W >= 2 && N > 0, "maxpool2: bad shape");
   const long rows = (long)N * (C / 8) * (H / 2);
   UNCL_REQUIRE(rows < (1L << 31), "maxpool2: too many rows");
-  const int threads = (W / 2) <= 32 ? 32 : ((W / 2) <= 64 ? 64 : 128);
-  UNCL_DISPATCH_DTYPE(dtype, T, (maxpool2_kernel<T><<<(unsigned)rows, threads, 0, stream>>>((const T*)in, in_img_stride, (const T*)prev, prev_img_stride, r, (T*)out, out_img_stride, C, H, W, N)));
+  const int wo = W / 2;
+  const int tpr = wo <= 16 ? 16 : (wo <= 32 ? 32 : (wo <= 64 ? 64 : 128));
+  const int rows_per_cta = 128 / tpr;
+  const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
+  UNCL_DISPATCH_DTYPE(dtype, T, (maxpool2_kernel<T><<<grid, 128, 0, stream>>>((const T*)in, in_img_stride, (const T*)prev, prev_img_stride, r, (T*)out, out_img_stride, C, H, W, (int)rows, tpr, rows_per_cta)));
   return uncl_check_launch("maxpool2");
 }
 
