@@ -58,6 +58,13 @@ int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w_packed, co
                     int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b, float* out_img,
                     float* out_logit, uncl_stream_t stream);
 
+/* Tile plan uncl_conv3x3_tc would use for a problem: pure host arithmetic, callable without a GPU (tests check the tile
+ * coverage and that uncltmo_b200/packing.py packs the weights for the kernel the library will pick).
+ * plan[16] = { kind (0: one tap per MMA, conv_tc.cu; 1: kx-merged, conv_tc_merged.cu), NT, NS, MMA N, M blocks per tile,
+ *   tile advance in positions, PW, PH, BW, column bands, tiles per band, work items, pipeline stages, accumulator stages,
+ *   K=16 steps per stage, dynamic shared memory bytes }. */
+int uncl_conv3x3_tc_plan(int N, int C_in, int H, int W, int C_out, int pad, int* plan);
+
 /* up.up: nn.ConvTranspose2d(C, C, 2, stride=2) + bias, written into an (H2 x W2) channel slice of the skip
  * concat buffer with F.pad(..., mode='replicate') semantics.  unet_parts.py:283-299.  w [C][4][C] fp32.
  * prev/r: video generator recurrence - the first r input channels come from `prev` (Unet.py:270). */

@@ -143,3 +143,60 @@ def test_unsupported_configs_fail_loudly():
         net(torch.zeros(1, 1, 256, 256))  # CPU tensor: no fallback
     with torch.no_grad(), pytest.raises(ValueError):
         net(torch.zeros(1, 1, 128, 128))
+
+
+def _conv_plan(n, ci, h, w, co, pad):
+    import ctypes
+    from uncltmo_b200 import _lib
+    plan = (ctypes.c_int * 16)()
+    rc = _lib.lib().uncl_conv3x3_tc_plan(n, ci, h, w, co, pad, plan)
+    assert rc == 0, _lib.lib().uncl_last_error()
+    keys = ("kind", "NT", "NS", "mma_n", "MB", "adv", "PW", "PH", "BW", "bands", "tiles_per_band", "items", "stages", "nacc",
+            "ksteps", "smem")
+    return dict(zip(keys, list(plan)))
+
+
+def test_conv3x3_tc_plan_invariants():
+    """Tile plans of the tensor-core conv (pure host arithmetic behind the C ABI): every output position is covered, the
+    halo box holds every pixel an MMA row can touch, and the plan fits TMEM / shared memory / the TMA box limits."""
+    rng = np.random.default_rng(3)
+    shapes = [(60, 32, 254, 254, 32, 0), (60, 128, 252, 252, 32, 2), (60, 512, 57, 57, 64, 2), (60, 1024, 24, 24, 128, 2),
+              (60, 256, 12, 12, 256, 0), (1, 64, 3, 3, 32, 0), (2, 64, 5, 5, 64, 2), (1, 16, 3, 3, 32, 0)]
+    for _ in range(60):
+        ci = int(rng.choice([16, 32, 48, 64, 96, 128, 256]))
+        co = int(rng.choice([32, 64, 96, 128, 256]))
+        shapes.append((int(rng.integers(1, 5)), ci, int(rng.integers(3, 300)), int(rng.integers(3, 300)), co, int(rng.choice([0, 2]))))
+    for n, ci, h, w, co, pad in shapes:
+        p = _conv_plan(n, ci, h, w, co, pad)
+        ho, wo = h + 2 * pad - 2, w + 2 * pad - 2
+        halo = 2
+        assert p["PW"] == p["BW"] + halo and p["PW"] <= 128 and p["PH"] <= 256          # TMA box limits
+        assert p["bands"] * p["BW"] >= wo > (p["bands"] - 1) * p["BW"]                   # bands tile the width
+        band_total = ho * p["PW"]
+        last_valid = band_total - 1 - halo                                                # last non-garbage flattened position
+        assert p["tiles_per_band"] * p["adv"] > last_valid                                # tiles tile the band
+        assert (p["tiles_per_band"] - 1) * p["adv"] <= last_valid                         # ... without an empty tile
+        # the deepest pixel an MMA row reads: tile start offset (< PW) + 128*MB rows + two filter rows (+2 columns); the last
+        # two taps of wrap-around rows (masked outputs) may read up to two pixels past the box, inside the stage
+        assert (p["PW"] - 1 + 128 * p["MB"] - 1 + 2 * p["PW"] + 2) < p["PH"] * p["PW"] + p["PW"]
+        assert p["MB"] * p["mma_n"] <= (512 if p["nacc"] == 1 else 256)                   # TMEM columns per stage
+        assert p["stages"] >= 2 and p["smem"] <= 227 * 1024
+        assert p["items"] == n * p["bands"] * p["tiles_per_band"] * p["NS"]
+        assert p["NT"] * p["NS"] == co and ci % (16 * p["ksteps"]) == 0
+        if p["kind"] == 1:
+            assert p["mma_n"] == 3 * p["NT"] and p["adv"] == 128 * p["MB"] - 2 and p["MB"] * (p["NT"] // 32) == 2
+        else:
+            assert p["adv"] == 128 * p["MB"]
+
+
+def test_weight_packing_follows_the_kernel_choice():
+    """packing.conv3x3_tc and uncl_conv3x3_tc apply the same (C_in, C_out) rule: a mismatch would feed one kernel the other
+    kernel's weight layout."""
+    for ci in (16, 32, 48, 64, 80, 96, 128, 256, 512, 1024):
+        for co in (32, 64, 96, 128, 256):
+            p = _conv_plan(1, ci, 20, 20, co, 0)
+            packed = packing.conv3x3_tc(torch.zeros(9, ci, co))
+            if p["kind"] == 1:
+                assert packed.shape == (p["NS"], ci // 16, 3, 2, p["mma_n"], 8)
+            else:
+                assert packed.shape == (p["NS"], ci // 16, 9, 2, p["NT"], 8)

@@ -545,9 +545,8 @@ namespace {
 unsigned long long* g_dbg = nullptr;   // diagnostics only, see uncl_conv_tc_set_debug
 
 // fills the tile geometry for an (ntaps = 9: 3x3 with halo | ntaps = 1: pointwise GEMM) problem and launches
-int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, int H, int W, int epi, int bias_floats,
-              const char* what, cudaStream_t stream) {
-  UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "%s: input must be 16-byte aligned", what);
+// pure host arithmetic (no CUDA calls): also behind uncl_conv3x3_tc_plan
+int plan_tc(TcParams& p, int N, int C_in, int bias_floats, const char* what, int* smem_bytes_out) {
   const int halo = p.ntaps == 9 ? 2 : 0;
   if (p.nchunk <= 0) p.nchunk = C_in / 16;
   p.ksteps = 1;
@@ -603,6 +602,15 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
   UNCL_REQUIRE(p.stages >= 2, "%s: tile does not fit shared memory (%d B per stage)", what, p.stage_bytes);
   int smem_bytes = p.stages * p.stage_bytes + tail;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // force one CTA per SM (each CTA owns all 512 TMEM columns)
+  *smem_bytes_out = smem_bytes;
+  return UNCL_OK;
+}
+
+int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, int H, int W, int epi, int bias_floats,
+              const char* what, cudaStream_t stream) {
+  UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "%s: input must be 16-byte aligned", what);
+  int smem_bytes = 0;
+  if (int rc = plan_tc(p, N, C_in, bias_floats, what, &smem_bytes)) return rc;
 
   EncodeTiledFn encode = get_encode();
   if (!encode) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled unavailable", what);
@@ -743,6 +751,30 @@ extern "C" int uncl_pw_conv_tc(const void* in, long in_img_stride, const void* w
   p.act = act;
   p.ntaps = 1;
   return launch_tc(p, in, in_img_stride, N, C_in, H, W, 2, 2 * C_out, "pw_conv_tc", stream);
+}
+
+int uncl_plan_conv3x3_tc_merged(int N, int C_in, int H, int W, int C_out, int pad, int* plan);
+
+// Tile plan of uncl_conv3x3_tc for a problem - pure host arithmetic, no GPU needed.  plan[16]: kind (0 one-tap kernel,
+// 1 kx-merged kernel), NT, NS, MMA N, M blocks per tile, tile advance in positions, PW, PH, BW, bands, tiles per band,
+// work items, pipeline stages, accumulator stages, K=16 steps per stage, dynamic shared memory bytes.
+extern "C" int uncl_conv3x3_tc_plan(int N, int C_in, int H, int W, int C_out, int pad, int* plan) {
+  UNCL_REQUIRE(plan != nullptr && N > 0 && C_in % 16 == 0 && C_out % 32 == 0 && (pad == 0 || pad == 2) &&
+                   H + 2 * pad - 2 > 0 && W + 2 * pad - 2 > 0,
+               "conv3x3_tc_plan: unsupported C_in=%d C_out=%d pad=%d H=%d W=%d", C_in, C_out, pad, H, W);
+  if (use_merged(C_in, C_out)) return uncl_plan_conv3x3_tc_merged(N, C_in, H, W, C_out, pad, plan);
+  TcParams p{};
+  p.NT = C_out < 128 ? C_out : 128;
+  UNCL_REQUIRE(C_out % p.NT == 0 && C_out <= 1024, "conv3x3_tc_plan: unsupported C_out=%d", C_out);
+  p.NS = C_out / p.NT;
+  p.Ho = H + 2 * pad - 2; p.Wo = W + 2 * pad - 2;
+  p.ntaps = 9;
+  int smem = 0;
+  if (int rc = plan_tc(p, N, C_in, 2 * C_out, "conv3x3_tc_plan", &smem)) return rc;
+  const int v[16] = {0, p.NT, p.NS, p.NT, p.MB, 128 * p.MB, p.PW, p.PH, p.BW, p.nbands, p.tiles_per_band, p.num_items,
+                     p.stages, p.nacc, p.ksteps, smem};
+  for (int i = 0; i < 16; ++i) plan[i] = v[i];
+  return UNCL_OK;
 }
 
 // Diagnostics: when set (device pointer to 8 zeroed uint64), every tensor-core conv launch adds, summed over its CTAs,

@@ -397,25 +397,16 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 
 }  // namespace
 
-// Called by uncl_conv3x3_tc (conv_tc.cu) for C_out <= 64; arguments already validated there.
-int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
-                                  long out_img_stride, int out_f32, int N, int C_in, int H, int W, int C_out, int pad,
-                                  int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
-                                  float* out_img, float* out_logit, unsigned long long* dbg, cudaStream_t stream) {
-  const char* what = "conv3x3_tc(merged)";
-  UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "%s: input must be 16-byte aligned", what);
-  MgParams p{};
+namespace {
+// tile geometry and pipeline sizing: pure host arithmetic (no CUDA calls), shared with uncl_plan_conv3x3_tc_merged
+int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int fuse_outc, const char* what, int* smem_bytes_out) {
   p.NT = C_out < 64 ? C_out : 64;
   UNCL_REQUIRE(p.NT % 32 == 0 && C_out % p.NT == 0, "%s: unsupported C_out=%d", what, C_out);
   UNCL_REQUIRE(!fuse_outc || C_out == 32, "%s: the fused out conv needs C_out == 32", what);
   p.NS = C_out / p.NT;
   p.NP = 3 * p.NT;
-  p.w = reinterpret_cast<const bf16*>(w_packed);
-  p.bias = bias; p.out = out; p.out_f32 = out_f32; p.out_img_stride = out_img_stride;
-  p.outc_w = outc_w; p.outc_b = outc_b; p.out_img = out_img; p.out_logit = out_logit;
   p.C_out = C_out; p.pad = pad;
   p.Ho = H + 2 * pad - 2; p.Wo = W + 2 * pad - 2;
-  p.act = act; p.emit_skip = emit_skip; p.fuse_outc = fuse_outc;
   const int kKSteps = p.NT == 32 ? 2 : 1;   // must match the mg_mma_role instantiation chosen by MB
   p.ksteps = kKSteps;
   UNCL_REQUIRE(C_in % (16 * kKSteps) == 0, "%s: C_in must be a multiple of %d", what, 16 * kKSteps);
@@ -452,9 +443,38 @@ int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void
   UNCL_REQUIRE(p.stages >= 2, "%s: tile does not fit shared memory (%d B per stage)", what, p.stage_bytes);
   int smem_bytes = p.stages * p.stage_bytes + tail;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM (each owns all 512 TMEM columns)
+  *smem_bytes_out = smem_bytes;
+  return UNCL_OK;
+}
+}  // namespace
+
+int uncl_plan_conv3x3_tc_merged(int N, int C_in, int H, int W, int C_out, int pad, int* plan) {
+  MgParams p{};
+  int smem = 0;
+  if (int rc = mg_plan(p, N, C_in, H, W, C_out, pad, 0, "conv3x3_tc_plan(merged)", &smem)) return rc;
+  const int v[16] = {1, p.NT, p.NS, p.NP, p.MB, p.ADV, p.PW, p.PH, p.BW, p.tiles_per_img / p.tiles_per_band, p.tiles_per_band,
+                     p.num_items, p.stages, p.nacc, p.ksteps, smem};
+  for (int i = 0; i < 16; ++i) plan[i] = v[i];
+  return UNCL_OK;
+}
+
+// Called by uncl_conv3x3_tc (conv_tc.cu) for the layers use_merged() selects; arguments already validated there.
+int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                                  long out_img_stride, int out_f32, int N, int C_in, int H, int W, int C_out, int pad,
+                                  int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
+                                  float* out_img, float* out_logit, unsigned long long* dbg, cudaStream_t stream) {
+  const char* what = "conv3x3_tc(merged)";
+  UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "%s: input must be 16-byte aligned", what);
+  MgParams p{};
+  int smem_bytes = 0;
+  if (int rc = mg_plan(p, N, C_in, H, W, C_out, pad, fuse_outc, what, &smem_bytes)) return rc;
+  p.w = reinterpret_cast<const bf16*>(w_packed);
+  p.bias = bias; p.out = out; p.out_f32 = out_f32; p.out_img_stride = out_img_stride;
+  p.outc_w = outc_w; p.outc_b = outc_b; p.out_img = out_img; p.out_logit = out_logit;
+  p.act = act; p.emit_skip = emit_skip; p.fuse_outc = fuse_outc;
 
   CUtensorMap tmap;
-  CUresult r = encode_blocked_bf16(&tmap, in, W, H, C_in / 8, N, in_img_stride, p.PW, p.PH, 2 * kKSteps);
+  CUresult r = encode_blocked_bf16(&tmap, in, W, H, C_in / 8, N, in_img_stride, p.PW, p.PH, 2 * p.ksteps);
   if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
   p.dbg = dbg;
   p.probe_noload = getenv("UNCL_PROBE_NOLOAD") != nullptr ? 1 : 0;   // bit 0: no loads, 1: no epilogue work, 2: MMA free-runs
