@@ -106,6 +106,12 @@ int uncl_nchw_to_blocked(const float* in, void* out, long out_img_stride, int N,
 int uncl_gcn_add_pos(const void* in, long in_img_stride, const float* pos, float* out, int N, int C, int dtype,
                      uncl_stream_t stream);
 
+/* The same, additionally writing x0 as bf16 blocked [N][3C/8][144][8] = [hi | hi | lo] (hi = bf16(x0), lo = bf16(x0 - hi)):
+ * the A operand of the three-term bf16 GEMM that computes Grapher fc1 (torch_vertex.py:219) on the tensor cores to
+ * ~2^-16 relative accuracy; weights from uncltmo_b200/packing.py:pointwise_tc_split, GEMM = uncl_pw_conv_tc. */
+int uncl_gcn_add_pos_split(const void* in, long in_img_stride, const float* pos, float* out, void* split, int N, int C,
+                           int dtype, uncl_stream_t stream);
+
 /* 1x1 conv (+groups, bias, act, residual, per-sample DropPath scale): Grapher fc1/fc2, BasicConv (groups=4), FFN.
  * gcn_lib/torch_vertex.py:219-227, gcn_lib/torch_nn.py:54-78, Unet_singleFrame.py:36-42.
  * w [groups][C_in/groups][C_out/groups] fp32; out = scale[n] * act(conv + bias) + res. */

@@ -12,14 +12,26 @@ constexpr int GN = 144;   // nodes
 constexpr int GK = 9;     // neighbours
 
 // x0 = in + pos_embed (pos_embed pre-blocked [C/8][144][8] fp32)
+// `split` (optional, bf16 blocked [N][3C/8][144][8]): x0 as [hi | hi | lo] with hi = bf16(x0), lo = bf16(x0 - hi), the A
+// operand of the three-term bf16 GEMM x_hi.w_hi + x_hi.w_lo + x_lo.w_hi that stands in for the fp32 fc1 on the tensor
+// cores (relative error ~2^-16 per product instead of bf16's 2^-9; packing.pointwise_tc_split builds the matching weights)
 template <typename T>
 __global__ void gcn_add_pos_kernel(const T* __restrict__ in, long in_img_stride, const float* __restrict__ pos,
-                                   float* __restrict__ out, int C, int N) {
+                                   float* __restrict__ out, bf16* __restrict__ split, int C, int N) {
   const long per = (long)C * GN;
   const long total = (long)N * per;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long n = i / per, o = i % per;
-    out[i] = to_f(in[n * in_img_stride + o]) + pos[o];
+    const float v = to_f(in[n * in_img_stride + o]) + pos[o];
+    out[i] = v;
+    if (split != nullptr) {
+      const bf16 hi = __float2bfloat16_rn(v);
+      const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      bf16* s = split + n * 3 * per + o;
+      s[0] = hi;
+      s[per] = hi;
+      s[2 * per] = lo;
+    }
   }
 }
 
@@ -228,14 +240,25 @@ __global__ void __launch_bounds__(512) gcn_knn_agg_kernel(const float* __restric
 // ================================================================================================
 // C ABI
 // ================================================================================================
-extern "C" int uncl_gcn_add_pos(const void* in, long in_img_stride, const float* pos, float* out, int N, int C,
-                                int dtype, cudaStream_t stream) {
+static int launch_add_pos(const void* in, long in_img_stride, const float* pos, float* out, void* split, int N, int C,
+                          int dtype, cudaStream_t stream) {
   UNCL_REQUIRE(C % 8 == 0 && N > 0, "gcn_add_pos: bad shape");
   const long total = (long)N * C * GN;
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  UNCL_DISPATCH_DTYPE(dtype, T, (gcn_add_pos_kernel<T><<<grid, 256, 0, stream>>>((const T*)in, in_img_stride, pos, out, C, N)));
+  UNCL_DISPATCH_DTYPE(dtype, T, (gcn_add_pos_kernel<T><<<grid, 256, 0, stream>>>((const T*)in, in_img_stride, pos, out, (bf16*)split, C, N)));
   return uncl_check_launch("gcn_add_pos");
+}
+
+extern "C" int uncl_gcn_add_pos(const void* in, long in_img_stride, const float* pos, float* out, int N, int C,
+                                int dtype, cudaStream_t stream) {
+  return launch_add_pos(in, in_img_stride, pos, out, nullptr, N, C, dtype, stream);
+}
+
+extern "C" int uncl_gcn_add_pos_split(const void* in, long in_img_stride, const float* pos, float* out, void* split, int N,
+                                      int C, int dtype, cudaStream_t stream) {
+  UNCL_REQUIRE(split != nullptr, "gcn_add_pos_split: no split output");
+  return launch_add_pos(in, in_img_stride, pos, out, split, N, C, dtype, stream);
 }
 
 // out dtype: fp32 or bf16 (the last FFN conv writes the generator's working dtype)

@@ -143,6 +143,8 @@ class _GeneratorBase(nn.Module):
                                     ("g_fc2", g.fc2[0], 1), ("f_fc1", ffn.fc1[0], 1), ("f_fc2", ffn.fc2[0], 1)):
                 pack = packing.pointwise_tc if tc and name != "g_fc1" else packing.pointwise
                 P[name] = (pack(m.weight.detach(), groups), m.bias.detach().float().contiguous())
+            if tc:   # fc1 on the tensor cores as a three-term bf16 split GEMM (it feeds the KNN selection: ~2^-16, not 2^-9)
+                P["g_fc1_split"] = (packing.pointwise_tc_split(g.fc1[0].weight.detach()), P["g_fc1"][1])
             for i in range(4):
                 u = self.up_path[i]
                 P["u%d_up" % i] = (packing.convT2x2_tc(u.up.weight.detach()) if tc else packing.convT2x2(u.up.weight.detach()),
@@ -227,9 +229,17 @@ class _GeneratorBase(nn.Module):
         idx = torch.empty((n, 144, 9), device=dev, dtype=torch.int32) if keep is not None else None
         x0, y = f32buf(C), f32buf(C)
         gout = buf(C, 12, 12)
-        call("uncl_gcn_add_pos", cur, st(cur), P["pos"], x0, n, C, dt)
-        # fc1 feeds the KNN selection: kept in fp32 on the CUDA cores in both precisions
-        call("uncl_pw_conv", x0, P["g_fc1"][0], P["g_fc1"][1], None, None, y, st(y), n, C, C, 1, 144, ACT_NONE, _lib.F32)
+        # fc1 feeds the KNN selection (a discrete choice): fp32 on the CUDA cores in the exact path; in the bf16 path a
+        # three-term bf16 split GEMM on the tensor cores (x_hi.w_hi + x_hi.w_lo + x_lo.w_hi, fp32 accumulation and output:
+        # ~2^-16 relative, far below the 2^-9 of the bf16 activations it reads)
+        if self.precision == "bf16" and "g_fc1_split" in P:
+            xs = torch.empty((n, 3 * C // 8, 144, 8), device=dev, dtype=torch.bfloat16)
+            call("uncl_gcn_add_pos_split", cur, st(cur), P["pos"], x0, xs, n, C, dt)
+            call("uncl_pw_conv_tc", xs, st(xs), P["g_fc1_split"][0], P["g_fc1_split"][1], None, 0, _lib.F32, None, y, st(y),
+                 _lib.F32, n, 3 * C, C, 1, 12, 12, ACT_NONE)
+        else:
+            call("uncl_gcn_add_pos", cur, st(cur), P["pos"], x0, n, C, dt)
+            call("uncl_pw_conv", x0, P["g_fc1"][0], P["g_fc1"][1], None, None, y, st(y), n, C, C, 1, 144, ACT_NONE, _lib.F32)
         if self.precision == "bf16":
             # the other four 1x1 convs (92 % of the block's MACs) run as tensor-core GEMMs on bf16 tensors
             def b16buf(c):

@@ -73,6 +73,17 @@ def pointwise_tc(w, groups=1):
     return b.to(torch.bfloat16)
 
 
+def pointwise_tc_split(w):
+    """1x1 Conv2d weight [C_out][C_in][1][1] fp32 -> the B operand of the three-term bf16 GEMM x_hi.w_hi + x_hi.w_lo +
+    x_lo.w_hi (input channels [w_hi | w_lo | w_hi], matching uncl_gcn_add_pos_split's [hi | hi | lo]): bf16
+    [NS][3*C_in/16][2][NT][8]."""
+    w2 = w.reshape(w.shape[0], w.shape[1]).float()
+    hi = w2.to(torch.bfloat16)
+    lo = (w2 - hi.float()).to(torch.bfloat16)
+    cat = torch.cat([hi, lo, hi], dim=1).float()
+    return pointwise_tc(cat.reshape(cat.shape[0], cat.shape[1], 1, 1), 1)
+
+
 def conv_first(w):
     """Conv2d(1, C_out, 3) weight [C_out][1][3][3] -> [9][C_out] fp32."""
     return w.reshape(w.shape[0], 9).t().contiguous().float()
