@@ -40,6 +40,14 @@ for C, H, H2 in ((256, 12, 24), (128, 28, 57), (64, 61, 122), (32, 126, 252)):
     mb = (x.numel() + out.numel()) * 2 / 1e6
     print("convT2x2_tc C=%3d %3d->%3d: %6.1f us  %6.0f GB/s  rel err %.2e" % (C, H, H2, us, mb / us * 1e3 / 1e3 * 1e3 / 1e3, rel), flush=True)
 
+x = torch.rand((60, 1, 256, 256), device="cuda", generator=g)
+wt = torch.randn((32, 1, 3, 3), device="cuda", generator=g) * 0.3
+b = torch.randn(32, device="cuda", generator=g) * 0.1
+o = torch.empty((60, 4, 254, 254, 8), device="cuda", dtype=torch.bfloat16)
+w9, ws = packing.conv_first(wt), packing.conv_first_tc_split(wt)
+print("conv_first (CUDA cores): %6.1f us" % timed(lambda: _lib.call("uncl_conv_first", x, w9, b, o, o.stride(0), 60, 256, 256, 32, 1, _lib.BF16)))
+print("conv_first_tc          : %6.1f us" % timed(lambda: _lib.call("uncl_conv_first_tc", x, ws, b, o, o.stride(0), 60, 256, 256, 32, 1)))
+
 pipe = FramePipeline(None)
 for shape in ((1088, 1936), (1080, 1920, 3)):
     d = torch.rand(shape, device="cuda", generator=g)

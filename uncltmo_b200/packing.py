@@ -89,6 +89,18 @@ def conv_first(w):
     return w.reshape(w.shape[0], 9).t().contiguous().float()
 
 
+def conv_first_tc_split(w):
+    """Conv2d(1, 32, 3) weight [32][1][3][3] -> the B operand of uncl_conv_first_tc: bf16 [4][32][8], K slot k = 8*g + j:
+    k < 9: w_hi[tap k]; 9 <= k < 18: w_lo[tap k-9]; 18 <= k < 27: w_hi[tap k-18]; zero above (pairs with the kernel's
+    [x_hi | x_hi | x_lo] rows)."""
+    w9 = conv_first(w)                                   # [9][C_out] fp32
+    hi = w9.to(torch.bfloat16)
+    lo = (w9 - hi.float()).to(torch.bfloat16)
+    k = torch.zeros((32, w9.shape[1]), device=w.device, dtype=torch.bfloat16)
+    k[0:9], k[9:18], k[18:27] = hi, lo, hi
+    return k.reshape(4, 8, w9.shape[1]).permute(0, 2, 1).contiguous()
+
+
 def blocked_param(t):
     """[1][C][H][W] -> C8-blocked [C/8][H*W][8] fp32 (pos_embed)."""
     _, c, h, w = t.shape
