@@ -38,7 +38,7 @@ for C, H, H2 in ((256, 12, 24), (128, 28, 57), (64, 61, 122), (32, 126, 252)):
     got = out[:2].float().permute(0, 1, 4, 2, 3).reshape(2, C, H2, H2)
     rel = ((got - ref).norm() / ref.norm()).item()
     mb = (x.numel() + out.numel()) * 2 / 1e6
-    print("convT2x2_tc C=%3d %3d->%3d: %6.1f us  %6.0f GB/s  rel err %.2e" % (C, H, H2, us, mb / us * 1e3 / 1e3 * 1e3 / 1e3, rel), flush=True)
+    print("convT2x2_tc C=%3d %3d->%3d: %6.1f us  %6.0f GB/s  rel err %.2e" % (C, H, H2, us, mb / us * 1e3, rel), flush=True)
 
 x = torch.rand((60, 1, 256, 256), device="cuda", generator=g)
 wt = torch.randn((32, 1, 3, 3), device="cuda", generator=g) * 0.3
