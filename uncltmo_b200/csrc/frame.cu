@@ -596,8 +596,10 @@ extern "C" int uncl_percentile_pair(const float* data, long n, float clamp_lo, f
       void* args[] = {(void*)&data, (void*)&n, (void*)&per_cta, (void*)&clamp_lo, (void*)&clamp_hi, (void*)&hist3, (void*)&bar,
                       (void*)&ranks, (void*)&t0, (void*)&t1, (void*)&pct_out};
       e = cudaLaunchCooperativeKernel((const void*)select_fused_kernel, dim3(sms), dim3(kFusedThreads), args, smem, stream);
-      if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "percentile_pair: cooperative launch: %s", cudaGetErrorString(e));
-      return uncl_check_launch("percentile_pair");
+      if (e == cudaSuccess) return uncl_check_launch("percentile_pair");
+      // a device partition that cannot hold one CTA per SM at once (MPS / green-context limits) refuses the cooperative
+      // launch synchronously: clear the error and take the three-launch path, which needs no co-residency
+      (void)cudaGetLastError();
     }
   }
   // three-pass path (large planes).  One 1024-thread CTA per SM: every CTA merges up to 4 x 2048 shared-memory bins
