@@ -303,7 +303,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     }
     __syncwarp();
   } else {
-    // =============================== epilogue (8 warps: 4 TMEM lane quarters x 2 M-block parities) ========
+    // =============================== epilogue (16 warps: 4 TMEM lane quarters x 4 round-robin unit slots) ========
     const int quarter = warp & 3;
     const int k4 = (warp - 2) >> 2;     // this warp takes the units u = (block, 32-column chunk) with u % 4 == k4
     const int cpb = p.NT >> 5;          // 32-column chunks per M block

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(1024) select_pass_kernel(const float* __restri
   auto visit = [&](float raw) {
     const float v = fminf(fmaxf(raw, clamp_lo), clamp_hi);
     const unsigned k = order_key(v);
-    if (PASS == 0) {
+    if constexpr (PASS == 0) {
       // tone-mapped values cluster in a few exponent bins: aggregate equal digits inside the warp, one atomic per group
       const unsigned bin = k >> SHIFT;
       const unsigned active = __activemask();
