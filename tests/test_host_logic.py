@@ -225,3 +225,30 @@ def test_split_bf16_weight_packings():
     co, tap = 21, 5
     for k, want in ((tap, h9[tap, co]), (9 + tap, l9[tap, co]), (18 + tap, h9[tap, co]), (29, torch.tensor(0.0))):
         assert pf[k // 8, co, k % 8].float() == want.float()
+
+
+def test_merged_packing_reproduces_the_convolution_on_cpu():
+    """The kx-merged formulation restated with torch on the CPU, reading the weights exactly as conv_tc_merged.cu does from
+    packing.conv3x3_tc's layout: D[p][kx*C + co] = sum_{ky,ci} X[p + ky*PW][ci] W[ky][kx][ci][co] over flattened positions
+    (pitch PW = W), out[q] = D[q][0] + D[q+1][1] + D[q+2][2].  Guards the layout contract without a GPU."""
+    g = torch.Generator().manual_seed(11)
+    ci, co, h, w = 64, 32, 9, 11
+    x = torch.randn(1, ci, h, w, generator=g)
+    wt = torch.randn(co, ci, 3, 3, generator=g) / (9 * ci) ** 0.5
+    w9 = packing.conv3x3_taps(wt, transposed=False)               # [9][ci][co]
+    p = packing.conv3x3_tc(w9).float()                             # [1][ci/16][3][2][3*co][8]
+    assert p.shape == (1, ci // 16, 3, 2, 3 * co, 8)
+    xf = x[0].permute(1, 2, 0).reshape(h * w, ci)                   # flattened positions, pitch PW = w
+    xf = torch.cat([xf, torch.zeros(2 * w + 2, ci)])                # rows the shifted reads run into (masked outputs)
+    npos = h * w
+    d = torch.zeros(npos + 2, 3 * co)
+    for ch in range(ci // 16):
+        for ky in range(3):
+            a = xf[ky * w: ky * w + npos + 2, ch * 16:(ch + 1) * 16]                      # A rows shifted by one filter row
+            b = p[0, ch, ky].permute(1, 0, 2).reshape(3 * co, 16)                          # [N'][k = half*8 + k8]
+            d += a @ b.t()
+    out = d[0:npos, 0:co] + d[1:npos + 1, co:2 * co] + d[2:npos + 2, 2 * co:3 * co]
+    out = out.reshape(h, w, co)[: h - 2, : w - 2].permute(2, 0, 1)                         # the last two columns / rows wrap
+    # the packed weights are bf16: compare against the convolution of the bf16-rounded weights with fp32 activations
+    want = torch.nn.functional.conv2d(x, wt.to(torch.bfloat16).float())[0]
+    assert torch.allclose(out, want, atol=2e-5, rtol=1e-5)
