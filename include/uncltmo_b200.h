@@ -37,13 +37,6 @@ int uncl_probe_device(int* out_dev, uncl_stream_t stream);   /* writes __CUDA_AR
 int uncl_conv_first(const float* x, const float* w, const float* bias, void* out, long out_img_stride, int N, int H,
                     int W, int C_out, int act, int dtype, uncl_stream_t stream);
 
-/* The same layer on the tcgen05 tensor cores for the bf16 path (C_out = 32): every CTA builds the im2col rows of 128
- * output pixels in shared memory (9 taps as a three-term bf16 split of the fp32 image, fp32 accumulation) and issues one
- * pair of MMAs.  w_split: bf16 [4][32][8] from uncltmo_b200/packing.py:conv_first_tc_split; out: bf16 blocked.
- * Measured slower than uncl_conv_first on the generator's shapes (instruction-bound operand build): opt-in, see the source. */
-int uncl_conv_first_tc(const float* x, const void* w_split, const float* bias, void* out, long out_img_stride, int N, int H,
-                       int W, int C_out, int act, uncl_stream_t stream);
-
 /* 3x3 stride-1 conv, CUDA-core fp32-accumulate path.  pad 0 = nn.Conv2d valid (unet_parts.py:18,27);
  * pad 2 = nn.ConvTranspose2d(k=3, s=1, p=0) with flipped weights (unet_parts.py:114, 148-159).
  * w [9][C_in][C_out] fp32.  emit_skip=1 additionally writes y^2 and sqrt(y+1e-8) at channel-block offsets

@@ -10,7 +10,7 @@ outputs of the reference itself, imported in place on CPU by `tests/golden/make_
 (fixtures committed under `tests/golden/*.npz`, checked by `tests/test_oracle_golden.py`).
 """
 from .generator import (unet_forward, unet_video_forward, gcn_block, relative_pos_table,  # noqa: F401
-                        knn_indices)
+                        knn_indices, bf16_operands)
 from .discriminator import simple_discriminator_forward, contrast_map, gauss_window  # noqa: F401
 from .losses import (struct_loss, contrastive_d_loss, nce, l1_mean_terms, tv_loss)  # noqa: F401
 from .frame_path import (log_lambda_normalise, to_gray, resize_im, tile_and_blend, tile_grid,  # noqa: F401

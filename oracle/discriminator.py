@@ -19,7 +19,7 @@ def gauss_window(size=11, sigma=1.5):
 def contrast_map(x, win=None):
     """Local variance under an 11x11 gaussian (valid): E[x^2] - E[x]^2, per channel."""
     b, c, h, w = x.shape
-    win = (gauss_window() if win is None else win).to(x.dtype)
+    win = (gauss_window() if win is None else win).to(x)   # dtype and device of x
     xr = x.reshape(b * c, 1, h, w)
     mu = F.conv2d(xr, win)
     var = F.conv2d(xr * xr, win) - mu * mu

@@ -12,30 +12,89 @@ import torch.nn.functional as F
 
 EPS = 1e-8  # utils/params.py:52 (params.epsilon)
 
+# ---------------------------------------------------------------------------------------------------------------
+# bf16-operand emulation.  NOT reference behaviour (the reference is fp32 throughout): with `bf16_operands(True)` the
+# oracle rounds, to bfloat16 and back, exactly the tensors the mixed-precision CUDA path stores in bf16 - the
+# activation and weight operands of every tensor-core convolution and the pre-activation gradients dz that feed the
+# data- and weight-gradient GEMMs - while every accumulation stays in the oracle's dtype (float64 in the tests).  The
+# remaining difference to the CUDA path is fp32 accumulation order, so gradient parity can be gated per tensor instead
+# of by cosine similarity.
+_BF16_OPERANDS = False
+
+
+class _Round(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _GradRound(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class bf16_operands:
+    """Context manager: `with oracle.bf16_operands(True): ...` (see above)."""
+
+    def __init__(self, on=True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        global _BF16_OPERANDS
+        self.prev, _BF16_OPERANDS = _BF16_OPERANDS, self.on
+
+    def __exit__(self, *a):
+        global _BF16_OPERANDS
+        _BF16_OPERANDS = self.prev
+
+
+def _r(t):
+    """operand stored / read as bf16 by the tensor-core path"""
+    return _Round.apply(t) if _BF16_OPERANDS else t
+
+
+def _conv(x, w, b, transposed=False, **kw):
+    """A convolution that the CUDA path runs on the tensor cores: bf16 operands, pre-activation gradient in bf16."""
+    if not _BF16_OPERANDS:
+        return (F.conv_transpose2d if transposed else F.conv2d)(x, w, b, **kw)
+    z = (F.conv_transpose2d if transposed else F.conv2d)(_Round.apply(x), _Round.apply(w), None, **kw)
+    z = _GradRound.apply(z)
+    return z if b is None else z + b.view(1, -1, 1, 1)
+
 
 def _double_conv(sd, p, x):
     # unet_parts.py:57-87 with padding=0, unet_norm='none', activation='relu'
-    x = F.relu(F.conv2d(x, sd[p + "conv.weight"], sd[p + "conv.bias"]))
-    return F.relu(F.conv2d(x, sd[p + "conv1.weight"], sd[p + "conv1.bias"]))
+    first = sd[p + "conv.weight"].shape[1] == 1   # inc.conv.conv (1 -> 32): fp32 CUDA cores in both precision modes
+    x = F.relu((F.conv2d if first else _conv)(x, sd[p + "conv.weight"], sd[p + "conv.bias"]))
+    return F.relu(_conv(x, sd[p + "conv1.weight"], sd[p + "conv1.bias"]))
 
 
 def _double_last_conv(sd, p, x):
     # unet_parts.py:126-141: conv3 valid -> ReLU -> ConvTranspose 3x3 s1 p0 -> ReLU
-    x = F.relu(F.conv2d(x, sd[p + "conv.weight"], sd[p + "conv.bias"]))
-    return F.relu(F.conv_transpose2d(x, sd[p + "conv1.weight"], sd[p + "conv1.bias"]))
+    x = F.relu(_conv(x, sd[p + "conv.weight"], sd[p + "conv.bias"]))
+    return F.relu(_conv(x, sd[p + "conv1.weight"], sd[p + "conv1.bias"], transposed=True))
 
 
 def _up(sd, p, x1, x2):
     # unet_parts.py:283-335, up_mode=0, convtranspose_kernel=2, con_operator='square_and_square_root'
-    x1 = F.conv_transpose2d(x1, sd[p + "up.weight"], sd[p + "up.bias"], stride=2)
+    x1 = _conv(x1, sd[p + "up.weight"], sd[p + "up.bias"], transposed=True, stride=2)
     dy = x2.shape[2] - x1.shape[2]
     dx = x2.shape[3] - x1.shape[3]
     if dx or dy:
         x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2), mode="replicate")
     x = torch.cat([x2, x1, x2 * x2, torch.pow(x2 + EPS, 0.5)], dim=1)  # :319-322
     # double_conv_traspose, unet_parts.py:183-193
-    x = F.relu(F.conv_transpose2d(x, sd[p + "conv.conv.weight"], sd[p + "conv.conv.bias"]))
-    return F.relu(F.conv_transpose2d(x, sd[p + "conv.conv1.weight"], sd[p + "conv.conv1.bias"]))
+    x = F.relu(_conv(x, sd[p + "conv.conv.weight"], sd[p + "conv.conv.bias"], transposed=True))
+    return F.relu(_conv(x, sd[p + "conv.conv1.weight"], sd[p + "conv.conv1.bias"], transposed=True))
 
 
 def relative_pos_table(channels=256, grid=12):
@@ -88,14 +147,14 @@ def gcn_block(sd, x, droppath_masks=None, return_idx=False):
                       idx.unsqueeze(1).expand(B, C, n, idx.shape[-1]))
     agg = (yj - y.unsqueeze(-1)).max(dim=-1)[0]
     z = torch.stack([y, agg], dim=2).reshape(B, 2 * C, H, W)
-    z = F.gelu(F.conv2d(z, sd[p + "0.graph_conv.gconv.nn.0.weight"],
-                        sd[p + "0.graph_conv.gconv.nn.0.bias"], groups=4))
-    z = F.conv2d(z, sd[p + "0.fc2.0.weight"], sd[p + "0.fc2.0.bias"])
+    z = F.gelu(_conv(z, sd[p + "0.graph_conv.gconv.nn.0.weight"],
+                     sd[p + "0.graph_conv.gconv.nn.0.bias"], groups=4))
+    z = _conv(z, sd[p + "0.fc2.0.weight"], sd[p + "0.fc2.0.bias"])
     if droppath_masks is not None:
         z = z * droppath_masks[0].view(B, 1, 1, 1)
     x = z + x
-    f = F.gelu(F.conv2d(x, sd[p + "1.fc1.0.weight"], sd[p + "1.fc1.0.bias"]))
-    f = F.conv2d(f, sd[p + "1.fc2.0.weight"], sd[p + "1.fc2.0.bias"])
+    f = F.gelu(_conv(x, sd[p + "1.fc1.0.weight"], sd[p + "1.fc1.0.bias"]))
+    f = _conv(f, sd[p + "1.fc2.0.weight"], sd[p + "1.fc2.0.bias"])
     if droppath_masks is not None:
         f = f * droppath_masks[1].view(B, 1, 1, 1)
     out = f + x
@@ -133,6 +192,7 @@ def unet_forward(sd, x, droppath_masks=None, return_all=False):
     for i in range(4):
         up_x = _up(sd, "up_path.%d." % i, up_x, skips[3 - i])
         inter["ups"].append(up_x)
+    up_x = _r(up_x)   # stored as bf16 by the tensor-core path; the out conv and the feature consumers read that tensor
     logit = F.conv2d(up_x, sd["outc.conv.weight"], sd["outc.conv.bias"])
     out = torch.sigmoid(logit)
     if return_all:
@@ -182,6 +242,7 @@ def unet_video_forward(sd, x, droppath_masks=None, detach_state=False):
                 fea = torch.cat((prev[5 + i], up_x[:, r:]), 1)  # Unet.py:270
             up_x = _up(sd, "up_path.%d." % i, fea, skips[3 - i])
             cur.append(up_x[:, :up_x.shape[1] // 32])
+        up_x = _r(up_x)
         feats.append(_contrast_features(up_x).unsqueeze(1))
         out = torch.sigmoid(F.conv2d(up_x, sd["outc.conv.weight"], sd["outc.conv.bias"]))
         outs.append(out.unsqueeze(1))

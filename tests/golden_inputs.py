@@ -74,3 +74,22 @@ def act_stride(shape):
     """Spatial stride used when storing one image's activation [C,H,W] in the fixtures (<= ~40k values)."""
     import math
     return max(1, math.ceil(math.sqrt(shape[1] * shape[2] * shape[3] / 40000.0)))
+
+
+def train_batch(b, video=False):
+    """(hdr_input, real_ldr_pos, real_ldr_neg), each [b/2, 2, 1, 256, 256]: loader batch x 2 crops for the image trainer
+    (ProcessedDatasetFolderImg.py), b/2 clips of T = 2 frames for the video trainer.  b = 16 is the reference recipe
+    (run_imageTMO_train.sh:6-7: batch 8 x 2)."""
+    hdr = torch.from_numpy(synth.normalised_batch(b, seed=4)).reshape(b // 2, 2, 1, 256, 256)
+    pos = torch.from_numpy(synth.ldr_batch(b, seed=5)).reshape(b // 2, 2, 1, 256, 256)
+    neg = torch.from_numpy(synth.ldr_batch(b, seed=6)).reshape(b // 2, 2, 1, 256, 256)
+    return hdr, pos, neg
+
+
+def droppath_masks(b, keep=0.95):
+    """Two [b] per-sample scale vectors (mask / keep_prob) for the two residual branches of the graph block: sample 3 is
+    dropped in the first branch, sample b-5 in the second (train-mode DropPath p = 0.05, Unet_singleFrame.py:62-77)."""
+    m0, m1 = torch.full((b,), 1.0 / keep), torch.full((b,), 1.0 / keep)
+    m0[3 % b] = 0.0
+    m1[(b - 5) % b] = 0.0
+    return [m0, m1]

@@ -186,3 +186,41 @@ def test_streaming_host_api_matches_single_frame_calls(net):
     for f, g in zip(frames, got):
         want = pipe.tonemap(f.cuda(), 50.0, uint8=True).cpu()
         assert torch.equal(g, want)
+
+
+@pytest.mark.parametrize("h,w", [(769, 1025), (1080, 1920)])
+def test_bf16_full_frame_matches_oracle(h, w):
+    """The configuration bench.py reports - a whole 1080p frame (and the HDR-Survey 1/4-resolution size) through the
+    bf16 tensor-core generator and the GPU frame path - against the fp32 oracle's sequential restatement of
+    run_model_on_single_image2 (tile by tile at batch 1, Python cross-fade, np.percentile).
+    Tolerances: the blended generator output (before the stretch) carries the per-tile bf16 error (rel-L2 <= 1e-2 is
+    BASELINE.json's gate; measured ~3e-4); the post-process divides by (p99.5 - p0.5) of a nearly flat random-init
+    output, which amplifies absolute errors ~50-100x, so the colour frame is held to rel-L2 <= 2e-2 and the 8-bit image
+    to +-8 levels with >= 99 % of the pixels within +-2."""
+    sd = make_generator_state_dict()
+    rgb = torch.from_numpy(synth.hdr_frame(h, w, seed=0))
+    want = oracle.tonemap_frame(rgb, gi.LAMBDA, lambda t: oracle.unet_forward(sd, t)[0])
+    want_u8 = oracle.frame_path.to_uint8_stretch(want)
+    net_bf = UNet(*G_ARGS, up_mode=0, precision="bf16").cuda().eval()
+    net_bf.load_state_dict(sd)
+    pipe = FramePipeline(net_bf)
+    # stage 1: blended generator output against the oracle's
+    _, g = oracle.log_lambda_normalise(rgb, gi.LAMBDA)
+    g_p, _, _ = oracle.resize_im(g)
+    fake_want = oracle.tile_and_blend(g_p[None], lambda t: oracle.unet_forward(sd, t)[0])[0, 0]
+    pl = pipe.plan(h, w, torch.device("cuda"))
+    gray_p, _ = pipe.normalise_pad(rgb.cuda(), gi.LAMBDA)
+    fake_got = pipe.blend(pipe.run_generator(pipe.gather_tiles(gray_p, pl)), pl).cpu()
+    rel_fake = ((fake_got.double() - fake_want.double()).norm() / fake_want.double().norm()).item()
+    # the quantity the stretch amplifies: error relative to the spread of the output, not to its level
+    spread = (fake_want.max() - fake_want.min()).item()
+    rel_spread = (fake_got - fake_want).abs().max().item() / spread
+    col = pipe.tonemap(rgb.cuda(), gi.LAMBDA).cpu()
+    rel_col = ((col.double() - want.double()).norm() / want.double().norm()).item()
+    u8 = pipe.tonemap(rgb.cuda(), gi.LAMBDA, uint8=True).cpu().numpy()
+    d = np.abs(u8.astype(int) - want_u8.astype(int))
+    print("bf16 frame %dx%d: blended rel-L2 %.2e, max err / output spread %.2e, colour rel-L2 %.2e, u8 max diff %d, "
+          "within +-1: %.4f, +-2: %.4f" % (w, h, rel_fake, rel_spread, rel_col, d.max(), (d <= 1).mean(), (d <= 2).mean()))
+    assert rel_fake <= 1e-2
+    assert rel_col <= 2e-2
+    assert d.max() <= 8 and (d <= 2).mean() >= 0.99

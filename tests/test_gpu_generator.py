@@ -161,28 +161,6 @@ def test_merged_conv_fused_out_conv_and_fp32_output(ci, h, pad):
     assert (img - torch.sigmoid(want)).abs().max().item() <= 1e-5
 
 
-@pytest.mark.parametrize("n,h,w", [(3, 256, 256), (2, 37, 50), (1, 3, 3)])
-def test_first_conv_on_tensor_cores(n, h, w):
-    """inc.conv as an im2col-in-shared-memory tcgen05 GEMM with a three-term bf16 split of the fp32 image: agrees with
-    the fp32 CUDA-core kernel to the bf16 rounding of the output."""
-    g = torch.Generator(device="cuda").manual_seed(h * 7 + w)
-    x = torch.rand((n, 1, h, w), device="cuda", generator=g)
-    wt = torch.randn((32, 1, 3, 3), device="cuda", generator=g) * 0.3
-    b = torch.randn(32, device="cuda", generator=g) * 0.1
-    ref = torch.empty((n, 4, h - 2, w - 2, 8), device="cuda", dtype=torch.bfloat16)
-    out = torch.full_like(ref, float("nan"))
-    _lib.call("uncl_conv_first", x, packing.conv_first(wt), b, ref, ref.stride(0), n, h, w, 32, 1, _lib.BF16)
-    _lib.call("uncl_conv_first_tc", x, packing.conv_first_tc_split(wt), b, out, out.stride(0), n, h, w, 32, 1)
-    torch.cuda.synchronize()
-    assert not torch.isnan(out.float()).any()
-    assert (out.float() - ref.float()).abs().max().item() <= 2.0 ** -7 * max(1.0, ref.float().abs().max().item())
-    assert rel(out.float(), ref.float()) <= 2e-3
-    # the split keeps fp32-grade accuracy: against an fp64 convolution the error is the bf16 rounding of the output only
-    want = torch.relu(torch.nn.functional.conv2d(x.double(), wt.double(), b.double()))
-    got = out.float().permute(0, 1, 4, 2, 3).reshape(n, 32, h - 2, w - 2).double()
-    assert rel(got, want) <= 3e-3
-
-
 def test_video_generator_matches_oracle(golden):
     sd = make_generator_state_dict()
     xv = gi.video_input()

@@ -203,7 +203,7 @@ def test_weight_packing_follows_the_kernel_choice():
 
 
 def test_split_bf16_weight_packings():
-    """pointwise_tc_split / conv_first_tc_split: [w_hi | w_lo | w_hi] in the K order the kernels' [x_hi | x_hi | x_lo] rows
+    """pointwise_tc_split: [w_hi | w_lo | w_hi] in the K order the kernel's [x_hi | x_hi | x_lo] rows
     expect, hi + lo reproducing the fp32 weight to ~2^-16."""
     g = torch.Generator().manual_seed(7)
     w = torch.randn(256, 64, 1, 1, generator=g)
@@ -216,15 +216,6 @@ def test_split_bf16_weight_packings():
         k = term * 64 + ci
         assert p[ns, k // 16, (k % 16) // 8, n, k % 8] == want[ns * 128 + n, ci]
     assert ((hi.float() + lo.float()) - w.reshape(256, 64)).abs().max() <= 2.0 ** -15 * w.abs().max()
-    wf = torch.randn(32, 1, 3, 3, generator=g)
-    pf = packing.conv_first_tc_split(wf)                    # [4][32][8], K slot k = 8*g + j
-    assert pf.shape == (4, 32, 8) and pf.dtype == torch.bfloat16
-    w9 = packing.conv_first(wf)                             # [9][32]
-    h9 = w9.to(torch.bfloat16)
-    l9 = (w9 - h9.float()).to(torch.bfloat16)
-    co, tap = 21, 5
-    for k, want in ((tap, h9[tap, co]), (9 + tap, l9[tap, co]), (18 + tap, h9[tap, co]), (29, torch.tensor(0.0))):
-        assert pf[k // 8, co, k % 8].float() == want.float()
 
 
 def test_merged_packing_reproduces_the_convolution_on_cpu():

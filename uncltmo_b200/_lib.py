@@ -9,7 +9,8 @@ import re
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libuncltmo_b200.so")
+# UNCL_LIB selects another build of the same ABI (tools/ use the -DUNCL_PROBES variant); the default is the product library
+LIB_PATH = os.environ.get("UNCL_LIB") or os.path.join(_HERE, "libuncltmo_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "uncltmo_b200.h")
 
 F32, BF16 = 0, 1
@@ -102,10 +103,22 @@ def stop_call_timing():
 
 
 def call(name, *args):
-    """Invoke a C-ABI entry point on the current CUDA stream; raise RuntimeError on a non-zero return."""
+    """Invoke a C-ABI entry point on the current CUDA stream of the device the tensor arguments live on; raise
+    RuntimeError on a non-zero return.  All tensors of a call must be on one device; when that is not the current device
+    the call runs under torch.cuda.device(...) so that the kernels, the stream and the pointers agree."""
     global _launches
     l = lib()
+    dev = None
+    for a in args:
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            if dev is None:
+                dev = a.device
+            elif a.device != dev:
+                raise RuntimeError("%s: tensors on different devices (%s, %s)" % (name, dev, a.device))
     argv = [ptr(a) for a in args]
+    if dev is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return call(name, *args)
     stream = torch.cuda.current_stream().cuda_stream
     if _timing is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

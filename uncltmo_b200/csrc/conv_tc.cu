@@ -173,7 +173,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       const int a_stage_bytes = p.a_stage_bytes;
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
       const int ns_per_group = p.ns_per_group;
-      unsigned long long* const dbg = p.dbg;
+      unsigned long long* const dbg = UNCL_PROBE(1, 1) ? p.dbg : nullptr;
       long long w_empty = 0;
       const long long t_begin = dbg ? clock64() : 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -181,12 +181,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const uint8_t* wsrc = wbase + (size_t)it.ns * nchunk * b_bytes;
         const int kblk0 = (it.ns / ns_per_group) * nchunk * 2 * p.ksteps;   // first input channel block of this split's group
         for (int ch = 0; ch < nchunk; ++ch) {
-          if (p.probe_noload & 4) continue;
+          if (UNCL_PROBE(p.probe_noload, 4)) continue;
           const long long tw0 = dbg ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1);
           if (dbg) w_empty += clock64() - tw0;
           uint8_t* sa = stage_base + (size_t)stage * stage_bytes;
-          if ((p.probe_noload & 1) && (item != (int)blockIdx.x || ch >= stages)) { mbar_arrive(&full[stage]); }
+          if ((UNCL_PROBE(p.probe_noload, 1)) && (item != (int)blockIdx.x || ch >= stages)) { mbar_arrive(&full[stage]); }
           else {
           mbar_expect_tx(&full[stage], tx_bytes);
           tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, kblk0 + ch * 2 * p.ksteps, it.n);
@@ -218,7 +218,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       const int nacc = p.nacc, acc_cols = p.acc_cols;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      unsigned long long* const dbg = p.dbg;
+      unsigned long long* const dbg = UNCL_PROBE(1, 1) ? p.dbg : nullptr;
       long long w_full = 0, w_tempty = 0;
       const long long t_begin = dbg ? clock64() : 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -231,7 +231,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const uint32_t mb = (uint32_t)it.mb_act;
         for (int ch = 0; ch < nchunk; ++ch) {
           const long long tw1 = dbg ? clock64() : 0;
-          if (!(p.probe_noload & 4)) mbar_wait(&full[stage], phase);
+          if (!(UNCL_PROBE(p.probe_noload, 4))) mbar_wait(&full[stage], phase);
           if (dbg) w_full += clock64() - tw1;
           tc_fence_after();
           const uint32_t sa16 = stage0_16 + (uint32_t)stage * stage_16;
@@ -287,7 +287,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             }
             __syncwarp();
           }
-          if (!(p.probe_noload & 4) && elect_one()) tc_commit(&empty[stage]);
+          if (!(UNCL_PROBE(p.probe_noload, 4)) && elect_one()) tc_commit(&empty[stage]);
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -324,7 +324,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const int nacc = p.nacc, acc_cols = p.acc_cols;
     int acc = 0;
     uint32_t acc_phase = 0;
-    unsigned long long* const dbg = (warp == 2 && lane == 0) ? p.dbg : nullptr;
+    unsigned long long* const dbg = (UNCL_PROBE(1, 1) && warp == 2 && lane == 0) ? p.dbg : nullptr;
     long long w_tfull = 0;
     const long long t_begin = dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -335,7 +335,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       tc_fence_after();
       if constexpr (EPI == 0) {
         const int cbase0 = it.ns * NT;
-        const int units = ((p.probe_noload & 2) ? 0 : it.mb_act) * cpb;
+        const int units = ((UNCL_PROBE(p.probe_noload, 2)) ? 0 : it.mb_act) * cpb;
         for (int u = k4, b = 0, cc = k4; u < units; u += kEpiPerQuarter, cc += kEpiPerQuarter) {
           while (cc >= cpb) { cc -= cpb; ++b; }
           const int c0 = cc * 32;
@@ -542,7 +542,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 
 namespace {
 
-unsigned long long* g_dbg = nullptr;   // diagnostics only, see uncl_conv_tc_set_debug
+#ifdef UNCL_PROBES
+unsigned long long* g_dbg = nullptr;   // probe build only (tools/), see uncl_conv_tc_set_debug
+static const char* probe_env(const char* name) { return getenv(name); }
+#else
+constexpr unsigned long long* g_dbg = nullptr;
+static const char* probe_env(const char*) { return nullptr; }   // the product library reads no environment variable
+#endif
 
 // fills the tile geometry for an (ntaps = 9: 3x3 with halo | ntaps = 1: pointwise GEMM) problem and launches
 // pure host arithmetic (no CUDA calls): also behind uncl_conv3x3_tc_plan
@@ -558,7 +564,7 @@ int plan_tc(TcParams& p, int N, int C_in, int bias_floats, const char* what, int
   // stages so that the epilogue of tile i overlaps the MMAs of tile i+1.  Measured per layer (profiles/README.md): the
   // single stage pays off for N = 128 with K >= 512*9 (up0.conv: 167 -> 129 us); for narrower N the exposed epilogue
   // and the coarser tiles cost more than the amortisation gains.
-  p.nacc = (p.NT == 128 && C_in >= 512 && p.ntaps == 9 && getenv("UNCL_PROBE_DOUBLE_ACC") == nullptr) ? 1 : 2;
+  p.nacc = (p.NT == 128 && C_in >= 512 && p.ntaps == 9 && probe_env("UNCL_PROBE_DOUBLE_ACC") == nullptr) ? 1 : 2;
   p.acc_cols = p.nacc == 1 ? 512 : kAccCols;
   const int mb_max = p.acc_cols / p.NT;
   // column bands: the TMA box row is PW pixels = 2*PW 8-byte elements and a box dimension holds <= 256 elements
@@ -572,7 +578,7 @@ int plan_tc(TcParams& p, int N, int C_in, int bias_floats, const char* what, int
     const int tiles = ceil_div(blocks, mb_max);
     p.MB = ceil_div(blocks, tiles);
   }
-  if (const char* e = getenv("UNCL_PROBE_MB")) {   // timing probe: force the M blocks per tile
+  if (const char* e = probe_env("UNCL_PROBE_MB")) {   // timing probe: force the M blocks per tile
     const int want = atoi(e);
     if (want >= 1 && want < p.MB) p.MB = want;
   }
@@ -586,7 +592,7 @@ int plan_tc(TcParams& p, int N, int C_in, int bias_floats, const char* what, int
   const int budget = 227 * 1024 - tail;
   // pointwise GEMMs are short, latency-bound launches: fewer, fatter pipeline stages (up to 64 input channels) cut the
   // issuing warp's barrier round trips - as long as four stages still fit
-  if (p.ntaps == 1 && getenv("UNCL_PROBE_PW_KSTEPS1") == nullptr) {
+  if (p.ntaps == 1 && probe_env("UNCL_PROBE_PW_KSTEPS1") == nullptr) {
     for (int ks = 4; ks > 1; ks >>= 1) {
       const int sb = ((2 * ks * p.PH * p.PW * 16 + 127) & ~127) + ks * 2 * p.NT * 16;
       if (p.nchunk % ks == 0 && 4 * sb <= budget) { p.ksteps = ks; break; }
@@ -612,30 +618,21 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
   int smem_bytes = 0;
   if (int rc = plan_tc(p, N, C_in, bias_floats, what, &smem_bytes)) return rc;
 
-  EncodeTiledFn encode = get_encode();
-  if (!encode) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled unavailable", what);
-  CUtensorMap tmap;
   // 4-D map over 8-byte elements: (x*2 + half, y, channel block, image); one pixel's 8 bf16 channels = 2 elements,
   // so a box row is PW*16 contiguous bytes in global memory (full 32-byte sectors) and lands pixel-major in smem.
-  const cuuint64_t gdim[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)(C_in / 8), (cuuint64_t)N};
-  const cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)in_img_stride * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)p.PW * 2, (cuuint32_t)p.PH, (cuuint32_t)(2 * p.ksteps), 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(in), gdim, gstr, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUtensorMap tmap;
+  CUresult r = encode_blocked_bf16(&tmap, in, W, H, C_in / 8, N, in_img_stride, p.PW, p.PH, 2 * p.ksteps);
   if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
 
   if (p.ns_per_group <= 0) p.ns_per_group = p.NS;
   p.dbg = g_dbg;
-  p.probe_noload = getenv("UNCL_PROBE_NOLOAD") != nullptr ? 1 : 0;
-  if (const char* e = getenv("UNCL_PROBE_FLAGS")) p.probe_noload = atoi(e);
+  p.probe_noload = probe_env("UNCL_PROBE_NOLOAD") != nullptr ? 1 : 0;
+  if (const char* e = probe_env("UNCL_PROBE_FLAGS")) p.probe_noload = atoi(e);
   auto kern = epi == 0 ? conv3x3_tc_kernel<0> : (epi == 1 ? conv3x3_tc_kernel<1> : conv3x3_tc_kernel<2>);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  static thread_local int smem_ok[3] = {0, 0, 0}, smem_dev[3] = {-1, -1, -1};
+  cudaError_t e = ensure_smem(kern, smem_bytes, smem_ok[epi], smem_dev[epi]);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const int grid = p.num_items < sms ? p.num_items : sms;
   kern<<<grid, kThreads, smem_bytes, stream>>>(tmap, p);
   return uncl_check_launch(what);
@@ -653,7 +650,7 @@ int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void
 // K loop is long enough to hide its heavier epilogue (C_in >= 64: 500 -> 327 us, 253 -> 155 us, 184 -> 113 us) and loses
 // on the C_in = 32 layers, which are epilogue-bound either way.
 static bool use_merged(int C_in, int C_out) {
-  const char* e = getenv("UNCL_MERGED_MIN_CI");
+  const char* e = probe_env("UNCL_MERGED_MIN_CI");
   return C_out <= 64 && C_in % 32 == 0 && C_in >= (e ? atoi(e) : 64);
 }
 
@@ -675,7 +672,7 @@ extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w
   }
   TcParams p{};
   p.NT = C_out < 128 ? C_out : 128;
-  if (C_out == 256 && getenv("UNCL_PROBE_NT256") != nullptr) p.NT = 256;   // timing probe (weights packed by the caller)
+  if (C_out == 256 && probe_env("UNCL_PROBE_NT256") != nullptr) p.NT = 256;   // timing probe (weights packed by the caller)
   UNCL_REQUIRE(C_out % p.NT == 0 && C_out <= 1024, "conv3x3_tc: unsupported C_out=%d", C_out);
   UNCL_REQUIRE(out_dtype == UNCL_F32 || out_dtype == UNCL_BF16, "conv3x3_tc: bad out_dtype");
   UNCL_REQUIRE(!fuse_outc || (C_out == 32 && outc_w && outc_b && out_img), "conv3x3_tc: fuse_outc needs C_out == 32 and outc params");
@@ -780,8 +777,15 @@ extern "C" int uncl_conv3x3_tc_plan(int N, int C_in, int H, int W, int C_out, in
 // Diagnostics: when set (device pointer to 8 zeroed uint64), every tensor-core conv launch adds, summed over its CTAs,
 // [0] producer cycles, [1] producer wait-for-empty-stage, [2] MMA-issuer cycles, [3] its wait-for-full-stage,
 // [4] its wait-for-free-accumulator, [5] epilogue-warp cycles, [6] its wait-for-accumulator, [7] CTA count.
-// Not thread-safe, not for production use (the only mutable global of the library); pass NULL to switch off.
+// Exists only in the -DUNCL_PROBES build (tools/): the product library has no mutable global and returns
+// UNCL_EUNSUPPORTED here.  Not thread-safe; pass NULL to switch off.
 extern "C" int uncl_conv_tc_set_debug(void* counters) {
+#ifdef UNCL_PROBES
   g_dbg = reinterpret_cast<unsigned long long*>(counters);
   return UNCL_OK;
+#else
+  (void)counters;
+  return uncl_set_error(UNCL_EUNSUPPORTED, "conv_tc_set_debug: this library was built without -DUNCL_PROBES "
+                                           "(python -m uncltmo_b200.build --probes)");
+#endif
 }

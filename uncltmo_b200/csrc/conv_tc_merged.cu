@@ -109,7 +109,7 @@ __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_ba
   const int nacc = p.nacc, acc_cols = p.acc_cols, nchunk = p.nchunk, stages = p.stages, num_items = p.num_items;
   int stage = 0, acc = 0;
   uint32_t phase = 0, acc_phase = 0;
-  unsigned long long* const dbg = p.dbg;
+  unsigned long long* const dbg = UNCL_PROBE(1, 1) ? p.dbg : nullptr;
   long long w_full = 0, w_tempty = 0;
   const long long t_begin = dbg ? clock64() : 0;
   for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -121,7 +121,7 @@ __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_ba
     const uint32_t d0 = tmem_base + (uint32_t)(acc * acc_cols);
     for (int ch = 0; ch < nchunk; ++ch) {
       const long long tw1 = dbg ? clock64() : 0;
-      if (!(p.probe_noload & 4)) mbar_wait(&full[stage], phase);
+      if (!(UNCL_PROBE(p.probe_noload, 4))) mbar_wait(&full[stage], phase);
       if (dbg) w_full += clock64() - tw1;
       tc_fence_after();
       const uint32_t sa16 = stage0_16 + (uint32_t)stage * stage_16;
@@ -141,7 +141,7 @@ __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_ba
             }
           }
         }
-        if (!(p.probe_noload & 4)) tc_commit(&empty[stage]);
+        if (!(UNCL_PROBE(p.probe_noload, 4))) tc_commit(&empty[stage]);
       }
       __syncwarp();
       if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -202,19 +202,19 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
       const uint32_t tx_bytes = (uint32_t)(p.a_box_bytes + p.b_stage_bytes), b_bytes = (uint32_t)p.b_stage_bytes;
       const int a_stage_bytes = p.a_stage_bytes;
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
-      unsigned long long* const dbg = p.dbg;
+      unsigned long long* const dbg = UNCL_PROBE(1, 1) ? p.dbg : nullptr;
       long long w_empty = 0;
       const long long t_begin = dbg ? clock64() : 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const MgItem it = mg_decode(p, item);
         const uint8_t* wsrc = wbase + (size_t)it.ns * nchunk * b_bytes;
         for (int ch = 0; ch < nchunk; ++ch) {
-          if (p.probe_noload & 4) continue;
+          if (UNCL_PROBE(p.probe_noload, 4)) continue;
           const long long tw0 = dbg ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1);
           if (dbg) w_empty += clock64() - tw0;
           uint8_t* sa = stage_base + (size_t)stage * stage_bytes;
-          if ((p.probe_noload & 1) && (item != (int)blockIdx.x || ch >= stages)) { mbar_arrive(&full[stage]); }
+          if ((UNCL_PROBE(p.probe_noload, 1)) && (item != (int)blockIdx.x || ch >= stages)) { mbar_arrive(&full[stage]); }
           else {
           mbar_expect_tx(&full[stage], tx_bytes);
           tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, ch * 2 * p.ksteps, it.n);
@@ -270,7 +270,7 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     const int cb0 = c * 32 + h * 16;   // first channel of this warp inside the N split
     int acc = 0, par = 0;
     uint32_t acc_phase = 0;
-    unsigned long long* const dbg = (warp == 2 && lane == 0) ? p.dbg : nullptr;
+    unsigned long long* const dbg = (UNCL_PROBE(1, 1) && warp == 2 && lane == 0) ? p.dbg : nullptr;
     long long w_tfull = 0;
     const long long t_begin = dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -288,7 +288,7 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);   // everything this warp needs is in registers: release the accumulator
-      if (p.probe_noload & 2) { par ^= 1; if (++acc == nacc) { acc = 0; acc_phase ^= 1; } continue; }
+      if (UNCL_PROBE(p.probe_noload, 2)) { par ^= 1; if (++acc == nacc) { acc = 0; acc_phase ^= 1; } continue; }
       float* const xpar = xbuf + par * (kUnits * 4 * kXSlot);
       // lanes 0 and 1 publish what the previous warp's lanes 30 / 31 need ...
       if (lane < 2) {
@@ -398,6 +398,11 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 }  // namespace
 
 namespace {
+#ifdef UNCL_PROBES
+static const char* probe_env(const char* name) { return getenv(name); }
+#else
+static const char* probe_env(const char*) { return nullptr; }   // the product library reads no environment variable
+#endif
 // tile geometry and pipeline sizing: pure host arithmetic (no CUDA calls), shared with uncl_plan_conv3x3_tc_merged
 int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int fuse_outc, const char* what, int* smem_bytes_out) {
   p.NT = C_out < 64 ? C_out : 64;
@@ -417,7 +422,7 @@ int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
   p.MB = p.acc_cols / p.NP;   // 2 blocks of 96 columns or 1 block of 192: always two 32-channel work units per tile
   p.ADV = 128 * p.MB - 2;
   int bw_max = 126;
-  if (const char* e = getenv("UNCL_MG_BW")) { const int want = atoi(e); if (want >= 8 && want < bw_max) bw_max = want; }
+  if (const char* e = probe_env("UNCL_MG_BW")) { const int want = atoi(e); if (want >= 8 && want < bw_max) bw_max = want; }
   const int nbands = ceil_div(p.Wo, bw_max);
   p.BW = ceil_div(p.Wo, nbands);
   p.PW = p.BW + 2;
@@ -439,7 +444,7 @@ int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
   const int budget = 227 * 1024 - tail;
   p.stages = budget / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
-  if (const char* e = getenv("UNCL_MG_STAGES")) { const int want = atoi(e); if (want >= 2 && want < p.stages) p.stages = want; }
+  if (const char* e = probe_env("UNCL_MG_STAGES")) { const int want = atoi(e); if (want >= 2 && want < p.stages) p.stages = want; }
   UNCL_REQUIRE(p.stages >= 2, "%s: tile does not fit shared memory (%d B per stage)", what, p.stage_bytes);
   int smem_bytes = p.stages * p.stage_bytes + tail;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM (each owns all 512 TMEM columns)
@@ -477,13 +482,12 @@ int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void
   CUresult r = encode_blocked_bf16(&tmap, in, W, H, C_in / 8, N, in_img_stride, p.PW, p.PH, 2 * p.ksteps);
   if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
   p.dbg = dbg;
-  p.probe_noload = getenv("UNCL_PROBE_NOLOAD") != nullptr ? 1 : 0;   // bit 0: no loads, 1: no epilogue work, 2: MMA free-runs
-  if (const char* e = getenv("UNCL_PROBE_FLAGS")) p.probe_noload = atoi(e);
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_merged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  p.probe_noload = probe_env("UNCL_PROBE_NOLOAD") != nullptr ? 1 : 0;   // bit 0: no loads, 1: no epilogue work, 2: MMA free-runs
+  if (const char* e = probe_env("UNCL_PROBE_FLAGS")) p.probe_noload = atoi(e);
+  static thread_local int smem_ok = 0, smem_dev = -1;
+  cudaError_t e = ensure_smem(conv3x3_tc_merged_kernel, smem_bytes, smem_ok, smem_dev);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const int grid = p.num_items < sms ? p.num_items : sms;
   conv3x3_tc_merged_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap, p);
   return uncl_check_launch(what);

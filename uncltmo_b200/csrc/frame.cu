@@ -580,13 +580,18 @@ extern "C" int uncl_percentile_pair(const float* data, long n, float clamp_lo, f
   const SelRanks ranks = {{(unsigned)k0, (unsigned)(k0 + 1), (unsigned)k1, (unsigned)(k1 + 1)}};
   const double t0 = v0 - (double)k0, t1 = v1 - (double)k1;
   // fused path: one cooperative launch when every CTA's slice of keys fits in its shared memory
+#ifdef UNCL_PROBES
+  const bool force_3pass = getenv("UNCL_SELECT_3PASS") != nullptr;   // probe build only
+#else
+  const bool force_3pass = false;
+#endif
   {
     int dev = 0, sms = 148, coop = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     long per_cta = ((n + sms - 1) / sms + 3) & ~3L;
-    if (coop && per_cta <= kFusedMaxKeys && (reinterpret_cast<uintptr_t>(data) & 15) == 0 && getenv("UNCL_SELECT_3PASS") == nullptr) {
+    if (coop && per_cta <= kFusedMaxKeys && (reinterpret_cast<uintptr_t>(data) & 15) == 0 && !force_3pass) {
       const size_t smem = (size_t)((kSelQ << 11) + per_cta) * sizeof(unsigned);
       cudaError_t e = cudaFuncSetAttribute(select_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "percentile_pair: smem attr: %s", cudaGetErrorString(e));

@@ -4,6 +4,15 @@
 
 #include "common.cuh"
 
+// Timing probes and per-role cycle counters exist only in the `-DUNCL_PROBES` build that tools/ uses
+// (`python -m uncltmo_b200.build --probes` -> libuncltmo_b200_probes.so); the product library carries none of them,
+// reads no environment variable and keeps no mutable global.
+#ifdef UNCL_PROBES
+#define UNCL_PROBE(flags, bit) ((flags) & (bit))
+#else
+#define UNCL_PROBE(flags, bit) 0
+#endif
+
 namespace tcptx {
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -129,17 +138,60 @@ inline EncodeTiledFn get_encode() {
 
 // 4-D tensor map over 8-byte elements of a C8-blocked bf16 tensor: (2*x + half, y, channel block, image).
 // One pixel's 8 channels are 2 elements, so a box row of `box_w` pixels is box_w*16 contiguous bytes.
+// Encoded maps are kept in a small thread-local direct-mapped cache keyed on (pointer, shape, box): a network replays
+// the same ~60 (tensor, tile) pairs every step and the driver call is the most expensive host work of a launch.
+struct TmapKey {
+  const void* base; long stride; int W, H, Cb, N, bw, bh, bc;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && stride == o.stride && W == o.W && H == o.H && Cb == o.Cb && N == o.N && bw == o.bw &&
+           bh == o.bh && bc == o.bc;
+  }
+};
 inline CUresult encode_blocked_bf16(CUtensorMap* tmap, const void* base, int W, int H, int Cb, int N, long img_stride_elems,
                                     int box_w, int box_h, int box_cb) {
+  constexpr int kSlots = 256;
+  struct Slot { TmapKey key; CUtensorMap map; bool used; };
+  static thread_local Slot cache[kSlots];
+  const TmapKey key{base, img_stride_elems, W, H, Cb, N, box_w, box_h, box_cb};
+  size_t hsh = reinterpret_cast<uintptr_t>(base) >> 8;
+  hsh = hsh * 1000003u ^ (size_t)(W * 131 + H * 31 + Cb * 7 + box_w * 3 + box_h + box_cb * 17 + N * 1009) ^ (size_t)img_stride_elems;
+  Slot& slot = cache[hsh % kSlots];
+  if (slot.used && slot.key == key) { *tmap = slot.map; return CUDA_SUCCESS; }
   EncodeTiledFn encode = get_encode();
   if (!encode) return CUDA_ERROR_NOT_SUPPORTED;
   const cuuint64_t gdim[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)Cb, (cuuint64_t)N};
   const cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)img_stride_elems * 2};
   const cuuint32_t box[4] = {(cuuint32_t)box_w * 2, (cuuint32_t)box_h, (cuuint32_t)box_cb, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  return encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(base), gdim, gstr, box, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) { slot.key = key; slot.map = *tmap; slot.used = true; }
+  return r;
+}
+
+// SM count of the current device (thread-local cache: one attribute query per thread and device)
+inline int sm_count() {
+  static thread_local int cached_dev = -1, cached_sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+  }
+  return cached_sms;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (thread, device, kernel): `state` is a thread_local int of the
+// caller holding the largest size already granted on `state_dev`
+template <typename K>
+inline cudaError_t ensure_smem(K kern, int smem_bytes, int& state, int& state_dev) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev == state_dev && smem_bytes <= state) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) { state = 227 * 1024; state_dev = dev; }
+  return e;
 }
 
 }  // namespace tcptx

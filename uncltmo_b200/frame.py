@@ -183,18 +183,29 @@ class FramePipeline:
         col = self.postprocess(fake_p, rgb, stats, pl)
         return self.to_uint8(col) if uint8 else col
 
-    def tonemap_host_frames(self, host_frames, lam, out=None):
+    def tonemap_host_frames(self, host_frames, lam, out=None, sync=True):
         """Stream pinned HOST frames through the path: [3,H,W] fp32 each -> HWC uint8 host tensors.
 
         The host->device copy of frame i+1 and the device->host copy of result i-1 run on their own streams while
         frame i computes (double-buffered device staging), so a long sequence costs max(copy, compute) per frame.
-        Every frame's input and output still cross PCIe inside the call."""
+        Every frame's input and output still cross PCIe inside the call.
+
+        sync=True (default): the call returns when the LAST device->host copy has landed - the returned host tensors are
+        complete and may be read or saved at once.  sync=False returns while copies are still in flight; the caller must
+        wait on `self.last_d2h_event` (or synchronise the device) before touching the results."""
         if not host_frames:
             return []
         dev = next(self.g.parameters()).device
         compute = torch.cuda.current_stream(dev)
-        h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        if getattr(self, "_copy_streams", None) is None or self._copy_streams[0].device != dev:
+            self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        h2d, d2h = self._copy_streams
         stage = [torch.empty(host_frames[0].shape, device=dev, dtype=torch.float32) for _ in range(2)]
+        # the staging buffers come from the compute stream's allocator pool: kernels queued there by an earlier call may
+        # still be reading the blocks they were carved from, so the first upload must order itself after them
+        h2d.wait_stream(compute)
+        for t in stage:
+            t.record_stream(h2d)
         ready = [torch.cuda.Event() for _ in range(2)]     # staging buffer i holds a fresh frame
         free = [torch.cuda.Event() for _ in range(2)]      # staging buffer i has been consumed
         results = []
@@ -222,7 +233,11 @@ class FramePipeline:
                 out[i].copy_(u8, non_blocking=True)
                 u8.record_stream(d2h)
             results.append(out[i])
+        self.last_d2h_event = torch.cuda.Event()
+        self.last_d2h_event.record(d2h)
         compute.wait_stream(d2h)
+        if sync:
+            self.last_d2h_event.synchronize()   # blocks the HOST: the pinned results are complete on return
         return results
 
     def tonemap_clip(self, frames, lam, uint8=False, shard_tiles=False):

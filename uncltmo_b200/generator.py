@@ -10,8 +10,6 @@ precision:
   "bf16" - bf16 activations; the 3x3 convolutions run on tcgen05 tensor cores (conv_tc.cu), fp32 accumulation;
            the KNN graph of the bottleneck stays fp32 (rel-L2 <= 1e-2).
 """
-import os
-
 import torch
 import torch.nn as nn
 
@@ -133,8 +131,6 @@ class _GeneratorBase(nn.Module):
 
         with torch.no_grad():
             P["inc0"] = (packing.conv_first(self.inc.conv.conv.weight.detach()), self.inc.conv.conv.bias.detach().float().contiguous())
-            if tc and self.inc.conv.conv.weight.shape[0] == 32:   # first conv on the tensor cores (three-term bf16 split)
-                P["inc0_tc"] = packing.conv_first_tc_split(self.inc.conv.conv.weight.detach())
             conv("inc1", self.inc.conv.conv1, False)
             for i in range(4):
                 blk = self.down_path[i].mpconv[1]
@@ -200,12 +196,7 @@ class _GeneratorBase(nn.Module):
         sizes = [(f, 252), (2 * f, 122), (4 * f, 57), (8 * f, 24)]
         cat = [buf(4 * c, s, s) for c, s in sizes]
         a0 = buf(f, 254, 254)
-        # measured (tools/convt_bench.py): the tensor-core variant is instruction-bound by its own im2col build + epilogue
-        # (81 us vs 74 us for the CUDA-core kernel on 60 tiles), so it is opt-in
-        if "inc0_tc" in P and os.environ.get("UNCL_CONV_FIRST_TC") is not None:
-            call("uncl_conv_first_tc", x, P["inc0_tc"], P["inc0"][1], a0, st(a0), n, 256, 256, f, ACT_RELU)
-        else:
-            call("uncl_conv_first", x, P["inc0"][0], P["inc0"][1], a0, st(a0), n, 256, 256, f, ACT_RELU, dt)
+        call("uncl_conv_first", x, P["inc0"][0], P["inc0"][1], a0, st(a0), n, 256, 256, f, ACT_RELU, dt)
         self._conv3(P, "inc1", a0, st(a0), cat[0], st(cat[0]), n, f, 254, 254, f, 0, emit_skip=1)
         state = [cat[0]]  # tensors whose first C/32 channels feed the next frame (Unet.py:229,251,264,272)
         cur, cur_c, cur_s = cat[0], f, 252

@@ -4,8 +4,6 @@ These run on the device with torch tensor ops when weights are (re)loaded - plum
 Reference weight layouts: nn.Conv2d [C_out, C_in, kH, kW]; nn.ConvTranspose2d [C_in, C_out, kH, kW]
 (SURVEY.md Appendix B).
 """
-import os
-
 import torch
 
 
@@ -19,7 +17,16 @@ def conv3x3_taps(w, transposed):
     return w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]).contiguous().float()
 
 
-MERGED_MIN_CI = int(os.environ.get("UNCL_MERGED_MIN_CI", "64"))   # must match conv_tc.cu:use_merged()
+def conv3x3_tc_is_merged(ci, co):
+    """True when uncl_conv3x3_tc routes a (C_in, C_out) layer to the kx-merged kernel.  Asked of the library itself
+    (uncl_conv3x3_tc_plan is pure host arithmetic), so the packing can never drift from conv_tc.cu:use_merged()."""
+    import ctypes
+    from . import _lib
+    plan = (ctypes.c_int * 16)()
+    rc = _lib.lib().uncl_conv3x3_tc_plan(1, ci, 64, 64, co, 0, ctypes.cast(plan, ctypes.c_void_p))
+    if rc != 0:
+        raise RuntimeError("uncl_conv3x3_tc_plan failed (%d): %s" % (rc, _lib.lib().uncl_last_error().decode()))
+    return plan[0] == 1
 
 
 def conv3x3_tc(w9):
@@ -29,7 +36,7 @@ def conv3x3_tc(w9):
         [NS][C_in/16][3 ky][2][3*NT (kx, n)][8], NT = min(C_out, 64)
     wider layers (conv_tc.cu, one tap per MMA): [NS][C_in/16][9][2][NT][8], NT = min(C_out, 128)."""
     _, ci, co = w9.shape
-    if co <= 64 and ci % 32 == 0 and ci >= MERGED_MIN_CI:
+    if conv3x3_tc_is_merged(ci, co):
         nt = min(co, 64)
         ns = co // nt
         t = w9.reshape(3, 3, ci // 16, 2, 8, ns, nt)       # ky, kx, chunk, half, k8, ns, n
@@ -87,18 +94,6 @@ def pointwise_tc_split(w):
 def conv_first(w):
     """Conv2d(1, C_out, 3) weight [C_out][1][3][3] -> [9][C_out] fp32."""
     return w.reshape(w.shape[0], 9).t().contiguous().float()
-
-
-def conv_first_tc_split(w):
-    """Conv2d(1, 32, 3) weight [32][1][3][3] -> the B operand of uncl_conv_first_tc: bf16 [4][32][8], K slot k = 8*g + j:
-    k < 9: w_hi[tap k]; 9 <= k < 18: w_lo[tap k-9]; 18 <= k < 27: w_hi[tap k-18]; zero above (pairs with the kernel's
-    [x_hi | x_hi | x_lo] rows)."""
-    w9 = conv_first(w)                                   # [9][C_out] fp32
-    hi = w9.to(torch.bfloat16)
-    lo = (w9 - hi.float()).to(torch.bfloat16)
-    k = torch.zeros((32, w9.shape[1]), device=w.device, dtype=torch.bfloat16)
-    k[0:9], k[9:18], k[18:27] = hi, lo, hi
-    return k.reshape(4, 8, w9.shape[1]).permute(0, 2, 1).contiguous()
 
 
 def blocked_param(t):
