@@ -58,6 +58,16 @@ int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w_packed, co
                     int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b, float* out_img,
                     float* out_logit, uncl_stream_t stream);
 
+/* Data gradient of the same operator with the ReLU backward of the PRODUCING layer fused into the epilogue:
+ * out = corr(dZ, w_packed) * (mask > 0).  in = dZ bf16 blocked; w_packed = packing.conv3x3_tc of the flipped / transposed
+ * taps; pad = 2 - (forward pad); mask = the forward INPUT of the conv (post-ReLU output of the previous layer, bf16 blocked,
+ * C_out channels, image stride mask_img_stride elements; NULL = no mask).  out: bf16 or fp32 blocked - the previous
+ * layer's pre-activation gradient, ready to be the operand of its own gradient GEMMs.  torch autograd of
+ * unet_parts.py:57-87 / 183-193 (conv -> ReLU chains). */
+int uncl_conv3x3_tc_dgrad(const void* in, long in_img_stride, const void* w_packed, const void* mask, long mask_img_stride,
+                          void* out, long out_img_stride, int out_dtype, int N, int C_in, int H, int W, int C_out, int pad,
+                          uncl_stream_t stream);
+
 /* Tile plan uncl_conv3x3_tc would use for a problem: pure host arithmetic, callable without a GPU (tests check the tile
  * coverage and that uncltmo_b200/packing.py packs the weights for the kernel the library will pick).
  * plan[16] = { kind (0: one tap per MMA, conv_tc.cu; 1: kx-merged, conv_tc_merged.cu), NT, NS, MMA N, M blocks per tile,
@@ -138,6 +148,11 @@ int uncl_pw_conv_tc(const void* in, long in_img_stride, const void* w_packed, co
                     long res_img_stride, int res_dtype, const float* scale, void* out, long out_img_stride,
                     int out_dtype, int N, int C_in, int C_out, int groups, int H, int W, int act,
                     uncl_stream_t stream);
+
+/* Pointwise data gradient with a fused ReLU mask (see uncl_conv3x3_tc_dgrad): dX of the k2 s2 up-convolution. */
+int uncl_pw_conv_tc_dgrad(const void* in, long in_img_stride, const void* w_packed, const void* mask, long mask_img_stride,
+                          void* out, long out_img_stride, int out_dtype, int N, int C_in, int C_out, int groups, int H, int W,
+                          uncl_stream_t stream);
 
 /* ---- frame path (utils/model_save_util.py, utils/hdr_image_util.py, utils/data_loader_util.py) ---- */
 
@@ -261,6 +276,49 @@ int uncl_gcn_agg_bwd(const float* dz, const float* y, const int* idx, float* dy,
 /* outconv + sigmoid backward; dw / db zeroed by the caller */
 int uncl_outc_sigmoid_bwd(const float* d_out, const float* out, const float* up, long up_img_stride, const float* w,
                           float* d_up, float* dw, float* db, int N, int C, int HW, uncl_stream_t stream);
+
+/* ---- bf16-activation training path (uncltmo_b200/train_graph.py): every activation and pre-activation gradient of the
+ * generator is a C8-blocked bf16 tensor; these are the places where gradient paths meet or a layout changes ---- */
+
+/* Gradient of a skip tensor x2 (post-ReLU output of an encoder conv; lives in its concat buffer, image stride
+ * x2_img_stride): dz = (x2 > 0) * (dcat[0:C] + 2 x2 dcat[2C:3C] + 0.5 dcat[3C:4C] / sqrt(x2 + 1e-8) + maxpool2_bwd(dpool)),
+ * i.e. the backward of cat([x2, x1, x2^2, sqrt(x2+1e-8)]) (unet_parts.py:319-322), of MaxPool2d(2) (:210-213; first
+ * maximum in row-major order takes the gradient) and of the ReLU of the layer that produced x2, in one pass.
+ * dcat: bf16 dense [N][4C/8][H][W][8] or NULL; dpool: bf16 dense [N][C/8][H/2][W/2][8] or NULL; dz: bf16 dense;
+ * db[C] += column sums of dz (NULL to skip). */
+int uncl_skip_pool_bwd(const void* x2, long x2_img_stride, const void* dcat, const void* dpool, void* dz, float* db, int N,
+                       int C, int H, int W, uncl_stream_t stream);
+/* db[c] += sum over images and pixels of a bf16 blocked tensor (bias gradient of a conv whose dz a GEMM epilogue wrote) */
+int uncl_bias_grad_bf16(const void* dz, long img_stride, float* db, int N, int C, int HW, uncl_stream_t stream);
+/* bf16 form of uncl_convT2x2_s2d reading a channel slice of the concat gradient (image stride dy_img_stride);
+ * db[C] += the up-convolution's bias gradient (NULL to skip). */
+int uncl_convT2x2_s2d_bf16(const void* dY, long dy_img_stride, void* out, float* db, int N, int C, int H, int W, int H2,
+                           int W2, uncl_stream_t stream);
+/* 1x1 out conv + sigmoid backward (unet_parts.py:338-345, Unet_singleFrame.py:207-209) merged with the gradient that
+ * arrives through the feature output and the ReLU of up_path.3.conv.conv1:  dl = d_out * o * (1 - o);
+ * dz[c] = up[c] > 0 ? dl * w[c] + d_feat[c] : 0 (bf16 dense);  dw[c] += sum dl * up[c];  db_out += sum dl;
+ * db_up[c] += sum dz[c].  d_out (fp32 [N][HW]) and d_feat (bf16 blocked dense) may each be NULL.  C = 32. */
+int uncl_outc_feat_bwd(const float* d_out, const float* out, const void* up, long up_img_stride, const void* d_feat,
+                       const float* w, void* dz, float* dw, float* db_out, float* db_up, int N, int C, int HW,
+                       uncl_stream_t stream);
+/* dst_bf16[i] = bf16(src[idx[i]]); idx bit 30 set: the bf16 residual src - bf16(src) instead (`lo` half of a split-bf16
+ * operand); idx < 0: zero.  One launch re-lays out every weight of the generator for the forward and the data-gradient
+ * GEMMs (index maps from uncltmo_b200/packing.py, built once). */
+int uncl_pack_gather(const float* src, const int* idx, void* dst_bf16, long n, uncl_stream_t stream);
+/* dst[i] = src[idx[i]] (idx < 0: dst untouched): fp32 gather, e.g. GEMM-layout weight gradients -> parameter layout. */
+int uncl_unpack_gather(const float* src, const int* idx, float* dst, long n, uncl_stream_t stream);
+/* GanTrainer.nce as infoNCE2 calls it (GanTrainerImg.py:384-439): positive / negative are rows sel[0] / sel[1] (device
+ * int64) of the anchor tensor itself, broadcast over the batch.  fea: bf16 [B][CHW] in ANY element order (the
+ * similarity is a sum over all elements).  logits_scratch: 2*B floats (kept for the backward). */
+int uncl_nce_self_fwd(const void* fea, const long* sel, int B, long CHW, int HW, float k, float constant,
+                      float* logits_scratch, float* loss_out, uncl_stream_t stream);
+/* d_fea (bf16 or fp32, d_dtype): anchor gradient of every row + the batch-summed gradient of the two selected rows */
+int uncl_nce_self_bwd(const void* fea, const long* sel, int B, long CHW, int HW, float k, float constant,
+                      const float* logits, const float* g_up, void* d_fea, int d_dtype, uncl_stream_t stream);
+/* torch.optim.Adam's update (no amsgrad / weight decay) on one flat fp32 buffer; `step` is a device float, incremented
+ * by the call (bias corrections need no host value: capturable in a CUDA graph). */
+int uncl_adam_flat(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
+                   float* step, uncl_stream_t stream);
 
 /* ---- loss / discriminator backward.  `g_up` is the upstream gradient as a DEVICE scalar (no host sync). ---- */
 

@@ -62,6 +62,8 @@ struct TcParams {
   long res_img_stride;
   int res_f32;
   const float* scale;       // per-image factor (DropPath) or null
+  const bf16* mask;         // data-gradient mode: out = (mask > 0) ? acc : 0 - the ReLU of the layer that PRODUCED this
+  long mask_img_stride;     // conv's input, applied where its gradient is formed (blocked bf16, C_out channels, Ho x Wo)
   int ns_per_group;         // grouped 1x1 conv: N splits per group (K range of a split = its group's input channels)
   unsigned long long* dbg;  // diagnostics (uncl_conv_tc_set_debug): cycle counters of the three roles, or null
   unsigned long long m_PW;  // 2^40 / PW + 1 (fastdiv_pw)
@@ -320,6 +322,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     float* const out_img = p.out_img;
     float* const out_logit = p.out_logit;
     const float outc_b = fuse_outc ? __ldg(p.outc_b) : 0.f;
+    const bf16* const mask = p.mask;
+    const long mask_img_stride = p.mask_img_stride;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int nacc = p.nacc, acc_cols = p.acc_cols;
     int acc = 0;
@@ -355,6 +359,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 float v[8];
   #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[g * 8 + j]) + bias[g * 8 + j], act_floor);
+                if (mask != nullptr) {
+                  float m[8];
+                  load8(mask + (long)it.n * mask_img_stride + (long)(cbase0 / 8 + c0 / 8 + g) * cb_stride + pix * 8, m);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = m[j] > 0.f ? v[j] : 0.f;
+                }
                 if (out != nullptr) {
                   const long off = (long)it.n * out_img_stride + (long)(cbase0 / 8 + c0 / 8 + g) * cb_stride + pix * 8;
                   float s2[8], s3[8];
@@ -419,6 +429,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                   else load8(resb + (long)it.n * res_img_stride + cpix, rr);
 #pragma unroll
                   for (int j = 0; j < 8; ++j) v[j] += rr[j];
+                }
+                if (mask != nullptr) {
+                  float m[8];
+                  load8(mask + (long)it.n * mask_img_stride + cpix, m);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = m[j] > 0.f ? v[j] : 0.f;
                 }
                 const long off = (long)it.n * out_img_stride + cpix;
                 if (out_f32) store8(outf + off, v);
@@ -643,7 +659,8 @@ int launch_tc(TcParams& p, const void* in, long in_img_stride, int N, int C_in, 
 int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
                                   long out_img_stride, int out_f32, int N, int C_in, int H, int W, int C_out, int pad,
                                   int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
-                                  float* out_img, float* out_logit, unsigned long long* dbg, cudaStream_t stream);
+                                  float* out_img, float* out_logit, const void* mask, long mask_img_stride,
+                                  unsigned long long* dbg, cudaStream_t stream);
 
 // Which 3x3 layers run in the kx-merged kernel (conv_tc_merged.cu); packing.conv3x3_tc packs the weights to match.
 // Measured per layer of the 1080p frame (profiles/README.md): with C_out <= 64 the merged formulation wins when the
@@ -654,10 +671,10 @@ static bool use_merged(int C_in, int C_out) {
   return C_out <= 64 && C_in % 32 == 0 && C_in >= (e ? atoi(e) : 64);
 }
 
-extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
-                               long out_img_stride, int out_dtype, int N, int C_in, int H, int W, int C_out, int pad,
-                               int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
-                               float* out_img, float* out_logit, cudaStream_t stream) {
+static int conv3x3_tc_impl(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                           long out_img_stride, int out_dtype, int N, int C_in, int H, int W, int C_out, int pad,
+                           int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
+                           float* out_img, float* out_logit, const void* mask, long mask_img_stride, cudaStream_t stream) {
   UNCL_REQUIRE(N > 0 && C_in % 16 == 0 && C_out % 32 == 0 && (pad == 0 || pad == 2),
                "conv3x3_tc: unsupported C_in=%d C_out=%d pad=%d", C_in, C_out, pad);
   if (use_merged(C_in, C_out)) {
@@ -668,7 +685,7 @@ extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w
     UNCL_REQUIRE(H + 2 * pad - 2 > 0 && W + 2 * pad - 2 > 0, "conv3x3_tc: empty output");
     return uncl_launch_conv3x3_tc_merged(in, in_img_stride, w_packed, bias, out, out_img_stride, out_dtype == UNCL_F32, N, C_in,
                                          H, W, C_out, pad, act, emit_skip, fuse_outc, outc_w, outc_b, out_img, out_logit,
-                                         g_dbg, stream);
+                                         mask, mask_img_stride, g_dbg, stream);
   }
   TcParams p{};
   p.NT = C_out < 128 ? C_out : 128;
@@ -689,8 +706,32 @@ extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w
   p.Ho = H + 2 * pad - 2; p.Wo = W + 2 * pad - 2;
   UNCL_REQUIRE(p.Ho > 0 && p.Wo > 0, "conv3x3_tc: empty output");
   p.act = act; p.emit_skip = emit_skip; p.fuse_outc = fuse_outc;
+  p.mask = reinterpret_cast<const bf16*>(mask); p.mask_img_stride = mask_img_stride;
   p.ntaps = 9;
   return launch_tc(p, in, in_img_stride, N, C_in, H, W, 0, 2 * C_out, "conv3x3_tc", stream);
+}
+
+extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                               long out_img_stride, int out_dtype, int N, int C_in, int H, int W, int C_out, int pad,
+                               int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
+                               float* out_img, float* out_logit, cudaStream_t stream) {
+  return conv3x3_tc_impl(in, in_img_stride, w_packed, bias, out, out_img_stride, out_dtype, N, C_in, H, W, C_out, pad, act,
+                         emit_skip, fuse_outc, outc_w, outc_b, out_img, out_logit, nullptr, 0, stream);
+}
+
+// Data gradient of a 3x3 conv / ConvTranspose 3x3 with the ReLU backward of the PRODUCING layer fused into the epilogue:
+// dX = corr(dZ, flipped / transposed taps; pad 2 - p), then dX *= (mask > 0) where `mask` is that layer's (post-ReLU)
+// output = this conv's forward input.  The result is the pre-activation gradient dZ of the previous layer, written as
+// bf16 (the operand of its own data / weight gradient GEMMs) or fp32.  mask == NULL: plain data gradient.
+// in: dZ bf16 blocked [N][C_in/8][H][W][8]; w_packed: packing.conv3x3_tc of the transposed taps; mask: bf16 blocked with
+// C_out channels and the output extent, image stride mask_img_stride elements (it may live in a concat buffer).
+extern "C" int uncl_conv3x3_tc_dgrad(const void* in, long in_img_stride, const void* w_packed, const void* mask,
+                                     long mask_img_stride, void* out, long out_img_stride, int out_dtype, int N, int C_in,
+                                     int H, int W, int C_out, int pad, cudaStream_t stream) {
+  UNCL_REQUIRE(out != nullptr && (mask == nullptr || ((reinterpret_cast<uintptr_t>(mask) & 15) == 0 && mask_img_stride % 8 == 0)),
+               "conv3x3_tc_dgrad: bad output / mask");
+  return conv3x3_tc_impl(in, in_img_stride, w_packed, nullptr, out, out_img_stride, out_dtype, N, C_in, H, W, C_out, pad,
+                         UNCL_ACT_NONE, 0, 0, nullptr, nullptr, nullptr, nullptr, mask, mask_img_stride, stream);
 }
 
 // ConvTranspose2d(C, C, 2, stride=2) as a GEMM [pixels x C] . [C x 4C] with a pixel-shuffle epilogue.
@@ -721,10 +762,10 @@ extern "C" int uncl_convT2x2_tc(const void* in, long in_img_stride, const void* 
 // out = scale[n] * act(W x + b) + res.  gcn_lib/torch_nn.py:54-78 (BasicConv), torch_vertex.py:219-227, Unet_singleFrame.py:36-42;
 // also the data gradient of the k2 s2 up-convolution (a 4C -> C pointwise GEMM over the space-to-depth gradient).
 // in: bf16 blocked [N][C_in/8][H][W][8], W <= 128.  w_packed: bf16 [NS][C_in/g/16][2][NT][8], NT = min(C_out/g, 128).
-extern "C" int uncl_pw_conv_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, const void* res,
-                               long res_img_stride, int res_dtype, const float* scale, void* out, long out_img_stride,
-                               int out_dtype, int N, int C_in, int C_out, int groups, int H, int W, int act,
-                               cudaStream_t stream) {
+static int pw_conv_tc_impl(const void* in, long in_img_stride, const void* w_packed, const float* bias, const void* res,
+                           long res_img_stride, int res_dtype, const float* scale, void* out, long out_img_stride,
+                           int out_dtype, int N, int C_in, int C_out, int groups, int H, int W, int act, const void* mask,
+                           long mask_img_stride, cudaStream_t stream) {
   UNCL_REQUIRE(N > 0 && groups > 0 && C_in % (16 * groups) == 0 && C_out % (32 * groups) == 0 && W <= 128 && H > 0,
                "pw_conv_tc: unsupported C_in=%d C_out=%d groups=%d W=%d", C_in, C_out, groups, W);
   UNCL_REQUIRE((out_dtype == UNCL_F32 || out_dtype == UNCL_BF16) && out != nullptr, "pw_conv_tc: bad output");
@@ -746,8 +787,26 @@ extern "C" int uncl_pw_conv_tc(const void* in, long in_img_stride, const void* w
   p.N = N; p.C_in = C_in; p.C_out = C_out; p.pad = 0;
   p.Ho = H; p.Wo = W;
   p.act = act;
+  p.mask = reinterpret_cast<const bf16*>(mask); p.mask_img_stride = mask_img_stride;
   p.ntaps = 1;
   return launch_tc(p, in, in_img_stride, N, C_in, H, W, 2, 2 * C_out, "pw_conv_tc", stream);
+}
+
+extern "C" int uncl_pw_conv_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, const void* res,
+                               long res_img_stride, int res_dtype, const float* scale, void* out, long out_img_stride,
+                               int out_dtype, int N, int C_in, int C_out, int groups, int H, int W, int act,
+                               cudaStream_t stream) {
+  return pw_conv_tc_impl(in, in_img_stride, w_packed, bias, res, res_img_stride, res_dtype, scale, out, out_img_stride,
+                         out_dtype, N, C_in, C_out, groups, H, W, act, nullptr, 0, stream);
+}
+
+// Pointwise data gradient with the ReLU backward of the producing layer fused (see uncl_conv3x3_tc_dgrad): the k2 s2
+// up-convolution's dX = [space-to-depth dY (4C)] . W^T, masked by the decoder activation it up-sampled.
+extern "C" int uncl_pw_conv_tc_dgrad(const void* in, long in_img_stride, const void* w_packed, const void* mask,
+                                     long mask_img_stride, void* out, long out_img_stride, int out_dtype, int N, int C_in,
+                                     int C_out, int groups, int H, int W, cudaStream_t stream) {
+  return pw_conv_tc_impl(in, in_img_stride, w_packed, nullptr, nullptr, 0, UNCL_BF16, nullptr, out, out_img_stride, out_dtype,
+                         N, C_in, C_out, groups, H, W, UNCL_ACT_NONE, mask, mask_img_stride, stream);
 }
 
 int uncl_plan_conv3x3_tc_merged(int N, int C_in, int H, int W, int C_out, int pad, int* plan);

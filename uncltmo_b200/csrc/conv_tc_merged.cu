@@ -44,6 +44,8 @@ struct MgParams {
   const float* outc_b;
   float* out_img;
   float* out_logit;
+  const bf16* mask;         // data-gradient mode (uncl_conv3x3_tc_dgrad): out = (mask > 0) ? acc : 0
+  long mask_img_stride;
   int C_out, Ho, Wo, pad;
   int NT, NS, NP;           // channels per N split, N splits, MMA N = 3 * NT
   int MB, ADV;              // M blocks per tile, tile advance in positions (128 * MB - 2)
@@ -344,6 +346,12 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
           float o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[g * 8 + j] + bias[g * 8 + j], act_floor);
+          if (p.mask != nullptr) {
+            float m[8];
+            load8(p.mask + (long)it.n * p.mask_img_stride + (long)(cbase / 8 + g) * cb_stride + pix * 8, m);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = m[j] > 0.f ? o[j] : 0.f;
+          }
           if (out != nullptr) {
             const long off = (long)it.n * out_img_stride + (long)(cbase / 8 + g) * cb_stride + pix * 8;
             float s2[8], s3[8];
@@ -467,7 +475,8 @@ int uncl_plan_conv3x3_tc_merged(int N, int C_in, int H, int W, int C_out, int pa
 int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
                                   long out_img_stride, int out_f32, int N, int C_in, int H, int W, int C_out, int pad,
                                   int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
-                                  float* out_img, float* out_logit, unsigned long long* dbg, cudaStream_t stream) {
+                                  float* out_img, float* out_logit, const void* mask, long mask_img_stride,
+                                  unsigned long long* dbg, cudaStream_t stream) {
   const char* what = "conv3x3_tc(merged)";
   UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "%s: input must be 16-byte aligned", what);
   MgParams p{};
@@ -477,6 +486,7 @@ int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void
   p.bias = bias; p.out = out; p.out_f32 = out_f32; p.out_img_stride = out_img_stride;
   p.outc_w = outc_w; p.outc_b = outc_b; p.out_img = out_img; p.out_logit = out_logit;
   p.act = act; p.emit_skip = emit_skip; p.fuse_outc = fuse_outc;
+  p.mask = reinterpret_cast<const bf16*>(mask); p.mask_img_stride = mask_img_stride;
 
   CUtensorMap tmap;
   CUresult r = encode_blocked_bf16(&tmap, in, W, H, C_in / 8, N, in_img_stride, p.PW, p.PH, 2 * p.ksteps);

@@ -1,0 +1,435 @@
+// Elementwise / reduction kernels of the bf16-activation training path (uncltmo_b200/train_graph.py).
+//
+// The generator backward keeps every activation and every pre-activation gradient as a C8-blocked bf16 tensor, exactly
+// like the inference path.  The tensor-core kernels produce most of those gradients themselves (data gradient with the
+// ReLU mask of the producing layer fused, uncl_conv3x3_tc_dgrad); what is left are the places where several gradient
+// paths meet or a layout changes:
+//   * skip_pool_bwd : a skip tensor x2 receives gradient from the decoder's concat [x2 | up | x2^2 | sqrt(x2+eps)]
+//                     (unet_parts.py:319-322) and from the next encoder stage through MaxPool2d(2) (:210-213); both are
+//                     combined, masked by the ReLU of the layer that produced x2, written once as bf16, and the bias
+//                     gradient of that layer is reduced in the same pass.
+//   * convT2x2_s2d  : space-to-depth of the up-convolution's output gradient (a channel slice of the concat gradient),
+//                     replicate-pad fold included, + its bias gradient.
+//   * outc_feat_bwd : 1x1 out conv + sigmoid backward, merged with the gradient arriving through the feature output
+//                     (infoNCE2 on up_x, GanTrainerImg.py:384-408) and the ReLU mask of up3.conv1.
+//   * bias_grad     : column sums of a bf16 gradient tensor.
+//   * pack / unpack : all weights of a step re-laid out by ONE gather launch each (index maps built once on the host
+//                     from uncltmo_b200/packing.py), instead of ~60 torch permute/contiguous kernels per step.
+//   * nce (self)    : GanTrainer.nce for infoNCE2, positive / negative = rows of the anchor tensor chosen on the device.
+//   * adam_flat     : torch.optim.Adam's update on one flat parameter buffer.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void block_reduce8_atomic(float (&s)[8], float* dst, float* sm /* [8][32] */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = warp_sum(s[j]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[j * 32 + wid] = s[j];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = lane < nw ? sm[j * 32 + lane] : 0.f;
+      t = warp_sum(t);
+      if (lane == 0) atomicAdd(dst + j, t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// grid (chunks, N * C/8); every block reduces its share of db for one channel block
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) skip_pool_bwd_kernel(const bf16* __restrict__ x2, long x2_img_stride,
+                                                           const bf16* __restrict__ dcat, const bf16* __restrict__ dpool,
+                                                           bf16* __restrict__ dz, float* __restrict__ db, int C, int H,
+                                                           int W) {
+  __shared__ float sm[8 * 32];
+  const int Cb = C / 8, cb = blockIdx.y % Cb, n = blockIdx.y / Cb;
+  const int HW = H * W, Hp = H / 2, Wp = W / 2;
+  const bf16* xb = x2 + (long)n * x2_img_stride + (long)cb * HW * 8;
+  const bf16* g0 = dcat ? dcat + ((long)n * 4 * Cb + cb) * HW * 8 : nullptr;
+  const bf16* dp = dpool ? dpool + ((long)n * Cb + cb) * Hp * Wp * 8 : nullptr;
+  bf16* o = dz + ((long)n * Cb + cb) * HW * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < HW; i += gridDim.x * 256) {
+    const int y = i / W, x = i - y * W;
+    float a[8], g[8];
+    load8(xb + (long)i * 8, a);
+    if (g0 != nullptr) {
+      float d0[8], d2[8], d3[8];
+      load8(g0 + (long)i * 8, d0);
+      load8(g0 + ((long)2 * Cb * HW + i) * 8, d2);
+      load8(g0 + ((long)3 * Cb * HW + i) * 8, d3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = d0[j] + 2.f * a[j] * d2[j] + 0.5f * d3[j] * rsqrtf(a[j] + 1e-8f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    }
+    const int py = y >> 1, px = x >> 1;
+    if (dp != nullptr && py < Hp && px < Wp) {
+      // MaxPool2d(2) backward: the FIRST maximum of the window in row-major order takes the gradient (as PyTorch)
+      float v[4][8], d[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) load8(xb + ((long)(2 * py + (k >> 1)) * W + 2 * px + (k & 1)) * 8, v[k]);
+      load8(dp + ((long)py * Wp + px) * 8, d);
+      const int me = ((y & 1) << 1) | (x & 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int best = 0;
+        float bv = v[0][j];
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+          if (v[k][j] > bv) { bv = v[k][j]; best = k; }
+        if (best == me) g[j] += d[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      g[j] = a[j] > 0.f ? g[j] : 0.f;      // ReLU of the layer that produced x2
+      g[j] = __bfloat162float(__float2bfloat16_rn(g[j]));   // db sums what the gradient GEMMs will read
+      acc[j] += g[j];
+    }
+    store8(o + (long)i * 8, g);
+  }
+  if (db != nullptr) block_reduce8_atomic(acc, db + cb * 8, sm);
+}
+
+__global__ void __launch_bounds__(256) bias_grad_kernel(const bf16* __restrict__ dz, long img_stride, float* __restrict__ db,
+                                                       int C, int HW) {
+  __shared__ float sm[8 * 32];
+  const int Cb = C / 8, cb = blockIdx.y % Cb, n = blockIdx.y / Cb;
+  const bf16* d = dz + (long)n * img_stride + (long)cb * HW * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < HW; i += gridDim.x * 256) {
+    float v[8];
+    load8(d + (long)i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+  block_reduce8_atomic(acc, db + cb * 8, sm);
+}
+
+// out[n, pos*C + co, y, x] = sum over the replicate-padded copies of dY[n, co, 2y+dy, 2x+dx]; db[co] += everything
+__global__ void __launch_bounds__(256) convT2x2_s2d_bf16_kernel(const bf16* __restrict__ dY, long dy_img_stride,
+                                                               bf16* __restrict__ out, float* __restrict__ db, int C,
+                                                               int H, int W, int H2, int W2) {
+  __shared__ float sm[8 * 32];
+  const int Cb = C / 8, cb4 = blockIdx.y % (4 * Cb), n = blockIdx.y / (4 * Cb);
+  const int pos = cb4 / Cb, cb = cb4 - pos * Cb;
+  const int padT = (H2 - 2 * H) / 2, padL = (W2 - 2 * W) / 2;
+  const bf16* d = dY + (long)n * dy_img_stride + (long)cb * H2 * W2 * 8;
+  bf16* o = out + ((long)n * 4 * Cb + cb4) * H * W * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < H * W; i += gridDim.x * 256) {
+    const int y = i / W, x = i - y * W;
+    const int Y = 2 * y + (pos >> 1), X = 2 * x + (pos & 1);
+    const int y_lo = (Y == 0) ? 0 : Y + padT, y_hi = (Y == 2 * H - 1) ? H2 - 1 : Y + padT;
+    const int x_lo = (X == 0) ? 0 : X + padL, x_hi = (X == 2 * W - 1) ? W2 - 1 : X + padL;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int yy = y_lo; yy <= y_hi; ++yy)
+      for (int xx = x_lo; xx <= x_hi; ++xx) {
+        float v[8];
+        load8(d + ((long)yy * W2 + xx) * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += v[j];
+      }
+    store8(o + (long)i * 8, s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += s[j];
+  }
+  if (db != nullptr) block_reduce8_atomic(acc, db + cb * 8, sm);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// out conv (1x1, C = 32 -> 1) + sigmoid backward, merged with the feature-path gradient and the ReLU of `up`:
+//   dl = d_out * o * (1 - o);  dz[c] = up[c] > 0 ? dl * w[c] + d_feat[c] : 0
+//   dw[c] += sum dl * up[c];  db_out += sum dl;  db_up[c] += sum dz[c]
+// one thread per pixel; per-thread partial sums over a grid-stride loop, reduced once per block
+// ---------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) outc_feat_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ out,
+                                                           const bf16* __restrict__ up, long up_img_stride,
+                                                           const bf16* __restrict__ d_feat, const float* __restrict__ w,
+                                                           bf16* __restrict__ dz, float* __restrict__ dw,
+                                                           float* __restrict__ db_out, float* __restrict__ db_up, int HW,
+                                                           int N) {
+  __shared__ float s_acc[2 * C + 1];
+  for (int i = threadIdx.x; i <= 2 * C; i += 256) s_acc[i] = 0.f;
+  __syncthreads();
+  float wl[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) wl[c] = __ldg(w + c);
+  float a_dw[C], a_db[C], a_lb = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) { a_dw[c] = 0.f; a_db[c] = 0.f; }
+  const long total = (long)N * HW;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int p = (int)(i % HW), n = (int)(i / HW);
+    const float o = out[i];
+    const float dl = d_out ? d_out[i] * o * (1.f - o) : 0.f;
+    a_lb += dl;
+#pragma unroll
+    for (int cb = 0; cb < C / 8; ++cb) {
+      float u[8], g[8], f[8];
+      load8(up + (long)n * up_img_stride + ((long)cb * HW + p) * 8, u);
+      if (d_feat != nullptr) load8(d_feat + (((long)n * (C / 8) + cb) * HW + p) * 8, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = dl * wl[cb * 8 + j] + (d_feat != nullptr ? f[j] : 0.f);
+        v = u[j] > 0.f ? v : 0.f;
+        v = __bfloat162float(__float2bfloat16_rn(v));
+        g[j] = v;
+        a_dw[cb * 8 + j] = fmaf(dl, u[j], a_dw[cb * 8 + j]);
+        a_db[cb * 8 + j] += v;
+      }
+      store8(dz + (((long)n * (C / 8) + cb) * HW + p) * 8, g);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float s1 = warp_sum(a_dw[c]), s2 = warp_sum(a_db[c]);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_acc[c], s1); atomicAdd(&s_acc[C + c], s2); }
+  }
+  a_lb = warp_sum(a_lb);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[2 * C], a_lb);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) {
+    atomicAdd(dw + i, s_acc[i]);
+    if (db_up) atomicAdd(db_up + i, s_acc[C + i]);
+  }
+  if (threadIdx.x == 0) atomicAdd(db_out, s_acc[2 * C]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight packing / gradient unpacking by index map
+// ---------------------------------------------------------------------------------------------------------
+// idx bit 30: store the bf16 RESIDUAL w - bf16(w) (the `lo` term of a split-bf16 operand); bits 0-29: source element
+__global__ void __launch_bounds__(256) pack_gather_kernel(const float* __restrict__ src, const int* __restrict__ idx,
+                                                         bf16* __restrict__ dst, long n) {
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+    const int k = idx[i];
+    if (k < 0) { dst[i] = __float2bfloat16_rn(0.f); continue; }
+    const float v = __ldg(src + (k & 0x3fffffff));
+    const bf16 hi = __float2bfloat16_rn(v);
+    dst[i] = (k & 0x40000000) ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+  }
+}
+__global__ void __launch_bounds__(256) unpack_gather_kernel(const float* __restrict__ src, const int* __restrict__ idx,
+                                                           float* __restrict__ dst, long n) {
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+    const int k = idx[i];
+    if (k >= 0) dst[i] = __ldg(src + k);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// nce on one feature tensor whose positive / negative are two of its own rows (infoNCE2), any element layout
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float nce_term(float a, float q, float k, float c0) { return (a * q) / (c0 + k * fabsf(a - q)); }
+// d/da and d/dq of a*q / (c0 + k|a-q|)
+__device__ __forceinline__ void nce_grad(float a, float q, float k, float c0, float& da, float& dq) {
+  const float d = a - q, den = c0 + k * fabsf(d), inv = 1.f / den;
+  const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+  const float t = a * q * k * sg * inv * inv;
+  da = q * inv - t;
+  dq = a * inv + t;
+}
+
+__global__ void __launch_bounds__(256) nce_self_fwd_kernel(const bf16* __restrict__ fea, const long* __restrict__ sel,
+                                                          long CHW, float k, float c0, float inv_hw,
+                                                          float* __restrict__ logits) {
+  __shared__ float red[33];
+  const int b = blockIdx.y;
+  const bf16* ab = fea + (long)b * CHW;
+  const bf16* pb = fea + sel[0] * CHW;
+  const bf16* nb = fea + sel[1] * CHW;
+  float sp = 0.f, sn = 0.f;
+  for (long i = ((long)blockIdx.x * 256 + threadIdx.x) * 8; i < CHW; i += (long)gridDim.x * 256 * 8) {
+    float a[8], p[8], q[8];
+    load8(ab + i, a); load8(pb + i, p); load8(nb + i, q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sp += nce_term(a[j], p[j], k, c0); sn += nce_term(a[j], q[j], k, c0); }
+  }
+  sp = block_sum(sp * inv_hw, red);
+  sn = block_sum(sn * inv_hw, red);
+  if (threadIdx.x == 0) { atomicAdd(logits + 2 * b, sp); atomicAdd(logits + 2 * b + 1, sn); }
+}
+
+__global__ void nce_ce_kernel(const float* __restrict__ logits, int B, float* __restrict__ loss) {
+  // cross entropy of [pos, neg] rows against class 0, mean over the batch (one warp)
+  float v = 0.f;
+  for (int b = threadIdx.x; b < B; b += 32) {
+    const float l0 = logits[2 * b], l1 = logits[2 * b + 1], mx = fmaxf(l0, l1);
+    v += mx + logf(expf(l0 - mx) + expf(l1 - mx)) - l0;
+  }
+  v = warp_sum(v);
+  if (threadIdx.x == 0) loss[0] = v / (float)B;
+}
+
+__global__ void __launch_bounds__(256) nce_self_bwd_kernel(const bf16* __restrict__ fea, const long* __restrict__ sel,
+                                                          long CHW, float k, float c0, float inv_hw,
+                                                          const float* __restrict__ logits, int B,
+                                                          const float* __restrict__ g_up, float* __restrict__ d_fea_f32,
+                                                          bf16* __restrict__ d_fea) {
+  extern __shared__ float s_dl[];   // [2][B]
+  for (int b = threadIdx.x; b < B; b += 256) {
+    const float l0 = logits[2 * b], l1 = logits[2 * b + 1], mx = fmaxf(l0, l1);
+    const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), p0 = e0 / (e0 + e1);
+    const float g = __ldg(g_up) / (float)B * inv_hw;
+    s_dl[b] = g * (p0 - 1.f);
+    s_dl[B + b] = g * (1.f - p0);
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const long ip = sel[0], in = sel[1];
+  const bf16* ab = fea + (long)b * CHW;
+  const bf16* pb = fea + ip * CHW;
+  const bf16* nb = fea + in * CHW;
+  const float dl0 = s_dl[b], dl1 = s_dl[B + b];
+  for (long i = ((long)blockIdx.x * 256 + threadIdx.x) * 8; i < CHW; i += (long)gridDim.x * 256 * 8) {
+    float a[8], p[8], q[8], o[8];
+    load8(ab + i, a); load8(pb + i, p); load8(nb + i, q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float da_p, dp_, da_n, dn_;
+      nce_grad(a[j], p[j], k, c0, da_p, dp_);
+      nce_grad(a[j], q[j], k, c0, da_n, dn_);
+      o[j] = dl0 * da_p + dl1 * da_n;
+    }
+    if (b == ip || b == in) {
+      // this row is also the broadcast positive (negative): its gradient sums over the whole batch
+      const bool is_p = b == ip, is_n = b == in;
+      for (int bb = 0; bb < B; ++bb) {
+        float x[8];
+        load8(fea + (long)bb * CHW + i, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float da_, dq_;
+          nce_grad(x[j], a[j], k, c0, da_, dq_);
+          if (is_p) o[j] = fmaf(s_dl[bb], dq_, o[j]);
+          if (is_n) o[j] = fmaf(s_dl[B + bb], dq_, o[j]);
+        }
+      }
+    }
+    if (d_fea != nullptr) store8(d_fea + (long)b * CHW + i, o);
+    else store8(d_fea_f32 + (long)b * CHW + i, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam semantics, no amsgrad / weight decay / maximize) on a flat buffer; `step` lives on the device
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ m, float* __restrict__ v, long n, float lr,
+                                                       float b1, float b2, float eps, const float* __restrict__ step) {
+  const float t = step[0];
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+}
+__global__ void bump_step_kernel(float* step) { step[0] += 1.f; }
+
+int grid_for(long n, int per_sm = 8) {
+  long g = (n + 255) / 256;
+  const long cap = 148L * per_sm;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace
+
+extern "C" int uncl_skip_pool_bwd(const void* x2, long x2_img_stride, const void* dcat, const void* dpool, void* dz, float* db,
+                                  int N, int C, int H, int W, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && C % 8 == 0 && H > 1 && W > 1 && x2 && dz && x2_img_stride % 8 == 0, "skip_pool_bwd: bad arguments");
+  int chunks = ceil_div(H * W, 256 * 4);
+  if (chunks > 64) chunks = 64;
+  skip_pool_bwd_kernel<<<dim3(chunks, N * (C / 8)), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(x2), x2_img_stride, reinterpret_cast<const bf16*>(dcat),
+      reinterpret_cast<const bf16*>(dpool), reinterpret_cast<bf16*>(dz), db, C, H, W);
+  return uncl_check_launch("skip_pool_bwd");
+}
+
+extern "C" int uncl_bias_grad_bf16(const void* dz, long img_stride, float* db, int N, int C, int HW, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && C % 8 == 0 && HW > 0 && dz && db && img_stride % 8 == 0, "bias_grad_bf16: bad arguments");
+  int chunks = ceil_div(HW, 256 * 8);
+  if (chunks > 32) chunks = 32;
+  bias_grad_kernel<<<dim3(chunks, N * (C / 8)), 256, 0, stream>>>(reinterpret_cast<const bf16*>(dz), img_stride, db, C, HW);
+  return uncl_check_launch("bias_grad_bf16");
+}
+
+extern "C" int uncl_convT2x2_s2d_bf16(const void* dY, long dy_img_stride, void* out, float* db, int N, int C, int H, int W,
+                                      int H2, int W2, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && C % 8 == 0 && H2 >= 2 * H && W2 >= 2 * W && dY && out && dy_img_stride % 8 == 0,
+               "convT2x2_s2d_bf16: bad arguments");
+  int chunks = ceil_div(H * W, 256 * 4);
+  if (chunks > 32) chunks = 32;
+  convT2x2_s2d_bf16_kernel<<<dim3(chunks, N * 4 * (C / 8)), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(dY), dy_img_stride, reinterpret_cast<bf16*>(out), db, C, H, W, H2, W2);
+  return uncl_check_launch("convT2x2_s2d_bf16");
+}
+
+extern "C" int uncl_outc_feat_bwd(const float* d_out, const float* out, const void* up, long up_img_stride,
+                                  const void* d_feat, const float* w, void* dz, float* dw, float* db_out, float* db_up, int N,
+                                  int C, int HW, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && C == 32 && HW > 0 && out && up && w && dz && dw && db_out, "outc_feat_bwd: only C = 32 is built");
+  outc_feat_bwd_kernel<32><<<148 * 2, 256, 0, stream>>>(d_out, out, reinterpret_cast<const bf16*>(up), up_img_stride,
+                                                      reinterpret_cast<const bf16*>(d_feat), w, reinterpret_cast<bf16*>(dz),
+                                                      dw, db_out, db_up, HW, N);
+  return uncl_check_launch("outc_feat_bwd");
+}
+
+extern "C" int uncl_pack_gather(const float* src, const int* idx, void* dst_bf16, long n, cudaStream_t stream) {
+  UNCL_REQUIRE(n > 0 && src && idx && dst_bf16, "pack_gather: bad arguments");
+  pack_gather_kernel<<<grid_for(n), 256, 0, stream>>>(src, idx, reinterpret_cast<bf16*>(dst_bf16), n);
+  return uncl_check_launch("pack_gather");
+}
+
+extern "C" int uncl_unpack_gather(const float* src, const int* idx, float* dst, long n, cudaStream_t stream) {
+  UNCL_REQUIRE(n > 0 && src && idx && dst, "unpack_gather: bad arguments");
+  unpack_gather_kernel<<<grid_for(n), 256, 0, stream>>>(src, idx, dst, n);
+  return uncl_check_launch("unpack_gather");
+}
+
+extern "C" int uncl_nce_self_fwd(const void* fea, const long* sel, int B, long CHW, int HW, float k, float constant,
+                                 float* logits_scratch, float* loss_out, cudaStream_t stream) {
+  UNCL_REQUIRE(B > 0 && CHW % 8 == 0 && HW > 0 && fea && sel && logits_scratch && loss_out, "nce_self_fwd: bad arguments");
+  cudaMemsetAsync(logits_scratch, 0, 2 * B * sizeof(float), stream);
+  int gx = grid_for(CHW / 8, 4) / B;
+  if (gx < 1) gx = 1;
+  nce_self_fwd_kernel<<<dim3(gx, B), 256, 0, stream>>>(reinterpret_cast<const bf16*>(fea), sel, CHW, k, constant,
+                                                      1.f / (float)HW, logits_scratch);
+  nce_ce_kernel<<<1, 32, 0, stream>>>(logits_scratch, B, loss_out);
+  return uncl_check_launch("nce_self_fwd");
+}
+
+extern "C" int uncl_nce_self_bwd(const void* fea, const long* sel, int B, long CHW, int HW, float k, float constant,
+                                 const float* logits, const float* g_up, void* d_fea, int d_dtype, cudaStream_t stream) {
+  UNCL_REQUIRE(B > 0 && B <= 1024 && CHW % 8 == 0 && fea && sel && logits && g_up && d_fea, "nce_self_bwd: bad arguments");
+  int gx = grid_for(CHW / 8, 4) / B;
+  if (gx < 1) gx = 1;
+  nce_self_bwd_kernel<<<dim3(gx, B), 256, 2 * B * sizeof(float), stream>>>(
+      reinterpret_cast<const bf16*>(fea), sel, CHW, k, constant, 1.f / (float)HW, logits, B, g_up,
+      d_dtype == UNCL_F32 ? reinterpret_cast<float*>(d_fea) : nullptr,
+      d_dtype == UNCL_BF16 ? reinterpret_cast<bf16*>(d_fea) : nullptr);
+  return uncl_check_launch("nce_self_bwd");
+}
+
+extern "C" int uncl_adam_flat(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
+                              float eps, float* step, cudaStream_t stream) {
+  UNCL_REQUIRE(n > 0 && p && g && m && v && step, "adam_flat: bad arguments");
+  bump_step_kernel<<<1, 1, 0, stream>>>(step);
+  adam_flat_kernel<<<grid_for(n), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step);
+  return uncl_check_launch("adam_flat");
+}

@@ -12,9 +12,20 @@ def conv3x3_taps(w, transposed):
 
     transposed=True: ConvTranspose2d 3x3 s1 p0 == correlation over a 2-px zero-padded input with the kernel
     flipped in both axes (unet_parts.py:114, 148-159)."""
+    return conv3x3_taps_layout(w, transposed).float()
+
+
+def conv3x3_taps_layout(w, transposed):
+    """conv3x3_taps without the cast (pure permutation: also applied to index tensors, see build_pack_maps)."""
     if transposed:
-        return w.flip(2, 3).permute(2, 3, 0, 1).reshape(9, w.shape[0], w.shape[1]).contiguous().float()
-    return w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]).contiguous().float()
+        return w.flip(2, 3).permute(2, 3, 0, 1).reshape(9, w.shape[0], w.shape[1]).contiguous()
+    return w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]).contiguous()
+
+
+def conv3x3_dgrad_taps_layout(w9):
+    """[9][C_in][C_out] taps of a correlation -> the taps of its data gradient (a correlation of dZ with pad 2 - p):
+    reversed tap order, input / output channels swapped."""
+    return w9.flip(0).transpose(1, 2).contiguous()
 
 
 def conv3x3_tc_is_merged(ci, co):
@@ -35,18 +46,21 @@ def conv3x3_tc(w9):
     C_out <= 64, C_in >= 64 and C_in % 32 == 0 (conv_tc_merged.cu, the three kx taps of a filter row merged into N):
         [NS][C_in/16][3 ky][2][3*NT (kx, n)][8], NT = min(C_out, 64)
     wider layers (conv_tc.cu, one tap per MMA): [NS][C_in/16][9][2][NT][8], NT = min(C_out, 128)."""
+    return conv3x3_tc_layout(w9).to(torch.bfloat16)
+
+
+def conv3x3_tc_layout(w9):
     _, ci, co = w9.shape
     if conv3x3_tc_is_merged(ci, co):
         nt = min(co, 64)
         ns = co // nt
         t = w9.reshape(3, 3, ci // 16, 2, 8, ns, nt)       # ky, kx, chunk, half, k8, ns, n
         t = t.permute(5, 2, 0, 3, 1, 6, 4).contiguous()    # ns, chunk, ky, half, kx, n, k8
-        return t.reshape(ns, ci // 16, 3, 2, 3 * nt, 8).to(torch.bfloat16)
+        return t.reshape(ns, ci // 16, 3, 2, 3 * nt, 8)
     nt = min(co, 128)
     ns = co // nt
     t = w9.reshape(9, ci // 16, 2, 8, ns, nt)          # tap, chunk, half, k8, ns, n
-    t = t.permute(4, 1, 0, 2, 5, 3).contiguous()       # ns, chunk, tap, half, n, k8
-    return t.to(torch.bfloat16)
+    return t.permute(4, 1, 0, 2, 5, 3).contiguous()    # ns, chunk, tap, half, n, k8
 
 
 def convT2x2(w):
@@ -54,15 +68,30 @@ def convT2x2(w):
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], 4, w.shape[1]).contiguous().float()
 
 
+def convT2x2_gemm_layout(w):
+    """ConvTranspose2d k2 s2 weight [C_in][C_out][2][2] -> [C_in][4*C_out] with column j = (dy*2+dx)*C_out + co: the
+    layout of the up-convolution's weight-gradient GEMM (dW[ci][j] = sum_pix X[pix][ci] * s2d(dY)[pix][j])."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], 4 * w.shape[1]).contiguous()
+
+
+def convT2x2_dgrad_layout(w):
+    """The same weight as the 1x1 conv [C_out' = C_in][C_in' = 4*C_out][1][1] that maps the space-to-depth output
+    gradient back to the input gradient (uncl_pw_conv_tc_dgrad)."""
+    return pointwise_tc_layout(convT2x2_gemm_layout(w).reshape(w.shape[0], 4 * w.shape[1], 1, 1), 1)
+
+
 def convT2x2_tc(w):
     """ConvTranspose2d k2 s2 weight [C_in][C_out][2][2] -> bf16 [NS][C_in/16][2][NT][8] (GEMM B operand, K-major):
     column j = (dy*2+dx)*C_out + co, NT = min(4*C_out, 128)."""
+    return convT2x2_tc_layout(w).to(torch.bfloat16)
+
+
+def convT2x2_tc_layout(w):
     ci, co = w.shape[0], w.shape[1]
     n_total = 4 * co
     nt = min(n_total, 128)
     b = w.permute(2, 3, 1, 0).reshape(n_total, ci)             # [j][ci]
-    b = b.reshape(n_total // nt, nt, ci // 16, 2, 8).permute(0, 2, 3, 1, 4).contiguous()
-    return b.to(torch.bfloat16)
+    return b.reshape(n_total // nt, nt, ci // 16, 2, 8).permute(0, 2, 3, 1, 4).contiguous()
 
 
 def pointwise(w, groups=1):
@@ -74,10 +103,13 @@ def pointwise(w, groups=1):
 def pointwise_tc(w, groups=1):
     """1x1 Conv2d weight [C_out][C_in/g][1][1] -> bf16 [NS][C_in/g/16][2][NT][8] (conv_tc.cu pointwise B operand, K-major):
     N split ns covers output channels ns*NT .. ns*NT+NT-1 (inside one group), NT = min(C_out/g, 128)."""
+    return pointwise_tc_layout(w, groups).to(torch.bfloat16)
+
+
+def pointwise_tc_layout(w, groups=1):
     co, cig = w.shape[0], w.shape[1]
     nt = min(co // groups, 128)
-    b = w.reshape(co // nt, nt, cig // 16, 2, 8).permute(0, 2, 3, 1, 4).contiguous()
-    return b.to(torch.bfloat16)
+    return w.reshape(co // nt, nt, cig // 16, 2, 8).permute(0, 2, 3, 1, 4).contiguous()
 
 
 def pointwise_tc_split(w):
@@ -93,10 +125,28 @@ def pointwise_tc_split(w):
 
 def conv_first(w):
     """Conv2d(1, C_out, 3) weight [C_out][1][3][3] -> [9][C_out] fp32."""
-    return w.reshape(w.shape[0], 9).t().contiguous().float()
+    return conv_first_layout(w).float()
+
+
+def conv_first_layout(w):
+    return w.reshape(w.shape[0], 9).t().contiguous()
 
 
 def blocked_param(t):
     """[1][C][H][W] -> C8-blocked [C/8][H*W][8] fp32 (pos_embed)."""
+    return blocked_param_layout(t).float()
+
+
+def blocked_param_layout(t):
     _, c, h, w = t.shape
-    return t.reshape(c // 8, 8, h * w).permute(0, 2, 1).contiguous().float()
+    return t.reshape(c // 8, 8, h * w).permute(0, 2, 1).contiguous()
+
+
+LO_FLAG = 1 << 30   # index-map flag: store the bf16 residual w - bf16(w) (uncl_pack_gather)
+
+
+def pointwise_tc_split_index_layout(idx):
+    """Index-map form of pointwise_tc_split: [C_out][C_in][1][1] int64 source indices -> [hi | lo | hi] B operand."""
+    i2 = idx.reshape(idx.shape[0], idx.shape[1])
+    cat = torch.cat([i2, i2 + LO_FLAG, i2], dim=1)
+    return pointwise_tc_layout(cat.reshape(cat.shape[0], cat.shape[1], 1, 1), 1)
