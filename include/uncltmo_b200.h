@@ -252,6 +252,11 @@ int uncl_conv3x3_wgrad(const float* X, long x_img_stride, const float* dZ, float
  * dW9): a GEMM with K = pixels whose operands are read MN-major straight from the C8-blocked TMA tiles. */
 int uncl_conv3x3_wgrad_tc(const void* X, long x_img_stride, const void* dZ, float* dW9, int N, int C_in, int H, int W,
                           int C_out, int pad, uncl_stream_t stream);
+/* Pointwise (GEMM) weight gradient on the same tensor-core kernel (one tap): dW[ci][co] += sum_pix X[pix,ci] * dZ[pix,co];
+ * bf16 blocked operands with their own image strides, dW fp32 [C_in][C_out] (zeroed by the caller).  Weight gradient of
+ * the k2 s2 up-convolution over the space-to-depth output gradient (C_out = 4C). */
+int uncl_pw_wgrad_tc(const void* X, long x_img_stride, const void* dZ, long dz_img_stride, float* dW, int N, int C_in,
+                     int C_out, int H, int W, uncl_stream_t stream);
 int uncl_conv_first_wgrad(const float* x, const float* dZ, float* dW, int N, int H, int W, int C, uncl_stream_t stream);
 int uncl_maxpool2_bwd(const float* X, long x_img_stride, const float* dP, float* dX, int N, int C, int H, int W,
                       uncl_stream_t stream);
@@ -307,6 +312,8 @@ int uncl_outc_feat_bwd(const float* d_out, const float* out, const void* up, lon
 int uncl_pack_gather(const float* src, const int* idx, void* dst_bf16, long n, uncl_stream_t stream);
 /* dst[i] = src[idx[i]] (idx < 0: dst untouched): fp32 gather, e.g. GEMM-layout weight gradients -> parameter layout. */
 int uncl_unpack_gather(const float* src, const int* idx, float* dst, long n, uncl_stream_t stream);
+/* dst[i] += src[idx[i]]: accumulating form (all GEMM-layout weight gradients of a backward pass into the flat p.grad). */
+int uncl_unpack_add(const float* src, const int* idx, float* dst, long n, uncl_stream_t stream);
 /* GanTrainer.nce as infoNCE2 calls it (GanTrainerImg.py:384-439): positive / negative are rows sel[0] / sel[1] (device
  * int64) of the anchor tensor itself, broadcast over the batch.  fea: bf16 [B][CHW] in ANY element order (the
  * similarity is a sum over all elements).  logits_scratch: 2*B floats (kept for the backward). */

@@ -243,3 +243,60 @@ def test_merged_packing_reproduces_the_convolution_on_cpu():
     # the packed weights are bf16: compare against the convolution of the bf16-rounded weights with fp32 activations
     want = torch.nn.functional.conv2d(x, wt.to(torch.bfloat16).float())[0]
     assert torch.allclose(out, want, atol=2e-5, rtol=1e-5)
+
+
+def test_flat_parameter_index_maps():
+    """train_graph.FlatParams: the one-launch weight packing (dst[i] = bf16(flat[idx[i]])) reproduces packing.py's torch
+    re-layouts operand by operand, the split-bf16 flag selects the residual, and the gradient un-packing map is the inverse
+    permutation of the GEMM layouts (a staged 'gradient' equal to the re-laid-out weight returns the weight itself)."""
+    from uncltmo_b200.generator import UNet
+    from uncltmo_b200.train_graph import FlatParams
+    from uncltmo_b200.weights import make_generator_state_dict
+    args = (1, 1, "sigmoid", 4, 4, "square_and_square_root", 32, 0, "unet", 0, 0, "none", "none", "relu", 1, "replicate", 2)
+    net = UNet(*args, up_mode=0, precision="bf16")
+    sd = make_generator_state_dict()
+    net.load_state_dict(sd)
+    fp = FlatParams(net)
+    assert fp.is_current() and fp.grads_attached()
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, sd[k]), k     # the flat buffer holds the same parameters
+    idx = fp.pack_idx.long()
+    src = fp.flat[(idx & 0x3fffffff).clamp(min=0)]
+    hi = src.to(torch.bfloat16)
+    lo = (src - hi.float()).to(torch.bfloat16)
+    packed = torch.where(idx < 0, torch.zeros_like(hi), torch.where((idx & packing.LO_FLAG) != 0, lo, hi))
+
+    def operand(name):
+        o, n = fp.pack_off[name], int(np.prod(fp.pack_shape[name]))
+        return packed[o:o + n].reshape(fp.pack_shape[name])
+
+    for name, key, transposed in fp.conv3:
+        w9 = packing.conv3x3_taps(sd[key + ".weight"], transposed)
+        assert torch.equal(operand(name), packing.conv3x3_tc(w9)), name
+        assert torch.equal(operand(name + "_d"), packing.conv3x3_tc(w9.flip(0).transpose(1, 2).contiguous())), name
+    for i in range(4):
+        w = sd["up_path.%d.up.weight" % i]
+        c = w.shape[0]
+        assert torch.equal(operand("u%d_up" % i), packing.convT2x2_tc(w))
+        assert torch.equal(operand("u%d_up_d" % i), packing.pointwise_tc(w.permute(0, 2, 3, 1).reshape(c, 4 * c, 1, 1)))
+    gp = "gcn.module.0."
+    assert torch.equal(operand("g_gconv"), packing.pointwise_tc(sd[gp + "0.graph_conv.gconv.nn.0.weight"], 4))
+    assert torch.equal(operand("g_fc1_split"), packing.pointwise_tc_split(sd[gp + "0.fc1.0.weight"]))
+    f32 = fp.flat[fp.f32_idx.long()]
+    assert torch.equal(f32[:fp.n_cf].reshape(9, 32), packing.conv_first(sd["inc.conv.conv.weight"]))
+    assert torch.equal(f32[fp.n_cf:].reshape(32, 144, 8), packing.blocked_param(sd["gcn.pos_embed"]))
+    # un-packing: stage the re-laid-out weights as if they were gradients, scatter them back
+    stage = torch.zeros(fp.stage_total)
+    for name, key, transposed in fp.conv3:
+        w9 = packing.conv3x3_taps(sd[key + ".weight"], transposed)
+        stage[fp.stage_off[name]:fp.stage_off[name] + w9.numel()] = w9.reshape(-1)
+    for i in range(4):
+        g = packing.convT2x2_gemm_layout(sd["up_path.%d.up.weight" % i])
+        stage[fp.stage_off["u%d_up" % i]:fp.stage_off["u%d_up" % i] + g.numel()] = g.reshape(-1)
+    cf = packing.conv_first(sd["inc.conv.conv.weight"])
+    stage[fp.stage_off["inc0"]:fp.stage_off["inc0"] + cf.numel()] = cf.reshape(-1)
+    u = fp.unpack_idx.long()
+    grad = torch.where(u >= 0, stage[u.clamp(min=0)], torch.zeros(fp.total))
+    for name, key, _ in fp.conv3 + [("", "up_path.%d.up" % i, 0) for i in range(4)] + [("", "inc.conv.conv", 0)]:
+        assert torch.equal(fp.view(grad, key + ".weight"), sd[key + ".weight"]), key
+    assert (fp.view(grad, "outc.conv.weight") == 0).all()      # parameters without a staged gradient are left alone

@@ -32,6 +32,22 @@ for n, ms in rec: agg[n] = agg.get(n, 0) + ms
 for n, ms in sorted(agg.items(), key=lambda kv: -kv[1])[:14]: print("  %-32s %8.3f ms" % (n, ms))
 print("  total kernels", sum(agg.values()))
 print("  top-level count", len(rec))
+# the whole iteration as one CUDA graph (what bench.py times)
+try:
+    gG = UNet(*G_ARGS, up_mode=0, precision=PREC).cuda().train(); gG.load_state_dict(make_generator_state_dict())
+    gD = SimpleDiscriminator(256, 1, 16, "none", "none", 0, 0).cuda().train(); gD.load_state_dict(make_discriminator_state_dict())
+    oG = torch.optim.Adam([p for p in gG.parameters() if p.requires_grad], lr=1e-5, betas=(0.5, 0.999), capturable=True, fused=True)
+    oD = torch.optim.Adam(gD.parameters(), lr=1.5e-5, betas=(0.5, 0.999), capturable=True, fused=True)
+    tg = GanTrainerStep(gG, gD, oG, oD)
+    tg.capture(hdr, None, pos, neg, 0)
+    for _ in range(3): tg.replay(hdr, None, pos, neg, 0)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20): tg.replay(hdr, None, pos, neg, 0)
+    e1.record(); torch.cuda.synchronize()
+    print(PREC, "graph replay: %.3f ms/step -> %.1f steps/s" % (e0.elapsed_time(e1) / 20, 20 / (e0.elapsed_time(e1) / 1e3)))
+except Exception as e:
+    import traceback; traceback.print_exc()
 try:
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:

@@ -370,18 +370,21 @@ class OutcSigmoid(Function):
 
 
 class BlockedToNCHW(Function):
+    """C8-blocked (fp32 or bf16) -> NCHW fp32 at the module boundary; the gradient returns in the input's dtype."""
+
     @staticmethod
     def forward(ctx, x):
         x = x.contiguous()
         n, cb, h, w, _ = x.shape
         o = _empty((n, cb * 8, h, w), x)
-        call("uncl_blocked_to_nchw", x, x.stride(0), o, n, cb * 8, h * w, F32)
+        call("uncl_blocked_to_nchw", x, x.stride(0), o, n, cb * 8, h * w, _lib.DTYPE_OF[x.dtype])
+        ctx.dtype = x.dtype
         return o
 
     @staticmethod
     def backward(ctx, do):
         do = do.contiguous().float()
         n, c, h, w = do.shape
-        dx = _empty((n, c // 8, h, w, 8), do)
-        call("uncl_nchw_to_blocked", do, dx, dx.stride(0), n, c, h * w, F32)
+        dx = torch.empty((n, c // 8, h, w, 8), device=do.device, dtype=ctx.dtype)
+        call("uncl_nchw_to_blocked", do, dx, dx.stride(0), n, c, h * w, _lib.DTYPE_OF[ctx.dtype])
         return dx

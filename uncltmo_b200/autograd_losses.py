@@ -5,7 +5,7 @@ import ctypes
 import torch
 from torch.autograd import Function
 
-from ._lib import call
+from ._lib import BF16, call
 
 
 def _f(t):
@@ -90,6 +90,35 @@ class NceFn(Function):
         dn = torch.empty_like(n) if ctx.needs_input_grad[2] else None
         call("uncl_nce_bwd", a, p, ps, n, ns, b, c, h * w, k, constant, logits, _f(g), da, dp, dn)
         return da, dp, dn, None, None
+
+
+class NceSelfFn(Function):
+    """GanTrainer.nce as infoNCE2 calls it (GanTrainerImg.py:384-439) on a feature tensor in ANY element order (the
+    similarity is a sum over all elements): the C8-blocked bf16 `up_x` of the bf16 training path is read as it is.
+    sel: device int64 [2] = (row of the positive, row of the negative), both rows of `fea` itself."""
+
+    @staticmethod
+    def forward(ctx, fea, sel, hw, k, constant):
+        fea = fea.contiguous()
+        if fea.dtype != torch.bfloat16:
+            raise TypeError("NceSelfFn reads bf16 features")
+        b = fea.shape[0]
+        chw = fea.numel() // b
+        logits = torch.empty(2 * b, device=fea.device, dtype=torch.float32)
+        out = _scalar(fea)
+        call("uncl_nce_self_fwd", fea, sel, b, chw, hw, float(k), float(constant), logits, out)
+        ctx.save_for_backward(fea, sel, logits)
+        ctx.cfg = (hw, float(k), float(constant))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        fea, sel, logits = ctx.saved_tensors
+        hw, k, constant = ctx.cfg
+        b = fea.shape[0]
+        d = torch.empty_like(fea)
+        call("uncl_nce_self_bwd", fea, sel, b, fea.numel() // b, hw, k, constant, logits, _f(g), d, BF16)
+        return d, None, None, None, None
 
 
 class PlaneMeanContrastFn(Function):

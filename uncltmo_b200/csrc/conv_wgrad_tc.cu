@@ -23,7 +23,7 @@ constexpr int kWgMaxStages = 4;
 struct WgParams {
   float* dW;
   int N, C_in, C_out, Ho, Wo, pad;
-  int taps9, nky, Nc, n_co_chunks, n_ci_chunks, Mc_blocks;
+  int taps9, nky, nkx, Nc, n_co_chunks, n_ci_chunks, Mc_blocks;   // nkx = 1: pointwise (1 tap) mode
   int RB, BW, RBx, PWx;
   int bands, row_tiles, tiles_per_img, total_tiles;
   int groups, ctas_per_group;
@@ -47,7 +47,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   const int stages = p.stages, stage_bytes = p.stage_bytes;
   const int group = blockIdx.x / p.ctas_per_group, slot = blockIdx.x % p.ctas_per_group;
   const int kyi = group % p.nky, cic = (group / p.nky) % p.n_ci_chunks, coc = group / (p.nky * p.n_ci_chunks);
-  const int ntaps = p.taps9 ? 9 : 3;
+  const int ntaps = p.taps9 ? 9 : p.nkx;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
@@ -110,10 +110,14 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             uint32_t d = tmem_base;
             for (int ky = 0; ky < nky_local; ++ky) {
               const uint32_t a_row = lo_const | (sx16 + (uint32_t)(r + ky) * pwx + 16u * (uint32_t)k);
+              if (p.nkx == 3) {
 #pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                tc_mma_bf16(d, a_row + (uint32_t)kx, a_hi, b_lo, b_hi, idesc, accum);
-                d += nc;
+                for (int kx = 0; kx < 3; ++kx) {
+                  tc_mma_bf16(d, a_row + (uint32_t)kx, a_hi, b_lo, b_hi, idesc, accum);
+                  d += nc;
+                }
+              } else {
+                tc_mma_bf16(d, a_row, a_hi, b_lo, b_hi, idesc, accum);
               }
             }
           }
@@ -161,8 +165,8 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 
 // X: bf16 blocked [N][C_in/8][H][W][8] (image stride x_img_stride elements); dZ: bf16 blocked dense
 // [N][C_out/8][Ho][Wo][8]; dW9: fp32 [9][C_in][C_out], accumulated (zeroed by the caller).
-extern "C" int uncl_conv3x3_wgrad_tc(const void* X, long x_img_stride, const void* dZ, float* dW9, int N, int C_in, int H,
-                                     int W, int C_out, int pad, cudaStream_t stream) {
+static int wgrad_tc_impl(const void* X, long x_img_stride, const void* dZ, long dz_img_stride, float* dW9, int N, int C_in,
+                         int H, int W, int C_out, int pad, int pointwise, cudaStream_t stream) {
   UNCL_REQUIRE(N > 0 && C_in % 32 == 0 && C_out % 32 == 0 && (pad == 0 || pad == 2) && (C_in <= 128 || C_in % 128 == 0),
                "conv3x3_wgrad_tc: unsupported C_in=%d C_out=%d pad=%d", C_in, C_out, pad);
   UNCL_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(dZ) & 15) == 0 && x_img_stride % 8 == 0,
@@ -170,17 +174,18 @@ extern "C" int uncl_conv3x3_wgrad_tc(const void* X, long x_img_stride, const voi
   WgParams p{};
   p.dW = dW9;
   p.N = N; p.C_in = C_in; p.C_out = C_out; p.pad = pad;
-  p.Ho = H + 2 * pad - 2; p.Wo = W + 2 * pad - 2;
+  p.Ho = pointwise ? H : H + 2 * pad - 2; p.Wo = pointwise ? W : W + 2 * pad - 2;
   UNCL_REQUIRE(p.Ho > 0 && p.Wo > 0, "conv3x3_wgrad_tc: empty output");
-  p.taps9 = C_out <= 48;
-  p.nky = p.taps9 ? 1 : 3;
+  p.taps9 = !pointwise && C_out <= 48;
+  p.nky = (p.taps9 || pointwise) ? 1 : 3;
+  p.nkx = pointwise ? 1 : 3;
   p.Nc = p.taps9 ? C_out : (C_out < 128 ? C_out : 128);
   UNCL_REQUIRE(C_out % p.Nc == 0 && p.Nc % 32 == 0, "conv3x3_wgrad_tc: unsupported C_out=%d", C_out);
   p.n_co_chunks = C_out / p.Nc;
   p.n_ci_chunks = (C_in + 127) / 128;
   p.Mc_blocks = C_in < 128 ? C_in / 8 : 16;
   p.BW = p.Wo >= 64 ? 64 : ((p.Wo + 15) / 16) * 16;
-  p.PWx = p.BW + 2;
+  p.PWx = pointwise ? p.BW : p.BW + 2;
   const int halo = p.taps9 ? 2 : 0;
   int rb = 4;
   for (;; rb >>= 1) {
@@ -206,9 +211,7 @@ extern "C" int uncl_conv3x3_wgrad_tc(const void* X, long x_img_stride, const voi
   p.tiles_per_img = p.bands * p.row_tiles;
   p.total_tiles = N * p.tiles_per_img;
   p.groups = p.nky * p.n_ci_chunks * p.n_co_chunks;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   p.ctas_per_group = sms / p.groups;
   if (p.ctas_per_group < 1) p.ctas_per_group = 1;
   if (p.ctas_per_group > p.total_tiles) p.ctas_per_group = p.total_tiles;
@@ -216,10 +219,26 @@ extern "C" int uncl_conv3x3_wgrad_tc(const void* X, long x_img_stride, const voi
   CUtensorMap tmx, tmz;
   CUresult r = encode_blocked_bf16(&tmx, X, W, H, C_in / 8, N, x_img_stride, p.PWx, p.RBx, p.Mc_blocks);
   if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "conv3x3_wgrad_tc: tensor map (X) failed (%d)", (int)r);
-  r = encode_blocked_bf16(&tmz, dZ, p.Wo, p.Ho, C_out / 8, N, (long)C_out * p.Ho * p.Wo, p.BW, p.RB, p.Nc / 8);
+  r = encode_blocked_bf16(&tmz, dZ, p.Wo, p.Ho, C_out / 8, N, dz_img_stride, p.BW, p.RB, p.Nc / 8);
   if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "conv3x3_wgrad_tc: tensor map (dZ) failed (%d)", (int)r);
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  static thread_local int smem_ok = 0, smem_dev = -1;
+  cudaError_t e = ensure_smem(conv3x3_wgrad_tc_kernel, smem_bytes, smem_ok, smem_dev);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "conv3x3_wgrad_tc: smem attr: %s", cudaGetErrorString(e));
   conv3x3_wgrad_tc_kernel<<<p.groups * p.ctas_per_group, kWgThreads, smem_bytes, stream>>>(tmx, tmz, p);
   return uncl_check_launch("conv3x3_wgrad_tc");
+}
+
+extern "C" int uncl_conv3x3_wgrad_tc(const void* X, long x_img_stride, const void* dZ, float* dW9, int N, int C_in, int H,
+                                     int W, int C_out, int pad, cudaStream_t stream) {
+  return wgrad_tc_impl(X, x_img_stride, dZ, (long)C_out * (H + 2 * pad - 2) * (W + 2 * pad - 2), dW9, N, C_in, H, W, C_out, pad,
+                       0, stream);
+}
+
+// Pointwise (1x1 / GEMM) weight gradient on the same kernel with one tap:  dW[ci][co] += sum_pix X[pix, ci] * dZ[pix, co].
+// The k2 s2 up-convolution's weight gradient is this GEMM over the space-to-depth output gradient (C_out = 4C).
+// X: bf16 blocked [N][C_in/8][H][W][8]; dZ: bf16 blocked [N][C_out/8][H][W][8]; both with their own image strides.
+extern "C" int uncl_pw_wgrad_tc(const void* X, long x_img_stride, const void* dZ, long dz_img_stride, float* dW, int N,
+                                int C_in, int C_out, int H, int W, cudaStream_t stream) {
+  UNCL_REQUIRE(dz_img_stride % 8 == 0, "pw_wgrad_tc: dZ stride must be a multiple of 8");
+  return wgrad_tc_impl(X, x_img_stride, dZ, dz_img_stride, dW, N, C_in, H, W, C_out, 0, 1, stream);
 }

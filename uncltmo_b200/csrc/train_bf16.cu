@@ -228,6 +228,14 @@ __global__ void __launch_bounds__(256) unpack_gather_kernel(const float* __restr
   }
 }
 
+__global__ void __launch_bounds__(256) unpack_add_kernel(const float* __restrict__ src, const int* __restrict__ idx,
+                                                        float* __restrict__ dst, long n) {
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+    const int k = idx[i];
+    if (k >= 0) dst[i] += __ldg(src + k);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // nce on one feature tensor whose positive / negative are two of its own rows (infoNCE2), any element layout
 // ---------------------------------------------------------------------------------------------------------
@@ -400,6 +408,12 @@ extern "C" int uncl_unpack_gather(const float* src, const int* idx, float* dst, 
   UNCL_REQUIRE(n > 0 && src && idx && dst, "unpack_gather: bad arguments");
   unpack_gather_kernel<<<grid_for(n), 256, 0, stream>>>(src, idx, dst, n);
   return uncl_check_launch("unpack_gather");
+}
+
+extern "C" int uncl_unpack_add(const float* src, const int* idx, float* dst, long n, cudaStream_t stream) {
+  UNCL_REQUIRE(n > 0 && src && idx && dst, "unpack_add: bad arguments");
+  unpack_add_kernel<<<grid_for(n), 256, 0, stream>>>(src, idx, dst, n);
+  return uncl_check_launch("unpack_add");
 }
 
 extern "C" int uncl_nce_self_fwd(const void* fea, const long* sel, int B, long CHW, int HW, float k, float constant,

@@ -115,6 +115,10 @@ class _GeneratorBase(nn.Module):
         return tuple((p.data_ptr(), p._version) for p in self.parameters()) + (self.precision,)
 
     def packed(self):
+        flat = getattr(self, "_flat", None)
+        if flat is not None and self.precision == "bf16" and flat.is_current():
+            # training keeps the parameters in one flat buffer: every operand comes from ONE gather launch per update
+            return flat.pack().P()
         key = self._pack_key()
         if self._packed is None or key != self._packed_key:
             self._packed = self._pack()
@@ -393,9 +397,38 @@ class UNet(_GeneratorBase):
     from `uncltmo_b200.autograd` Functions (fp32 path), so `loss.backward()` runs the library's backward kernels.
     """
 
+    def forward_blocked(self, x):
+        """(sigmoid map [N,1,256,256] fp32, up_x as the C8-blocked bf16 tensor [N,4,256,256,8] the network computed it in).
+        The fast trainer's entry (uncltmo_b200.trainer): losses.infoNCE2 reads the blocked features directly, so the
+        134 MB NCHW fp32 copy of `forward` and its gradient never exist.  bf16 precision only.  Without autograd the
+        features are not materialised at all (second value None)."""
+        if self.precision != "bf16":
+            raise RuntimeError("forward_blocked is the bf16 path's entry")
+        scale = self._droppath_scale(x.shape[0], x.device)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._train_bf16(x, scale)
+        out, _, _, _ = self._run_frame(x, droppath_scale=scale, want_features=False)
+        return out, None
+
+    def _train_bf16(self, x, scale):
+        """bf16-activation training pass as ONE autograd node (uncltmo_b200/train_graph.py)."""
+        from .train_graph import GeneratorTrainFn, flat_params
+        if x.dim() != 4 or tuple(x.shape[1:]) != (1, 256, 256) or not x.is_cuda:
+            raise ValueError("the generator expects CUDA [N,1,256,256] inputs")
+        flat_params(self)
+        anchor = getattr(self, "_anchor", None)
+        if anchor is None or anchor.device != x.device:
+            anchor = self._anchor = torch.zeros(1, device=x.device, requires_grad=True)
+        return GeneratorTrainFn.apply(x, anchor, self, scale)
+
     def forward(self, x, apply_crop=True, diffY=0, diffX=0):
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            out, feats = self._forward_train(x, self._droppath_scale(x.shape[0], x.device))
+            if self.precision == "bf16" and not x.requires_grad:
+                from . import autograd as A
+                out, up = self._train_bf16(x, self._droppath_scale(x.shape[0], x.device))
+                feats = A.BlockedToNCHW.apply(up)
+            else:
+                out, feats = self._forward_train(x, self._droppath_scale(x.shape[0], x.device))
         else:
             out, up, _, _ = self._run_frame(x, droppath_scale=self._droppath_scale(x.shape[0], x.device))
             feats = self._features_nchw(up)

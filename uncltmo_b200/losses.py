@@ -7,7 +7,7 @@ The reference picks the positives / negatives of infoNCE2 and the pseudo label w
 """
 import torch
 
-from .autograd_losses import (ContrastiveDFn, L1MeanFn, NceFn, PlaneMeanContrastFn, TVFn, tmqi_naturalness)
+from .autograd_losses import (ContrastiveDFn, L1MeanFn, NceFn, NceSelfFn, PlaneMeanContrastFn, TVFn, tmqi_naturalness)
 
 
 def contrastive_D_loss(real_logits, fake_logits):
@@ -37,6 +37,12 @@ def nce_from_indices(fea_fake, pos_index, neg_index, cl_loss_type, k, constant):
 def infoNCE2(fea_fake, fake, hdr_input, cl_loss_type, k, constant):
     """GanTrainerImg.py:384-408: positive / negative = the batch samples with the highest / lowest TMQI naturalness."""
     n = tmqi_naturalness(fake)
+    if fea_fake.dim() == 5 and fea_fake.dtype == torch.bfloat16:
+        # the bf16 training path hands over up_x as the C8-blocked tensor it was computed in (UNet.forward_blocked)
+        if cl_loss_type != "InfoNCE":
+            raise NotImplementedError("only InfoNCE is built")
+        sel = torch.stack([torch.argmax(n), torch.argmin(n)])
+        return NceSelfFn.apply(fea_fake, sel, fea_fake.shape[2] * fea_fake.shape[3], k, constant)
     return nce_from_indices(fea_fake, torch.argmax(n), torch.argmin(n), cl_loss_type, k, constant)
 
 

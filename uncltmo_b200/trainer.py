@@ -60,6 +60,9 @@ class GanTrainerStep:
                 raise ValueError("the video trainer expects [B,T,1,256,256] clips")
             fake, fea = self.netG(hdr_input.float())
             return self._flat(fake), self._flat(fea)
+        if getattr(self.netG, "precision", None) == "bf16" and hasattr(self.netG, "forward_blocked"):
+            # bf16 path: one autograd node for the whole generator, features stay C8-blocked bf16 (losses.infoNCE2 reads them)
+            return self.netG.forward_blocked(self._flat(hdr_input))
         return self.netG(self._flat(hdr_input))
 
     # ------------------------------------------------------------------ D step
@@ -153,6 +156,12 @@ class GanTrainerStep:
         return self.train_G(hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch)
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole iteration
+    def _invalidate_packed(self):
+        self.netG._packed = None
+        flat = getattr(self.netG, "_flat", None)
+        if flat is not None:
+            flat._packed_version = None
+
     def _branch(self, epoch):
         return 0 if epoch <= self.epoch_step1 else (1 if epoch <= self.epoch_step2 else 2)
 
@@ -178,11 +187,11 @@ class GanTrainerStep:
         torch.cuda.current_stream().wait_stream(side)
         self.netG.zero_grad(set_to_none=True)
         self.netD.zero_grad(set_to_none=True)
-        self.netG._packed = None      # the weight re-layout of the D-step generator pass must be part of the graph
+        self._invalidate_packed()     # the weight re-layout of the D-step generator pass must be part of the graph
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             err_g, err_s = self.step(static[0], None, static[1], static[2], epoch)
-        self.netG._packed = None
+        self._invalidate_packed()
         self._graphs[self._branch(epoch)] = (graph, static, (self.errD, err_g, err_s))
         return graph
 
@@ -193,6 +202,6 @@ class GanTrainerStep:
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         graph.replay()
-        self.netG._packed = None      # parameters changed behind the version counters the packing cache keys on
+        self._invalidate_packed()     # parameters changed behind the version counters the packing caches key on
         self.errD, self.errG_d, self.errG_struct = err_d, err_g, err_s
         return err_g, err_s
