@@ -316,12 +316,16 @@ int uncl_unpack_gather(const float* src, const int* idx, float* dst, long n, unc
 int uncl_unpack_add(const float* src, const int* idx, float* dst, long n, uncl_stream_t stream);
 /* GanTrainer.nce as infoNCE2 calls it (GanTrainerImg.py:384-439): positive / negative are rows sel[0] / sel[1] (device
  * int64) of the anchor tensor itself, broadcast over the batch.  fea: bf16 [B][CHW] in ANY element order (the
- * similarity is a sum over all elements).  logits_scratch: 2*B floats (kept for the backward). */
-int uncl_nce_self_fwd(const void* fea, const long* sel, int B, long CHW, int HW, float k, float constant,
+ * similarity is a sum over all elements).  A row index >= B selects row (index - B) of `ext` (bf16 [2][CHW]) instead:
+ * data-parallel training, where the global arg-max / arg-min sample may live on another rank (ext may be NULL when both
+ * indices are < B).  logits_scratch: 2*B floats (kept for the backward). */
+int uncl_nce_self_fwd(const void* fea, const long* sel, const void* ext, int B, long CHW, int HW, float k, float constant,
                       float* logits_scratch, float* loss_out, uncl_stream_t stream);
-/* d_fea (bf16 or fp32, d_dtype): anchor gradient of every row + the batch-summed gradient of the two selected rows */
-int uncl_nce_self_bwd(const void* fea, const long* sel, int B, long CHW, int HW, float k, float constant,
-                      const float* logits, const float* g_up, void* d_fea, int d_dtype, uncl_stream_t stream);
+/* d_fea (bf16 or fp32, d_dtype): anchor gradient of every row + the batch-summed gradient of the selected rows that are
+ * local; d_ext (fp32 [2][CHW], may be NULL without ext rows): this rank's partial gradient of the external rows. */
+int uncl_nce_self_bwd(const void* fea, const long* sel, const void* ext, int B, long CHW, int HW, float k, float constant,
+                      const float* logits, const float* g_up, void* d_fea, int d_dtype, float* d_ext,
+                      uncl_stream_t stream);
 /* torch.optim.Adam's update (no amsgrad / weight decay) on one flat fp32 buffer; `step` is a device float, incremented
  * by the call (bias corrections need no host value: capturable in a CUDA graph). */
 int uncl_adam_flat(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,

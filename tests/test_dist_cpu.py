@@ -86,3 +86,59 @@ def test_gradient_buckets_and_gather_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def _global_selection_worker(rank, world, port, out):
+    """Global-batch selection under data parallelism (GanTrainerImg.py:341-408: arg-max / arg-min over the WHOLE batch):
+    world-2 sum of the per-rank gradients must equal the single-process gradient of the same loss on the full batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(3)
+    b, d = 3, 5
+    full = torch.randn(world * b, d)
+    scores = torch.tensor([0.3, 0.9, 0.1, 0.5, 0.95, 0.2])[:world * b]          # best = 4 (rank 1), worst = 2 (rank 0)
+
+    def sim(a, q):       # stand-in for the nce similarity (the CUDA kernel cannot run here); any smooth pair function
+        return (a * q / (1.0 + (a - q).abs())).sum(-1)
+
+    def nce_like(anchor, pos, neg):
+        lg = torch.stack([sim(anchor, pos), sim(anchor, neg)], 1)
+        return torch.nn.functional.cross_entropy(lg, torch.zeros(anchor.shape[0], dtype=torch.long))
+
+    # single process, full batch
+    xf = full.clone().requires_grad_(True)
+    gi = torch.stack([scores.argmax(), scores.argmin()])
+    nce_like(xf, xf[gi[0]:gi[0] + 1], xf[gi[1]:gi[1] + 1]).backward()
+    want = xf.grad[rank * b:(rank + 1) * b]
+    # data parallel: local slice, global indices, rows broadcast from their owners, loss scaled by 1/world, grads summed
+    x = full[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+    g = udist.all_gather_flat(scores[rank * b:(rank + 1) * b])
+    g_idx = torch.stack([g.argmax(), g.argmin()])
+    rows = udist.BroadcastRowsFn.apply(x, g_idx)
+    ok = torch.equal(rows.detach(), full[gi])
+    (nce_like(x, rows[0:1], rows[1:2]) / world).backward()
+    ok = ok and torch.allclose(x.grad, want, atol=1e-6)
+    # pseudo-label form: mean_i |s_i - s_best| with the label's gradient owed to its owner
+    stat = full[:, :1].clone()
+    sf = stat.clone().requires_grad_(True)
+    (sf - sf[gi[0]:gi[0] + 1]).abs().mean().backward()
+    want_s = sf.grad[rank * b:(rank + 1) * b]
+    s = stat[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+    gs = udist.all_gather_cat(s)
+    lab = gs.index_select(0, g_idx[:1])
+    a_r = (s - lab.detach()).abs().mean()
+    b_all = world * (gs.detach() - lab).abs().mean()
+    ((a_r + (b_all - b_all.detach())) / world).backward()
+    ok = ok and torch.allclose(s.grad, want_s, atol=1e-6)
+    vals = [torch.zeros(1) for _ in range(world)]
+    dist.all_gather(vals, (a_r.detach() / world).reshape(1))
+    ok = ok and torch.allclose(sum(vals), (stat - stat[gi[0]]).abs().mean().reshape(1), atol=1e-6)   # values add up too
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_global_batch_selection_world2():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_global_selection_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert out[0] and out[1]

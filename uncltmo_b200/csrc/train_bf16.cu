@@ -239,10 +239,12 @@ __global__ void __launch_bounds__(256) unpack_add_kernel(const float* __restrict
 // ---------------------------------------------------------------------------------------------------------
 // nce on one feature tensor whose positive / negative are two of its own rows (infoNCE2), any element layout
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float nce_term(float a, float q, float k, float c0) { return (a * q) / (c0 + k * fabsf(a - q)); }
+__device__ __forceinline__ float nce_term(float a, float q, float k, float c0) {
+  return __fdividef(a * q, c0 + k * fabsf(a - q));
+}
 // d/da and d/dq of a*q / (c0 + k|a-q|)
 __device__ __forceinline__ void nce_grad(float a, float q, float k, float c0, float& da, float& dq) {
-  const float d = a - q, den = c0 + k * fabsf(d), inv = 1.f / den;
+  const float d = a - q, inv = __fdividef(1.f, c0 + k * fabsf(d));
   const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
   const float t = a * q * k * sg * inv * inv;
   da = q * inv - t;
@@ -250,13 +252,14 @@ __device__ __forceinline__ void nce_grad(float a, float q, float k, float c0, fl
 }
 
 __global__ void __launch_bounds__(256) nce_self_fwd_kernel(const bf16* __restrict__ fea, const long* __restrict__ sel,
-                                                          long CHW, float k, float c0, float inv_hw,
-                                                          float* __restrict__ logits) {
+                                                          const bf16* __restrict__ ext, int B, long CHW, float k,
+                                                          float c0, float inv_hw, float* __restrict__ logits) {
   __shared__ float red[33];
   const int b = blockIdx.y;
   const bf16* ab = fea + (long)b * CHW;
-  const bf16* pb = fea + sel[0] * CHW;
-  const bf16* nb = fea + sel[1] * CHW;
+  const long ip = sel[0], in = sel[1];   // rows >= B live in `ext` (selected on another rank, data parallel)
+  const bf16* pb = ip < B ? fea + ip * CHW : ext + (ip - B) * CHW;
+  const bf16* nb = in < B ? fea + in * CHW : ext + (in - B) * CHW;
   float sp = 0.f, sn = 0.f;
   for (long i = ((long)blockIdx.x * 256 + threadIdx.x) * 8; i < CHW; i += (long)gridDim.x * 256 * 8) {
     float a[8], p[8], q[8];
@@ -280,11 +283,15 @@ __global__ void nce_ce_kernel(const float* __restrict__ logits, int B, float* __
   if (threadIdx.x == 0) loss[0] = v / (float)B;
 }
 
+// One thread owns 8 consecutive elements of EVERY row: it walks the batch once, writes each row's anchor gradient and
+// accumulates the gradient of the broadcast positive / negative in registers; the two selected rows are stored last,
+// with that sum added.  (A row-parallel grid leaves the two selected rows with B times the work of the others.)
+template <bool OUT_BF16>
 __global__ void __launch_bounds__(256) nce_self_bwd_kernel(const bf16* __restrict__ fea, const long* __restrict__ sel,
-                                                          long CHW, float k, float c0, float inv_hw,
-                                                          const float* __restrict__ logits, int B,
-                                                          const float* __restrict__ g_up, float* __restrict__ d_fea_f32,
-                                                          bf16* __restrict__ d_fea) {
+                                                          const bf16* __restrict__ ext, long CHW, float k, float c0,
+                                                          float inv_hw, const float* __restrict__ logits, int B,
+                                                          const float* __restrict__ g_up, void* __restrict__ d_fea_v,
+                                                          float* __restrict__ d_ext) {
   extern __shared__ float s_dl[];   // [2][B]
   for (int b = threadIdx.x; b < B; b += 256) {
     const float l0 = logits[2 * b], l1 = logits[2 * b + 1], mx = fmaxf(l0, l1);
@@ -294,39 +301,62 @@ __global__ void __launch_bounds__(256) nce_self_bwd_kernel(const bf16* __restric
     s_dl[B + b] = g * (1.f - p0);
   }
   __syncthreads();
-  const int b = blockIdx.y;
   const long ip = sel[0], in = sel[1];
-  const bf16* ab = fea + (long)b * CHW;
-  const bf16* pb = fea + ip * CHW;
-  const bf16* nb = fea + in * CHW;
-  const float dl0 = s_dl[b], dl1 = s_dl[B + b];
+  bf16* const d16 = reinterpret_cast<bf16*>(d_fea_v);
+  float* const d32 = reinterpret_cast<float*>(d_fea_v);
   for (long i = ((long)blockIdx.x * 256 + threadIdx.x) * 8; i < CHW; i += (long)gridDim.x * 256 * 8) {
-    float a[8], p[8], q[8], o[8];
-    load8(ab + i, a); load8(pb + i, p); load8(nb + i, q);
+    float p[8], q[8], dp[8], dq[8], op[8], oq[8];
+    load8((ip < B ? fea + ip * CHW : ext + (ip - B) * CHW) + i, p);
+    load8((in < B ? fea + in * CHW : ext + (in - B) * CHW) + i, q);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float da_p, dp_, da_n, dn_;
-      nce_grad(a[j], p[j], k, c0, da_p, dp_);
-      nce_grad(a[j], q[j], k, c0, da_n, dn_);
-      o[j] = dl0 * da_p + dl1 * da_n;
-    }
-    if (b == ip || b == in) {
-      // this row is also the broadcast positive (negative): its gradient sums over the whole batch
-      const bool is_p = b == ip, is_n = b == in;
-      for (int bb = 0; bb < B; ++bb) {
-        float x[8];
-        load8(fea + (long)bb * CHW + i, x);
+    for (int j = 0; j < 8; ++j) { dp[j] = 0.f; dq[j] = 0.f; op[j] = 0.f; oq[j] = 0.f; }
+    for (int b = 0; b < B; ++b) {
+      float a[8], o[8];
+      load8(fea + (long)b * CHW + i, a);
+      const float dl0 = s_dl[b], dl1 = s_dl[B + b];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float da_, dq_;
-          nce_grad(x[j], a[j], k, c0, da_, dq_);
-          if (is_p) o[j] = fmaf(s_dl[bb], dq_, o[j]);
-          if (is_n) o[j] = fmaf(s_dl[B + bb], dq_, o[j]);
-        }
+      for (int j = 0; j < 8; ++j) {
+        float da_p, dp_, da_n, dn_;
+        nce_grad(a[j], p[j], k, c0, da_p, dp_);
+        nce_grad(a[j], q[j], k, c0, da_n, dn_);
+        o[j] = dl0 * da_p + dl1 * da_n;
+        dp[j] = fmaf(dl0, dp_, dp[j]);
+        dq[j] = fmaf(dl1, dn_, dq[j]);
+      }
+      if (b == ip || b == in) {
+        // deferred: this row also receives the batch-summed gradient of the broadcast operand (both, if ip == in)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { if (b == ip) op[j] = o[j]; if (b == in) oq[j] = o[j]; }
+      } else if (OUT_BF16) {
+        store8(d16 + (long)b * CHW + i, o);
+      } else {
+        store8(d32 + (long)b * CHW + i, o);
       }
     }
-    if (d_fea != nullptr) store8(d_fea + (long)b * CHW + i, o);
-    else store8(d_fea_f32 + (long)b * CHW + i, o);
+    if (ip >= B || in >= B) {
+      // external rows: their (partial, this rank's anchors only) gradient goes to d_ext [2][CHW] fp32
+      if (ip >= B) store8(d_ext + (ip - B) * CHW + i, dp);
+      if (in >= B) store8(d_ext + (in - B) * CHW + i, dq);
+      if (ip < B) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) op[j] += dp[j];
+        if (OUT_BF16) store8(d16 + ip * CHW + i, op); else store8(d32 + ip * CHW + i, op);
+      }
+      if (in < B) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) oq[j] += dq[j];
+        if (OUT_BF16) store8(d16 + in * CHW + i, oq); else store8(d32 + in * CHW + i, oq);
+      }
+    } else if (ip == in) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) op[j] += dp[j] + dq[j];
+      if (OUT_BF16) store8(d16 + ip * CHW + i, op); else store8(d32 + ip * CHW + i, op);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { op[j] += dp[j]; oq[j] += dq[j]; }
+      if (OUT_BF16) { store8(d16 + ip * CHW + i, op); store8(d16 + in * CHW + i, oq); }
+      else { store8(d32 + ip * CHW + i, op); store8(d32 + in * CHW + i, oq); }
+    }
   }
 }
 
@@ -416,27 +446,33 @@ extern "C" int uncl_unpack_add(const float* src, const int* idx, float* dst, lon
   return uncl_check_launch("unpack_add");
 }
 
-extern "C" int uncl_nce_self_fwd(const void* fea, const long* sel, int B, long CHW, int HW, float k, float constant,
-                                 float* logits_scratch, float* loss_out, cudaStream_t stream) {
+extern "C" int uncl_nce_self_fwd(const void* fea, const long* sel, const void* ext, int B, long CHW, int HW, float k,
+                                 float constant, float* logits_scratch, float* loss_out, cudaStream_t stream) {
   UNCL_REQUIRE(B > 0 && CHW % 8 == 0 && HW > 0 && fea && sel && logits_scratch && loss_out, "nce_self_fwd: bad arguments");
   cudaMemsetAsync(logits_scratch, 0, 2 * B * sizeof(float), stream);
   int gx = grid_for(CHW / 8, 4) / B;
   if (gx < 1) gx = 1;
-  nce_self_fwd_kernel<<<dim3(gx, B), 256, 0, stream>>>(reinterpret_cast<const bf16*>(fea), sel, CHW, k, constant,
+  nce_self_fwd_kernel<<<dim3(gx, B), 256, 0, stream>>>(reinterpret_cast<const bf16*>(fea), sel,
+                                                      reinterpret_cast<const bf16*>(ext), B, CHW, k, constant,
                                                       1.f / (float)HW, logits_scratch);
   nce_ce_kernel<<<1, 32, 0, stream>>>(logits_scratch, B, loss_out);
   return uncl_check_launch("nce_self_fwd");
 }
 
-extern "C" int uncl_nce_self_bwd(const void* fea, const long* sel, int B, long CHW, int HW, float k, float constant,
-                                 const float* logits, const float* g_up, void* d_fea, int d_dtype, cudaStream_t stream) {
+extern "C" int uncl_nce_self_bwd(const void* fea, const long* sel, const void* ext, int B, long CHW, int HW, float k,
+                                 float constant, const float* logits, const float* g_up, void* d_fea, int d_dtype,
+                                 float* d_ext, cudaStream_t stream) {
   UNCL_REQUIRE(B > 0 && B <= 1024 && CHW % 8 == 0 && fea && sel && logits && g_up && d_fea, "nce_self_bwd: bad arguments");
-  int gx = grid_for(CHW / 8, 4) / B;
-  if (gx < 1) gx = 1;
-  nce_self_bwd_kernel<<<dim3(gx, B), 256, 2 * B * sizeof(float), stream>>>(
-      reinterpret_cast<const bf16*>(fea), sel, CHW, k, constant, 1.f / (float)HW, logits, B, g_up,
-      d_dtype == UNCL_F32 ? reinterpret_cast<float*>(d_fea) : nullptr,
-      d_dtype == UNCL_BF16 ? reinterpret_cast<bf16*>(d_fea) : nullptr);
+  UNCL_REQUIRE(d_dtype == UNCL_F32 || d_dtype == UNCL_BF16, "nce_self_bwd: bad d_dtype");
+  const int gx = grid_for(CHW / 8, 8);
+  if (d_dtype == UNCL_BF16)
+    nce_self_bwd_kernel<true><<<gx, 256, 2 * B * sizeof(float), stream>>>(
+        reinterpret_cast<const bf16*>(fea), sel, reinterpret_cast<const bf16*>(ext), CHW, k, constant, 1.f / (float)HW, logits,
+        B, g_up, d_fea, d_ext);
+  else
+    nce_self_bwd_kernel<false><<<gx, 256, 2 * B * sizeof(float), stream>>>(
+        reinterpret_cast<const bf16*>(fea), sel, reinterpret_cast<const bf16*>(ext), CHW, k, constant, 1.f / (float)HW, logits,
+        B, g_up, d_fea, d_ext);
   return uncl_check_launch("nce_self_bwd");
 }
 

@@ -19,7 +19,9 @@ class SimpleDiscriminator(nn.Module):
                                     nn.Conv2d(32, 1, 1)])
         self.tail = nn.ModuleList([nn.Identity(), nn.Linear(62 * 62, 1, bias=False)])
 
-    def forward(self, x):
+    def forward(self, x, want_features=True):
+        """want_features=False (an addition to the reference signature): skip the [N,2,1,1] feature statistics when only
+        the logits are used (the D step), second return value None."""
         if x.dim() != 4 or tuple(x.shape[1:]) != (1, 256, 256):
             raise ValueError("SimpleDiscriminator expects [N,1,256,256]")
         if not x.is_cuda:
@@ -27,5 +29,7 @@ class SimpleDiscriminator(nn.Module):
         m = self.model
         logits, fea = DiscFn.apply(x, m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias,
                                    self.tail[1].weight)
+        if not want_features:
+            return logits, None
         mean, con = PlaneMeanContrastFn.apply(fea)
         return logits, torch.cat([mean, con], dim=1)[:, :, None, None]

@@ -182,3 +182,48 @@ def all_gather_cat(t, group=None):
     dist.all_gather(parts, t.detach().contiguous(), group=group)
     parts[rank] = t
     return torch.cat(parts, dim=0)
+
+
+def is_parallel(group=None):
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def all_gather_flat(t, group=None):
+    """[world * len(t)] concatenation of a small 1-D per-rank tensor, no autograd (scores that only drive a selection)."""
+    world = dist.get_world_size(group)
+    out = torch.empty(world * t.numel(), device=t.device, dtype=t.dtype)
+    dist.all_gather_into_tensor(out, t.detach().contiguous().reshape(-1), group=group)
+    return out
+
+
+class BroadcastRowsFn(torch.autograd.Function):
+    """rows[j] = x[g_idx[j]] of the GLOBAL batch, on every rank, without the host learning who owns them.
+
+    x: this rank's [b, ...] slice of a batch split evenly over the ranks; g_idx: device int64 [R] global sample indices
+    (identical on all ranks).  Forward: every rank contributes its own rows (zeros for the others) to one all-reduce.
+    Backward: the partial gradients of the rows are summed over the ranks (all-reduce) and the owner adds them to its
+    samples - so a loss that uses a sample chosen over the global batch (infoNCE2's arg-max / arg-min TMQI naturalness,
+    GanTrainerImg.py:384-408) back-propagates into that sample on the rank that holds it, as under nn.DataParallel."""
+
+    @staticmethod
+    def forward(ctx, x, g_idx, group=None):
+        b = x.shape[0]
+        rank = dist.get_rank(group)
+        local = g_idx - rank * b
+        mine = (local >= 0) & (local < b)
+        rows = x.detach().index_select(0, local.clamp(0, b - 1))
+        rows = rows * mine.view(-1, *([1] * (x.dim() - 1))).to(rows.dtype)
+        dist.all_reduce(rows, op=dist.ReduceOp.SUM, group=group)
+        ctx.save_for_backward(local.clamp(0, b - 1), mine)
+        ctx.meta = (x.shape, x.dtype, group)
+        return rows
+
+    @staticmethod
+    def backward(ctx, d_rows):
+        local, mine = ctx.saved_tensors
+        shape, dtype, group = ctx.meta
+        d_rows = d_rows.contiguous().float()
+        dist.all_reduce(d_rows, op=dist.ReduceOp.SUM, group=group)
+        dx = torch.zeros(shape, device=d_rows.device, dtype=torch.float32)
+        dx.index_add_(0, local, d_rows * mine.view(-1, *([1] * (d_rows.dim() - 1))).to(d_rows.dtype))
+        return dx.to(dtype), None, None

@@ -17,8 +17,10 @@ changes a gradient that reaches an optimizer:
 Multi-GPU (one process per GPU, torch.distributed initialised): every rank takes an equal slice of the global batch.
 Per-sample-mean losses are scaled by 1/world and gradients are SUMMED over ranks with bucketed NCCL all-reduces
 (uncltmo_b200.dist.GradientBuckets) - the reference's counterpart is nn.DataParallel.  The all-pairs contrastive loss
-sees the all-gathered logits of the global batch.  The TMQI selections of infoNCE2 / pseudo_label_loss are made within
-a rank's slice when world > 1 (their loss weight is 1e-7 for epoch <= 6): a stated deviation from global-batch semantics.
+sees the all-gathered logits of the global batch.  The TMQI selections of infoNCE2 / pseudo_label_loss are made over the
+GLOBAL batch (all-gather of the scores; the chosen feature maps / statistics are broadcast from the rank that holds them
+and their gradient is returned to it - uncltmo_b200.losses, dist.BroadcastRowsFn), as under nn.DataParallel.
+The bf16 image path keeps all generator gradients in one flat buffer and sums it with ONE all-reduce, no flattening copy.
 """
 import torch
 import torch.distributed as dist
@@ -48,6 +50,11 @@ class GanTrainerStep:
         self.buckets_G = GradientBuckets(netG.parameters()).install_hooks() if self.world > 1 else None
         self.buckets_D = GradientBuckets(netD.parameters()) if self.world > 1 else None
 
+    def _generator_is_flat(self):
+        """True when the generator ran through train_graph (bf16 image path): every p.grad is a view of one flat buffer."""
+        fp = getattr(self.netG, "_flat", None)
+        return (not self.video) and getattr(self.netG, "precision", None) == "bf16" and fp is not None and fp.grads_attached()
+
     @staticmethod
     def _flat(t):
         return t.reshape(-1, t.shape[-3], t.shape[-2], t.shape[-1]).float()
@@ -68,10 +75,13 @@ class GanTrainerStep:
     # ------------------------------------------------------------------ D step
     def train_D(self, hdr_input, real_ldr_pos, real_ldr_neg, epoch):
         self.netD.zero_grad(set_to_none=True)
-        d_real_pos, _ = self.netD(self._flat(real_ldr_pos))
         with torch.no_grad():
             fake, _ = self._generate(hdr_input)
-        d_fake, _ = self.netD(fake.detach())
+        # D(real_pos) and D(fake) as ONE discriminator pass over the stacked batch (per-sample network: identical values,
+        # half the launches and twice the CTAs per launch); the feature statistics are not needed in the D step
+        pos = self._flat(real_ldr_pos)
+        logits, _ = self.netD(torch.cat([pos, fake.detach()]), want_features=False)
+        d_real_pos, d_fake = logits[:pos.shape[0]], logits[pos.shape[0]:]
         w = self.adv_weight_list[0] * (1.0 if epoch <= self.epoch_step1 else 1e-6)
         self.errD = w * losses.contrastive_D_loss(all_gather_cat(d_real_pos), all_gather_cat(d_fake))
         self.errD.backward()
@@ -123,9 +133,9 @@ class GanTrainerStep:
                 self._side = torch.cuda.Stream()
             self._side.wait_stream(cur)
         with torch.cuda.stream(self._side if fork else cur), torch.no_grad():
-            d_real_pos_bp, d_fea_real_pos = self.netD(pos)
-            _, d_fea_real_neg = self.netD(neg)
-            _, d_fea_input = self.netD(hdr)
+            nb = pos.shape[0]
+            lg, fe = self.netD(torch.cat([pos, neg, hdr]))      # one pass over the three gradient-free batches
+            d_real_pos_bp, d_fea_real_pos, d_fea_real_neg, d_fea_input = lg[:nb], fe[:nb], fe[nb:2 * nb], fe[2 * nb:]
         fake, fea_fake = self._generate(hdr_input)
         if fork:
             cur.wait_stream(self._side)
@@ -138,14 +148,17 @@ class GanTrainerStep:
         if self.struct_loss_factor:
             self.errG_struct = (self.struct_loss_factor / self.world) * self.struct_loss(fake, None, hdr, self.pyramid_weight_list)
             total = total + self.errG_struct
-        if self.buckets_G is not None:
+        flat_mode = self.world > 1 and self._generator_is_flat()
+        if self.buckets_G is not None and not flat_mode:
             self.buckets_G.arm()
         total.backward()
         del total
         self.errG_d = self.errG_d.detach()
         if self.errG_struct is not None:
             self.errG_struct = self.errG_struct.detach()
-        if self.buckets_G is not None:
+        if flat_mode:
+            dist.all_reduce(self.netG._flat.grad, op=dist.ReduceOp.SUM)    # the persistent flat gradient buffer, in place
+        elif self.buckets_G is not None:
             self.buckets_G.finish()
         self.optimizerG.step()
         return self.errG_d, self.errG_struct
