@@ -17,7 +17,10 @@ __device__ __forceinline__ void atomic_add_block(float v, float* dst, float* red
 // per-plane mean and mean local variance under the 11x11 gaussian (sigma 1.5, valid):  E_g[x^2] - E_g[x]^2
 // tile 32x32 outputs, halo 10, separable filter in shared memory.  sums[2*m] += sum x, sums[2*m+1] += sum var
 // ---------------------------------------------------------------------------------------------------------
-__constant__ float c_gauss11[11];
+// fspecial_gauss(11, 1.5) is separable: g2[i][j] = g[i] g[j], g = exp(-t^2 / 4.5) / sum (statically initialised: the library
+// keeps no mutable global and uploads nothing at run time)
+__constant__ float c_gauss11[11] = {1.028380084e-03f, 7.598758135e-03f, 3.600077213e-02f, 1.093606895e-01f, 2.130055377e-01f, 2.660117249e-01f,
+                                   2.130055377e-01f, 1.093606895e-01f, 3.600077213e-02f, 7.598758135e-03f, 1.028380084e-03f};
 
 __global__ void __launch_bounds__(256) plane_contrast_kernel(const float* __restrict__ x, long plane_stride, int H,
                                                             int W, float* __restrict__ sums) {
@@ -397,18 +400,7 @@ inline int cap_grid(long total, int block, int per_sm) {
   return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 
-bool g_gauss_ready = false;
-int ensure_gauss() {
-  // fspecial_gauss(11, 1.5) is separable: g2[i][j] = g[i] g[j], g = exp(-t^2 / 4.5) / sum
-  if (g_gauss_ready) return 0;
-  double g[11], s = 0;
-  for (int i = 0; i < 11; ++i) { g[i] = exp(-((i - 5) * (i - 5)) / (2.0 * 1.5 * 1.5)); s += g[i]; }
-  float gf[11];
-  for (int i = 0; i < 11; ++i) gf[i] = (float)(g[i] / s);
-  if (cudaMemcpyToSymbol(c_gauss11, gf, sizeof(gf)) != cudaSuccess) return -1;
-  g_gauss_ready = true;
-  return 0;
-}
+int ensure_gauss() { return 0; }
 
 }  // namespace
 
