@@ -52,17 +52,21 @@ G_ARGS = (1, 1, "sigmoid", 4, 4, "square_and_square_root", 32, 0, "unet", 0, 0, 
 
 
 def measured_peaks():
+    """(burst bf16 TFLOP/s, sustained bf16 TFLOP/s, HBM GB/s, source).  A kernel timed per launch in the instrumented pass
+    runs under burst conditions (short, cool, full clocks): its roofline denominator is the BURST figure."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json, sustained)"
-    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        burst = d.get("bf16_tflops", d.get("bf16_tflops_sustained"))
+        return burst, d.get("bf16_tflops_sustained", burst), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)"
+    return 1650.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
     FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, power=False):
+        self.power = power
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
@@ -83,10 +87,11 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
-        sm, reasons = [], set()
+        sm, reasons, watts = [], set(), []
         for r in rows:
             try:
                 sm.append(float(r[1]))
+                watts.append(float(r[3]))
                 out["sm_max_mhz"] = float(r[2])
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                     if "Active" in v and "Not" not in v:
@@ -97,14 +102,17 @@ class ClockSampler:
             out["sm_mhz"] = float(np.median(sm))
         out["reasons"] = sorted(reasons)
         out["samples"] = len(sm)
+        if self.power and watts:
+            out["power_w_median"], out["power_w_max"] = float(np.median(watts)), float(np.max(watts))
+            out["sm_mhz_min"] = float(np.min(sm))
         return out
 
 
 def cpu_reference_arm(steps, warmup, threads=None):
-    """The CPU oracle on the host cores.  One step = the generator on ONE 256x256 tile at batch 1 (the reference
-    runs tile by tile, utils/model_save_util.py:417-427); the rest of the frame path (normalise, pad, sequential
-    cross-fade, percentiles, back-to-colour) is timed once on the full 1080p frame with the generator stubbed out.
-    frame time = 60 * median(tile) + rest."""
+    """The CPU oracle on the host cores.  One step = one WHOLE 1080p frame through the oracle's restatement of
+    run_model_on_single_image2: log-lambda normalise, pad, the generator tile by tile at batch 1 (60 tiles, as the
+    reference runs them, utils/model_save_util.py:417-427), sequential cross-fade, np.percentile, back-to-colour, 8-bit
+    stretch.  Nothing is extrapolated."""
     import oracle
     from uncltmo_b200 import synth
     from uncltmo_b200.weights import make_generator_state_dict
@@ -112,27 +120,20 @@ def cpu_reference_arm(steps, warmup, threads=None):
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     sd = make_generator_state_dict()
-    rgb = torch.from_numpy(synth.hdr_frame(H, W, seed=0))
-    _, gray = oracle.log_lambda_normalise(rgb, LAMBDA)
-    gp, _, _ = oracle.resize_im(gray)
-    tiles = [gp[None, :, y:y + 256, x:x + 256].contiguous() for y in (0, 192, 384) for x in (0, 576, 1152, 1680)]
+    frames = [torch.from_numpy(synth.hdr_frame(H, W, seed=i)) for i in range(2)]
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        oracle.unet_forward(sd, tiles[i % len(tiles)])
+        col = oracle.tonemap_frame(frames[i % 2], LAMBDA, lambda t: oracle.unet_forward(sd, t)[0])
+        oracle.frame_path.to_uint8_stretch(col)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    t_tile = float(np.median(times))
-    t0 = time.perf_counter()
-    col = oracle.tonemap_frame(rgb, LAMBDA, lambda t: t * 0.5 + 0.25)
-    oracle.frame_path.to_uint8_stretch(col)
-    t_rest = time.perf_counter() - t0
-    t_frame = TILES * t_tile + t_rest
+    t_frame = float(np.mean(times))
     return {"value": 1.0 / t_frame, "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": "%d generator tiles at batch 1 (median %.1f ms/tile, x60 tiles) + the rest of the 1080p frame path "
-                      "timed once with the generator stubbed (%.2f s)" % (len(times), t_tile * 1e3, t_rest),
-            "ms_per_tile": t_tile * 1e3, "rest_s": t_rest}, float(np.sum(times)) + t_rest
+            "sample": "%d whole 1080p frames (60 tiles at batch 1 + the sequential frame path each), mean %.2f s/frame, "
+                      "%d warm-up frame(s)" % (len(times), t_frame, warmup),
+            "ms_per_frame": t_frame * 1e3}, float(np.sum(times))
 
 
 TRAIN_GFLOP_STEP = 4 * GFLOP_TILE * 16   # G fwd (D step) + G fwd (G step) + one merged backward, 16 images
@@ -173,7 +174,7 @@ def video_inference_workload(dev, precision, world, rank, frames=8, iters=2):
                        "parallelism": "tile chains sharded over %d rank(s), one NCCL all-gather per scene" % world}}
 
 
-def train_workload(dev, precision, steps, warmup, world=1, rank=0, video=False):
+def train_workload(dev, precision, steps, warmup, world=1, rank=0, video=False, weak=False):
     """256x256 image-TMO training step, global batch 8x2 = 16 images (GanTrainerImg.train_D + train_G, epoch-0 loss
     schedule, Adam as main_train_image.py builds it).  Strong scaling: ranks split the 16 images."""
     from uncltmo_b200 import _lib, synth
@@ -186,10 +187,15 @@ def train_workload(dev, precision, steps, warmup, world=1, rank=0, video=False):
     netG.load_state_dict(make_generator_state_dict())
     netD = SimpleDiscriminator(256, 1, 16, "none", "none", 0, 0).to(dev).train()
     netD.load_state_dict(make_discriminator_state_dict())
-    optG = torch.optim.Adam([p for p in netG.parameters() if p.requires_grad], lr=1e-5, betas=(0.5, 0.999), capturable=True, fused=True)
+    flat = precision == "bf16" and not video
+    if flat:   # Adam on the flat parameter buffer of the bf16 training path: one launch (uncltmo_b200/optim.py)
+        from uncltmo_b200.optim import FlatAdam
+        optG = FlatAdam(netG, lr=1e-5, betas=(0.5, 0.999))
+    else:
+        optG = torch.optim.Adam([p for p in netG.parameters() if p.requires_grad], lr=1e-5, betas=(0.5, 0.999), capturable=True, fused=True)
     optD = torch.optim.Adam(netD.parameters(), lr=1.5e-5, betas=(0.5, 0.999), capturable=True, fused=True)
     tr = GanTrainerStep(netG, netD, optG, optD)
-    b_local = max(1, 8 // world)
+    b_local = 8 if weak else max(1, 8 // world)
     mk = lambda a: torch.from_numpy(a).reshape(b_local, 2, 1, 256, 256)  # noqa: E731
     host = [(mk(synth.normalised_batch(2 * b_local, seed=40 + 10 * rank + i)).pin_memory(),
              mk(synth.ldr_batch(2 * b_local, seed=50 + 10 * rank + i)).pin_memory(),
@@ -251,13 +257,16 @@ def train_workload(dev, precision, steps, warmup, world=1, rank=0, video=False):
     what = "video TMO, 8 clips x 2 consecutive frames (recurrent generator, GanTrainer.py)" if video else \
         "16 images/step: train_D + train_G"
     return {"metric": "256^2 train steps/s (%s)" % what, "value": steps / (ms / 1e3), "unit": "steps/s",
-            "ms_per_step": ms / steps, "scaling": "strong", "execution": "CUDA graph replay of the whole iteration",
+            "ms_per_step": ms / steps, "scaling": "weak (16 images per GPU)" if weak else "strong",
+            "images_per_s": steps * 2 * b_local * world / (ms / 1e3), "execution": "CUDA graph replay of the whole iteration",
             "eager_launch_path": {"value": steps / (ms_eager / 1e3), "unit": "steps/s", "ms_per_step": ms_eager / steps,
-                                  "note": "same trainer without capture; launch-bound, and Adam(capturable=True) is slower eagerly"}, "dtype": "f32" if precision == "fp32" else "bf16 operands / f32 tensors (mixed)",
+                                  "note": "same trainer without capture; launch-bound, and Adam(capturable=True) is slower eagerly"}, "dtype": "f32" if precision == "fp32" else ("bf16 activations and gradient operands, f32 accumulation / parameters / optimizer" if flat else "bf16 operands / f32 tensors (mixed)"),
             "tflops_algorithmic": steps * TRAIN_GFLOP_STEP / ms, "gpu_launches": launches,
             "e2e": {"value": steps / (ms_e2e / 1e3), "unit": "steps/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 8},
             "config": {"global_batch": "8 x 2 crops = 16 images of 256x256", "per_gpu_images": 2 * b_local, "loss_schedule": "epoch 0",
-                       "optimizer": "torch.optim.Adam(lr 1e-5 / 1.5e-5, betas (0.5, 0.999), fused=True, capturable=True)", "parallelism": "dp%d, NCCL gradient all-reduce" % world}}
+                       "optimizer": ("uncltmo_b200.optim.FlatAdam (G, one launch) + torch Adam fused (D)" if flat else "torch.optim.Adam(fused=True, capturable=True)") + ", lr 1e-5 / 1.5e-5, betas (0.5, 0.999)",
+                       "droppath": "p = 0.05, fresh masks in both generator passes (reference schedule)",
+                       "parallelism": "dp%d, NCCL gradient all-reduce%s" % (world, " of the flat gradient buffer" if flat else "")}}
 
 
 def cpu_train_arm(threads=None):
@@ -285,7 +294,7 @@ def run_reference(args):
         return
     base, _ = cpu_reference_arm(args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_tile"], "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_frame"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": CONFIG,
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -304,6 +313,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
     ap.add_argument("--train-precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--sustain-s", type=float, default=2.5, help="seconds of back-to-back frames for the `sustained` field (0: skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -393,8 +403,18 @@ def main():
     ms_e2e = timed_e2e(args.steps)
     clocks = sampler.stop() if sampler else None
 
+    # endurance: the same step back to back for >= args.sustain_s seconds of device time, clocks and power sampled through it
+    sustained = None
+    if args.sustain_s > 0:
+        n_sus = max(args.steps, int(args.sustain_s * 1e3 / (ms_res / args.steps)) + 1)
+        sus_sampler = ClockSampler(local, power=True) if rank == 0 else None
+        ms_sus = timed(step_resident, n_sus)
+        sus_clocks = sus_sampler.stop() if sus_sampler else None
+        sustained = {"value": world * n_sus / (ms_sus / 1e3), "unit": "frames/s", "frames_per_gpu": n_sus, "seconds": ms_sus / 1e3,
+                     "ms_per_step": ms_sus / n_sus, "clocks": sus_clocks}
+
     # per-kernel device time (separate instrumented pass: an event pair around every C-ABI call)
-    roof = None
+    roof = roofline_hbm = None
     if rank == 0:
         per_call = {}
         reps = 3
@@ -410,7 +430,7 @@ def main():
         tot = {k: sum(v) / reps for k, v in per_call.items()}
         cnt = {k: len(v) // reps for k, v in per_call.items()}
         tc_ms = tot.get("uncl_conv3x3_tc", None) if args.precision == "bf16" else tot.get("uncl_conv3x3_simt")
-        peak, hbm, how = measured_peaks()
+        burst, sus_peak, hbm, how = measured_peaks()
         if tc_ms:
             name = "conv3x3_tc" if args.precision == "bf16" else "conv3x3_simt"
             n_launch = cnt["uncl_" + name]
@@ -419,23 +439,62 @@ def main():
             tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
             if os.path.exists(tpath):
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch_avg")
-            roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": how,
+            roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
+                    "frac": achieved / burst, "frac_of_sustained_peak": achieved / sus_peak, "traffic": traffic,
+                    "peak_source": how + ": burst figure (the kernel is timed per launch in a short instrumented pass)",
+                    "traffic_source": "profiles/conv_tc_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, per launch)",
                     "launches_per_step": n_launch, "avg_launch_ms": tc_ms / n_launch,
                     "algorithmic_gflop_per_launch_avg": TILES * GFLOP_TILE_TC / n_launch,
                     "share_of_step": tc_ms / sum(tot.values()),
                     "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
+        # memory-bound kernels of the frame path: ALGORITHMIC bytes per call (SURVEY.md 8d / DESIGN.md section 3) over the
+        # device time of the call, against the measured copy bandwidth
+        h1, w1 = 16 * (H // 16) + 16, 16 * (W // 16) + 16
+        algo = {"uncl_frame_normalise_pad": 28 * H * W, "uncl_tiles_gather": TILES * 65536 * 8,
+                "uncl_tiles_blend": TILES * 65536 * 4 + h1 * w1 * 4, "uncl_frame_postprocess": h1 * w1 * 4 + 24 * H * W,
+                "uncl_frame_to_u8": 15 * H * W, "uncl_percentile_pair": 4 * (h1 * w1 + 3 * H * W) // 2,
+                "uncl_conv_first": TILES * (256 * 256 * 4 + 254 * 254 * 32 * 2),
+                "uncl_maxpool2": int(TILES * 2 * 1.25 * (32 * 252 ** 2 + 64 * 122 ** 2 + 128 * 57 ** 2 + 256 * 24 ** 2) / 4)}
+        hbm_rows = []
+        for k, nbytes in algo.items():
+            if k in tot and cnt.get(k):
+                us = tot[k] / cnt[k] * 1e3
+                hbm_rows.append({"kernel": k[5:], "calls_per_step": cnt[k], "bytes": int(nbytes), "us": round(us, 2),
+                                 "frac": round(nbytes / (us * 1e-6) / 1e9 / hbm, 3)})
+        roofline_hbm = {"peak_gbs": hbm, "note": "bytes = algorithmic bytes per CALL (percentile_pair / maxpool2: mean over the "
+                        "calls of a step); us = device time per call, events around the C-ABI call", "kernels": hbm_rows}
 
     train = video = None
+    fp32_exact = {}
+    if not args.no_train and world == 1 and args.precision == "bf16":
+        # the exact path (fp32 CUDA cores end to end, generator rel-L2 7e-8 vs the reference): the same frame step
+        net32 = UNet(*G_ARGS, up_mode=0, precision="fp32").to(dev).eval()
+        net32.load_state_dict(make_generator_state_dict())
+        pipe32 = FramePipeline(net32)
+        for _ in range(2):
+            pipe32.tonemap(dev_frames[0], LAMBDA, uint8=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(4):
+            pipe32.tonemap(dev_frames[i % nframes], LAMBDA, uint8=True)
+        e1.record()
+        torch.cuda.synchronize()
+        fp32_exact["frames_per_s"] = 4 / (e0.elapsed_time(e1) / 1e3)
+        net32 = pipe32 = None
     if not args.no_train:
         net = pipe = None
         dev_frames = None
         torch.cuda.empty_cache()
         with torch.enable_grad():
-            train = train_workload(dev, args.train_precision, max(5, args.steps // 2), args.warmup, world, rank)
+            train = train_workload(dev, args.train_precision, max(10, args.steps), args.warmup, world, rank)
             exact = train_workload(dev, "fp32", 5, 3, 1, 0) if world == 1 else None
+            if world > 1:
+                weak = train_workload(dev, args.train_precision, max(10, args.steps), args.warmup, world, rank, weak=True)
+                train["weak_16_images_per_gpu"] = {k: weak[k] for k in ("value", "unit", "ms_per_step", "images_per_s", "scaling")}
         if exact is not None:
             train["fp32_exact_path"] = {"value": exact["value"], "unit": "steps/s", "ms_per_step": exact["ms_per_step"]}
+            fp32_exact["steps_per_s"] = exact["value"]
             if not args.no_cpu_baseline:
                 train["cpu_baseline"] = cpu_train_arm()
         # BASELINE.json configs[3] / configs[4]: the video generator (inference on a 1080p clip, 256^2 training step)
@@ -447,7 +506,7 @@ def main():
     if rank == 0:
         base = None
         if world == 1 and not args.no_cpu_baseline:
-            base, _ = cpu_reference_arm(steps=12, warmup=2)
+            base, _ = cpu_reference_arm(steps=8, warmup=1)
             base = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         fps = world * args.steps / (ms_res / 1e3)
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -457,8 +516,20 @@ def main():
                 "tflops_generator": world * args.steps * TILES * GFLOP_TILE / ms_res,
                 "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": "frames/s",
                         "h2d_bytes_per_step": 3 * H * W * 4, "d2h_bytes_per_step": H * W * 3},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": base, "clocks": clocks, "train": train,
-                "video": video}
+                "gpu_launches": launches, "roofline": roof, "roofline_hbm": roofline_hbm, "cpu_baseline": base,
+                "clocks": clocks, "sustained": sustained, "fp32_exact": fp32_exact or None, "train": train, "video": video}
+        # short scalars LAST: a reader that keeps only the tail of the line still sees every headline number
+        line["summary"] = {
+            "fps": round(fps, 1), "e2e_fps": round(line["e2e"]["value"], 1),
+            "sustained_fps": round(sustained["value"], 1) if sustained else None,
+            "conv_frac_of_burst_peak": round(roof["frac"], 3) if roof else None,
+            "train_steps_per_s": round(train["value"], 1) if train else None,
+            "train_weak_steps_per_s": round(train["weak_16_images_per_gpu"]["value"], 1) if train and "weak_16_images_per_gpu" in train else None,
+            "video_train_steps_per_s": round(video["train"]["value"], 1) if video else None,
+            "video_fps": round(video["inference"]["value"], 1) if video else None,
+            "fp32_exact_fps": round(fp32_exact["frames_per_s"], 1) if fp32_exact.get("frames_per_s") else None,
+            "fp32_exact_steps_per_s": round(fp32_exact["steps_per_s"], 1) if fp32_exact.get("steps_per_s") else None,
+            "n_gpus": world}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -299,6 +299,10 @@ int uncl_bias_grad_bf16(const void* dz, long img_stride, float* db, int N, int C
  * db[C] += the up-convolution's bias gradient (NULL to skip). */
 int uncl_convT2x2_s2d_bf16(const void* dY, long dy_img_stride, void* out, float* db, int N, int C, int H, int W, int H2,
                            int W2, uncl_stream_t stream);
+/* Weight AND bias gradient of the first conv (Conv2d(1, C, 3), unet_parts.py:57-87) in one pass over its pre-activation
+ * gradient dZ (blocked dense [N][C/8][H-2][W-2][8], fp32 or bf16): dW[9][C] += ..., db[C] += ... (db may be NULL). */
+int uncl_conv_first_wgrad_bias(const float* x, const void* dZ, int dz_dtype, float* dW, float* db, int N, int H, int W,
+                               int C, uncl_stream_t stream);
 /* 1x1 out conv + sigmoid backward (unet_parts.py:338-345, Unet_singleFrame.py:207-209) merged with the gradient that
  * arrives through the feature output and the ReLU of up_path.3.conv.conv1:  dl = d_out * o * (1 - o);
  * dz[c] = up[c] > 0 ? dl * w[c] + d_feat[c] : 0 (bf16 dense);  dw[c] += sum dl * up[c];  db_out += sum dl;

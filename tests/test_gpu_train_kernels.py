@@ -163,6 +163,18 @@ def test_out_conv_feature_backward():
     assert rel(dbu, got.double().sum(dim=(0, 2, 3))) < 1e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_first_conv_weight_and_bias_gradient(dtype):
+    n, c, h, w = 2, 32, 40, 45
+    x, dz = rnd(n, 1, h, w, seed=20), rnd(n, c, h - 2, w - 2, seed=21)
+    wt = torch.zeros(c, 1, 3, 3, dtype=torch.float64, requires_grad=True)
+    b = torch.zeros(c, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), wt, b).backward(dz.double())
+    dw, db = torch.zeros(9, c, device="cuda"), torch.zeros(c, device="cuda")
+    call("uncl_conv_first_wgrad_bias", x.cuda(), to_blocked(dz, dtype), _lib.DTYPE_OF[dtype], dw, db, n, h, w, c)
+    assert rel(dw, wt.grad.reshape(c, 9).t()) < 2e-6 and rel(db, b.grad) < 2e-6
+
+
 def test_pack_and_unpack_gathers():
     g = torch.Generator().manual_seed(1)
     src = torch.randn(5000, generator=g).cuda()
@@ -209,6 +221,9 @@ def test_self_nce_on_blocked_features(sel, use_ext):
     d = torch.empty((b, chw), device="cuda")
     d_ext = torch.zeros((2, chw), device="cuda") if use_ext else None
     call("uncl_nce_self_bwd", fb, s, eb, b, chw, hw, 1.0, 1e-2, logits, torch.tensor(0.7, device="cuda"), d, F32, d_ext)
+    if sel[0] == sel[1]:     # positive == negative: the loss is the constant log 2, the exact gradient is zero
+        assert fr.grad.abs().max().item() == 0.0 and d.abs().max().item() <= 1e-9
+        return
     assert rel(d, fr.grad) < 1e-5
     if use_ext:
         for j in range(2):

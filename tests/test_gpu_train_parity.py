@@ -69,8 +69,10 @@ def _nets(video, precision, droppath=None):
 # gradients: 0.42 / 0.23 / 0.10-0.18 / 0.01.)  A fixed per-tensor bound of 1e-2 is therefore not a property any bf16
 # implementation of this network can have; the full-tensor test below calibrates its bound on that intrinsic
 # sensitivity instead, and this test holds the gradient NORMS of the 16-image step to the stated bounds.
-GRAD_TOL_NORM = {"up_path.2": 2e-2, "up_path.3": 2e-2, "outc": 2e-2, "up_path.1": 5e-2, "up_path.0": 1e-1, "gcn": 2e-1,
-                 "down_path.3": 2e-1, "down_path.2": 5e-1, "down_path.1": 3e-1, "down_path.0": 2e-1, "inc": 1e-1}
+# (measured at 16 images, worst case over epochs 0 / 7 / 10 and the DropPath case: down_path.2 6.4e-2, down_path.1 1.7e-2,
+# every other group <= 1.6e-2)
+GRAD_TOL_NORM = {"up_path.2": 2e-2, "up_path.3": 2e-2, "outc": 2e-2, "up_path.1": 3e-2, "up_path.0": 5e-2, "gcn": 5e-2,
+                 "down_path.3": 5e-2, "down_path.2": 1.5e-1, "down_path.1": 5e-2, "down_path.0": 5e-2, "inc": 5e-2}
 
 
 def _norm_tol(k):

@@ -147,6 +147,46 @@ __global__ void __launch_bounds__(256) convT2x2_s2d_bf16_kernel(const bf16* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// first conv (C_in = 1) weight + bias gradient in one pass over dZ:  dW[t][c] += sum x[n, y+ky, x+kx] * dZ[n, c, y, x],
+// db[c] += sum dZ.  One thread takes the 8 channels of a channel block at one pixel (one 16 / 32-byte load) and keeps
+// 9 x 8 + 8 partial sums in registers; grid (chunks, N * C/8).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) conv_first_wgrad_bias_kernel(const float* __restrict__ x, const T* __restrict__ dZ,
+                                                                   float* __restrict__ dW, float* __restrict__ db, int H,
+                                                                   int W, int C) {
+  __shared__ float sm[8 * 32];
+  const int Cb = C / 8, cb = blockIdx.y % Cb, n = blockIdx.y / Cb;
+  const int Ho = H - 2, Wo = W - 2, HWo = Ho * Wo;
+  const T* g0 = dZ + ((long)n * Cb + cb) * HWo * 8;
+  const float* xn = x + (long)n * H * W;
+  float acc[10][8];
+#pragma unroll
+  for (int t = 0; t < 10; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < HWo; p += gridDim.x * 256) {
+    const int oy = p / Wo, ox = p - oy * Wo;
+    float g[8];
+    load8(g0 + (long)p * 8, g);
+    const float* xi = xn + (long)oy * W + ox;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float xv = __ldg(xi + (t / 3) * W + t % 3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(xv, g[j], acc[t][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[9][j] += g[j];
+  }
+#pragma unroll
+  for (int t = 0; t < 10; ++t) {
+    float* dst = t < 9 ? dW + t * C + cb * 8 : (db != nullptr ? db + cb * 8 : nullptr);
+    if (dst != nullptr) block_reduce8_atomic(acc[t], dst, sm);   // (uniform branch: every thread takes it)
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // out conv (1x1, C = 32 -> 1) + sigmoid backward, merged with the feature-path gradient and the ReLU of `up`:
 //   dl = d_out * o * (1 - o);  dz[c] = up[c] > 0 ? dl * w[c] + d_feat[c] : 0
 //   dw[c] += sum dl * up[c];  db_out += sum dl;  db_up[c] += sum dz[c]
@@ -416,6 +456,21 @@ extern "C" int uncl_convT2x2_s2d_bf16(const void* dY, long dy_img_stride, void* 
   convT2x2_s2d_bf16_kernel<<<dim3(chunks, N * 4 * (C / 8)), 256, 0, stream>>>(
       reinterpret_cast<const bf16*>(dY), dy_img_stride, reinterpret_cast<bf16*>(out), db, C, H, W, H2, W2);
   return uncl_check_launch("convT2x2_s2d_bf16");
+}
+
+extern "C" int uncl_conv_first_wgrad_bias(const float* x, const void* dZ, int dz_dtype, float* dW, float* db, int N, int H,
+                                          int W, int C, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && C % 8 == 0 && H > 2 && W > 2 && x && dZ && dW, "conv_first_wgrad_bias: bad arguments");
+  int chunks = ceil_div((H - 2) * (W - 2), 256 * 8);
+  if (chunks > 32) chunks = 32;
+  const dim3 grid(chunks, N * (C / 8));
+  if (dz_dtype == UNCL_BF16)
+    conv_first_wgrad_bias_kernel<bf16><<<grid, 256, 0, stream>>>(x, reinterpret_cast<const bf16*>(dZ), dW, db, H, W, C);
+  else if (dz_dtype == UNCL_F32)
+    conv_first_wgrad_bias_kernel<float><<<grid, 256, 0, stream>>>(x, reinterpret_cast<const float*>(dZ), dW, db, H, W, C);
+  else
+    return uncl_set_error(UNCL_EINVAL, "conv_first_wgrad_bias: bad dz_dtype");
+  return uncl_check_launch("conv_first_wgrad_bias");
 }
 
 extern "C" int uncl_outc_feat_bwd(const float* d_out, const float* out, const void* up, long up_img_stride,

@@ -388,9 +388,8 @@ def backward_train(S, d_out, d_feat):
         call("uncl_skip_pool_bwd", S.cat[i], st(S.cat[i]), dcats[i], dpool, dz, fp.g(prod_bias + ".bias"), n, c, s, s)
     # ---- inc: conv1 (32 -> 32) and the first conv (1 -> 32, fp32 CUDA cores)
     wgrad("inc1", S.a0, f, 254, dz, f, 0)
-    dz_a0 = dgrad("inc1", dz, f, 252, f, 2, S.a0, out_dtype=torch.float32)
-    call("uncl_relu_bwd_bias", dz_a0, None, 0, fp.g("inc.conv.conv.bias"), n, f, 254 * 254, 0)
-    call("uncl_conv_first_wgrad", S.x, dz_a0, fp.stage_view("inc0", 9 * f), n, 256, 256, f)
+    dz_a0 = dgrad("inc1", dz, f, 252, f, 2, S.a0)
+    call("uncl_conv_first_wgrad_bias", S.x, dz_a0, BF16, fp.stage_view("inc0", 9 * f), fp.g("inc.conv.conv.bias"), n, 256, 256, f)
     # ---- GEMM-layout weight gradients -> parameter layout, accumulated into the flat gradient buffer
     call("uncl_unpack_add", fp.stage, fp.unpack_idx, fp.grad, fp.total)
 
