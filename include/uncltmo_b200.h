@@ -88,6 +88,12 @@ int uncl_convT2x2_tc(const void* in, long in_img_stride, const void* w_packed, c
                      long out_img_stride, int out_dtype, int N, int C, int H, int W, int H2, int W2,
                      uncl_stream_t stream);
 
+/* The same GEMM with C_in != C: the exact path's three-term bf16 split, in = [x_hi | x_hi | x_lo] (C_in = 3C) from
+ * uncl_split_bf16, w_packed = packing.convT2x2_tc_split ([w_hi ; w_lo ; w_hi]). */
+int uncl_convT2x2_tc_cin(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                         long out_img_stride, int out_dtype, int N, int C_in, int C, int H, int W, int H2, int W2,
+                         uncl_stream_t stream);
+
 /* Video recurrence for kernels without a `prev` input: dst[:, :r] = src[:, :r] (r <= 8).  Unet.py:244, 270. */
 int uncl_splice_channels(void* dst, long dst_img_stride, const void* src, long src_img_stride, int r, int N, int HW,
                          int dtype, uncl_stream_t stream);
@@ -101,6 +107,11 @@ int uncl_maxpool2(const void* in, long in_img_stride, const void* prev, long pre
 int uncl_outc_sigmoid(const void* in, long in_img_stride, const float* w, const float* b, float* out, float* logit,
                       int N, int C, int HW, int dtype, uncl_stream_t stream);
 
+/* fp32 blocked [N][C/8][HW][8] (image stride in elements) -> bf16 blocked [N][3C/8][HW][8] = [hi | hi | lo] with
+ * hi = bf16(x), lo = bf16(x - hi): the activation operand of the exact tensor-core path, where every product is the
+ * three-term sum x_hi.w_hi + x_hi.w_lo + x_lo.w_hi accumulated in fp32 (relative error ~2^-16 instead of bf16's 2^-9). */
+int uncl_split_bf16(const float* in, long in_img_stride, void* out, long out_img_stride, int N, int C, long HW,
+                    uncl_stream_t stream);
 /* dense fp32 <-> bf16 conversion of a blocked tensor (n elements, multiple of 8) */
 int uncl_convert(const void* in, int in_dtype, void* out, int out_dtype, long n, uncl_stream_t stream);
 

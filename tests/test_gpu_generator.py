@@ -82,6 +82,28 @@ def test_module_forward_surface(oracle_run):
     assert rel(out, o_out) <= 1e-4 and rel(feats, o_up) <= 1e-5
 
 
+def test_exact_path_on_tensor_cores(oracle_run, golden):
+    """precision='fp32_tc': every 3x3 / k2 s2 convolution as a three-term bf16 split on tcgen05 (fp32 activations and
+    accumulation).  Gate: BASELINE.json's fp32/TF32 bound, generator rel-L2 <= 1e-4; measured values are printed."""
+    sd, x, o_out, o_up, inter = oracle_run
+    net = make("fp32_tc")
+    keep = {}
+    out, up, logit, _ = net._run_frame(x.cuda(), want_logit=True, keep=keep)
+    errs = {"out": rel(out, o_out), "out_vs_reference_fixture": rel(out, golden["g_img_out"]), "logit": rel(logit, inter["logit"]),
+            "up_x": rel(blocked_to_nchw(up), o_up), "gcn": rel(blocked_to_nchw(keep["gcn"]), inter["gcn"])}
+    print("fp32_tc generator vs oracle:", {k: "%.1e" % v for k, v in errs.items()})
+    assert errs["out"] <= 1e-4 and errs["out_vs_reference_fixture"] <= 1e-4
+    assert errs["logit"] <= 1e-3 and errs["up_x"] <= 1e-4
+    _, oidx = oracle.gcn_block(sd, inter["skips"][4], return_idx=True)
+    agree = (keep["idx"].cpu().long().sort(dim=-1)[0] == oidx.sort(dim=-1)[0]).float().mean().item()
+    assert agree >= 0.995
+    # the video generator (recurrent hand-over through the split path)
+    xv = gi.video_input()
+    o_v, _ = oracle.unet_video_forward(sd, xv)
+    v, _ = make("fp32_tc", UNetVideo)(xv.cuda())
+    assert rel(v, o_v) <= 1e-4
+
+
 def test_fused_outc_path(oracle_run):
     _, x, o_out, _, inter = oracle_run
     net = make("bf16")

@@ -222,7 +222,7 @@ def test_self_nce_on_blocked_features(sel, use_ext):
     d_ext = torch.zeros((2, chw), device="cuda") if use_ext else None
     call("uncl_nce_self_bwd", fb, s, eb, b, chw, hw, 1.0, 1e-2, logits, torch.tensor(0.7, device="cuda"), d, F32, d_ext)
     if sel[0] == sel[1]:     # positive == negative: the loss is the constant log 2, the exact gradient is zero
-        assert fr.grad.abs().max().item() == 0.0 and d.abs().max().item() <= 1e-9
+        assert fr.grad.abs().max().item() <= 1e-12 and d.abs().max().item() <= 1e-9
         return
     assert rel(d, fr.grad) < 1e-5
     if use_ext:

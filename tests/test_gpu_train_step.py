@@ -158,3 +158,27 @@ def test_graph_replay_matches_eager_steps():
         assert rel(gB(hdr[0])[0], gA(hdr[0])[0]) < 2e-2
     with pytest.raises(ValueError):
         GanTrainerStep(gA, dA, torch.optim.Adam(gA.parameters()), torch.optim.Adam(dA.parameters())).capture(hdr, None, pos, neg, 0)
+
+
+def test_capture_after_eager_steps_on_the_default_stream():
+    """The same trainer first steps eagerly on the legacy default stream and is then captured (what bench.py does): the
+    nested graph-block autograd of the bf16 path must not tie parameter bookkeeping to the legacy stream."""
+    from uncltmo_b200.optim import FlatAdam
+    hdr = torch.from_numpy(synth.normalised_batch(4, seed=4)).reshape(2, 2, 1, 256, 256).cuda()
+    pos = torch.from_numpy(synth.ldr_batch(4, seed=5)).reshape(2, 2, 1, 256, 256).cuda()
+    neg = torch.from_numpy(synth.ldr_batch(4, seed=6)).reshape(2, 2, 1, 256, 256).cuda()
+    netG = UNet(*G_ARGS, up_mode=0, precision="bf16").cuda().train()
+    netG.load_state_dict(make_generator_state_dict())
+    netD = SimpleDiscriminator(256, 1, 16, "none", "none", 0, 0).cuda().train()
+    netD.load_state_dict(make_discriminator_state_dict())
+    tr = GanTrainerStep(netG, netD, FlatAdam(netG, lr=1e-4, betas=(0.5, 0.999)),
+                        torch.optim.Adam(netD.parameters(), lr=1e-4, betas=(0.5, 0.999), capturable=True, fused=True))
+    for _ in range(2):
+        eg, es = tr.step(hdr, None, pos, neg, 0)
+    torch.cuda.synchronize()
+    first = es.item()
+    tr.capture(hdr, None, pos, neg, 0, warmup=1)
+    for _ in range(3):
+        rg, rs = tr.replay(hdr, None, pos, neg, 0)
+    torch.cuda.synchronize()
+    assert np.isfinite(rs.item()) and rs.item() < first      # training continued through the replays

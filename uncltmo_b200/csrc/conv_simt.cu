@@ -427,6 +427,39 @@ extern "C" int uncl_splice_channels(void* dst, long dst_img_stride, const void* 
   return uncl_check_launch("splice_channels");
 }
 
+// fp32 blocked [N][C/8][HW][8] (image stride in_img_stride) -> bf16 blocked [N][3C/8][HW][8] = [hi | hi | lo],
+// hi = bf16(x), lo = bf16(x - hi): the A operand of a three-term bf16 product x_hi.w_hi + x_hi.w_lo + x_lo.w_hi
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ in, long in_img_stride,
+                                                        bf16* __restrict__ out, long out_img_stride, int Cb, long HW,
+                                                        long total) {
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const long p = i % HW;
+    const int cb = (int)((i / HW) % Cb);
+    const long n = i / (HW * Cb);
+    float v[8], hi[8], lo[8];
+    load8(in + n * in_img_stride + ((long)cb * HW + p) * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      hi[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+      lo[j] = v[j] - hi[j];
+    }
+    bf16* o = out + n * out_img_stride + ((long)cb * HW + p) * 8;
+    store8(o, hi);
+    store8(o + (long)Cb * HW * 8, hi);
+    store8(o + (long)2 * Cb * HW * 8, lo);
+  }
+}
+
+extern "C" int uncl_split_bf16(const float* in, long in_img_stride, void* out, long out_img_stride, int N, int C, long HW,
+                               cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && C % 8 == 0 && HW > 0 && in && out && in_img_stride % 8 == 0 && out_img_stride % 8 == 0,
+               "split_bf16: bad arguments");
+  const long total = (long)N * (C / 8) * HW;
+  split_bf16_kernel<<<grid1d(total), 256, 0, stream>>>(in, in_img_stride, reinterpret_cast<bf16*>(out), out_img_stride, C / 8, HW,
+                                                       total);
+  return uncl_check_launch("split_bf16");
+}
+
 extern "C" int uncl_convert(const void* in, int in_dtype, void* out, int out_dtype, long n, cudaStream_t stream) {
   UNCL_REQUIRE(n > 0 && n % 8 == 0, "convert: element count must be a positive multiple of 8");
   const long n8 = n / 8;

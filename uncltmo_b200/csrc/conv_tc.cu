@@ -736,10 +736,11 @@ extern "C" int uncl_conv3x3_tc_dgrad(const void* in, long in_img_stride, const v
 
 // ConvTranspose2d(C, C, 2, stride=2) as a GEMM [pixels x C] . [C x 4C] with a pixel-shuffle epilogue.
 // w_packed: bf16 [NS][C/16][1][2][NT][8], column j = (dy*2+dx)*C + co, NT = min(4C, 128).
-extern "C" int uncl_convT2x2_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
-                                long out_img_stride, int out_dtype, int N, int C, int H, int W, int H2, int W2,
-                                cudaStream_t stream) {
-  UNCL_REQUIRE(N > 0 && C % 32 == 0 && H2 >= 2 * H && W2 >= 2 * W && W <= 128, "convT2x2_tc: unsupported C=%d W=%d", C, W);
+static int convT2x2_tc_impl(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                            long out_img_stride, int out_dtype, int N, int C_in, int C, int H, int W, int H2, int W2,
+                            cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && C % 32 == 0 && C_in % 16 == 0 && H2 >= 2 * H && W2 >= 2 * W && W <= 128,
+               "convT2x2_tc: unsupported C_in=%d C=%d W=%d", C_in, C, W);
   UNCL_REQUIRE(out_dtype == UNCL_F32 || out_dtype == UNCL_BF16, "convT2x2_tc: bad out_dtype");
   TcParams p{};
   const int n_total = 4 * C;
@@ -750,12 +751,26 @@ extern "C" int uncl_convT2x2_tc(const void* in, long in_img_stride, const void* 
   p.out = out;
   p.out_f32 = out_dtype == UNCL_F32;
   p.out_img_stride = out_img_stride;
-  p.N = N; p.C_in = C; p.C_out = C; p.pad = 0;
+  p.N = N; p.C_in = C_in; p.C_out = C; p.pad = 0;
   p.Ho = H; p.Wo = W;
   p.act = UNCL_ACT_NONE;
   p.ntaps = 1;
   p.sh_C = C; p.sh_H2 = H2; p.sh_W2 = W2;
-  return launch_tc(p, in, in_img_stride, N, C, H, W, 1, 2 * C, "convT2x2_tc", stream);
+  return launch_tc(p, in, in_img_stride, N, C_in, H, W, 1, 2 * C, "convT2x2_tc", stream);
+}
+
+extern "C" int uncl_convT2x2_tc(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                                long out_img_stride, int out_dtype, int N, int C, int H, int W, int H2, int W2,
+                                cudaStream_t stream) {
+  return convT2x2_tc_impl(in, in_img_stride, w_packed, bias, out, out_img_stride, out_dtype, N, C, C, H, W, H2, W2, stream);
+}
+
+// The same GEMM with C_in input channels != C output channels: the exact path feeds the three-term bf16 split
+// [x_hi | x_hi | x_lo] (C_in = 3C) against [w_hi ; w_lo ; w_hi] (packing.convT2x2_tc_split).
+extern "C" int uncl_convT2x2_tc_cin(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                                    long out_img_stride, int out_dtype, int N, int C_in, int C, int H, int W, int H2, int W2,
+                                    cudaStream_t stream) {
+  return convT2x2_tc_impl(in, in_img_stride, w_packed, bias, out, out_img_stride, out_dtype, N, C_in, C, H, W, H2, W2, stream);
 }
 
 // 1x1 (optionally grouped) convolution as a tensor-core GEMM [pixels x C_in/g] . [C_in/g x C_out/g] per group:

@@ -83,10 +83,15 @@ def read_hdr_image(path):
             im = im[()]
             im = im.get("hdr_image", im) if isinstance(im, dict) else im
         return np.asarray(im, dtype=np.float32)
+    if path.lower().endswith(".dng"):
+        # the reference reads camera RAW through imageio's FreeImage plugin (hdr_image_util.py:35-53); neither imageio nor
+        # a RAW decoder is a dependency here and OpenCV cannot decode DNG: fail with the reason instead of "cannot decode"
+        raise IOError("%s: .dng (camera RAW) needs imageio + FreeImage as in the reference; convert to .hdr / .exr / .npy" % path)
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")     # recent OpenCV builds refuse .exr without it
     import cv2
     im = cv2.imread(path, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_COLOR)
     if im is None:
-        raise IOError("cannot decode %s" % path)
+        raise IOError("cannot decode %s (OpenCV: Radiance .hdr and OpenEXR are supported)" % path)
     return np.ascontiguousarray(im[..., ::-1], dtype=np.float32)
 
 

@@ -19,7 +19,7 @@ extensions = common.EXTENSIONS
 default_params = {"model_path": "model_weights_retrain20220815",
                   "model_name": "11_08_lr15D_size268_D_[1,1,1]_pad_0_G_ssr_doubleConvT__d1.0_struct_1.0[1,1,1]__trans2_replicate__noframe__min_log_0.1hist_fit_",
                   "input_images_path": "input_images",
-                  "f_factor_path": "lambda_data/input_images_lambdas.npy",
+                  "f_factor_path": "lambda_data/input_images_lambdas_HDRSdataset.npy",
                   "output_path": "output",
                   "mean_hist_path": "lambda_data/ldr_avg_hist_900_images_20_bins.npy",
                   "lambda_output_path": "lambda_data",

@@ -6,9 +6,13 @@ every operator runs as an sm_100a kernel from libuncltmo_b200.so.  Only the ship
 built (SURVEY.md §5 "config"); anything else raises at construction - there is no fallback.
 
 precision:
-  "fp32" - CUDA-core fp32 kernels (generator rel-L2 <= 1e-4 vs the reference).
-  "bf16" - bf16 activations; the 3x3 convolutions run on tcgen05 tensor cores (conv_tc.cu), fp32 accumulation;
-           the KNN graph of the bottleneck stays fp32 (rel-L2 <= 1e-2).
+  "fp32"    - CUDA-core fp32 kernels (generator rel-L2 <= 1e-4 vs the reference).
+  "bf16"    - bf16 activations; the 3x3 convolutions run on tcgen05 tensor cores (conv_tc.cu), fp32 accumulation;
+              the KNN graph of the bottleneck stays fp32 (rel-L2 <= 1e-2).
+  "fp32_tc" - the exact path ON the tensor cores (inference): fp32 activations, every 3x3 / k2 s2 convolution as a
+              three-term bf16 split x_hi.w_hi + x_hi.w_lo + x_lo.w_hi with fp32 accumulation (~2^-16 per product instead
+              of bf16's 2^-9; rel-L2 <= 1e-4), through the same tcgen05 kernels with 3x the input channels; the graph
+              block stays on the fp32 CUDA-core kernels.
 """
 import torch
 import torch.nn as nn
@@ -57,8 +61,8 @@ class _GeneratorBase(nn.Module):
             raise NotImplementedError("uncltmo_b200 builds the shipped generator configuration only; unsupported: %r "
                                       "(bilinear=%r up_mode=%r doubleConvTranspose=%r)"
                                       % (bad, bilinear, up_mode, doubleConvTranspose))
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in ("fp32", "bf16", "fp32_tc"):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'fp32_tc'")
         self.precision = precision
         self.to_crop = to_crop
         self.depth = depth
@@ -127,11 +131,13 @@ class _GeneratorBase(nn.Module):
 
     def _pack(self):
         tc = self.precision == "bf16"
+        split = self.precision == "fp32_tc"
         P = {}
 
         def conv(name, m, transposed):
             w9 = packing.conv3x3_taps(m.weight.detach(), transposed)
-            P[name] = (packing.conv3x3_tc(w9) if tc else w9, m.bias.detach().float().contiguous())
+            wp = packing.conv3x3_tc(w9) if tc else (packing.conv3x3_tc_split(w9) if split else w9)
+            P[name] = (wp, m.bias.detach().float().contiguous())
 
         with torch.no_grad():
             P["inc0"] = (packing.conv_first(self.inc.conv.conv.weight.detach()), self.inc.conv.conv.bias.detach().float().contiguous())
@@ -151,7 +157,8 @@ class _GeneratorBase(nn.Module):
                 P["g_fc1_split"] = (packing.pointwise_tc_split(g.fc1[0].weight.detach()), P["g_fc1"][1])
             for i in range(4):
                 u = self.up_path[i]
-                P["u%d_up" % i] = (packing.convT2x2_tc(u.up.weight.detach()) if tc else packing.convT2x2(u.up.weight.detach()),
+                wu = u.up.weight.detach()
+                P["u%d_up" % i] = (packing.convT2x2_tc(wu) if tc else (packing.convT2x2_tc_split(wu) if split else packing.convT2x2(wu)),
                                    u.up.bias.detach().float().contiguous())
                 conv("u%d_0" % i, u.conv.conv, True)
                 conv("u%d_1" % i, u.conv.conv1, True)
@@ -170,6 +177,11 @@ class _GeneratorBase(nn.Module):
                 ow, ob, out_img, out_logit = fuse
                 call("uncl_conv3x3_tc", src, src_stride, wt, b, dst, dst_stride, _lib.BF16, n, ci, h, w, co, pad, ACT_RELU,
                      emit_skip, 1, ow, ob, out_img, out_logit)
+        elif self.precision == "fp32_tc":
+            xs = torch.empty((n, 3 * ci // 8, h, w, 8), device=src.device, dtype=torch.bfloat16)
+            call("uncl_split_bf16", src, src_stride, xs, xs.stride(0), n, ci, h * w)
+            call("uncl_conv3x3_tc", xs, xs.stride(0), wt, b, dst, dst_stride, _lib.F32, n, 3 * ci, h, w, co, pad, ACT_RELU,
+                 emit_skip, 0, None, None, None, None)
         else:
             call("uncl_conv3x3_simt", src, src_stride, wt, b, dst, dst_stride, n, ci, h, w, co, pad, ACT_RELU,
                  emit_skip, _lib.F32)
@@ -288,6 +300,14 @@ class _GeneratorBase(nn.Module):
                     call("uncl_splice_channels", up, st(up), pv, st(pv), up_c // 32, n, up_s * up_s, dt)
                 call("uncl_convT2x2_tc", up, st(up), P["u%d_up" % i][0], P["u%d_up" % i][1], dst, st(cb), _lib.BF16, n,
                      up_c, up_s, up_s, sk_s, sk_s)
+            elif self.precision == "fp32_tc":
+                if pv is not None:
+                    state[5 + i] = up[:, :1].clone()
+                    call("uncl_splice_channels", up, st(up), pv, st(pv), up_c // 32, n, up_s * up_s, dt)
+                xs = torch.empty((n, 3 * up_c // 8, up_s, up_s, 8), device=dev, dtype=torch.bfloat16)
+                call("uncl_split_bf16", up, st(up), xs, st(xs), n, up_c, up_s * up_s)
+                call("uncl_convT2x2_tc_cin", xs, st(xs), P["u%d_up" % i][0], P["u%d_up" % i][1], dst, st(cb), _lib.F32, n,
+                     3 * up_c, up_c, up_s, up_s, sk_s, sk_s)
             else:
                 call("uncl_convT2x2", up, st(up), pv, st(pv) if pv is not None else 0,
                      up_c // 32 if pv is not None else 0, P["u%d_up" % i][0], P["u%d_up" % i][1], dst, st(cb), n, up_c,
@@ -410,22 +430,26 @@ class UNet(_GeneratorBase):
         out, _, _, _ = self._run_frame(x, droppath_scale=scale, want_features=False)
         return out, None
 
-    def _train_bf16(self, x, scale):
-        """bf16-activation training pass as ONE autograd node (uncltmo_b200/train_graph.py)."""
+    def _train_bf16(self, x, scale, through_autograd=False):
+        """bf16-activation training pass as ONE autograd node (uncltmo_b200/train_graph.py).  through_autograd: parameter
+        gradients are returned to autograd (hooks / DDP / any optimizer see them) instead of being accumulated into the flat
+        gradient buffer as a side effect."""
         from .train_graph import GeneratorTrainFn, flat_params
         if x.dim() != 4 or tuple(x.shape[1:]) != (1, 256, 256) or not x.is_cuda:
             raise ValueError("the generator expects CUDA [N,1,256,256] inputs")
-        flat_params(self)
+        fp = flat_params(self)
         anchor = getattr(self, "_anchor", None)
         if anchor is None or anchor.device != x.device:
             anchor = self._anchor = torch.zeros(1, device=x.device, requires_grad=True)
+        if through_autograd:
+            return GeneratorTrainFn.apply(x, anchor, self, scale, *[p for _, p in fp.named if p.requires_grad])
         return GeneratorTrainFn.apply(x, anchor, self, scale)
 
     def forward(self, x, apply_crop=True, diffY=0, diffX=0):
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             if self.precision == "bf16" and not x.requires_grad:
                 from . import autograd as A
-                out, up = self._train_bf16(x, self._droppath_scale(x.shape[0], x.device))
+                out, up = self._train_bf16(x, self._droppath_scale(x.shape[0], x.device), through_autograd=True)
                 feats = A.BlockedToNCHW.apply(up)
             else:
                 out, feats = self._forward_train(x, self._droppath_scale(x.shape[0], x.device))

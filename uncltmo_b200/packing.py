@@ -63,6 +63,24 @@ def conv3x3_tc_layout(w9):
     return t.permute(4, 1, 0, 2, 5, 3).contiguous()    # ns, chunk, tap, half, n, k8
 
 
+def _hi_lo(w):
+    hi = w.float().to(torch.bfloat16).float()
+    return hi, w.float() - hi
+
+
+def conv3x3_tc_split(w9):
+    """[9][C_in][C_out] fp32 -> the B operand of the exact (three-term bf16 split) tensor-core conv: input channels
+    [w_hi ; w_lo ; w_hi] (3 C_in), matching uncl_split_bf16's [x_hi | x_hi | x_lo]; packed like conv3x3_tc for (3 C_in, C_out)."""
+    hi, lo = _hi_lo(w9)
+    return conv3x3_tc(torch.cat([hi, lo, hi], dim=1))
+
+
+def convT2x2_tc_split(w):
+    """ConvTranspose2d k2 s2 weight [C_in][C_out][2][2] -> convT2x2_tc layout of [w_hi ; w_lo ; w_hi] (3 C_in rows)."""
+    hi, lo = _hi_lo(w)
+    return convT2x2_tc(torch.cat([hi, lo, hi], dim=0))
+
+
 def convT2x2(w):
     """ConvTranspose2d k2 s2 weight [C_in][C_out][2][2] -> [C_in][4][C_out] fp32 (pos = dy*2+dx)."""
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], 4, w.shape[1]).contiguous().float()

@@ -187,8 +187,23 @@ class FlatParams:
         return P
 
     def g(self, key):
-        """gradient view (flat buffer) of parameter `key`"""
-        return self.view(self.grad, key)
+        """gradient view of parameter `key` in the buffer the running backward accumulates into (`self.gbuf`: the flat
+        p.grad buffer in side-effect mode, a scratch `delta` buffer handed to autograd in autograd mode)"""
+        return self.view(self.gbuf, key)
+
+    def begin_backward(self, through_autograd):
+        if through_autograd:
+            if getattr(self, "delta", None) is None:
+                self.delta = torch.zeros_like(self.grad)
+            else:
+                self.delta.zero_()
+            self.gbuf = self.delta
+        else:
+            if not self.grads_attached():     # first backward after zero_grad(set_to_none=True): a new accumulation cycle
+                self.grad.zero_()
+                self.attach_grads()
+            self.gbuf = self.grad
+        self.stage.zero_()
 
     def stage_view(self, name, numel):
         o = self.stage_off[name]
@@ -257,16 +272,22 @@ def forward_train(net, x, droppath_scale):
     g, ffn = net.gcn.module[0][0], net.gcn.module[0][1]
     s0 = droppath_scale[0] if droppath_scale is not None else None
     s1 = droppath_scale[1] if droppath_scale is not None else None
+    # The nested graph's leaves are FRESH detached views of the parameters (same storage): autograd ties a leaf's gradient
+    # bookkeeping to the stream it first saw the leaf on, and a parameter first used in an eager step on the legacy stream
+    # would make a later CUDA-graph capture of the same trainer fail ("legacy stream depends on a capturing stream").
+    gkeys = [k for k, p in fp.named if k.startswith("gcn.") and p.requires_grad]
+    leaf = {k: fp.view(fp.flat, k).detach().requires_grad_(True) for k in gkeys}
+    gp = "gcn.module.0."
     with torch.enable_grad():
-        x0 = A.AddPos.apply(S.x4f, net.gcn.pos_embed)
-        y = A.PwConv.apply(x0, g.fc1[0].weight, g.fc1[0].bias, None, None, 1, False, False)   # feeds KNN: fp32
+        x0 = A.AddPos.apply(S.x4f, leaf["gcn.pos_embed"])
+        y = A.PwConv.apply(x0, leaf[gp + "0.fc1.0.weight"], leaf[gp + "0.fc1.0.bias"], None, None, 1, False, False)   # feeds KNN: fp32
         z = A.KnnAggregate.apply(y, g.relative_pos.detach().reshape(144, 144).float().contiguous())
-        gc = g.graph_conv.gconv.nn[0]
-        z2 = A.PwConv.apply(z, gc.weight, gc.bias, None, None, 4, True, True)
-        x1 = A.PwConv.apply(z2, g.fc2[0].weight, g.fc2[0].bias, x0, s0, 1, False, True)
-        f1 = A.PwConv.apply(x1, ffn.fc1[0].weight, ffn.fc1[0].bias, None, None, 1, True, True)
-        S.gout_f = A.PwConv.apply(f1, ffn.fc2[0].weight, ffn.fc2[0].bias, x1, s1, 1, False, True)
-    S.gcn_params = [p for p in net.gcn.parameters() if p.requires_grad]
+        z2 = A.PwConv.apply(z, leaf[gp + "0.graph_conv.gconv.nn.0.weight"], leaf[gp + "0.graph_conv.gconv.nn.0.bias"], None, None,
+                            4, True, True)
+        x1 = A.PwConv.apply(z2, leaf[gp + "0.fc2.0.weight"], leaf[gp + "0.fc2.0.bias"], x0, s0, 1, False, True)
+        f1 = A.PwConv.apply(x1, leaf[gp + "1.fc1.0.weight"], leaf[gp + "1.fc1.0.bias"], None, None, 1, True, True)
+        S.gout_f = A.PwConv.apply(f1, leaf[gp + "1.fc2.0.weight"], leaf[gp + "1.fc2.0.bias"], x1, s1, 1, False, True)
+    S.gcn_keys, S.gcn_leaves = gkeys, [leaf[k] for k in gkeys]
     gout = _bf((n, C // 8, 12, 12, 8), dev)
     call("uncl_convert", S.gout_f.detach(), F32, gout, BF16, gout.numel())
     # ---- decoder
@@ -295,15 +316,14 @@ def forward_train(net, x, droppath_scale):
     return out, up, S
 
 
-def backward_train(S, d_out, d_feat):
+def backward_train(S, d_out, d_feat, through_autograd=False):
     """d_out: fp32 [N,1,256,256] or None; d_feat: bf16 blocked [N,4,256,256,8] or None.  Accumulates every parameter
-    gradient into the flat gradient buffer (S.fp.grad)."""
+    gradient into the flat gradient buffer every p.grad is a view of (side-effect mode, the fast trainer), or into a
+    scratch buffer whose per-parameter views are returned to autograd (through_autograd: hooks, DDP and optimizers see
+    ordinary gradients)."""
     fp, n = S.fp, S.n
     dev = S.x.device
-    if not fp.grads_attached():     # first backward after zero_grad(set_to_none=True): a new accumulation cycle
-        fp.grad.zero_()
-        fp.attach_grads()
-    fp.stage.zero_()
+    fp.begin_backward(through_autograd)
 
     def st(t):
         return t.stride(0)
@@ -360,11 +380,11 @@ def backward_train(S, d_out, d_feat):
             call("uncl_pw_conv_tc_dgrad", s2d, st(s2d), fp.w("u0_up_d"), None, 0, d_gout, st(d_gout), F32, n, 4 * c_up, c_up,
                  1, h_up, h_up)
     # ---- graph block (nested autograd graph)
-    grads = torch.autograd.grad([S.gout_f], [S.x4f] + S.gcn_params, [d_gout.reshape(S.gout_f.shape)], retain_graph=True,
+    grads = torch.autograd.grad([S.gout_f], [S.x4f] + S.gcn_leaves, [d_gout.reshape(S.gout_f.shape)], retain_graph=True,
                                 allow_unused=True)
-    for p, g in zip(S.gcn_params, grads[1:]):
+    for k, g in zip(S.gcn_keys, grads[1:]):
         if g is not None:
-            p.grad.add_(g)
+            fp.g(k).add_(g)
     C = 256
     dz = _bf((n, C // 8, 12, 12, 8), dev)
     call("uncl_relu_bwd_bias_out", grads[0].contiguous(), S.x4f.detach(), S.x4f.stride(0), dz, BF16,
@@ -391,17 +411,24 @@ def backward_train(S, d_out, d_feat):
     dz_a0 = dgrad("inc1", dz, f, 252, f, 2, S.a0)
     call("uncl_conv_first_wgrad_bias", S.x, dz_a0, BF16, fp.stage_view("inc0", 9 * f), fp.g("inc.conv.conv.bias"), n, 256, 256, f)
     # ---- GEMM-layout weight gradients -> parameter layout, accumulated into the flat gradient buffer
-    call("uncl_unpack_add", fp.stage, fp.unpack_idx, fp.grad, fp.total)
+    call("uncl_unpack_add", fp.stage, fp.unpack_idx, fp.gbuf, fp.total)
 
 
 class GeneratorTrainFn(Function):
-    """(x, anchor) -> (out, up): `anchor` is a 1-element tensor that requires grad, so autograd schedules the backward;
-    parameter gradients are accumulated into the flat buffer as a side effect (every p.grad is a view of it)."""
+    """(x, anchor, net, droppath, *params) -> (out, up).
+
+    Side-effect mode (no `params`; UNet.forward_blocked, the fast trainer): `anchor` is a 1-element tensor that requires
+    grad so that autograd schedules the backward; parameter gradients are accumulated straight into the flat buffer that
+    every p.grad is a view of - no per-parameter AccumulateGrad work, no hooks.
+    Autograd mode (`params` = the trainable parameters; UNet.forward, the drop-in surface): the backward returns one
+    gradient per parameter, so hooks, nn.parallel.DistributedDataParallel and uncltmo_b200.dist.GradientBuckets work as
+    with any module."""
 
     @staticmethod
-    def forward(ctx, x, anchor, net, droppath_scale):
+    def forward(ctx, x, anchor, net, droppath_scale, *params):
         out, up, S = forward_train(net, x.contiguous().float(), droppath_scale)
         ctx.S = S
+        ctx.keys = [k for k, p in S.fp.named if p.requires_grad] if params else None
         ctx.set_materialize_grads(False)   # an unused output (features at epoch > 9) arrives as None, not as zeros
         return out, up
 
@@ -413,5 +440,8 @@ class GeneratorTrainFn(Function):
             d_up = d_up.contiguous()
             if d_up.dtype != torch.bfloat16:
                 d_up = d_up.to(torch.bfloat16)
-        backward_train(S, d_out, d_up)
-        return None, None, None, None
+        backward_train(S, d_out, d_up, through_autograd=ctx.keys is not None)
+        if ctx.keys is None:
+            return None, None, None, None
+        # clones: a later backward (retain_graph) reuses the scratch buffer while autograd may still hold these
+        return (None, None, None, None) + tuple(S.fp.view(S.fp.delta, k).clone() for k in ctx.keys)
