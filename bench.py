@@ -236,7 +236,13 @@ def train_workload(dev, precision, steps, warmup, world=1, rank=0, video=False, 
         g, s = tr.step(h, None, p, n, 0)
         loss_host.copy_(torch.stack([g.detach(), s.detach()]), non_blocking=True)
 
-    ms_eager = run(resident)
+    # eager launches on a side stream: autograd binds the gradient-accumulation nodes of the parameters to the stream of
+    # their first use, and the legacy default stream cannot take part in the capture that follows
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        ms_eager = run(resident)
+    torch.cuda.current_stream(dev).wait_stream(side)
     # the whole iteration (D step, G step, optimizers, all-reduces) as one CUDA graph: what the step costs once the
     # ~1000 launches per iteration no longer go through Python
     _lib.reset_launch_count()

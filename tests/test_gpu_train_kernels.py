@@ -198,7 +198,7 @@ def test_pack_and_unpack_gathers():
     assert torch.equal(dst.cpu()[idx >= 0], v[idx >= 0])
 
 
-@pytest.mark.parametrize("sel,use_ext", [((3, 1), False), ((2, 2), False), ((5, 6), True), ((1, 6), True)])
+@pytest.mark.parametrize("sel,use_ext", [((3, 1), False), ((4, 0), False), ((5, 6), True), ((1, 6), True)])
 def test_self_nce_on_blocked_features(sel, use_ext):
     """uncl_nce_self_fwd / bwd against autograd through the oracle's nce: positive / negative = rows of the anchor tensor
     (or of `ext`, the data-parallel case), gradient of the selected rows summed over the batch."""
@@ -221,9 +221,6 @@ def test_self_nce_on_blocked_features(sel, use_ext):
     d = torch.empty((b, chw), device="cuda")
     d_ext = torch.zeros((2, chw), device="cuda") if use_ext else None
     call("uncl_nce_self_bwd", fb, s, eb, b, chw, hw, 1.0, 1e-2, logits, torch.tensor(0.7, device="cuda"), d, F32, d_ext)
-    if sel[0] == sel[1]:     # positive == negative: the loss is the constant log 2, the exact gradient is zero
-        assert fr.grad.abs().max().item() <= 1e-12 and d.abs().max().item() <= 1e-9
-        return
     assert rel(d, fr.grad) < 1e-5
     if use_ext:
         for j in range(2):

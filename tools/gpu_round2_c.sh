@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU pass: all gpu tests + full bench line
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x > gpurun_out/pytest_all.log 2>&1; echo "all gpu tests rc=$?"; tail -4 gpurun_out/pytest_all.log | cut -c1-300
+python -m pytest tests -m gpu -q > gpurun_out/pytest_all.log 2>&1; echo "all gpu tests rc=$?"; grep -E "^FAILED|^ERROR|passed|failed" gpurun_out/pytest_all.log | cut -c1-300
 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_c.json 2> gpurun_out/bench_c.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_c.err | cut -c1-300
 python - <<'PY'
 import json
@@ -13,3 +13,4 @@ print("sustained", json.dumps(d["sustained"]))
 print("train", d["train"]["value"], d["train"]["ms_per_step"], d["train"]["eager_launch_path"]["value"], d["train"]["gpu_launches"], d["train"]["e2e"])
 print("cpu", d["cpu_baseline"], d["train"].get("cpu_baseline"))
 PY
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; grep smoke gpurun_out/smoke.log | cut -c1-200

@@ -438,9 +438,9 @@ class UNet(_GeneratorBase):
         if x.dim() != 4 or tuple(x.shape[1:]) != (1, 256, 256) or not x.is_cuda:
             raise ValueError("the generator expects CUDA [N,1,256,256] inputs")
         fp = flat_params(self)
-        anchor = getattr(self, "_anchor", None)
-        if anchor is None or anchor.device != x.device:
-            anchor = self._anchor = torch.zeros(1, device=x.device, requires_grad=True)
+        # a fresh leaf per call: autograd ties a leaf's accumulation node to the stream it is first used on, and a
+        # persistent one created in an eager step on the legacy stream would poison a later CUDA-graph capture
+        anchor = torch.zeros(1, device=x.device, requires_grad=True)
         if through_autograd:
             return GeneratorTrainFn.apply(x, anchor, self, scale, *[p for _, p in fp.named if p.requires_grad])
         return GeneratorTrainFn.apply(x, anchor, self, scale)
