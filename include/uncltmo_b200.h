@@ -304,6 +304,19 @@ int uncl_outc_sigmoid_bwd(const float* d_out, const float* out, const float* up,
  * db[C] += column sums of dz (NULL to skip). */
 int uncl_skip_pool_bwd(const void* x2, long x2_img_stride, const void* dcat, const void* dpool, void* dz, float* db, int N,
                        int C, int H, int W, uncl_stream_t stream);
+/* The same with the video generator's recurrence (Unet.py:244: the pool read cat(prev[:, :r], x2[:, r:]), r <= 8 channels of
+ * channel block 0): window values of channels < r come from `prev` (bf16 blocked, first block used), their pool gradient is
+ * written to d_prev (bf16 dense [N][1][H][W][8], channels >= r zero) instead of dz; d_state (bf16 dense [N][1][H][W][8] or
+ * NULL) - the gradient the NEXT frame sent to this frame's own first r channels - is added before the ReLU mask.
+ * prev / d_prev both NULL: no splice at this level (first frame of a clip). */
+int uncl_skip_pool_bwd_rec(const void* x2, long x2_img_stride, const void* dcat, const void* dpool, void* dz, float* db, int N,
+                           int C, int H, int W, const void* prev, long prev_img_stride, int r, void* d_prev,
+                           const void* d_state, uncl_stream_t stream);
+/* Recurrence fix-up on a decoder tensor's gradient (Unet.py:270), channel block 0 of dz [N][C/8][HW][8] in place:
+ * d_prev != NULL (the up-conv read prev's first r channels): d_prev[ch<r] = dz[ch], dz[ch<r] = 0;
+ * d_state != NULL: dz[ch<r] += (own[ch] > 0) * d_state[ch] (own NULL: no mask). */
+int uncl_splice_grad(void* dz, long dz_img_stride, const void* own, long own_img_stride, int r, void* d_prev,
+                     const void* d_state, int N, long HW, uncl_stream_t stream);
 /* db[c] += sum over images and pixels of a bf16 blocked tensor (bias gradient of a conv whose dz a GEMM epilogue wrote) */
 int uncl_bias_grad_bf16(const void* dz, long img_stride, float* db, int N, int C, int HW, uncl_stream_t stream);
 /* bf16 form of uncl_convT2x2_s2d reading a channel slice of the concat gradient (image stride dy_img_stride);

@@ -116,6 +116,56 @@ def test_skip_pool_backward():
     assert rel(from_blocked(dz), zr.grad) < 4e-3
 
 
+def test_skip_pool_backward_with_recurrence():
+    """uncl_skip_pool_bwd_rec: the video generator pools cat(prev[:, :r], x2[:, r:]) (Unet.py:244).  Against autograd:
+    gradient to x2's producer (with the gradient the next frame sends to the own slice) and to prev's first r channels."""
+    n, c, h, w, r = 2, 64, 22, 25, 2
+    z, zp = rnd(n, c, h, w, seed=30), rnd(n, c, h, w, seed=31)
+    gcat, gpool = rnd(n, 4 * c, h, w, seed=32), rnd(n, c, h // 2, w // 2, seed=33)
+    gstate = rnd(n, r, h, w, seed=34)
+    zr, pr = z.double().requires_grad_(True), F.relu(zp.double()).requires_grad_(True)
+    x2 = F.relu(zr)
+    cat = torch.cat([x2, torch.zeros_like(x2), x2 * x2, torch.pow(x2 + 1e-8, 0.5)], 1)
+    fea = torch.cat([pr[:, :r], x2[:, r:]], 1)
+    ((cat * gcat.double()).sum() + (F.max_pool2d(fea, 2) * gpool.double()).sum() + (x2[:, :r] * gstate.double()).sum()).backward()
+    catb = torch.zeros((n, 4 * c // 8, h, w, 8), device="cuda", dtype=torch.bfloat16)
+    catb[:, :c // 8] = to_blocked(F.relu(z))
+    prevb = to_blocked(F.relu(zp))
+    ds = torch.zeros(n, 8, h, w)
+    ds[:, :r] = gstate
+    dz = torch.empty((n, c // 8, h, w, 8), device="cuda", dtype=torch.bfloat16)
+    dprev = torch.full((n, 1, h, w, 8), float("nan"), device="cuda", dtype=torch.bfloat16)
+    db = torch.zeros(c, device="cuda")
+    call("uncl_skip_pool_bwd_rec", catb, catb.stride(0), to_blocked(gcat), to_blocked(gpool), dz, db, n, c, h, w, prevb,
+         prevb.stride(0), r, dprev, to_blocked(ds))
+    got, gotp = from_blocked(dz), from_blocked(dprev)
+    assert rel(got, zr.grad) < 4e-3
+    assert rel(gotp[:, :r], pr.grad[:, :r]) < 4e-3 and (gotp[:, r:] == 0).all()
+
+
+def test_decoder_splice_gradient_fixup():
+    """uncl_splice_grad: the up-convolution read cat(prev[:, :r], up[:, r:]) (Unet.py:270)."""
+    n, c, h, r = 2, 64, 15, 2
+    g = rnd(n, c, h, h, seed=35)
+    own = rnd(n, c, h, h, seed=36).clamp(min=0)
+    gstate = rnd(n, 8, h, h, seed=37)
+    dz = to_blocked(g)
+    dprev = torch.full((n, 1, h, h, 8), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ownb = to_blocked(own)
+    call("uncl_splice_grad", dz, dz.stride(0), ownb, ownb.stride(0), r, dprev, to_blocked(gstate), n, h * h)
+    want = g.clone()
+    want[:, :r] = (own[:, :r] > 0) * gstate[:, :r]
+    assert rel(from_blocked(dz), want) < 4e-3
+    p = from_blocked(dprev)
+    assert torch.equal(p[:, :r], g[:, :r]) and (p[:, r:] == 0).all()
+    # no splice at this tensor (first frame): only the next frame's gradient is added
+    dz = to_blocked(g)
+    call("uncl_splice_grad", dz, dz.stride(0), ownb, ownb.stride(0), r, None, to_blocked(gstate), n, h * h)
+    want = g.clone()
+    want[:, :r] += (own[:, :r] > 0) * gstate[:, :r]
+    assert rel(from_blocked(dz), want) < 4e-3
+
+
 @pytest.mark.parametrize("c,h,h2", [(32, 13, 26), (64, 28, 57)])
 def test_upconv_space_to_depth_backward(c, h, h2):
     """uncl_convT2x2_s2d_bf16: the k2 s2 up-convolution's output gradient (a channel slice of the concat gradient, with the

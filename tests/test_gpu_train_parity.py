@@ -125,23 +125,25 @@ def test_mixed_precision_step_16_images(video, epoch, dp, train_golden):
     assert not bad, bad
 
 
-def test_mixed_precision_gradients_full_tensors():
-    """2 images, every element of every generator gradient: rel-L2 per tensor against the bf16-operand oracle run live
+@pytest.mark.parametrize("video", [False, True])
+def test_mixed_precision_gradients_full_tensors(video):
+    """2 images (video: one clip of two frames, gradients flow through the recurrent hand-over), every element of every generator gradient: rel-L2 per tensor against the bf16-operand oracle run live
     (float64 accumulation), with the bound CALIBRATED on the oracle itself: a second bf16-operand evaluation whose input
     is perturbed by 1e-6 relative (the size of fp32 accumulation error) gives, per tensor, the distance between two
     equally valid bf16 evaluations of the same step; the CUDA path must be within 3x that distance (floor 2e-2)."""
-    hdr, pos, neg = gi.train_batch(2)
+    hdr, pos, neg = gi.train_batch(2, video)
     g_sd = {k: v.double() for k, v in make_generator_state_dict().items()}
     d_sd = {k: v.double() for k, v in make_discriminator_state_dict().items()}
-    h = hdr[0].double()
+    h = hdr.double() if video else hdr[0].double()
     with oracle.bf16_operands(True):
         ref = oracle.train_step_losses(g_sd, d_sd, h, pos[0].double(), neg[0].double(), 0)
         gen = torch.Generator().manual_seed(0)
         h2 = h * (1 + 1e-6 * torch.randn(h.shape, generator=gen, dtype=torch.float64))
         ref2 = oracle.train_step_losses(g_sd, d_sd, h2, pos[0].double(), neg[0].double(), 0)
-    netG, netD = _nets(False, "bf16")
+    netG, netD = _nets(video, "bf16")
     optG = RecordingSGD([p for p in netG.parameters() if p.requires_grad], lr=0.0)
     tr = GanTrainerStep(netG, netD, optG, RecordingSGD(netD.parameters(), lr=0.0))
+    assert tr.video == video
     err_g, err_s = tr.step(hdr.cuda(), None, pos.cuda(), neg.cuda(), 0)
     for name, v, w in (("errD", tr.errD.item(), ref["errD"]), ("errG_d", err_g.item(), ref["errG_d"]),
                        ("errG_struct", err_s.item(), ref["errG_struct"])):
@@ -152,7 +154,7 @@ def test_mixed_precision_gradients_full_tensors():
             a, b = optG.seen[id(p)].double().cpu(), ref["grads_G"][k]
             rels[k] = ((a - b).norm() / (b.norm() + 1e-30)).item()
             noise[k] = ((ref2["grads_G"][k] - b).norm() / (b.norm() + 1e-30)).item()
-    print("mixed gradients vs bf16-operand oracle (rel-L2, oracle's own bf16 sensitivity):",
+    print("mixed gradients (%s) vs bf16-operand oracle (rel-L2, oracle's own bf16 sensitivity):" % ("video" if video else "image"),
           [(k, "%.1e" % rels[k], "%.1e" % noise[k]) for k in sorted(rels, key=lambda k: -rels[k])[:10]])
     bad = {k: (v, noise[k]) for k, v in rels.items() if v > max(2e-2, 3.0 * noise[k])}
     assert not bad, bad

@@ -44,14 +44,24 @@ __device__ __forceinline__ void block_reduce8_atomic(float (&s)[8], float* dst, 
 // ---------------------------------------------------------------------------------------------------------
 // grid (chunks, N * C/8); every block reduces its share of db for one channel block
 // ---------------------------------------------------------------------------------------------------------
+// Video recurrence (Unet.py:244): the max-pool read cat(prev[:, :r], x2[:, r:]).  With `prev` given (first channel block
+// only, r <= 8), the window values of channels < r come from prev, their pool gradient goes to d_prev (dense [N][1][H][W][8],
+// channels >= r zero) instead of dz, and d_state (dense [N][1][H][W][8], may be null) - the gradient the NEXT frame sent to
+// this frame's own first r channels - is added before the ReLU mask.
 __global__ void __launch_bounds__(256) skip_pool_bwd_kernel(const bf16* __restrict__ x2, long x2_img_stride,
                                                            const bf16* __restrict__ dcat, const bf16* __restrict__ dpool,
                                                            bf16* __restrict__ dz, float* __restrict__ db, int C, int H,
-                                                           int W) {
+                                                           int W, const bf16* __restrict__ prev, long prev_img_stride,
+                                                           int r, bf16* __restrict__ d_prev,
+                                                           const bf16* __restrict__ d_state) {
   __shared__ float sm[8 * 32];
   const int Cb = C / 8, cb = blockIdx.y % Cb, n = blockIdx.y / Cb;
   const int HW = H * W, Hp = H / 2, Wp = W / 2;
   const bf16* xb = x2 + (long)n * x2_img_stride + (long)cb * HW * 8;
+  const bool rec0 = cb == 0;       // the recurrent channels live in channel block 0
+  const bf16* pb = (prev != nullptr && rec0) ? prev + (long)n * prev_img_stride : nullptr;
+  bf16* dpo = (d_prev != nullptr && rec0) ? d_prev + (long)n * HW * 8 : nullptr;
+  const bf16* dst_in = (d_state != nullptr && rec0) ? d_state + (long)n * HW * 8 : nullptr;
   const bf16* g0 = dcat ? dcat + ((long)n * 4 * Cb + cb) * HW * 8 : nullptr;
   const bf16* dp = dpool ? dpool + ((long)n * Cb + cb) * Hp * Wp * 8 : nullptr;
   bf16* o = dz + ((long)n * Cb + cb) * HW * 8;
@@ -72,11 +82,21 @@ __global__ void __launch_bounds__(256) skip_pool_bwd_kernel(const bf16* __restri
       for (int j = 0; j < 8; ++j) g[j] = 0.f;
     }
     const int py = y >> 1, px = x >> 1;
+    float gp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // pool gradient owed to the previous frame (channels < r)
     if (dp != nullptr && py < Hp && px < Wp) {
       // MaxPool2d(2) backward: the FIRST maximum of the window in row-major order takes the gradient (as PyTorch)
       float v[4][8], d[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) load8(xb + ((long)(2 * py + (k >> 1)) * W + 2 * px + (k & 1)) * 8, v[k]);
+      for (int k = 0; k < 4; ++k) {
+        const long o = ((long)(2 * py + (k >> 1)) * W + 2 * px + (k & 1)) * 8;
+        load8(xb + o, v[k]);
+        if (pb != nullptr) {
+          float pv[8];
+          load8(pb + o, pv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (j < r) v[k][j] = pv[j];
+        }
+      }
       load8(dp + ((long)py * Wp + px) * 8, d);
       const int me = ((y & 1) << 1) | (x & 1);
 #pragma unroll
@@ -86,8 +106,18 @@ __global__ void __launch_bounds__(256) skip_pool_bwd_kernel(const bf16* __restri
 #pragma unroll
         for (int k = 1; k < 4; ++k)
           if (v[k][j] > bv) { bv = v[k][j]; best = k; }
-        if (best == me) g[j] += d[j];
+        if (best == me) {
+          if (pb != nullptr && j < r) gp[j] = d[j];
+          else g[j] += d[j];
+        }
       }
+    }
+    if (dpo != nullptr) store8(dpo + (long)i * 8, gp);
+    if (dst_in != nullptr) {
+      float ds[8];
+      load8(dst_in + (long)i * 8, ds);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j < r) g[j] += ds[j];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -98,6 +128,36 @@ __global__ void __launch_bounds__(256) skip_pool_bwd_kernel(const bf16* __restri
     store8(o + (long)i * 8, g);
   }
   if (db != nullptr) block_reduce8_atomic(acc, db + cb * 8, sm);
+}
+
+// Video recurrence on a decoder tensor (Unet.py:270: the up-convolution read cat(prev[:, :r], up[:, r:])), channel block 0
+// of the gradient dz [N][C/8][HW][8] that the up-conv's data gradient produced for its (spliced) input:
+//   spliced (d_prev != null): d_prev[ch < r] = dz[ch], dz[ch < r] = 0     (those channels belonged to the previous frame)
+//   d_state != null          : dz[ch < r] += (own[ch] > 0) * d_state[ch]   (what the NEXT frame sent to this frame's slice)
+__global__ void __launch_bounds__(256) splice_grad_kernel(bf16* __restrict__ dz, long dz_img_stride,
+                                                         const bf16* __restrict__ own, long own_img_stride, int r,
+                                                         bf16* __restrict__ d_prev, const bf16* __restrict__ d_state,
+                                                         long HW, long total) {
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const long n = i / HW, p = i - n * HW;
+    float g[8], o[8];
+    bf16* gz = dz + n * dz_img_stride + p * 8;
+    load8(gz, g);
+    if (d_prev != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { o[j] = j < r ? g[j] : 0.f; if (j < r) g[j] = 0.f; }
+      store8(d_prev + (n * HW + p) * 8, o);
+    }
+    if (d_state != nullptr) {
+      float ds[8], m[8];
+      load8(d_state + (n * HW + p) * 8, ds);
+      if (own != nullptr) load8(own + n * own_img_stride + p * 8, m);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < r && (own == nullptr || m[j] > 0.f)) g[j] += ds[j];
+    }
+    store8(gz, g);
+  }
 }
 
 __global__ void __launch_bounds__(256) bias_grad_kernel(const bf16* __restrict__ dz, long img_stride, float* __restrict__ db,
@@ -435,8 +495,35 @@ extern "C" int uncl_skip_pool_bwd(const void* x2, long x2_img_stride, const void
   if (chunks > 64) chunks = 64;
   skip_pool_bwd_kernel<<<dim3(chunks, N * (C / 8)), 256, 0, stream>>>(
       reinterpret_cast<const bf16*>(x2), x2_img_stride, reinterpret_cast<const bf16*>(dcat),
-      reinterpret_cast<const bf16*>(dpool), reinterpret_cast<bf16*>(dz), db, C, H, W);
+      reinterpret_cast<const bf16*>(dpool), reinterpret_cast<bf16*>(dz), db, C, H, W, nullptr, 0, 0, nullptr, nullptr);
   return uncl_check_launch("skip_pool_bwd");
+}
+
+extern "C" int uncl_skip_pool_bwd_rec(const void* x2, long x2_img_stride, const void* dcat, const void* dpool, void* dz,
+                                      float* db, int N, int C, int H, int W, const void* prev, long prev_img_stride, int r,
+                                      void* d_prev, const void* d_state, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && C % 8 == 0 && H > 1 && W > 1 && x2 && dz && x2_img_stride % 8 == 0 && r >= 0 && r <= 8 &&
+                   prev_img_stride % 8 == 0 && (prev == nullptr) == (d_prev == nullptr),
+               "skip_pool_bwd_rec: bad arguments");
+  int chunks = ceil_div(H * W, 256 * 4);
+  if (chunks > 64) chunks = 64;
+  skip_pool_bwd_kernel<<<dim3(chunks, N * (C / 8)), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(x2), x2_img_stride, reinterpret_cast<const bf16*>(dcat),
+      reinterpret_cast<const bf16*>(dpool), reinterpret_cast<bf16*>(dz), db, C, H, W, reinterpret_cast<const bf16*>(prev),
+      prev_img_stride, r, reinterpret_cast<bf16*>(d_prev), reinterpret_cast<const bf16*>(d_state));
+  return uncl_check_launch("skip_pool_bwd_rec");
+}
+
+extern "C" int uncl_splice_grad(void* dz, long dz_img_stride, const void* own, long own_img_stride, int r, void* d_prev,
+                                const void* d_state, int N, long HW, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && HW > 0 && dz && r >= 0 && r <= 8 && dz_img_stride % 8 == 0 && own_img_stride % 8 == 0,
+               "splice_grad: bad arguments");
+  const long total = (long)N * HW;
+  splice_grad_kernel<<<grid_for(total), 256, 0, stream>>>(reinterpret_cast<bf16*>(dz), dz_img_stride,
+                                                         reinterpret_cast<const bf16*>(own), own_img_stride, r,
+                                                         reinterpret_cast<bf16*>(d_prev), reinterpret_cast<const bf16*>(d_state),
+                                                         HW, total);
+  return uncl_check_launch("splice_grad");
 }
 
 extern "C" int uncl_bias_grad_bf16(const void* dz, long img_stride, float* db, int N, int C, int HW, cudaStream_t stream) {

@@ -240,14 +240,19 @@ class FramePipeline:
             self.last_d2h_event.synchronize()   # blocks the HOST: the pinned results are complete on return
         return results
 
-    def tonemap_clip(self, frames, lam, uint8=False, shard_tiles=False):
+    def tonemap_clip(self, frames, lam, uint8=False, shard_tiles=False, shard_frames_out=False):
         """Video path (run_model_on_video, model_save_util.py:567-614): frames [T,3,H,W] fp32 CUDA of ONE scene, one
         lambda per scene.  `self.g` must be the video generator (UNetVideo): every tile is a chain over the T frames
         that hands its recurrent channel slices from frame to frame; tiles are independent of each other.
 
         shard_tiles=True (torch.distributed initialised, every rank holding the same frames): the scene is split by tile
         chain - a rank runs its contiguous share of the tiles through all T frames, one all-gather returns every rank
-        the full set (splitting by frame would change the results), blend / post-process follow."""
+        the full set (splitting by frame would change the results), blend / post-process follow.
+
+        shard_frames_out=True (with shard_tiles): blend / percentiles / back-to-colour / 8-bit stretch are per-frame work
+        with no coupling between frames, so rank r finishes only frames r, r + world, ... and returns those (a list of
+        (frame index, result)); nothing of the post-process is replicated.  Normalisation stays on every rank (it needs
+        each frame's global min / max and costs one 25 MB read per frame), the recurrent tile chains are what is sharded."""
         if not (frames.is_cuda and frames.dtype == torch.float32 and frames.dim() == 4 and frames.shape[1] == 3):
             raise ValueError("tonemap_clip expects a CUDA fp32 [T,3,H,W] tensor")
         import torch.distributed as tdist
@@ -273,8 +278,13 @@ class FramePipeline:
             full = gather_tile_chains(torch.stack(per_frame), pl.ntiles)
             per_frame = [full[t] for t in range(t_len)]
         res = []
-        for t in range(t_len):
+        mine = range(t_len)
+        if sharded and shard_frames_out:
+            mine = range(tdist.get_rank(), t_len, tdist.get_world_size())
+        for t in mine:
             fake_p = self.blend(per_frame[t], pl)
             col = self.postprocess(fake_p, frames[t], norm[t][1], pl)
             res.append(self.to_uint8(col) if uint8 else col)
+        if sharded and shard_frames_out:
+            return list(zip(mine, res))
         return torch.stack(res)

@@ -473,9 +473,42 @@ class UNetVideo(_GeneratorBase):
     eight stage inputs from frame k-1.
     """
 
+    def _train_clip_bf16(self, x, through_autograd):
+        """bf16 training pass over a clip as one autograd node (train_graph.VideoTrainFn): ([N,T,1,256,256] frames,
+        [N,T,64,1,1] features)."""
+        from . import autograd as A
+        from .features import plane_mean_contrast
+        from .train_graph import VideoTrainFn, flat_params
+        if x.dim() != 5 or tuple(x.shape[2:]) != (1, 256, 256) or not x.is_cuda:
+            raise ValueError("the video generator expects CUDA [N,T,1,256,256] inputs")
+        fp = flat_params(self)
+        t_len = x.shape[1]
+        scales = [self._droppath_scale(x.shape[0], x.device) for _ in range(t_len)]
+        anchor = torch.zeros(1, device=x.device, requires_grad=True)
+        params = [p for _, p in fp.named if p.requires_grad] if through_autograd else []
+        res = VideoTrainFn.apply(x, anchor, self, scales if scales[0] is not None else None, *params)
+        outs, feats = [], []
+        for k in range(t_len):
+            out, up = res[2 * k], res[2 * k + 1]
+            mean, con = plane_mean_contrast(A.BlockedToNCHW.apply(up))
+            feats.append(torch.cat([mean, con], dim=1)[:, None, :, None, None])
+            outs.append(out.unsqueeze(1))
+        return torch.cat(outs, 1), torch.cat(feats, 1)
+
+    def forward_blocked(self, x):
+        """The fast trainer's entry (uncltmo_b200.trainer): same values as forward(), parameter gradients accumulated
+        straight into the flat gradient buffer (no per-parameter autograd work).  bf16 precision only."""
+        if self.precision != "bf16":
+            raise RuntimeError("forward_blocked is the bf16 path's entry")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._train_clip_bf16(x, through_autograd=False)
+        return self.forward(x)
+
     def forward(self, x, apply_crop=True, diffY=0, diffX=0):
         from .features import contrast_features, plane_mean_contrast
         train = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if train and self.precision == "bf16" and not x.requires_grad and not self.to_crop:
+            return self._train_clip_bf16(x, through_autograd=True)
         outs, feats, prev = [], [], None
         for k in range(x.shape[1]):
             scale = self._droppath_scale(x.shape[0], x.device)

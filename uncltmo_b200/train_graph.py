@@ -226,12 +226,14 @@ class _Saved:
     pass
 
 
-def forward_train(net, x, droppath_scale):
-    """bf16 forward that keeps what the backward needs.  Returns (out fp32 [N,1,256,256], up bf16 blocked, saved)."""
+def forward_train(net, x, droppath_scale, prev=None):
+    """bf16 forward that keeps what the backward needs.  Returns (out fp32 [N,1,256,256], up bf16 blocked, saved).
+    prev: the saved state of the PREVIOUS frame of the clip (video generator, Unet.py:229-286): the first C/32 channels of
+    the four max-pool inputs and of the four up-convolution inputs are taken from that frame's tensors."""
     fp = flat_params(net).pack()
     n, dev = x.shape[0], x.device
     S = _Saved()
-    S.fp, S.n, S.x = fp, n, x
+    S.fp, S.n, S.x, S.prev = fp, n, x, prev
     f = 32
 
     def st(t):
@@ -250,7 +252,9 @@ def forward_train(net, x, droppath_scale):
     for i in range(4):
         ps = cur_s // 2
         pooled = _bf((n, cur_c // 8, ps, ps, 8), dev)
-        call("uncl_maxpool2", cur, st(cur), None, 0, 0, pooled, st(pooled), n, cur_c, cur_s, cur_s, BF16)
+        pv = prev.cat[i] if prev is not None else None
+        call("uncl_maxpool2", cur, st(cur), pv, st(pv) if pv is not None else 0, cur_c // 32 if pv is not None else 0, pooled,
+             st(pooled), n, cur_c, cur_s, cur_s, BF16)
         co = cur_c * 2 if i < 3 else cur_c
         mid = _bf((n, co // 8, ps - 2, ps - 2, 8), dev)
         key = "down_path.%d.mpconv.1." % i
@@ -290,6 +294,7 @@ def forward_train(net, x, droppath_scale):
     S.gcn_keys, S.gcn_leaves = gkeys, [leaf[k] for k in gkeys]
     gout = _bf((n, C // 8, 12, 12, 8), dev)
     call("uncl_convert", S.gout_f.detach(), F32, gout, BF16, gout.numel())
+    S.gout = gout
     # ---- decoder
     S.ups_in, S.dmid, S.ups = [], [], []
     up, up_c, up_s = gout, C, 12
@@ -297,9 +302,16 @@ def forward_train(net, x, droppath_scale):
         sk_c, sk_s = LEVELS[3 - i]
         cb = S.cat[3 - i]
         dst = cb[:, sk_c // 8:]
-        call("uncl_convT2x2_tc", up, st(up), fp.w("u%d_up" % i), fp.bias("up_path.%d.up" % i), dst, st(cb), BF16, n, up_c,
+        if prev is not None:
+            # the up-convolution reads cat(prev[:, :r], up[:, r:]); `up` itself stays intact (skip / mask / hand-over)
+            pv = prev.gout if i == 0 else prev.ups[i - 1]
+            up_in = up.clone()
+            call("uncl_splice_channels", up_in, st(up_in), pv, st(pv), up_c // 32, n, up_s * up_s, BF16)
+        else:
+            up_in = up
+        call("uncl_convT2x2_tc", up_in, st(up_in), fp.w("u%d_up" % i), fp.bias("up_path.%d.up" % i), dst, st(cb), BF16, n, up_c,
              up_s, up_s, sk_s, sk_s)
-        S.ups_in.append(up)
+        S.ups_in.append(up_in)
         co = f if i >= 2 else up_c // 2
         mid = _bf((n, co // 8, sk_s + 2, sk_s + 2, 8), dev)
         key = "up_path.%d.conv." % i
@@ -317,13 +329,31 @@ def forward_train(net, x, droppath_scale):
 
 
 def backward_train(S, d_out, d_feat, through_autograd=False):
+    """One image batch: begin, the frame's backward, the final gradient un-packing."""
+    S.fp.begin_backward(through_autograd)
+    backward_frame(S, d_out, d_feat, None)
+    backward_end(S.fp)
+
+
+def backward_end(fp):
+    # GEMM-layout weight gradients -> parameter layout, accumulated into the gradient buffer of this backward
+    call("uncl_unpack_add", fp.stage, fp.unpack_idx, fp.gbuf, fp.total)
+
+
+def backward_frame(S, d_out, d_feat, d_state):
     """d_out: fp32 [N,1,256,256] or None; d_feat: bf16 blocked [N,4,256,256,8] or None.  Accumulates every parameter
-    gradient into the flat gradient buffer every p.grad is a view of (side-effect mode, the fast trainer), or into a
-    scratch buffer whose per-parameter views are returned to autograd (through_autograd: hooks, DDP and optimizers see
-    ordinary gradients)."""
+    gradient into `fp.gbuf`: the flat gradient buffer every p.grad is a view of (side-effect mode, the fast trainer), or a
+    scratch buffer whose per-parameter views are returned to autograd (hooks, DDP and optimizers see ordinary gradients).
+
+    Video recurrence: d_state = the gradients the NEXT frame of the clip sent to this frame's handed-over channel slices
+    (dict: "cat"[i] for the four pool inputs, "gout", "ups"[i] for the three decoder tensors; bf16 dense [N,1,H,W,8], or
+    None for the last frame); returns the same structure for the PREVIOUS frame (None for the first frame of a clip)."""
     fp, n = S.fp, S.n
     dev = S.x.device
-    fp.begin_backward(through_autograd)
+    prev = S.prev
+    rec = prev is not None
+    d_prev = {"cat": [None] * 4, "gout": None, "ups": [None] * 3} if rec else None
+    ds = d_state or {"cat": [None] * 4, "gout": None, "ups": [None] * 3}
 
     def st(t):
         return t.stride(0)
@@ -370,15 +400,29 @@ def backward_train(S, d_out, d_feat, through_autograd=False):
              sk_s, sk_s)
         call("uncl_pw_wgrad_tc", up_in, st(up_in), s2d, st(s2d), fp.stage_view("u%d_up" % i, 4 * c_up * c_up), n, c_up,
              4 * c_up, h_up, h_up)
+        r_up = c_up // 32
         if i > 0:
             dz = _bf((n, c_up // 8, h_up, h_up, 8), dev)
+            # mask = the (spliced) tensor the up-conv read: own channels by this frame's ReLU, handed-over ones by prev's
             call("uncl_pw_conv_tc_dgrad", s2d, st(s2d), fp.w("u%d_up_d" % i), up_in, st(up_in), dz, st(dz), BF16, n, 4 * c_up,
                  c_up, 1, h_up, h_up)
+            if rec or ds["ups"][i - 1] is not None:
+                if rec:
+                    d_prev["ups"][i - 1] = _bf((n, 1, h_up, h_up, 8), dev)
+                own = S.ups[i - 1]
+                call("uncl_splice_grad", dz, st(dz), own, st(own), r_up, d_prev["ups"][i - 1] if rec else None, ds["ups"][i - 1],
+                     n, h_up * h_up)
             bias_grad(dz, "up_path.%d.conv.conv1" % (i - 1), c_up, h_up * h_up)
         else:
             d_gout = torch.empty((n, c_up // 8, h_up, h_up, 8), device=dev, dtype=torch.float32)
             call("uncl_pw_conv_tc_dgrad", s2d, st(s2d), fp.w("u0_up_d"), None, 0, d_gout, st(d_gout), F32, n, 4 * c_up, c_up,
                  1, h_up, h_up)
+            if rec:    # the graph block's output has no ReLU: plain slicing (12 x 12 tensors)
+                d_prev["gout"] = torch.zeros((n, 1, h_up, h_up, 8), device=dev, dtype=torch.bfloat16)
+                d_prev["gout"][..., :r_up] = d_gout[:, :1, :, :, :r_up].to(torch.bfloat16)
+                d_gout[:, :1, :, :, :r_up] = 0
+            if ds["gout"] is not None:
+                d_gout[:, :1, :, :, :r_up] += ds["gout"][..., :r_up].float()
     # ---- graph block (nested autograd graph)
     grads = torch.autograd.grad([S.gout_f], [S.x4f] + S.gcn_leaves, [d_gout.reshape(S.gout_f.shape)], retain_graph=True,
                                 allow_unused=True)
@@ -405,13 +449,19 @@ def backward_train(S, d_out, d_feat, through_autograd=False):
         c, s = LEVELS[i]
         dz = _bf((n, c // 8, s, s, 8), dev)
         prod_bias = ("down_path.%d.mpconv.1.conv1" % (i - 1)) if i > 0 else "inc.conv.conv1"
-        call("uncl_skip_pool_bwd", S.cat[i], st(S.cat[i]), dcats[i], dpool, dz, fp.g(prod_bias + ".bias"), n, c, s, s)
+        if rec or ds["cat"][i] is not None:
+            pv = prev.cat[i] if rec else None
+            if rec:
+                d_prev["cat"][i] = _bf((n, 1, s, s, 8), dev)
+            call("uncl_skip_pool_bwd_rec", S.cat[i], st(S.cat[i]), dcats[i], dpool, dz, fp.g(prod_bias + ".bias"), n, c, s, s,
+                 pv, st(pv) if rec else 0, c // 32, d_prev["cat"][i] if rec else None, ds["cat"][i])
+        else:
+            call("uncl_skip_pool_bwd", S.cat[i], st(S.cat[i]), dcats[i], dpool, dz, fp.g(prod_bias + ".bias"), n, c, s, s)
     # ---- inc: conv1 (32 -> 32) and the first conv (1 -> 32, fp32 CUDA cores)
     wgrad("inc1", S.a0, f, 254, dz, f, 0)
     dz_a0 = dgrad("inc1", dz, f, 252, f, 2, S.a0)
     call("uncl_conv_first_wgrad_bias", S.x, dz_a0, BF16, fp.stage_view("inc0", 9 * f), fp.g("inc.conv.conv.bias"), n, 256, 256, f)
-    # ---- GEMM-layout weight gradients -> parameter layout, accumulated into the flat gradient buffer
-    call("uncl_unpack_add", fp.stage, fp.unpack_idx, fp.gbuf, fp.total)
+    return d_prev
 
 
 class GeneratorTrainFn(Function):
@@ -445,3 +495,44 @@ class GeneratorTrainFn(Function):
             return None, None, None, None
         # clones: a later backward (retain_graph) reuses the scratch buffer while autograd may still hold these
         return (None, None, None, None) + tuple(S.fp.view(S.fp.delta, k).clone() for k in ctx.keys)
+
+
+class VideoTrainFn(Function):
+    """The recurrent (video) generator over a clip as ONE autograd node: (x [N,T,1,256,256], anchor, net, droppath scales
+    per frame, *params) -> (out_0, up_0, out_1, up_1, ...).  Frame k's forward takes the first C/32 channels of eight stage
+    inputs from frame k-1 (Unet.py:229-286); the backward walks the frames in reverse and hands the gradients of those
+    slices back (they are not detached in the reference).  Parameter gradients of all frames accumulate in one staging
+    buffer and are un-packed once."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, net, scales, *params):
+        x = x.contiguous().float()
+        saved, outs, prev = [], [], None
+        for k in range(x.shape[1]):
+            out, up, S = forward_train(net, x[:, k].contiguous(), scales[k] if scales is not None else None, prev)
+            saved.append(S)
+            outs += [out, up]
+            prev = S
+        ctx.saved = saved
+        ctx.keys = [k for k, p in saved[0].fp.named if p.requires_grad] if params else None
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        saved = ctx.saved
+        fp = saved[0].fp
+        fp.begin_backward(ctx.keys is not None)
+        d_state = None
+        for k in range(len(saved) - 1, -1, -1):
+            d_out, d_up = grads[2 * k], grads[2 * k + 1]
+            d_out = d_out.contiguous().float() if d_out is not None else None
+            if d_up is not None:
+                d_up = d_up.contiguous()
+                if d_up.dtype != torch.bfloat16:
+                    d_up = d_up.to(torch.bfloat16)
+            d_state = backward_frame(saved[k], d_out, d_up, d_state)
+        backward_end(fp)
+        if ctx.keys is None:
+            return None, None, None, None
+        return (None, None, None, None) + tuple(fp.view(fp.delta, k).clone() for k in ctx.keys)

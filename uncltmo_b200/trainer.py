@@ -53,7 +53,7 @@ class GanTrainerStep:
     def _generator_is_flat(self):
         """True when the generator ran through train_graph (bf16 image path): every p.grad is a view of one flat buffer."""
         fp = getattr(self.netG, "_flat", None)
-        return (not self.video) and getattr(self.netG, "precision", None) == "bf16" and fp is not None and fp.grads_attached()
+        return getattr(self.netG, "precision", None) == "bf16" and fp is not None and fp.grads_attached()
 
     @staticmethod
     def _flat(t):
@@ -65,7 +65,10 @@ class GanTrainerStep:
         if self.video:
             if hdr_input.dim() != 5:
                 raise ValueError("the video trainer expects [B,T,1,256,256] clips")
-            fake, fea = self.netG(hdr_input.float())
+            if getattr(self.netG, "precision", None) == "bf16" and hasattr(self.netG, "forward_blocked"):
+                fake, fea = self.netG.forward_blocked(hdr_input.float())    # the clip as one autograd node, flat gradients
+            else:
+                fake, fea = self.netG(hdr_input.float())
             return self._flat(fake), self._flat(fea)
         if getattr(self.netG, "precision", None) == "bf16" and hasattr(self.netG, "forward_blocked"):
             # bf16 path: one autograd node for the whole generator, features stay C8-blocked bf16 (losses.infoNCE2 reads them)
