@@ -50,7 +50,7 @@ def infoNCE2(fea_fake, fake, hdr_input, cl_loss_type, k, constant):
         rows = udist.BroadcastRowsFn.apply(fea_fake, g_idx)
         b = fea_fake.shape[0]
         if blocked:
-            sel = torch.tensor([b, b + 1], device=fea_fake.device, dtype=torch.int64)
+            sel = torch.arange(b, b + 2, device=fea_fake.device, dtype=torch.int64)   # (no H2D copy: graph-capture safe)
             return NceSelfFn.apply(fea_fake, sel, fea_fake.shape[2] * fea_fake.shape[3], k, constant, rows)
         return nce(fea_fake, [rows[0:1]], [rows[1:2]], cl_loss_type, k, constant)
     if blocked:
