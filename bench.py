@@ -344,7 +344,19 @@ def main():
         import torch.distributed as dist
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # rank 0 prints exactly one JSON line on stdout: NCCL / torch print their version banner on file descriptor 1 when
+        # the first communicator is created, so that happens here with fd 1 pointed at stderr
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     net = UNet(*G_ARGS, up_mode=0, precision=args.precision).to(dev).eval()
     net.load_state_dict(make_generator_state_dict())
