@@ -386,6 +386,17 @@ int uncl_disc_backward(const float* x, const float* h1, const float* a2, const f
                        float* dx, float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3,
                        float* dw_tail, float* scratch, int N, uncl_stream_t stream);
 
+/* ---- HDR file decode at the head of the entry path (utils/hdr_image_util.py:35-53 reads on the host) ---- */
+
+/* HOST function (host pointers, no CUDA call): byte offset of every scanline of a Radiance RGBE (.hdr) file's pixel stream.
+ * data_host: the whole file; pixel_offset: first byte after the header's resolution line; offsets_host[H + 1];
+ * *rle_out = 1 (run-length coded scanlines) or 0 (flat RGBE).  One sequential pass over the packet headers only. */
+int uncl_hdr_scan_host(const unsigned char* data_host, long size, long pixel_offset, int W, int H, long* offsets_host,
+                       int* rle_out);
+/* Expand the scanlines on the device (one CTA per scanline) and convert RGBE to float exactly as Radiance / OpenCV do
+ * (mantissa * 2^(e - 136)).  data / offsets: DEVICE copies of the file bytes and of the scan's offsets; out fp32 [3][H][W]. */
+int uncl_hdr_decode(const unsigned char* data, const long* offsets, int W, int H, int rle, float* out, uncl_stream_t stream);
+
 /* ---- off-default-path operators ---- */
 
 /* adaptive_lambda.cross_entropy (utils/adaptive_lambda.py:7-21) for a population of L candidate lambdas at once:

@@ -104,3 +104,28 @@ def test_data_parallel_and_ddp_style_wrapping():
     finally:
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("h,w", [(268, 300), (1080, 1920), (37, 7)])
+def test_hdr_decode_on_device_matches_opencv(tmp_path, h, w):
+    """Radiance .hdr decode with the scanlines expanded on the GPU (uncl_hdr_scan_host + uncl_hdr_decode) is bit-identical
+    to cv2.imread: run-length coded files as OpenCV writes them, and flat RGBE (widths < 8 cannot be run-length coded)."""
+    import cv2
+    rgb = synth.hdr_frame(h, w, seed=41)
+    rgb[:, : h // 3] *= 1e-3            # long runs of equal exponents and a wide dynamic range
+    rgb[:, -2:] = 0.0                   # zero pixels (exponent byte 0)
+    path = str(tmp_path / "f.hdr")
+    assert cv2.imwrite(path, np.ascontiguousarray(rgb.transpose(1, 2, 0)[..., ::-1]))
+    want = cv2.imread(path, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_COLOR)[..., ::-1].transpose(2, 0, 1)
+    got = common.read_hdr_image_device(path, torch.device("cuda"))
+    torch.cuda.synchronize()
+    assert got.shape == (3, h, w)
+    assert np.array_equal(got.cpu().numpy(), want)
+    # a corrupted stream is refused by the host scan, not decoded into garbage
+    raw = bytearray(open(path, "rb").read())
+    if w >= 8:
+        raw[-1:] = b""
+        bad = str(tmp_path / "bad.hdr")
+        open(bad, "wb").write(bytes(raw))
+        with pytest.raises(IOError):
+            common.read_hdr_image_device(bad, torch.device("cuda"))

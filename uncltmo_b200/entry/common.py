@@ -95,6 +95,32 @@ def read_hdr_image(path):
     return np.ascontiguousarray(im[..., ::-1], dtype=np.float32)
 
 
+def read_hdr_image_device(path, device):
+    """Radiance .hdr -> fp32 RGB planes [3,H,W] ON THE DEVICE: the file's bytes are uploaded as they are, the host only walks
+    the run-length packet headers to find the scanline starts (uncl_hdr_scan_host), expansion and RGBE -> float run on
+    the GPU (uncl_hdr_decode).  Bit-identical to cv2.imread(..., IMREAD_ANYDEPTH) (tests/test_gpu_entry.py)."""
+    import ctypes
+    import re
+    from .. import _lib
+    raw = np.fromfile(path, dtype=np.uint8)
+    head = bytes(raw[:4096])
+    m = re.search(rb"\n\n(-Y|\+Y) (\d+) (\+X|-X) (\d+)\n", head)
+    if not head.startswith(b"#?") or m is None or m.group(1) != b"-Y" or m.group(3) != b"+X":
+        raise IOError("%s: not a top-down Radiance RGBE file" % path)
+    h, w = int(m.group(2)), int(m.group(4))
+    offsets = np.empty(h + 1, dtype=np.int64)
+    rle = ctypes.c_int(0)
+    lib = _lib.lib()
+    rc = lib.uncl_hdr_scan_host(raw.ctypes.data, raw.size, m.end(), w, h, offsets.ctypes.data, ctypes.addressof(rle))
+    if rc != 0:
+        raise IOError("%s: %s" % (path, lib.uncl_last_error().decode()))
+    data = torch.from_numpy(raw).pin_memory().to(device, non_blocking=True)
+    offs = torch.from_numpy(offsets).pin_memory().to(device, non_blocking=True)
+    out = torch.empty((3, h, w), device=device, dtype=torch.float32)
+    _lib.call("uncl_hdr_decode", data, offs, w, h, int(rle.value), out)
+    return out
+
+
 def load_lambda(f_factor_path, key):
     data = np.load(f_factor_path, allow_pickle=True)[()]
     return float(data[key])
