@@ -143,10 +143,12 @@ def blocked144(x):  # [N,C,12,12] -> [N, C/8, 144, 8]
     return to_blocked(x).reshape(x.shape[0], x.shape[1] // 8, 144, 8)
 
 
-@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("tc", [False, True, "split"])
 @pytest.mark.parametrize("ci,co,groups,gelu,with_res", [(256, 256, 1, False, False), (512, 512, 4, True, False),
                                                        (512, 256, 1, False, True), (256, 256, 1, True, False)])
 def test_pw_conv(ci, co, groups, gelu, with_res, tc):
+    if tc == "split" and groups != 1:
+        pytest.skip("the split forward is built for ungrouped 1x1 convs (fc1)")
     x = rnd(3, ci, 12, 12, seed=14)
     w, b = rnd(co, ci // groups, 1, 1, seed=15, scale=(ci // groups) ** -0.5), rnd(co, seed=16, scale=0.1)
     res = rnd(3, co, 12, 12, seed=17) if with_res else None
@@ -165,10 +167,10 @@ def test_pw_conv(ci, co, groups, gelu, with_res, tc):
     y.backward(blocked144(g).cuda())
     unb = lambda t: from_blocked(t.reshape(t.shape[0], t.shape[1], 12, 12, 8))  # noqa: E731
     tol = 6e-3 if tc else 1e-5   # tc: bf16-rounded operands, fp32 accumulation
-    assert rel(unb(y), yr) < tol
+    assert rel(unb(y), yr) < (2e-5 if tc == "split" else tol)     # three-term split: ~2^-16 per product
     assert rel(unb(xb.grad), xr.grad) < tol
-    # the weight gradient is an fp32 kernel; with GELU it sees the tc forward's pre-activation through gelu'
-    assert rel(wc.grad, wr.grad) < (tol if gelu else 1e-5) and rel(bc.grad, br.grad) < (tol if gelu else 1e-5)
+    # tc: the weight gradient is a tensor-core GEMM on bf16-rounded x and dz; the bias gradient stays fp32
+    assert rel(wc.grad, wr.grad) < tol and rel(bc.grad, br.grad) < (tol if gelu else 1e-5)
     if with_res:
         assert rel(unb(rb.grad), rr.grad) < 1e-7
 

@@ -259,7 +259,9 @@ class AddPos(Function):
 class PwConv(Function):
     """1x1 conv (+groups) with optional GELU, residual and per-sample DropPath scale:
     out = scale[n] * act(W x + b) + res.  gcn_lib/torch_vertex.py:219-227, torch_nn.py:54-78, Unet_singleFrame.py:36-42.
-    tc=True: forward and data gradient are tensor-core GEMMs on bf16-rounded operands (fp32 accumulation / outputs)."""
+    tc=True: forward, data gradient and weight gradient are tensor-core GEMMs on bf16-rounded operands (fp32 accumulation /
+    outputs).  tc="split": the forward is the three-term bf16 split GEMM x_hi.w_hi + x_hi.w_lo + x_lo.w_hi (~2^-16, for fc1,
+    whose output drives the discrete KNN selection); gradients as tc=True."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, res, scale, groups, gelu, tc=False):
@@ -273,19 +275,28 @@ class PwConv(Function):
             assert res is None and scale is None
             u = _empty(out.shape, x)
         r = res.contiguous() if res is not None else None
+        xb = None
         if tc:
             assert hw == 144
             xb = _to_bf16(x)
-            wq = packing.pointwise_tc(weight.detach(), groups)
-            call("uncl_pw_conv_tc", xb, xb.stride(0), wq, b, r, r.stride(0) if r is not None else 0, F32, scale,
-                 u if gelu else out, out.stride(0), F32, n, ci, co, groups, 12, 12, ACT_NONE)
+            if tc == "split":
+                assert groups == 1
+                xs = torch.empty((n, 3 * cbi, hw, 8), device=x.device, dtype=torch.bfloat16)
+                call("uncl_split_bf16", x, x.stride(0), xs, xs.stride(0), n, ci, hw)
+                call("uncl_pw_conv_tc", xs, xs.stride(0), packing.pointwise_tc_split(weight.detach()), b, r,
+                     r.stride(0) if r is not None else 0, F32, scale, u if gelu else out, out.stride(0), F32, n, 3 * ci, co, 1,
+                     12, 12, ACT_NONE)
+            else:
+                wq = packing.pointwise_tc(weight.detach(), groups)
+                call("uncl_pw_conv_tc", xb, xb.stride(0), wq, b, r, r.stride(0) if r is not None else 0, F32, scale,
+                     u if gelu else out, out.stride(0), F32, n, ci, co, groups, 12, 12, ACT_NONE)
         else:
             wq = packing.pointwise(weight.detach(), groups)
             call("uncl_pw_conv", x, wq, b, r, scale, u if gelu else out, out.stride(0), n, ci, co, groups, hw, ACT_NONE, F32)
         if gelu:
             call("uncl_gelu_fwd", u, out, u.numel())
-        ctx.save_for_backward(x, weight, u, scale)
-        ctx.cfg = (groups, gelu, res is not None, tc)
+        ctx.save_for_backward(xb if tc else x, weight, u, scale)
+        ctx.cfg = (groups, gelu, res is not None, bool(tc))
         return out
 
     @staticmethod
@@ -300,25 +311,32 @@ class PwConv(Function):
             d = dout.clone()
             call("uncl_scale_rows", d, scale, n, co * hw)
         if gelu:
-            du = _empty(d.shape, x)
+            du = _empty(d.shape, d)
             call("uncl_gelu_bwd", u, d, du, d.numel())
             d = du
         dx = None
+        db16 = _to_bf16(d) if tc else None
         if ctx.needs_input_grad[0]:
-            dx = _empty(x.shape, x)
+            dx = _empty(x.shape, d)
             if tc:
                 # transposed 1x1 conv: per group [C_out/g -> C_in/g], i.e. a conv with weight [C_in][C_out/g]
                 wt = weight.detach().reshape(groups, co // groups, ci // groups).transpose(1, 2).reshape(ci, co // groups, 1, 1)
-                db16 = _to_bf16(d)
                 call("uncl_pw_conv_tc", db16, db16.stride(0), packing.pointwise_tc(wt, groups), None, None, 0, F32, None, dx,
                      dx.stride(0), F32, n, co, ci, groups, 12, 12, ACT_NONE)
             else:
                 wt = packing.pointwise(weight.detach(), groups).transpose(1, 2).contiguous()   # [g][Cout_g][Cin_g]
                 call("uncl_pw_conv", d, wt, None, None, None, dx, dx.stride(0), n, co, ci, groups, hw, ACT_NONE, F32)
-        dwp = _zeros((groups, ci // groups, co // groups), x)
-        call("uncl_pw_wgrad", x, d, dwp, n, ci, co, groups, hw)
+        dwp = _zeros((groups, ci // groups, co // groups), d)
+        if tc:
+            # weight gradient on the tensor cores, one GEMM over pixels per group (channel-block slices of x and dz)
+            cig, cog = ci // groups, co // groups
+            for g in range(groups):
+                xg, zg = x[:, g * cig // 8:(g + 1) * cig // 8], db16[:, g * cog // 8:(g + 1) * cog // 8]
+                call("uncl_pw_wgrad_tc", xg, x.stride(0), zg, db16.stride(0), dwp[g], n, cig, cog, 12, 12)
+        else:
+            call("uncl_pw_wgrad", x, d, dwp, n, ci, co, groups, hw)
         dw = dwp.permute(0, 2, 1).reshape(co, ci // groups, 1, 1).contiguous()
-        db = _zeros(co, x)
+        db = _zeros(co, d)
         call("uncl_relu_bwd_bias", d, None, 0, db, n, co, hw, 0)
         return dx, dw, db, (dout if has_res else None), None, None, None, None
 

@@ -276,6 +276,84 @@ __global__ void __launch_bounds__(256) plane_mean_contrast_bwd_kernel(const floa
   }
 }
 
+// The same gradient as ONE tiled, separable kernel (the two kernels above do 2 x 121 taps per pixel).  A tile of 32 x 32 dx
+// pixels needs mu on the 42 x 42 outputs that cover it, i.e. x on 52 x 52: horizontal then vertical 11-tap pass give mu
+// (zero outside the valid output range), the transposed passes give B; A_p is the product of two 1-D partial sums of g.
+__global__ void __launch_bounds__(256) plane_mean_contrast_bwd_tiled_kernel(const float* __restrict__ x,
+                                                                           const float* __restrict__ d_mean,
+                                                                           const float* __restrict__ d_cmean, int H, int W,
+                                                                           float* __restrict__ dx) {
+  __shared__ float s_x[52][53];
+  __shared__ float s_h[52][43];
+  __shared__ float s_mu[42][43];
+  __shared__ float s_t[42][33];
+  const int m = blockIdx.z;
+  const int Ho = H - 10, Wo = W - 10;
+  const int px0 = blockIdx.x * 32, py0 = blockIdx.y * 32;
+  const float* xp = x + (long)m * H * W;
+  const float gm = d_mean ? d_mean[m] / (float)((long)H * W) : 0.f;
+  if (d_cmean == nullptr) {
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+      const int py = py0 + i / 32, px = px0 + i % 32;
+      if (py < H && px < W) dx[(long)m * H * W + (long)py * W + px] = gm;
+    }
+    return;
+  }
+  const float dc = d_cmean[m] / (float)((long)Ho * Wo);
+  // x tile: rows py0 - 10 .. py0 + 41, cols px0 - 10 .. px0 + 41
+  for (int i = threadIdx.x; i < 52 * 52; i += 256) {
+    const int ly = i / 52, lx = i % 52;
+    const int gy = py0 - 10 + ly, gx = px0 - 10 + lx;
+    s_x[ly][lx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(xp + (long)gy * W + gx) : 0.f;
+  }
+  __syncthreads();
+  // horizontal pass: h[ly][ox] for output columns ox = px0 - 10 + lx, lx < 42
+  for (int i = threadIdx.x; i < 52 * 42; i += 256) {
+    const int ly = i / 42, lx = i % 42;
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) a = fmaf(c_g11[k], s_x[ly][lx + k], a);
+    s_h[ly][lx] = a;
+  }
+  __syncthreads();
+  // vertical pass: mu at outputs (oy, ox) = (py0 - 10 + ly, px0 - 10 + lx); zero outside [0, Ho) x [0, Wo)
+  for (int i = threadIdx.x; i < 42 * 42; i += 256) {
+    const int ly = i / 42, lx = i % 42;
+    const int oy = py0 - 10 + ly, ox = px0 - 10 + lx;
+    float a = 0.f;
+    if (oy >= 0 && oy < Ho && ox >= 0 && ox < Wo) {
+#pragma unroll
+      for (int k = 0; k < 11; ++k) a = fmaf(c_g11[k], s_h[ly + k][lx], a);
+    }
+    s_mu[ly][lx] = a;
+  }
+  __syncthreads();
+  // transposed horizontal pass: t[ly][lxp] = sum_kx g[kx] mu(oy, px - kx), px = px0 + lxp  ->  mu column lxp + 10 - kx
+  for (int i = threadIdx.x; i < 42 * 32; i += 256) {
+    const int ly = i / 32, lx = i % 32;
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) a = fmaf(c_g11[k], s_mu[ly][lx + 10 - k], a);
+    s_t[ly][lx] = a;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+    const int ly = i / 32, lx = i % 32;
+    const int py = py0 + ly, px = px0 + lx;
+    if (py >= H || px >= W) continue;
+    float Bv = 0.f, ay = 0.f, ax = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      Bv = fmaf(c_g11[k], s_t[ly + 10 - k][lx], Bv);
+      const int oy = py - k, ox = px - k;
+      if (oy >= 0 && oy < Ho) ay += c_g11[k];
+      if (ox >= 0 && ox < Wo) ax += c_g11[k];
+    }
+    const float xv = s_x[ly + 10][lx + 10];
+    dx[(long)m * H * W + (long)py * W + px] = gm + dc * (2.f * xv * ay * ax - 2.f * Bv);
+  }
+}
+
 // L1 of two vectors: out = mean |a - b| ; da = g sign(a-b)/n, db = -da
 __global__ void l1_mean_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int n,
                                    const float* __restrict__ g_up, float* __restrict__ da, float* __restrict__ db) {
@@ -555,6 +633,11 @@ extern "C" int uncl_plane_mean_contrast_bwd(const float* x, int M, int H, int W,
                                             float* dx, float* mu_scratch, cudaStream_t stream) {
   UNCL_REQUIRE(M > 0 && H > 10 && W > 10, "plane_mean_contrast_bwd: bad shape");
   if (ensure_gauss() != 0) return uncl_set_error(UNCL_ECUDA, "plane_mean_contrast_bwd: constant upload failed");
+  (void)mu_scratch;   // the tiled kernel keeps mu in shared memory (the argument stays for ABI stability)
+  if ((long)M <= 65535) {
+    plane_mean_contrast_bwd_tiled_kernel<<<dim3(ceil_div(W, 32), ceil_div(H, 32), M), 256, 0, stream>>>(x, d_mean, d_cmean, H, W, dx);
+    return uncl_check_launch("plane_mean_contrast_bwd");
+  }
   if (d_cmean) {
     const long to = (long)M * (H - 10) * (W - 10);
     plane_mu_kernel<<<cap_grid(to, 256, 8), 256, 0, stream>>>(x, H, W, to, mu_scratch);

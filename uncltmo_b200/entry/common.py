@@ -1,7 +1,9 @@
 """Shared helpers of the two entry points: settings, checkpoint loading, HDR file decode, PNG write.
 
-File decode / encode stays on the host (out of scope): cv2 reads Radiance .hdr / .exr, .npy is
-loaded directly; everything between the decoded float frame and the 8-bit result runs on the GPU.
+Radiance .hdr frames are decoded ON THE DEVICE (read_hdr_image_device: the file's bytes are uploaded, the host only walks the
+run-length packet headers); .exr goes through cv2 on the host, .npy is loaded directly.  The PNG write stays
+on the host (cv2): its entropy-coding stage is sequential, see DESIGN.md section 8.  Everything between the decoded float
+frame and the 8-bit result runs on the GPU.
 """
 import os
 

@@ -71,12 +71,15 @@ def run_model_on_path(model_params, device, net_path, input_images_path, output_
 
 def run_model_on_single_image2(pipe, im_path, device, im_name, output_path, f_factor_path, scale=4):
     """utils/model_save_util.py:293-407: host decode (+ the hard-coded cv2 down-scale), then the GPU frame path."""
-    rgb = common.read_hdr_image(im_path)
-    if scale != 1:
-        import cv2
-        rgb = cv2.resize(rgb, (rgb.shape[1] // scale, rgb.shape[0] // scale))
     lam = common.load_lambda(f_factor_path, im_name)
-    x = torch.from_numpy(np.ascontiguousarray(rgb.transpose(2, 0, 1))).pin_memory().to(device, non_blocking=True)
+    if scale == 1 and im_path.lower().endswith(".hdr"):
+        x = common.read_hdr_image_device(im_path, device)      # file bytes -> GPU, scanlines expanded there
+    else:
+        rgb = common.read_hdr_image(im_path)
+        if scale != 1:
+            import cv2
+            rgb = cv2.resize(rgb, (rgb.shape[1] // scale, rgb.shape[0] // scale))
+        x = torch.from_numpy(np.ascontiguousarray(rgb.transpose(2, 0, 1))).pin_memory().to(device, non_blocking=True)
     with torch.no_grad():
         u8 = pipe.tonemap(x, lam, uint8=True)
     return common.save_png(u8.cpu().numpy(), output_path, im_name + "_UnCLTMO")

@@ -71,8 +71,11 @@ def run_model_on_path(model_params, device, net_path, input_images_path, output_
 def run_model_on_video(pipe, im_paths, device, im_names, output_path, f_factor_path, scene):
     """utils/model_save_util.py:567-614."""
     lam = common.load_lambda(f_factor_path, scene)
-    frames = np.stack([common.read_hdr_image(p).transpose(2, 0, 1) for p in im_paths])
-    x = torch.from_numpy(np.ascontiguousarray(frames)).pin_memory().to(device, non_blocking=True)
+    if all(p.lower().endswith(".hdr") for p in im_paths):
+        x = torch.stack([common.read_hdr_image_device(p, device) for p in im_paths])     # decoded on the GPU
+    else:
+        frames = np.stack([common.read_hdr_image(p).transpose(2, 0, 1) for p in im_paths])
+        x = torch.from_numpy(np.ascontiguousarray(frames)).pin_memory().to(device, non_blocking=True)
     with torch.no_grad():
         u8 = pipe.tonemap_clip(x, lam, uint8=True).cpu().numpy()
     return [common.save_png(u8[i], output_path, im_names[i] + "_UnCLTMO") for i in range(len(im_paths))]

@@ -284,7 +284,8 @@ def forward_train(net, x, droppath_scale, prev=None):
     gp = "gcn.module.0."
     with torch.enable_grad():
         x0 = A.AddPos.apply(S.x4f, leaf["gcn.pos_embed"])
-        y = A.PwConv.apply(x0, leaf[gp + "0.fc1.0.weight"], leaf[gp + "0.fc1.0.bias"], None, None, 1, False, False)   # feeds KNN: fp32
+        # fc1 feeds the discrete KNN selection: three-term bf16 split forward (~2^-16), bf16 tensor-core gradients
+        y = A.PwConv.apply(x0, leaf[gp + "0.fc1.0.weight"], leaf[gp + "0.fc1.0.bias"], None, None, 1, False, "split")
         z = A.KnnAggregate.apply(y, g.relative_pos.detach().reshape(144, 144).float().contiguous())
         z2 = A.PwConv.apply(z, leaf[gp + "0.graph_conv.gconv.nn.0.weight"], leaf[gp + "0.graph_conv.gconv.nn.0.bias"], None, None,
                             4, True, True)
