@@ -146,7 +146,7 @@ int uncl_pw_conv(const float* in, const float* w, const float* bias, const float
 int uncl_gcn_knn_aggregate(const float* y, const float* relpos, void* z, int z_dtype, int* idx_out, int N, int C,
                            uncl_stream_t stream);
 
-/* Diagnostics for profiling only: per-role cycle counters of the tensor-core conv kernels (8 uint64 on the device,
+/* Diagnostics for profiling only: per-role cycle counters of the tensor-core conv kernels (10 uint64 on the device,
  * zeroed by the caller; NULL switches off).  See conv_tc.cu. */
 int uncl_conv_tc_set_debug(void* counters);
 

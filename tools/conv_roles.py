@@ -10,7 +10,7 @@ G_ARGS = (1, 1, "sigmoid", 4, 4, "square_and_square_root", 32, 0, "unet", 0, 0, 
 net = G.UNet(*G_ARGS, up_mode=0, precision="bf16").cuda().eval()
 net.load_state_dict(make_generator_state_dict())
 x = torch.rand(60, 1, 256, 256, device="cuda")
-cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
+cnt = torch.zeros(10, dtype=torch.int64, device="cuda")
 rows = []
 orig = G.call
 
@@ -41,7 +41,7 @@ with torch.no_grad():
     _lib.lib().uncl_conv_tc_set_debug(None)
 print("%-18s %-44s %8s | producer: wait-empty | mma: wait-full wait-acc busy | epi: wait-acc" % ("kernel", "int args", "us"))
 for name, ints, us, c in rows:
-    prod, p_we, mma, m_wf, m_wa, epi, e_wa, n = c
-    print("%-18s %-44s %8.1f | %5.1f%% | %5.1f%% %5.1f%% %5.1f%% | %5.1f%%  (ctas %d, mma cycles/cta %.0f)" % (
+    prod, p_we, mma, m_wf, m_wa, epi, e_wa, n, ns = c[:9]
+    print("%-18s %-44s %8.1f | %5.1f%% | %5.1f%% %5.1f%% %5.1f%% | %5.1f%%  (ctas %d, mma cycles/cta %.0f, SM clock %.0f MHz)" % (
         name, str(ints), us, 100 * p_we / max(prod, 1), 100 * m_wf / max(mma, 1), 100 * m_wa / max(mma, 1),
-        100 * (mma - m_wf - m_wa) / max(mma, 1), 100 * e_wa / max(epi, 1), n, mma / max(n, 1)))
+        100 * (mma - m_wf - m_wa) / max(mma, 1), 100 * e_wa / max(epi, 1), n, mma / max(n, 1), 1e3 * mma / max(ns, 1)))

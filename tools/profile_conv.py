@@ -30,6 +30,10 @@ def run(name, n=60, reps=1):
     ow, ob = torch.randn(co, device="cuda"), torch.zeros(1, device="cuda")
     img = torch.empty((n, ho, ho), device="cuda")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cnt = None
+    if os.environ.get("PROFILE_DBG"):   # probes library only: per-role cycle counters + the SM clock the launch ran at
+        cnt = torch.zeros(10, dtype=torch.int64, device="cuda")
+        _lib.lib().uncl_conv_tc_set_debug(cnt.data_ptr())
     for i in range(reps + 1):
         if i == 1:
             e0.record()
@@ -40,7 +44,13 @@ def run(name, n=60, reps=1):
     if reps:
         ms = e0.elapsed_time(e1) / reps
         fl = 2.0 * 9 * ci * co * ho * ho * n
-        print("%-5s %8.1f us  %7.1f TFLOP/s" % (name, ms * 1e3, fl / ms / 1e9), flush=True)
+        extra = ""
+        if cnt is not None:
+            c = cnt.tolist()
+            _lib.lib().uncl_conv_tc_set_debug(None)
+            extra = "  mma cycles/cta/launch %.0f  SM clock %.0f MHz  mma wait-full %.1f%% wait-acc %.1f%%" % (
+                c[2] / max(c[7], 1), 1e3 * c[2] / max(c[8], 1), 100 * c[3] / max(c[2], 1), 100 * c[4] / max(c[2], 1))
+        print("%-5s %8.1f us  %7.1f TFLOP/s%s" % (name, ms * 1e3, fl / ms / 1e9, extra), flush=True)
 
 
 if __name__ == "__main__":

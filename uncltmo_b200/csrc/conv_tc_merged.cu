@@ -28,7 +28,8 @@ namespace {
 
 using namespace tcptx;
 
-constexpr int kThreads = 576;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2-17: epilogue
+constexpr int kThreads = 608;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2-17: epilogue, warp 18: second MMA issuer
+constexpr int kMma2Warp = 18;     // issues the second M block of a tile when MgParams::mma_warps == 2
 constexpr int kEpiWarps = 16;     // 4 TMEM lane quarters x 2 work units x 2 halves of 16 channels
 constexpr int kMaxStages = 8;
 constexpr int kUnits = 2;         // (M block, 32-channel chunk) pairs per tile: 2 blocks x 32 ch or 1 block x 64 ch
@@ -52,6 +53,7 @@ struct MgParams {
   int PW, PH, BW;
   int band_total, tiles_per_band, tiles_per_img, num_items;
   int nchunk, ksteps, stages, nacc, acc_cols;   // ksteps: K = 16 steps (16 input channels each) per pipeline stage
+  int mma_warps;            // 1, or 2: the M blocks of a tile are issued by two warps (each commits its own arrivals)
   int a_box_bytes, a_stage_bytes, b_stage_bytes, stage_bytes;
   int act, emit_skip, fuse_outc;
   int probe_noload;         // timing probe: the producer only loads the first `stages` chunks, then re-signals stale stages
@@ -97,7 +99,9 @@ __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 
 // MMA issuer: 3 filter rows x MB blocks per K chunk, straight-line (MB is a compile-time constant), every block of
 // the tile is always issued (blocks past the end of a band read zero-filled / stale rows and are masked later).
-template <int MB, int kKSteps>
+// B0..B1: the M blocks this warp issues (with two issuing warps each block has its own accumulator columns, so the two
+// instruction streams never touch the same TMEM columns and need no ordering between them).
+template <int MB, int kKSteps, int B0, int B1>
 __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_base, uint64_t* full, uint64_t* empty,
                                             uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base, int lane) {
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NP >> 3) << 17) | ((128u >> 4) << 24);
@@ -111,9 +115,10 @@ __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_ba
   const int nacc = p.nacc, acc_cols = p.acc_cols, nchunk = p.nchunk, stages = p.stages, num_items = p.num_items;
   int stage = 0, acc = 0;
   uint32_t phase = 0, acc_phase = 0;
-  unsigned long long* const dbg = UNCL_PROBE(1, 1) ? p.dbg : nullptr;
+  unsigned long long* const dbg = (UNCL_PROBE(1, 1) && B0 == 0) ? p.dbg : nullptr;
   long long w_full = 0, w_tempty = 0;
   const long long t_begin = dbg ? clock64() : 0;
+  const unsigned long long g_begin = dbg ? globaltimer_ns() : 0ull;
   for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
     const MgItem it = mg_decode(p, item);
     const long long tw0 = dbg ? clock64() : 0;
@@ -136,7 +141,7 @@ __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_ba
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-            for (int b = 0; b < MB; ++b) {
+            for (int b = B0; b < B1; ++b) {
               tc_mma_bf16(d0 + (uint32_t)b * np, a_row + (uint32_t)kc * a_kstep_16 + (uint32_t)ky * pw + (uint32_t)b * 128u,
                           desc_hi, b_lo + (uint32_t)(kc * 3 + ky) * b_row_16, desc_hi, idesc,
                           (kc > 0 || ky > 0) ? 1u : (ch > 0 ? 1u : 0u));
@@ -156,6 +161,7 @@ __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_ba
     atomicAdd(dbg + 2, (unsigned long long)(clock64() - t_begin));
     atomicAdd(dbg + 3, (unsigned long long)w_full);
     atomicAdd(dbg + 4, (unsigned long long)w_tempty);
+    atomicAdd(dbg + 8, globaltimer_ns() - g_begin);   // with [2]: the SM clock this launch actually ran at
   }
 }
 
@@ -179,8 +185,8 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpiWarps); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)p.mma_warps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], (uint32_t)p.mma_warps); mbar_init(&tempty[s], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -236,8 +242,14 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     // N' = 96: two M blocks, 32 input channels per stage (halves the barrier round trips of the latency-bound issuing
     // warp: 329 -> 302 us on up3.conv); N' = 192: one M block, 16 channels per stage (the 18 KB weight stage would
     // leave only 3 pipeline stages otherwise: 101 -> 108 us on up1.conv)
-    if (p.MB == 1) mg_mma_role<1, 1>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
-    else mg_mma_role<2, 2>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
+    // The issuing warp is a serial, latency-bound instruction stream (uniform-datapath adds, R2UR, barrier polls): with
+    // two M blocks per tile a second warp on another scheduler takes block 1, halving the instructions behind each MMA.
+    if (p.MB == 1) mg_mma_role<1, 1, 0, 1>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
+    else if (p.mma_warps == 2) mg_mma_role<2, 2, 0, 1>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
+    else mg_mma_role<2, 2, 0, 2>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
+    __syncwarp();
+  } else if (warp == kMma2Warp) {
+    if (p.mma_warps == 2) mg_mma_role<2, 2, 1, 2>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
     __syncwarp();
   } else {
     // =============================== epilogue ===============================
@@ -450,6 +462,8 @@ int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
   p.stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   const int tail = 128 + 2 * kUnits * 4 * kXSlot * 4 + 2 * kUnits * 128 * 4 + (2 * kMaxStages + 4) * 8 + 16 + 2 * C_out * 4 + 256;
   const int budget = 227 * 1024 - tail;
+  p.mma_warps = p.MB == 2 ? 2 : 1;
+  if (const char* e = probe_env("UNCL_MMA_WARPS")) { if (atoi(e) == 1) p.mma_warps = 1; }
   p.stages = budget / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (const char* e = probe_env("UNCL_MG_STAGES")) { const int want = atoi(e); if (want >= 2 && want < p.stages) p.stages = want; }

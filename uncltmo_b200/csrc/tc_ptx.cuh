@@ -101,6 +101,12 @@ __device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]
       : "memory");
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
