@@ -70,7 +70,7 @@ int uncl_conv3x3_tc_dgrad(const void* in, long in_img_stride, const void* w_pack
 
 /* Tile plan uncl_conv3x3_tc would use for a problem: pure host arithmetic, callable without a GPU (tests check the tile
  * coverage and that uncltmo_b200/packing.py packs the weights for the kernel the library will pick).
- * plan[16] = { kind (0: one tap per MMA, conv_tc.cu; 1: kx-merged, conv_tc_merged.cu), NT, NS, MMA N, M blocks per tile,
+ * plan[16] = { kind (0: one tap per MMA, conv_tc.cu; bit 0: kx-merged, conv_tc_merged.cu, bit 1: row-aligned tiles, bit 2: resident weights), NT, NS, MMA N, M blocks per tile,
  *   tile advance in positions, PW, PH, BW, column bands, tiles per band, work items, pipeline stages, accumulator stages,
  *   K=16 steps per stage, dynamic shared memory bytes }. */
 int uncl_conv3x3_tc_plan(int N, int C_in, int H, int W, int C_out, int pad, int* plan);

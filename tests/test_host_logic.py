@@ -178,13 +178,18 @@ def test_conv3x3_tc_plan_invariants():
         assert (p["tiles_per_band"] - 1) * p["adv"] <= last_valid                         # ... without an empty tile
         # the deepest pixel an MMA row reads: tile start offset (< PW) + 128*MB rows + two filter rows (+2 columns); the last
         # two taps of wrap-around rows (masked outputs) may read up to two pixels past the box, inside the stage
-        assert (p["PW"] - 1 + 128 * p["MB"] - 1 + 2 * p["PW"] + 2) < p["PH"] * p["PW"] + p["PW"]
+        # (row-aligned tiles of the merged kernel always start at a row start)
+        aligned = (p["kind"] & 3) == 3
+        moff_max = 0 if aligned else p["PW"] - 1
+        assert (moff_max + 128 * p["MB"] - 1 + 2 * p["PW"] + 2) <= p["PH"] * p["PW"] + p["PW"]
+        if aligned:
+            assert p["adv"] <= 128 * p["MB"] and p["PH"] == p["adv"] // p["PW"] + 2
         assert p["MB"] * p["mma_n"] <= (512 if p["nacc"] == 1 else 256)                   # TMEM columns per stage
         assert p["stages"] >= 2 and p["smem"] <= 227 * 1024
         assert p["items"] == n * p["bands"] * p["tiles_per_band"] * p["NS"]
         assert p["NT"] * p["NS"] == co and ci % (16 * p["ksteps"]) == 0
-        if p["kind"] == 1:
-            assert p["mma_n"] == 3 * p["NT"] and p["adv"] == 128 * p["MB"] - 2 and p["MB"] * (p["NT"] // 32) == 2
+        if p["kind"] & 1:
+            assert p["mma_n"] == 3 * p["NT"] and (p["adv"] == 128 * p["MB"] - 2 or aligned) and p["MB"] * (p["NT"] // 32) == 2
         else:
             assert p["adv"] == 128 * p["MB"]
 
@@ -196,7 +201,7 @@ def test_weight_packing_follows_the_kernel_choice():
         for co in (32, 64, 96, 128, 256):
             p = _conv_plan(1, ci, 20, 20, co, 0)
             packed = packing.conv3x3_tc(torch.zeros(9, ci, co))
-            if p["kind"] == 1:
+            if p["kind"] & 1:
                 assert packed.shape == (p["NS"], ci // 16, 3, 2, p["mma_n"], 8)
             else:
                 assert packed.shape == (p["NS"], ci // 16, 9, 2, p["NT"], 8)

@@ -850,7 +850,7 @@ extern "C" int uncl_pw_conv_tc_dgrad(const void* in, long in_img_stride, const v
 int uncl_plan_conv3x3_tc_merged(int N, int C_in, int H, int W, int C_out, int pad, int* plan);
 
 // Tile plan of uncl_conv3x3_tc for a problem - pure host arithmetic, no GPU needed.  plan[16]: kind (0 one-tap kernel,
-// 1 kx-merged kernel), NT, NS, MMA N, M blocks per tile, tile advance in positions, PW, PH, BW, bands, tiles per band,
+// bit 0 kx-merged kernel, bit 1 its tiles are row-aligned, bit 2 its weights stay resident in shared memory), NT, NS, MMA N, M blocks per tile, tile advance in positions, PW, PH, BW, bands, tiles per band,
 // work items, pipeline stages, accumulator stages, K=16 steps per stage, dynamic shared memory bytes.
 extern "C" int uncl_conv3x3_tc_plan(int N, int C_in, int H, int W, int C_out, int pad, int* plan) {
   UNCL_REQUIRE(plan != nullptr && N > 0 && C_in % 16 == 0 && C_out % 32 == 0 && (pad == 0 || pad == 2) &&

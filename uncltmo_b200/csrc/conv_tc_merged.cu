@@ -54,6 +54,8 @@ struct MgParams {
   int band_total, tiles_per_band, tiles_per_img, num_items;
   int nchunk, ksteps, stages, nacc, acc_cols;   // ksteps: K = 16 steps (16 input channels each) per pipeline stage
   int mma_warps;            // 1, or 2: the M blocks of a tile are issued by two warps (each commits its own arrivals)
+  int w_res, w_total;       // weights resident in shared memory (loaded once per CTA) and their size in bytes
+  int aligned;              // row-aligned tiles (ADV = R * PW) instead of flat tiles (ADV = 128 * MB - 2)
   int a_box_bytes, a_stage_bytes, b_stage_bytes, stage_bytes;
   int act, emit_skip, fuse_outc;
   int probe_noload;         // timing probe: the producer only loads the first `stages` chunks, then re-signals stale stages
@@ -103,13 +105,16 @@ __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 // instruction streams never touch the same TMEM columns and need no ordering between them).
 template <int MB, int kKSteps, int B0, int B1>
 __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_base, uint64_t* full, uint64_t* empty,
-                                            uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base, int lane) {
+                                            uint64_t* tfull, uint64_t* tempty, uint64_t* wfull, uint32_t tmem_base, int lane) {
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NP >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t desc_hi = (128u >> 4) | (1u << 14);
   const uint32_t a_lo_const = ((uint32_t)(p.PH * p.PW) & 0x3fffu) << 16;   // LBO_A = PH*PW*16 B
   const uint32_t b_lo_const = ((uint32_t)p.NP & 0x3fffu) << 16;            // LBO_B = NP*16 B
   const uint32_t stage0_16 = smem_u32(stage_base) >> 4, stage_16 = (uint32_t)p.stage_bytes >> 4;
   const uint32_t a_bytes_16 = (uint32_t)p.a_stage_bytes >> 4, b_row_16 = (uint32_t)(2 * p.NP);
+  // resident weights live behind the stage ring: chunk ch at wres + ch * b_stage_bytes
+  const bool w_res = p.w_res != 0;
+  const uint32_t wres_16 = stage0_16 + (uint32_t)p.stages * stage_16, b_stage_16 = (uint32_t)p.b_stage_bytes >> 4;
   const uint32_t pw = (uint32_t)p.PW, np = (uint32_t)p.NP;
   const uint32_t a_kstep_16 = (uint32_t)(2 * p.PH * p.PW);   // the next two channel blocks of the halo box
   const int nacc = p.nacc, acc_cols = p.acc_cols, nchunk = p.nchunk, stages = p.stages, num_items = p.num_items;
@@ -119,6 +124,7 @@ __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_ba
   long long w_full = 0, w_tempty = 0;
   const long long t_begin = dbg ? clock64() : 0;
   const unsigned long long g_begin = dbg ? globaltimer_ns() : 0ull;
+  if (w_res) mbar_wait(wfull, 0);
   for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
     const MgItem it = mg_decode(p, item);
     const long long tw0 = dbg ? clock64() : 0;
@@ -133,7 +139,7 @@ __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_ba
       tc_fence_after();
       const uint32_t sa16 = stage0_16 + (uint32_t)stage * stage_16;
       const uint32_t a_row = a_lo_const | (sa16 + (uint32_t)it.moff0);
-      const uint32_t b_lo = b_lo_const | (sa16 + a_bytes_16);
+      const uint32_t b_lo = b_lo_const | (w_res ? wres_16 + (uint32_t)ch * b_stage_16 : sa16 + a_bytes_16);
       if (elect_one()) {
         // a stage holds kKSteps K=16 steps (32 input channels): kKSteps x 3 filter rows x MB blocks, straight-line
 #pragma unroll
@@ -170,14 +176,15 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   uint8_t* stage_base = smem;
-  float* xbuf = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes);   // [2][kUnits][4][kXSlot]
+  float* xbuf = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes + (p.w_res ? p.w_total : 0));   // [2][kUnits][4][kXSlot]
   float* lbuf = xbuf + 2 * kUnits * 4 * kXSlot;                                       // [2][kUnits][128] partial logits
   uint64_t* bars = reinterpret_cast<uint64_t*>(lbuf + 2 * kUnits * 128);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* wfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [C_out] (+ [C_out] outc weights)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -187,6 +194,7 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)p.mma_warps); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], (uint32_t)p.mma_warps); mbar_init(&tempty[s], kEpiWarps); }
+    mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -207,9 +215,15 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = (uint32_t)(p.a_box_bytes + p.b_stage_bytes), b_bytes = (uint32_t)p.b_stage_bytes;
+      const bool w_res = p.w_res != 0;
+      const uint32_t b_bytes = (uint32_t)p.b_stage_bytes, tx_bytes = (uint32_t)p.a_box_bytes + (w_res ? 0u : b_bytes);
       const int a_stage_bytes = p.a_stage_bytes;
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
+      if (w_res) {   // the whole filter bank once per CTA (NS == 1), chunk by chunk behind the stage ring
+        uint8_t* wres = stage_base + (size_t)stages * stage_bytes;
+        mbar_expect_tx(wfull, (uint32_t)p.w_total);
+        for (int ch = 0; ch < nchunk; ++ch) bulk_load(wres + (size_t)ch * b_bytes, wbase + (size_t)ch * b_bytes, b_bytes, wfull);
+      }
       unsigned long long* const dbg = UNCL_PROBE(1, 1) ? p.dbg : nullptr;
       long long w_empty = 0;
       const long long t_begin = dbg ? clock64() : 0;
@@ -226,7 +240,7 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
           else {
           mbar_expect_tx(&full[stage], tx_bytes);
           tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, ch * 2 * p.ksteps, it.n);
-          bulk_load(sa + a_stage_bytes, wsrc + (size_t)ch * b_bytes, b_bytes, &full[stage]);
+          if (!w_res) bulk_load(sa + a_stage_bytes, wsrc + (size_t)ch * b_bytes, b_bytes, &full[stage]);
           }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -244,12 +258,13 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     // leave only 3 pipeline stages otherwise: 101 -> 108 us on up1.conv)
     // The issuing warp is a serial, latency-bound instruction stream (uniform-datapath adds, R2UR, barrier polls): with
     // two M blocks per tile a second warp on another scheduler takes block 1, halving the instructions behind each MMA.
-    if (p.MB == 1) mg_mma_role<1, 1, 0, 1>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
-    else if (p.mma_warps == 2) mg_mma_role<2, 2, 0, 1>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
-    else mg_mma_role<2, 2, 0, 2>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
+    if (p.MB == 1 && p.ksteps == 1) mg_mma_role<1, 1, 0, 1>(p, stage_base, full, empty, tfull, tempty, wfull, tmem_base, lane);
+    else if (p.MB == 1) mg_mma_role<1, 2, 0, 1>(p, stage_base, full, empty, tfull, tempty, wfull, tmem_base, lane);
+    else if (p.mma_warps == 2) mg_mma_role<2, 2, 0, 1>(p, stage_base, full, empty, tfull, tempty, wfull, tmem_base, lane);
+    else mg_mma_role<2, 2, 0, 2>(p, stage_base, full, empty, tfull, tempty, wfull, tmem_base, lane);
     __syncwarp();
   } else if (warp == kMma2Warp) {
-    if (p.mma_warps == 2) mg_mma_role<2, 2, 1, 2>(p, stage_base, full, empty, tfull, tempty, tmem_base, lane);
+    if (p.mma_warps == 2) mg_mma_role<2, 2, 1, 2>(p, stage_base, full, empty, tfull, tempty, wfull, tmem_base, lane);
     __syncwarp();
   } else {
     // =============================== epilogue ===============================
@@ -432,43 +447,66 @@ int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
   p.NP = 3 * p.NT;
   p.C_out = C_out; p.pad = pad;
   p.Ho = H + 2 * pad - 2; p.Wo = W + 2 * pad - 2;
-  const int kKSteps = p.NT == 32 ? 2 : 1;   // must match the mg_mma_role instantiation chosen by MB
-  p.ksteps = kKSteps;
-  UNCL_REQUIRE(C_in % (16 * kKSteps) == 0, "%s: C_in must be a multiple of %d", what, 16 * kKSteps);
-  p.nchunk = C_in / (16 * kKSteps);
   // accumulator staging: two stages of 256 TMEM columns (epilogue of tile i overlaps the MMAs of tile i+1)
   p.nacc = 2;
   p.acc_cols = 256;
   p.MB = p.acc_cols / p.NP;   // 2 blocks of 96 columns or 1 block of 192: always two 32-channel work units per tile
-  p.ADV = 128 * p.MB - 2;
   int bw_max = 126;
   if (const char* e = probe_env("UNCL_MG_BW")) { const int want = atoi(e); if (want >= 8 && want < bw_max) bw_max = want; }
   const int nbands = ceil_div(p.Wo, bw_max);
   p.BW = ceil_div(p.Wo, nbands);
   p.PW = p.BW + 2;
   p.band_total = p.Ho * p.PW;
-  p.tiles_per_band = ceil_div(p.band_total - 2, p.ADV);
-  if (p.tiles_per_band < 1) p.tiles_per_band = 1;
+  // Tile = 128*MB consecutive positions of the band flattened with pitch PW.  Flat tiling advances by 128*MB - 2 (tiles
+  // overlap by two positions so that the kx sum never crosses a tile) and a tile may start anywhere in a row: the halo
+  // box needs ceil rows + 1 + 2.  When one or two whole rows nearly fill the tile (R*PW >= 97 % of it: PW = 124..128) tiles
+  // are row-aligned instead: R rows per tile, box = R + 2 rows (3 instead of 5 rows for one 124-wide row, 4 instead of 6
+  // for two), no overlap needed because a row ends with its two wrap-around columns.  Measured (1080p frame): 256 -> 32
+  // at 124^2 141 -> 130 us; narrower pitches (61, 63) lose more to the unused tile tail than the smaller box saves.
+  const int rows_al = (128 * p.MB) / p.PW;
+  const bool aligned = rows_al >= 1 && rows_al <= 2 && p.PW >= 100 && rows_al * p.PW * 100 >= 97 * (128 * p.MB - 2) &&
+                       probe_env("UNCL_MG_FLAT") == nullptr;
+  p.aligned = aligned ? 1 : 0;
+  if (aligned) {
+    p.ADV = rows_al * p.PW;
+    p.tiles_per_band = ceil_div(p.Ho, rows_al);
+    p.PH = rows_al + 2;
+  } else {
+    p.ADV = 128 * p.MB - 2;
+    p.tiles_per_band = ceil_div(p.band_total - 2, p.ADV);
+    if (p.tiles_per_band < 1) p.tiles_per_band = 1;
+    p.PH = (p.PW - 1 + 128 * p.MB - 1) / p.PW + 1 + 2;
+  }
   p.tiles_per_img = nbands * p.tiles_per_band;
-  p.PH = (p.PW - 1 + 128 * p.MB - 1) / p.PW + 1 + 2;
   UNCL_REQUIRE(p.PW <= 128 && p.PH <= 256, "%s: halo tile too large (%d x %d)", what, p.PW, p.PH);
   p.num_items = N * p.tiles_per_img * p.NS;
   UNCL_REQUIRE(p.num_items < (1 << 24), "%s: too many tiles (%d)", what, p.num_items);
   p.m_NS = (1ull << 40) / (unsigned)p.NS + 1; p.m_tpi = (1ull << 40) / (unsigned)p.tiles_per_img + 1;
   p.m_tpb = (1ull << 40) / (unsigned)p.tiles_per_band + 1; p.m_PW = (1ull << 40) / (unsigned)p.PW + 1;
-  p.a_box_bytes = 2 * kKSteps * p.PH * p.PW * 16;
-  p.a_stage_bytes = (p.a_box_bytes + 127) & ~127;
-  p.b_stage_bytes = kKSteps * 3 * 2 * p.NP * 16;
-  p.stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
-  const int tail = 128 + 2 * kUnits * 4 * kXSlot * 4 + 2 * kUnits * 128 * 4 + (2 * kMaxStages + 4) * 8 + 16 + 2 * C_out * 4 + 256;
-  const int budget = 227 * 1024 - tail;
   p.mma_warps = p.MB == 2 ? 2 : 1;
   if (const char* e = probe_env("UNCL_MMA_WARPS")) { if (atoi(e) == 1) p.mma_warps = 1; }
-  p.stages = budget / p.stage_bytes;
+  const int tail = 128 + 2 * kUnits * 4 * kXSlot * 4 + 2 * kUnits * 128 * 4 + (2 * kMaxStages + 5) * 8 + 16 + 2 * C_out * 4 + 256;
+  const int budget = 227 * 1024 - tail;
+  // Pipeline stage = the halo box of `ksteps` K = 16 steps (+ their weights).  When the whole filter bank fits next to
+  // at least three A stages it is loaded ONCE per CTA and stays resident (the weight stage is otherwise re-fetched from
+  // L2 for every tile: 35 % of the L2 -> shared-memory traffic of the 128 -> 32 layer); N' = 96 issues 32 channels per
+  // stage (halves the barrier round trips of the issuing warps), N' = 192 too when its weights are resident.
+  p.w_total = (C_in / 16) * 3 * 2 * p.NP * 16;
+  auto a_bytes = [&](int ks) { return (2 * ks * p.PH * p.PW * 16 + 127) & ~127; };
+  int ks = (p.NT == 32 && C_in % 32 == 0) ? 2 : 1;
+  p.w_res = (p.NS == 1 && p.w_total + 3 * a_bytes(ks) <= budget && probe_env("UNCL_MG_NO_WRES") == nullptr) ? 1 : 0;
+  UNCL_REQUIRE(p.NT == 64 || ks == 2, "%s: C_in must be a multiple of 32 for C_out = 32", what);
+  p.ksteps = ks;
+  p.nchunk = C_in / (16 * ks);
+  p.a_box_bytes = 2 * ks * p.PH * p.PW * 16;
+  p.a_stage_bytes = a_bytes(ks);
+  p.b_stage_bytes = ks * 3 * 2 * p.NP * 16;
+  p.stage_bytes = p.a_stage_bytes + (p.w_res ? 0 : p.b_stage_bytes);
+  p.stages = (budget - (p.w_res ? p.w_total : 0)) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (const char* e = probe_env("UNCL_MG_STAGES")) { const int want = atoi(e); if (want >= 2 && want < p.stages) p.stages = want; }
   UNCL_REQUIRE(p.stages >= 2, "%s: tile does not fit shared memory (%d B per stage)", what, p.stage_bytes);
-  int smem_bytes = p.stages * p.stage_bytes + tail;
+  int smem_bytes = p.stages * p.stage_bytes + (p.w_res ? p.w_total : 0) + tail;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM (each owns all 512 TMEM columns)
   *smem_bytes_out = smem_bytes;
   return UNCL_OK;
@@ -479,7 +517,7 @@ int uncl_plan_conv3x3_tc_merged(int N, int C_in, int H, int W, int C_out, int pa
   MgParams p{};
   int smem = 0;
   if (int rc = mg_plan(p, N, C_in, H, W, C_out, pad, 0, "conv3x3_tc_plan(merged)", &smem)) return rc;
-  const int v[16] = {1, p.NT, p.NS, p.NP, p.MB, p.ADV, p.PW, p.PH, p.BW, p.tiles_per_img / p.tiles_per_band, p.tiles_per_band,
+  const int v[16] = {1 | (p.aligned << 1) | (p.w_res << 2), p.NT, p.NS, p.NP, p.MB, p.ADV, p.PW, p.PH, p.BW, p.tiles_per_img / p.tiles_per_band, p.tiles_per_band,
                      p.num_items, p.stages, p.nacc, p.ksteps, smem};
   for (int i = 0; i < 16; ++i) plan[i] = v[i];
   return UNCL_OK;

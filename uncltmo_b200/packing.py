@@ -37,7 +37,7 @@ def conv3x3_tc_is_merged(ci, co):
     rc = _lib.lib().uncl_conv3x3_tc_plan(1, ci, 64, 64, co, 0, ctypes.cast(plan, ctypes.c_void_p))
     if rc != 0:
         raise RuntimeError("uncl_conv3x3_tc_plan failed (%d): %s" % (rc, _lib.lib().uncl_last_error().decode()))
-    return plan[0] == 1
+    return (plan[0] & 1) == 1
 
 
 def conv3x3_tc(w9):
