@@ -68,6 +68,17 @@ int uncl_conv3x3_tc_dgrad(const void* in, long in_img_stride, const void* w_pack
                           void* out, long out_img_stride, int out_dtype, int N, int C_in, int H, int W, int C_out, int pad,
                           uncl_stream_t stream);
 
+/* up.conv.conv with the skip operators fused: unet_parts.py:311-332 computes cat([x2, x1, x2^2, sqrt(x2 + 1e-8)]) and feeds
+ * it to ConvTranspose2d 3x3.  Here `in` holds only [x2 (C_skip) | x1 (C_skip)] (bf16 blocked, 2*C_skip channels); the
+ * squared and square-root planes are built in shared memory from the x2 chunk the kernel has just loaded and never touch
+ * HBM.  w_packed = packing.conv3x3_tc of the full [9][4*C_skip][C_out] bank in concat order.  C_out == 32, C_skip % 32 == 0. */
+int uncl_conv3x3_tc_skipcat(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                            long out_img_stride, int out_dtype, int N, int C_skip, int H, int W, int C_out, int pad,
+                            int act, uncl_stream_t stream);
+
+/* Tile plan of uncl_conv3x3_tc_skipcat (the 16 fields of uncl_conv3x3_tc_plan): pure host arithmetic, no GPU needed. */
+int uncl_conv3x3_tc_skipcat_plan(int N, int C_skip, int H, int W, int C_out, int pad, int* plan);
+
 /* Tile plan uncl_conv3x3_tc would use for a problem: pure host arithmetic, callable without a GPU (tests check the tile
  * coverage and that uncltmo_b200/packing.py packs the weights for the kernel the library will pick).
  * plan[16] = { kind (0: one tap per MMA, conv_tc.cu; bit 0: kx-merged, conv_tc_merged.cu, bit 1: row-aligned tiles, bit 2: resident weights), NT, NS, MMA N, M blocks per tile,
@@ -146,7 +157,7 @@ int uncl_pw_conv(const float* in, const float* w, const float* bias, const float
 int uncl_gcn_knn_aggregate(const float* y, const float* relpos, void* z, int z_dtype, int* idx_out, int N, int C,
                            uncl_stream_t stream);
 
-/* Diagnostics for profiling only: per-role cycle counters of the tensor-core conv kernels (10 uint64 on the device,
+/* Diagnostics for profiling only: per-role cycle counters of the tensor-core conv kernels (12 uint64 on the device,
  * zeroed by the caller; NULL switches off).  See conv_tc.cu. */
 int uncl_conv_tc_set_debug(void* counters);
 

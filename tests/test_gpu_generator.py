@@ -154,6 +154,46 @@ def test_tcgen05_conv_against_cuda_core_conv(ci, co, h, pad, n):
     assert torch.isnan(out[:, co // 8:2 * co // 8].float()).all()  # untouched slice stays untouched
 
 
+@pytest.mark.parametrize("cs,h,pad,n", [(32, 252, 2, 1), (64, 122, 2, 2), (32, 5, 2, 3), (32, 40, 0, 1), (64, 129, 2, 1),
+                                        (96, 33, 2, 1)])
+def test_fused_skip_operators_conv(cs, h, pad, n):
+    """uncl_conv3x3_tc_skipcat (skip^2 and sqrt(skip + eps) built in shared memory from the [skip | up] tensor) against the
+    same conv over the materialised concat [skip | up | skip^2 | sqrt(skip + eps)]: identical bf16 operands (the derived
+    planes are rounded to bf16 exactly as the materialising epilogue rounds them), so only the summation order differs.
+    unet_parts.py:311-332.  Zero padding applies to the concatenated tensor: sqrt is 0, not sqrt(eps), outside the image."""
+    co = 32
+    g = torch.Generator(device="cuda").manual_seed(cs * 1000 + h)
+    x = torch.randn((n, 2 * cs // 8, h, h, 8), device="cuda", generator=g)
+    x[:, :cs // 8] = x[:, :cs // 8].relu()          # the skip tensor is a post-ReLU activation (exact zeros included)
+    x = x.to(torch.bfloat16)
+    skip = x[:, :cs // 8].float()
+    full = torch.cat([x, (skip * skip).to(torch.bfloat16), torch.sqrt(skip + 1e-8).to(torch.bfloat16)], dim=1).contiguous()
+    w9 = (torch.randn((9, 4 * cs, co), device="cuda", generator=g) / (9 * 4 * cs) ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(co, device="cuda", generator=g) * 0.1
+    ho = h + 2 * pad - 2
+    ref = torch.empty((n, co // 8, ho, ho, 8), device="cuda", dtype=torch.float32)
+    out = torch.full((n, co // 8, ho, ho, 8), float("nan"), device="cuda", dtype=torch.float32)
+    wp = packing.conv3x3_tc(w9)
+    _lib.call("uncl_conv3x3_tc", full, full.stride(0), wp, b, ref, ref.stride(0), _lib.F32, n, 4 * cs, h, h, co, pad, 1, 0, 0,
+              None, None, None, None)
+    _lib.call("uncl_conv3x3_tc_skipcat", x, x.stride(0), wp, b, out, out.stride(0), _lib.F32, n, cs, h, h, co, pad, 1)
+    torch.cuda.synchronize()
+    assert not torch.isnan(out).any()
+    assert (out - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item()) and rel(out, ref) <= 1e-3
+
+
+def test_fused_skip_matches_materialised_network(oracle_run):
+    """The bf16 generator with the skip operators fused into the consuming convs (default) against the same network
+    with the three skip planes materialised, and both against the oracle."""
+    _, x, o_out, _, _ = oracle_run
+    net = make("bf16")
+    net.fused_skip = True
+    fused = net.tonemap_tiles(x.cuda())
+    net.fused_skip = False
+    mat = net.tonemap_tiles(x.cuda())
+    assert rel(fused, mat) <= 2e-3 and rel(fused, o_out) <= 1e-2 and rel(mat, o_out) <= 1e-2
+
+
 @pytest.mark.parametrize("ci,h,pad", [(64, 37, 0), (128, 20, 2)])
 def test_merged_conv_fused_out_conv_and_fp32_output(ci, h, pad):
     """kx-merged kernel: fp32 feature-map output, and the fused 1x1 out conv + sigmoid (two 16-channel halves of a pixel

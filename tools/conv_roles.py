@@ -10,7 +10,7 @@ G_ARGS = (1, 1, "sigmoid", 4, 4, "square_and_square_root", 32, 0, "unet", 0, 0, 
 net = G.UNet(*G_ARGS, up_mode=0, precision="bf16").cuda().eval()
 net.load_state_dict(make_generator_state_dict())
 x = torch.rand(60, 1, 256, 256, device="cuda")
-cnt = torch.zeros(10, dtype=torch.int64, device="cuda")
+cnt = torch.zeros(12, dtype=torch.int64, device="cuda")
 rows = []
 orig = G.call
 

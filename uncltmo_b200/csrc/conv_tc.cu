@@ -683,7 +683,7 @@ int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void
                                   long out_img_stride, int out_f32, int N, int C_in, int H, int W, int C_out, int pad,
                                   int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
                                   float* out_img, float* out_logit, const void* mask, long mask_img_stride,
-                                  unsigned long long* dbg, cudaStream_t stream);
+                                  unsigned long long* dbg, int derive, cudaStream_t stream);
 
 // Which 3x3 layers run in the kx-merged kernel (conv_tc_merged.cu); packing.conv3x3_tc packs the weights to match.
 // Measured per layer of the 1080p frame (profiles/README.md): with C_out <= 64 the merged formulation wins when the
@@ -708,7 +708,7 @@ static int conv3x3_tc_impl(const void* in, long in_img_stride, const void* w_pac
     UNCL_REQUIRE(H + 2 * pad - 2 > 0 && W + 2 * pad - 2 > 0, "conv3x3_tc: empty output");
     return uncl_launch_conv3x3_tc_merged(in, in_img_stride, w_packed, bias, out, out_img_stride, out_dtype == UNCL_F32, N, C_in,
                                          H, W, C_out, pad, act, emit_skip, fuse_outc, outc_w, outc_b, out_img, out_logit,
-                                         mask, mask_img_stride, g_dbg, stream);
+                                         mask, mask_img_stride, g_dbg, 0, stream);
   }
   TcParams p{};
   p.NT = C_out < 128 ? C_out : 128;
@@ -740,6 +740,25 @@ extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w
                                float* out_img, float* out_logit, cudaStream_t stream) {
   return conv3x3_tc_impl(in, in_img_stride, w_packed, bias, out, out_img_stride, out_dtype, N, C_in, H, W, C_out, pad, act,
                          emit_skip, fuse_outc, outc_w, outc_b, out_img, out_logit, nullptr, 0, stream);
+}
+
+// First conv of an `up` block with the skip operators FUSED (unet_parts.py:311-332: x2 -> [x2, x2^2, sqrt(x2 + 1e-8)],
+// cat with the up-sampled x1, ConvTranspose 3x3).  `in` holds only [skip (C_skip) | up-sampled (C_skip)] channels; the
+// squared and square-root planes are never written to memory: the kernel builds them in shared memory from the skip
+// chunk it has just loaded (conv_tc_merged.cu, derive mode), which halves the layer's DRAM reads and lets the producing
+// layer write one plane instead of three.  w_packed: packing.conv3x3_tc of the full [9][4*C_skip][C_out] filter bank
+// (concat order skip | up | skip^2 | sqrt).  Built for C_out == 32 (the 252^2 and 124^2 levels of the generator).
+extern "C" int uncl_conv3x3_tc_skipcat(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                                       long out_img_stride, int out_dtype, int N, int C_skip, int H, int W, int C_out, int pad,
+                                       int act, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && C_skip > 0 && C_skip % 32 == 0 && C_out == 32 && (pad == 0 || pad == 2) && out != nullptr,
+               "conv3x3_tc_skipcat: unsupported C_skip=%d C_out=%d pad=%d", C_skip, C_out, pad);
+  UNCL_REQUIRE(out_dtype == UNCL_F32 || out_dtype == UNCL_BF16, "conv3x3_tc_skipcat: bad out_dtype");
+  UNCL_REQUIRE(act == UNCL_ACT_RELU || act == UNCL_ACT_NONE, "conv3x3_tc_skipcat: only ReLU / identity epilogues are built");
+  UNCL_REQUIRE(H + 2 * pad - 2 > 0 && W + 2 * pad - 2 > 0, "conv3x3_tc_skipcat: empty output");
+  return uncl_launch_conv3x3_tc_merged(in, in_img_stride, w_packed, bias, out, out_img_stride, out_dtype == UNCL_F32, N,
+                                       4 * C_skip, H, W, C_out, pad, act, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                                       g_dbg, 1, stream);
 }
 
 // Data gradient of a 3x3 conv / ConvTranspose 3x3 with the ReLU backward of the PRODUCING layer fused into the epilogue:

@@ -28,8 +28,12 @@ namespace {
 
 using namespace tcptx;
 
-constexpr int kThreads = 608;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2-17: epilogue, warp 18: second MMA issuer
+constexpr int kThreads = 608;     // warp 0: TMA producer, 1: MMA issuer, 2-17: epilogue, 18: second MMA issuer
+constexpr int kThreadsDerive = 736;   // ... + warps 19-22: skip-operator warps (the kDerive instantiation only)
 constexpr int kMma2Warp = 18;     // issues the second M block of a tile when MgParams::mma_warps == 2
+constexpr int kDeriveWarp0 = 19;  // fused skip operators (MgParams::derive): x^2 and sqrt(x + eps) chunks built in shared memory
+constexpr int kDeriveWarps = 4;
+constexpr int kMaxProg = 16;      // ring positions (K chunks) per tile in derive mode
 constexpr int kEpiWarps = 16;     // 4 TMEM lane quarters x 2 work units x 2 halves of 16 channels
 constexpr int kMaxStages = 8;
 constexpr int kUnits = 2;         // (M block, 32-channel chunk) pairs per tile: 2 blocks x 32 ch or 1 block x 64 ch
@@ -56,6 +60,12 @@ struct MgParams {
   int mma_warps;            // 1, or 2: the M blocks of a tile are issued by two warps (each commits its own arrivals)
   int w_res, w_total;       // weights resident in shared memory (loaded once per CTA) and their size in bytes
   int aligned;              // row-aligned tiles (ADV = R * PW) instead of flat tiles (ADV = 128 * MB - 2)
+  // Fused skip operators (unet_parts.py:319-322).  The input tensor holds [skip (Cs) | up-sampled (Cs)] only; the K loop
+  // also visits skip^2 and sqrt(skip + 1e-8), which four extra warps build from the skip chunk's shared-memory image.
+  // A tile walks `nchunk` ring positions; position k is a TMA chunk (kind 0, channel block prog_cb[k]) or a derived chunk
+  // (kind 1: square, 2: square root) of the TMA chunk prog_back[k] positions earlier; prog_wch[k] = its weight chunk.
+  int derive, H_in, W_in;
+  unsigned char prog_kind[kMaxProg], prog_cb[kMaxProg], prog_wch[kMaxProg], prog_back[kMaxProg];
   int a_box_bytes, a_stage_bytes, b_stage_bytes, stage_bytes;
   int act, emit_skip, fuse_outc;
   int probe_noload;         // timing probe: the producer only loads the first `stages` chunks, then re-signals stale stages
@@ -99,6 +109,18 @@ __device__ __forceinline__ void tc_ld16_nw(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// two bf16 in one register: elementwise product (one rounding of the exact product, like bf16(x * x) of a float x)
+__device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+// two bf16 -> bf16(sqrt(x + 1e-8)) each (unet_parts.py:321), MUFU square root as in the producing epilogue
+__device__ __forceinline__ uint32_t bf16x2_sqrt_eps(uint32_t v) {
+  const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
+  return pack_bf16x2(fast_sqrt(lo + 1e-8f), fast_sqrt(hi + 1e-8f));
+}
+
 // MMA issuer: 3 filter rows x MB blocks per K chunk, straight-line (MB is a compile-time constant), every block of
 // the tile is always issued (blocks past the end of a band read zero-filled / stale rows and are masked later).
 // B0..B1: the M blocks this warp issues (with two issuing warps each block has its own accumulator columns, so the two
@@ -139,7 +161,8 @@ __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_ba
       tc_fence_after();
       const uint32_t sa16 = stage0_16 + (uint32_t)stage * stage_16;
       const uint32_t a_row = a_lo_const | (sa16 + (uint32_t)it.moff0);
-      const uint32_t b_lo = b_lo_const | (w_res ? wres_16 + (uint32_t)ch * b_stage_16 : sa16 + a_bytes_16);
+      const uint32_t wch = p.derive ? (uint32_t)p.prog_wch[ch] : (uint32_t)ch;
+      const uint32_t b_lo = b_lo_const | (w_res ? wres_16 + wch * b_stage_16 : sa16 + a_bytes_16);
       if (elect_one()) {
         // a stage holds kKSteps K=16 steps (32 input channels): kKSteps x 3 filter rows x MB blocks, straight-line
 #pragma unroll
@@ -171,7 +194,8 @@ __device__ __forceinline__ void mg_mma_role(const MgParams& p, uint8_t* stage_ba
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kDerive>
+__global__ void __launch_bounds__(kDerive ? kThreadsDerive : kThreads, 1)
 conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MgParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -192,7 +216,10 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)p.mma_warps); }
+    // derive mode: the skip-operator warps arrive on every full (they fill the derived stages) and on every empty (they
+    // read the skip stages)
+    const uint32_t extra = p.derive ? (uint32_t)kDeriveWarps : 0u;
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1 + extra); mbar_init(&empty[s], (uint32_t)p.mma_warps + extra); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], (uint32_t)p.mma_warps); mbar_init(&tempty[s], kEpiWarps); }
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -201,7 +228,7 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = threadIdx.x; i < p.C_out; i += kThreads) {
+  for (int i = threadIdx.x; i < p.C_out; i += (int)blockDim.x) {
     s_bias[i] = p.bias ? p.bias[i] : 0.f;
     if (p.fuse_outc) s_bias[p.C_out + i] = p.outc_w[i];
   }
@@ -237,6 +264,19 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
           if (dbg) w_empty += clock64() - tw0;
           uint8_t* sa = stage_base + (size_t)stage * stage_bytes;
           if ((UNCL_PROBE(p.probe_noload, 1)) && (item != (int)blockIdx.x || ch >= stages)) { mbar_arrive(&full[stage]); }
+          else if (p.derive) {
+            const int wch = p.prog_wch[ch];
+            if (p.prog_kind[ch] == 0) {
+              mbar_expect_tx(&full[stage], tx_bytes);
+              tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, (int)p.prog_cb[ch], it.n);
+              if (!w_res) bulk_load(sa + a_stage_bytes, wsrc + (size_t)wch * b_bytes, b_bytes, &full[stage]);
+            } else if (!w_res) {   // derived chunk: only its weights come from memory
+              mbar_expect_tx(&full[stage], b_bytes);
+              bulk_load(sa + a_stage_bytes, wsrc + (size_t)wch * b_bytes, b_bytes, &full[stage]);
+            } else {
+              mbar_arrive(&full[stage]);
+            }
+          }
           else {
           mbar_expect_tx(&full[stage], tx_bytes);
           tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by, ch * 2 * p.ksteps, it.n);
@@ -266,6 +306,90 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
   } else if (warp == kMma2Warp) {
     if (p.mma_warps == 2) mg_mma_role<2, 2, 1, 2>(p, stage_base, full, empty, tfull, tempty, wfull, tmem_base, lane);
     __syncwarp();
+  } else if (warp >= kDeriveWarp0) {
+    // =============================== fused skip operators ===============================
+    // These warps walk the stage ring like a producer.  At a TMA position they only add their arrival; at a derived
+    // position they wait for the source chunk (the skip activations, landed by TMA `back` positions earlier), read its
+    // shared-memory image [2*ksteps channel blocks][PH*PW pixels][8] and write x*x or sqrt(x + 1e-8) at the same offsets
+    // of their own stage - the layout IS the MMA operand layout, so the transform is elementwise.  The zero padding of the
+    // transposed conv applies to the concatenated tensor: sqrt is 0 outside the image, not sqrt(eps).
+    if constexpr (kDerive) {
+      const int dtid = (warp - kDeriveWarp0) * 32 + lane;
+      const int PHPW = p.PH * p.PW, PW = p.PW, H_in = p.H_in, W_in = p.W_in;   // derive mode: ksteps == 2, four channel blocks per stage
+      int stage = 0;
+      uint32_t phase = 0;
+      unsigned long long* const dbg = (UNCL_PROBE(1, 1) && warp == kDeriveWarp0 && lane == 0) ? p.dbg : nullptr;
+      long long w_e = 0, w_s = 0;
+      const long long t_begin = dbg ? clock64() : 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const MgItem it = mg_decode(p, item);
+        for (int ch = 0; ch < nchunk; ++ch) {
+          const int kind = p.prog_kind[ch];
+          if (kind == 2) {   // built together with the square (previous position)
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          const long long tw0 = dbg ? clock64() : 0;
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (kind != 0) {
+            // ONE pass builds both derived chunks: the square into this stage, the square root into the next one
+            int src = stage - 1, nst = stage + 1;
+            uint32_t src_phase = phase, n_phase = phase;
+            if (src < 0) { src += stages; src_phase ^= 1; }
+            if (nst == stages) { nst = 0; n_phase ^= 1; }
+            mbar_wait(&empty[nst], n_phase ^ 1);
+            if (dbg) w_e += clock64() - tw0;
+            const long long tw1 = dbg ? clock64() : 0;
+            mbar_wait(&full[src], src_phase);
+            if (dbg) w_s += clock64() - tw1;
+            const uint8_t* sp = stage_base + (size_t)src * stage_bytes;
+            uint8_t* dp = stage_base + (size_t)stage * stage_bytes;
+            uint8_t* dq = stage_base + (size_t)nst * stage_bytes;
+            constexpr int kStep = kDeriveWarps * 32;
+            for (int pos = dtid; pos < PHPW; pos += kStep) {
+              if (UNCL_PROBE(p.probe_noload, 16)) continue;   // timing probe: no transform at all (wrong results)
+              uint4 v[4], q[4];
+#pragma unroll
+              for (int cb = 0; cb < 4; ++cb) v[cb] = *reinterpret_cast<const uint4*>(sp + (cb * PHPW + pos) * 16);
+              const int r0 = fastdiv(pos, p.m_PW), c0 = pos - r0 * PW;
+              const uint32_t in0 = ((unsigned)(it.by + r0) < (unsigned)H_in && (unsigned)(it.bx + c0) < (unsigned)W_in) ? 0xffffffffu : 0u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                q[j].x = bf16x2_sqrt_eps(v[j].x) & in0; q[j].y = bf16x2_sqrt_eps(v[j].y) & in0;
+                q[j].z = bf16x2_sqrt_eps(v[j].z) & in0; q[j].w = bf16x2_sqrt_eps(v[j].w) & in0;
+                v[j].x = bf16x2_mul(v[j].x, v[j].x); v[j].y = bf16x2_mul(v[j].y, v[j].y);
+                v[j].z = bf16x2_mul(v[j].z, v[j].z); v[j].w = bf16x2_mul(v[j].w, v[j].w);
+              }
+#pragma unroll
+              for (int cb = 0; cb < 4; ++cb) {
+                *reinterpret_cast<uint4*>(dp + (cb * PHPW + pos) * 16) = v[cb];
+                *reinterpret_cast<uint4*>(dq + (cb * PHPW + pos) * 16) = q[cb];
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> the MMA's async-proxy reads
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&full[stage]); mbar_arrive(&empty[stage]);   // the derived stages are never read by these warps
+              mbar_arrive(&full[nst]); mbar_arrive(&empty[nst]);
+              mbar_arrive(&empty[src]);                                 // done reading the skip chunk
+            }
+          } else {
+            if (dbg) w_e += clock64() - tw0;
+            if (lane == 0) {
+              mbar_arrive(&full[stage]);
+              if (p.prog_back[ch] == 0) mbar_arrive(&empty[stage]);   // a TMA chunk nothing is derived from (prog_back = 1 marks a source)
+            }
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (dbg) {   // [9] skip-operator warp cycles, [10] its wait for a free stage, [11] its wait for the skip chunk
+        atomicAdd(dbg + 9, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(dbg + 10, (unsigned long long)w_e);
+        atomicAdd(dbg + 11, (unsigned long long)w_s);
+      }
+    }
   } else {
     // =============================== epilogue ===============================
     // A tile has two work units (M block b, 32-channel chunk c): 2 x 32 channels (NT = 32) or 1 x 64 channels (NT = 64).
@@ -439,7 +563,9 @@ static const char* probe_env(const char* name) { return getenv(name); }
 static const char* probe_env(const char*) { return nullptr; }   // the product library reads no environment variable
 #endif
 // tile geometry and pipeline sizing: pure host arithmetic (no CUDA calls), shared with uncl_plan_conv3x3_tc_merged
-int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int fuse_outc, const char* what, int* smem_bytes_out) {
+// derive: C_in is the LOGICAL channel count 4*Cs of [skip | up | skip^2 | sqrt(skip)]; the tensor holds the first 2*Cs
+int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int fuse_outc, int derive, const char* what,
+            int* smem_bytes_out) {
   p.NT = C_out < 64 ? C_out : 64;
   UNCL_REQUIRE(p.NT % 32 == 0 && C_out % p.NT == 0, "%s: unsupported C_out=%d", what, C_out);
   UNCL_REQUIRE(!fuse_outc || C_out == 32, "%s: the fused out conv needs C_out == 32", what);
@@ -453,7 +579,16 @@ int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
   p.MB = p.acc_cols / p.NP;   // 2 blocks of 96 columns or 1 block of 192: always two 32-channel work units per tile
   int bw_max = 126;
   if (const char* e = probe_env("UNCL_MG_BW")) { const int want = atoi(e); if (want >= 8 && want < bw_max) bw_max = want; }
-  const int nbands = ceil_div(p.Wo, bw_max);
+  const int tail = 128 + 2 * kUnits * 4 * kXSlot * 4 + 2 * kUnits * 128 * 4 + (2 * kMaxStages + 5) * 8 + 16 + 2 * C_out * 4 + 256;
+  const int budget = 227 * 1024 - tail;
+  const int nbands0 = ceil_div(p.Wo, bw_max);
+  // Fused skip operators hold three ring slots per skip chunk (x, x^2, sqrt): with a ring of exactly one tile (4 slots)
+  // the next tile's skip chunk could only load after this tile's derived chunks were built - a serial TMA + transform
+  // chain per tile.  Narrower column bands shrink the halo box until FIVE stages fit, which rotates the slots from tile
+  // to tile and lets the next skip chunk land early.
+  const int want_stages = derive ? 5 : 0;
+  int nbands = nbands0;
+  for (;; ++nbands) {
   p.BW = ceil_div(p.Wo, nbands);
   p.PW = p.BW + 2;
   p.band_total = p.Ho * p.PW;
@@ -464,8 +599,8 @@ int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
   // for two), no overlap needed because a row ends with its two wrap-around columns.  Measured (1080p frame): 256 -> 32
   // at 124^2 141 -> 130 us; narrower pitches (61, 63) lose more to the unused tile tail than the smaller box saves.
   const int rows_al = (128 * p.MB) / p.PW;
-  const bool aligned = rows_al >= 1 && rows_al <= 2 && p.PW >= 100 && rows_al * p.PW * 100 >= 97 * (128 * p.MB - 2) &&
-                       probe_env("UNCL_MG_FLAT") == nullptr;
+  const bool aligned = rows_al >= 1 && (derive || (rows_al <= 2 && p.PW >= 100)) &&
+                       rows_al * p.PW * 100 >= 97 * (128 * p.MB - 2) && probe_env("UNCL_MG_FLAT") == nullptr;
   p.aligned = aligned ? 1 : 0;
   if (aligned) {
     p.ADV = rows_al * p.PW;
@@ -485,8 +620,6 @@ int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
   p.m_tpb = (1ull << 40) / (unsigned)p.tiles_per_band + 1; p.m_PW = (1ull << 40) / (unsigned)p.PW + 1;
   p.mma_warps = p.MB == 2 ? 2 : 1;
   if (const char* e = probe_env("UNCL_MMA_WARPS")) { if (atoi(e) == 1) p.mma_warps = 1; }
-  const int tail = 128 + 2 * kUnits * 4 * kXSlot * 4 + 2 * kUnits * 128 * 4 + (2 * kMaxStages + 5) * 8 + 16 + 2 * C_out * 4 + 256;
-  const int budget = 227 * 1024 - tail;
   // Pipeline stage = the halo box of `ksteps` K = 16 steps (+ their weights).  When the whole filter bank fits next to
   // at least three A stages it is loaded ONCE per CTA and stays resident (the weight stage is otherwise re-fetched from
   // L2 for every tile: 35 % of the L2 -> shared-memory traffic of the 128 -> 32 layer); N' = 96 issues 32 channels per
@@ -494,7 +627,7 @@ int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
   p.w_total = (C_in / 16) * 3 * 2 * p.NP * 16;
   auto a_bytes = [&](int ks) { return (2 * ks * p.PH * p.PW * 16 + 127) & ~127; };
   int ks = (p.NT == 32 && C_in % 32 == 0) ? 2 : 1;
-  p.w_res = (p.NS == 1 && p.w_total + 3 * a_bytes(ks) <= budget && probe_env("UNCL_MG_NO_WRES") == nullptr) ? 1 : 0;
+  p.w_res = (p.NS == 1 && p.w_total + (derive ? 4 : 3) * a_bytes(ks) <= budget && probe_env("UNCL_MG_NO_WRES") == nullptr) ? 1 : 0;
   UNCL_REQUIRE(p.NT == 64 || ks == 2, "%s: C_in must be a multiple of 32 for C_out = 32", what);
   p.ksteps = ks;
   p.nchunk = C_in / (16 * ks);
@@ -504,19 +637,39 @@ int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
   p.stage_bytes = p.a_stage_bytes + (p.w_res ? 0 : p.b_stage_bytes);
   p.stages = (budget - (p.w_res ? p.w_total : 0)) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
+  if (p.stages >= want_stages || nbands >= nbands0 + 8 || p.BW <= 16) break;
+  }
   if (const char* e = probe_env("UNCL_MG_STAGES")) { const int want = atoi(e); if (want >= 2 && want < p.stages) p.stages = want; }
   UNCL_REQUIRE(p.stages >= 2, "%s: tile does not fit shared memory (%d B per stage)", what, p.stage_bytes);
   int smem_bytes = p.stages * p.stage_bytes + (p.w_res ? p.w_total : 0) + tail;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM (each owns all 512 TMEM columns)
+  p.derive = derive ? 1 : 0;
+  p.H_in = H; p.W_in = W;
+  if (derive) {
+    // ring program of a tile: per 32-channel skip chunk j  [skip_j (TMA), skip_j^2, sqrt(skip_j)], then the up-sampled chunks
+    const int cs32 = C_in / 4 / 32;   // 32-channel chunks of the skip tensor
+    UNCL_REQUIRE(p.NT == 32 && p.ksteps == 2 && C_in % 128 == 0 && p.nchunk == 4 * cs32 && p.nchunk <= kMaxProg,
+                 "%s: fused skip operators need C_out == 32 and C_skip a multiple of 32 (<= 128)", what);
+    UNCL_REQUIRE(p.stages >= 4, "%s: fused skip operators need four pipeline stages (%d fit)", what, p.stages);
+    int k = 0;
+    for (int j = 0; j < cs32; ++j) {
+      p.prog_kind[k] = 0; p.prog_cb[k] = (unsigned char)(4 * j); p.prog_wch[k] = (unsigned char)j; p.prog_back[k] = 1; ++k;
+      p.prog_kind[k] = 1; p.prog_cb[k] = 0; p.prog_wch[k] = (unsigned char)(2 * cs32 + j); p.prog_back[k] = 1; ++k;
+      p.prog_kind[k] = 2; p.prog_cb[k] = 0; p.prog_wch[k] = (unsigned char)(3 * cs32 + j); p.prog_back[k] = 2; ++k;
+    }
+    for (int j = 0; j < cs32; ++j) {
+      p.prog_kind[k] = 0; p.prog_cb[k] = (unsigned char)(4 * (cs32 + j)); p.prog_wch[k] = (unsigned char)(cs32 + j); p.prog_back[k] = 0; ++k;
+    }
+  }
   *smem_bytes_out = smem_bytes;
   return UNCL_OK;
 }
 }  // namespace
 
-int uncl_plan_conv3x3_tc_merged(int N, int C_in, int H, int W, int C_out, int pad, int* plan) {
+static int plan_merged_impl(int N, int C_in, int H, int W, int C_out, int pad, int derive, int* plan) {
   MgParams p{};
   int smem = 0;
-  if (int rc = mg_plan(p, N, C_in, H, W, C_out, pad, 0, "conv3x3_tc_plan(merged)", &smem)) return rc;
+  if (int rc = mg_plan(p, N, C_in, H, W, C_out, pad, 0, derive, "conv3x3_tc_plan(merged)", &smem)) return rc;
   const int v[16] = {1 | (p.aligned << 1) | (p.w_res << 2), p.NT, p.NS, p.NP, p.MB, p.ADV, p.PW, p.PH, p.BW, p.tiles_per_img / p.tiles_per_band, p.tiles_per_band,
                      p.num_items, p.stages, p.nacc, p.ksteps, smem};
   for (int i = 0; i < 16; ++i) plan[i] = v[i];
@@ -524,16 +677,28 @@ int uncl_plan_conv3x3_tc_merged(int N, int C_in, int H, int W, int C_out, int pa
 }
 
 // Called by uncl_conv3x3_tc (conv_tc.cu) for the layers use_merged() selects; arguments already validated there.
+int uncl_plan_conv3x3_tc_merged(int N, int C_in, int H, int W, int C_out, int pad, int* plan) {
+  return plan_merged_impl(N, C_in, H, W, C_out, pad, 0, plan);
+}
+
+// Tile plan of uncl_conv3x3_tc_skipcat (same 16 fields as uncl_conv3x3_tc_plan): pure host arithmetic.
+extern "C" int uncl_conv3x3_tc_skipcat_plan(int N, int C_skip, int H, int W, int C_out, int pad, int* plan) {
+  UNCL_REQUIRE(plan != nullptr && N > 0 && C_skip > 0 && C_skip % 32 == 0 && C_out == 32 && (pad == 0 || pad == 2) &&
+                   H + 2 * pad - 2 > 0 && W + 2 * pad - 2 > 0,
+               "conv3x3_tc_skipcat_plan: unsupported C_skip=%d C_out=%d pad=%d H=%d W=%d", C_skip, C_out, pad, H, W);
+  return plan_merged_impl(N, 4 * C_skip, H, W, C_out, pad, 1, plan);
+}
+
 int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
                                   long out_img_stride, int out_f32, int N, int C_in, int H, int W, int C_out, int pad,
                                   int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
                                   float* out_img, float* out_logit, const void* mask, long mask_img_stride,
-                                  unsigned long long* dbg, cudaStream_t stream) {
-  const char* what = "conv3x3_tc(merged)";
+                                  unsigned long long* dbg, int derive, cudaStream_t stream) {
+  const char* what = derive ? "conv3x3_tc_skipcat" : "conv3x3_tc(merged)";
   UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "%s: input must be 16-byte aligned", what);
   MgParams p{};
   int smem_bytes = 0;
-  if (int rc = mg_plan(p, N, C_in, H, W, C_out, pad, fuse_outc, what, &smem_bytes)) return rc;
+  if (int rc = mg_plan(p, N, C_in, H, W, C_out, pad, fuse_outc, derive, what, &smem_bytes)) return rc;
   p.w = reinterpret_cast<const bf16*>(w_packed);
   p.bias = bias; p.out = out; p.out_f32 = out_f32; p.out_img_stride = out_img_stride;
   p.outc_w = outc_w; p.outc_b = outc_b; p.out_img = out_img; p.out_logit = out_logit;
@@ -541,16 +706,19 @@ int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void
   p.mask = reinterpret_cast<const bf16*>(mask); p.mask_img_stride = mask_img_stride;
 
   CUtensorMap tmap;
-  CUresult r = encode_blocked_bf16(&tmap, in, W, H, C_in / 8, N, in_img_stride, p.PW, p.PH, 2 * p.ksteps);
+  CUresult r = encode_blocked_bf16(&tmap, in, W, H, (derive ? C_in / 2 : C_in) / 8, N, in_img_stride, p.PW, p.PH, 2 * p.ksteps);
   if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
   p.dbg = dbg;
   p.probe_noload = probe_env("UNCL_PROBE_NOLOAD") != nullptr ? 1 : 0;   // bit 0: no loads, 1: no epilogue work, 2: MMA free-runs
   if (const char* e = probe_env("UNCL_PROBE_FLAGS")) p.probe_noload = atoi(e);
   static thread_local int smem_ok = 0, smem_dev = -1;
-  cudaError_t e = ensure_smem(conv3x3_tc_merged_kernel, smem_bytes, smem_ok, smem_dev);
+  static thread_local int smem_ok_d = 0, smem_dev_d = -1;
+  cudaError_t e = derive ? ensure_smem(conv3x3_tc_merged_kernel<true>, smem_bytes, smem_ok_d, smem_dev_d)
+                         : ensure_smem(conv3x3_tc_merged_kernel<false>, smem_bytes, smem_ok, smem_dev);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));
   const int sms = sm_count();
   const int grid = p.num_items < sms ? p.num_items : sms;
-  conv3x3_tc_merged_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap, p);
+  if (derive) conv3x3_tc_merged_kernel<true><<<grid, kThreadsDerive, smem_bytes, stream>>>(tmap, p);
+  else conv3x3_tc_merged_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tmap, p);
   return uncl_check_launch(what);
 }

@@ -64,6 +64,11 @@ class _GeneratorBase(nn.Module):
         if precision not in ("fp32", "bf16", "fp32_tc"):
             raise ValueError("precision must be 'fp32', 'bf16' or 'fp32_tc'")
         self.precision = precision
+        # bf16 inference option: skip^2 / sqrt(skip + eps) of the two largest levels built inside the consuming conv instead of
+        # being written by the producer (uncl_conv3x3_tc_skipcat).  Halves those layers' DRAM traffic; measured net-neutral in
+        # time on B200 (the N' = 96 MMAs already saturate shared-memory bandwidth, which the in-kernel transform also needs:
+        # DESIGN.md section 9), so it is off by default.
+        self.fused_skip = False
         self.to_crop = to_crop
         self.depth = depth
         self.recurrent_ch_ratio = recurrent_ch_ratio
@@ -208,12 +213,15 @@ class _GeneratorBase(nn.Module):
             return t.stride(0)
 
         f = 32
-        # encoder.  cat[i] is the concat buffer of up stage 3-i: [skip | upsampled | skip^2 | sqrt(skip)]
+        # encoder.  cat[i] is the concat buffer of up stage 3-i: [skip | upsampled | skip^2 | sqrt(skip)].  On the bf16
+        # inference path the two largest levels (252^2, 124^2: 70 % of the concat bytes) keep only [skip | upsampled]: the
+        # consuming conv builds skip^2 / sqrt(skip + eps) in shared memory (uncl_conv3x3_tc_skipcat, unet_parts.py:311-332)
         sizes = [(f, 252), (2 * f, 122), (4 * f, 57), (8 * f, 24)]
-        cat = [buf(4 * c, s, s) for c, s in sizes]
+        nfused = 2 if (self.precision == "bf16" and keep is None and self.fused_skip) else 0
+        cat = [buf((2 if i < nfused else 4) * c, s, s) for i, (c, s) in enumerate(sizes)]
         a0 = buf(f, 254, 254)
         call("uncl_conv_first", x, P["inc0"][0], P["inc0"][1], a0, st(a0), n, 256, 256, f, ACT_RELU, dt)
-        self._conv3(P, "inc1", a0, st(a0), cat[0], st(cat[0]), n, f, 254, 254, f, 0, emit_skip=1)
+        self._conv3(P, "inc1", a0, st(a0), cat[0], st(cat[0]), n, f, 254, 254, f, 0, emit_skip=0 if nfused > 0 else 1)
         state = [cat[0]]  # tensors whose first C/32 channels feed the next frame (Unet.py:229,251,264,272)
         cur, cur_c, cur_s = cat[0], f, 252
         for i in range(4):
@@ -227,7 +235,8 @@ class _GeneratorBase(nn.Module):
             self._conv3(P, "d%d_0" % i, pooled, st(pooled), mid, st(mid), n, cur_c, ps, ps, co, 0)
             if i < 3:
                 dst = cat[i + 1]
-                self._conv3(P, "d%d_1" % i, mid, st(mid), dst, st(dst), n, co, ps - 2, ps - 2, co, 0, emit_skip=1)
+                self._conv3(P, "d%d_1" % i, mid, st(mid), dst, st(dst), n, co, ps - 2, ps - 2, co, 0,
+                            emit_skip=0 if i + 1 < nfused else 1)
                 cur, cur_c, cur_s = dst, co, ps - 4
             else:
                 x4 = buf(co, ps, ps)
@@ -314,7 +323,11 @@ class _GeneratorBase(nn.Module):
                      up_s, up_s, sk_s, sk_s, dt)
             co = f if i >= 2 else up_c // 2
             mid = buf(co, sk_s + 2, sk_s + 2)
-            self._conv3(P, "u%d_0" % i, cb, st(cb), mid, st(mid), n, 4 * sk_c, sk_s, sk_s, co, 2)
+            if 3 - i < nfused:
+                call("uncl_conv3x3_tc_skipcat", cb, st(cb), P["u%d_0" % i][0], P["u%d_0" % i][1], mid, st(mid), _lib.BF16, n,
+                     sk_c, sk_s, sk_s, co, 2, ACT_RELU)
+            else:
+                self._conv3(P, "u%d_0" % i, cb, st(cb), mid, st(mid), n, 4 * sk_c, sk_s, sk_s, co, 2)
             last = i == 3
             if last and self.precision == "bf16" and not want_features:
                 self._conv3(P, "u3_1", mid, st(mid), None, 0, n, co, sk_s + 2, sk_s + 2, co, 2,
