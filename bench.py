@@ -469,7 +469,13 @@ def main():
         # memory-bound kernels of the frame path: ALGORITHMIC bytes per call (SURVEY.md 8d / DESIGN.md section 3) over the
         # device time of the call, against the measured copy bandwidth
         h1, w1 = 16 * (H // 16) + 16, 16 * (W // 16) + 16
-        algo = {"uncl_frame_normalise_pad": 28 * H * W, "uncl_tiles_gather": TILES * 65536 * 8,
+        # fused stage calls (one cooperative launch each): normalise_tiles reads rgb twice (statistics, then values) and writes
+        # the tiles; blend_percentiles reads the tiles, writes the plane (its keys stay in shared memory); post_u8 reads
+        # plane + rgb and writes the 8-bit image (keys in shared memory)
+        algo = {"uncl_frame_normalise_tiles": 24 * H * W + TILES * 65536 * 4,
+                "uncl_frame_blend_percentiles": TILES * 65536 * 4 + h1 * w1 * 4,
+                "uncl_frame_post_u8": h1 * w1 * 4 + 12 * H * W + 3 * H * W,
+                "uncl_frame_normalise_pad": 28 * H * W, "uncl_tiles_gather": TILES * 65536 * 8,
                 "uncl_tiles_blend": TILES * 65536 * 4 + h1 * w1 * 4, "uncl_frame_postprocess": h1 * w1 * 4 + 24 * H * W,
                 "uncl_frame_to_u8": 15 * H * W, "uncl_percentile_pair": 4 * (h1 * w1 + 3 * H * W) // 2,
                 "uncl_conv_first": TILES * (256 * 256 * 4 + 254 * 254 * 32 * 2),

@@ -209,6 +209,29 @@ int uncl_percentile_pair(const float* data, long n, float clamp_lo, float clamp_
 int uncl_frame_postprocess(const float* fake, int H1, int W1, const float* rgb, int H, int W, const float* stats,
                            const float* pct, float* out, uncl_stream_t stream);
 
+/* ---- the same frame stages fused into ONE cooperative launch each (bit-identical values; a 1080p frame is a handful of
+ * 4-9 us memory passes, so the staged path above is bound by its 14 launches, not by HBM) ---- */
+
+/* 1 if the three fused calls below can run for this geometry on the current device, else 0 (use the staged calls). */
+int uncl_frame_fused_supported(int H, int W, int H1, int W1, int K);
+
+/* uncl_frame_normalise_pad + uncl_tiles_gather: statistics, (shifted statistics), normalisation written directly as the
+ * T 256x256 tiles at origins[t] = (y, x) of the padded frame - which is never stored.  model_save_util.py:232-239, 417-470. */
+int uncl_frame_normalise_tiles(const float* rgb, int H, int W, float f_factor, int H1, int W1, const int* origins, int T,
+                               float* tiles, float* stats_out, void* workspace, uncl_stream_t stream);
+
+/* uncl_tiles_blend + uncl_percentile_pair of the blended plane (K <= 3): plane_out [H1][W1], pct_out[2].
+ * model_save_util.py:428-481, 389-390. */
+int uncl_frame_blend_percentiles(const float* tiles, const int* yidx, const float* yw, const int* ystart, const int* xidx,
+                                 const float* xw, const int* xstart, int TX, int K, float* plane_out, int H1, int W1,
+                                 double p_lo, double p_hi, float* pct_out, void* workspace, uncl_stream_t stream);
+
+/* uncl_frame_postprocess + uncl_percentile_pair(clip(col,0,1)) + uncl_frame_to_u8: col_out [3][H][W] (may be NULL),
+ * pct_out[2] = the colour percentiles, u8_out HWC.  model_save_util.py:393-402, hdr_image_util.py:93-102, 122-132, 237-245. */
+int uncl_frame_post_u8(const float* fake, int H1, int W1, const float* rgb, int H, int W, const float* stats,
+                       const float* pct_plane, float* col_out, double p_lo, double p_hi, float* pct_out,
+                       unsigned char* u8_out, void* workspace, uncl_stream_t stream);
+
 /* clamp(0,1), stretch between pct[0..1], clip, *255 -> uint8 HWC.  hdr_image_util.py:237-245, 93-102. */
 int uncl_frame_to_u8(const float* col, int H, int W, const float* pct, unsigned char* out, uncl_stream_t stream);
 

@@ -226,3 +226,35 @@ def test_bf16_full_frame_matches_oracle(h, w):
     assert rel_fake <= 1e-2
     assert rel_col <= 2e-2
     assert d.max() <= 10 and (d <= 2).mean() >= 0.97 and (d <= 1).mean() >= 0.85
+
+
+@pytest.mark.parametrize("h,w,negative", [(272, 304, False), (769, 1025, False), (1080, 1920, False), (500, 700, True)])
+def test_fused_frame_stages_equal_the_staged_ones(h, w, negative):
+    """The three cooperative kernels (normalise -> tiles, blend -> percentiles, post-process -> percentiles -> 8-bit image)
+    against the staged calls they replace: the same arithmetic on the same values, so everything is bit-identical -
+    tiles, statistics, blended plane, both percentile pairs, the fp32 colour frame and the 8-bit image.  Covers the
+    negative-input (shifted statistics) branch and three padded geometries."""
+    rgb = torch.from_numpy(synth.hdr_frame(h, w, seed=h + w)).cuda()
+    if negative:
+        rgb = rgb - 0.37 * rgb.mean()
+    pipe = FramePipeline(CheapG())
+    pl = pipe.plan(h, w, rgb.device)
+    assert pipe.fused_ok(pl)
+    gray_p, stats_s = pipe.normalise_pad(rgb, 37.0)
+    tiles_s = pipe.gather_tiles(gray_p, pl)
+    tiles_f, stats_f = pipe.normalise_tiles(rgb, 37.0, pl)
+    assert torch.equal(tiles_s, tiles_f) and torch.equal(stats_s[:3], stats_f[:3])
+    out_tiles = pipe.run_generator(tiles_f)
+    fake_s = pipe.blend(out_tiles, pl)
+    pct_s = pipe.percentiles(fake_s, 0.5, 99.5)
+    fake_f, pct_f = pipe.blend_percentiles(out_tiles, pl)
+    assert torch.equal(fake_s, fake_f) and torch.equal(pct_s, pct_f)
+    col_s = pipe.postprocess(fake_s, rgb, stats_s, pl)
+    u8_s = pipe.to_uint8(col_s)
+    u8_f, col_f = pipe.post_uint8(fake_f, pct_f, rgb, stats_f, pl, want_col=True)
+    assert torch.equal(col_s, col_f) and torch.equal(u8_s, u8_f)
+    # whole path, both switches
+    full_f = pipe.tonemap(rgb, 37.0, uint8=True)
+    pipe.fused = False
+    full_s = pipe.tonemap(rgb, 37.0, uint8=True)
+    assert torch.equal(full_f, full_s)

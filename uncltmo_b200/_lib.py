@@ -73,7 +73,7 @@ def ptr(t):
 
 
 # kernels launched by one C-ABI call (1 unless listed); used for the launch count bench.py reports
-KERNELS_PER_CALL = {"uncl_frame_normalise_pad": 5, "uncl_percentile_pair": 3, "uncl_plane_mean_contrast": 2,
+KERNELS_PER_CALL = {"uncl_frame_fused_supported": 0, "uncl_frame_normalise_pad": 5, "uncl_percentile_pair": 3, "uncl_plane_mean_contrast": 2,
                     "uncl_disc_forward": 3, "uncl_nce_fwd": 2, "uncl_tv_loss": 2}
 _launches = 0
 _timing = None

@@ -375,27 +375,103 @@ __device__ __forceinline__ void select_scan_block(unsigned* s_pre, unsigned* s_r
   }
 }
 
+// ---- pieces of the fused select, shared by the plain kernel and by the frame-stage kernels that produce their values on
+// the fly (blend -> select, post-process -> select -> 8-bit image) ----------------------------------------------------
+struct SelSmem {
+  unsigned* hist;    // [4][2048]
+  unsigned* keys;    // this CTA's order keys
+  unsigned* pre;     // [4]
+  unsigned* rank;    // [4]
+  unsigned* wtot;    // [4 * 8]
+};
+
+// pass 0 visit of one (already clamped) value: remember its order key, count its top 11 bits.  Warp-aggregated atomics;
+// may be called from a partially active warp.
+__device__ __forceinline__ void sel_visit0(const SelSmem& sm, float clamped, int idx) {
+  const unsigned k = order_key(clamped);
+  sm.keys[idx] = k;
+  const unsigned bin = k >> 21;
+  const unsigned peers = __match_any_sync(__activemask(), bin);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sm.hist[bin], (unsigned)__popc(peers));
+}
+
+__device__ __forceinline__ void sel_clear_hist(const SelSmem& sm) {
+  for (int i = threadIdx.x; i < (kSelQ << 11); i += blockDim.x) sm.hist[i] = 0;
+  __syncthreads();
+}
+
+// after every thread's sel_visit0 calls: merge pass 0, then passes 1 and 2 from the shared-memory keys.  `bar_base` is the
+// value of the grid-barrier counter when the kernel's select started (a kernel may run other grid barriers before).
+// On return sm.pre[0..3] hold the keys of the four order statistics - in EVERY CTA.
+__device__ __forceinline__ void sel_finish(const SelSmem& sm, int cnt, unsigned* __restrict__ hist3, unsigned* barrier,
+                                           unsigned bar_base, const SelRanks& ranks) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+    if (sm.hist[i]) atomicAdd(&hist3[i], sm.hist[i]);
+  select_grid_barrier(barrier, bar_base + gridDim.x);
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) sm.hist[i] = __ldcg(hist3 + i);
+  __syncthreads();
+  select_scan_block<0>(sm.pre, sm.rank, sm.hist, ranks, sm.wtot);
+  __syncthreads();
+#pragma unroll
+  for (int pass = 1; pass <= 2; ++pass) {
+    const int BITS = pass == 2 ? 10 : 11, SHIFT = pass == 1 ? 10 : 0;
+    unsigned pre[kSelQ];
+    bool first[kSelQ];
+#pragma unroll
+    for (int q = 0; q < kSelQ; ++q) {
+      pre[q] = sm.pre[q];
+      first[q] = true;
+#pragma unroll
+      for (int q2 = 0; q2 < q; ++q2) first[q] = first[q] && (sm.pre[q2] != pre[q]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (kSelQ << 11); i += blockDim.x) sm.hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const unsigned k = sm.keys[i];
+      const unsigned hi = k >> (SHIFT + BITS), bin = (k >> SHIFT) & ((1u << BITS) - 1);
+#pragma unroll
+      for (int q = 0; q < kSelQ; ++q)
+        if (first[q] && hi == pre[q]) atomicAdd(&sm.hist[(q << BITS) + bin], 1u);
+    }
+    __syncthreads();
+    unsigned* gh = hist3 + pass * (kSelQ << 11);
+    for (int i = threadIdx.x; i < (kSelQ << BITS); i += blockDim.x)
+      if (sm.hist[i]) atomicAdd(&gh[i], sm.hist[i]);
+    select_grid_barrier(barrier, bar_base + gridDim.x * (unsigned)(pass + 1));
+    for (int i = threadIdx.x; i < (kSelQ << BITS); i += blockDim.x) sm.hist[i] = __ldcg(gh + i);
+    __syncthreads();
+    if (pass == 1) select_scan_block<1>(sm.pre, sm.rank, sm.hist, ranks, sm.wtot);
+    else select_scan_block<2>(sm.pre, sm.rank, sm.hist, ranks, sm.wtot);
+    __syncthreads();
+  }
+}
+
+// numpy 'linear' interpolation between the two neighbouring order statistics of each percentile
+__device__ __forceinline__ void sel_result(const SelSmem& sm, double t0, double t1, float& lo, float& hi) {
+  const double a0 = key_value(sm.pre[0]), b0 = key_value(sm.pre[1]);
+  const double a1 = key_value(sm.pre[2]), b1 = key_value(sm.pre[3]);
+  lo = (float)(t0 < 0.5 ? a0 + (b0 - a0) * t0 : b0 - (b0 - a0) * (1.0 - t0));
+  hi = (float)(t1 < 0.5 ? a1 + (b1 - a1) * t1 : b1 - (b1 - a1) * (1.0 - t1));
+}
+
+#define UNCL_SEL_SMEM(sm)                                                          \
+  extern __shared__ __align__(16) unsigned s_dyn[];                                \
+  __shared__ unsigned s_pre_[kSelQ], s_rank_[kSelQ], s_wtot_[kSelQ * 8];           \
+  const SelSmem sm = {s_dyn, s_dyn + (kSelQ << 11), s_pre_, s_rank_, s_wtot_}
+
 __global__ void __launch_bounds__(kFusedThreads, 1)
 select_fused_kernel(const float* __restrict__ data, long n, long per_cta, float clamp_lo, float clamp_hi,
                     unsigned* __restrict__ hist3, unsigned* barrier, const SelRanks ranks, double t0, double t1,
                     float* out) {
-  extern __shared__ __align__(16) unsigned s_dyn[];
-  unsigned* s_hist = s_dyn;                       // [4][2048]
-  unsigned* s_keys = s_dyn + (kSelQ << 11);       // [per_cta]
-  __shared__ unsigned s_pre[kSelQ], s_rank[kSelQ], s_wtot[kSelQ * 8];
+  UNCL_SEL_SMEM(sm);
   const long begin = (long)blockIdx.x * per_cta;
   const int cnt = (int)max(0L, min(per_cta, n - begin));
-  for (int i = threadIdx.x; i < (kSelQ << 11); i += blockDim.x) s_hist[i] = 0;
-  __syncthreads();
+  sel_clear_hist(sm);
   // ---- load + pass 0 (top 11 bits)
   {
-    auto visit0 = [&](float raw, int idx) {
-      const unsigned k = order_key(fminf(fmaxf(raw, clamp_lo), clamp_hi));
-      s_keys[idx] = k;
-      const unsigned bin = k >> 21;
-      const unsigned peers = __match_any_sync(__activemask(), bin);
-      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (unsigned)__popc(peers));
-    };
+    auto visit0 = [&](float raw, int idx) { sel_visit0(sm, fminf(fmaxf(raw, clamp_lo), clamp_hi), idx); };
     const float* d = data + begin;   // begin is a multiple of 4 and data is 16-byte aligned (checked by the host)
     const int c4 = cnt >> 2;
     const float4* d4 = reinterpret_cast<const float4*>(d);
@@ -412,53 +488,226 @@ select_fused_kernel(const float* __restrict__ data, long n, long per_cta, float 
     }
     for (int t = (c4 << 2) + threadIdx.x; t < cnt; t += kFusedThreads) visit0(__ldg(d + t), t);
   }
+  sel_finish(sm, cnt, hist3, barrier, 0u, ranks);
+  if (blockIdx.x == 0 && threadIdx.x == 0) sel_result(sm, t0, t1, out[0], out[1]);
+}
+
+// ---- frame stage 1 in ONE cooperative launch: statistics -> (shifted statistics) -> log-lambda normalisation written
+// straight into the generator's 256 x 256 tiles (the replicate-padded frame is never materialised).  Same arithmetic as
+// frame_stats_kernel / frame_normalise_pad_kernel / tiles_gather_kernel: the tiles are bit-identical to the staged path.
+__device__ __forceinline__ void cta_minmax3(float& mn, float& ymn, float& ymx, float (*red)[32]) {
+  mn = warp_min(mn); ymn = warp_min(ymn); ymx = warp_max(ymx);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   __syncthreads();
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
-    if (s_hist[i]) atomicAdd(&hist3[i], s_hist[i]);
-  select_grid_barrier(barrier, gridDim.x);
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = __ldcg(hist3 + i);
+  if (lane == 0) { red[0][wid] = mn; red[1][wid] = ymn; red[2][wid] = ymx; }
   __syncthreads();
-  select_scan_block<0>(s_pre, s_rank, s_hist, ranks, s_wtot);
-  __syncthreads();
-  // ---- passes 1 (next 11 bits) and 2 (last 10 bits) from the shared-memory keys
+  mn = red[0][0]; ymn = red[1][0]; ymx = red[2][0];
+  for (int w = 1; w < nw; ++w) { mn = fminf(mn, red[0][w]); ymn = fminf(ymn, red[1][w]); ymx = fmaxf(ymx, red[2][w]); }
+}
+
+__device__ __forceinline__ void frame_stats_slice(const float* __restrict__ rgb, long HW, float shift, float& mn, float& ymn,
+                                                  float& ymx) {
+  mn = INFINITY; ymn = INFINITY; ymx = -INFINITY;
+  const long n4 = HW / 4;
+  if (HW % 4 == 0) {
+    const float4* r4 = reinterpret_cast<const float4*>(rgb);
+    const float4* g4 = reinterpret_cast<const float4*>(rgb + HW);
+    const float4* b4 = reinterpret_cast<const float4*>(rgb + 2 * HW);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+      const float4 r = __ldg(r4 + i), g = __ldg(g4 + i), b = __ldg(b4 + i);
+      const float rr[4] = {r.x, r.y, r.z, r.w}, gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-  for (int pass = 1; pass <= 2; ++pass) {
-    const int BITS = pass == 2 ? 10 : 11, SHIFT = pass == 1 ? 10 : 0;
-    unsigned pre[kSelQ];
-    bool first[kSelQ];
-#pragma unroll
-    for (int q = 0; q < kSelQ; ++q) {
-      pre[q] = s_pre[q];
-      first[q] = true;
-#pragma unroll
-      for (int q2 = 0; q2 < q; ++q2) first[q] = first[q] && (s_pre[q2] != pre[q]);
+      for (int k = 0; k < 4; ++k) {
+        mn = fminf(mn, fminf(rr[k], fminf(gg[k], bb[k])));
+        const float y = gray_of(rr[k] - shift, gg[k] - shift, bb[k] - shift);
+        ymn = fminf(ymn, y);
+        ymx = fmaxf(ymx, y);
+      }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < (kSelQ << 11); i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const unsigned k = s_keys[i];
-      const unsigned hi = k >> (SHIFT + BITS), bin = (k >> SHIFT) & ((1u << BITS) - 1);
-#pragma unroll
-      for (int q = 0; q < kSelQ; ++q)
-        if (first[q] && hi == pre[q]) atomicAdd(&s_hist[(q << BITS) + bin], 1u);
+  } else {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long)gridDim.x * blockDim.x) {
+      const float r = rgb[i], g = rgb[HW + i], b = rgb[2 * HW + i];
+      mn = fminf(mn, fminf(r, fminf(g, b)));
+      const float y = gray_of(r - shift, g - shift, b - shift);
+      ymn = fminf(ymn, y);
+      ymx = fmaxf(ymx, y);
     }
-    __syncthreads();
-    unsigned* gh = hist3 + pass * (kSelQ << 11);
-    for (int i = threadIdx.x; i < (kSelQ << BITS); i += blockDim.x)
-      if (s_hist[i]) atomicAdd(&gh[i], s_hist[i]);
-    select_grid_barrier(barrier, gridDim.x * (unsigned)(pass + 1));
-    for (int i = threadIdx.x; i < (kSelQ << BITS); i += blockDim.x) s_hist[i] = __ldcg(gh + i);
-    __syncthreads();
-    if (pass == 1) select_scan_block<1>(s_pre, s_rank, s_hist, ranks, s_wtot);
-    else select_scan_block<2>(s_pre, s_rank, s_hist, ranks, s_wtot);
-    __syncthreads();
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const double a0 = key_value(s_pre[0]), b0 = key_value(s_pre[1]);
-    const double a1 = key_value(s_pre[2]), b1 = key_value(s_pre[3]);
-    out[0] = (float)(t0 < 0.5 ? a0 + (b0 - a0) * t0 : b0 - (b0 - a0) * (1.0 - t0));
-    out[1] = (float)(t1 < 0.5 ? a1 + (b1 - a1) * t1 : b1 - (b1 - a1) * (1.0 - t1));
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+frame_normalise_tiles_kernel(const float* __restrict__ rgb, int H, int W, float f, int H1, int W1,
+                             const int* __restrict__ origins, int T, float* __restrict__ tiles, float* __restrict__ stats_out,
+                             float* __restrict__ partials, unsigned* barrier) {
+  __shared__ float red[3][32];
+  const long HW = (long)H * W;
+  // ---- statistics: per-CTA partials, grid barrier, every CTA reduces the (<= 148) partials itself
+  float mn, ymn, ymx;
+  frame_stats_slice(rgb, HW, 0.f, mn, ymn, ymx);
+  cta_minmax3(mn, ymn, ymx, red);
+  if (threadIdx.x == 0) { partials[3 * blockIdx.x] = mn; partials[3 * blockIdx.x + 1] = ymn; partials[3 * blockIdx.x + 2] = ymx; }
+  select_grid_barrier(barrier, gridDim.x);
+  mn = INFINITY; ymn = INFINITY; ymx = -INFINITY;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+    mn = fminf(mn, __ldcg(partials + 3 * i)); ymn = fminf(ymn, __ldcg(partials + 3 * i + 1)); ymx = fmaxf(ymx, __ldcg(partials + 3 * i + 2));
+  }
+  cta_minmax3(mn, ymn, ymx, red);
+  const float shift = fminf(mn, 0.f);
+  if (shift != 0.f) {   // negative inputs (exr): luminance range of the shifted image (grid-uniform branch)
+    float m2, y0, y1;
+    frame_stats_slice(rgb, HW, shift, m2, y0, y1);
+    cta_minmax3(m2, y0, y1, red);
+    float* p2 = partials + 3 * gridDim.x;
+    if (threadIdx.x == 0) { p2[3 * blockIdx.x + 1] = y0; p2[3 * blockIdx.x + 2] = y1; }
+    select_grid_barrier(barrier, 2 * gridDim.x);
+    ymn = INFINITY; ymx = -INFINITY;
+    float dummy = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+      ymn = fminf(ymn, __ldcg(p2 + 3 * i + 1)); ymx = fmaxf(ymx, __ldcg(p2 + 3 * i + 2));
+    }
+    cta_minmax3(dummy, ymn, ymx, red);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { stats_out[0] = mn; stats_out[1] = ymn; stats_out[2] = ymx; }
+  // ---- normalise, written as tiles: tile pixel (t, ly, lx) = padded pixel (oy + ly, ox + lx) = source pixel clamped
+  const float gmax = ymx - ymn;
+  const float lmax = log10f((gmax / gmax) * f + 1.f);
+  const int padT = (H1 - H) / 2, padL = (W1 - W) / 2;
+  const long total4 = (long)T * (65536 / 4);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+    const int t = (int)(i >> 14), r = (int)(i & 16383);
+    const int ly = r >> 6, lx = (r & 63) << 2;
+    const int y = min(max(__ldg(origins + 2 * t) + ly - padT, 0), H - 1);
+    const int x1 = __ldg(origins + 2 * t + 1) + lx - padL;
+    const float* row = rgb + (long)y * W;
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = min(max(x1 + k, 0), W - 1);
+      const float g = gray_of(__ldg(row + x) - shift, __ldg(row + HW + x) - shift, __ldg(row + 2 * HW + x) - shift) - ymn;
+      o[k] = log10f((g / gmax) * f + 1.f) / lmax;
+    }
+    *reinterpret_cast<float4*>(tiles + (i << 2)) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---- frame stage 2 in ONE cooperative launch: closed-form blend of the tiles -> padded plane (written out for the
+// post-process) with its order keys kept in shared memory -> percentiles of the plane.  K <= 3 (overlap <= 3 tiles).
+__global__ void __launch_bounds__(kFusedThreads, 1)
+blend_select_kernel(const float* __restrict__ tiles, const int* __restrict__ yidx, const float* __restrict__ yw,
+                    const int* __restrict__ ystart, const int* __restrict__ xidx, const float* __restrict__ xw,
+                    const int* __restrict__ xstart, int TX, int K, float* __restrict__ plane, int H1, int W1, long per_cta,
+                    unsigned* __restrict__ hist3, unsigned* barrier, const SelRanks ranks, double t0, double t1,
+                    float* pct_out) {
+  UNCL_SEL_SMEM(sm);
+  const long n = (long)H1 * W1;
+  const long begin = (long)blockIdx.x * per_cta;
+  const int cnt = (int)max(0L, min(per_cta, n - begin));
+  sel_clear_hist(sm);
+  // four consecutive pixels of a row per thread and step (W1, per_cta and hence `begin` are multiples of 4): the row's
+  // tables are read once, the 4 x up-to-9 tile loads are independent of each other, the plane is written as float4
+  const int W4 = W1 >> 2, cnt4 = cnt >> 2;
+  const int g0 = (int)(begin >> 2);
+  for (int j = threadIdx.x; j < cnt4; j += blockDim.x) {
+    const int g = g0 + j;
+    const int y = g / W4, x0 = (g - y * W4) << 2;
+    float wa[3];
+    long rowoff[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      wa[a] = a < K ? __ldg(yw + K * y + a) : 0.f;
+      const int ty = a < K ? __ldg(yidx + K * y + a) : 0;
+      rowoff[a] = ((long)(ty * TX) << 16) + ((y - __ldg(ystart + ty)) << 8);
+    }
+    float acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = x0 + k;
+      float wb[3];
+      long off[3];
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        wb[b] = b < K ? __ldg(xw + K * x + b) : 0.f;
+        const int tx = b < K ? __ldg(xidx + K * x + b) : 0;
+        off[b] = ((long)tx << 16) + (x - __ldg(xstart + tx));
+      }
+      float t = 0.f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (wa[a] == 0.f) continue;
+        float row = 0.f;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          if (wb[b] == 0.f) continue;
+          row = fmaf(wb[b], __ldg(tiles + rowoff[a] + off[b]), row);
+        }
+        t = fmaf(wa[a], row, t);
+      }
+      acc[k] = t;
+    }
+    *reinterpret_cast<float4*>(plane + ((long)g << 2)) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sel_visit0(sm, acc[k], 4 * j + k);
+  }
+  sel_finish(sm, cnt, hist3, barrier, 0u, ranks);
+  if (blockIdx.x == 0 && threadIdx.x == 0) sel_result(sm, t0, t1, pct_out[0], pct_out[1]);
+}
+
+// ---- frame stage 3 in ONE cooperative launch: post-process (clamp to the plane's percentiles, stretch, back to colour,
+// crop) -> colour values as order keys in shared memory (and, if asked, in `col_out`) -> their percentiles after the
+// clamp to [0, 1] -> the 8-bit image straight from the shared-memory keys.  A CTA owns a contiguous range of PIXELS and
+// keeps their three channels side by side, so its slice of the interleaved 8-bit image is contiguous too.
+__global__ void __launch_bounds__(kFusedThreads, 1)
+post_select_u8_kernel(const float* __restrict__ fake, int W1, int padT, int padL, const float* __restrict__ rgb, int H, int W,
+                      const float* __restrict__ stats, const float* __restrict__ pct_plane, float* __restrict__ col_out,
+                      long px_per_cta, unsigned* __restrict__ hist3, unsigned* barrier, const SelRanks ranks, double t0,
+                      double t1, float* pct_out, unsigned char* __restrict__ u8_out) {
+  UNCL_SEL_SMEM(sm);
+  const long HW = (long)H * W;
+  const long pbegin = (long)blockIdx.x * px_per_cta;
+  const int pcnt = (int)max(0L, min(px_per_cta, HW - pbegin));
+  sel_clear_hist(sm);
+  {
+    const float shift = fminf(stats[0], 0.f);
+    const float lo = pct_plane[0], hi = pct_plane[1];
+    const float inv = 1.f / (hi - lo);
+    // two pixels per thread and step: their eight loads are issued before any arithmetic
+    for (int j = threadIdx.x; j < pcnt; j += 2 * blockDim.x) {
+      const int j1 = j + blockDim.x;
+      const bool has1 = j1 < pcnt;
+      float fk[2], r[2], g[2], b[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const long i = pbegin + (u == 0 || has1 ? (u == 0 ? j : j1) : j);
+        const int y = (int)(i / W), x = (int)(i - (long)y * W);
+        fk[u] = __ldg(fake + (long)(y + padT) * W1 + (x + padL));
+        r[u] = __ldg(rgb + i); g[u] = __ldg(rgb + HW + i); b[u] = __ldg(rgb + 2 * HW + i);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !has1) break;
+        const int jj = u == 0 ? j : j1;
+        const long i = pbegin + jj;
+        const float s = (fminf(fmaxf(fk[u], lo), hi) - lo) * inv;
+        const float rr = r[u] - shift, gg = g[u] - shift, bb = b[u] - shift;
+        const float d = gray_of(rr, gg, bb) + 1e-8f;
+        const float c0 = sqrtf(rr / d) * s, c1 = sqrtf(gg / d) * s, c2 = sqrtf(bb / d) * s;
+        if (col_out != nullptr) { col_out[i] = c0; col_out[HW + i] = c1; col_out[2 * HW + i] = c2; }
+        sel_visit0(sm, fminf(fmaxf(c0, 0.f), 1.f), 3 * jj);
+        sel_visit0(sm, fminf(fmaxf(c1, 0.f), 1.f), 3 * jj + 1);
+        sel_visit0(sm, fminf(fmaxf(c2, 0.f), 1.f), 3 * jj + 2);
+      }
+    }
+  }
+  sel_finish(sm, 3 * pcnt, hist3, barrier, 0u, ranks);
+  float lo, hi;
+  sel_result(sm, t0, t1, lo, hi);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { pct_out[0] = lo; pct_out[1] = hi; }
+  // 8-bit image: clip((clamp(c,0,1) - lo) / (hi - lo), 0, 1) * 255 truncated - the keys ARE the clamped values
+  unsigned char* o = u8_out + 3 * pbegin;
+  for (int j = threadIdx.x; j < 3 * pcnt; j += blockDim.x) {
+    float v = key_value(sm.keys[j]);
+    v = fminf(fmaxf((v - lo) / (hi - lo), 0.f), 1.f);
+    o[j] = (unsigned char)(v * 255.f);
   }
 }
 
@@ -629,4 +878,132 @@ extern "C" int uncl_frame_to_u8(const float* col, int H, int W, const float* pct
   UNCL_REQUIRE(H > 0 && W > 0, "frame_to_u8: bad arguments");
   frame_to_u8_kernel<<<grid_for((long)H * W, 256, 8), 256, 0, stream>>>(col, (long)H * W, pct, out);
   return uncl_check_launch("frame_to_u8");
+}
+
+
+// ================================================================================================
+// Fused frame stages: one cooperative launch each (one 1024-thread CTA per SM, grid barriers inside)
+// ================================================================================================
+namespace {
+
+struct SelPlan { SelRanks ranks; double t0, t1; };
+// numpy.percentile 'linear': the two neighbouring order statistics of each percentile and the interpolation weights
+inline SelPlan sel_plan(long n, double p_lo, double p_hi) {
+  const double v0 = p_lo / 100.0 * (double)(n - 1), v1 = p_hi / 100.0 * (double)(n - 1);
+  long k0 = (long)v0, k1 = (long)v1;
+  if (k0 > n - 2) k0 = n - 2;
+  if (k1 > n - 2) k1 = n - 2;
+  SelPlan sp;
+  sp.ranks = {{(unsigned)k0, (unsigned)(k0 + 1), (unsigned)k1, (unsigned)(k1 + 1)}};
+  sp.t0 = v0 - (double)k0; sp.t1 = v1 - (double)k1;
+  return sp;
+}
+
+struct CoopDev { int sms, coop; };
+inline CoopDev coop_device() {
+  static thread_local int cached_dev = -1;
+  static thread_local CoopDev cd = {148, 0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cd.sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&cd.coop, cudaDevAttrCooperativeLaunch, dev);
+    cached_dev = dev;
+  }
+  return cd;
+}
+
+template <typename K>
+inline int coop_launch(K kern, int sms, void** args, size_t smem, cudaStream_t stream, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024));
+  if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));
+  e = cudaLaunchCooperativeKernel((const void*)kern, dim3(sms), dim3(kFusedThreads), args, smem, stream);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return uncl_set_error(UNCL_EUNSUPPORTED, "%s: cooperative launch refused (%s) - use the staged calls", what, cudaGetErrorString(e));
+  }
+  return uncl_check_launch(what);
+}
+
+}  // namespace
+
+// 1 when the three fused frame-stage calls below can run for this geometry on the current device (cooperative launch
+// available, every CTA's slice of order keys fits its shared memory, blend overlap of at most 3 tiles per axis), else 0:
+// callers then use the staged calls (uncl_frame_normalise_pad ... uncl_frame_to_u8), which compute the same values.
+extern "C" int uncl_frame_fused_supported(int H, int W, int H1, int W1, int K) {
+  if (H <= 0 || W <= 0 || H1 < H || W1 < W || K <= 0 || K > 3) return 0;
+  const CoopDev cd = coop_device();
+  if (!cd.coop) return 0;
+  const long per_plane = (((long)H1 * W1 + cd.sms - 1) / cd.sms + 3) & ~3L;
+  const long px = ((long)H * W + cd.sms - 1) / cd.sms;
+  return (per_plane <= kFusedMaxKeys && 3 * px <= kFusedMaxKeys && (long)H1 * W1 < (1L << 31)) ? 1 : 0;
+}
+
+// uncl_frame_normalise_pad + uncl_tiles_gather in one launch: statistics, (shifted statistics), normalisation written
+// directly as the T 256x256 generator tiles at origins[t] = (y, x) of the padded (H1 x W1) frame, which is never stored.
+extern "C" int uncl_frame_normalise_tiles(const float* rgb, int H, int W, float f_factor, int H1, int W1, const int* origins,
+                                          int T, float* tiles, float* stats_out, void* workspace, cudaStream_t stream) {
+  UNCL_REQUIRE(H > 0 && W > 0 && H1 >= H && W1 >= W && H1 >= 256 && W1 >= 256 && T > 0 && f_factor > 0.f,
+               "frame_normalise_tiles: bad arguments");
+  UNCL_REQUIRE((reinterpret_cast<uintptr_t>(rgb) & 15) == 0 && (reinterpret_cast<uintptr_t>(tiles) & 15) == 0,
+               "frame_normalise_tiles: rgb / tiles must be 16-byte aligned");
+  const CoopDev cd = coop_device();
+  if (!cd.coop || 2 * cd.sms > kStatBlocks) return uncl_set_error(UNCL_EUNSUPPORTED, "frame_normalise_tiles: no cooperative launch");
+  FrameWs w = carve(workspace);
+  cudaMemsetAsync(w.fused_barrier, 0, 16, stream);
+  float* partials = w.partials;
+  unsigned* bar = w.fused_barrier;
+  void* args[] = {(void*)&rgb, (void*)&H, (void*)&W, (void*)&f_factor, (void*)&H1, (void*)&W1, (void*)&origins, (void*)&T,
+                  (void*)&tiles, (void*)&stats_out, (void*)&partials, (void*)&bar};
+  return coop_launch(frame_normalise_tiles_kernel, cd.sms, args, 0, stream, "frame_normalise_tiles");
+}
+
+// uncl_tiles_blend + uncl_percentile_pair(plane, p_lo, p_hi) in one launch: the blended plane is written to `plane_out`
+// and its percentiles to pct_out[0..1].  K <= 3.
+extern "C" int uncl_frame_blend_percentiles(const float* tiles, const int* yidx, const float* yw, const int* ystart,
+                                            const int* xidx, const float* xw, const int* xstart, int TX, int K,
+                                            float* plane_out, int H1, int W1, double p_lo, double p_hi, float* pct_out,
+                                            void* workspace, cudaStream_t stream) {
+  UNCL_REQUIRE(TX > 0 && K > 0 && K <= 3 && H1 >= 256 && W1 >= 256 && p_lo >= 0 && p_hi <= 100 && p_lo <= p_hi,
+               "frame_blend_percentiles: bad arguments (K=%d)", K);
+  const CoopDev cd = coop_device();
+  const long n = (long)H1 * W1;
+  long per_cta = ((n + cd.sms - 1) / cd.sms + 3) & ~3L;
+  if (!cd.coop || per_cta > kFusedMaxKeys || n >= (1L << 31))
+    return uncl_set_error(UNCL_EUNSUPPORTED, "frame_blend_percentiles: plane too large for the fused kernel");
+  FrameWs w = carve(workspace);
+  const SelPlan sp = sel_plan(n, p_lo, p_hi);
+  cudaMemsetAsync(w.fused_barrier, 0, 16 + 3 * 4 * 2048 * 4, stream);
+  unsigned* hist3 = w.fused_hist;
+  unsigned* bar = w.fused_barrier;
+  const size_t smem = (size_t)((kSelQ << 11) + per_cta) * sizeof(unsigned);
+  void* args[] = {(void*)&tiles, (void*)&yidx, (void*)&yw, (void*)&ystart, (void*)&xidx, (void*)&xw, (void*)&xstart, (void*)&TX,
+                  (void*)&K, (void*)&plane_out, (void*)&H1, (void*)&W1, (void*)&per_cta, (void*)&hist3, (void*)&bar,
+                  (void*)&sp.ranks, (void*)&sp.t0, (void*)&sp.t1, (void*)&pct_out};
+  return coop_launch(blend_select_kernel, cd.sms, args, smem, stream, "frame_blend_percentiles");
+}
+
+// uncl_frame_postprocess + uncl_percentile_pair(clip(col, 0, 1), p_lo, p_hi) + uncl_frame_to_u8 in one launch.
+// col_out ([3][H][W] fp32) may be NULL when only the 8-bit HWC image is wanted; pct_out[0..1] receives the colour percentiles.
+extern "C" int uncl_frame_post_u8(const float* fake, int H1, int W1, const float* rgb, int H, int W, const float* stats,
+                                  const float* pct_plane, float* col_out, double p_lo, double p_hi, float* pct_out,
+                                  unsigned char* u8_out, void* workspace, cudaStream_t stream) {
+  UNCL_REQUIRE(H > 0 && W > 0 && H1 >= H && W1 >= W && u8_out != nullptr && p_lo >= 0 && p_hi <= 100 && p_lo <= p_hi,
+               "frame_post_u8: bad arguments");
+  const CoopDev cd = coop_device();
+  const long HW = (long)H * W;
+  long px_per_cta = (HW + cd.sms - 1) / cd.sms;
+  if (!cd.coop || 3 * px_per_cta > kFusedMaxKeys || 3 * HW >= (1L << 32))
+    return uncl_set_error(UNCL_EUNSUPPORTED, "frame_post_u8: frame too large for the fused kernel");
+  FrameWs w = carve(workspace);
+  const SelPlan sp = sel_plan(3 * HW, p_lo, p_hi);
+  cudaMemsetAsync(w.fused_barrier, 0, 16 + 3 * 4 * 2048 * 4, stream);
+  unsigned* hist3 = w.fused_hist;
+  unsigned* bar = w.fused_barrier;
+  const int padT = (H1 - H) / 2, padL = (W1 - W) / 2;
+  const size_t smem = (size_t)((kSelQ << 11) + 3 * px_per_cta) * sizeof(unsigned);
+  void* args[] = {(void*)&fake, (void*)&W1, (void*)&padT, (void*)&padL, (void*)&rgb, (void*)&H, (void*)&W, (void*)&stats,
+                  (void*)&pct_plane, (void*)&col_out, (void*)&px_per_cta, (void*)&hist3, (void*)&bar, (void*)&sp.ranks,
+                  (void*)&sp.t0, (void*)&sp.t1, (void*)&pct_out, (void*)&u8_out};
+  return coop_launch(post_select_u8_kernel, cd.sms, args, smem, stream, "frame_post_u8");
 }

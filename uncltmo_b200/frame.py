@@ -89,6 +89,7 @@ class _Plan:
             return out
 
         self.k = k
+        self.fused_ok = None   # uncl_frame_fused_supported, asked once
         self.ty, self.tx = len(ys), len(xs)
         self.ntiles = self.ty * self.tx
         origins = np.array([(y, x) for y in ys for x in xs], dtype=np.int32)
@@ -106,6 +107,8 @@ class FramePipeline:
         self.factor_coeff = factor_coeff
         self.overlap = overlap
         self.max_tiles = max_tiles_per_batch
+        self.fused = True   # one cooperative launch per frame stage when the device / geometry allow it
+        self.fused_stages = ("norm", "blend", "post")   # which stages take the fused kernel (all; tools/ measure subsets)
         self._plans = {}
         self._ws = None
 
@@ -170,6 +173,54 @@ class FramePipeline:
         call("uncl_frame_to_u8", col, h, w, pct, out)
         return out
 
+    # -- the same stages fused into one cooperative launch each (bit-identical values, 3 launches instead of 14) --
+    def fused_ok(self, pl):
+        """True when the fused stage kernels can run for this plan on the current device (uncl_frame_fused_supported)."""
+        if not self.fused:
+            return False
+        if pl.fused_ok is None:
+            pl.fused_ok = bool(_lib.lib().uncl_frame_fused_supported(pl.h, pl.w, pl.h1, pl.w1, pl.k))
+        return pl.fused_ok
+
+    def normalise_tiles(self, rgb, lam, pl):
+        """normalise_pad + gather_tiles in one launch -> (tiles [T,1,256,256], stats [4])."""
+        tiles = torch.empty((pl.ntiles, 1, PATCH, PATCH), device=rgb.device, dtype=torch.float32)
+        stats = torch.empty(4, device=rgb.device, dtype=torch.float32)
+        call("uncl_frame_normalise_tiles", rgb, pl.h, pl.w, float(lam * 255 * self.factor_coeff), pl.h1, pl.w1, pl.origins,
+             pl.ntiles, tiles, stats, self._workspace(rgb.device))
+        return tiles, stats
+
+    def blend_percentiles(self, tiles, pl, p_lo=0.5, p_hi=99.5):
+        """blend + percentiles of the blended plane in one launch -> (fake_p [H1,W1], pct [2])."""
+        out = torch.empty((pl.h1, pl.w1), device=tiles.device, dtype=torch.float32)
+        pct = torch.empty(2, device=tiles.device, dtype=torch.float32)
+        call("uncl_frame_blend_percentiles", tiles, pl.yidx, pl.yw, pl.ystart, pl.xidx, pl.xw, pl.xstart, pl.tx, pl.k, out,
+             pl.h1, pl.w1, float(p_lo), float(p_hi), pct, self._workspace(tiles.device))
+        return out, pct
+
+    def post_uint8(self, fake_p, pct, rgb, stats, pl, want_col=False):
+        """post-process + colour percentiles + 8-bit stretch in one launch -> HWC uint8 (and the fp32 colour frame)."""
+        col = torch.empty((3, pl.h, pl.w), device=rgb.device, dtype=torch.float32) if want_col else None
+        u8 = torch.empty((pl.h, pl.w, 3), device=rgb.device, dtype=torch.uint8)
+        pct2 = torch.empty(2, device=rgb.device, dtype=torch.float32)
+        call("uncl_frame_post_u8", fake_p, pl.h1, pl.w1, rgb, pl.h, pl.w, stats, pct, col, 0.1, 99.0, pct2, u8,
+             self._workspace(rgb.device))
+        return (u8, col) if want_col else u8
+
+    def finish(self, out_tiles, rgb, stats, pl, uint8):
+        """generator tiles -> tone-mapped frame: blend, percentile clamp / stretch, back to colour, (8-bit stretch)."""
+        ok = self.fused_ok(pl)
+        if ok and "blend" in self.fused_stages:
+            fake_p, pct = self.blend_percentiles(out_tiles, pl)
+        else:
+            fake_p = self.blend(out_tiles, pl)
+            pct = self.percentiles(fake_p, 0.5, 99.5)
+        if ok and uint8 and "post" in self.fused_stages:
+            return self.post_uint8(fake_p, pct, rgb, stats, pl)
+        col = torch.empty((3, pl.h, pl.w), device=rgb.device, dtype=torch.float32)
+        call("uncl_frame_postprocess", fake_p, pl.h1, pl.w1, rgb, pl.h, pl.w, stats, pct, col)
+        return self.to_uint8(col) if uint8 else col
+
     # -- whole path --
     def tonemap(self, rgb, lam, uint8=False):
         """rgb [3,H,W] fp32 CUDA, lam = the image's lambda (f = lam*255*factor_coeff) -> [3,H,W] fp32 or HWC uint8."""
@@ -177,11 +228,12 @@ class FramePipeline:
             raise ValueError("tonemap expects a CUDA fp32 [3,H,W] tensor")
         rgb = rgb.contiguous()
         pl = self.plan(rgb.shape[1], rgb.shape[2], rgb.device)
-        gray_p, stats = self.normalise_pad(rgb, lam)
-        tiles = self.gather_tiles(gray_p, pl)
-        fake_p = self.blend(self.run_generator(tiles), pl)
-        col = self.postprocess(fake_p, rgb, stats, pl)
-        return self.to_uint8(col) if uint8 else col
+        if self.fused_ok(pl) and "norm" in self.fused_stages:
+            tiles, stats = self.normalise_tiles(rgb, lam, pl)
+        else:
+            gray_p, stats = self.normalise_pad(rgb, lam)
+            tiles = self.gather_tiles(gray_p, pl)
+        return self.finish(self.run_generator(tiles), rgb, stats, pl, uint8)
 
     def tonemap_host_frames(self, host_frames, lam, out=None, sync=True):
         """Stream pinned HOST frames through the path: [3,H,W] fp32 each -> HWC uint8 host tensors.
@@ -260,8 +312,12 @@ class FramePipeline:
         frames = frames.contiguous()
         t_len = frames.shape[0]
         pl = self.plan(frames.shape[2], frames.shape[3], frames.device)
-        norm = [self.normalise_pad(frames[t], lam) for t in range(t_len)]
-        tiles = [self.gather_tiles(g, pl) for g, _ in norm]
+        if self.fused_ok(pl):
+            norm = [self.normalise_tiles(frames[t], lam, pl) for t in range(t_len)]
+            tiles = [tl for tl, _ in norm]
+        else:
+            norm = [self.normalise_pad(frames[t], lam) for t in range(t_len)]
+            tiles = [self.gather_tiles(g, pl) for g, _ in norm]
         lo, hi = 0, pl.ntiles
         sharded = shard_tiles and tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1
         if sharded:
@@ -282,9 +338,7 @@ class FramePipeline:
         if sharded and shard_frames_out:
             mine = range(tdist.get_rank(), t_len, tdist.get_world_size())
         for t in mine:
-            fake_p = self.blend(per_frame[t], pl)
-            col = self.postprocess(fake_p, frames[t], norm[t][1], pl)
-            res.append(self.to_uint8(col) if uint8 else col)
+            res.append(self.finish(per_frame[t], frames[t], norm[t][1], pl, uint8))
         if sharded and shard_frames_out:
             return list(zip(mine, res))
         return torch.stack(res)
