@@ -28,8 +28,9 @@ namespace {
 
 using namespace tcptx;
 
-constexpr int kThreads = 608;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-17: epilogue, warp 18: second MMA issuer
-constexpr int kMma2Warp = 18;          // issues the upper half of a tile's M blocks when TcParams::mma_warps == 2
+constexpr int kThreads = 640;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-17: epilogue, warps 18-19: further MMA issuers
+constexpr int kMma2Warp = 18;          // first of the extra issuing warps (TcParams::mma_warps == 2 or 3: the M blocks of a tile are dealt
+                                       // out; 20 warps = 5 per scheduler keep 96 registers per thread, a 21st would cap them at 80)
 constexpr int kEpiWarps = 16;          // four warps per TMEM lane quarter; (M block, 32-column chunk) units dealt round-robin
 constexpr int kEpiPerQuarter = kEpiWarps / 4;
 constexpr int kAccCols = 256;          // TMEM columns per accumulator stage when double-buffered (2 stages = 512 = all of TMEM)
@@ -55,7 +56,7 @@ struct TcParams {
   int nchunk, ntaps, stages;
   int ksteps;               // K = 16 steps per pipeline stage (pointwise GEMMs: up to 4 = 64 input channels per barrier round trip)
   int nacc, acc_cols;       // accumulator stages (2 x 256 columns, or 1 x 512 for K-heavy layers: see launch_tc)
-  int mma_warps;            // 1, or 2: M blocks [0, MB/2) and [MB/2, MB) of every tile are issued by two warps
+  int mma_warps;            // 1, 2 or 3 issuing warps: warp slot w issues the M blocks [w * per, (w + 1) * per), per = ceil(MB / warps)
   int a_box_bytes, a_stage_bytes, b_stage_bytes, stage_bytes;
   int act, emit_skip, fuse_outc;
   int sh_C, sh_H2, sh_W2;   // pixel-shuffle epilogue (ConvTranspose k2 s2): channels, target extent (replicate pad)
@@ -113,7 +114,8 @@ __device__ __forceinline__ Item decode_item(const Geo& g, int item) {
 // 9 taps x MB blocks of one K chunk, fully unrolled: descriptor low words are base + compile-time-shaped offsets
 // B0..B1: the blocks of the tile this warp issues (each block owns its accumulator columns, so two issuing warps
 // never touch the same TMEM columns and need no ordering between their instruction streams)
-template <int B0, int B1>
+// NB: the number of blocks this warp issues; d0 / a_row already point at its first block
+template <int NB>
 __device__ __forceinline__ void issue_taps9(uint32_t d0, uint32_t a_row, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
                                             uint32_t pw, uint32_t nt, uint32_t b_tap_16, uint32_t first) {
 #pragma unroll
@@ -121,7 +123,7 @@ __device__ __forceinline__ void issue_taps9(uint32_t d0, uint32_t a_row, uint32_
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-      for (int b = B0; b < B1; ++b) {
+      for (int b = 0; b < NB; ++b) {
         tc_mma_bf16(d0 + (uint32_t)b * nt, a_row + (uint32_t)ky * pw + (uint32_t)(kx + b * 128), desc_hi,
                     b_lo + (uint32_t)(ky * 3 + kx) * b_tap_16, desc_hi, idesc, (ky > 0 || kx > 0) ? 1u : first);
       }
@@ -207,13 +209,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       }
     }
     __syncwarp();
-  } else if (warp == 1 || warp == kMma2Warp) {
+  } else if (warp == 1 || warp >= kMma2Warp) {
     // =============================== MMA issuer(s) ===============================
     // the whole warp walks the (uniform) loop so that descriptors live in uniform registers; one elected lane issues.
     // The issuing warp is a serial, latency-bound instruction stream (~85 cycles per MMA measured against 64 of math at
-    // N = 128): with mma_warps == 2 a second warp on another scheduler issues the upper half of every tile's M blocks.
-    const bool second = warp == kMma2Warp;
-    if (!second || p.mma_warps == 2) {
+    // N = 128, ~57 against 40 at N = 32): with mma_warps == 2 / 3 further warps on the other schedulers issue their share
+    // of every tile's M blocks (each block has its own accumulator columns: the streams need no ordering between them).
+    const int slot = warp == 1 ? 0 : warp - kMma2Warp + 1;
+    const bool second = slot != 0;
+    if (slot < p.mma_warps) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
       // K-major no-swizzle descriptors: lo = (addr >> 4) | (LBO >> 4) << 16 ; hi = (SBO >> 4) | version 1 << 14
       const uint32_t desc_hi = (128u >> 4) | (1u << 14);
@@ -231,8 +235,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       long long w_full = 0, w_tempty = 0;
       const long long t_begin = dbg ? clock64() : 0;
       const unsigned long long g_begin = dbg ? globaltimer_ns() : 0ull;
-      const bool split = p.mma_warps == 2;
-      const uint32_t b_split = (uint32_t)p.MB >> 1;   // first block of the second warp
+      const uint32_t per = (uint32_t)((p.MB + p.mma_warps - 1) / p.mma_warps);
+      const uint32_t blk_lo = min((uint32_t)slot * per, (uint32_t)p.MB), blk_hi = min(blk_lo + per, (uint32_t)p.MB);
+      const uint32_t nblk = blk_hi - blk_lo;   // blocks this warp issues (launch-uniform)
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const Item it = decode_item(geo, item);
         const long long tw0 = dbg ? clock64() : 0;
@@ -241,8 +246,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * acc_cols);
         // runtime block range of this warp (pointwise GEMMs and unusual tile heights)
-        const uint32_t mb_lo = (split && second) ? b_split : 0u;
-        const uint32_t mb = (split && !second) ? min((uint32_t)it.mb_act, b_split) : (uint32_t)it.mb_act;
+        const uint32_t mb_lo = blk_lo;
+        const uint32_t mb = min((uint32_t)it.mb_act, blk_hi);
         for (int ch = 0; ch < nchunk; ++ch) {
           const long long tw1 = dbg ? clock64() : 0;
           if (!(UNCL_PROBE(p.probe_noload, 4))) mbar_wait(&full[stage], phase);
@@ -260,20 +265,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             // and are skipped by the epilogue.
             if (elect_one()) {
               const uint32_t first = ch > 0 ? 1u : 0u;
-              switch (p.MB * 4 + (split ? (second ? 2 : 1) : 0)) {
-                case 1 * 4: issue_taps9<0, 1>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
-                case 2 * 4: issue_taps9<0, 2>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
-                case 3 * 4: issue_taps9<0, 3>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
-                case 4 * 4: issue_taps9<0, 4>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
-                case 8 * 4: issue_taps9<0, 8>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
-                case 2 * 4 + 1: issue_taps9<0, 1>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
-                case 2 * 4 + 2: issue_taps9<1, 2>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
-                case 3 * 4 + 1: issue_taps9<0, 1>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
-                case 3 * 4 + 2: issue_taps9<1, 3>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
-                case 4 * 4 + 1: issue_taps9<0, 2>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
-                case 4 * 4 + 2: issue_taps9<2, 4>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
-                case 8 * 4 + 1: issue_taps9<0, 4>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
-                case 8 * 4 + 2: issue_taps9<4, 8>(d0, a_row, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
+              const uint32_t dw = d0 + blk_lo * nt, aw = a_row + blk_lo * mstep;   // this warp's first block
+              switch (nblk) {
+                case 0: break;
+                case 1: issue_taps9<1>(dw, aw, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
+                case 2: issue_taps9<2>(dw, aw, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
+                case 3: issue_taps9<3>(dw, aw, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
+                case 4: issue_taps9<4>(dw, aw, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
+                case 8: issue_taps9<8>(dw, aw, b_lo, desc_hi, idesc, pw, nt, b_tap_16, first); break;
                 default:
 #pragma unroll
                   for (int ky = 0; ky < 3; ++ky) {
@@ -619,8 +618,8 @@ int plan_tc(TcParams& p, int N, int C_in, int bias_floats, const char* what, int
     const int want = atoi(e);
     if (want >= 1 && want < p.MB) p.MB = want;
   }
-  p.mma_warps = p.MB >= 2 ? 2 : 1;
-  if (const char* e = probe_env("UNCL_MMA_WARPS")) { if (atoi(e) == 1) p.mma_warps = 1; }
+  p.mma_warps = p.MB >= 6 ? 3 : (p.MB >= 2 ? 2 : 1);
+  if (const char* e = probe_env("UNCL_MMA_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= 3 && w <= p.MB) p.mma_warps = w; }
   p.PH = (p.PW - 1 + 128 * p.MB - 1) / p.PW + 1 + halo;
   p.tiles_per_band = ceil_div(p.band_total, 128 * p.MB);
   p.tiles_per_img = p.nbands * p.tiles_per_band;
