@@ -267,7 +267,7 @@ def train_workload(dev, precision, steps, warmup, world=1, rank=0, video=False, 
             "ms_per_step": ms / steps, "scaling": "weak (16 images per GPU)" if weak else "strong",
             "images_per_s": steps * 2 * b_local * world / (ms / 1e3), "execution": "CUDA graph replay of the whole iteration",
             "eager_launch_path": {"value": steps / (ms_eager / 1e3), "unit": "steps/s", "ms_per_step": ms_eager / steps,
-                                  "note": "same trainer without capture; launch-bound, and Adam(capturable=True) is slower eagerly"}, "dtype": "f32" if precision == "fp32" else ("bf16 activations and gradient operands, f32 accumulation / parameters / optimizer" if flat else "bf16 operands / f32 tensors (mixed)"),
+                                  "note": "same trainer without capture; launch-bound, and Adam(capturable=True) is slower eagerly"}, "dtype": "f32" if precision == "fp32" else ("f32 (3x3 convolutions as three-term bf16 split tensor-core GEMMs, ~2^-16)" if precision == "fp32_tc" else ("bf16 activations and gradient operands, f32 accumulation / parameters / optimizer" if flat else "bf16 operands / f32 tensors (mixed)")),
             "tflops_algorithmic": steps * TRAIN_GFLOP_STEP / ms, "gpu_launches": launches,
             "e2e": {"value": steps / (ms_e2e / 1e3), "unit": "steps/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 8},
             "config": {"global_batch": "8 x 2 crops = 16 images of 256x256", "per_gpu_images": 2 * b_local, "loss_schedule": "epoch 0",
@@ -508,7 +508,7 @@ def main():
         torch.cuda.synchronize()
         fp32_exact["frames_per_s"] = 4 / (e0.elapsed_time(e1) / 1e3)
         fp32_exact["inference_path"] = "precision='fp32_tc' (tcgen05, three-term bf16 split)"
-        fp32_exact["training_path"] = "precision='fp32' (CUDA cores)"
+        fp32_exact["training_path"] = "precision='fp32_tc' (3x3 convolutions forward / data / weight gradient as three-term bf16 split GEMMs on tcgen05, the rest on fp32 CUDA cores)"
         net32 = pipe32 = None
     if not args.no_train:
         net = pipe = None
@@ -516,7 +516,7 @@ def main():
         torch.cuda.empty_cache()
         with torch.enable_grad():
             train = train_workload(dev, args.train_precision, max(10, args.steps), args.warmup, world, rank)
-            exact = train_workload(dev, "fp32", 5, 3, 1, 0) if world == 1 else None
+            exact = train_workload(dev, "fp32_tc", 5, 3, 1, 0) if world == 1 else None
             if world > 1:
                 weak = train_workload(dev, args.train_precision, max(10, args.steps), args.warmup, world, rank, weak=True)
                 train["weak_16_images_per_gpu"] = {k: weak[k] for k in ("value", "unit", "ms_per_step", "images_per_s", "scaling")}

@@ -297,6 +297,10 @@ int uncl_conv3x3_wgrad(const float* X, long x_img_stride, const float* dZ, float
  * dW9): a GEMM with K = pixels whose operands are read MN-major straight from the C8-blocked TMA tiles. */
 int uncl_conv3x3_wgrad_tc(const void* X, long x_img_stride, const void* dZ, float* dW9, int N, int C_in, int H, int W,
                           int C_out, int pad, uncl_stream_t stream);
+/* The same with an explicit dZ image stride (elements): dZ may be a channel slice of a wider tensor.  The exact training
+ * path (precision 'fp32_tc') accumulates x_hi.dz_hi + x_hi.dz_lo + x_lo.dz_hi into one dW9 with three calls. */
+int uncl_conv3x3_wgrad_tc_strided(const void* X, long x_img_stride, const void* dZ, long dz_img_stride, float* dW9, int N,
+                                  int C_in, int H, int W, int C_out, int pad, uncl_stream_t stream);
 /* Pointwise (GEMM) weight gradient on the same tensor-core kernel (one tap): dW[ci][co] += sum_pix X[pix,ci] * dZ[pix,co];
  * bf16 blocked operands with their own image strides, dW fp32 [C_in][C_out] (zeroed by the caller).  Weight gradient of
  * the k2 s2 up-convolution over the space-to-depth output gradient (C_out = 4C). */

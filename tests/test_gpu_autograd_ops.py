@@ -76,6 +76,28 @@ def test_conv3x3_tensor_core_path(ci, co, h, transposed):
     assert rel(wc.grad, wr.grad) < 1e-5 and rel(bc.grad, br.grad) < 1e-5
 
 
+@pytest.mark.parametrize("ci,co,h,transposed,relu", [(32, 32, 40, False, True), (64, 128, 30, False, True), (128, 32, 66, True, True),
+                                                    (256, 256, 12, False, False), (512, 64, 29, True, True)])
+def test_conv3x3_exact_split_path(ci, co, h, transposed, relu):
+    """tc="split" (precision 'fp32_tc'): forward, data gradient and weight gradient as three-term bf16 split GEMMs on the
+    tensor cores with UNROUNDED fp32 inputs against float64 - ~2^-16 per product, i.e. fp32-grade results (the bf16 path
+    on the same inputs would sit at ~4e-3)."""
+    x = rnd(2, ci, h, h + 2, seed=1)
+    w = rnd(*((ci, co, 3, 3) if transposed else (co, ci, 3, 3)), seed=2, scale=(9 * ci) ** -0.5)
+    b = rnd(co, seed=3, scale=0.1)
+    xr, wr, br = leaf(x), leaf(w), leaf(b)
+    yr = F.conv_transpose2d(xr, wr, br) if transposed else F.conv2d(xr, wr, br)
+    yr = F.relu(yr) if relu else yr
+    g = rnd(*yr.shape, seed=4)
+    yr.backward(g.double())
+    xb, wc, bc = leaf(to_blocked(x), "cuda"), leaf(w, "cuda"), leaf(b, "cuda")
+    y = A.Conv3x3.apply(xb, wc, bc, transposed, relu, "split")
+    y.backward(to_blocked(g).cuda())
+    assert rel(from_blocked(y), yr) < 2e-5
+    assert rel(from_blocked(xb.grad), xr.grad) < 2e-5
+    assert rel(wc.grad, wr.grad) < 2e-5 and rel(bc.grad, br.grad) < 1e-5
+
+
 def test_conv_first():
     x = rnd(2, 1, 40, 52, seed=1)
     w, b = rnd(32, 1, 3, 3, seed=2, scale=0.3), rnd(32, seed=3, scale=0.1)

@@ -27,8 +27,10 @@ class RecordingSGD(torch.optim.SGD):
         self.seen = {id(p): p.grad.detach().clone() for g in self.param_groups for p in g["params"] if p.grad is not None}
 
 
-@pytest.mark.parametrize("epoch", [0, 7, 10])
-def test_train_step_matches_oracle(epoch):
+@pytest.mark.parametrize("epoch,precision", [(0, "fp32"), (7, "fp32"), (10, "fp32"), (0, "fp32_tc"), (10, "fp32_tc")])
+def test_train_step_matches_oracle(epoch, precision):
+    """precision 'fp32': CUDA-core kernels; 'fp32_tc': the exact path on the tensor cores (3x3 convolutions - forward, data
+    and weight gradients - as three-term bf16 split GEMMs, ~2^-16 per product): the same gates on losses and D gradients."""
     g_sd, d_sd = make_generator_state_dict(), make_discriminator_state_dict()
     hdr = torch.from_numpy(synth.normalised_batch(2, seed=4)).reshape(1, 2, 1, 256, 256)
     pos = torch.from_numpy(synth.ldr_batch(2, seed=5)).reshape(1, 2, 1, 256, 256)
@@ -38,7 +40,7 @@ def test_train_step_matches_oracle(epoch):
     ref = oracle.train_step_losses({k: v.double() for k, v in g_sd.items()}, {k: v.double() for k, v in d_sd.items()},
                                    hdr[0].double(), pos[0].double(), neg[0].double(), epoch)
 
-    netG = UNet(*G_ARGS, up_mode=0, precision="fp32").cuda().train()
+    netG = UNet(*G_ARGS, up_mode=0, precision=precision).cuda().train()
     netG.load_state_dict(g_sd)
     netG.drop_path_prob = 0.0
     netD = SimpleDiscriminator(256, 1, 16, "none", "none", 0, 0).cuda().train()
@@ -64,9 +66,16 @@ def test_train_step_matches_oracle(epoch):
             e = rel(optG.seen[id(p)], ref["grads_G"][k])
             # outc.conv.bias = sum over all pixels of d(logit): the struct-loss part of that sum cancels to ~0 window by
             # window while its terms are ~1e4 larger, so fp32 leaves ~1e-2 of noise on the small remainder
-            if e > (5e-2 if k == "outc.conv.bias" else 2e-3):
+            tol = 5e-2 if k == "outc.conv.bias" else 2e-3
+            # fp32_tc: the features that reach the graph block carry ~2^-16 instead of ~2^-23, which flips a handful of
+            # near-tie KNN choices (discrete).  The block's output, and the gradient that flows back through it, then differ
+            # by a fraction of a per cent in the layers next to it (measured 2e-3 ... 7e-3: deepest encoder stage, the block,
+            # the first two decoder stages); everything further away stays at the 2e-3 gate
+            if precision == "fp32_tc" and k.startswith(("down_path.3", "gcn.", "up_path.0", "up_path.1")):
+                tol = 2e-2
+            if e > tol:
                 bad[k] = e
-    assert not bad, bad
+    assert not bad, "\n".join("%s %.3e" % kv for kv in sorted(bad.items()))
 
 
 def test_adam_training_reduces_struct_loss():

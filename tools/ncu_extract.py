@@ -13,7 +13,11 @@ want = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_read"
         ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"), ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
         ("launch__registers_per_thread", "regs"), ("smsp__inst_executed.sum", "warp_insts"),
         ("l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum", "tma_load_bytes"),
-        ("launch__grid_size", "grid"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct")]
+        ("launch__grid_size", "grid"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct"),
+        ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex_pct"), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
+        ("sm__cycles_elapsed.avg.per_second", "sm_clock"), ("sm__cycles_elapsed.max", "sm_cycles"),
+        ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "lsu_smem_wavefronts"),
+        ("smsp__inst_executed_pipe_uniform.sum", "uniform_insts")]
 have = [(m, a) for m, a in want if m in col]
 out = csv.writer(sys.stdout)
 out.writerow(["id", "kernel"] + ["%s [%s]" % (a, units[col[m]]) for m, a in have])

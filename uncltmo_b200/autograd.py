@@ -53,6 +53,13 @@ def _to_bf16(t):
     return o
 
 
+def _split3(x, n, c, hw):
+    """fp32 blocked [N][C/8][HW][8] -> bf16 [N][3C/8][HW][8] = [hi | hi | lo] (uncl_split_bf16)."""
+    xs = torch.empty((n, 3 * c // 8) + tuple(x.shape[2:]), device=x.device, dtype=torch.bfloat16)
+    call("uncl_split_bf16", x, x.stride(0), xs, xs.stride(0), n, c, hw)
+    return xs
+
+
 class Conv3x3(Function):
     """nn.Conv2d(k=3, valid) or nn.ConvTranspose2d(k=3, s=1, p=0) (+ReLU).  unet_parts.py:57-87, 126-141, 183-193.
 
@@ -70,7 +77,13 @@ class Conv3x3(Function):
         y = _empty((n, co // 8, ho, wo, 8), x)
         b = bias.detach().float().contiguous()
         act = ACT_RELU if relu else ACT_NONE
-        if tc:
+        if tc == "split":
+            # exact path on the tensor cores: [x_hi | x_hi | x_lo] against [w_hi ; w_lo ; w_hi], fp32 accumulation (~2^-16)
+            xs = _split3(x, n, ci, h * w)
+            call("uncl_conv3x3_tc", xs, xs.stride(0), packing.conv3x3_tc_split(w9), b, y, y.stride(0), F32, n, 3 * ci, h, w, co,
+                 pad, act, 0, 0, None, None, None, None)
+            x = xs   # the backward reads the hi / lo thirds of the split copy (weight gradient on the tensor cores)
+        elif tc:
             xb = _to_bf16(x)
             call("uncl_conv3x3_tc", xb, xb.stride(0), packing.conv3x3_tc(w9), b, y, y.stride(0), F32, n, ci, h, w, co, pad,
                  act, 0, 0, None, None, None, None)
@@ -90,11 +103,30 @@ class Conv3x3(Function):
         ho, wo = y.shape[2], y.shape[3]
         dy = dy.contiguous()
         db = _zeros(co, dy)
+        split = tc == "split"
         # one pass: ReLU mask + bias gradient + the operand the gradient GEMMs read (bf16 on the tensor-core path)
-        dz = torch.empty(dy.shape, device=dy.device, dtype=torch.bfloat16 if tc else torch.float32)
-        call("uncl_relu_bwd_bias_out", dy, y, y.stride(0), dz, BF16 if tc else F32, db, n, co, ho * wo, 1 if relu else 0)
+        dz = torch.empty(dy.shape, device=dy.device, dtype=torch.bfloat16 if (tc and not split) else torch.float32)
+        call("uncl_relu_bwd_bias_out", dy, y, y.stride(0), dz, BF16 if (tc and not split) else F32, db, n, co, ho * wo,
+             1 if relu else 0)
         dx = None
         dzb = dz
+        if split:
+            dzs = _split3(dz, n, co, ho * wo)     # [dz_hi | dz_hi | dz_lo]
+            if ctx.needs_input_grad[0]:
+                wt = w9.flip(0).transpose(1, 2).contiguous()
+                dx = torch.empty((n, ci // 8, h, w, 8), device=dy.device, dtype=torch.float32)
+                call("uncl_conv3x3_tc", dzs, dzs.stride(0), packing.conv3x3_tc_split(wt), _zeros(ci, dy), dx, dx.stride(0), F32,
+                     n, 3 * co, ho, wo, ci, 2 - pad, ACT_NONE, 0, 0, None, None, None, None)
+            dw9 = _zeros((9, ci, co), dy)
+            cb, cob = ci // 8, co // 8
+            x_hi, x_lo, z_hi, z_lo = x[:, :cb], x[:, 2 * cb:], dzs[:, :cob], dzs[:, 2 * cob:]
+            for xa, za in ((x_hi, z_hi), (x_hi, z_lo), (x_lo, z_hi)):   # three-term split, accumulated by the kernel's atomics
+                call("uncl_conv3x3_wgrad_tc_strided", xa, x.stride(0), za, dzs.stride(0), dw9, n, ci, h, w, co, pad)
+            if transposed:
+                dw = dw9.reshape(3, 3, ci, co).permute(2, 3, 0, 1).flip(2, 3)
+            else:
+                dw = dw9.reshape(3, 3, ci, co).permute(3, 2, 0, 1)
+            return dx, dw.contiguous(), db, None, None, None
         if ctx.needs_input_grad[0]:
             # dgrad of a correlation with pad p = correlation of dz with pad 2-p and the taps reversed / transposed
             wt = w9.flip(0).transpose(1, 2).contiguous()

@@ -441,6 +441,14 @@ extern "C" int uncl_conv3x3_wgrad_tc(const void* X, long x_img_stride, const voi
                        0, stream);
 }
 
+// The same with an explicit dZ image stride (elements): dZ may be a channel slice of a wider tensor - the exact path's
+// three-term split passes the hi / lo thirds of [dz_hi | dz_hi | dz_lo] (uncl_split_bf16) without copying them out.
+extern "C" int uncl_conv3x3_wgrad_tc_strided(const void* X, long x_img_stride, const void* dZ, long dz_img_stride, float* dW9,
+                                             int N, int C_in, int H, int W, int C_out, int pad, cudaStream_t stream) {
+  UNCL_REQUIRE(dz_img_stride % 8 == 0, "conv3x3_wgrad_tc_strided: dZ stride must be a multiple of 8");
+  return wgrad_tc_impl(X, x_img_stride, dZ, dz_img_stride, dW9, N, C_in, H, W, C_out, pad, 0, stream);
+}
+
 // Pointwise (1x1 / GEMM) weight gradient on the same kernel with one tap:  dW[ci][co] += sum_pix X[pix, ci] * dZ[pix, co].
 // The k2 s2 up-convolution's weight gradient is this GEMM over the space-to-depth output gradient (C_out = 4C).
 // X: bf16 blocked [N][C_in/8][H][W][8]; dZ: bf16 blocked [N][C_out/8][H][W][8]; both with their own image strides.

@@ -358,7 +358,10 @@ class _GeneratorBase(nn.Module):
         kernels with bf16-rounded operands and fp32 accumulation; every tensor between kernels is fp32.
         prev / want_state: recurrent channel hand-over of the video generator (Unet.py:229-286)."""
         from . import autograd as A
-        tc = self.precision == "bf16"
+        # 'fp32_tc': the 3x3 convolutions (98 % of the FLOPs; forward, data and weight gradients) as three-term bf16 split
+        # GEMMs on the tensor cores (~2^-16 per product), everything else on the fp32 CUDA-core kernels
+        tc = True if self.precision == "bf16" else ("split" if self.precision == "fp32_tc" else False)
+        tc_other = tc is True   # up-convs and the graph block: tensor cores only on the mixed path
         if x.dim() != 4 or tuple(x.shape[1:]) != (1, 256, 256) or not x.is_cuda:
             raise ValueError("the generator expects CUDA [N,1,256,256] inputs")
         n = x.shape[0]
@@ -380,16 +383,16 @@ class _GeneratorBase(nn.Module):
         y = A.PwConv.apply(x0, g.fc1[0].weight, g.fc1[0].bias, None, None, 1, False, False)   # feeds KNN: fp32
         z = A.KnnAggregate.apply(y, g.relative_pos.detach().reshape(144, 144).float().contiguous())
         gc = g.graph_conv.gconv.nn[0]
-        z2 = A.PwConv.apply(z, gc.weight, gc.bias, None, None, 4, True, tc)
-        x1 = A.PwConv.apply(z2, g.fc2[0].weight, g.fc2[0].bias, x0, s0, 1, False, tc)
-        f1 = A.PwConv.apply(x1, ffn.fc1[0].weight, ffn.fc1[0].bias, None, None, 1, True, tc)
-        up = A.PwConv.apply(f1, ffn.fc2[0].weight, ffn.fc2[0].bias, x1, s1, 1, False, tc).reshape(n, -1, 12, 12, 8)
+        z2 = A.PwConv.apply(z, gc.weight, gc.bias, None, None, 4, True, tc_other)
+        x1 = A.PwConv.apply(z2, g.fc2[0].weight, g.fc2[0].bias, x0, s0, 1, False, tc_other)
+        f1 = A.PwConv.apply(x1, ffn.fc1[0].weight, ffn.fc1[0].bias, None, None, 1, True, tc_other)
+        up = A.PwConv.apply(f1, ffn.fc2[0].weight, ffn.fc2[0].bias, x1, s1, 1, False, tc_other).reshape(n, -1, 12, 12, 8)
         state.append(up)
         for i in range(4):
             u = self.up_path[i]
             sk = skips[3 - i]
             fea = up if prev is None else A.SpliceChannels.apply(up, prev[5 + i], up.shape[1] * 8 // 32)
-            x1u = A.ConvT2x2.apply(fea, u.up.weight, u.up.bias, sk.shape[2], sk.shape[3], tc)
+            x1u = A.ConvT2x2.apply(fea, u.up.weight, u.up.bias, sk.shape[2], sk.shape[3], tc_other)
             cat = A.SkipConcat.apply(sk, x1u)
             m = A.Conv3x3.apply(cat, u.conv.conv.weight, u.conv.conv.bias, True, True, tc)
             up = A.Conv3x3.apply(m, u.conv.conv1.weight, u.conv.conv1.bias, True, True, tc)
