@@ -76,12 +76,14 @@ def test_conv3x3_tensor_core_path(ci, co, h, transposed):
     assert rel(wc.grad, wr.grad) < 1e-5 and rel(bc.grad, br.grad) < 1e-5
 
 
-@pytest.mark.parametrize("ci,co,h,transposed,relu", [(32, 32, 40, False, True), (64, 128, 30, False, True), (128, 32, 66, True, True),
-                                                    (256, 256, 12, False, False), (512, 64, 29, True, True)])
-def test_conv3x3_exact_split_path(ci, co, h, transposed, relu):
+@pytest.mark.parametrize("ci,co,h,transposed", [(32, 32, 40, False), (64, 128, 30, False), (128, 32, 66, True),
+                                               (256, 256, 12, False), (512, 64, 29, True)])
+def test_conv3x3_exact_split_path(ci, co, h, transposed):
     """tc="split" (precision 'fp32_tc'): forward, data gradient and weight gradient as three-term bf16 split GEMMs on the
     tensor cores with UNROUNDED fp32 inputs against float64 - ~2^-16 per product, i.e. fp32-grade results (the bf16 path
-    on the same inputs would sit at ~4e-3)."""
+    on the same inputs would sit at ~4e-3).  No ReLU: a pre-activation within 1e-5 of 0 would take a different side of the
+    mask on the two sides (the mask itself is covered by test_conv3x3)."""
+    relu = False
     x = rnd(2, ci, h, h + 2, seed=1)
     w = rnd(*((ci, co, 3, 3) if transposed else (co, ci, 3, 3)), seed=2, scale=(9 * ci) ** -0.5)
     b = rnd(co, seed=3, scale=0.1)

@@ -329,6 +329,17 @@ def forward_train(net, x, droppath_scale, prev=None):
     return out, up, S
 
 
+SIDE_STREAM_WGRAD = True
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
 def backward_train(S, d_out, d_feat, through_autograd=False):
     """One image batch: begin, the frame's backward, the final gradient un-packing."""
     S.fp.begin_backward(through_autograd)
@@ -359,8 +370,27 @@ def backward_frame(S, d_out, d_feat, d_state):
     def st(t):
         return t.stride(0)
 
+    # Weight and bias gradients are leaves of the backward: nothing downstream reads them before the final un-packing.
+    # They run on a second stream next to the data-gradient chain (which, at 16 images, leaves most SMs idle on the deeper
+    # layers); inside a CUDA-graph capture this becomes a parallel branch of the graph.  Joined before this frame returns.
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev) if SIDE_STREAM_WGRAD else None
+    if side is not None:
+        side.wait_stream(main)
+
+    def aside(fn, *deps):
+        if side is None:
+            return fn()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        for t in deps:
+            t.record_stream(side)
+        with torch.cuda.stream(side):
+            fn()
+
     def wgrad(name, x, ci, h, dz, co, pad):
-        call("uncl_conv3x3_wgrad_tc", x, st(x), dz, fp.stage_view(name, 9 * ci * co), n, ci, h, h, co, pad)
+        aside(lambda: call("uncl_conv3x3_wgrad_tc", x, st(x), dz, fp.stage_view(name, 9 * ci * co), n, ci, h, h, co, pad), x, dz)
 
     def dgrad(name, dz, ci_d, h_d, co_d, pad_d, mask, out_dtype=torch.bfloat16):
         """data gradient of layer `name`: dz [n, ci_d, h_d] -> [n, co_d, h_d + 2*pad_d - 2], masked by `mask` (> 0)"""
@@ -371,7 +401,7 @@ def backward_frame(S, d_out, d_feat, d_state):
         return o
 
     def bias_grad(dz, key, c, hw):
-        call("uncl_bias_grad_bf16", dz, st(dz), fp.g(key + ".bias"), n, c, hw)
+        aside(lambda: call("uncl_bias_grad_bf16", dz, st(dz), fp.g(key + ".bias"), n, c, hw), dz)
 
     f = 32
     # ---- out conv + sigmoid + feature gradient + ReLU of up3.conv1
@@ -399,8 +429,9 @@ def backward_frame(S, d_out, d_feat, d_state):
         s2d = _bf((n, 4 * c_up // 8, h_up, h_up, 8), dev)
         call("uncl_convT2x2_s2d_bf16", dcat[:, sk_c // 8:], st(dcat), s2d, fp.g("up_path.%d.up.bias" % i), n, c_up, h_up, h_up,
              sk_s, sk_s)
-        call("uncl_pw_wgrad_tc", up_in, st(up_in), s2d, st(s2d), fp.stage_view("u%d_up" % i, 4 * c_up * c_up), n, c_up,
-             4 * c_up, h_up, h_up)
+        aside(lambda up_in=up_in, s2d=s2d, c_up=c_up, h_up=h_up, i=i: call(
+            "uncl_pw_wgrad_tc", up_in, st(up_in), s2d, st(s2d), fp.stage_view("u%d_up" % i, 4 * c_up * c_up), n, c_up, 4 * c_up,
+            h_up, h_up), up_in, s2d)
         r_up = c_up // 32
         if i > 0:
             dz = _bf((n, c_up // 8, h_up, h_up, 8), dev)
@@ -462,6 +493,8 @@ def backward_frame(S, d_out, d_feat, d_state):
     wgrad("inc1", S.a0, f, 254, dz, f, 0)
     dz_a0 = dgrad("inc1", dz, f, 252, f, 2, S.a0)
     call("uncl_conv_first_wgrad_bias", S.x, dz_a0, BF16, fp.stage_view("inc0", 9 * f), fp.g("inc.conv.conv.bias"), n, 256, 256, f)
+    if side is not None:
+        main.wait_stream(side)
     return d_prev
 
 
