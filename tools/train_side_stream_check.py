@@ -5,13 +5,24 @@ sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 sys.argv = ["bench"]
 import torch
 import bench
-from uncltmo_b200 import train_graph
+from uncltmo_b200 import train_graph, trainer
 dev = torch.device("cuda:0")
+_init = trainer.GanTrainerStep.__init__
+OVERLAP = [True]
+
+
+def _patched(self, *a, **k):
+    _init(self, *a, **k)
+    self.overlap_g_forward = OVERLAP[0]
+
+
+trainer.GanTrainerStep.__init__ = _patched
 with torch.enable_grad():
     for rep in range(2):
-        for flag in (False, True):
+        for flag, ov in ((False, False), (True, False), (True, True)):
             train_graph.SIDE_STREAM_WGRAD = flag
+            OVERLAP[0] = ov
             r = bench.train_workload(dev, "bf16", 20, 5, 1, 0)
-            print("side stream %-5s  %.1f steps/s  %.3f ms" % (flag, r["value"], r["ms_per_step"]), flush=True)
+            print("wgrad side stream %-5s  G forward next to the D step %-5s  %.1f steps/s  %.3f ms" % (flag, ov, r["value"], r["ms_per_step"]), flush=True)
     r = bench.train_workload(dev, "bf16", 5, 3, 1, 0, video=True)
     print("video, side stream on: %.1f steps/s" % r["value"])

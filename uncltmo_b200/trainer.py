@@ -45,6 +45,12 @@ class GanTrainerStep:
         self.struct_loss = StructLoss(self.pyramid_weight_list)
         self.errD = self.errG_d = self.errG_struct = None
         self._side = None
+        self._side_g = None
+        self._loss_streams = []
+        # bf16 path: run train_G's generator forward on a second stream NEXT TO the whole D step (it depends on nothing the
+        # D step produces - the D step's own generator pass is a separate, gradient-free forward with its own DropPath
+        # masks, as in the reference); at 16 images neither chain fills the GPU
+        self.overlap_g_forward = True
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         # generator gradients (19.7 MB) are reduced bucket by bucket WHILE backward is still running (hooks)
         self.buckets_G = GradientBuckets(netG.parameters()).install_hooks() if self.world > 1 else None
@@ -94,12 +100,55 @@ class GanTrainerStep:
         self.optimizerD.step()
         return self.errD
 
+    # ------------------------------------------------------------------ independent loss branches on their own streams
+    def _fork(self, idx, fn, *inputs):
+        """Run `fn` (a loss term that depends only on `inputs`) on side stream `idx` while the caller continues.  Only inside a
+        CUDA-graph capture: there the terms become parallel branches of the graph (forward AND backward - autograd runs a
+        node's backward on its forward's stream), which matters because every term is a chain of 3-30 us kernels; eager
+        launches are CPU-bound and would gain nothing.  Returns a handle for `_get`."""
+        if not torch.cuda.is_current_stream_capturing():
+            return (None, fn())
+        cur = torch.cuda.current_stream()
+        while len(self._loss_streams) <= idx:
+            self._loss_streams.append(torch.cuda.Stream())
+        s = self._loss_streams[idx]
+        s.wait_stream(cur)
+        for t in inputs:
+            if t is not None:
+                t.record_stream(s)
+        with torch.cuda.stream(s):
+            out = fn()
+        return (s, out)
+
+    @staticmethod
+    def _get(handle):
+        s, out = handle
+        if s is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(s)
+            for t in (out if isinstance(out, (tuple, list)) else (out,)):
+                t.record_stream(cur)
+        return out
+
     # ------------------------------------------------------------------ G step
+    def image_terms(self, fea_fake, fake, hdr_input, ldr_pos, epoch):
+        """The terms of update_g_d_loss that read only the generator's outputs (not the discriminator's): started right
+        after the generator forward, each on its own branch (`_fork`), next to the D(fake) pass."""
+        if epoch <= self.epoch_step2:
+            return {"nce2": self._fork(0, lambda: losses.infoNCE2(fea_fake, fake, hdr_input, "InfoNCE", 1, 1e-2), fea_fake, fake),
+                    "l1": self._fork(1, lambda: losses.l1_mean_terms(fake, ldr_pos), fake, ldr_pos),
+                    "pseudo": self._fork(2, lambda: losses.pseudo_label_loss(fake, hdr_input), fake)}
+        return {"l1": self._fork(1, lambda: losses.l1_mean_terms(fake, ldr_pos), fake, ldr_pos),
+                "pseudo": self._fork(2, lambda: losses.pseudo_label_loss(fake, hdr_input), fake),
+                "tv": self._fork(0, lambda: losses.L_TV()(fake), fake)}
+
     def g_d_loss(self, d_fake_bp, d_real_pos_bp, d_fea_fake, d_fea_real_pos, d_fea_real_neg, d_fea_input, fea_fake, fake,
-                 hdr_input, ldr_pos, epoch):
+                 hdr_input, ldr_pos, epoch, terms=None):
         """update_g_d_loss (GanTrainerImg.py:302-339) without the backward call."""
         f = self.loss_g_d_factor
         s = 1.0 / self.world   # per-sample-mean terms: local mean * (local / global batch)
+        if terms is None:
+            terms = self.image_terms(fea_fake, fake, hdr_input, ldr_pos, epoch)
         gathered = losses.contrastive_D_loss(all_gather_cat(d_fake_bp), all_gather_cat(d_real_pos_bp))
         if epoch <= self.epoch_step2:
             first = epoch <= self.epoch_step1
@@ -107,21 +156,22 @@ class GanTrainerStep:
             f = f * s
             err = err + f * 0.5 * losses.infoNCE(d_fea_fake, d_fea_real_pos, d_fea_input, fake, hdr_input, "InfoNCE", 1, 1e-2)
             err = err + f * 0.5 * 0.2 * losses.infoNCE(d_fea_fake, d_fea_real_pos, d_fea_real_neg, fake, hdr_input, "InfoNCE", 1e3, 2)
-            err = err + f * (1e-6 if first else 0.5) * losses.infoNCE2(fea_fake, fake, hdr_input, "InfoNCE", 1, 1e-2)
-            l_mean, l_con = losses.l1_mean_terms(fake, ldr_pos)
+            err = err + f * (1e-6 if first else 0.5) * self._get(terms["nce2"])
+            l_mean, l_con = self._get(terms["l1"])
             err = err + f * (1e-6 if first else 0.5 * 1e2) * l_mean
             err = err + f * (1e-6 if first else 0.5 * 2) * l_con
-            err = err + f * 1e-6 * losses.pseudo_label_loss(fake, hdr_input)
+            err = err + f * 1e-6 * self._get(terms["pseudo"])
         else:
             err = f * 1e-6 * gathered
             f = f * s
-            l_mean, _ = losses.l1_mean_terms(fake, ldr_pos)
+            l_mean, _ = self._get(terms["l1"])
             err = err + f * 0.5 * 1e2 * l_mean
-            err = err + f * 0.5 * 1e2 * losses.pseudo_label_loss(fake, hdr_input)
-            err = err + f * 0.2 * 1e5 * losses.L_TV()(fake)
+            err = err + f * 0.5 * 1e2 * self._get(terms["pseudo"])
+            err = err + f * 0.2 * 1e5 * self._get(terms["tv"])
         return err
 
-    def train_G(self, hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch):
+    def train_G(self, hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch, generated=None):
+        """generated: (fake, fea_fake) of THIS step's generator forward when `step` already ran it next to the D step."""
         self.netG.zero_grad(set_to_none=True)
         hdr = self._flat(hdr_input)
         pos, neg = self._flat(real_ldr_pos), self._flat(real_ldr_neg)
@@ -139,17 +189,21 @@ class GanTrainerStep:
             nb = pos.shape[0]
             lg, fe = self.netD(torch.cat([pos, neg, hdr]))      # one pass over the three gradient-free batches
             d_real_pos_bp, d_fea_real_pos, d_fea_real_neg, d_fea_input = lg[:nb], fe[:nb], fe[nb:2 * nb], fe[2 * nb:]
-        fake, fea_fake = self._generate(hdr_input)
+        fake, fea_fake = generated if generated is not None else self._generate(hdr_input)
         if fork:
             cur.wait_stream(self._side)
             for t in (d_real_pos_bp, d_fea_real_pos, d_fea_real_neg, d_fea_input):
                 t.record_stream(cur)
+        # the loss terms that only read the generator's outputs start now, as parallel branches next to D(fake)
+        terms = self.image_terms(fea_fake, fake, hdr, pos, epoch)
+        struct = self._fork(3, lambda: self.struct_loss(fake, None, hdr, self.pyramid_weight_list), fake, hdr) \
+            if self.struct_loss_factor else None
         d_fake_bp, d_fea_fake = self.netD(fake)
         self.errG_d = self.g_d_loss(d_fake_bp, d_real_pos_bp, d_fea_fake, d_fea_real_pos, d_fea_real_neg, d_fea_input,
-                                    fea_fake, fake, hdr, pos, epoch)
+                                    fea_fake, fake, hdr, pos, epoch, terms)
         total = self.errG_d
-        if self.struct_loss_factor:
-            self.errG_struct = (self.struct_loss_factor / self.world) * self.struct_loss(fake, None, hdr, self.pyramid_weight_list)
+        if struct is not None:
+            self.errG_struct = (self.struct_loss_factor / self.world) * self._get(struct)
             total = total + self.errG_struct
         flat_mode = self.world > 1 and self._generator_is_flat()
         if self.buckets_G is not None and not flat_mode:
@@ -168,8 +222,24 @@ class GanTrainerStep:
 
     def step(self, hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch):
         """One iteration of GanTrainer.train_epoch's loop body (GanTrainerImg.py:178-186)."""
+        generated = None
+        if self.overlap_g_forward and getattr(self.netG, "precision", None) == "bf16" and hasattr(self.netG, "forward_blocked") \
+                and torch.is_grad_enabled():
+            from .train_graph import flat_params
+            cur = torch.cuda.current_stream()
+            flat_params(self.netG).pack()          # both generator passes read the packed weights: pack before the fork
+            if self._side_g is None:
+                self._side_g = torch.cuda.Stream()
+            self._side_g.wait_stream(cur)
+            with torch.cuda.stream(self._side_g):
+                generated = self._generate(hdr_input)
         self.train_D(hdr_input, real_ldr_pos, real_ldr_neg, epoch)
-        return self.train_G(hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch)
+        if generated is not None:
+            cur.wait_stream(self._side_g)
+            for t in generated:
+                if t is not None:
+                    t.record_stream(cur)
+        return self.train_G(hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch, generated)
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole iteration
     def _invalidate_packed(self):
