@@ -106,7 +106,8 @@ class GanTrainerStep:
         CUDA-graph capture: there the terms become parallel branches of the graph (forward AND backward - autograd runs a
         node's backward on its forward's stream), which matters because every term is a chain of 3-30 us kernels; eager
         launches are CPU-bound and would gain nothing.  Returns a handle for `_get`."""
-        if not torch.cuda.is_current_stream_capturing():
+        # (single GPU only: with several ranks some terms contain collectives, which stay on the main stream in program order)
+        if self.world > 1 or not torch.cuda.is_current_stream_capturing():
             return (None, fn())
         cur = torch.cuda.current_stream()
         while len(self._loss_streams) <= idx:
@@ -170,8 +171,9 @@ class GanTrainerStep:
             err = err + f * 0.2 * 1e5 * self._get(terms["tv"])
         return err
 
-    def train_G(self, hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch, generated=None):
-        """generated: (fake, fea_fake) of THIS step's generator forward when `step` already ran it next to the D step."""
+    def train_G(self, hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch, generated=None, early=None):
+        """generated: (fake, fea_fake) of THIS step's generator forward when `step` already ran it next to the D step;
+        early: the (terms, struct) branch handles `step` forked from that forward."""
         self.netG.zero_grad(set_to_none=True)
         hdr = self._flat(hdr_input)
         pos, neg = self._flat(real_ldr_pos), self._flat(real_ldr_neg)
@@ -195,9 +197,12 @@ class GanTrainerStep:
             for t in (d_real_pos_bp, d_fea_real_pos, d_fea_real_neg, d_fea_input):
                 t.record_stream(cur)
         # the loss terms that only read the generator's outputs start now, as parallel branches next to D(fake)
-        terms = self.image_terms(fea_fake, fake, hdr, pos, epoch)
-        struct = self._fork(3, lambda: self.struct_loss(fake, None, hdr, self.pyramid_weight_list), fake, hdr) \
-            if self.struct_loss_factor else None
+        if early is not None:
+            terms, struct = early
+        else:
+            terms = self.image_terms(fea_fake, fake, hdr, pos, epoch)
+            struct = self._fork(3, lambda: self.struct_loss(fake, None, hdr, self.pyramid_weight_list), fake, hdr) \
+                if self.struct_loss_factor else None
         d_fake_bp, d_fea_fake = self.netD(fake)
         self.errG_d = self.g_d_loss(d_fake_bp, d_real_pos_bp, d_fea_fake, d_fea_real_pos, d_fea_real_neg, d_fea_input,
                                     fea_fake, fake, hdr, pos, epoch, terms)
@@ -231,15 +236,25 @@ class GanTrainerStep:
             if self._side_g is None:
                 self._side_g = torch.cuda.Stream()
             self._side_g.wait_stream(cur)
+            early = None
             with torch.cuda.stream(self._side_g):
                 generated = self._generate(hdr_input)
+                if self.world == 1 and torch.cuda.is_current_stream_capturing():
+                    # the loss terms that read only the generator's outputs branch off here, next to the D step as well
+                    fake, fea_fake = generated
+                    hdr, pos = self._flat(hdr_input), self._flat(real_ldr_pos)
+                    terms = self.image_terms(fea_fake, fake, hdr, pos, epoch)
+                    struct = self._fork(3, lambda: self.struct_loss(fake, None, hdr, self.pyramid_weight_list), fake, hdr) \
+                        if self.struct_loss_factor else None
+                    early = (terms, struct)
         self.train_D(hdr_input, real_ldr_pos, real_ldr_neg, epoch)
         if generated is not None:
             cur.wait_stream(self._side_g)
             for t in generated:
                 if t is not None:
                     t.record_stream(cur)
-        return self.train_G(hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch, generated)
+            return self.train_G(hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch, generated, early)
+        return self.train_G(hdr_input, hdr_original_gray_norm, real_ldr_pos, real_ldr_neg, epoch)
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole iteration
     def _invalidate_packed(self):
