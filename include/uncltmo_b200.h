@@ -418,7 +418,8 @@ int uncl_l1_mean_bwd(const float* a, const float* b, int n, const float* g_up, f
 int uncl_tv_bwd(const float* x, int B, int C, int H, int W, const float* g_up, float* dx, uncl_stream_t stream);
 /* SimpleDiscriminator backward (models/Discriminator.py:98-126).  d_fea [N][62][62] holds the gradient arriving
  * through the feature branch on entry (zeros if none); the tail's contribution is added.  dx may be NULL.
- * dw3 / db3 must be zeroed by the caller.  scratch: N*(32*62*62 + 16*127*127) floats. */
+ * dw3 / db3 must be zeroed by the caller.  dw1 / db1 and dw2 / db2 may be NULL: the two convolutions' weight gradients are
+ * then skipped (back-propagation THROUGH the discriminator in the generator step).  scratch: N*(32*62*62 + 16*127*127) floats. */
 int uncl_disc_backward(const float* x, const float* h1, const float* a2, const float* fea, const float* w1,
                        const float* w2, const float* w3, const float* w_tail, const float* d_logits, float* d_fea,
                        float* dx, float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3,

@@ -223,10 +223,16 @@ class DiscFn(Function):
         dfe = _f(d_fea).clone() if d_fea is not None else torch.zeros_like(fea)
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         z = lambda *s: torch.zeros(s, device=dev, dtype=torch.float32)  # noqa: E731
-        dw1, db1, dw2, db2, dw3, db3, dwt = z(16, 1, 4, 4), z(16), z(32, 16, 4, 4), z(32), z(1, 32, 1, 1), z(1), z(1, 62 * 62)
+        want_w = any(ctx.needs_input_grad[1:])
+        dw3, db3, dwt = z(1, 32, 1, 1), z(1), z(1, 62 * 62)
+        # parameters frozen by the caller (the generator step back-propagates THROUGH the discriminator): the two
+        # convolutions' weight gradients - a third of the backward's time - are not computed
+        dw1, db1, dw2, db2 = (z(16, 1, 4, 4), z(16), z(32, 16, 4, 4), z(32)) if want_w else (None, None, None, None)
         scratch = torch.empty(n * (32 * 62 * 62 + 16 * 127 * 127), device=dev, dtype=torch.float32)
         call("uncl_disc_backward", x, h1, a2, fea, w1, w2, w3, wt, _f(d_logits) if d_logits is not None else None, dfe, dx,
              dw1, db1, dw2, db2, dw3, db3, dwt, scratch, n)
+        if not want_w:
+            return dx, None, None, None, None, None, None, None
         return dx, dw1, db1, dw2, db2, dw3, db3, dwt
 
 

@@ -678,13 +678,17 @@ extern "C" int uncl_disc_backward(const float* x, const float* h1, const float* 
   disc_top_bwd_kernel<<<cap_grid((long)N * P, 256, 2), 256, 0, stream>>>(d_fea, a2, w3, d_z2, dw3, db3, P, N);
   const int ctas = 148 * 2;
   const long t2 = (long)N * H2 * H2;
-  conv4s2_wgrad_kernel<16, 32><<<ctas, 256, 0, stream>>>(h1, d_z2, dw2, db2, H1, H1, H2, H2, t2, (t2 + ctas - 1) / ctas);
+  // dw2 / dw1 == NULL: the caller does not want the convolutions' weight gradients (the generator step back-propagates
+  // THROUGH the discriminator only; its parameter gradients would be thrown away by the next zero_grad)
+  if (dw2 != nullptr)
+    conv4s2_wgrad_kernel<16, 32><<<ctas, 256, 0, stream>>>(h1, d_z2, dw2, db2, H1, H1, H2, H2, t2, (t2 + ctas - 1) / ctas);
   cudaError_t e = cudaFuncSetAttribute(conv4s2_dgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 16 * 16 * 4);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "disc_backward: %s", cudaGetErrorString(e));
   const long q1 = (long)N * 64 * 64;   // pixels per parity class (upper bound)
   conv4s2_dgrad_kernel<16><<<dim3(cap_grid(q1, 256, 2), 4), 256, 32 * 16 * 16 * 4, stream>>>(d_z2, w2, h1, d_z1, 32, H1, H1, H2, H2, N);
   const long t1 = (long)N * H1 * H1;
-  conv4s2_wgrad_kernel<1, 16><<<ctas, 256, 0, stream>>>(x, d_z1, dw1, db1, H, H, H1, H1, t1, (t1 + ctas - 1) / ctas);
+  if (dw1 != nullptr)
+    conv4s2_wgrad_kernel<1, 16><<<ctas, 256, 0, stream>>>(x, d_z1, dw1, db1, H, H, H1, H1, t1, (t1 + ctas - 1) / ctas);
   if (dx) {
     const long q0 = (long)N * 128 * 128;
     conv4s2_dgrad_kernel<1><<<dim3(cap_grid(q0, 256, 4), 4), 256, 16 * 16 * 4, stream>>>(d_z1, w1, nullptr, dx, 16, H, H, H1, H1, N);

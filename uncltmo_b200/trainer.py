@@ -9,6 +9,8 @@ changes a gradient that reaches an optimizer:
     (the reference builds the graphs and throws them away; `D(real_neg)` of the D step is computed and never used
     there - GanTrainerImg.py:237 - and is skipped here);
   * errG_d and errG_struct are summed and back-propagated once instead of twice with retain_graph=True;
+  * the generator step back-propagates through the discriminator without forming the discriminator's own parameter
+    gradients (the reference accumulates them and zeroes them unread at the start of the next train_D);
   * the TMQI naturalness that picks positives / negatives / the pseudo label is computed on the device
     (the reference makes 80 host numpy calls per step), so a step has no host synchronisation;
   * the `epoch > epoch_step2` branch uses L_TV from GanTrainer.py:669-682 (the image trainer references an undefined
@@ -203,7 +205,16 @@ class GanTrainerStep:
             terms = self.image_terms(fea_fake, fake, hdr, pos, epoch)
             struct = self._fork(3, lambda: self.struct_loss(fake, None, hdr, self.pyramid_weight_list), fake, hdr) \
                 if self.struct_loss_factor else None
-        d_fake_bp, d_fea_fake = self.netD(fake)
+        # back-propagation THROUGH the discriminator: its own parameter gradients would be zeroed unread by the next train_D
+        # (GanTrainerImg.py:201), so they are not computed (a third of the discriminator backward)
+        d_params = [p for p in self.netD.parameters() if p.requires_grad]
+        for p in d_params:
+            p.requires_grad_(False)
+        try:
+            d_fake_bp, d_fea_fake = self.netD(fake)
+        finally:
+            for p in d_params:
+                p.requires_grad_(True)
         self.errG_d = self.g_d_loss(d_fake_bp, d_real_pos_bp, d_fea_fake, d_fea_real_pos, d_fea_real_neg, d_fea_input,
                                     fea_fake, fake, hdr, pos, epoch, terms)
         total = self.errG_d
