@@ -1,6 +1,7 @@
 """Workload for compute-sanitizer (memcheck / racecheck / synccheck): one small bf16 frame through the whole frame path
 (tensor-core convs with their mbarrier pipelines and TMEM allocation, the cooperative grid-barrier percentile select,
-blend, post-process) and one mixed-precision training step on 2 images (tensor-core dgrad / wgrad with fp32 atomics,
+blend, post-process - as the three fused cooperative stage kernels, as the staged path, and with the skip operators fused
+into the consuming convs) and one mixed-precision training step on 2 images (tensor-core dgrad / wgrad with fp32 atomics,
 discriminator, every loss forward + backward).
 
     compute-sanitizer --tool memcheck  python tools/sanitize_run.py            > profiles/r2_sanitizer_memcheck.txt
@@ -28,9 +29,18 @@ if what in ("all", "frame"):
     net.load_state_dict(make_generator_state_dict())
     rgb = torch.from_numpy(synth.hdr_frame(268, 300, seed=5)).cuda()
     with torch.no_grad():
-        u8 = FramePipeline(net).tonemap(rgb, 50.0, uint8=True)
+        pipe = FramePipeline(net)
+        u8 = pipe.tonemap(rgb, 50.0, uint8=True)          # fused cooperative stage kernels
+        torch.cuda.synchronize()
+        print("frame ok:", tuple(u8.shape), int(u8.min()), int(u8.max()))
+        pipe.fused = False                                 # the staged 14-launch path
+        u8s = pipe.tonemap(rgb, 50.0, uint8=True)
+        net.fused_skip = True                              # skip operators built inside the consuming conv (ring program)
+        pipe.fused = True
+        u8f = pipe.tonemap(rgb, 50.0, uint8=True)
     torch.cuda.synchronize()
-    print("frame ok:", tuple(u8.shape), int(u8.min()), int(u8.max()))
+    print("staged == fused:", bool(torch.equal(u8, u8s)), " fused-skip max |diff| (8-bit levels):",
+          int((u8f.int() - u8.int()).abs().max()))
 
 if what in ("all", "train"):
     netG = UNet(*G_ARGS, up_mode=0, precision="bf16").cuda().train()
