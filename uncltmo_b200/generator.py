@@ -64,11 +64,12 @@ class _GeneratorBase(nn.Module):
         if precision not in ("fp32", "bf16", "fp32_tc"):
             raise ValueError("precision must be 'fp32', 'bf16' or 'fp32_tc'")
         self.precision = precision
-        # bf16 inference option: skip^2 / sqrt(skip + eps) of the two largest levels built inside the consuming conv instead of
-        # being written by the producer (uncl_conv3x3_tc_skipcat).  Halves those layers' DRAM traffic; measured net-neutral in
-        # time on B200 (the N' = 96 MMAs already saturate shared-memory bandwidth, which the in-kernel transform also needs:
-        # DESIGN.md section 9), so it is off by default.
-        self.fused_skip = False
+        # bf16 inference: skip^2 / sqrt(skip + eps) of the two largest levels are built inside the consuming conv instead of
+        # being written by the producer (uncl_conv3x3_tc_skipcat): 1.1 GB less DRAM traffic per 1080p frame.  Kernel for kernel
+        # the time is neutral (the in-kernel transform shares the shared-memory port the N' = 96 MMAs saturate: producers -76
+        # us, consumers +70 us), but back-to-back frames run at the 1 kW power cap, where the saved traffic buys clock:
+        # 485 -> 496 frames/s sustained (tools/fused_skip_sustained.py).  False = materialised planes.
+        self.fused_skip = True
         self.to_crop = to_crop
         self.depth = depth
         self.recurrent_ch_ratio = recurrent_ch_ratio
