@@ -175,6 +175,14 @@ def video_inference_workload(dev, precision, world, rank, frames=8, iters=2):
                                       "dealt round-robin over the ranks (each 8-bit frame is finished on one rank)" % world}}
 
 
+def _release():
+    """Drop the previous workload's networks, captured graphs and their private memory pools (reference cycles through
+    autograd contexts keep them alive until a collection) before the next workload allocates its own."""
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
 def train_workload(dev, precision, steps, warmup, world=1, rank=0, video=False, weak=False):
     """256x256 image-TMO training step, global batch 8x2 = 16 images (GanTrainerImg.train_D + train_G, epoch-0 loss
     schedule, Adam as main_train_image.py builds it).  Strong scaling: ranks split the 16 images."""
@@ -184,6 +192,7 @@ def train_workload(dev, precision, steps, warmup, world=1, rank=0, video=False, 
     from uncltmo_b200.trainer import GanTrainerStep
     from uncltmo_b200.weights import make_discriminator_state_dict, make_generator_state_dict
     import torch.distributed as dist
+    _release()
     netG = (UNetVideo if video else UNet)(*G_ARGS, up_mode=0, precision=precision).to(dev).train()
     netG.load_state_dict(make_generator_state_dict())
     netD = SimpleDiscriminator(256, 1, 16, "none", "none", 0, 0).to(dev).train()

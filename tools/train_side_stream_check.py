@@ -17,12 +17,14 @@ def _patched(self, *a, **k):
 
 
 trainer.GanTrainerStep.__init__ = _patched
+print("stream priority range", torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else "?")
 with torch.enable_grad():
     for rep in range(2):
-        for flag, ov in ((False, False), (True, False), (True, True)):
-            train_graph.SIDE_STREAM_WGRAD = flag
-            OVERLAP[0] = ov
+        for pm, pg in ((0, 0), (-3, -2), (-3, -3), (-2, -3)):
+            trainer.PRIO_MAIN, trainer.PRIO_G = pm, pg
             r = bench.train_workload(dev, "bf16", 20, 5, 1, 0)
-            print("wgrad side stream %-5s  G forward next to the D step %-5s  %.1f steps/s  %.3f ms" % (flag, ov, r["value"], r["ms_per_step"]), flush=True)
+            import gc; gc.collect(); torch.cuda.empty_cache()
+            print("mem allocated GB %.1f" % (torch.cuda.memory_allocated() / 2**30), flush=True)
+            print("priorities main %d generator %d  %.1f steps/s  %.3f ms" % (pm, pg, r["value"], r["ms_per_step"]), flush=True)
     r = bench.train_workload(dev, "bf16", 5, 3, 1, 0, video=True)
     print("video, side stream on: %.1f steps/s" % r["value"])

@@ -32,6 +32,11 @@ from .dist import GradientBuckets, all_gather_cat
 from .struct_loss import StructLoss
 
 
+# stream priorities of the captured iteration (lower = more urgent; clamped to the device's range): the main chain, the
+# generator's forward / data-gradient chain, everything else (weight gradients, loss branches, gradient-free D passes)
+PRIO_MAIN, PRIO_G = -3, -2
+
+
 class GanTrainerStep:
     def __init__(self, netG, netD, optimizerG, optimizerD, loss_g_d_factor=0.1, struct_loss_factor=1.0,
                  adv_weight_list=(0.2, 0.2, 0.2), pyramid_weight_list=(1.0, 1.0, 1.0), epoch_step1=6, epoch_step2=9):
@@ -245,7 +250,7 @@ class GanTrainerStep:
             cur = torch.cuda.current_stream()
             flat_params(self.netG).pack()          # both generator passes read the packed weights: pack before the fork
             if self._side_g is None:
-                self._side_g = torch.cuda.Stream()
+                self._side_g = torch.cuda.Stream(priority=PRIO_G)
             self._side_g.wait_stream(cur)
             early = None
             with torch.cuda.stream(self._side_g):
@@ -301,7 +306,11 @@ class GanTrainerStep:
         self.netD.zero_grad(set_to_none=True)
         self._invalidate_packed()     # the weight re-layout of the D-step generator pass must be part of the graph
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # the capture stream carries the iteration's critical chain (D step -> D(fake) -> backward): highest priority, so that
+        # its kernels are scheduled ahead of the side branches' (graph kernel nodes inherit the capturing stream's priority)
+        if getattr(self, "_capture_stream", None) is None:
+            self._capture_stream = torch.cuda.Stream(priority=PRIO_MAIN)
+        with torch.cuda.graph(graph, stream=self._capture_stream):
             err_g, err_s = self.step(static[0], None, static[1], static[2], epoch)
         self._invalidate_packed()
         self._graphs[self._branch(epoch)] = (graph, static, (self.errD, err_g, err_s))
