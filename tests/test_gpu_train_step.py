@@ -193,14 +193,14 @@ def test_capture_after_eager_steps_on_the_default_stream():
     assert np.isfinite(rs.item()) and rs.item() < first      # training continued through the replays
 
 
-@pytest.mark.parametrize("video", [False, True])
-def test_eager_steps_do_not_accumulate_device_memory(video):
+@pytest.mark.parametrize("video,precision", [(False, "bf16"), (True, "bf16"), (False, "fp32_tc")])
+def test_eager_steps_do_not_accumulate_device_memory(video, precision):
     """Regression: the bf16 generator's single autograd node kept its saved state on `ctx` together with the very tensor
     objects it returned (ctx.S -> out -> grad_fn -> node -> ctx, a cycle through C++ the garbage collector cannot see), so
     every eager step left its activations - 0.8 GB at 16 images - allocated for ever.  Steps must be memory-neutral."""
     import gc
     from uncltmo_b200.generator import UNetVideo
-    netG = (UNetVideo if video else UNet)(*G_ARGS, up_mode=0, precision="bf16").cuda().train()
+    netG = (UNetVideo if video else UNet)(*G_ARGS, up_mode=0, precision=precision).cuda().train()
     netG.load_state_dict(make_generator_state_dict())
     netD = SimpleDiscriminator(256, 1, 16, "none", "none", 0, 0).cuda().train()
     netD.load_state_dict(make_discriminator_state_dict())
