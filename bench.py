@@ -43,6 +43,9 @@ GFLOP_TILE_TC = 2 * (9.1429 - 0.0186 - 0.2151 - 0.0566 - 0.0021)
 METRIC = "1080p tone-mapped frames/s (UNet fwd)"
 CONFIG = {"workload": "image TMO inference, one 1920x1080 HDR frame per step per GPU = 60 tiles of 256x256 "
                       "(pad to 1088x1936, overlap 64), random-init weights, lambda 371.4",
+          "frames_per_generator_call": "4 (default --frames-per-call): consecutive frames share one generator call of 240 "
+                                       "independent tiles; every frame still runs its own normalise / blend / percentile / "
+                                       "post-process stages and K steps = exactly K frames",
           "tiles_per_frame": TILES, "gflop_per_frame": TILES * GFLOP_TILE,
           "l2": "3 frames rotate per rank and each step writes/reads >2 GB of activations (>> 126 MB L2), "
                 "so no input survives in L2 between steps",
@@ -326,6 +329,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--frames-per-call", type=int, default=4,
+                    help="consecutive frames that share one generator call (their tiles are independent); 1 = frame by frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
     ap.add_argument("--train-precision", default="bf16", choices=["bf16", "fp32"])
@@ -381,11 +386,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    loop = {"n": 0}     # length of the loop that is running (the last generator call of a loop takes the frames that are left)
+
     def timed(fn, steps):
+        loop["n"] = args.warmup
         for i in range(args.warmup):
             fn(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        loop["n"] = steps
         e0.record()
         for i in range(steps):
             fn(i)
@@ -398,8 +407,18 @@ def main():
             ms = t.item()
         return ms
 
+    FPC = max(1, args.frames_per_call)
+
+    def batch_call(i, count=None):
+        """`count` (default FPC) consecutive frames (steps i .. i + count - 1) through the path with ONE generator call
+        (their tiles are independent; at 60 tiles the deeper half of the network does not fill the GPU)."""
+        pipe.tonemap_frames([dev_frames[(i + k) % nframes] for k in range(count or FPC)], LAMBDA, uint8=True)
+
     def step_resident(i):
-        pipe.tonemap(dev_frames[i % nframes], LAMBDA, uint8=True)
+        # a step is one frame; frames are processed FPC at a time, so every FPC-th step does the work of up to FPC steps -
+        # exactly K frames are processed in a loop of K steps
+        if i % FPC == 0:
+            batch_call(i, min(FPC, loop["n"] - i))
 
     host_outs = [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(8)]
 
@@ -407,7 +426,7 @@ def main():
         """K frames from pinned host memory to 8-bit results in pinned host memory through the streaming API."""
         frames = [host_frames[i % nframes] for i in range(steps)]
         outs = [host_outs[i % len(host_outs)] for i in range(steps)]
-        pipe.tonemap_host_frames(frames, LAMBDA, out=outs)
+        pipe.tonemap_host_frames(frames, LAMBDA, out=outs, frames_per_batch=FPC)
 
     def timed_e2e(steps):
         e2e_run(args.warmup)
@@ -427,7 +446,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     _lib.reset_launch_count()
     ms_res = timed(step_resident, args.steps)
-    launches = _lib.launch_count() * args.steps // (args.steps + args.warmup)
+    launches = _lib.launch_count() * args.steps // (args.steps + args.warmup)   # (kernel launches, averaged over warm-up + timed frames)
     ms_e2e = timed_e2e(args.steps)
     clocks = sampler.stop() if sampler else None
 
@@ -448,7 +467,7 @@ def main():
         reps = 3
         for i in range(reps + 1):
             _lib.start_call_timing()
-            step_resident(i)
+            batch_call(i * FPC)
             torch.cuda.synchronize()
             rec = _lib.stop_call_timing()
             if i == 0:
@@ -463,17 +482,18 @@ def main():
         if tc_ms:
             name = "conv3x3_tc" if args.precision == "bf16" else "conv3x3_simt"
             n_launch = cnt["uncl_" + name] + (cnt.get("uncl_conv3x3_tc_skipcat", 0) if args.precision == "bf16" else 0)
-            achieved = TILES * GFLOP_TILE_TC / tc_ms  # GFLOP/ms == TFLOP/s
+            achieved = FPC * TILES * GFLOP_TILE_TC / tc_ms  # GFLOP/ms == TFLOP/s (tot / cnt are per generator call = FPC frames)
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
-            if os.path.exists(tpath):
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch_avg")
+            if os.path.exists(tpath):   # captured at 60 tiles per launch; a launch of FPC frames moves FPC times the bytes
+                traffic = FPC * json.load(open(tpath)).get("dram_bytes_per_launch_avg")
             roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
                     "frac": achieved / burst, "frac_of_sustained_peak": achieved / sus_peak, "traffic": traffic,
                     "peak_source": how + ": burst figure (the kernel is timed per launch in a short instrumented pass)",
                     "traffic_source": "profiles/conv_tc_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, per launch)",
-                    "launches_per_step": n_launch, "avg_launch_ms": tc_ms / n_launch,
-                    "algorithmic_gflop_per_launch_avg": TILES * GFLOP_TILE_TC / n_launch,
+                    "launches_per_call": n_launch, "frames_per_call": FPC, "tiles_per_launch": FPC * TILES,
+                    "avg_launch_ms": tc_ms / n_launch,
+                    "algorithmic_gflop_per_launch_avg": FPC * TILES * GFLOP_TILE_TC / n_launch,
                     "share_of_step": tc_ms / sum(tot.values()),
                     "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
         # memory-bound kernels of the frame path: ALGORITHMIC bytes per call (SURVEY.md 8d / DESIGN.md section 3) over the
@@ -493,8 +513,10 @@ def main():
         hbm_rows = []
         for k, nbytes in algo.items():
             if k in tot and cnt.get(k):
+                if k in ("uncl_conv_first", "uncl_maxpool2"):
+                    nbytes *= FPC          # generator kernels see the tiles of all FPC frames in one call
                 us = tot[k] / cnt[k] * 1e3
-                hbm_rows.append({"kernel": k[5:], "calls_per_step": cnt[k], "bytes": int(nbytes), "us": round(us, 2),
+                hbm_rows.append({"kernel": k[5:], "calls_per_generator_call": cnt[k], "bytes": int(nbytes), "us": round(us, 2),
                                  "frac": round(nbytes / (us * 1e-6) / 1e9 / hbm, 3)})
         roofline_hbm = {"peak_gbs": hbm, "note": "bytes = algorithmic bytes per CALL (percentile_pair / maxpool2: mean over the "
                         "calls of a step); us = device time per call, events around the C-ABI call", "kernels": hbm_rows}

@@ -258,3 +258,22 @@ def test_fused_frame_stages_equal_the_staged_ones(h, w, negative):
     pipe.fused = False
     full_s = pipe.tonemap(rgb, 37.0, uint8=True)
     assert torch.equal(full_f, full_s)
+
+
+def test_frames_batched_through_one_generator_call_equal_single_frames(net):
+    """tonemap_frames (several frames' tiles in ONE generator call) and the streaming host API with frames_per_batch = 2
+    give exactly the frames tonemap() gives one by one: tiles are independent and every frame keeps its own statistics,
+    percentiles and lambda."""
+    frames = [torch.from_numpy(synth.hdr_frame(300, 420, seed=s)).cuda() for s in (1, 2, 3)]
+    lams = [31.0, 57.0, 44.0]
+    pipe = FramePipeline(net)
+    single = [pipe.tonemap(f, l, uint8=True) for f, l in zip(frames, lams)]
+    batched = pipe.tonemap_frames(frames, lams, uint8=True)
+    assert all(torch.equal(a, b) for a, b in zip(single, batched))
+    col = pipe.tonemap_frames(frames[:2], lams[0])
+    assert torch.equal(col[1], pipe.tonemap(frames[1], lams[0]))
+    host = [f.cpu().pin_memory() for f in frames]
+    for fpb in (1, 2, 3):
+        outs = pipe.tonemap_host_frames(host, lams[0], frames_per_batch=fpb)
+        want = [pipe.tonemap(f, lams[0], uint8=True).cpu() for f in frames]
+        assert all(torch.equal(a, b) for a, b in zip(outs, want)), fpb
