@@ -679,9 +679,31 @@ extern "C" int uncl_disc_backward(const float* x, const float* h1, const float* 
   const int ctas = 148 * 2;
   const long t2 = (long)N * H2 * H2;
   // dw2 / dw1 == NULL: the caller does not want the convolutions' weight gradients (the generator step back-propagates
-  // THROUGH the discriminator only; its parameter gradients would be thrown away by the next zero_grad)
-  if (dw2 != nullptr)
-    conv4s2_wgrad_kernel<16, 32><<<ctas, 256, 0, stream>>>(h1, d_z2, dw2, db2, H1, H1, H2, H2, t2, (t2 + ctas - 1) / ctas);
+  // THROUGH the discriminator only; its parameter gradients would be thrown away by the next zero_grad).
+  // The second conv's weight gradient is a leaf: it runs on a forked stream next to the data-gradient -> first-conv
+  // weight-gradient chain (both need only d_z2) and is joined before this call returns; inside a CUDA-graph capture the
+  // fork becomes a parallel branch.  (Each of the three kernels is ~100 us at 32 images and none fills the GPU.)
+  static thread_local cudaStream_t fork_stream = nullptr;
+  static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  static thread_local int fork_dev = -1;
+  bool forked = false;
+  if (dw2 != nullptr) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (fork_dev != dev) {
+      fork_stream = nullptr;
+      if (cudaStreamCreateWithFlags(&fork_stream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
+        fork_stream = nullptr;
+      fork_dev = dev;
+    }
+    forked = fork_stream != nullptr && cudaEventRecord(ev_fork, stream) == cudaSuccess &&
+             cudaStreamWaitEvent(fork_stream, ev_fork, 0) == cudaSuccess;
+    conv4s2_wgrad_kernel<16, 32><<<ctas, 256, 0, forked ? fork_stream : stream>>>(h1, d_z2, dw2, db2, H1, H1, H2, H2, t2,
+                                                                                (t2 + ctas - 1) / ctas);
+    if (forked) cudaEventRecord(ev_join, fork_stream);
+  }
   cudaError_t e = cudaFuncSetAttribute(conv4s2_dgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 16 * 16 * 4);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "disc_backward: %s", cudaGetErrorString(e));
   const long q1 = (long)N * 64 * 64;   // pixels per parity class (upper bound)
@@ -693,5 +715,6 @@ extern "C" int uncl_disc_backward(const float* x, const float* h1, const float* 
     const long q0 = (long)N * 128 * 128;
     conv4s2_dgrad_kernel<1><<<dim3(cap_grid(q0, 256, 4), 4), 256, 16 * 16 * 4, stream>>>(d_z1, w1, nullptr, dx, 16, H, H, H1, H1, N);
   }
+  if (forked) cudaStreamWaitEvent(stream, ev_join, 0);
   return uncl_check_launch("disc_backward");
 }
