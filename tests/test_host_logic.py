@@ -305,3 +305,34 @@ def test_flat_parameter_index_maps():
     for name, key, _ in fp.conv3 + [("", "up_path.%d.up" % i, 0) for i in range(4)] + [("", "inc.conv.conv", 0)]:
         assert torch.equal(fp.view(grad, key + ".weight"), sd[key + ".weight"]), key
     assert (fp.view(grad, "outc.conv.weight") == 0).all()      # parameters without a staged gradient are left alone
+
+
+def test_skipcat_plan_invariants():
+    """Tile plans of the fused-skip convolution (uncl_conv3x3_tc_skipcat): the ring program holds three slots per skip chunk,
+    so the plan narrows its column bands until at least four (normally five) pipeline stages fit; tiles still cover the
+    output, boxes respect the TMA limits, everything fits shared memory; unsupported channel counts are refused."""
+    import ctypes
+    from uncltmo_b200 import _lib
+    keys = ("kind", "NT", "NS", "mma_n", "MB", "adv", "PW", "PH", "BW", "bands", "tiles_per_band", "items", "stages", "nacc",
+            "ksteps", "smem")
+    for n, cs, h, w, pad in [(60, 32, 252, 252, 2), (60, 64, 122, 122, 2), (2, 32, 5, 7, 2), (1, 96, 33, 40, 2), (3, 64, 129, 65, 0),
+                             (1, 128, 57, 57, 2)]:
+        plan = (ctypes.c_int * 16)()
+        rc = _lib.lib().uncl_conv3x3_tc_skipcat_plan(n, cs, h, w, 32, pad, plan)
+        assert rc == 0, _lib.lib().uncl_last_error()
+        p = dict(zip(keys, list(plan)))
+        ho, wo = h + 2 * pad - 2, w + 2 * pad - 2
+        assert p["kind"] & 1 and p["NT"] == 32 and p["mma_n"] == 96 and p["MB"] == 2 and p["ksteps"] == 2
+        assert p["stages"] >= 4 and p["smem"] <= 227 * 1024
+        assert p["PW"] == p["BW"] + 2 and p["PW"] <= 128 and p["PH"] <= 256
+        assert p["bands"] * p["BW"] >= wo > (p["bands"] - 1) * p["BW"]
+        last_valid = ho * p["PW"] - 3
+        assert p["tiles_per_band"] * p["adv"] > last_valid and (p["tiles_per_band"] - 1) * p["adv"] <= last_valid
+        assert p["items"] == n * p["bands"] * p["tiles_per_band"]
+        aligned = (p["kind"] & 3) == 3
+        moff_max = 0 if aligned else p["PW"] - 1
+        assert (moff_max + 128 * p["MB"] - 1 + 2 * p["PW"] + 2) <= p["PH"] * p["PW"] + p["PW"]
+    plan = (ctypes.c_int * 16)()
+    assert _lib.lib().uncl_conv3x3_tc_skipcat_plan(1, 48, 20, 20, 32, 2, plan) != 0      # C_skip must be a multiple of 32
+    assert _lib.lib().uncl_conv3x3_tc_skipcat_plan(1, 32, 20, 20, 64, 2, plan) != 0      # C_out must be 32
+    assert _lib.lib().uncl_conv3x3_tc_skipcat_plan(1, 160, 20, 20, 32, 2, plan) != 0     # ring program: C_skip <= 128
