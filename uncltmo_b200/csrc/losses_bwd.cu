@@ -511,6 +511,72 @@ __global__ void __launch_bounds__(256) conv4s2_wgrad_kernel(const float* __restr
   if (db && threadIdx.x < COUT) atomicAdd(db + threadIdx.x, s_db[threadIdx.x]);
 }
 
+// First conv of the discriminator (1 -> 16 channels, 4x4 stride 2): dW[co][k] = sum_pix x[2oy+ky][2ox+kx] * dz[co][oy][ox].
+// The generic kernel above stages 32 pixels per barrier pair and is bound by those round trips (108 us for 132 MFLOP at 32
+// images).  Here a thread owns (output pixel, group of 4 output channels): 16 patch values x 4 dz values = 64 accumulators,
+// no shared memory in the loop; a warp's lanes are 32 consecutive pixels of the same channel group, so the final reduction is
+// a warp shuffle tree + one shared-memory stage + 256 atomics per CTA.  db[co] = sum dz rides along.
+__global__ void __launch_bounds__(256) conv4s2_wgrad_c1_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                                              float* __restrict__ dW, float* __restrict__ db, int Hi, int Wi,
+                                                              int Ho, int Wo, long total) {
+  __shared__ float s_red[8][64 + 4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int cg = wid & 3;                       // channel group of this warp: co = 4 cg .. 4 cg + 3
+  const long HWo = (long)Ho * Wo, HWi = (long)Hi * Wi;
+  float acc[4][16];
+  float accb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[c][k] = 0.f;
+  // warps (wid >> 2) in {0, 1} of every CTA interleave over pixel chunks of 32
+  const long nchunks = (total + 31) / 32;
+  for (long ch = (long)blockIdx.x * 2 + (wid >> 2); ch < nchunks; ch += (long)gridDim.x * 2) {
+    const long p = ch * 32 + lane;
+    if (p >= total) continue;
+    const long n = p / HWo, r = p - n * HWo;
+    const int oy = (int)(r / Wo), ox = (int)(r - (long)oy * Wo);
+    const float* xp = x + n * HWi + (long)(2 * oy) * Wi + 2 * ox;
+    float v[16];
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const float2 a = __ldg(reinterpret_cast<const float2*>(xp + (long)ky * Wi));       // 2 ox is even and Wi is even: 8-byte aligned
+      const float2 b = __ldg(reinterpret_cast<const float2*>(xp + (long)ky * Wi + 2));
+      v[ky * 4 + 0] = a.x; v[ky * 4 + 1] = a.y; v[ky * 4 + 2] = b.x; v[ky * 4 + 3] = b.y;
+    }
+    const float* dp = dz + (n * 16 + 4 * cg) * HWo + r;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float g = __ldg(dp + c * HWo);
+      accb[c] += g;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[c][k] = fmaf(v[k], g, acc[c][k]);
+    }
+  }
+  // warp reduction of the 64 + 4 partial sums, then across the two warps of a channel group, then atomics
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float t = acc[c][k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) s_red[wid][c * 16 + k] = t;
+    }
+    float t = accb[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) s_red[wid][64 + c] = t;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * 68; i += 256) {
+    const int g = i / 68, j = i - g * 68;
+    const float t = s_red[g][j] + s_red[g + 4][j];
+    if (j < 64) atomicAdd(dW + (4 * g + (j >> 4)) * 16 + (j & 15), t);       // dW is [co][1][16]
+    else if (db) atomicAdd(db + 4 * g + (j - 64), t);
+  }
+}
+
 // 4x4 stride-2 conv data gradient: d_in[n][ci][y][x] = sum_{co,k} dz[n][co][(y-ky)/2][(x-kx)/2] * w[co][ci][k],
 // optionally times lrelu'(act_in) (act_in = the post-LeakyReLU tensor that fed the conv).
 // blockIdx.y = parity class (y&1, x&1): all threads of a CTA use the same (ky, kx) taps, so the weights are shared-memory
@@ -710,7 +776,7 @@ extern "C" int uncl_disc_backward(const float* x, const float* h1, const float* 
   conv4s2_dgrad_kernel<16><<<dim3(cap_grid(q1, 256, 2), 4), 256, 32 * 16 * 16 * 4, stream>>>(d_z2, w2, h1, d_z1, 32, H1, H1, H2, H2, N);
   const long t1 = (long)N * H1 * H1;
   if (dw1 != nullptr)
-    conv4s2_wgrad_kernel<1, 16><<<ctas, 256, 0, stream>>>(x, d_z1, dw1, db1, H, H, H1, H1, t1, (t1 + ctas - 1) / ctas);
+    conv4s2_wgrad_c1_kernel<<<148 * 4, 256, 0, stream>>>(x, d_z1, dw1, db1, H, H, H1, H1, t1);
   if (dx) {
     const long q0 = (long)N * 128 * 128;
     conv4s2_dgrad_kernel<1><<<dim3(cap_grid(q0, 256, 4), 4), 256, 16 * 16 * 4, stream>>>(d_z1, w1, nullptr, dx, 16, H, H, H1, H1, N);
