@@ -629,6 +629,58 @@ __global__ void __launch_bounds__(256) conv4s2_dgrad_kernel(const float* __restr
   }
 }
 
+// Data gradient of the FIRST discriminator conv (16 -> 1 channel, 4x4 stride 2; the gradient that flows back into the
+// generator).  A thread owns a 2x2 block of input pixels (all four parity classes): they share the same four dz positions
+// (oy in {y2, y2-1}, ox in {x2, x2-1}), so each dz value is loaded once for four FMAs instead of once per FMA as in the
+// per-pixel kernel above (49 -> ~12 us at 16 images).  Weights: 16 channels x 16 taps, shared-memory broadcasts.
+__global__ void __launch_bounds__(256) conv4s2_dgrad_c1_kernel(const float* __restrict__ dz, const float* __restrict__ w,
+                                                              float* __restrict__ d_in, int Hi, int Wi, int Ho, int Wo,
+                                                              int N) {
+  __shared__ __align__(16) float s_w[16 * 16];   // [co][ky*4+kx]
+  if (threadIdx.x < 256) s_w[threadIdx.x] = w[threadIdx.x];
+  __syncthreads();
+  const int Hb = (Hi + 1) / 2, Wb = (Wi + 1) / 2;
+  const long total = (long)N * Hb * Wb;
+  const long HWo = (long)Ho * Wo, HWi = (long)Hi * Wi;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int x2 = (int)(i % Wb), y2 = (int)((i / Wb) % Hb);
+    const long n = i / ((long)Wb * Hb);
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    const float* dn = dz + n * 16 * HWo;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int oy = y2 - a;
+      if (oy < 0 || oy >= Ho) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ox = x2 - b;
+        if (ox < 0 || ox >= Wo) continue;
+        const float* dp = dn + (long)oy * Wo + ox;
+#pragma unroll
+        for (int co = 0; co < 16; ++co) {
+          const float g = __ldg(dp + co * HWo);
+          // pixel (py, px) of the block takes tap (ky, kx) = (py + 2a, px + 2b)
+          const float* wk = s_w + co * 16 + (2 * a) * 4 + 2 * b;
+          acc[0][0] = fmaf(g, wk[0], acc[0][0]);
+          acc[0][1] = fmaf(g, wk[1], acc[0][1]);
+          acc[1][0] = fmaf(g, wk[4], acc[1][0]);
+          acc[1][1] = fmaf(g, wk[5], acc[1][1]);
+        }
+      }
+    }
+    const int y = 2 * y2, x = 2 * x2;
+    float* o = d_in + n * HWi + (long)y * Wi + x;
+    if (x + 1 < Wi && (Wi & 1) == 0) {
+      *reinterpret_cast<float2*>(o) = make_float2(acc[0][0], acc[0][1]);
+      if (y + 1 < Hi) *reinterpret_cast<float2*>(o + Wi) = make_float2(acc[1][0], acc[1][1]);
+    } else {
+      o[0] = acc[0][0];
+      if (x + 1 < Wi) o[1] = acc[0][1];
+      if (y + 1 < Hi) { o[Wi] = acc[1][0]; if (x + 1 < Wi) o[Wi + 1] = acc[1][1]; }
+    }
+  }
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -779,7 +831,7 @@ extern "C" int uncl_disc_backward(const float* x, const float* h1, const float* 
     conv4s2_wgrad_c1_kernel<<<148 * 4, 256, 0, stream>>>(x, d_z1, dw1, db1, H, H, H1, H1, t1);
   if (dx) {
     const long q0 = (long)N * 128 * 128;
-    conv4s2_dgrad_kernel<1><<<dim3(cap_grid(q0, 256, 4), 4), 256, 16 * 16 * 4, stream>>>(d_z1, w1, nullptr, dx, 16, H, H, H1, H1, N);
+    conv4s2_dgrad_c1_kernel<<<cap_grid(q0, 256, 4), 256, 0, stream>>>(d_z1, w1, dx, H, H, H1, H1, N);
   }
   if (forked) cudaStreamWaitEvent(stream, ev_join, 0);
   return uncl_check_launch("disc_backward");
