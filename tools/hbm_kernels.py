@@ -60,6 +60,17 @@ report("percentile_pair (4K plane, 3 passes)", 3 * HW1 * 4, timed(lambda: pipe.p
 report("frame_postprocess (+ its percentile pair)", 3 * HW1 * 4 + HW1 * 4 + HW * 24, timed(lambda: pipe.postprocess(fake_p, rgb, stats, pl)))
 col = pipe.postprocess(fake_p, rgb, stats, pl)
 report("frame_to_u8 (+ its percentile pair)", 3 * HW * 12 + HW * 15, timed(lambda: pipe.to_uint8(col)))
+# the fused cooperative stage kernels at the size they are built for (1080p: every CTA's order keys fit its shared memory)
+H2, W2 = 1080, 1920
+rgb2 = torch.from_numpy(synth.hdr_frame(H2, W2, seed=1)).cuda()
+pl2 = pipe.plan(H2, W2, rgb2.device)
+assert pipe.fused_ok(pl2)
+hw2, hw12 = H2 * W2, pl2.h1 * pl2.w1
+tiles2, stats2 = pipe.normalise_tiles(rgb2, 50.0, pl2)
+report("frame_normalise_tiles (1080p, 1 cooperative launch)", hw2 * 24 + pl2.ntiles * 65536 * 4, timed(lambda: pipe.normalise_tiles(rgb2, 50.0, pl2)))
+fake2, pct2 = pipe.blend_percentiles(tiles2, pl2)
+report("frame_blend_percentiles (1080p, 1 launch)", pl2.ntiles * 65536 * 4 + hw12 * 4, timed(lambda: pipe.blend_percentiles(tiles2, pl2)))
+report("frame_post_u8 (1080p, 1 launch)", hw12 * 4 + hw2 * 15, timed(lambda: pipe.post_uint8(fake2, pct2, rgb2, stats2, pl2)))
 # generator-side memory-bound kernels at 220 tiles
 n = 220
 x = torch.rand(n, 1, 256, 256, device="cuda")
