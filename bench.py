@@ -296,15 +296,15 @@ def cpu_train_arm(threads=None):
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     g_sd, d_sd = make_generator_state_dict(), make_discriminator_state_dict()
-    hdr = torch.from_numpy(synth.normalised_batch(2, seed=4))
-    pos, neg = torch.from_numpy(synth.ldr_batch(2, seed=5)), torch.from_numpy(synth.ldr_batch(2, seed=6))
+    hdr = torch.from_numpy(synth.normalised_batch(16, seed=4))
+    pos, neg = torch.from_numpy(synth.ldr_batch(16, seed=5)), torch.from_numpy(synth.ldr_batch(16, seed=6))
     with torch.enable_grad():
-        oracle.train_step_losses(g_sd, d_sd, hdr, pos, neg, 0)
+        oracle.train_step_losses(g_sd, d_sd, hdr[:2], pos[:2], neg[:2], 0)          # warm-up (thread pools, allocator)
         t0 = time.perf_counter()
-        oracle.train_step_losses(g_sd, d_sd, hdr, pos, neg, 0)
+        oracle.train_step_losses(g_sd, d_sd, hdr, pos, neg, 0)                       # the whole 16-image step, nothing extrapolated
         dt = time.perf_counter() - t0
-    return {"value": 1.0 / (8 * dt), "unit": "steps/s", "cores": threads, "kind": "port",
-            "sample": "one D+G step of the oracle on 2 of the 16 images (%.2f s), x8" % dt}
+    return {"value": 1.0 / dt, "unit": "steps/s", "cores": threads, "kind": "port",
+            "sample": "one whole D+G step of the oracle on the 16-image batch (%.2f s), after a 2-image warm-up step" % dt}
 
 
 def run_reference(args):
