@@ -523,6 +523,28 @@ def main():
         roofline_hbm = {"peak_gbs": hbm, "note": "bytes = algorithmic bytes per CALL (percentile_pair / maxpool2: mean over the "
                         "calls of a step); us = device time per call, events around the C-ABI call", "kernels": hbm_rows}
 
+    # BASELINE.json configs[2]: the other image resolutions (HDR-Survey 1/4 resolution, 4K), same path, frames resident in HBM
+    other_res = None
+    if not args.no_train and world == 1 and rank == 0 and args.precision == "bf16":
+        other_res = {}
+        for (h2, w2, per_call, reps) in ((768, 1024, 8, 6), (2160, 3840, 1, 6)):
+            fr = [torch.from_numpy(synth.hdr_frame(h2, w2, seed=200 + i)).to(dev) for i in range(2)]
+            batch = [fr[k % 2] for k in range(per_call)]
+            for _ in range(2):
+                pipe.tonemap_frames(batch, LAMBDA, uint8=True)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                pipe.tonemap_frames(batch, LAMBDA, uint8=True)
+            e1.record()
+            torch.cuda.synchronize()
+            pl2 = pipe.plan(h2, w2, dev)
+            other_res["%dx%d" % (w2, h2)] = {"frames_per_s": reps * per_call / (e0.elapsed_time(e1) / 1e3), "tiles_per_frame": pl2.ntiles,
+                                             "frames_per_generator_call": per_call,
+                                             "frame_stages": "fused cooperative kernels" if pipe.fused_ok(pl2) else "staged kernels (order keys exceed shared memory)"}
+            del fr, batch
+        torch.cuda.empty_cache()
     train = video = None
     fp32_exact = {}
     if not args.no_train and world == 1 and args.precision == "bf16":
@@ -579,7 +601,8 @@ def main():
                 "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": "frames/s",
                         "h2d_bytes_per_step": 3 * H * W * 4, "d2h_bytes_per_step": H * W * 3},
                 "gpu_launches": launches, "roofline": roof, "roofline_hbm": roofline_hbm, "cpu_baseline": base,
-                "clocks": clocks, "sustained": sustained, "fp32_exact": fp32_exact or None, "train": train, "video": video}
+                "clocks": clocks, "sustained": sustained, "fp32_exact": fp32_exact or None, "other_resolutions": other_res,
+                "train": train, "video": video}
         # short scalars LAST: a reader that keeps only the tail of the line still sees every headline number
         line["summary"] = {
             "fps": round(fps, 1), "e2e_fps": round(line["e2e"]["value"], 1),
