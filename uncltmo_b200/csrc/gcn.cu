@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(512) gcn_knn_agg_kernel(const float* __restric
   constexpr int ROWS = GN / KNN_SPLIT;
   float* s_yn = smem;                 // [144][C+4]
   float* s_sq = smem + GN * LD;       // [144]
-  int* s_idx = reinterpret_cast<int*>(s_sq + GN);  // [ROWS][9]
+  float* s_nrm = s_sq + GN;           // [144] max(|y|, 1e-12): de-normalises the shared-memory copy for the aggregation
+  int* s_idx = reinterpret_cast<int*>(s_nrm + GN);  // [ROWS][9]
   const int n = blockIdx.x / KNN_SPLIT, part = blockIdx.x % KNN_SPLIT;
   const int i_begin = part * ROWS;
   const float* yn_g = y + (long)n * C * GN;
@@ -142,7 +143,9 @@ __global__ void __launch_bounds__(512) gcn_knn_agg_kernel(const float* __restric
     float s = 0.f;
     for (int c = lane; c < C; c += 32) { const float v = s_yn[node * LD + c]; s = fmaf(v, v, s); }
     s = warp_sum(s);
-    const float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);
+    const float nrm = fmaxf(sqrtf(s), 1e-12f);
+    const float inv = 1.f / nrm;
+    if (lane == 0) s_nrm[node] = nrm;
     float s2 = 0.f;
     for (int c = lane; c < C; c += 32) {
       const float v = s_yn[node * LD + c] * inv;
@@ -214,7 +217,9 @@ __global__ void __launch_bounds__(512) gcn_knn_agg_kernel(const float* __restric
   __syncthreads();
   if (idx_out)
     for (int i = threadIdx.x; i < ROWS * GK; i += blockDim.x) idx_out[((long)n * GN + i_begin) * GK + i] = s_idx[i];
-  // aggregation on the raw (un-normalised) features, straight from global / L2
+  // aggregation on the raw (un-normalised) features: the node's own row from global memory (exact), its nine neighbours
+  // from the shared-memory copy times their norm (within 2 ulp of the raw value; the 9 dependent 32-byte gathers per lane
+  // from L2 were 58 % of this kernel's time, ncu source page)
   TZ* zn = z + (long)n * 2 * C * GN;
   for (int il = wid; il < ROWS; il += nw) {
     const int i = i_begin + il;
@@ -223,9 +228,13 @@ __global__ void __launch_bounds__(512) gcn_knn_agg_kernel(const float* __restric
       load8(yn_g + ((long)cb * GN + i) * 8, yi);
 #pragma unroll
       for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
       for (int k = 0; k < GK; ++k) {
-        float yj8[8];
-        load8(yn_g + ((long)cb * GN + s_idx[il * GK + k]) * 8, yj8);
+        const int jn = s_idx[il * GK + k];
+        const float nj = s_nrm[jn];
+        const float4 p0 = *reinterpret_cast<const float4*>(s_yn + jn * LD + cb * 8);
+        const float4 p1 = *reinterpret_cast<const float4*>(s_yn + jn * LD + cb * 8 + 4);
+        const float yj8[8] = {p0.x * nj, p0.y * nj, p0.z * nj, p0.w * nj, p1.x * nj, p1.y * nj, p1.z * nj, p1.w * nj};
 #pragma unroll
         for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], yj8[j] - yi[j]);
       }
@@ -287,7 +296,7 @@ extern "C" int uncl_pw_conv(const float* in, const float* w, const float* bias, 
 extern "C" int uncl_gcn_knn_aggregate(const float* y, const float* relpos, void* z, int z_dtype, int* idx_out, int N, int C,
                                       cudaStream_t stream) {
   UNCL_REQUIRE(C == 256 && N > 0, "gcn_knn_aggregate: only C=256 (shipped config) is built, got %d", C);
-  const size_t smem = (size_t)(GN * (C + 4) + GN) * sizeof(float) + (size_t)GN * GK * sizeof(int);
+  const size_t smem = (size_t)(GN * (C + 4) + 2 * GN) * sizeof(float) + (size_t)GN * GK * sizeof(int);
   cudaError_t e = cudaFuncSetAttribute(gcn_knn_agg_kernel<256, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(gcn_knn_agg_kernel<256, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "gcn_knn_aggregate: smem attr: %s", cudaGetErrorString(e));
