@@ -501,11 +501,14 @@ def main():
         tot = {k: sum(v) / reps for k, v in per_call.items()}
         cnt = {k: len(v) // reps for k, v in per_call.items()}
         # (two of the 17 conv launches go through uncl_conv3x3_tc_skipcat: the same kernel family with the skip operators fused)
-        tc_ms = (tot.get("uncl_conv3x3_tc", 0.0) + tot.get("uncl_conv3x3_tc_skipcat", 0.0)) if args.precision == "bf16" else tot.get("uncl_conv3x3_simt")
+        # ... and the C_out = 32 layers at 124..256 pixels through uncl_conv3x3_tc_rows / _rows_skipcat (conv_tc_rows.cu; a call
+        # covers its trailing-column launch of the older kernel as well)
+        TC_CALLS = ("uncl_conv3x3_tc", "uncl_conv3x3_tc_skipcat", "uncl_conv3x3_tc_rows", "uncl_conv3x3_tc_rows_skipcat")
+        tc_ms = sum(tot.get(k, 0.0) for k in TC_CALLS) if args.precision == "bf16" else tot.get("uncl_conv3x3_simt")
         burst, sus_peak, hbm, how = measured_peaks()
         if tc_ms:
             name = "conv3x3_tc" if args.precision == "bf16" else "conv3x3_simt"
-            n_launch = cnt["uncl_" + name] + (cnt.get("uncl_conv3x3_tc_skipcat", 0) if args.precision == "bf16" else 0)
+            n_launch = sum(cnt.get(k, 0) for k in TC_CALLS) if args.precision == "bf16" else cnt["uncl_" + name]
             achieved = FPC * TILES * GFLOP_TILE_TC / tc_ms  # GFLOP/ms == TFLOP/s (tot / cnt are per generator call = FPC frames)
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")

@@ -336,3 +336,40 @@ def test_skipcat_plan_invariants():
     assert _lib.lib().uncl_conv3x3_tc_skipcat_plan(1, 48, 20, 20, 32, 2, plan) != 0      # C_skip must be a multiple of 32
     assert _lib.lib().uncl_conv3x3_tc_skipcat_plan(1, 32, 20, 20, 64, 2, plan) != 0      # C_out must be 32
     assert _lib.lib().uncl_conv3x3_tc_skipcat_plan(1, 160, 20, 20, 32, 2, plan) != 0     # ring program: C_skip <= 128
+
+
+def test_row_kernel_plan_and_packing():
+    """Row kernel (conv_tc_rows.cu) host arithmetic: strips cover the output rows, whole 126-column bands go to the row
+    kernel and the remainder to the older kernels, stage ring + resident filter bank fit shared memory, the multi-chunk
+    row-group rule (G <= 3, five slots) holds; packing puts tap (ky, kx), channel ci, output co where the kernel's
+    descriptors look for it."""
+    import torch
+    from uncltmo_b200 import packing
+    keys = ("ok", "cols", "tail", "bands", "BW", "R", "strips", "items", "G", "nchunk", "stages", "stage_bytes", "w_bytes",
+            "smem", "sms", "_")
+    cases = [(240, 32, 254, 254, 0, False), (240, 32, 124, 124, 2, False), (240, 32, 254, 254, 2, False),
+             (240, 128, 252, 252, 2, True), (60, 128, 252, 252, 2, False), (1, 32, 3, 3, 0, False), (7, 96, 66, 300, 2, False),
+             (2, 128, 40, 40, 0, True), (240, 256, 122, 122, 2, True)]
+    for n, ci, h, w, pad, derive in cases:
+        p = dict(zip(keys, packing.conv3x3_tc_rows_plan(n, ci, h, w, pad, derive)))
+        ho, wo = h + 2 * pad - 2, w + 2 * pad - 2
+        assert p["ok"] == 1 and p["cols"] + p["tail"] == wo and p["cols"] > 0
+        assert p["tail"] == 0 or (p["cols"] % 126 == 0 and p["tail"] < 64)
+        assert p["BW"] <= 126 and p["bands"] * p["BW"] >= p["cols"] > (p["bands"] - 1) * p["BW"]
+        assert p["strips"] * p["R"] >= ho > (p["strips"] - 1) * p["R"] and p["items"] == n * p["bands"] * p["strips"]
+        assert p["nchunk"] == ci // 32 and p["w_bytes"] == ci * 576 and p["stage_bytes"] == p["G"] * 8192
+        assert 1 <= p["G"] <= (4 if p["nchunk"] == 1 else 3)
+        assert p["stages"] >= (5 if derive else 3) and p["smem"] <= 227 * 1024
+        assert p["stages"] * p["stage_bytes"] + p["w_bytes"] < p["smem"]
+    # the generator's shipped layers: 13 waves of 63-row strips on 148 SMs for four 1080p frames
+    p = dict(zip(keys, packing.conv3x3_tc_rows_plan(240, 32, 254, 254, 0)))
+    assert (p["R"], p["strips"], p["items"]) == (63, 4, 1920)
+    p = dict(zip(keys, packing.conv3x3_tc_rows_plan(240, 256, 122, 122, 2, True)))   # up2.conv0: 144 KB of filters + 5 x 2 rows
+    assert p["ok"] == 1 and p["G"] == 2 and p["stages"] >= 5 and p["smem"] <= 227 * 1024
+    assert packing.conv3x3_tc_rows_plan(1, 512, 59, 59, 2, False)[0] == 0        # 288 KB of filters: stays on the older kernels
+    w9 = torch.arange(9 * 64 * 32, dtype=torch.float32).reshape(9, 64, 32)
+    t = packing.conv3x3_tc_rows_layout(w9)
+    assert tuple(t.shape) == (2, 2, 3, 2, 96, 8)
+    for ky, kx, ci, co in [(0, 0, 0, 0), (2, 1, 37, 5), (1, 2, 63, 31), (0, 2, 16, 9)]:
+        chunk, ks, half, k8 = ci // 32, (ci % 32) // 16, (ci % 16) // 8, ci % 8
+        assert t[chunk, ks, kx, half, ky * 32 + co, k8] == w9[ky * 3 + kx, ci, co]

@@ -47,6 +47,7 @@ struct TcParams {
   float* out_img;           // [N][Ho][Wo] fp32 (fuse_outc)
   float* out_logit;         // optional
   int N, C_in, C_out, Ho, Wo, pad;
+  int x0;                   // first output column of this launch (the row kernel's trailing columns, conv_tc_rows.cu); bands cover [x0, Wo)
   int NT, NS;               // N tile (<=128) and number of N splits
   int MB;                   // M blocks (128 pixels each) per tile
   int PW, PH;               // TMA box (halo tile) extent in pixels; PW is also the flattening pitch of a band
@@ -86,7 +87,7 @@ struct Item {
 };
 
 struct Geo {  // hot scalars of TcParams, hoisted into registers
-  int NS, tiles_per_img, tiles_per_band, MB, PW, BW, pad, band_total;
+  int NS, tiles_per_img, tiles_per_band, MB, PW, BW, pad, band_total, x0;
 };
 
 // q / PW with the host-computed magic m = 2^40 / PW + 1 (exact for q < 2^24, PW <= 128)
@@ -104,7 +105,7 @@ __device__ __forceinline__ Item decode_item(const Geo& g, int item) {
   const int tb = t - it.band * g.tiles_per_band;
   it.q0 = tb * 128 * g.MB;
   const int y0 = it.q0 / g.PW;
-  it.bx = it.band * g.BW - g.pad;
+  it.bx = g.x0 + it.band * g.BW - g.pad;
   it.by = y0 - g.pad;
   it.moff0 = it.q0 - y0 * g.PW;
   it.mb_act = min(g.MB, (g.band_total - it.q0 + 127) / 128);
@@ -150,7 +151,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);  // [C_out] (+ [C_out] outc weights)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const Geo geo = {p.NS, p.tiles_per_img, p.tiles_per_band, p.MB, p.PW, p.BW, p.pad, p.band_total};
+  const Geo geo = {p.NS, p.tiles_per_img, p.tiles_per_band, p.MB, p.PW, p.BW, p.pad, p.band_total, p.x0};
   const int num_items = p.num_items, nchunk = p.nchunk, stages = p.stages, stage_bytes = p.stage_bytes;
 
   if (warp == 0 && lane == 0) {
@@ -365,7 +366,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           const int c0 = cc * 32;
           const int q = it.q0 + b * 128 + row;
           const int oy = fastdiv_pw(q, p.m_PW), xl = q - oy * geo.PW;
-          const int ox = it.band * geo.BW + xl;
+          const int ox = geo.x0 + it.band * geo.BW + xl;
           const bool valid = (oy < Ho) && (xl < geo.BW) && (ox < Wo);
           const long pix = (long)oy * Wo + ox;
           float logit = 0.f;
@@ -429,7 +430,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           const int c0 = cc * 32;
           const int q = it.q0 + b * 128 + row;
           const int oy = fastdiv_pw(q, p.m_PW), xl = q - oy * geo.PW;
-          const int ox = it.band * geo.BW + xl;
+          const int ox = geo.x0 + it.band * geo.BW + xl;
           const bool valid = (oy < Ho) && (xl < geo.BW) && (ox < Wo);
           const long pix = (long)oy * Wo + ox;
           {
@@ -604,8 +605,8 @@ int plan_tc(TcParams& p, int N, int C_in, int bias_floats, const char* what, int
   p.acc_cols = p.nacc == 1 ? 512 : kAccCols;
   const int mb_max = p.acc_cols / p.NT;
   // column bands: the TMA box row is PW pixels = 2*PW 8-byte elements and a box dimension holds <= 256 elements
-  p.nbands = ceil_div(p.Wo, 128 - halo);
-  p.BW = ceil_div(p.Wo, p.nbands);
+  p.nbands = ceil_div(p.Wo - p.x0, 128 - halo);
+  p.BW = ceil_div(p.Wo - p.x0, p.nbands);
   p.PW = p.BW + halo;
   p.band_total = p.Ho * p.PW;
   {
@@ -682,7 +683,7 @@ int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void
                                   long out_img_stride, int out_f32, int N, int C_in, int H, int W, int C_out, int pad,
                                   int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
                                   float* out_img, float* out_logit, const void* mask, long mask_img_stride,
-                                  unsigned long long* dbg, int derive, cudaStream_t stream);
+                                  unsigned long long* dbg, int derive, int x0, cudaStream_t stream);
 
 // Which 3x3 layers run in the kx-merged kernel (conv_tc_merged.cu); packing.conv3x3_tc packs the weights to match.
 // Measured per layer of the 1080p frame (profiles/README.md): with C_out <= 64 the merged formulation wins when the
@@ -696,9 +697,11 @@ static bool use_merged(int C_in, int C_out) {
 static int conv3x3_tc_impl(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
                            long out_img_stride, int out_dtype, int N, int C_in, int H, int W, int C_out, int pad,
                            int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
-                           float* out_img, float* out_logit, const void* mask, long mask_img_stride, cudaStream_t stream) {
+                           float* out_img, float* out_logit, const void* mask, long mask_img_stride, int x0,
+                           cudaStream_t stream) {
   UNCL_REQUIRE(N > 0 && C_in % 16 == 0 && C_out % 32 == 0 && (pad == 0 || pad == 2),
                "conv3x3_tc: unsupported C_in=%d C_out=%d pad=%d", C_in, C_out, pad);
+  UNCL_REQUIRE(x0 >= 0 && x0 < W + 2 * pad - 2, "conv3x3_tc: first column %d outside the output", x0);
   if (use_merged(C_in, C_out)) {
     UNCL_REQUIRE(out_dtype == UNCL_F32 || out_dtype == UNCL_BF16, "conv3x3_tc: bad out_dtype");
     UNCL_REQUIRE(!fuse_outc || (outc_w && outc_b && out_img), "conv3x3_tc: fuse_outc needs outc params");
@@ -707,9 +710,10 @@ static int conv3x3_tc_impl(const void* in, long in_img_stride, const void* w_pac
     UNCL_REQUIRE(H + 2 * pad - 2 > 0 && W + 2 * pad - 2 > 0, "conv3x3_tc: empty output");
     return uncl_launch_conv3x3_tc_merged(in, in_img_stride, w_packed, bias, out, out_img_stride, out_dtype == UNCL_F32, N, C_in,
                                          H, W, C_out, pad, act, emit_skip, fuse_outc, outc_w, outc_b, out_img, out_logit,
-                                         mask, mask_img_stride, g_dbg, 0, stream);
+                                         mask, mask_img_stride, g_dbg, 0, x0, stream);
   }
   TcParams p{};
+  p.x0 = x0;
   p.NT = C_out < 128 ? C_out : 128;
   if (C_out == 256 && probe_env("UNCL_PROBE_NT256") != nullptr) p.NT = 256;   // timing probe (weights packed by the caller)
   UNCL_REQUIRE(C_out % p.NT == 0 && C_out <= 1024, "conv3x3_tc: unsupported C_out=%d", C_out);
@@ -738,7 +742,27 @@ extern "C" int uncl_conv3x3_tc(const void* in, long in_img_stride, const void* w
                                int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
                                float* out_img, float* out_logit, cudaStream_t stream) {
   return conv3x3_tc_impl(in, in_img_stride, w_packed, bias, out, out_img_stride, out_dtype, N, C_in, H, W, C_out, pad, act,
-                         emit_skip, fuse_outc, outc_w, outc_b, out_img, out_logit, nullptr, 0, stream);
+                         emit_skip, fuse_outc, outc_w, outc_b, out_img, out_logit, nullptr, 0, 0, stream);
+}
+
+// uncl_conv3x3_tc restricted to the output columns [x0, Wo): the trailing columns of a layer whose whole 126-column bands
+// run in the row kernel (conv_tc_rows.cu).  Not part of the C ABI.
+int uncl_conv3x3_tc_cols(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                         long out_img_stride, int out_dtype, int N, int C_in, int H, int W, int C_out, int pad, int act,
+                         int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b, float* out_img,
+                         float* out_logit, int x0, cudaStream_t stream) {
+  return conv3x3_tc_impl(in, in_img_stride, w_packed, bias, out, out_img_stride, out_dtype, N, C_in, H, W, C_out, pad, act,
+                         emit_skip, fuse_outc, outc_w, outc_b, out_img, out_logit, nullptr, 0, x0, stream);
+}
+
+// uncl_conv3x3_tc_skipcat restricted to the output columns [x0, Wo) (arguments validated by the callers).
+int uncl_conv3x3_tc_skipcat_cols(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                                 long out_img_stride, int out_dtype, int N, int C_skip, int H, int W, int C_out, int pad,
+                                 int act, int x0, cudaStream_t stream) {
+  UNCL_REQUIRE(x0 >= 0 && x0 < W + 2 * pad - 2, "conv3x3_tc_skipcat: first column %d outside the output", x0);
+  return uncl_launch_conv3x3_tc_merged(in, in_img_stride, w_packed, bias, out, out_img_stride, out_dtype == UNCL_F32, N,
+                                       4 * C_skip, H, W, C_out, pad, act, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                                       g_dbg, 1, x0, stream);
 }
 
 // First conv of an `up` block with the skip operators FUSED (unet_parts.py:311-332: x2 -> [x2, x2^2, sqrt(x2 + 1e-8)],
@@ -755,9 +779,8 @@ extern "C" int uncl_conv3x3_tc_skipcat(const void* in, long in_img_stride, const
   UNCL_REQUIRE(out_dtype == UNCL_F32 || out_dtype == UNCL_BF16, "conv3x3_tc_skipcat: bad out_dtype");
   UNCL_REQUIRE(act == UNCL_ACT_RELU || act == UNCL_ACT_NONE, "conv3x3_tc_skipcat: only ReLU / identity epilogues are built");
   UNCL_REQUIRE(H + 2 * pad - 2 > 0 && W + 2 * pad - 2 > 0, "conv3x3_tc_skipcat: empty output");
-  return uncl_launch_conv3x3_tc_merged(in, in_img_stride, w_packed, bias, out, out_img_stride, out_dtype == UNCL_F32, N,
-                                       4 * C_skip, H, W, C_out, pad, act, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
-                                       g_dbg, 1, stream);
+  return uncl_conv3x3_tc_skipcat_cols(in, in_img_stride, w_packed, bias, out, out_img_stride, out_dtype, N, C_skip, H, W, C_out,
+                                      pad, act, 0, stream);
 }
 
 // Data gradient of a 3x3 conv / ConvTranspose 3x3 with the ReLU backward of the PRODUCING layer fused into the epilogue:
@@ -772,7 +795,7 @@ extern "C" int uncl_conv3x3_tc_dgrad(const void* in, long in_img_stride, const v
   UNCL_REQUIRE(out != nullptr && (mask == nullptr || ((reinterpret_cast<uintptr_t>(mask) & 15) == 0 && mask_img_stride % 8 == 0)),
                "conv3x3_tc_dgrad: bad output / mask");
   return conv3x3_tc_impl(in, in_img_stride, w_packed, nullptr, out, out_img_stride, out_dtype, N, C_in, H, W, C_out, pad,
-                         UNCL_ACT_NONE, 0, 0, nullptr, nullptr, nullptr, nullptr, mask, mask_img_stride, stream);
+                         UNCL_ACT_NONE, 0, 0, nullptr, nullptr, nullptr, nullptr, mask, mask_img_stride, 0, stream);
 }
 
 // ConvTranspose2d(C, C, 2, stride=2) as a GEMM [pixels x C] . [C x 4C] with a pixel-shuffle epilogue.

@@ -52,6 +52,7 @@ struct MgParams {
   const bf16* mask;         // data-gradient mode (uncl_conv3x3_tc_dgrad): out = (mask > 0) ? acc : 0
   long mask_img_stride;
   int C_out, Ho, Wo, pad;
+  int x0;                   // first output column of this launch: bands cover [x0, Wo) (trailing columns of conv_tc_rows.cu)
   int NT, NS, NP;           // channels per N split, N splits, MMA N = 3 * NT
   int MB, ADV;              // M blocks per tile, tile advance in positions (128 * MB - 2)
   int PW, PH, BW;
@@ -92,7 +93,7 @@ __device__ __forceinline__ MgItem mg_decode(const MgParams& p, int item) {
   const int tb = t - it.band * p.tiles_per_band;
   it.q0 = tb * p.ADV;
   const int y0 = fastdiv(it.q0, p.m_PW);
-  it.bx = it.band * p.BW - p.pad;
+  it.bx = p.x0 + it.band * p.BW - p.pad;
   it.by = y0 - p.pad;
   it.moff0 = it.q0 - y0 * p.PW;
   return it;
@@ -485,7 +486,7 @@ conv3x3_tc_merged_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                __shfl_sync(0xffffffffu, __uint_as_float(r2[j]), src2);
       const int q = it.q0 + l;
       const int oy = fastdiv(q, p.m_PW), xl = q - oy * PW;
-      const int ox = it.band * BW + xl;
+      const int ox = p.x0 + it.band * BW + xl;
       const bool valid = (l < ADV) && (oy < Ho) && (xl < BW) && (ox < Wo);
       const long pix = (long)oy * Wo + ox;
       const int cbase = it.ns * NT + cb0;
@@ -565,7 +566,8 @@ static const char* probe_env(const char*) { return nullptr; }   // the product l
 // tile geometry and pipeline sizing: pure host arithmetic (no CUDA calls), shared with uncl_plan_conv3x3_tc_merged
 // derive: C_in is the LOGICAL channel count 4*Cs of [skip | up | skip^2 | sqrt(skip)]; the tensor holds the first 2*Cs
 int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int fuse_outc, int derive, const char* what,
-            int* smem_bytes_out) {
+            int* smem_bytes_out, int x0 = 0) {
+  p.x0 = x0;
   p.NT = C_out < 64 ? C_out : 64;
   UNCL_REQUIRE(p.NT % 32 == 0 && C_out % p.NT == 0, "%s: unsupported C_out=%d", what, C_out);
   UNCL_REQUIRE(!fuse_outc || C_out == 32, "%s: the fused out conv needs C_out == 32", what);
@@ -581,7 +583,8 @@ int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
   if (const char* e = probe_env("UNCL_MG_BW")) { const int want = atoi(e); if (want >= 8 && want < bw_max) bw_max = want; }
   const int tail = 128 + 2 * kUnits * 4 * kXSlot * 4 + 2 * kUnits * 128 * 4 + (2 * kMaxStages + 5) * 8 + 16 + 2 * C_out * 4 + 256;
   const int budget = 227 * 1024 - tail;
-  const int nbands0 = ceil_div(p.Wo, bw_max);
+  const int wcols = p.Wo - x0;   // output columns of this launch
+  const int nbands0 = ceil_div(wcols, bw_max);
   // Fused skip operators hold three ring slots per skip chunk (x, x^2, sqrt): with a ring of exactly one tile (4 slots)
   // the next tile's skip chunk could only load after this tile's derived chunks were built - a serial TMA + transform
   // chain per tile.  Narrower column bands shrink the halo box until FIVE stages fit, which rotates the slots from tile
@@ -589,7 +592,7 @@ int mg_plan(MgParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
   const int want_stages = derive ? 5 : 0;
   int nbands = nbands0;
   for (;; ++nbands) {
-  p.BW = ceil_div(p.Wo, nbands);
+  p.BW = ceil_div(wcols, nbands);
   p.PW = p.BW + 2;
   p.band_total = p.Ho * p.PW;
   // Tile = 128*MB consecutive positions of the band flattened with pitch PW.  Flat tiling advances by 128*MB - 2 (tiles
@@ -693,12 +696,12 @@ int uncl_launch_conv3x3_tc_merged(const void* in, long in_img_stride, const void
                                   long out_img_stride, int out_f32, int N, int C_in, int H, int W, int C_out, int pad,
                                   int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
                                   float* out_img, float* out_logit, const void* mask, long mask_img_stride,
-                                  unsigned long long* dbg, int derive, cudaStream_t stream) {
+                                  unsigned long long* dbg, int derive, int x0, cudaStream_t stream) {
   const char* what = derive ? "conv3x3_tc_skipcat" : "conv3x3_tc(merged)";
   UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "%s: input must be 16-byte aligned", what);
   MgParams p{};
   int smem_bytes = 0;
-  if (int rc = mg_plan(p, N, C_in, H, W, C_out, pad, fuse_outc, derive, what, &smem_bytes)) return rc;
+  if (int rc = mg_plan(p, N, C_in, H, W, C_out, pad, fuse_outc, derive, what, &smem_bytes, x0)) return rc;
   p.w = reinterpret_cast<const bf16*>(w_packed);
   p.bias = bias; p.out = out; p.out_f32 = out_f32; p.out_img_stride = out_img_stride;
   p.outc_w = outc_w; p.outc_b = outc_b; p.out_img = out_img; p.out_logit = out_logit;

@@ -1,0 +1,565 @@
+// 3x3 stride-1 convolution / ConvTranspose 3x3 with C_out = 32 on the tensor cores, the three ky taps (filter ROWS)
+// merged into the N dimension of one tcgen05.mma and the input streamed through shared memory ONE IMAGE ROW AT A TIME.
+//
+// Why (profiles/r1_mma_probe.csv): a kind::f16 M=128 K=16 instruction reads its 4 KB A tile at
+// 128 B/cycle whatever N is, so N = C_out = 32 runs at 16/40 of the tensor peak.  conv_tc_merged.cu merges the three kx
+// taps (N' = 96: 56 cycles for three taps) but pays for it twice: its accumulator rows of one output pixel sit in
+// neighbouring TMEM LANES (a shuffle / shared-memory exchange epilogue of ~7500 warp instructions per tile) and every
+// 2-row tile reloads a 4-row halo box (2x the input through the shared-memory port the MMAs already saturate).  Here
+//     M block  = one input row of a 126-column band (128 positions, pitch 128)
+//     D_r[x][ky*32 + co] = sum_{kx, ci} X[r][x + kx][ci] * W[ky][kx][ci][co]      (3 kx x C_in/16 MMAs of N' = 96 per row;
+//                                                                                  kx = descriptor start + kx*16 B)
+//     out[y][x][co]      = D_y[x][co] + D_{y+1}[x][32 + co] + D_{y+2}[x][64 + co]
+// The three terms of an output pixel are in the SAME TMEM lane of three different accumulator slots, so the epilogue is
+// three lane-aligned tcgen05.ld + 64 adds per thread, and every input row is loaded into shared memory exactly once
+// per strip (a CTA walks a strip of R output rows = R + 2 input rows; 5 accumulator slots of 96 TMEM columns rotate).
+// The fused skip operators (unet_parts.py:319-322: x^2, sqrt(x + 1e-8) of the skip tensor built in shared memory) use
+// the same ring program as conv_tc_merged.cu, one row group at a time - each skip row is transformed once, not twice.
+//
+// Bands are 126 output columns (TMA box rows hold <= 256 8-byte elements = 128 pixels); the host entry points hand the
+// columns past the last whole band (2 of 254, 4 of 256) to the older kernels (x0 argument), see conv_tc.cu.
+// Reference operator: models/unet_multi_filters/unet_parts.py:57-87 (double_conv), :126-141 / :183-193 (ConvTranspose
+// 3x3 pair of `up`), :311-332 (skip operators + concat), :338-345 (outconv).
+// Weights: bf16 [C_in/32][2 ksteps][3 kx][2][96 (ky, co)][8] (packing.conv3x3_tc_rows).
+#include "tc_ptx.cuh"
+
+namespace {
+
+using namespace tcptx;
+
+constexpr int kRwThreads = 576;        // warp 0: TMA producer, 1: MMA issuer, 2-17: epilogue
+constexpr int kRwThreadsDerive = 704;  // ... + warps 18-21: skip-operator warps
+constexpr int kRwDeriveWarp0 = 18;
+constexpr int kRwDeriveWarps = 4;
+constexpr int kRwMaxStages = 8;
+constexpr int kRwSlots = 5;            // accumulator slots of 96 TMEM columns
+constexpr int kRwMaxProg = 16;
+constexpr int kRwRowBytes = 128 * 16;  // one row of one channel block in shared memory
+constexpr int kRwWChunk = 2 * 3 * 2 * 96 * 16;   // packed weights of 32 input channels: 18432 B
+
+struct RwParams {
+  const bf16* w;
+  const float* bias;
+  bf16* out;
+  long out_img_stride;
+  const float* outc_w;
+  const float* outc_b;
+  float* out_img;
+  float* out_logit;
+  int Ho, Wo, Wc, pad, H_in, W_in;     // Wc: output columns [0, Wc) are computed here
+  int BW, nbands, R, nstrips, items_per_img, num_items;
+  int G, nchunk, stages, stage_bytes, w_total;
+  int derive;
+  unsigned char prog_kind[kRwMaxProg], prog_cb[kRwMaxProg], prog_wch[kRwMaxProg], prog_back[kRwMaxProg];
+  int act, emit_skip, fuse_outc;
+};
+
+struct RwItem {
+  int n, bx, by, y0, x0, rows_out, rows_in;
+};
+
+__device__ __forceinline__ RwItem rw_decode(const RwParams& p, int item) {
+  RwItem it;
+  it.n = item / p.items_per_img;
+  const int t = item - it.n * p.items_per_img;
+  const int band = t / p.nstrips;
+  const int strip = t - band * p.nstrips;
+  it.y0 = strip * p.R;
+  it.x0 = band * p.BW;
+  it.rows_out = min(p.R, p.Ho - it.y0);
+  it.rows_in = it.rows_out + 2;
+  it.bx = it.x0 - p.pad;
+  it.by = it.y0 - p.pad;
+  return it;
+}
+
+__device__ __forceinline__ uint32_t rw_bf16x2_mul(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t rw_bf16x2_sqrt_eps(uint32_t v) {
+  const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
+  return pack_bf16x2(fast_sqrt(lo + 1e-8f), fast_sqrt(hi + 1e-8f));
+}
+
+template <bool kDerive>
+__global__ void __launch_bounds__(kDerive ? kRwThreadsDerive : kRwThreads, 1)
+conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RwParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint8_t* stage_base = smem;
+  uint8_t* wres = smem + (size_t)p.stages * p.stage_bytes;            // resident filter bank
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wres + p.w_total + 128);   // 128 B of slack: the kx = 2 reads of a stage's last row
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kRwMaxStages;
+  uint64_t* rowdone = bars + 2 * kRwMaxStages;
+  uint64_t* sfree = rowdone + kRwSlots;
+  uint64_t* wfull = sfree + kRwSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [32] bias + [32] out conv weights
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_items = p.num_items, nchunk = p.nchunk, stages = p.stages, stage_bytes = p.stage_bytes, G = p.G;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    const uint32_t extra = kDerive ? (uint32_t)kRwDeriveWarps : 0u;
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1 + extra); mbar_init(&empty[s], 1 + extra); }
+    // a slot is read by the epilogues of three output rows (its ky = 0, 1, 2 column groups), four warps each
+    for (int s = 0; s < kRwSlots; ++s) { mbar_init(&rowdone[s], 1); mbar_init(&sfree[s], 12); }
+    mbar_init(wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < 32; i += (int)blockDim.x) {
+    s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    s_bias[32 + i] = p.fuse_outc ? p.outc_w[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      mbar_expect_tx(wfull, (uint32_t)p.w_total);
+      {
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
+        for (int off = 0; off < p.w_total; off += kRwWChunk) bulk_load(wres + off, wsrc + off, kRwWChunk, wfull);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t box_bytes = (uint32_t)stage_bytes;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const RwItem it = rw_decode(p, item);
+        for (int r0 = 0; r0 < it.rows_in; r0 += G) {
+          for (int ch = 0; ch < nchunk; ++ch) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = stage_base + (size_t)stage * stage_bytes;
+            if (!kDerive || p.prog_kind[ch] == 0) {
+              mbar_expect_tx(&full[stage], box_bytes);
+              tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by + r0, kDerive ? (int)p.prog_cb[ch] : ch * 4, it.n);
+            } else {
+              mbar_arrive(&full[stage]);   // derived chunk: filled by the skip-operator warps
+            }
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    // One warp: the rows of a strip accumulate into rotating TMEM slots and a row's MMAs are ordinary K-loop accumulation
+    // into ONE slot (first MMA overwrites).  Waits are warp-uniform, the MMAs of a row are straight-line code of one
+    // elected lane (a divergent issuing thread costs 150+ cycles per instruction, profiles/README.md).
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo_const = ((uint32_t)(G * 128) & 0x3fffu) << 16;   // LBO_A: channel-block stride = G rows x 2048 B
+    const uint32_t b_lo_const = 96u << 16;                               // LBO_B = 96 x 16 B
+    const uint32_t stage0_16 = smem_u32(stage_base) >> 4, stage_16 = (uint32_t)stage_bytes >> 4;
+    const uint32_t wres_16 = smem_u32(wres) >> 4;
+    const uint32_t a_kstep_16 = (uint32_t)(2 * G * 128);
+    int stage = 0;
+    uint32_t phase = 0;
+    int t = 0;   // rows issued by this CTA so far: row t uses slot t % 5 for the (t / 5)-th time
+    mbar_wait(wfull, 0);
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const RwItem it = rw_decode(p, item);
+      for (int r0 = 0; r0 < it.rows_in; r0 += G) {
+        const int rows = min(G, it.rows_in - r0);
+        for (int ch = 0; ch < nchunk; ++ch) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa16 = stage0_16 + (uint32_t)stage * stage_16;
+          const uint32_t wch = kDerive ? (uint32_t)p.prog_wch[ch] : (uint32_t)ch;
+          const uint32_t b_base = b_lo_const | (wres_16 + wch * (uint32_t)(kRwWChunk >> 4));
+          const bool first = ch == 0, last = ch == nchunk - 1;
+          for (int r = 0; r < rows; ++r) {
+            const int tt = t + r;
+            const int slot = tt % kRwSlots;
+            if (first) {   // the slot's previous contents have been read by the three epilogues that needed them
+              mbar_wait(&sfree[slot], (uint32_t)(((tt / kRwSlots) & 1) ^ 1));
+              tc_fence_after();
+            }
+            if (elect_one()) {
+              const uint32_t d = tmem_base + (uint32_t)(slot * 96);
+              const uint32_t a_row = a_lo_const | (sa16 + (uint32_t)r * 128u);
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                  tc_mma_bf16(d, a_row + (uint32_t)ks * a_kstep_16 + (uint32_t)kx, desc_hi,
+                              b_base + (uint32_t)((ks * 3 + kx) * 192), desc_hi, idesc, (ks > 0 || kx > 0) ? 1u : (first ? 0u : 1u));
+                }
+              }
+              if (last) tc_commit(&rowdone[slot]);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) tc_commit(&empty[stage]);
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        t += rows;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kRwDeriveWarp0) {
+    // =============================== fused skip operators ===============================
+    // Same ring program as conv_tc_merged.cu: at a TMA position these warps only add their arrival; at the `square`
+    // position they wait for the skip chunk (previous ring position), and write x*x into this stage and sqrt(x + 1e-8)
+    // into the next one at identical offsets (the shared-memory image IS the MMA operand layout).  The zero padding of
+    // the transposed conv applies to the concatenated tensor: the square root is 0 outside the image, not sqrt(eps).
+    if constexpr (kDerive) {
+      const int dtid = (warp - kRwDeriveWarp0) * 32 + lane;
+      const int npos = G * 128, H_in = p.H_in, W_in = p.W_in;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const RwItem it = rw_decode(p, item);
+        for (int r0 = 0; r0 < it.rows_in; r0 += G) {
+          for (int ch = 0; ch < nchunk; ++ch) {
+            const int kind = p.prog_kind[ch];
+            if (kind == 2) {   // built together with the square (previous position)
+              if (++stage == stages) { stage = 0; phase ^= 1; }
+              continue;
+            }
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (kind != 0) {
+              int src = stage - 1, nst = stage + 1;
+              uint32_t src_phase = phase, n_phase = phase;
+              if (src < 0) { src += stages; src_phase ^= 1; }
+              if (nst == stages) { nst = 0; n_phase ^= 1; }
+              mbar_wait(&empty[nst], n_phase ^ 1);
+              mbar_wait(&full[src], src_phase);
+              const uint8_t* sp = stage_base + (size_t)src * stage_bytes;
+              uint8_t* dp = stage_base + (size_t)stage * stage_bytes;
+              uint8_t* dq = stage_base + (size_t)nst * stage_bytes;
+              for (int pos = dtid; pos < npos; pos += kRwDeriveWarps * 32) {
+                uint4 v[4], q[4];
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) v[cb] = *reinterpret_cast<const uint4*>(sp + (cb * npos + pos) * 16);
+                const int rr = pos >> 7, cc = pos & 127;
+                const uint32_t in0 = ((unsigned)(it.by + r0 + rr) < (unsigned)H_in && (unsigned)(it.bx + cc) < (unsigned)W_in) ? 0xffffffffu : 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  q[j].x = rw_bf16x2_sqrt_eps(v[j].x) & in0; q[j].y = rw_bf16x2_sqrt_eps(v[j].y) & in0;
+                  q[j].z = rw_bf16x2_sqrt_eps(v[j].z) & in0; q[j].w = rw_bf16x2_sqrt_eps(v[j].w) & in0;
+                  v[j].x = rw_bf16x2_mul(v[j].x, v[j].x); v[j].y = rw_bf16x2_mul(v[j].y, v[j].y);
+                  v[j].z = rw_bf16x2_mul(v[j].z, v[j].z); v[j].w = rw_bf16x2_mul(v[j].w, v[j].w);
+                }
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
+                  *reinterpret_cast<uint4*>(dp + (cb * npos + pos) * 16) = v[cb];
+                  *reinterpret_cast<uint4*>(dq + (cb * npos + pos) * 16) = q[cb];
+                }
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> the MMA's async-proxy reads
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive(&full[stage]); mbar_arrive(&empty[stage]);
+                mbar_arrive(&full[nst]); mbar_arrive(&empty[nst]);
+                mbar_arrive(&empty[src]);
+              }
+            } else {
+              if (lane == 0) {
+                mbar_arrive(&full[stage]);
+                if (p.prog_back[ch] == 0) mbar_arrive(&empty[stage]);   // a TMA chunk nothing is derived from
+              }
+            }
+            __syncwarp();
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    // 16 warps = 4 sets x 4 TMEM lane quarters; set s finishes the output rows u with u % 4 == s.  Output row u (CTA-wide
+    // row counter; rows u, u+1, u+2 are its three input rows) waits for row u+2's MMAs, adds the ky = 0 / 1 / 2 column
+    // groups of slots u, u+1, u+2 and releases its share of the three slots.  Rows whose three inputs are not in one
+    // strip (the last two of a strip, and the virtual rows -2, -1 before the first) only do the barrier protocol.
+    const int quarter = warp & 3, set = (warp - 2) >> 2;
+    const int xl = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int Ho = p.Ho, Wo = p.Wo, Wc = p.Wc, BW = p.BW;
+    const long cb_stride = (long)Ho * Wo * 8;
+    const float act_floor = (p.act == UNCL_ACT_RELU) ? 0.f : -INFINITY;
+    const bool emit_skip = p.emit_skip != 0, fuse_outc = p.fuse_outc != 0;
+    bf16* const out = p.out;
+    const float outc_b = fuse_outc ? __ldg(p.outc_b) : 0.f;
+    int t = 0;
+    for (int item = (int)blockIdx.x - (int)gridDim.x; item < num_items; item += (int)gridDim.x) {
+      // item < 0: the two virtual rows before the CTA's first strip
+      const bool virt = item < 0;
+      const RwItem it = rw_decode(p, virt ? 0 : item);
+      const int rows_in = virt ? 2 : it.rows_in, rows_out = virt ? 0 : it.rows_out;
+      const bool last_item = !virt && item + (int)gridDim.x >= num_items;
+      const int tb = virt ? -2 : t;
+      for (int j = 0; j < rows_in; ++j) {
+        const int u = tb + j;
+        if ((u & 3) != set) continue;
+        const bool valid = j < rows_out;
+        if (!valid && last_item) break;   // no later row exists: nothing waits for these slots any more
+        {
+          const int r2 = u + 2;
+          mbar_wait(&rowdone[r2 % kRwSlots], (uint32_t)((r2 / kRwSlots) & 1));
+          tc_fence_after();
+        }
+        float v[32];
+        if (valid) {
+          uint32_t r[32];
+          tc_ld32(tmem_base + lane_base + (uint32_t)((u % kRwSlots) * 96), r);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]);
+          tc_ld32(tmem_base + lane_base + (uint32_t)(((u + 1) % kRwSlots) * 96 + 32), r);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] += __uint_as_float(r[c]);
+          tc_ld32(tmem_base + lane_base + (uint32_t)(((u + 2) % kRwSlots) * 96 + 64), r);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] += __uint_as_float(r[c]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (u + k >= 0) mbar_arrive(&sfree[(u + k) % kRwSlots]);
+        }
+        if (!valid) continue;
+        const int oy = it.y0 + j, ox = it.x0 + xl;
+        if (xl < BW && ox < Wc) {
+          const long pix = (long)oy * Wo + ox;
+          float logit = outc_b;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float o[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[c] = fmaxf(v[g * 8 + c] + s_bias[g * 8 + c], act_floor);
+            if (out != nullptr) {
+              bf16* op = out + (long)it.n * p.out_img_stride + (long)g * cb_stride + pix * 8;
+              store8(op, o);
+              if (emit_skip) {
+                float s2[8], s3[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { s2[c] = o[c] * o[c]; s3[c] = fast_sqrt(o[c] + 1e-8f); }
+                store8(op + 8 * cb_stride, s2);
+                store8(op + 12 * cb_stride, s3);
+              }
+            }
+            if (fuse_outc) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) logit = fmaf(o[c], s_bias[32 + g * 8 + c], logit);
+            }
+          }
+          if (fuse_outc) {
+            const long o1 = (long)it.n * Ho * Wo + pix;
+            if (p.out_logit) p.out_logit[o1] = logit;
+            p.out_img[o1] = 1.f / (1.f + __expf(-logit));
+          }
+        }
+      }
+      if (!virt) t += rows_in;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// Strip height: the fewest waves of (image, band, strip) items over the SMs, weighted by the rows a strip really
+// computes (R + 2 input rows for R output rows).
+int rw_pick_R(int N, int nbands, int Ho, int sms) {
+  int best_R = Ho < 8 ? Ho : 8;
+  double best = 1e30;
+  for (int ns = 1; ns <= Ho; ++ns) {
+    const int R = ceil_div(Ho, ns);
+    if (R < 6 && ns > 1) break;
+    const int strips = ceil_div(Ho, R);
+    const long items = (long)N * nbands * strips;
+    const long waves = (items + sms - 1) / sms;
+    const double cost = (double)waves * (R + 2) + 0.5 * waves;   // + per-strip pipeline fill
+    if (cost < best) { best = cost; best_R = R; }
+  }
+  return best_R;
+}
+
+int rw_plan(RwParams& p, int N, int C_in, int H, int W, int pad, int Wc, int derive, int sms, const char* what, int* smem_bytes_out) {
+  p.pad = pad; p.H_in = H; p.W_in = W;
+  p.Ho = H + 2 * pad - 2; p.Wo = W + 2 * pad - 2;
+  UNCL_REQUIRE(p.Ho > 0 && p.Wo > 0 && Wc > 0 && Wc <= p.Wo, "%s: bad extent (Ho=%d Wo=%d cols=%d)", what, p.Ho, p.Wo, Wc);
+  UNCL_REQUIRE(C_in % 32 == 0 && C_in >= 32, "%s: C_in must be a multiple of 32", what);
+  p.Wc = Wc;
+  p.nbands = ceil_div(Wc, 126);
+  p.BW = ceil_div(Wc, p.nbands);
+  p.derive = derive ? 1 : 0;
+  p.nchunk = C_in / 32;
+  p.w_total = p.nchunk * kRwWChunk;
+  UNCL_REQUIRE(p.nchunk <= kRwMaxProg, "%s: C_in=%d too deep", what, C_in);
+  const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwSlots + 1) * 8 + 16 + 64 * 4 + 256;
+  const int budget = 227 * 1024 - tail - p.w_total;
+  // Rows per pipeline stage.  With several K chunks per row group a group's rows complete together, and row a + G + k of
+  // the next group needs the slot of row a + G + k - 5, whose epilogue waits for row a + G + k - 3: that row must belong
+  // to an earlier group, so G <= 3.  One-chunk layers commit row by row and take four rows per barrier round trip.
+  const int want_stages = derive ? 5 : 3;
+  int G = p.nchunk == 1 ? 4 : 3;
+  for (; G >= 1; --G) {
+    p.stage_bytes = G * 4 * kRwRowBytes;
+    p.stages = budget / p.stage_bytes;
+    if (p.stages >= want_stages) break;
+  }
+  UNCL_REQUIRE(G >= 1 && p.stages >= want_stages, "%s: filter bank of C_in=%d does not fit shared memory next to the stage ring", what, C_in);
+  if (p.stages > kRwMaxStages) p.stages = kRwMaxStages;
+  p.G = G;
+  p.R = rw_pick_R(N, p.nbands, p.Ho, sms);
+  p.nstrips = ceil_div(p.Ho, p.R);
+  p.items_per_img = p.nbands * p.nstrips;
+  UNCL_REQUIRE((long)N * p.items_per_img < (1 << 24), "%s: too many strips", what);
+  p.num_items = N * p.items_per_img;
+  if (derive) {
+    const int cs32 = C_in / 4 / 32;
+    UNCL_REQUIRE(C_in % 128 == 0 && p.nchunk == 4 * cs32, "%s: fused skip operators need C_skip a multiple of 32", what);
+    int k = 0;
+    for (int j = 0; j < cs32; ++j) {
+      p.prog_kind[k] = 0; p.prog_cb[k] = (unsigned char)(4 * j); p.prog_wch[k] = (unsigned char)j; p.prog_back[k] = 1; ++k;
+      p.prog_kind[k] = 1; p.prog_cb[k] = 0; p.prog_wch[k] = (unsigned char)(2 * cs32 + j); p.prog_back[k] = 1; ++k;
+      p.prog_kind[k] = 2; p.prog_cb[k] = 0; p.prog_wch[k] = (unsigned char)(3 * cs32 + j); p.prog_back[k] = 2; ++k;
+    }
+    for (int j = 0; j < cs32; ++j) {
+      p.prog_kind[k] = 0; p.prog_cb[k] = (unsigned char)(4 * (cs32 + j)); p.prog_wch[k] = (unsigned char)(cs32 + j); p.prog_back[k] = 0; ++k;
+    }
+  }
+  int smem_bytes = p.stages * p.stage_bytes + p.w_total + tail;
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM (each owns all 512 TMEM columns)
+  *smem_bytes_out = smem_bytes;
+  return UNCL_OK;
+}
+
+int rw_launch(const void* in, long in_img_stride, const void* w_rows, const float* bias, void* out, long out_img_stride, int N,
+              int C_in, int H, int W, int pad, int Wc, int act, int emit_skip, int fuse_outc, const float* outc_w,
+              const float* outc_b, float* out_img, float* out_logit, int derive, const char* what, cudaStream_t stream) {
+  UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_rows) & 15) == 0,
+               "%s: input / weights must be 16-byte aligned", what);
+  RwParams p{};
+  int smem_bytes = 0;
+  const int sms = sm_count();
+  if (int rc = rw_plan(p, N, C_in, H, W, pad, Wc, derive, sms, what, &smem_bytes)) return rc;
+  p.w = reinterpret_cast<const bf16*>(w_rows);
+  p.bias = bias; p.out = reinterpret_cast<bf16*>(out); p.out_img_stride = out_img_stride;
+  p.outc_w = outc_w; p.outc_b = outc_b; p.out_img = out_img; p.out_logit = out_logit;
+  p.act = act; p.emit_skip = emit_skip; p.fuse_outc = fuse_outc;
+  CUtensorMap tmap;
+  CUresult r = encode_blocked_bf16(&tmap, in, W, H, (derive ? C_in / 2 : C_in) / 8, N, in_img_stride, 128, p.G, 4);
+  if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
+  static thread_local int smem_ok = 0, smem_dev = -1;
+  static thread_local int smem_ok_d = 0, smem_dev_d = -1;
+  cudaError_t e = derive ? ensure_smem(conv3x3_tc_rows_kernel<true>, smem_bytes, smem_ok_d, smem_dev_d)
+                         : ensure_smem(conv3x3_tc_rows_kernel<false>, smem_bytes, smem_ok, smem_dev);
+  if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));
+  const int grid = p.num_items < sms ? p.num_items : sms;
+  if (derive) conv3x3_tc_rows_kernel<true><<<grid, kRwThreadsDerive, smem_bytes, stream>>>(tmap, p);
+  else conv3x3_tc_rows_kernel<false><<<grid, kRwThreads, smem_bytes, stream>>>(tmap, p);
+  return uncl_check_launch(what);
+}
+
+// columns the row kernel computes: whole 126-column bands, unless the remainder is wide enough to fill a band usefully
+int rw_cols(int Wo) {
+  const int rem = Wo % 126;
+  return (rem == 0 || rem >= 64 || Wo < 126) ? Wo : Wo - rem;
+}
+
+}  // namespace
+
+// the older kernels on the output columns [x0, Wo) (conv_tc.cu)
+int uncl_conv3x3_tc_cols(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                         long out_img_stride, int out_dtype, int N, int C_in, int H, int W, int C_out, int pad, int act,
+                         int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b, float* out_img,
+                         float* out_logit, int x0, cudaStream_t stream);
+int uncl_conv3x3_tc_skipcat_cols(const void* in, long in_img_stride, const void* w_packed, const float* bias, void* out,
+                                 long out_img_stride, int out_dtype, int N, int C_skip, int H, int W, int C_out, int pad,
+                                 int act, int x0, cudaStream_t stream);
+
+// 3x3 conv / ConvTranspose 3x3 (pad 0 / 2) with C_out = 32, bf16 blocked in and out, bias + ReLU / identity, optional
+// skip-plane emission and fused 1x1 out conv + sigmoid: the arguments of uncl_conv3x3_tc with two packed filter banks.
+// w_rows: packing.conv3x3_tc_rows; w_tail: packing.conv3x3_tc (used for the columns past the last whole 126-column band,
+// may be NULL when uncl_conv3x3_tc_rows_plan reports none).
+extern "C" int uncl_conv3x3_tc_rows(const void* in, long in_img_stride, const void* w_rows, const void* w_tail,
+                                    const float* bias, void* out, long out_img_stride, int N, int C_in, int H, int W, int pad,
+                                    int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
+                                    float* out_img, float* out_logit, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && C_in > 0 && C_in % 32 == 0 && (pad == 0 || pad == 2) && w_rows != nullptr,
+               "conv3x3_tc_rows: unsupported C_in=%d pad=%d", C_in, pad);
+  UNCL_REQUIRE(act == UNCL_ACT_RELU || act == UNCL_ACT_NONE, "conv3x3_tc_rows: only ReLU / identity epilogues are built");
+  UNCL_REQUIRE(!fuse_outc || (outc_w && outc_b && out_img), "conv3x3_tc_rows: fuse_outc needs outc params");
+  UNCL_REQUIRE(out != nullptr || fuse_outc, "conv3x3_tc_rows: no output requested");
+  const int Wo = W + 2 * pad - 2;
+  UNCL_REQUIRE(Wo > 0 && H + 2 * pad - 2 > 0, "conv3x3_tc_rows: empty output");
+  const int Wc = rw_cols(Wo);
+  if (int rc = rw_launch(in, in_img_stride, w_rows, bias, out, out_img_stride, N, C_in, H, W, pad, Wc, act, emit_skip, fuse_outc,
+                         outc_w, outc_b, out_img, out_logit, 0, "conv3x3_tc_rows", stream))
+    return rc;
+  if (Wc < Wo) {
+    UNCL_REQUIRE(w_tail != nullptr, "conv3x3_tc_rows: %d trailing columns need the one-tap filter bank (w_tail)", Wo - Wc);
+    return uncl_conv3x3_tc_cols(in, in_img_stride, w_tail, bias, out, out_img_stride, UNCL_BF16, N, C_in, H, W, 32, pad, act,
+                                emit_skip, fuse_outc, outc_w, outc_b, out_img, out_logit, Wc, stream);
+  }
+  return UNCL_OK;
+}
+
+// uncl_conv3x3_tc_skipcat (fused skip operators, `in` = [skip (C_skip) | up-sampled (C_skip)]) through the row kernel.
+// w_rows / w_tail: packing.conv3x3_tc_rows / packing.conv3x3_tc of the full [9][4*C_skip][32] filter bank.
+extern "C" int uncl_conv3x3_tc_rows_skipcat(const void* in, long in_img_stride, const void* w_rows, const void* w_tail,
+                                            const float* bias, void* out, long out_img_stride, int N, int C_skip, int H, int W,
+                                            int pad, int act, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && C_skip > 0 && C_skip % 32 == 0 && (pad == 0 || pad == 2) && out != nullptr && w_rows != nullptr,
+               "conv3x3_tc_rows_skipcat: unsupported C_skip=%d pad=%d", C_skip, pad);
+  UNCL_REQUIRE(act == UNCL_ACT_RELU || act == UNCL_ACT_NONE, "conv3x3_tc_rows_skipcat: only ReLU / identity epilogues are built");
+  const int Wo = W + 2 * pad - 2;
+  UNCL_REQUIRE(Wo > 0 && H + 2 * pad - 2 > 0, "conv3x3_tc_rows_skipcat: empty output");
+  const int Wc = rw_cols(Wo);
+  if (int rc = rw_launch(in, in_img_stride, w_rows, bias, out, out_img_stride, N, 4 * C_skip, H, W, pad, Wc, act, 0, 0, nullptr,
+                         nullptr, nullptr, nullptr, 1, "conv3x3_tc_rows_skipcat", stream))
+    return rc;
+  if (Wc < Wo) {
+    UNCL_REQUIRE(w_tail != nullptr, "conv3x3_tc_rows_skipcat: %d trailing columns need the kx-merged filter bank (w_tail)", Wo - Wc);
+    return uncl_conv3x3_tc_skipcat_cols(in, in_img_stride, w_tail, bias, out, out_img_stride, UNCL_BF16, N, C_skip, H, W, 32, pad,
+                                        act, Wc, stream);
+  }
+  return UNCL_OK;
+}
+
+// Plan of the row kernel - pure host arithmetic, no GPU needed.  C_in is the logical channel count (4 * C_skip with
+// derive).  plan[16]: 1 when the problem fits (0: filter bank too large for shared memory - use uncl_conv3x3_tc),
+// columns computed by the row kernel, trailing columns left to the older kernels, bands, band width, strip height,
+// strips per band, work items, rows per stage, K chunks per row group, pipeline stages, stage bytes, resident weight
+// bytes, dynamic shared memory, SMs assumed, 0.
+extern "C" int uncl_conv3x3_tc_rows_plan(int N, int C_in, int H, int W, int pad, int derive, int sms, int* plan) {
+  UNCL_REQUIRE(plan != nullptr && N > 0 && C_in > 0 && C_in % 32 == 0 && (pad == 0 || pad == 2) && sms > 0 &&
+                   H + 2 * pad - 2 > 0 && W + 2 * pad - 2 > 0,
+               "conv3x3_tc_rows_plan: unsupported C_in=%d pad=%d H=%d W=%d", C_in, pad, H, W);
+  for (int i = 0; i < 16; ++i) plan[i] = 0;
+  const int Wo = W + 2 * pad - 2;
+  const int nchunk = C_in / 32;
+  const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwSlots + 1) * 8 + 16 + 64 * 4 + 256;
+  if (nchunk > kRwMaxProg || (derive && C_in % 128 != 0) ||
+      227 * 1024 - tail - nchunk * kRwWChunk < (derive ? 5 : 3) * 4 * kRwRowBytes)
+    return UNCL_OK;   // plan[0] = 0: not eligible
+  RwParams p{};
+  int smem = 0;
+  const int Wc = rw_cols(Wo);
+  if (int rc = rw_plan(p, N, C_in, H, W, pad, Wc, derive, sms, "conv3x3_tc_rows_plan", &smem)) return rc;
+  const int v[16] = {1, Wc, Wo - Wc, p.nbands, p.BW, p.R, p.nstrips, p.num_items, p.G, p.nchunk, p.stages, p.stage_bytes,
+                     p.w_total, smem, sms, 0};
+  for (int i = 0; i < 16; ++i) plan[i] = v[i];
+  return UNCL_OK;
+}

@@ -70,6 +70,9 @@ class _GeneratorBase(nn.Module):
         # us, consumers +70 us), but back-to-back frames run at the 1 kW power cap, where the saved traffic buys clock:
         # 485 -> 496 frames/s sustained (tools/fused_skip_sustained.py).  False = materialised planes.
         self.fused_skip = True
+        # bf16 inference: the C_out = 32 layers at 124..256 pixels (inc.conv1, up2.conv1, up3.conv*) run in the row kernel
+        # (conv_tc_rows.cu: ky taps merged into N, every input row through shared memory once).  False = the older kernels.
+        self.row_kernel = True
         self.to_crop = to_crop
         self.depth = depth
         self.recurrent_ch_ratio = recurrent_ch_ratio
@@ -144,6 +147,10 @@ class _GeneratorBase(nn.Module):
             w9 = packing.conv3x3_taps(m.weight.detach(), transposed)
             wp = packing.conv3x3_tc(w9) if tc else (packing.conv3x3_tc_split(w9) if split else w9)
             P[name] = (wp, m.bias.detach().float().contiguous())
+            if tc and name in self._ROW_LAYERS:
+                ci, derive = self._ROW_LAYERS[name]
+                if packing.conv3x3_tc_rows_plan(1, ci, 64, 64, 0, derive)[0] == 1:
+                    P[name + "_rows"] = packing.conv3x3_tc_rows(w9)
 
         with torch.no_grad():
             P["inc0"] = (packing.conv_first(self.inc.conv.conv.weight.detach()), self.inc.conv.conv.bias.detach().float().contiguous())
@@ -172,10 +179,18 @@ class _GeneratorBase(nn.Module):
                          self.outc.conv.bias.detach().float().contiguous())
         return P
 
+    # layers the row kernel takes in bf16 inference: name -> (logical C_in, fused skip operators)
+    _ROW_LAYERS = {"inc1": (32, False), "u2_0": (256, True), "u2_1": (32, False), "u3_0": (128, True), "u3_1": (32, False)}
+
     # ------------------------------------------------------------------ one frame through the network
     def _conv3(self, P, name, src, src_stride, dst, dst_stride, n, ci, h, w, co, pad, emit_skip=0, fuse=None):
         wt, b = P[name]
-        if self.precision == "bf16":
+        rows = P.get(name + "_rows") if (self.precision == "bf16" and self.row_kernel) else None
+        if rows is not None:
+            ow, ob, out_img, out_logit = fuse if fuse is not None else (None, None, None, None)
+            call("uncl_conv3x3_tc_rows", src, src_stride, rows, wt, b, dst, dst_stride, n, ci, h, w, pad, ACT_RELU, emit_skip,
+                 0 if fuse is None else 1, ow, ob, out_img, out_logit)
+        elif self.precision == "bf16":
             if fuse is None:
                 call("uncl_conv3x3_tc", src, src_stride, wt, b, dst, dst_stride, _lib.BF16, n, ci, h, w, co, pad, ACT_RELU,
                      emit_skip, 0, None, None, None, None)
@@ -325,8 +340,13 @@ class _GeneratorBase(nn.Module):
             co = f if i >= 2 else up_c // 2
             mid = buf(co, sk_s + 2, sk_s + 2)
             if 3 - i < nfused:
-                call("uncl_conv3x3_tc_skipcat", cb, st(cb), P["u%d_0" % i][0], P["u%d_0" % i][1], mid, st(mid), _lib.BF16, n,
-                     sk_c, sk_s, sk_s, co, 2, ACT_RELU)
+                rows = P.get("u%d_0_rows" % i) if self.row_kernel else None
+                if rows is not None:
+                    call("uncl_conv3x3_tc_rows_skipcat", cb, st(cb), rows, P["u%d_0" % i][0], P["u%d_0" % i][1], mid, st(mid), n,
+                         sk_c, sk_s, sk_s, 2, ACT_RELU)
+                else:
+                    call("uncl_conv3x3_tc_skipcat", cb, st(cb), P["u%d_0" % i][0], P["u%d_0" % i][1], mid, st(mid), _lib.BF16, n,
+                         sk_c, sk_s, sk_s, co, 2, ACT_RELU)
             else:
                 self._conv3(P, "u%d_0" % i, cb, st(cb), mid, st(mid), n, 4 * sk_c, sk_s, sk_s, co, 2)
             last = i == 3
