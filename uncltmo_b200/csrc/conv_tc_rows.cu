@@ -83,24 +83,27 @@ __device__ __forceinline__ uint32_t rw_bf16x2_sqrt_eps(uint32_t v) {
   return pack_bf16x2(fast_sqrt(lo + 1e-8f), fast_sqrt(hi + 1e-8f));
 }
 
-template <bool kDerive>
+template <bool kDerive, int G>
 __global__ void __launch_bounds__(kDerive ? kRwThreadsDerive : kRwThreads, 1)
 conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RwParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   uint8_t* stage_base = smem;
   uint8_t* wres = smem + (size_t)p.stages * p.stage_bytes;            // resident filter bank
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wres + p.w_total + 128);   // 128 B of slack: the kx = 2 reads of a stage's last row
+  // 128 B of slack (the kx = 2 reads of a stage's last row), then [32] bias + [32] out conv weights, 16-byte aligned: the
+  // epilogue reads them as broadcast LDS.128 - every shared-memory wavefront competes with the MMAs' operand reads
+  float* s_bias = reinterpret_cast<float*>(wres + p.w_total + 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 64);
   uint64_t* full = bars;
   uint64_t* empty = bars + kRwMaxStages;
   uint64_t* rowdone = bars + 2 * kRwMaxStages;
   uint64_t* sfree = rowdone + kRwSlots;
   uint64_t* wfull = sfree + kRwSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [32] bias + [32] out conv weights
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_items = p.num_items, nchunk = p.nchunk, stages = p.stages, stage_bytes = p.stage_bytes, G = p.G;
+  const int num_items = p.num_items, nchunk = p.nchunk, stages = p.stages;
+  constexpr int stage_bytes = G * 4 * kRwRowBytes;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -156,18 +159,22 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     // One warp: the rows of a strip accumulate into rotating TMEM slots and a row's MMAs are ordinary K-loop accumulation
-    // into ONE slot (first MMA overwrites).  Waits are warp-uniform, the MMAs of a row are straight-line code of one
-    // elected lane (a divergent issuing thread costs 150+ cycles per instruction, profiles/README.md).
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-    const uint32_t a_lo_const = ((uint32_t)(G * 128) & 0x3fffu) << 16;   // LBO_A: channel-block stride = G rows x 2048 B
-    const uint32_t b_lo_const = 96u << 16;                               // LBO_B = 96 x 16 B
-    const uint32_t stage0_16 = smem_u32(stage_base) >> 4, stage_16 = (uint32_t)stage_bytes >> 4;
+    // into ONE slot (first MMA overwrites).  The issuing warp is a serial, latency-bound instruction stream (R2UR, uniform
+    // adds, barrier polls: profiles/README.md), so one elected lane issues ALL rows of a (row group, K chunk) stage as
+    // straight-line code - descriptor offsets are immediates (G is a template parameter) - and polls the slot barriers
+    // itself between rows.
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    constexpr uint32_t a_lo_const = ((uint32_t)(G * 128) & 0x3fffu) << 16;   // LBO_A: channel-block stride = G rows x 2048 B
+    constexpr uint32_t b_lo_const = 96u << 16;                               // LBO_B = 96 x 16 B
+    constexpr uint32_t stage_16 = (uint32_t)stage_bytes >> 4;
+    constexpr uint32_t a_kstep_16 = (uint32_t)(2 * G * 128);
+    const uint32_t stage0_16 = smem_u32(stage_base) >> 4;
     const uint32_t wres_16 = smem_u32(wres) >> 4;
-    const uint32_t a_kstep_16 = (uint32_t)(2 * G * 128);
     int stage = 0;
     uint32_t phase = 0;
-    int t = 0;   // rows issued by this CTA so far: row t uses slot t % 5 for the (t / 5)-th time
+    int slot0 = 0;          // slot of the next row group's first row
+    uint32_t par0 = 1;      // parity its sfree wait uses: (use count & 1) ^ 1
     mbar_wait(wfull, 0);
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const RwItem it = rw_decode(p, item);
@@ -180,33 +187,37 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
           const uint32_t wch = kDerive ? (uint32_t)p.prog_wch[ch] : (uint32_t)ch;
           const uint32_t b_base = b_lo_const | (wres_16 + wch * (uint32_t)(kRwWChunk >> 4));
           const bool first = ch == 0, last = ch == nchunk - 1;
-          for (int r = 0; r < rows; ++r) {
-            const int tt = t + r;
-            const int slot = tt % kRwSlots;
-            if (first) {   // the slot's previous contents have been read by the three epilogues that needed them
-              mbar_wait(&sfree[slot], (uint32_t)(((tt / kRwSlots) & 1) ^ 1));
-              tc_fence_after();
-            }
-            if (elect_one()) {
-              const uint32_t d = tmem_base + (uint32_t)(slot * 96);
-              const uint32_t a_row = a_lo_const | (sa16 + (uint32_t)r * 128u);
+          if (elect_one()) {
+            int slot = slot0;
+            uint32_t par = par0;
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                  tc_mma_bf16(d, a_row + (uint32_t)ks * a_kstep_16 + (uint32_t)kx, desc_hi,
-                              b_base + (uint32_t)((ks * 3 + kx) * 192), desc_hi, idesc, (ks > 0 || kx > 0) ? 1u : (first ? 0u : 1u));
+            for (int r = 0; r < G; ++r) {
+              if (r < rows) {
+                if (first) {   // the slot's previous contents have been read by the three epilogues that needed them
+                  mbar_wait(&sfree[slot], par);
+                  tc_fence_after();
                 }
+                const uint32_t d = tmem_base + (uint32_t)(slot * 96);
+                const uint32_t a_row = a_lo_const | (sa16 + (uint32_t)(r * 128));
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+                  for (int kx = 0; kx < 3; ++kx) {
+                    tc_mma_bf16(d, a_row + (uint32_t)(ks * a_kstep_16 + kx), desc_hi, b_base + (uint32_t)((ks * 3 + kx) * 192),
+                                desc_hi, idesc, (ks > 0 || kx > 0) ? 1u : (first ? 0u : 1u));
+                  }
+                }
+                if (last) tc_commit(&rowdone[slot]);
+                if (++slot == kRwSlots) { slot = 0; par ^= 1; }
               }
-              if (last) tc_commit(&rowdone[slot]);
             }
-            __syncwarp();
+            tc_commit(&empty[stage]);
           }
-          if (elect_one()) tc_commit(&empty[stage]);
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        t += rows;
+        slot0 += rows;
+        if (slot0 >= kRwSlots) { slot0 -= kRwSlots; par0 ^= 1; }
       }
     }
     __syncwarp();
@@ -282,9 +293,9 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
   } else {
     // =============================== epilogue ===============================
     // 16 warps = 4 sets x 4 TMEM lane quarters; set s finishes the output rows u with u % 4 == s.  Output row u (CTA-wide
-    // row counter; rows u, u+1, u+2 are its three input rows) waits for row u+2's MMAs, adds the ky = 0 / 1 / 2 column
-    // groups of slots u, u+1, u+2 and releases its share of the three slots.  Rows whose three inputs are not in one
-    // strip (the last two of a strip, and the virtual rows -2, -1 before the first) only do the barrier protocol.
+    // row counter; rows u, u+1, u+2 are its three input rows) takes the ky = 0 / 1 / 2 column group of slot u / u+1 / u+2
+    // as each of those rows completes and releases its share of that slot at once.  Rows whose three inputs are not in
+    // one strip (the last two of a strip, and the virtual rows -2, -1 before the first) only do the barrier protocol.
     const int quarter = warp & 3, set = (warp - 2) >> 2;
     const int xl = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
@@ -307,41 +318,40 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         if ((u & 3) != set) continue;
         const bool valid = j < rows_out;
         if (!valid && last_item) break;   // no later row exists: nothing waits for these slots any more
-        {
-          const int r2 = u + 2;
-          mbar_wait(&rowdone[r2 % kRwSlots], (uint32_t)((r2 / kRwSlots) & 1));
-          tc_fence_after();
-        }
+        // Slot r is read right after row r completes by all three output rows that need it (r, r-1, r-2), so it is free
+        // again one epilogue turn after its own MMAs - the issuing warp can run up to four rows ahead of the epilogue.
         float v[32];
-        if (valid) {
-          uint32_t r[32];
-          tc_ld32(tmem_base + lane_base + (uint32_t)((u % kRwSlots) * 96), r);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]);
-          tc_ld32(tmem_base + lane_base + (uint32_t)(((u + 1) % kRwSlots) * 96 + 32), r);
+        for (int k = 0; k < 3; ++k) {
+          const int r = u + k;
+          if (r < 0) continue;
+          const int slot = r % kRwSlots;
+          mbar_wait(&rowdone[slot], (uint32_t)((r / kRwSlots) & 1));
+          tc_fence_after();
+          if (valid) {
+            uint32_t rb[32];
+            tc_ld32(tmem_base + lane_base + (uint32_t)(slot * 96 + k * 32), rb);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] += __uint_as_float(r[c]);
-          tc_ld32(tmem_base + lane_base + (uint32_t)(((u + 2) % kRwSlots) * 96 + 64), r);
-#pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] += __uint_as_float(r[c]);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-            if (u + k >= 0) mbar_arrive(&sfree[(u + k) % kRwSlots]);
+            for (int c = 0; c < 32; ++c) v[c] = k == 0 ? __uint_as_float(rb[c]) : v[c] + __uint_as_float(rb[c]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sfree[slot]);
         }
         if (!valid) continue;
         const int oy = it.y0 + j, ox = it.x0 + xl;
         if (xl < BW && ox < Wc) {
           const long pix = (long)oy * Wo + ox;
           float logit = outc_b;
+          const float4* sb4 = reinterpret_cast<const float4*>(s_bias);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
+            const float4 b0 = sb4[2 * g], b1 = sb4[2 * g + 1];
             float o[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) o[c] = fmaxf(v[g * 8 + c] + s_bias[g * 8 + c], act_floor);
+            o[0] = fmaxf(v[g * 8 + 0] + b0.x, act_floor); o[1] = fmaxf(v[g * 8 + 1] + b0.y, act_floor);
+            o[2] = fmaxf(v[g * 8 + 2] + b0.z, act_floor); o[3] = fmaxf(v[g * 8 + 3] + b0.w, act_floor);
+            o[4] = fmaxf(v[g * 8 + 4] + b1.x, act_floor); o[5] = fmaxf(v[g * 8 + 5] + b1.y, act_floor);
+            o[6] = fmaxf(v[g * 8 + 6] + b1.z, act_floor); o[7] = fmaxf(v[g * 8 + 7] + b1.w, act_floor);
             if (out != nullptr) {
               bf16* op = out + (long)it.n * p.out_img_stride + (long)g * cb_stride + pix * 8;
               store8(op, o);
@@ -354,8 +364,10 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
               }
             }
             if (fuse_outc) {
-#pragma unroll
-              for (int c = 0; c < 8; ++c) logit = fmaf(o[c], s_bias[32 + g * 8 + c], logit);
+              const float4 w0 = sb4[8 + 2 * g], w1 = sb4[8 + 2 * g + 1];
+              logit = fmaf(o[0], w0.x, logit); logit = fmaf(o[1], w0.y, logit); logit = fmaf(o[2], w0.z, logit);
+              logit = fmaf(o[3], w0.w, logit); logit = fmaf(o[4], w1.x, logit); logit = fmaf(o[5], w1.y, logit);
+              logit = fmaf(o[6], w1.z, logit); logit = fmaf(o[7], w1.w, logit);
             }
           }
           if (fuse_outc) {
@@ -413,12 +425,12 @@ int rw_plan(RwParams& p, int N, int C_in, int H, int W, int pad, int Wc, int der
   // to an earlier group, so G <= 3.  One-chunk layers commit row by row and take four rows per barrier round trip.
   const int want_stages = derive ? 5 : 3;
   int G = p.nchunk == 1 ? 4 : 3;
-  for (; G >= 1; --G) {
+  for (; G >= 2; --G) {
     p.stage_bytes = G * 4 * kRwRowBytes;
     p.stages = budget / p.stage_bytes;
     if (p.stages >= want_stages) break;
   }
-  UNCL_REQUIRE(G >= 1 && p.stages >= want_stages, "%s: filter bank of C_in=%d does not fit shared memory next to the stage ring", what, C_in);
+  UNCL_REQUIRE(G >= 2 && p.stages >= want_stages, "%s: filter bank of C_in=%d does not fit shared memory next to the stage ring", what, C_in);
   if (p.stages > kRwMaxStages) p.stages = kRwMaxStages;
   p.G = G;
   p.R = rw_pick_R(N, p.nbands, p.Ho, sms);
@@ -461,14 +473,26 @@ int rw_launch(const void* in, long in_img_stride, const void* w_rows, const floa
   CUtensorMap tmap;
   CUresult r = encode_blocked_bf16(&tmap, in, W, H, (derive ? C_in / 2 : C_in) / 8, N, in_img_stride, 128, p.G, 4);
   if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
-  static thread_local int smem_ok = 0, smem_dev = -1;
-  static thread_local int smem_ok_d = 0, smem_dev_d = -1;
-  cudaError_t e = derive ? ensure_smem(conv3x3_tc_rows_kernel<true>, smem_bytes, smem_ok_d, smem_dev_d)
-                         : ensure_smem(conv3x3_tc_rows_kernel<false>, smem_bytes, smem_ok, smem_dev);
-  if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));
   const int grid = p.num_items < sms ? p.num_items : sms;
-  if (derive) conv3x3_tc_rows_kernel<true><<<grid, kRwThreadsDerive, smem_bytes, stream>>>(tmap, p);
-  else conv3x3_tc_rows_kernel<false><<<grid, kRwThreads, smem_bytes, stream>>>(tmap, p);
+  // one instantiation per (fused skip operators, rows per stage): the issuing warp's descriptor offsets are immediates
+  static thread_local int smem_ok[6] = {0, 0, 0, 0, 0, 0}, smem_dev[6] = {-1, -1, -1, -1, -1, -1};
+#define RW_LAUNCH(D, GG, slot_)                                                                                       \
+  do {                                                                                                                \
+    cudaError_t e = ensure_smem(conv3x3_tc_rows_kernel<D, GG>, smem_bytes, smem_ok[slot_], smem_dev[slot_]);            \
+    if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));         \
+    conv3x3_tc_rows_kernel<D, GG><<<grid, D ? kRwThreadsDerive : kRwThreads, smem_bytes, stream>>>(tmap, p);            \
+  } while (0)
+  if (derive) {
+    if (p.G == 3) RW_LAUNCH(true, 3, 0);
+    else if (p.G == 2) RW_LAUNCH(true, 2, 1);
+    else return uncl_set_error(UNCL_EINVAL, "%s: no kernel for %d rows per stage", what, p.G);
+  } else {
+    if (p.G == 4) RW_LAUNCH(false, 4, 2);
+    else if (p.G == 3) RW_LAUNCH(false, 3, 3);
+    else if (p.G == 2) RW_LAUNCH(false, 2, 4);
+    else return uncl_set_error(UNCL_EINVAL, "%s: no kernel for %d rows per stage", what, p.G);
+  }
+#undef RW_LAUNCH
   return uncl_check_launch(what);
 }
 
@@ -552,7 +576,7 @@ extern "C" int uncl_conv3x3_tc_rows_plan(int N, int C_in, int H, int W, int pad,
   const int nchunk = C_in / 32;
   const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwSlots + 1) * 8 + 16 + 64 * 4 + 256;
   if (nchunk > kRwMaxProg || (derive && C_in % 128 != 0) ||
-      227 * 1024 - tail - nchunk * kRwWChunk < (derive ? 5 : 3) * 4 * kRwRowBytes)
+      227 * 1024 - tail - nchunk * kRwWChunk < (derive ? 5 : 3) * 2 * 4 * kRwRowBytes)
     return UNCL_OK;   // plan[0] = 0: not eligible
   RwParams p{};
   int smem = 0;
