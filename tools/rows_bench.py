@@ -13,6 +13,9 @@ g = torch.Generator(device=dev).manual_seed(1)
 # name, logical C_in, H = W, pad, fused skip operators, fused out conv
 LAYERS = [("inc.conv1", 32, 254, 0, False, False), ("up2.conv0", 256, 122, 2, True, False), ("up2.conv1", 32, 124, 2, False, False),
           ("up3.conv0", 128, 252, 2, True, False), ("up3.conv1", 32, 254, 2, False, True)]
+if len(sys.argv) > 3:   # experiments around up3.conv1: no trailing columns, no fused out conv, no padding
+    LAYERS = [("u31", 32, 254, 2, False, True), ("u31-notail", 32, 250, 2, False, True), ("u31-nofuse", 32, 254, 2, False, False),
+              ("u31-nofuse-notail", 32, 250, 2, False, False), ("pad0-fuse-252", 32, 254, 0, False, True)]
 
 
 def timed(fn):

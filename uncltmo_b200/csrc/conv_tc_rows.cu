@@ -21,18 +21,28 @@
 // Reference operator: models/unet_multi_filters/unet_parts.py:57-87 (double_conv), :126-141 / :183-193 (ConvTranspose
 // 3x3 pair of `up`), :311-332 (skip operators + concat), :338-345 (outconv).
 // Weights: bf16 [C_in/32][2 ksteps][3 kx][2][96 (ky, co)][8] (packing.conv3x3_tc_rows).
+#include <cstdio>
+#include <cstdlib>
+
 #include "tc_ptx.cuh"
 
 namespace {
 
 using namespace tcptx;
 
-constexpr int kRwThreads = 576;        // warp 0: TMA producer, 1: MMA issuer, 2-17: epilogue
-constexpr int kRwThreadsDerive = 704;  // ... + warps 18-21: skip-operator warps
-constexpr int kRwDeriveWarp0 = 18;
+// warp 0: TMA producer, 1: MMA issuer, then the epilogue warps (sets of four, one per TMEM lane quarter).  An output row
+// costs an epilogue warp ~3000 cycles of mostly exposed latency (three barrier waits, three tcgen05.ld round trips, the
+// bias / activation / store tail: tools/gpu_rows_probe2.sh), so the one-chunk layers (336 MMA cycles per row) are bound by
+// the epilogue warps' instruction stream (six sets were slower than four: 344 -> 550 us on inc.conv1 - more warps only
+// dilute the issue slots).  The one-chunk layers therefore use the ring variant below (one tcgen05.ld per output row).
+constexpr int kRwSets = 4, kRwSetsDerive = 4;
+constexpr int kRwThreads = (2 + 4 * kRwSets) * 32;                 // 832
+constexpr int kRwDeriveWarp0 = 2 + 4 * kRwSetsDerive;              // warps 18-21: skip-operator warps
+constexpr int kRwThreadsDerive = (kRwDeriveWarp0 + 4) * 32;        // 704
 constexpr int kRwDeriveWarps = 4;
 constexpr int kRwMaxStages = 8;
 constexpr int kRwSlots = 5;            // accumulator slots of 96 TMEM columns
+constexpr int kRwRing = 16;            // ring variant: accumulator groups of 32 TMEM columns (one per output row)
 constexpr int kRwMaxProg = 16;
 constexpr int kRwRowBytes = 128 * 16;  // one row of one channel block in shared memory
 constexpr int kRwWChunk = 2 * 3 * 2 * 96 * 16;   // packed weights of 32 input channels: 18432 B
@@ -52,6 +62,8 @@ struct RwParams {
   int derive;
   unsigned char prog_kind[kRwMaxProg], prog_cb[kRwMaxProg], prog_wch[kRwMaxProg], prog_back[kRwMaxProg];
   int act, emit_skip, fuse_outc;
+  int ring;    // one-chunk layers: ring variant of the accumulators (host switch: 1 by default)
+  int probe;   // -DUNCL_PROBES build only (tools/): 1 = no TMA traffic after the first ring fill, 2 = epilogue does the barrier protocol only, 4 = one MMA per row instead of six (results are wrong while set), 8 = print the per-role cycle accounting of CTA 0
 };
 
 struct RwItem {
@@ -83,7 +95,18 @@ __device__ __forceinline__ uint32_t rw_bf16x2_sqrt_eps(uint32_t v) {
   return pack_bf16x2(fast_sqrt(lo + 1e-8f), fast_sqrt(hi + 1e-8f));
 }
 
-template <bool kDerive, int G>
+// 32 lanes x 32 columns of zeros into TMEM (ring variant: an accumulator group is handed back cleared)
+__device__ __forceinline__ void rw_tmem_zero32(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(z)
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+template <bool kDerive, int G, bool kRing>
 __global__ void __launch_bounds__(kDerive ? kRwThreadsDerive : kRwThreads, 1)
 conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RwParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -97,8 +120,8 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
   uint64_t* full = bars;
   uint64_t* empty = bars + kRwMaxStages;
   uint64_t* rowdone = bars + 2 * kRwMaxStages;
-  uint64_t* sfree = rowdone + kRwSlots;
-  uint64_t* wfull = sfree + kRwSlots;
+  uint64_t* sfree = rowdone + kRwRing;
+  uint64_t* wfull = sfree + kRwRing;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -110,7 +133,7 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     const uint32_t extra = kDerive ? (uint32_t)kRwDeriveWarps : 0u;
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1 + extra); mbar_init(&empty[s], 1 + extra); }
     // a slot is read by the epilogues of three output rows (its ky = 0, 1, 2 column groups), four warps each
-    for (int s = 0; s < kRwSlots; ++s) { mbar_init(&rowdone[s], 1); mbar_init(&sfree[s], 12); }
+    for (int s = 0; s < kRwRing; ++s) { mbar_init(&rowdone[s], 1); mbar_init(&sfree[s], kRing ? 4 : 12); }
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -126,6 +149,15 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if constexpr (kRing) {   // the MMAs only ever accumulate: all sixteen groups start cleared
+    if (warp >= 2 && warp < 2 + 4 * kRwSets) {
+      const uint32_t lb = (uint32_t)((warp & 3) * 32) << 16;
+      for (int g = (warp - 2) >> 2; g < kRwRing; g += kRwSets) rw_tmem_zero32(tmem_base + lb + (uint32_t)(g * 32));
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -144,7 +176,9 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
           for (int ch = 0; ch < nchunk; ++ch) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = stage_base + (size_t)stage * stage_bytes;
-            if (!kDerive || p.prog_kind[ch] == 0) {
+            if (UNCL_PROBE(p.probe, 1) && (item != (int)blockIdx.x || r0 >= G * stages)) {
+              mbar_arrive(&full[stage]);
+            } else if (!kDerive || p.prog_kind[ch] == 0) {
               mbar_expect_tx(&full[stage], box_bytes);
               tma_load_4d(sa, &tmap, &full[stage], it.bx * 2, it.by + r0, kDerive ? (int)p.prog_cb[ch] : ch * 4, it.n);
             } else {
@@ -176,17 +210,76 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     int slot0 = 0;          // slot of the next row group's first row
     uint32_t par0 = 1;      // parity its sfree wait uses: (use count & 1) ^ 1
     mbar_wait(wfull, 0);
+#ifdef UNCL_PROBES
+    long long mw_full = 0, mw_issue = 0, mrows = 0;
+    const long long mt0 = clock64();
+#endif
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const RwItem it = rw_decode(p, item);
       for (int r0 = 0; r0 < it.rows_in; r0 += G) {
         const int rows = min(G, it.rows_in - r0);
         for (int ch = 0; ch < nchunk; ++ch) {
+#ifdef UNCL_PROBES
+          const long long ma = clock64();
+#endif
           mbar_wait(&full[stage], phase);
+#ifdef UNCL_PROBES
+          const long long mb = clock64();
+          mw_full += mb - ma;
+#endif
           tc_fence_after();
           const uint32_t sa16 = stage0_16 + (uint32_t)stage * stage_16;
           const uint32_t wch = kDerive ? (uint32_t)p.prog_wch[ch] : (uint32_t)ch;
           const uint32_t b_base = b_lo_const | (wres_16 + wch * (uint32_t)(kRwWChunk >> 4));
           const bool first = ch == 0, last = ch == nchunk - 1;
+          if constexpr (kRing) {
+            // Ring variant (one K chunk per row): output row u owns ONE group of 32 TMEM columns at position (-u) mod 16,
+            // so the N' = 96 columns (ky = 0, 1, 2) of input row tt land on the groups of outputs tt, tt-1, tt-2, which are
+            // adjacent - every MMA accumulates, the epilogue reads one group and hands it back cleared.  Rows whose three
+            // groups wrap around the ring (2 of 16) issue an N = 64 and an N = 32 instruction instead of one N = 96.
+            constexpr uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint32_t idesc32 = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+            if (elect_one()) {
+              uint32_t tt = (uint32_t)slot0;   // ring variant: slot0 counts rows (never wrapped at five)
+#pragma unroll
+              for (int r = 0; r < G; ++r) {
+                if (r < rows) {
+                  mbar_wait(&sfree[tt & 15u], (((tt + 2u) >> 4) & 1u) ^ 1u);   // group of output tt: cleared by its previous owner
+                  tc_fence_after();
+                  const uint32_t pos = (16u - (tt & 15u)) & 15u;
+                  const uint32_t d = tmem_base + pos * 32u;
+                  const uint32_t a_row = a_lo_const | (sa16 + (uint32_t)(r * 128));
+                  if (pos <= 13u) {
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+                      for (int kx = 0; kx < 3; ++kx) {
+                        if (UNCL_PROBE(p.probe, 4) && (ks > 0 || kx > 0)) continue;
+                        tc_mma_bf16(d, a_row + (uint32_t)(ks * a_kstep_16 + kx), desc_hi, b_base + (uint32_t)((ks * 3 + kx) * 192),
+                                    desc_hi, idesc, 1u);
+                      }
+                    }
+                  } else {
+                    const bool two_first = pos == 14u;   // groups 14, 15 | 0   or   15 | 0, 1
+                    const uint32_t id_a = two_first ? idesc64 : idesc32, id_b = two_first ? idesc32 : idesc64;
+                    const uint32_t nb = two_first ? 64u : 32u;   // B rows (16 B each) taken by the first instruction
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+                      for (int kx = 0; kx < 3; ++kx) {
+                        const uint32_t a = a_row + (uint32_t)(ks * a_kstep_16 + kx), b = b_base + (uint32_t)((ks * 3 + kx) * 192);
+                        tc_mma_bf16(d, a, desc_hi, b, desc_hi, id_a, 1u);
+                        tc_mma_bf16(tmem_base, a, desc_hi, b + nb, desc_hi, id_b, 1u);
+                      }
+                    }
+                  }
+                  tc_commit(&rowdone[tt & 15u]);
+                  ++tt;
+                }
+              }
+              tc_commit(&empty[stage]);
+            }
+          } else
           if (elect_one()) {
             int slot = slot0;
             uint32_t par = par0;
@@ -203,6 +296,7 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
                   for (int kx = 0; kx < 3; ++kx) {
+                    if (UNCL_PROBE(p.probe, 4) && (ks > 0 || kx > 0)) continue;
                     tc_mma_bf16(d, a_row + (uint32_t)(ks * a_kstep_16 + kx), desc_hi, b_base + (uint32_t)((ks * 3 + kx) * 192),
                                 desc_hi, idesc, (ks > 0 || kx > 0) ? 1u : (first ? 0u : 1u));
                   }
@@ -214,14 +308,25 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             tc_commit(&empty[stage]);
           }
           __syncwarp();
+#ifdef UNCL_PROBES
+          mw_issue += clock64() - mb;
+#endif
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
+#ifdef UNCL_PROBES
+        mrows += rows;
+#endif
         slot0 += rows;
-        if (slot0 >= kRwSlots) { slot0 -= kRwSlots; par0 ^= 1; }
+        if (!kRing && slot0 >= kRwSlots) { slot0 -= kRwSlots; par0 ^= 1; }
       }
     }
+#ifdef UNCL_PROBES
+    if ((p.probe & 8) && blockIdx.x == 0 && lane == 0)
+      printf("rows probe: MMA warp total %lld cycles, %lld rows, per row: wait full %lld, issue block (incl. slot waits) %lld\n",
+             clock64() - mt0, mrows, mw_full / max(mrows, 1ll), mw_issue / max(mrows, 1ll));
+#endif
     __syncwarp();
-  } else if (warp >= kRwDeriveWarp0) {
+  } else if (kDerive && warp >= kRwDeriveWarp0) {
     // =============================== fused skip operators ===============================
     // Same ring program as conv_tc_merged.cu: at a TMA position these warps only add their arrival; at the `square`
     // position they wait for the skip chunk (previous ring position), and write x*x into this stage and sqrt(x + 1e-8)
@@ -292,10 +397,11 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     }
   } else {
     // =============================== epilogue ===============================
-    // 16 warps = 4 sets x 4 TMEM lane quarters; set s finishes the output rows u with u % 4 == s.  Output row u (CTA-wide
+    // kSets sets x 4 TMEM lane quarters; set s finishes the output rows u with u % kSets == s.  Output row u (CTA-wide
     // row counter; rows u, u+1, u+2 are its three input rows) takes the ky = 0 / 1 / 2 column group of slot u / u+1 / u+2
     // as each of those rows completes and releases its share of that slot at once.  Rows whose three inputs are not in
     // one strip (the last two of a strip, and the virtual rows -2, -1 before the first) only do the barrier protocol.
+    constexpr int kSets = kDerive ? kRwSetsDerive : kRwSets;
     const int quarter = warp & 3, set = (warp - 2) >> 2;
     const int xl = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
@@ -306,6 +412,10 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     bf16* const out = p.out;
     const float outc_b = fuse_outc ? __ldg(p.outc_b) : 0.f;
     int t = 0;
+#ifdef UNCL_PROBES
+    long long pw[3] = {0, 0, 0}, pwork = 0, prows = 0;
+    const long long pt0 = clock64();
+#endif
     for (int item = (int)blockIdx.x - (int)gridDim.x; item < num_items; item += (int)gridDim.x) {
       // item < 0: the two virtual rows before the CTA's first strip
       const bool virt = item < 0;
@@ -315,20 +425,48 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
       const int tb = virt ? -2 : t;
       for (int j = 0; j < rows_in; ++j) {
         const int u = tb + j;
-        if ((u & 3) != set) continue;
+        if ((u + 2 * kSets) % kSets != set) continue;
         const bool valid = j < rows_out;
         if (!valid && last_item) break;   // no later row exists: nothing waits for these slots any more
         // Slot r is read right after row r completes by all three output rows that need it (r, r-1, r-2), so it is free
         // again one epilogue turn after its own MMAs - the issuing warp can run up to four rows ahead of the epilogue.
         float v[32];
+        if constexpr (kRing) {
+          const int r2 = u + 2;
+#ifdef UNCL_PROBES
+          const long long pa = clock64();
+#endif
+          mbar_wait(&rowdone[r2 & 15], (uint32_t)((r2 >> 4) & 1));   // all three contributions have landed
+#ifdef UNCL_PROBES
+          pw[2] += clock64() - pa;
+#endif
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(((16 - (u & 15)) & 15) * 32);
+          if (valid && !UNCL_PROBE(p.probe, 2)) {
+            uint32_t rb[32];
+            tc_ld32(taddr, rb);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(rb[c]);
+          }
+          rw_tmem_zero32(taddr);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sfree[u & 15]);
+        } else {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const int r = u + k;
           if (r < 0) continue;
           const int slot = r % kRwSlots;
+#ifdef UNCL_PROBES
+          const long long pa = clock64();
+#endif
           mbar_wait(&rowdone[slot], (uint32_t)((r / kRwSlots) & 1));
+#ifdef UNCL_PROBES
+          pw[k] += clock64() - pa;
+#endif
           tc_fence_after();
-          if (valid) {
+          if (valid && !UNCL_PROBE(p.probe, 2)) {
             uint32_t rb[32];
             tc_ld32(tmem_base + lane_base + (uint32_t)(slot * 96 + k * 32), rb);
 #pragma unroll
@@ -338,7 +476,11 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
           __syncwarp();
           if (lane == 0) mbar_arrive(&sfree[slot]);
         }
-        if (!valid) continue;
+        }
+#ifdef UNCL_PROBES
+        const long long pb = clock64();
+#endif
+        if (!valid || UNCL_PROBE(p.probe, 2)) continue;
         const int oy = it.y0 + j, ox = it.x0 + xl;
         if (xl < BW && ox < Wc) {
           const long pix = (long)oy * Wo + ox;
@@ -376,9 +518,17 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             p.out_img[o1] = 1.f / (1.f + __expf(-logit));
           }
         }
+#ifdef UNCL_PROBES
+        pwork += clock64() - pb; ++prows;
+#endif
       }
       if (!virt) t += rows_in;
     }
+#ifdef UNCL_PROBES
+    if ((p.probe & 8) && blockIdx.x == 0 && warp == 2 && lane == 0)
+      printf("rows probe: epilogue warp total %lld cycles, %lld rows, per row: wait A %lld B %lld C %lld, finish %lld\n", clock64() - pt0,
+             prows, pw[0] / max(prows, 1ll), pw[1] / max(prows, 1ll), pw[2] / max(prows, 1ll), pwork / max(prows, 1ll));
+#endif
   }
 
   tc_fence_before();
@@ -418,7 +568,7 @@ int rw_plan(RwParams& p, int N, int C_in, int H, int W, int pad, int Wc, int der
   p.nchunk = C_in / 32;
   p.w_total = p.nchunk * kRwWChunk;
   UNCL_REQUIRE(p.nchunk <= kRwMaxProg, "%s: C_in=%d too deep", what, C_in);
-  const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwSlots + 1) * 8 + 16 + 64 * 4 + 256;
+  const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwRing + 1) * 8 + 16 + 64 * 4 + 256;
   const int budget = 227 * 1024 - tail - p.w_total;
   // Rows per pipeline stage.  With several K chunks per row group a group's rows complete together, and row a + G + k of
   // the next group needs the slot of row a + G + k - 5, whose epilogue waits for row a + G + k - 3: that row must belong
@@ -470,26 +620,32 @@ int rw_launch(const void* in, long in_img_stride, const void* w_rows, const floa
   p.bias = bias; p.out = reinterpret_cast<bf16*>(out); p.out_img_stride = out_img_stride;
   p.outc_w = outc_w; p.outc_b = outc_b; p.out_img = out_img; p.out_logit = out_logit;
   p.act = act; p.emit_skip = emit_skip; p.fuse_outc = fuse_outc;
+  p.ring = 1;
+#ifdef UNCL_PROBES
+  if (getenv("UNCL_RW_NORING")) p.ring = 0;
+  if (const char* e = getenv("UNCL_RW_PROBE")) p.probe = atoi(e);
+#endif
   CUtensorMap tmap;
   CUresult r = encode_blocked_bf16(&tmap, in, W, H, (derive ? C_in / 2 : C_in) / 8, N, in_img_stride, 128, p.G, 4);
   if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
   const int grid = p.num_items < sms ? p.num_items : sms;
   // one instantiation per (fused skip operators, rows per stage): the issuing warp's descriptor offsets are immediates
   static thread_local int smem_ok[6] = {0, 0, 0, 0, 0, 0}, smem_dev[6] = {-1, -1, -1, -1, -1, -1};
-#define RW_LAUNCH(D, GG, slot_)                                                                                       \
+#define RW_LAUNCH(D, GG, RING, slot_)                                                                                      \
   do {                                                                                                                \
-    cudaError_t e = ensure_smem(conv3x3_tc_rows_kernel<D, GG>, smem_bytes, smem_ok[slot_], smem_dev[slot_]);            \
+    cudaError_t e = ensure_smem(conv3x3_tc_rows_kernel<D, GG, RING>, smem_bytes, smem_ok[slot_], smem_dev[slot_]);      \
     if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));         \
-    conv3x3_tc_rows_kernel<D, GG><<<grid, D ? kRwThreadsDerive : kRwThreads, smem_bytes, stream>>>(tmap, p);            \
+    conv3x3_tc_rows_kernel<D, GG, RING><<<grid, D ? kRwThreadsDerive : kRwThreads, smem_bytes, stream>>>(tmap, p);      \
   } while (0)
   if (derive) {
-    if (p.G == 3) RW_LAUNCH(true, 3, 0);
-    else if (p.G == 2) RW_LAUNCH(true, 2, 1);
+    if (p.G == 3) RW_LAUNCH(true, 3, false, 0);
+    else if (p.G == 2) RW_LAUNCH(true, 2, false, 1);
     else return uncl_set_error(UNCL_EINVAL, "%s: no kernel for %d rows per stage", what, p.G);
   } else {
-    if (p.G == 4) RW_LAUNCH(false, 4, 2);
-    else if (p.G == 3) RW_LAUNCH(false, 3, 3);
-    else if (p.G == 2) RW_LAUNCH(false, 2, 4);
+    if (p.G == 4 && p.nchunk == 1 && p.ring) RW_LAUNCH(false, 4, true, 5);
+    else if (p.G == 4) RW_LAUNCH(false, 4, false, 2);
+    else if (p.G == 3) RW_LAUNCH(false, 3, false, 3);
+    else if (p.G == 2) RW_LAUNCH(false, 2, false, 4);
     else return uncl_set_error(UNCL_EINVAL, "%s: no kernel for %d rows per stage", what, p.G);
   }
 #undef RW_LAUNCH
@@ -574,7 +730,7 @@ extern "C" int uncl_conv3x3_tc_rows_plan(int N, int C_in, int H, int W, int pad,
   for (int i = 0; i < 16; ++i) plan[i] = 0;
   const int Wo = W + 2 * pad - 2;
   const int nchunk = C_in / 32;
-  const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwSlots + 1) * 8 + 16 + 64 * 4 + 256;
+  const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwRing + 1) * 8 + 16 + 64 * 4 + 256;
   if (nchunk > kRwMaxProg || (derive && C_in % 128 != 0) ||
       227 * 1024 - tail - nchunk * kRwWChunk < (derive ? 5 : 3) * 2 * 4 * kRwRowBytes)
     return UNCL_OK;   // plan[0] = 0: not eligible
