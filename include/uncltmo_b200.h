@@ -79,20 +79,21 @@ int uncl_conv3x3_tc_skipcat(const void* in, long in_img_stride, const void* w_pa
 /* Tile plan of uncl_conv3x3_tc_skipcat (the 16 fields of uncl_conv3x3_tc_plan): pure host arithmetic, no GPU needed. */
 int uncl_conv3x3_tc_skipcat_plan(int N, int C_skip, int H, int W, int C_out, int pad, int* plan);
 
-/* The C_out = 32 layers of the generator at 124..256 pixels (inc.conv1, up2/up3.conv*: unet_parts.py:57-87, :126-141,
- * :183-193) through the row kernel (conv_tc_rows.cu): the three ky taps share one A read in N' = 96, an M block is one
- * image row of a 126-column band, every input row enters shared memory once per strip and the three terms of an output
- * pixel are added from the same TMEM lane of three accumulator slots.  Arguments as uncl_conv3x3_tc with C_out = 32 and
- * bf16 blocked output; w_rows = packing.conv3x3_tc_rows(w9), w_tail = packing.conv3x3_tc(w9) serves the output columns
- * past the last whole band (uncl_conv3x3_tc_rows_plan field 2; NULL allowed when that is 0). */
+/* The narrow layers of the generator at 122..256 pixels (inc.conv1, down0.conv*, up2/up3.conv*: unet_parts.py:57-87,
+ * :126-141, :183-193) through the row kernel (conv_tc_rows.cu): the three ky taps share one A read in N' = 3 C_out, an M
+ * block is one image row of a 126-column band, every input row enters shared memory once per strip and the three terms
+ * of an output pixel meet in one TMEM lane (added by the MMAs themselves in the ring variant, by the epilogue from three
+ * accumulator slots otherwise).  Arguments as uncl_conv3x3_tc with C_out = 32 or 64 and bf16 blocked output (fuse_outc:
+ * C_out = 32); w_rows = packing.conv3x3_tc_rows(w9), w_tail = packing.conv3x3_tc(w9) serves the output columns past the
+ * last whole band (uncl_conv3x3_tc_rows_plan field 2; NULL allowed when that is 0). */
 int uncl_conv3x3_tc_rows(const void* in, long in_img_stride, const void* w_rows, const void* w_tail, const float* bias,
-                         void* out, long out_img_stride, int N, int C_in, int H, int W, int pad, int act, int emit_skip,
-                         int fuse_outc, const float* outc_w, const float* outc_b, float* out_img, float* out_logit,
-                         uncl_stream_t stream);
+                         void* out, long out_img_stride, int N, int C_in, int H, int W, int C_out, int pad, int act,
+                         int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b, float* out_img,
+                         float* out_logit, uncl_stream_t stream);
 
-/* uncl_conv3x3_tc_skipcat (unet_parts.py:311-332, skip operators built in shared memory) through the row kernel.
+/* uncl_conv3x3_tc_skipcat (unet_parts.py:311-332, skip operators built in shared memory, C_out = 32) through the row kernel.
  * `in` = [x2 (C_skip) | x1 (C_skip)] bf16 blocked; w_rows / w_tail = packing.conv3x3_tc_rows / packing.conv3x3_tc of the
- * full [9][4*C_skip][32] bank in concat order.  4*C_skip*576 B of filters must fit shared memory (C_skip = 32). */
+ * full [9][4*C_skip][32] bank in concat order.  4*C_skip*576 B of filters must fit shared memory (C_skip = 32, 64). */
 int uncl_conv3x3_tc_rows_skipcat(const void* in, long in_img_stride, const void* w_rows, const void* w_tail,
                                  const float* bias, void* out, long out_img_stride, int N, int C_skip, int H, int W, int pad,
                                  int act, uncl_stream_t stream);
@@ -101,8 +102,8 @@ int uncl_conv3x3_tc_rows_skipcat(const void* in, long in_img_stride, const void*
  * sms = SMs to balance the strips over.  plan[16] = { eligible (0: the filter bank does not fit - use uncl_conv3x3_tc),
  *   columns computed by the row kernel, trailing columns left to the older kernels, bands, band width, strip height,
  *   strips per band, work items, rows per pipeline stage, K chunks per row group, pipeline stages, stage bytes, resident
- *   filter bytes, dynamic shared memory bytes, sms, 0 }. */
-int uncl_conv3x3_tc_rows_plan(int N, int C_in, int H, int W, int pad, int derive, int sms, int* plan);
+ *   filter bytes, dynamic shared memory bytes, sms, ring variant (1) or slot variant (0) of the accumulators }. */
+int uncl_conv3x3_tc_rows_plan(int N, int C_in, int H, int W, int C_out, int pad, int derive, int sms, int* plan);
 
 /* Tile plan uncl_conv3x3_tc would use for a problem: pure host arithmetic, callable without a GPU (tests check the tile
  * coverage and that uncltmo_b200/packing.py packs the weights for the kernel the library will pick).

@@ -13,40 +13,62 @@ def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-def _problem(ci, h, n, seed):
+def _problem(ci, h, n, seed, co=32):
     g = torch.Generator(device="cuda").manual_seed(seed)
     x = torch.randn((n, ci // 8, h, h, 8), device="cuda", generator=g).to(torch.bfloat16)
-    w9 = (torch.randn((9, ci, 32), device="cuda", generator=g) / (9 * ci) ** 0.5).to(torch.bfloat16).float()
-    b = torch.randn(32, device="cuda", generator=g) * 0.1
+    w9 = (torch.randn((9, ci, co), device="cuda", generator=g) / (9 * ci) ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(co, device="cuda", generator=g) * 0.1
     return g, x, w9, b
 
 
 # (C_in, H = W, pad, images): the generator's own layers (inc.conv1 254 -> 252; up2.conv1 124 -> 126; up3.conv1 254 -> 256
 # with 4 trailing columns; up3.conv0 over the materialised concat 252 -> 254 with 2 trailing columns), a width that leaves
 # a 2-column tail after one band, tiny images (strips shorter than a row group), many images (several strips per CTA)
-@pytest.mark.parametrize("ci,h,pad,n", [(32, 254, 0, 2), (32, 124, 2, 2), (32, 254, 2, 1), (128, 252, 2, 1), (32, 130, 0, 1),
-                                        (32, 20, 0, 3), (64, 40, 2, 1), (32, 7, 2, 5), (32, 3, 0, 1), (32, 60, 0, 300),
-                                        (96, 66, 2, 7)])
-def test_row_kernel_matches_one_tap_and_fp32(ci, h, pad, n):
-    g, x, w9, b = _problem(ci, h, n, ci * 1000 + h + pad)
+@pytest.mark.parametrize("ci,h,pad,n,co", [(32, 254, 0, 2, 32), (32, 124, 2, 2, 32), (32, 254, 2, 1, 32), (128, 252, 2, 1, 32),
+                                           (32, 130, 0, 1, 32), (32, 20, 0, 3, 32), (64, 40, 2, 1, 32), (32, 7, 2, 5, 32),
+                                           (32, 3, 0, 1, 32), (32, 60, 0, 300, 32), (96, 66, 2, 7, 32),
+                                           # C_out = 64 (ring of eight 64-column groups): down0.conv0 126 -> 124, down0.conv1
+                                           # 124 -> 122, a trailing-column case, tiny and many-image cases
+                                           (32, 126, 0, 2, 64), (64, 124, 0, 2, 64), (64, 254, 2, 1, 64), (32, 9, 2, 4, 64),
+                                           (64, 30, 0, 150, 64), (128, 33, 2, 3, 64)])
+def test_row_kernel_matches_one_tap_and_fp32(ci, h, pad, n, co):
+    g, x, w9, b = _problem(ci, h, n, ci * 1000 + h + pad + co, co)
     ho = h + 2 * pad - 2
-    plan = packing.conv3x3_tc_rows_plan(n, ci, h, h, pad)
+    plan = packing.conv3x3_tc_rows_plan(n, ci, h, h, pad, co=co)
     assert plan[0] == 1 and plan[1] + plan[2] == ho
-    ref = torch.empty((n, 4, ho, ho, 8), device="cuda", dtype=torch.float32)
-    _lib.call("uncl_conv3x3_simt", x.float(), x.stride(0), w9, b, ref, ref.stride(0), n, ci, h, h, 32, pad, 1, 0, _lib.F32)
-    old = torch.empty((n, 4, ho, ho, 8), device="cuda", dtype=torch.bfloat16)
+    ref = torch.empty((n, co // 8, ho, ho, 8), device="cuda", dtype=torch.float32)
+    _lib.call("uncl_conv3x3_simt", x.float(), x.stride(0), w9, b, ref, ref.stride(0), n, ci, h, h, co, pad, 1, 0, _lib.F32)
+    old = torch.empty((n, co // 8, ho, ho, 8), device="cuda", dtype=torch.bfloat16)
     wt = packing.conv3x3_tc(w9)
-    _lib.call("uncl_conv3x3_tc", x, x.stride(0), wt, b, old, old.stride(0), _lib.BF16, n, ci, h, h, 32, pad, 1, 0, 0,
+    _lib.call("uncl_conv3x3_tc", x, x.stride(0), wt, b, old, old.stride(0), _lib.BF16, n, ci, h, h, co, pad, 1, 0, 0,
               None, None, None, None)
-    out = torch.full((n, 4, ho, ho, 8), float("nan"), device="cuda", dtype=torch.bfloat16)
-    _lib.call("uncl_conv3x3_tc_rows", x, x.stride(0), packing.conv3x3_tc_rows(w9), wt, b, out, out.stride(0), n, ci, h, h, pad, 1,
-              0, 0, None, None, None, None)
+    out = torch.full((n, co // 8, ho, ho, 8), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.call("uncl_conv3x3_tc_rows", x, x.stride(0), packing.conv3x3_tc_rows(w9), wt, b, out, out.stride(0), n, ci, h, h, co, pad,
+              1, 0, 0, None, None, None, None)
     torch.cuda.synchronize()
     assert not torch.isnan(out.float()).any()
     # same bf16 operands, fp32 accumulation, one bf16 rounding of the result: only the summation order differs
     assert rel(out, ref) <= 4e-3 and rel(old, ref) <= 4e-3
     assert (out.float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
     assert rel(out, old) <= 2e-3
+
+
+def test_row_kernel_skip_planes_64_channels():
+    """down0.conv1 with materialised skip planes: o, o^2, sqrt(o + 1e-8) into a 256-channel concat buffer."""
+    ci, co, h, n = 64, 64, 40, 3
+    g, x, w9, b = _problem(ci, h, n, 4242, co)
+    ho = h - 2
+    wt, wr = packing.conv3x3_tc(w9), packing.conv3x3_tc_rows(w9)
+    cat0 = torch.full((n, 32, ho, ho, 8), float("nan"), device="cuda", dtype=torch.bfloat16)
+    cat1 = torch.full((n, 32, ho, ho, 8), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.call("uncl_conv3x3_tc", x, x.stride(0), wt, b, cat0, cat0.stride(0), _lib.BF16, n, ci, h, h, co, 0, 1, 1, 0,
+              None, None, None, None)
+    _lib.call("uncl_conv3x3_tc_rows", x, x.stride(0), wr, wt, b, cat1, cat1.stride(0), n, ci, h, h, co, 0, 1, 1, 0,
+              None, None, None, None)
+    torch.cuda.synchronize()
+    for lo, hi in ((0, 8), (16, 24), (24, 32)):
+        assert not torch.isnan(cat1[:, lo:hi].float()).any() and rel(cat1[:, lo:hi], cat0[:, lo:hi]) <= 2e-3
+    assert torch.isnan(cat1[:, 8:16].float()).all()
 
 
 @pytest.mark.parametrize("h,pad,n", [(254, 2, 2), (60, 0, 3)])
@@ -62,12 +84,12 @@ def test_row_kernel_fused_out_conv_and_skip_planes(h, pad, n):
     _lib.call("uncl_conv3x3_tc", x, x.stride(0), wt, b, None, 0, _lib.BF16, n, ci, h, h, 32, pad, 1, 0, 1, ow, ob, img0, logit0)
     img = torch.full((n, ho, ho), float("nan"), device="cuda")
     logit = torch.full((n, ho, ho), float("nan"), device="cuda")
-    _lib.call("uncl_conv3x3_tc_rows", x, x.stride(0), wr, wt, b, None, 0, n, ci, h, h, pad, 1, 0, 1, ow, ob, img, logit)
+    _lib.call("uncl_conv3x3_tc_rows", x, x.stride(0), wr, wt, b, None, 0, n, ci, h, h, 32, pad, 1, 0, 1, ow, ob, img, logit)
     cat0 = torch.full((n, 16, ho, ho, 8), float("nan"), device="cuda", dtype=torch.bfloat16)
     cat1 = torch.full((n, 16, ho, ho, 8), float("nan"), device="cuda", dtype=torch.bfloat16)
     _lib.call("uncl_conv3x3_tc", x, x.stride(0), wt, b, cat0, cat0.stride(0), _lib.BF16, n, ci, h, h, 32, pad, 1, 1, 0,
               None, None, None, None)
-    _lib.call("uncl_conv3x3_tc_rows", x, x.stride(0), wr, wt, b, cat1, cat1.stride(0), n, ci, h, h, pad, 1, 1, 0,
+    _lib.call("uncl_conv3x3_tc_rows", x, x.stride(0), wr, wt, b, cat1, cat1.stride(0), n, ci, h, h, 32, pad, 1, 1, 0,
               None, None, None, None)
     torch.cuda.synchronize()
     assert not torch.isnan(logit).any() and not torch.isnan(img).any()
@@ -120,6 +142,6 @@ def test_row_kernel_network_matches_older_kernels():
                 net.fused_skip, net.row_kernel = fused, rows
                 outs[(fused, rows)] = net.tonemap_tiles(x).clone()
     torch.cuda.synchronize()
-    assert "u3_0_rows" in net.packed() and "inc1_rows" in net.packed() and "u2_0_rows" in net.packed()
+    assert all(k + "_rows" in net.packed() for k in ("inc1", "d0_0", "d0_1", "u2_0", "u2_1", "u3_0", "u3_1"))
     for fused in (True, False):
         assert rel(outs[(fused, True)], outs[(fused, False)]) <= 2e-3

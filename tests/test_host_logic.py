@@ -358,7 +358,7 @@ def test_row_kernel_plan_and_packing():
         assert p["BW"] <= 126 and p["bands"] * p["BW"] >= p["cols"] > (p["bands"] - 1) * p["BW"]
         assert p["strips"] * p["R"] >= ho > (p["strips"] - 1) * p["R"] and p["items"] == n * p["bands"] * p["strips"]
         assert p["nchunk"] == ci // 32 and p["w_bytes"] == ci * 576 and p["stage_bytes"] == p["G"] * 8192
-        assert 1 <= p["G"] <= (4 if p["nchunk"] == 1 else 3)
+        assert 2 <= p["G"] <= (4 if p["nchunk"] == 1 else 3) and p["_"] == (1 if (p["nchunk"] == 1 and not derive) else 0)
         assert p["stages"] >= (5 if derive else 3) and p["smem"] <= 227 * 1024
         assert p["stages"] * p["stage_bytes"] + p["w_bytes"] < p["smem"]
     # the generator's shipped layers: 13 waves of 63-row strips on 148 SMs for four 1080p frames
@@ -367,6 +367,13 @@ def test_row_kernel_plan_and_packing():
     p = dict(zip(keys, packing.conv3x3_tc_rows_plan(240, 256, 122, 122, 2, True)))   # up2.conv0: 144 KB of filters + 5 x 2 rows
     assert p["ok"] == 1 and p["G"] == 2 and p["stages"] >= 5 and p["smem"] <= 227 * 1024
     assert packing.conv3x3_tc_rows_plan(1, 512, 59, 59, 2, False)[0] == 0        # 288 KB of filters: stays on the older kernels
+    # C_out = 64 (down0.conv0 / conv1): ring of eight 64-column groups, four rows per stage, 36 KB of filters per 32 channels
+    for n, ci, h in [(240, 32, 126), (240, 64, 124), (3, 128, 33)]:
+        p = dict(zip(keys, packing.conv3x3_tc_rows_plan(n, ci, h, h, 0, False, co=64)))
+        assert p["ok"] == 1 and p["_"] == 1 and p["G"] == (4 if ci <= 64 else 3) and p["w_bytes"] == ci * 1152 and p["stages"] >= 3 and p["smem"] <= 227 * 1024
+    assert packing.conv3x3_tc_rows_plan(1, 256, 59, 59, 0, False, co=64)[0] == 0      # 288 KB of filters
+    t64 = packing.conv3x3_tc_rows_layout(torch.arange(9 * 32 * 64, dtype=torch.float32).reshape(9, 32, 64))
+    assert tuple(t64.shape) == (1, 2, 3, 2, 192, 8) and t64[0, 1, 2, 1, 2 * 64 + 7, 3] == (2 * 3 + 2) * 32 * 64 + (16 + 8 + 3) * 64 + 7
     w9 = torch.arange(9 * 64 * 32, dtype=torch.float32).reshape(9, 64, 32)
     t = packing.conv3x3_tc_rows_layout(w9)
     assert tuple(t.shape) == (2, 2, 3, 2, 96, 8)

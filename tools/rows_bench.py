@@ -10,12 +10,14 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 240
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(1)
-# name, logical C_in, H = W, pad, fused skip operators, fused out conv
-LAYERS = [("inc.conv1", 32, 254, 0, False, False), ("up2.conv0", 256, 122, 2, True, False), ("up2.conv1", 32, 124, 2, False, False),
-          ("up3.conv0", 128, 252, 2, True, False), ("up3.conv1", 32, 254, 2, False, True)]
+# name, logical C_in, H = W, pad, fused skip operators, fused out conv, C_out
+LAYERS = [("inc.conv1", 32, 254, 0, False, False, 32), ("down0.conv0", 32, 126, 0, False, False, 64),
+          ("down0.conv1", 64, 124, 0, False, False, 64), ("up2.conv0", 256, 122, 2, True, False, 32),
+          ("up2.conv1", 32, 124, 2, False, False, 32), ("up3.conv0", 128, 252, 2, True, False, 32),
+          ("up3.conv1", 32, 254, 2, False, True, 32)]
 if len(sys.argv) > 3:   # experiments around up3.conv1: no trailing columns, no fused out conv, no padding
-    LAYERS = [("u31", 32, 254, 2, False, True), ("u31-notail", 32, 250, 2, False, True), ("u31-nofuse", 32, 254, 2, False, False),
-              ("u31-nofuse-notail", 32, 250, 2, False, False), ("pad0-fuse-252", 32, 254, 0, False, True)]
+    LAYERS = [("u31", 32, 254, 2, False, True, 32), ("u31-notail", 32, 250, 2, False, True, 32), ("u31-nofuse", 32, 254, 2, False, False, 32),
+              ("u31-nofuse-notail", 32, 250, 2, False, False, 32), ("pad0-fuse-252", 32, 254, 0, False, True, 32)]
 
 
 def timed(fn):
@@ -32,16 +34,16 @@ def timed(fn):
 
 
 tot_old = tot_new = 0.0
-for name, ci, h, pad, derive, fuse in LAYERS:
+for name, ci, h, pad, derive, fuse, co in LAYERS:
     cs = ci // 4
     cin_t = 2 * cs if derive else ci
     x = torch.randn((n, cin_t // 8, h, h, 8), device=dev, generator=g).relu().to(torch.bfloat16)
-    w9 = (torch.randn((9, ci, 32), device=dev, generator=g) / (9 * ci) ** 0.5).to(torch.bfloat16).float()
-    b = torch.randn(32, device=dev, generator=g) * 0.1
+    w9 = (torch.randn((9, ci, co), device=dev, generator=g) / (9 * ci) ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(co, device=dev, generator=g) * 0.1
     ow, ob = torch.randn(32, device=dev, generator=g) * 0.3, torch.randn(1, device=dev, generator=g)
     ho = h + 2 * pad - 2
     wt, wr = packing.conv3x3_tc(w9), packing.conv3x3_tc_rows(w9)
-    o0 = torch.empty((n, 4, ho, ho, 8), device=dev, dtype=torch.bfloat16)
+    o0 = torch.empty((n, co // 8, ho, ho, 8), device=dev, dtype=torch.bfloat16)
     o1 = torch.empty_like(o0)
     img0, img1 = torch.empty((n, ho, ho), device=dev), torch.empty((n, ho, ho), device=dev)
     if derive:
@@ -49,15 +51,15 @@ for name, ci, h, pad, derive, fuse in LAYERS:
         f_new = lambda: _lib.call("uncl_conv3x3_tc_rows_skipcat", x, x.stride(0), wr, wt, b, o1, o1.stride(0), n, cs, h, h, pad, 1)
     elif fuse:
         f_old = lambda: _lib.call("uncl_conv3x3_tc", x, x.stride(0), wt, b, None, 0, _lib.BF16, n, ci, h, h, 32, pad, 1, 0, 1, ow, ob, img0, None)
-        f_new = lambda: _lib.call("uncl_conv3x3_tc_rows", x, x.stride(0), wr, wt, b, None, 0, n, ci, h, h, pad, 1, 0, 1, ow, ob, img1, None)
+        f_new = lambda: _lib.call("uncl_conv3x3_tc_rows", x, x.stride(0), wr, wt, b, None, 0, n, ci, h, h, 32, pad, 1, 0, 1, ow, ob, img1, None)
     else:
-        f_old = lambda: _lib.call("uncl_conv3x3_tc", x, x.stride(0), wt, b, o0, o0.stride(0), _lib.BF16, n, ci, h, h, 32, pad, 1, 0, 0, None, None, None, None)
-        f_new = lambda: _lib.call("uncl_conv3x3_tc_rows", x, x.stride(0), wr, wt, b, o1, o1.stride(0), n, ci, h, h, pad, 1, 0, 0, None, None, None, None)
+        f_old = lambda: _lib.call("uncl_conv3x3_tc", x, x.stride(0), wt, b, o0, o0.stride(0), _lib.BF16, n, ci, h, h, co, pad, 1, 0, 0, None, None, None, None)
+        f_new = lambda: _lib.call("uncl_conv3x3_tc_rows", x, x.stride(0), wr, wt, b, o1, o1.stride(0), n, ci, h, h, co, pad, 1, 0, 0, None, None, None, None)
     t_old, t_new = timed(f_old), timed(f_new)
     a, r = (img1, img0) if fuse else (o1.float(), o0.float())
     err = ((a - r).norm() / r.norm()).item()
-    gflop = 2 * 9 * ci * 32 * ho * ho * n / 1e9
-    plan = packing.conv3x3_tc_rows_plan(n, ci, h, h, pad, derive)
+    gflop = 2 * 9 * ci * co * ho * ho * n / 1e9
+    plan = packing.conv3x3_tc_rows_plan(n, ci, h, h, pad, derive, co=co)
     print("%-10s %4d tiles  old %8.1f us (%6.1f TFLOP/s)  rows %8.1f us (%6.1f TFLOP/s)  x%.2f  rel diff %.2e  plan %s"
           % (name, n, t_old, gflop / t_old * 1e3, t_new, gflop / t_new * 1e3, t_old / t_new, err, plan[:13]), flush=True)
     tot_old += t_old

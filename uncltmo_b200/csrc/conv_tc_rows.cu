@@ -42,10 +42,10 @@ constexpr int kRwThreadsDerive = (kRwDeriveWarp0 + 4) * 32;        // 704
 constexpr int kRwDeriveWarps = 4;
 constexpr int kRwMaxStages = 8;
 constexpr int kRwSlots = 5;            // accumulator slots of 96 TMEM columns
-constexpr int kRwRing = 16;            // ring variant: accumulator groups of 32 TMEM columns (one per output row)
+constexpr int kRwRing = 16;            // ring variant: accumulator groups of C_out TMEM columns, one per output row (16 x 32 or 8 x 64)
 constexpr int kRwMaxProg = 16;
 constexpr int kRwRowBytes = 128 * 16;  // one row of one channel block in shared memory
-constexpr int kRwWChunk = 2 * 3 * 2 * 96 * 16;   // packed weights of 32 input channels: 18432 B
+constexpr int kRwWChunk = 2 * 3 * 2 * 96 * 16;   // packed weights of 32 input channels, C_out = 32: 18432 B (x2 for C_out = 64)
 
 struct RwParams {
   const bf16* w;
@@ -56,6 +56,7 @@ struct RwParams {
   const float* outc_b;
   float* out_img;
   float* out_logit;
+  int NT;                              // C_out: 32, or 64 (ring variant only)
   int Ho, Wo, Wc, pad, H_in, W_in;     // Wc: output columns [0, Wc) are computed here
   int BW, nbands, R, nstrips, items_per_img, num_items;
   int G, nchunk, stages, stage_bytes, w_total;
@@ -106,7 +107,7 @@ __device__ __forceinline__ void rw_tmem_zero32(uint32_t taddr) {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-template <bool kDerive, int G, bool kRing>
+template <bool kDerive, int G, bool kRing, int NT>
 __global__ void __launch_bounds__(kDerive ? kRwThreadsDerive : kRwThreads, 1)
 conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RwParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -116,7 +117,7 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
   // 128 B of slack (the kx = 2 reads of a stage's last row), then [32] bias + [32] out conv weights, 16-byte aligned: the
   // epilogue reads them as broadcast LDS.128 - every shared-memory wavefront competes with the MMAs' operand reads
   float* s_bias = reinterpret_cast<float*>(wres + p.w_total + 128);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 64);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 128);   // [0, NT) bias, [64, 96) out conv weights
   uint64_t* full = bars;
   uint64_t* empty = bars + kRwMaxStages;
   uint64_t* rowdone = bars + 2 * kRwMaxStages;
@@ -141,9 +142,12 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = threadIdx.x; i < 32; i += (int)blockDim.x) {
-    s_bias[i] = p.bias ? p.bias[i] : 0.f;
-    s_bias[32 + i] = p.fuse_outc ? p.outc_w[i] : 0.f;
+  static_assert(NT == 32 || (NT == 64 && kRing && !kDerive), "C_out = 64 exists as the ring variant only");
+  constexpr int kGroups = 512 / NT;          // ring groups (power of two)
+  constexpr int kWChunk = kRwWChunk * (NT / 32);
+  for (int i = threadIdx.x; i < 64; i += (int)blockDim.x) {
+    s_bias[i] = (p.bias && i < NT) ? p.bias[i] : 0.f;
+    s_bias[64 + i] = (p.fuse_outc && i < 32) ? p.outc_w[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -152,7 +156,7 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
   if constexpr (kRing) {   // the MMAs only ever accumulate: all sixteen groups start cleared
     if (warp >= 2 && warp < 2 + 4 * kRwSets) {
       const uint32_t lb = (uint32_t)((warp & 3) * 32) << 16;
-      for (int g = (warp - 2) >> 2; g < kRwRing; g += kRwSets) rw_tmem_zero32(tmem_base + lb + (uint32_t)(g * 32));
+      for (int g = (warp - 2) >> 2; g < 16; g += kRwSets) rw_tmem_zero32(tmem_base + lb + (uint32_t)(g * 32));
     }
     tc_fence_before();
     __syncthreads();
@@ -165,7 +169,7 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
       mbar_expect_tx(wfull, (uint32_t)p.w_total);
       {
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
-        for (int off = 0; off < p.w_total; off += kRwWChunk) bulk_load(wres + off, wsrc + off, kRwWChunk, wfull);
+        for (int off = 0; off < p.w_total; off += kWChunk) bulk_load(wres + off, wsrc + off, kWChunk, wfull);
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -197,10 +201,11 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     // adds, barrier polls: profiles/README.md), so one elected lane issues ALL rows of a (row group, K chunk) stage as
     // straight-line code - descriptor offsets are immediates (G is a template parameter) - and polls the slot barriers
     // itself between rows.
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(3 * NT >> 3) << 17) | ((128u >> 4) << 24);
     constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
     constexpr uint32_t a_lo_const = ((uint32_t)(G * 128) & 0x3fffu) << 16;   // LBO_A: channel-block stride = G rows x 2048 B
-    constexpr uint32_t b_lo_const = 96u << 16;                               // LBO_B = 96 x 16 B
+    constexpr uint32_t b_lo_const = (uint32_t)(3 * NT) << 16;                // LBO_B = 3 C_out rows x 16 B
+    constexpr uint32_t b_tile_16 = (uint32_t)(2 * 3 * NT);                   // one (kstep, kx) tile of the filter bank
     constexpr uint32_t stage_16 = (uint32_t)stage_bytes >> 4;
     constexpr uint32_t a_kstep_16 = (uint32_t)(2 * G * 128);
     const uint32_t stage0_16 = smem_u32(stage_base) >> 4;
@@ -230,50 +235,54 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
           tc_fence_after();
           const uint32_t sa16 = stage0_16 + (uint32_t)stage * stage_16;
           const uint32_t wch = kDerive ? (uint32_t)p.prog_wch[ch] : (uint32_t)ch;
-          const uint32_t b_base = b_lo_const | (wres_16 + wch * (uint32_t)(kRwWChunk >> 4));
+          const uint32_t b_base = b_lo_const | (wres_16 + wch * (uint32_t)(kWChunk >> 4));
           const bool first = ch == 0, last = ch == nchunk - 1;
           if constexpr (kRing) {
             // Ring variant (one K chunk per row): output row u owns ONE group of 32 TMEM columns at position (-u) mod 16,
             // so the N' = 96 columns (ky = 0, 1, 2) of input row tt land on the groups of outputs tt, tt-1, tt-2, which are
             // adjacent - every MMA accumulates, the epilogue reads one group and hands it back cleared.  Rows whose three
             // groups wrap around the ring (2 of 16) issue an N = 64 and an N = 32 instruction instead of one N = 96.
-            constexpr uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-            constexpr uint32_t idesc32 = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * NT >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint32_t gm = (uint32_t)(kGroups - 1);
+            constexpr int glog = kGroups == 16 ? 4 : 3;
             if (elect_one()) {
               uint32_t tt = (uint32_t)slot0;   // ring variant: slot0 counts rows (never wrapped at five)
 #pragma unroll
               for (int r = 0; r < G; ++r) {
                 if (r < rows) {
-                  mbar_wait(&sfree[tt & 15u], (((tt + 2u) >> 4) & 1u) ^ 1u);   // group of output tt: cleared by its previous owner
-                  tc_fence_after();
-                  const uint32_t pos = (16u - (tt & 15u)) & 15u;
-                  const uint32_t d = tmem_base + pos * 32u;
+                  if (first) {   // group of output tt: cleared by its previous owner
+                    mbar_wait(&sfree[tt & gm], (((tt + 2u) >> glog) & 1u) ^ 1u);
+                    tc_fence_after();
+                  }
+                  const uint32_t pos = ((uint32_t)kGroups - (tt & gm)) & gm;
+                  const uint32_t d = tmem_base + pos * (uint32_t)NT;
                   const uint32_t a_row = a_lo_const | (sa16 + (uint32_t)(r * 128));
-                  if (pos <= 13u) {
+                  if (pos <= gm - 2u) {
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
                       for (int kx = 0; kx < 3; ++kx) {
                         if (UNCL_PROBE(p.probe, 4) && (ks > 0 || kx > 0)) continue;
-                        tc_mma_bf16(d, a_row + (uint32_t)(ks * a_kstep_16 + kx), desc_hi, b_base + (uint32_t)((ks * 3 + kx) * 192),
+                        tc_mma_bf16(d, a_row + (uint32_t)(ks * a_kstep_16 + kx), desc_hi, b_base + (uint32_t)(ks * 3 + kx) * b_tile_16,
                                     desc_hi, idesc, 1u);
                       }
                     }
                   } else {
-                    const bool two_first = pos == 14u;   // groups 14, 15 | 0   or   15 | 0, 1
-                    const uint32_t id_a = two_first ? idesc64 : idesc32, id_b = two_first ? idesc32 : idesc64;
-                    const uint32_t nb = two_first ? 64u : 32u;   // B rows (16 B each) taken by the first instruction
+                    const bool two_first = pos == gm - 1u;   // groups (last - 1, last | 0)   or   (last | 0, 1)
+                    const uint32_t id_a = two_first ? idesc2 : idesc1, id_b = two_first ? idesc1 : idesc2;
+                    const uint32_t nb = two_first ? (uint32_t)(2 * NT) : (uint32_t)NT;   // B rows (16 B each) of the first instruction
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
                       for (int kx = 0; kx < 3; ++kx) {
-                        const uint32_t a = a_row + (uint32_t)(ks * a_kstep_16 + kx), b = b_base + (uint32_t)((ks * 3 + kx) * 192);
+                        const uint32_t a = a_row + (uint32_t)(ks * a_kstep_16 + kx), b = b_base + (uint32_t)(ks * 3 + kx) * b_tile_16;
                         tc_mma_bf16(d, a, desc_hi, b, desc_hi, id_a, 1u);
                         tc_mma_bf16(tmem_base, a, desc_hi, b + nb, desc_hi, id_b, 1u);
                       }
                     }
                   }
-                  tc_commit(&rowdone[tt & 15u]);
+                  if (last) tc_commit(&rowdone[tt & gm]);
                   ++tt;
                 }
               }
@@ -297,7 +306,7 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
 #pragma unroll
                   for (int kx = 0; kx < 3; ++kx) {
                     if (UNCL_PROBE(p.probe, 4) && (ks > 0 || kx > 0)) continue;
-                    tc_mma_bf16(d, a_row + (uint32_t)(ks * a_kstep_16 + kx), desc_hi, b_base + (uint32_t)((ks * 3 + kx) * 192),
+                    tc_mma_bf16(d, a_row + (uint32_t)(ks * a_kstep_16 + kx), desc_hi, b_base + (uint32_t)(ks * 3 + kx) * b_tile_16,
                                 desc_hi, idesc, (ks > 0 || kx > 0) ? 1u : (first ? 0u : 1u));
                   }
                 }
@@ -430,62 +439,13 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         if (!valid && last_item) break;   // no later row exists: nothing waits for these slots any more
         // Slot r is read right after row r completes by all three output rows that need it (r, r-1, r-2), so it is free
         // again one epilogue turn after its own MMAs - the issuing warp can run up to four rows ahead of the epilogue.
-        float v[32];
-        if constexpr (kRing) {
-          const int r2 = u + 2;
-#ifdef UNCL_PROBES
-          const long long pa = clock64();
-#endif
-          mbar_wait(&rowdone[r2 & 15], (uint32_t)((r2 >> 4) & 1));   // all three contributions have landed
-#ifdef UNCL_PROBES
-          pw[2] += clock64() - pa;
-#endif
-          tc_fence_after();
-          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(((16 - (u & 15)) & 15) * 32);
-          if (valid && !UNCL_PROBE(p.probe, 2)) {
-            uint32_t rb[32];
-            tc_ld32(taddr, rb);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(rb[c]);
-          }
-          rw_tmem_zero32(taddr);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sfree[u & 15]);
-        } else {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int r = u + k;
-          if (r < 0) continue;
-          const int slot = r % kRwSlots;
-#ifdef UNCL_PROBES
-          const long long pa = clock64();
-#endif
-          mbar_wait(&rowdone[slot], (uint32_t)((r / kRwSlots) & 1));
-#ifdef UNCL_PROBES
-          pw[k] += clock64() - pa;
-#endif
-          tc_fence_after();
-          if (valid && !UNCL_PROBE(p.probe, 2)) {
-            uint32_t rb[32];
-            tc_ld32(tmem_base + lane_base + (uint32_t)(slot * 96 + k * 32), rb);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = k == 0 ? __uint_as_float(rb[c]) : v[c] + __uint_as_float(rb[c]);
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sfree[slot]);
-        }
-        }
-#ifdef UNCL_PROBES
-        const long long pb = clock64();
-#endif
-        if (!valid || UNCL_PROBE(p.probe, 2)) continue;
         const int oy = it.y0 + j, ox = it.x0 + xl;
-        if (xl < BW && ox < Wc) {
-          const long pix = (long)oy * Wo + ox;
-          float logit = outc_b;
-          const float4* sb4 = reinterpret_cast<const float4*>(s_bias);
+        const bool store = valid && !UNCL_PROBE(p.probe, 2) && xl < BW && ox < Wc;
+        const long pix = (long)oy * Wo + ox;
+        float logit = outc_b;
+        // bias, activation, bf16 store (+ skip planes / out conv) of the 32 channels [32 h, 32 h + 32) of this lane's pixel
+        auto finish = [&](const float (&v)[32], int h) {
+          const float4* sb4 = reinterpret_cast<const float4*>(s_bias) + 8 * h;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const float4 b0 = sb4[2 * g], b1 = sb4[2 * g + 1];
@@ -495,29 +455,93 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             o[4] = fmaxf(v[g * 8 + 4] + b1.x, act_floor); o[5] = fmaxf(v[g * 8 + 5] + b1.y, act_floor);
             o[6] = fmaxf(v[g * 8 + 6] + b1.z, act_floor); o[7] = fmaxf(v[g * 8 + 7] + b1.w, act_floor);
             if (out != nullptr) {
-              bf16* op = out + (long)it.n * p.out_img_stride + (long)g * cb_stride + pix * 8;
+              bf16* op = out + (long)it.n * p.out_img_stride + (long)(4 * h + g) * cb_stride + pix * 8;
               store8(op, o);
-              if (emit_skip) {
+              if (emit_skip) {   // concat buffer [skip | up-sampled | skip^2 | sqrt(skip + eps)], C_out channels each
                 float s2[8], s3[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) { s2[c] = o[c] * o[c]; s3[c] = fast_sqrt(o[c] + 1e-8f); }
-                store8(op + 8 * cb_stride, s2);
-                store8(op + 12 * cb_stride, s3);
+                store8(op + (2 * NT / 8) * cb_stride, s2);
+                store8(op + (3 * NT / 8) * cb_stride, s3);
               }
             }
-            if (fuse_outc) {
-              const float4 w0 = sb4[8 + 2 * g], w1 = sb4[8 + 2 * g + 1];
+            if (NT == 32 && fuse_outc) {
+              const float4 w0 = sb4[16 + 2 * g], w1 = sb4[16 + 2 * g + 1];
               logit = fmaf(o[0], w0.x, logit); logit = fmaf(o[1], w0.y, logit); logit = fmaf(o[2], w0.z, logit);
               logit = fmaf(o[3], w0.w, logit); logit = fmaf(o[4], w1.x, logit); logit = fmaf(o[5], w1.y, logit);
               logit = fmaf(o[6], w1.z, logit); logit = fmaf(o[7], w1.w, logit);
             }
           }
-          if (fuse_outc) {
-            const long o1 = (long)it.n * Ho * Wo + pix;
-            if (p.out_logit) p.out_logit[o1] = logit;
-            p.out_img[o1] = 1.f / (1.f + __expf(-logit));
+        };
+#ifdef UNCL_PROBES
+        long long pb = clock64();
+#endif
+        if constexpr (kRing) {
+          constexpr int gm = kGroups - 1, glog = kGroups == 16 ? 4 : 3;
+          const int r2 = u + 2;
+#ifdef UNCL_PROBES
+          const long long pa = clock64();
+#endif
+          mbar_wait(&rowdone[r2 & gm], (uint32_t)((r2 >> glog) & 1));   // all three contributions have landed
+#ifdef UNCL_PROBES
+          pw[2] += clock64() - pa;
+          pb = clock64();
+#endif
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(((kGroups - (u & gm)) & gm) * NT);
+#pragma unroll
+          for (int h = 0; h < NT / 32; ++h) {
+            float v[32];
+            if (valid && !UNCL_PROBE(p.probe, 2)) {
+              uint32_t rb[32];
+              tc_ld32(taddr + (uint32_t)(32 * h), rb);
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(rb[c]);
+            }
+            rw_tmem_zero32(taddr + (uint32_t)(32 * h));
+            if (h == NT / 32 - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&sfree[u & gm]);
+            }
+            if (store) finish(v, h);
           }
+        } else {
+          float v[32];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int r = u + k;
+            if (r < 0) continue;
+            const int slot = r % kRwSlots;
+#ifdef UNCL_PROBES
+            const long long pa = clock64();
+#endif
+            mbar_wait(&rowdone[slot], (uint32_t)((r / kRwSlots) & 1));
+#ifdef UNCL_PROBES
+            pw[k] += clock64() - pa;
+#endif
+            tc_fence_after();
+            if (valid && !UNCL_PROBE(p.probe, 2)) {
+              uint32_t rb[32];
+              tc_ld32(tmem_base + lane_base + (uint32_t)(slot * 96 + k * 32), rb);
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = k == 0 ? __uint_as_float(rb[c]) : v[c] + __uint_as_float(rb[c]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sfree[slot]);
+          }
+#ifdef UNCL_PROBES
+          pb = clock64();
+#endif
+          if (store) finish(v, 0);
         }
+        if (NT == 32 && fuse_outc && store) {
+          const long o1 = (long)it.n * Ho * Wo + pix;
+          if (p.out_logit) p.out_logit[o1] = logit;
+          p.out_img[o1] = 1.f / (1.f + __expf(-logit));
+        }
+        if (!valid) continue;
 #ifdef UNCL_PROBES
         pwork += clock64() - pb; ++prows;
 #endif
@@ -556,7 +580,10 @@ int rw_pick_R(int N, int nbands, int Ho, int sms) {
   return best_R;
 }
 
-int rw_plan(RwParams& p, int N, int C_in, int H, int W, int pad, int Wc, int derive, int sms, const char* what, int* smem_bytes_out) {
+int rw_plan(RwParams& p, int N, int C_in, int H, int W, int C_out, int pad, int Wc, int derive, int sms, const char* what,
+            int* smem_bytes_out) {
+  UNCL_REQUIRE(C_out == 32 || (C_out == 64 && !derive), "%s: C_out must be 32 (or 64 without fused skip operators), got %d", what, C_out);
+  p.NT = C_out;
   p.pad = pad; p.H_in = H; p.W_in = W;
   p.Ho = H + 2 * pad - 2; p.Wo = W + 2 * pad - 2;
   UNCL_REQUIRE(p.Ho > 0 && p.Wo > 0 && Wc > 0 && Wc <= p.Wo, "%s: bad extent (Ho=%d Wo=%d cols=%d)", what, p.Ho, p.Wo, Wc);
@@ -566,15 +593,17 @@ int rw_plan(RwParams& p, int N, int C_in, int H, int W, int pad, int Wc, int der
   p.BW = ceil_div(Wc, p.nbands);
   p.derive = derive ? 1 : 0;
   p.nchunk = C_in / 32;
-  p.w_total = p.nchunk * kRwWChunk;
+  p.w_total = p.nchunk * kRwWChunk * (C_out / 32);
   UNCL_REQUIRE(p.nchunk <= kRwMaxProg, "%s: C_in=%d too deep", what, C_in);
-  const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwRing + 1) * 8 + 16 + 64 * 4 + 256;
+  const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwRing + 1) * 8 + 16 + 128 * 4 + 256;
   const int budget = 227 * 1024 - tail - p.w_total;
-  // Rows per pipeline stage.  With several K chunks per row group a group's rows complete together, and row a + G + k of
-  // the next group needs the slot of row a + G + k - 5, whose epilogue waits for row a + G + k - 3: that row must belong
-  // to an earlier group, so G <= 3.  One-chunk layers commit row by row and take four rows per barrier round trip.
+  // Rows per pipeline stage.  Slot variant (C_out = 32 with several K chunks per row group): a group's rows complete together,
+  // and row a + G + k of the next group needs the slot of row a + G + k - 5, whose epilogue waits for row a + G + k - 3: that
+  // row must belong to an earlier group, so G <= 3.  The ring variant (one-chunk layers, C_out = 64) has 16 / 8 groups of
+  // slack and takes four rows per barrier round trip.
+  const bool ring = !derive && (C_out == 64 || p.nchunk == 1);
   const int want_stages = derive ? 5 : 3;
-  int G = p.nchunk == 1 ? 4 : 3;
+  int G = ring ? 4 : 3;
   for (; G >= 2; --G) {
     p.stage_bytes = G * 4 * kRwRowBytes;
     p.stages = budget / p.stage_bytes;
@@ -608,14 +637,14 @@ int rw_plan(RwParams& p, int N, int C_in, int H, int W, int pad, int Wc, int der
 }
 
 int rw_launch(const void* in, long in_img_stride, const void* w_rows, const float* bias, void* out, long out_img_stride, int N,
-              int C_in, int H, int W, int pad, int Wc, int act, int emit_skip, int fuse_outc, const float* outc_w,
+              int C_in, int H, int W, int C_out, int pad, int Wc, int act, int emit_skip, int fuse_outc, const float* outc_w,
               const float* outc_b, float* out_img, float* out_logit, int derive, const char* what, cudaStream_t stream) {
   UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_rows) & 15) == 0,
                "%s: input / weights must be 16-byte aligned", what);
   RwParams p{};
   int smem_bytes = 0;
   const int sms = sm_count();
-  if (int rc = rw_plan(p, N, C_in, H, W, pad, Wc, derive, sms, what, &smem_bytes)) return rc;
+  if (int rc = rw_plan(p, N, C_in, H, W, C_out, pad, Wc, derive, sms, what, &smem_bytes)) return rc;
   p.w = reinterpret_cast<const bf16*>(w_rows);
   p.bias = bias; p.out = reinterpret_cast<bf16*>(out); p.out_img_stride = out_img_stride;
   p.outc_w = outc_w; p.outc_b = outc_b; p.out_img = out_img; p.out_logit = out_logit;
@@ -630,22 +659,28 @@ int rw_launch(const void* in, long in_img_stride, const void* w_rows, const floa
   if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
   const int grid = p.num_items < sms ? p.num_items : sms;
   // one instantiation per (fused skip operators, rows per stage): the issuing warp's descriptor offsets are immediates
-  static thread_local int smem_ok[6] = {0, 0, 0, 0, 0, 0}, smem_dev[6] = {-1, -1, -1, -1, -1, -1};
-#define RW_LAUNCH(D, GG, RING, slot_)                                                                                      \
-  do {                                                                                                                \
-    cudaError_t e = ensure_smem(conv3x3_tc_rows_kernel<D, GG, RING>, smem_bytes, smem_ok[slot_], smem_dev[slot_]);      \
-    if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));         \
-    conv3x3_tc_rows_kernel<D, GG, RING><<<grid, D ? kRwThreadsDerive : kRwThreads, smem_bytes, stream>>>(tmap, p);      \
+  static thread_local int smem_ok[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, smem_dev[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+#define RW_LAUNCH(D, GG, RING, NTT, slot_)                                                                                   \
+  do {                                                                                                                      \
+    cudaError_t e = ensure_smem(conv3x3_tc_rows_kernel<D, GG, RING, NTT>, smem_bytes, smem_ok[slot_], smem_dev[slot_]);       \
+    if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));               \
+    conv3x3_tc_rows_kernel<D, GG, RING, NTT><<<grid, D ? kRwThreadsDerive : kRwThreads, smem_bytes, stream>>>(tmap, p);       \
   } while (0)
+  const bool ring = !derive && (C_out == 64 || (p.nchunk == 1 && p.ring));
   if (derive) {
-    if (p.G == 3) RW_LAUNCH(true, 3, false, 0);
-    else if (p.G == 2) RW_LAUNCH(true, 2, false, 1);
+    if (p.G == 3) RW_LAUNCH(true, 3, false, 32, 0);
+    else if (p.G == 2) RW_LAUNCH(true, 2, false, 32, 1);
+    else return uncl_set_error(UNCL_EINVAL, "%s: no kernel for %d rows per stage", what, p.G);
+  } else if (C_out == 64) {
+    if (p.G == 4) RW_LAUNCH(false, 4, true, 64, 6);
+    else if (p.G == 3) RW_LAUNCH(false, 3, true, 64, 7);
+    else if (p.G == 2) RW_LAUNCH(false, 2, true, 64, 8);
     else return uncl_set_error(UNCL_EINVAL, "%s: no kernel for %d rows per stage", what, p.G);
   } else {
-    if (p.G == 4 && p.nchunk == 1 && p.ring) RW_LAUNCH(false, 4, true, 5);
-    else if (p.G == 4) RW_LAUNCH(false, 4, false, 2);
-    else if (p.G == 3) RW_LAUNCH(false, 3, false, 3);
-    else if (p.G == 2) RW_LAUNCH(false, 2, false, 4);
+    if (p.G == 4 && ring) RW_LAUNCH(false, 4, true, 32, 5);
+    else if (p.G == 4) RW_LAUNCH(false, 4, false, 32, 2);
+    else if (p.G == 3) RW_LAUNCH(false, 3, false, 32, 3);
+    else if (p.G == 2) RW_LAUNCH(false, 2, false, 32, 4);
     else return uncl_set_error(UNCL_EINVAL, "%s: no kernel for %d rows per stage", what, p.G);
   }
 #undef RW_LAUNCH
@@ -669,35 +704,35 @@ int uncl_conv3x3_tc_skipcat_cols(const void* in, long in_img_stride, const void*
                                  long out_img_stride, int out_dtype, int N, int C_skip, int H, int W, int C_out, int pad,
                                  int act, int x0, cudaStream_t stream);
 
-// 3x3 conv / ConvTranspose 3x3 (pad 0 / 2) with C_out = 32, bf16 blocked in and out, bias + ReLU / identity, optional
-// skip-plane emission and fused 1x1 out conv + sigmoid: the arguments of uncl_conv3x3_tc with two packed filter banks.
-// w_rows: packing.conv3x3_tc_rows; w_tail: packing.conv3x3_tc (used for the columns past the last whole 126-column band,
-// may be NULL when uncl_conv3x3_tc_rows_plan reports none).
+// 3x3 conv / ConvTranspose 3x3 (pad 0 / 2) with C_out = 32 or 64, bf16 blocked in and out, bias + ReLU / identity, optional
+// skip-plane emission and (C_out = 32) fused 1x1 out conv + sigmoid: the arguments of uncl_conv3x3_tc with two packed
+// filter banks.  w_rows: packing.conv3x3_tc_rows; w_tail: packing.conv3x3_tc (used for the columns past the last whole
+// 126-column band, may be NULL when uncl_conv3x3_tc_rows_plan reports none).
 extern "C" int uncl_conv3x3_tc_rows(const void* in, long in_img_stride, const void* w_rows, const void* w_tail,
-                                    const float* bias, void* out, long out_img_stride, int N, int C_in, int H, int W, int pad,
-                                    int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
+                                    const float* bias, void* out, long out_img_stride, int N, int C_in, int H, int W, int C_out,
+                                    int pad, int act, int emit_skip, int fuse_outc, const float* outc_w, const float* outc_b,
                                     float* out_img, float* out_logit, cudaStream_t stream) {
-  UNCL_REQUIRE(N > 0 && C_in > 0 && C_in % 32 == 0 && (pad == 0 || pad == 2) && w_rows != nullptr,
-               "conv3x3_tc_rows: unsupported C_in=%d pad=%d", C_in, pad);
+  UNCL_REQUIRE(N > 0 && C_in > 0 && C_in % 32 == 0 && (C_out == 32 || C_out == 64) && (pad == 0 || pad == 2) && w_rows != nullptr,
+               "conv3x3_tc_rows: unsupported C_in=%d C_out=%d pad=%d", C_in, C_out, pad);
   UNCL_REQUIRE(act == UNCL_ACT_RELU || act == UNCL_ACT_NONE, "conv3x3_tc_rows: only ReLU / identity epilogues are built");
-  UNCL_REQUIRE(!fuse_outc || (outc_w && outc_b && out_img), "conv3x3_tc_rows: fuse_outc needs outc params");
+  UNCL_REQUIRE(!fuse_outc || (C_out == 32 && outc_w && outc_b && out_img), "conv3x3_tc_rows: fuse_outc needs C_out == 32 and outc params");
   UNCL_REQUIRE(out != nullptr || fuse_outc, "conv3x3_tc_rows: no output requested");
   const int Wo = W + 2 * pad - 2;
   UNCL_REQUIRE(Wo > 0 && H + 2 * pad - 2 > 0, "conv3x3_tc_rows: empty output");
   const int Wc = rw_cols(Wo);
-  if (int rc = rw_launch(in, in_img_stride, w_rows, bias, out, out_img_stride, N, C_in, H, W, pad, Wc, act, emit_skip, fuse_outc,
-                         outc_w, outc_b, out_img, out_logit, 0, "conv3x3_tc_rows", stream))
+  if (int rc = rw_launch(in, in_img_stride, w_rows, bias, out, out_img_stride, N, C_in, H, W, C_out, pad, Wc, act, emit_skip,
+                         fuse_outc, outc_w, outc_b, out_img, out_logit, 0, "conv3x3_tc_rows", stream))
     return rc;
   if (Wc < Wo) {
-    UNCL_REQUIRE(w_tail != nullptr, "conv3x3_tc_rows: %d trailing columns need the one-tap filter bank (w_tail)", Wo - Wc);
-    return uncl_conv3x3_tc_cols(in, in_img_stride, w_tail, bias, out, out_img_stride, UNCL_BF16, N, C_in, H, W, 32, pad, act,
+    UNCL_REQUIRE(w_tail != nullptr, "conv3x3_tc_rows: %d trailing columns need the older kernels' filter bank (w_tail)", Wo - Wc);
+    return uncl_conv3x3_tc_cols(in, in_img_stride, w_tail, bias, out, out_img_stride, UNCL_BF16, N, C_in, H, W, C_out, pad, act,
                                 emit_skip, fuse_outc, outc_w, outc_b, out_img, out_logit, Wc, stream);
   }
   return UNCL_OK;
 }
 
-// uncl_conv3x3_tc_skipcat (fused skip operators, `in` = [skip (C_skip) | up-sampled (C_skip)]) through the row kernel.
-// w_rows / w_tail: packing.conv3x3_tc_rows / packing.conv3x3_tc of the full [9][4*C_skip][32] filter bank.
+// uncl_conv3x3_tc_skipcat (fused skip operators, `in` = [skip (C_skip) | up-sampled (C_skip)], C_out = 32) through the row
+// kernel.  w_rows / w_tail: packing.conv3x3_tc_rows / packing.conv3x3_tc of the full [9][4*C_skip][32] filter bank.
 extern "C" int uncl_conv3x3_tc_rows_skipcat(const void* in, long in_img_stride, const void* w_rows, const void* w_tail,
                                             const float* bias, void* out, long out_img_stride, int N, int C_skip, int H, int W,
                                             int pad, int act, cudaStream_t stream) {
@@ -707,7 +742,7 @@ extern "C" int uncl_conv3x3_tc_rows_skipcat(const void* in, long in_img_stride, 
   const int Wo = W + 2 * pad - 2;
   UNCL_REQUIRE(Wo > 0 && H + 2 * pad - 2 > 0, "conv3x3_tc_rows_skipcat: empty output");
   const int Wc = rw_cols(Wo);
-  if (int rc = rw_launch(in, in_img_stride, w_rows, bias, out, out_img_stride, N, 4 * C_skip, H, W, pad, Wc, act, 0, 0, nullptr,
+  if (int rc = rw_launch(in, in_img_stride, w_rows, bias, out, out_img_stride, N, 4 * C_skip, H, W, 32, pad, Wc, act, 0, 0, nullptr,
                          nullptr, nullptr, nullptr, 1, "conv3x3_tc_rows_skipcat", stream))
     return rc;
   if (Wc < Wo) {
@@ -722,24 +757,24 @@ extern "C" int uncl_conv3x3_tc_rows_skipcat(const void* in, long in_img_stride, 
 // derive).  plan[16]: 1 when the problem fits (0: filter bank too large for shared memory - use uncl_conv3x3_tc),
 // columns computed by the row kernel, trailing columns left to the older kernels, bands, band width, strip height,
 // strips per band, work items, rows per stage, K chunks per row group, pipeline stages, stage bytes, resident weight
-// bytes, dynamic shared memory, SMs assumed, 0.
-extern "C" int uncl_conv3x3_tc_rows_plan(int N, int C_in, int H, int W, int pad, int derive, int sms, int* plan) {
-  UNCL_REQUIRE(plan != nullptr && N > 0 && C_in > 0 && C_in % 32 == 0 && (pad == 0 || pad == 2) && sms > 0 &&
-                   H + 2 * pad - 2 > 0 && W + 2 * pad - 2 > 0,
-               "conv3x3_tc_rows_plan: unsupported C_in=%d pad=%d H=%d W=%d", C_in, pad, H, W);
+// bytes, dynamic shared memory, SMs assumed, 1 for the ring variant of the accumulators.
+extern "C" int uncl_conv3x3_tc_rows_plan(int N, int C_in, int H, int W, int C_out, int pad, int derive, int sms, int* plan) {
+  UNCL_REQUIRE(plan != nullptr && N > 0 && C_in > 0 && C_in % 32 == 0 && (C_out == 32 || (C_out == 64 && !derive)) &&
+                   (pad == 0 || pad == 2) && sms > 0 && H + 2 * pad - 2 > 0 && W + 2 * pad - 2 > 0,
+               "conv3x3_tc_rows_plan: unsupported C_in=%d C_out=%d pad=%d H=%d W=%d", C_in, C_out, pad, H, W);
   for (int i = 0; i < 16; ++i) plan[i] = 0;
   const int Wo = W + 2 * pad - 2;
   const int nchunk = C_in / 32;
-  const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwRing + 1) * 8 + 16 + 64 * 4 + 256;
+  const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwRing + 1) * 8 + 16 + 128 * 4 + 256;
   if (nchunk > kRwMaxProg || (derive && C_in % 128 != 0) ||
-      227 * 1024 - tail - nchunk * kRwWChunk < (derive ? 5 : 3) * 2 * 4 * kRwRowBytes)
+      227 * 1024 - tail - nchunk * kRwWChunk * (C_out / 32) < (derive ? 5 : 3) * 2 * 4 * kRwRowBytes)
     return UNCL_OK;   // plan[0] = 0: not eligible
   RwParams p{};
   int smem = 0;
   const int Wc = rw_cols(Wo);
-  if (int rc = rw_plan(p, N, C_in, H, W, pad, Wc, derive, sms, "conv3x3_tc_rows_plan", &smem)) return rc;
+  if (int rc = rw_plan(p, N, C_in, H, W, C_out, pad, Wc, derive, sms, "conv3x3_tc_rows_plan", &smem)) return rc;
   const int v[16] = {1, Wc, Wo - Wc, p.nbands, p.BW, p.R, p.nstrips, p.num_items, p.G, p.nchunk, p.stages, p.stage_bytes,
-                     p.w_total, smem, sms, 0};
+                     p.w_total, smem, sms, (!derive && (C_out == 64 || p.nchunk == 1)) ? 1 : 0};
   for (int i = 0; i < 16; ++i) plan[i] = v[i];
   return UNCL_OK;
 }

@@ -70,7 +70,7 @@ class _GeneratorBase(nn.Module):
         # us, consumers +70 us), but back-to-back frames run at the 1 kW power cap, where the saved traffic buys clock:
         # 485 -> 496 frames/s sustained (tools/fused_skip_sustained.py).  False = materialised planes.
         self.fused_skip = True
-        # bf16 inference: the C_out = 32 layers at 124..256 pixels (inc.conv1, up2.conv1, up3.conv*) run in the row kernel
+        # bf16 inference: the narrow layers at 122..256 pixels (inc.conv1, down0.conv*, up2.conv*, up3.conv*) run in the row kernel
         # (conv_tc_rows.cu: ky taps merged into N, every input row through shared memory once).  False = the older kernels.
         self.row_kernel = True
         self.to_crop = to_crop
@@ -148,8 +148,8 @@ class _GeneratorBase(nn.Module):
             wp = packing.conv3x3_tc(w9) if tc else (packing.conv3x3_tc_split(w9) if split else w9)
             P[name] = (wp, m.bias.detach().float().contiguous())
             if tc and name in self._ROW_LAYERS:
-                ci, derive = self._ROW_LAYERS[name]
-                if packing.conv3x3_tc_rows_plan(1, ci, 64, 64, 0, derive)[0] == 1:
+                ci, co, derive = self._ROW_LAYERS[name]
+                if packing.conv3x3_tc_rows_plan(1, ci, 64, 64, 0, derive, co=co)[0] == 1:
                     P[name + "_rows"] = packing.conv3x3_tc_rows(w9)
 
         with torch.no_grad():
@@ -179,8 +179,9 @@ class _GeneratorBase(nn.Module):
                          self.outc.conv.bias.detach().float().contiguous())
         return P
 
-    # layers the row kernel takes in bf16 inference: name -> (logical C_in, fused skip operators)
-    _ROW_LAYERS = {"inc1": (32, False), "u2_0": (256, True), "u2_1": (32, False), "u3_0": (128, True), "u3_1": (32, False)}
+    # layers the row kernel takes in bf16 inference: name -> (logical C_in, C_out, fused skip operators)
+    _ROW_LAYERS = {"inc1": (32, 32, False), "d0_0": (32, 64, False), "d0_1": (64, 64, False), "u2_0": (256, 32, True),
+                   "u2_1": (32, 32, False), "u3_0": (128, 32, True), "u3_1": (32, 32, False)}
 
     # ------------------------------------------------------------------ one frame through the network
     def _conv3(self, P, name, src, src_stride, dst, dst_stride, n, ci, h, w, co, pad, emit_skip=0, fuse=None):
@@ -188,7 +189,7 @@ class _GeneratorBase(nn.Module):
         rows = P.get(name + "_rows") if (self.precision == "bf16" and self.row_kernel) else None
         if rows is not None:
             ow, ob, out_img, out_logit = fuse if fuse is not None else (None, None, None, None)
-            call("uncl_conv3x3_tc_rows", src, src_stride, rows, wt, b, dst, dst_stride, n, ci, h, w, pad, ACT_RELU, emit_skip,
+            call("uncl_conv3x3_tc_rows", src, src_stride, rows, wt, b, dst, dst_stride, n, ci, h, w, co, pad, ACT_RELU, emit_skip,
                  0 if fuse is None else 1, ow, ob, out_img, out_logit)
         elif self.precision == "bf16":
             if fuse is None:

@@ -63,28 +63,28 @@ def conv3x3_tc_layout(w9):
     return t.permute(4, 1, 0, 2, 5, 3).contiguous()    # ns, chunk, tap, half, n, k8
 
 
-def conv3x3_tc_rows_plan(n, ci, h, w, pad, derive=False, sms=148):
+def conv3x3_tc_rows_plan(n, ci, h, w, pad, derive=False, sms=148, co=32):
     """plan[16] of uncl_conv3x3_tc_rows_plan (pure host arithmetic, no GPU): plan[0] == 1 when the row kernel takes the
     layer, plan[2] = trailing output columns it leaves to uncl_conv3x3_tc / uncl_conv3x3_tc_skipcat."""
     import ctypes
     from . import _lib
     plan = (ctypes.c_int * 16)()
-    rc = _lib.lib().uncl_conv3x3_tc_rows_plan(n, ci, h, w, pad, 1 if derive else 0, sms, ctypes.cast(plan, ctypes.c_void_p))
+    rc = _lib.lib().uncl_conv3x3_tc_rows_plan(n, ci, h, w, co, pad, 1 if derive else 0, sms, ctypes.cast(plan, ctypes.c_void_p))
     if rc != 0:
         raise RuntimeError("uncl_conv3x3_tc_rows_plan failed (%d): %s" % (rc, _lib.lib().uncl_last_error().decode()))
     return list(plan)
 
 
 def conv3x3_tc_rows(w9):
-    """[9][C_in][32] fp32 -> the B operand of the row kernel (conv_tc_rows.cu, the three ky taps of a filter column merged
-    into N): bf16 [C_in/32][2 ksteps][3 kx][2][96 (ky, co)][8]."""
+    """[9][C_in][C_out] fp32 (C_out = 32 or 64) -> the B operand of the row kernel (conv_tc_rows.cu, the three ky taps of a
+    filter column merged into N): bf16 [C_in/32][2 ksteps][3 kx][2][3*C_out (ky, co)][8]."""
     return conv3x3_tc_rows_layout(w9).to(torch.bfloat16)
 
 
 def conv3x3_tc_rows_layout(w9):
     _, ci, co = w9.shape
-    if co != 32 or ci % 32 != 0:
-        raise ValueError("the row kernel is built for C_out == 32 and C_in %% 32 == 0 (got %d -> %d)" % (ci, co))
+    if co not in (32, 64) or ci % 32 != 0:
+        raise ValueError("the row kernel is built for C_out in (32, 64) and C_in %% 32 == 0 (got %d -> %d)" % (ci, co))
     t = w9.reshape(3, 3, ci // 32, 2, 2, 8, co)        # ky, kx, chunk, kstep, half, k8, co
     t = t.permute(2, 3, 1, 4, 0, 6, 5).contiguous()    # chunk, kstep, kx, half, ky, co, k8
     return t.reshape(ci // 32, 2, 3, 2, 3 * co, 8)
