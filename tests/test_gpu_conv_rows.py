@@ -145,3 +145,20 @@ def test_row_kernel_network_matches_older_kernels():
     assert all(k + "_rows" in net.packed() for k in ("inc1", "d0_0", "d0_1", "u2_0", "u2_1", "u3_0", "u3_1"))
     for fused in (True, False):
         assert rel(outs[(fused, True)], outs[(fused, False)]) <= 2e-3
+
+
+@pytest.mark.parametrize("ci,co,h,pad", [(32, 32, 70, 0), (64, 64, 70, 0), (128, 32, 70, 2), (32, 64, 70, 2)])
+def test_row_kernel_is_batch_invariant(ci, co, h, pad):
+    """Every output bit is independent of how many images share the launch (the strip height follows the batch size, the
+    summation order must not): image 0 alone, in a batch of 7 and in a batch of 300."""
+    g, x, w9, b = _problem(ci, h, 300, 99 + ci + co, co)
+    ho = h + 2 * pad - 2
+    wt, wr = packing.conv3x3_tc(w9), packing.conv3x3_tc_rows(w9)
+    outs = []
+    for n in (1, 7, 300):
+        out = torch.empty((n, co // 8, ho, ho, 8), device="cuda", dtype=torch.bfloat16)
+        _lib.call("uncl_conv3x3_tc_rows", x[:n], x.stride(0), wr, wt, b, out, out.stride(0), n, ci, h, h, co, pad, 1, 0, 0,
+                  None, None, None, None)
+        outs.append(out[0].clone())
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])

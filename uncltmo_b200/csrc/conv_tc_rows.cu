@@ -613,6 +613,10 @@ int rw_plan(RwParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
   if (p.stages > kRwMaxStages) p.stages = kRwMaxStages;
   p.G = G;
   p.R = rw_pick_R(N, p.nbands, p.Ho, sms);
+  // Ring variant with several K chunks: a group accumulates (row, chunk) contributions in the order the stages deliver them,
+  // chunk-major inside a row group.  Strips that start on a multiple of G keep the row groups at the same absolute rows
+  // whatever the strip height, so the summation order - and with it every output bit - does not depend on the batch size.
+  if (ring && p.nchunk > 1) p.R = ceil_div(p.R, G) * G;
   p.nstrips = ceil_div(p.Ho, p.R);
   p.items_per_img = p.nbands * p.nstrips;
   UNCL_REQUIRE((long)N * p.items_per_img < (1 << 24), "%s: too many strips", what);
