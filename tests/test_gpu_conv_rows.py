@@ -162,3 +162,55 @@ def test_row_kernel_is_batch_invariant(ci, co, h, pad):
         outs.append(out[0].clone())
     torch.cuda.synchronize()
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("n,h0,emit", [(2, 256, 0), (1, 256, 1), (3, 60, 0), (150, 40, 0), (1, 130, 1)])
+def test_row_kernel_front_mode_fuses_the_first_conv(n, h0, emit):
+    """uncl_conv_first_conv3x3_tc_rows (inc.conv computed into the stage ring of inc.conv1's launch, three-term bf16 split)
+    against uncl_conv_first (fp32 FMA, bf16 output) followed by the row kernel, and against the fp32 convs."""
+    g = torch.Generator(device="cuda").manual_seed(11 * n + h0)
+    x = torch.rand((n, 1, h0, h0), device="cuda", generator=g)
+    w1 = torch.randn((32, 1, 3, 3), device="cuda", generator=g) / 3
+    b1 = torch.randn(32, device="cuda", generator=g) * 0.1
+    w9 = (torch.randn((9, 32, 32), device="cuda", generator=g) / (9 * 32) ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(32, device="cuda", generator=g) * 0.1
+    ha, ho = h0 - 2, h0 - 4
+    a0 = torch.empty((n, 4, ha, ha, 8), device="cuda", dtype=torch.bfloat16)
+    _lib.call("uncl_conv_first", x, packing.conv_first(w1), b1, a0, a0.stride(0), n, h0, h0, 32, 1, _lib.BF16)
+    cb = 16 if emit else 4
+    two = torch.full((n, cb, ho, ho, 8), float("nan"), device="cuda", dtype=torch.bfloat16)
+    one = torch.full((n, cb, ho, ho, 8), float("nan"), device="cuda", dtype=torch.bfloat16)
+    wt, wr = packing.conv3x3_tc(w9), packing.conv3x3_tc_rows(w9)
+    _lib.call("uncl_conv3x3_tc_rows", a0, a0.stride(0), wr, wt, b, two, two.stride(0), n, 32, ha, ha, 32, 0, 1, emit, 0,
+              None, None, None, None)
+    _lib.call("uncl_conv_first_conv3x3_tc_rows", x, x.stride(0), packing.conv_first_rows(w1), b1, wr, b, one, one.stride(0), n,
+              h0, h0, 1, emit)
+    ref0 = torch.relu(torch.nn.functional.conv2d(x, w1, b1))
+    w2 = w9.reshape(3, 3, 32, 32).permute(3, 2, 0, 1).contiguous()
+    ref = torch.relu(torch.nn.functional.conv2d(ref0.to(torch.bfloat16).float(), w2, b))       # [n, 32, ho, ho]
+    ref_blocked = ref.reshape(n, 4, 8, ho, ho).permute(0, 1, 3, 4, 2)
+    torch.cuda.synchronize()
+    planes = ((0, 4), (8, 12), (12, 16)) if emit else ((0, 4),)
+    for lo, hi in planes:
+        assert not torch.isnan(one[:, lo:hi].float()).any()
+        assert rel(one[:, lo:hi], two[:, lo:hi]) <= 3e-3
+    if emit:
+        assert torch.isnan(one[:, 4:8].float()).all()
+    assert rel(one[:, :4], ref_blocked) <= 5e-3 and rel(two[:, :4], ref_blocked) <= 5e-3
+
+
+def test_front_mode_network_matches_unfused():
+    from uncltmo_b200.generator import UNet
+    from uncltmo_b200.weights import make_generator_state_dict
+    g_args = (1, 1, "sigmoid", 4, 4, "square_and_square_root", 32, 0, "unet", 0, 0, "none", "none", "relu", 1, "replicate", 2)
+    net = UNet(*g_args, up_mode=0, precision="bf16").cuda().eval()
+    net.load_state_dict(make_generator_state_dict())
+    x = torch.rand((5, 1, 256, 256), device="cuda", generator=torch.Generator(device="cuda").manual_seed(6))
+    with torch.no_grad():
+        net.fused_first = True
+        a = net.tonemap_tiles(x).clone()
+        a1 = net.tonemap_tiles(x[:1]).clone()
+        net.fused_first = False
+        b = net.tonemap_tiles(x).clone()
+    torch.cuda.synchronize()
+    assert rel(a, b) <= 2e-3 and torch.equal(a[:1], a1)

@@ -65,3 +65,26 @@ for name, ci, h, pad, derive, fuse, co in LAYERS:
     tot_old += t_old
     tot_new += t_new
 print("sum: old %.1f us, rows %.1f us" % (tot_old, tot_new))
+
+# inc.conv + inc.conv1: uncl_conv_first followed by the row kernel against the fused launch (front mode)
+if len(sys.argv) <= 3:
+    x = torch.rand((n, 1, 256, 256), device=dev, generator=g)
+    w1 = torch.randn((32, 1, 3, 3), device=dev, generator=g) / 3
+    b1 = torch.randn(32, device=dev, generator=g) * 0.1
+    w9 = (torch.randn((9, 32, 32), device=dev, generator=g) / (9 * 32) ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(32, device=dev, generator=g) * 0.1
+    a0 = torch.empty((n, 4, 254, 254, 8), device=dev, dtype=torch.bfloat16)
+    o0 = torch.empty((n, 4, 252, 252, 8), device=dev, dtype=torch.bfloat16)
+    o1 = torch.empty_like(o0)
+    wt, wr, cf, cfr = packing.conv3x3_tc(w9), packing.conv3x3_tc_rows(w9), packing.conv_first(w1), packing.conv_first_rows(w1)
+
+    def two():
+        _lib.call("uncl_conv_first", x, cf, b1, a0, a0.stride(0), n, 256, 256, 32, 1, _lib.BF16)
+        _lib.call("uncl_conv3x3_tc_rows", a0, a0.stride(0), wr, wt, b, o0, o0.stride(0), n, 32, 254, 254, 32, 0, 1, 0, 0, None, None, None, None)
+
+    def one():
+        _lib.call("uncl_conv_first_conv3x3_tc_rows", x, x.stride(0), cfr, b1, wr, b, o1, o1.stride(0), n, 256, 256, 1, 0)
+
+    t2, t1 = timed(two), timed(one)
+    print("inc.conv + inc.conv1  %4d tiles  two launches %8.1f us  fused %8.1f us  x%.2f  rel diff %.2e"
+          % (n, t2, t1, t2 / t1, ((o1.float() - o0.float()).norm() / o0.float().norm()).item()))

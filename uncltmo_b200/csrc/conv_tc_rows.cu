@@ -44,6 +44,9 @@ constexpr int kRwMaxStages = 8;
 constexpr int kRwSlots = 5;            // accumulator slots of 96 TMEM columns
 constexpr int kRwRing = 16;            // ring variant: accumulator groups of C_out TMEM columns, one per output row (16 x 32 or 8 x 64)
 constexpr int kRwMaxProg = 16;
+constexpr int kRwFrontScratch = 4 * 2 * 4096;          // front mode: x_hi / x_lo im2col tiles of the four rows of a stage
+constexpr int kRwFrontBytes = kRwFrontScratch + 2048;  // ... + the first conv's w_hi / w_lo tiles
+constexpr int kRwFrontCols = 384;                      // front mode: TMEM columns 384..511 hold the first conv's accumulators
 constexpr int kRwRowBytes = 128 * 16;  // one row of one channel block in shared memory
 constexpr int kRwWChunk = 2 * 3 * 2 * 96 * 16;   // packed weights of 32 input channels, C_out = 32: 18432 B (x2 for C_out = 64)
 
@@ -63,6 +66,13 @@ struct RwParams {
   int derive;
   unsigned char prog_kind[kRwMaxProg], prog_cb[kRwMaxProg], prog_wch[kRwMaxProg], prog_back[kRwMaxProg];
   int act, emit_skip, fuse_outc;
+  // front mode (inc.conv fused in front of inc.conv1): the stage ring is not loaded by TMA but COMPUTED by four extra warps from
+  // the fp32 image - im2col rows in shared memory, three-term bf16 split MMAs (x_hi w_hi + x_lo w_hi + x_hi w_lo), bias + ReLU
+  const float* fx;      // [N][H0][W0] fp32 image (1 channel)
+  const bf16* fw;       // packing.conv_first_rows: [2 (hi, lo)][2 halves][32][8] bf16
+  const float* fbias;   // [32]
+  long fx_img_stride;
+  int front, H0, W0, f_bytes;
   int ring;    // one-chunk layers: ring variant of the accumulators (host switch: 1 by default)
   int probe;   // -DUNCL_PROBES build only (tools/): 1 = no TMA traffic after the first ring fill, 2 = epilogue does the barrier protocol only, 4 = one MMA per row instead of six (results are wrong while set), 8 = print the per-role cycle accounting of CTA 0
 };
@@ -107,8 +117,8 @@ __device__ __forceinline__ void rw_tmem_zero32(uint32_t taddr) {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-template <bool kDerive, int G, bool kRing, int NT>
-__global__ void __launch_bounds__(kDerive ? kRwThreadsDerive : kRwThreads, 1)
+template <bool kDerive, int G, bool kRing, int NT, bool kFront>
+__global__ void __launch_bounds__((kDerive || kFront) ? kRwThreadsDerive : kRwThreads, 1)
 conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RwParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -116,23 +126,26 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
   uint8_t* wres = smem + (size_t)p.stages * p.stage_bytes;            // resident filter bank
   // 128 B of slack (the kx = 2 reads of a stage's last row), then [32] bias + [32] out conv weights, 16-byte aligned: the
   // epilogue reads them as broadcast LDS.128 - every shared-memory wavefront competes with the MMAs' operand reads
-  float* s_bias = reinterpret_cast<float*>(wres + p.w_total + 128);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 128);   // [0, NT) bias, [64, 96) out conv weights
+  uint8_t* fscr = wres + p.w_total + 128;                             // front mode: im2col tiles + first-conv filter tiles
+  float* s_bias = reinterpret_cast<float*>(fscr + (kFront ? kRwFrontBytes : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 128);   // [0, NT) bias, [64, 96) out conv weights, [96, 128) first-conv bias
   uint64_t* full = bars;
   uint64_t* empty = bars + kRwMaxStages;
   uint64_t* rowdone = bars + 2 * kRwMaxStages;
   uint64_t* sfree = rowdone + kRwRing;
   uint64_t* wfull = sfree + kRwRing;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  uint64_t* fbar = wfull + 1;                                         // front mode: the first conv's MMAs of a stage are done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fbar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = p.num_items, nchunk = p.nchunk, stages = p.stages;
   constexpr int stage_bytes = G * 4 * kRwRowBytes;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    if (!kFront) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     const uint32_t extra = kDerive ? (uint32_t)kRwDeriveWarps : 0u;
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1 + extra); mbar_init(&empty[s], 1 + extra); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], kFront ? 4u : 1 + extra); mbar_init(&empty[s], 1 + extra); }
+    mbar_init(fbar, 1);
     // a slot is read by the epilogues of three output rows (its ky = 0, 1, 2 column groups), four warps each
     for (int s = 0; s < kRwRing; ++s) { mbar_init(&rowdone[s], 1); mbar_init(&sfree[s], kRing ? 4 : 12); }
     mbar_init(wfull, 1);
@@ -143,11 +156,12 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   static_assert(NT == 32 || (NT == 64 && kRing && !kDerive), "C_out = 64 exists as the ring variant only");
-  constexpr int kGroups = 512 / NT;          // ring groups (power of two)
+  static_assert(!kFront || (kRing && !kDerive && NT == 32 && G == 4), "front mode: one-chunk ring variant, C_out = 32");
+  constexpr int kGroups = kFront ? kRwFrontCols / 32 : 512 / NT;   // ring groups: 16 x 32 or 8 x 64 columns; 12 x 32 next to the front accumulators
   constexpr int kWChunk = kRwWChunk * (NT / 32);
   for (int i = threadIdx.x; i < 64; i += (int)blockDim.x) {
     s_bias[i] = (p.bias && i < NT) ? p.bias[i] : 0.f;
-    s_bias[64 + i] = (p.fuse_outc && i < 32) ? p.outc_w[i] : 0.f;
+    s_bias[64 + i] = i < 32 ? ((p.fuse_outc) ? p.outc_w[i] : 0.f) : ((kFront && p.fbias) ? p.fbias[i - 32] : 0.f);
   }
   tc_fence_before();
   __syncthreads();
@@ -166,15 +180,16 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      mbar_expect_tx(wfull, (uint32_t)p.w_total);
+      mbar_expect_tx(wfull, (uint32_t)p.w_total + (kFront ? 2048u : 0u));
       {
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
         for (int off = 0; off < p.w_total; off += kWChunk) bulk_load(wres + off, wsrc + off, kWChunk, wfull);
+        if (kFront) bulk_load(fscr + kRwFrontScratch, p.fw, 2048, wfull);
       }
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t box_bytes = (uint32_t)stage_bytes;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = blockIdx.x; !kFront && item < num_items; item += gridDim.x) {
         const RwItem it = rw_decode(p, item);
         for (int r0 = 0; r0 < it.rows_in; r0 += G) {
           for (int ch = 0; ch < nchunk; ++ch) {
@@ -244,21 +259,21 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             // groups wrap around the ring (2 of 16) issue an N = 64 and an N = 32 instruction instead of one N = 96.
             constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * NT >> 3) << 17) | ((128u >> 4) << 24);
             constexpr uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-            constexpr uint32_t gm = (uint32_t)(kGroups - 1);
-            constexpr int glog = kGroups == 16 ? 4 : 3;
+            constexpr uint32_t kg = (uint32_t)kGroups;
             if (elect_one()) {
               uint32_t tt = (uint32_t)slot0;   // ring variant: slot0 counts rows (never wrapped at five)
 #pragma unroll
               for (int r = 0; r < G; ++r) {
                 if (r < rows) {
+                  const uint32_t gi = tt % kg;
                   if (first) {   // group of output tt: cleared by its previous owner
-                    mbar_wait(&sfree[tt & gm], (((tt + 2u) >> glog) & 1u) ^ 1u);
+                    mbar_wait(&sfree[gi], (((tt + 2u) / kg) & 1u) ^ 1u);
                     tc_fence_after();
                   }
-                  const uint32_t pos = ((uint32_t)kGroups - (tt & gm)) & gm;
+                  const uint32_t pos = (kg - gi) % kg;
                   const uint32_t d = tmem_base + pos * (uint32_t)NT;
                   const uint32_t a_row = a_lo_const | (sa16 + (uint32_t)(r * 128));
-                  if (pos <= gm - 2u) {
+                  if (pos <= kg - 3u) {
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
@@ -269,7 +284,7 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                       }
                     }
                   } else {
-                    const bool two_first = pos == gm - 1u;   // groups (last - 1, last | 0)   or   (last | 0, 1)
+                    const bool two_first = pos == kg - 2u;   // groups (last - 1, last | 0)   or   (last | 0, 1)
                     const uint32_t id_a = two_first ? idesc2 : idesc1, id_b = two_first ? idesc1 : idesc2;
                     const uint32_t nb = two_first ? (uint32_t)(2 * NT) : (uint32_t)NT;   // B rows (16 B each) of the first instruction
 #pragma unroll
@@ -282,7 +297,7 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                       }
                     }
                   }
-                  if (last) tc_commit(&rowdone[tt & gm]);
+                  if (last) tc_commit(&rowdone[gi]);
                   ++tt;
                 }
               }
@@ -404,6 +419,107 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         }
       }
     }
+  } else if (kFront && warp >= kRwDeriveWarp0) {
+    // =============================== first conv (front mode) ===============================
+    // inc.conv (Conv2d 1 -> 32, 3x3, ReLU: unet_parts.py:57-87) computed straight into the stage ring: these four warps are
+    // the 128 positions of a row.  Per stage (four rows of inc.conv's output): every lane gathers the 3x3 fp32 neighbourhood
+    // of its pixel and writes it as two bf16 im2col rows (x_hi, x_lo: K = 9 taps padded to 16) in the K-major operand
+    // layout; one elected lane issues x_hi w_hi + x_lo w_hi + x_hi w_lo (three N = 32 MMAs per row, ~2^-16 relative like the
+    // other split GEMMs) into the TMEM columns behind the ring; then each warp reads its lane quarter back, adds the bias,
+    // applies ReLU and stores the 32 bf16 channels of its pixel where the TMA box of the unfused kernel would have put them.
+    if constexpr (kFront) {
+      const int fw_ = warp - kRwDeriveWarp0;        // 0..3; TMEM lane quarter = warp % 4
+      const int quarter = warp & 3, pos = quarter * 32 + lane;
+      const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+      constexpr uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+      constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+      const uint32_t fscr_16 = smem_u32(fscr) >> 4;
+      const uint32_t a_lo_c = 128u << 16;            // LBO_A: 128 positions x 16 B between the two K halves
+      const uint32_t b_lo_c = 32u << 16;             // LBO_B: 32 filter rows x 16 B
+      const uint32_t bw_16 = fscr_16 + (uint32_t)(kRwFrontScratch >> 4);
+      const int H0 = p.H0, W0 = p.W0, Ha = H0 - 2, Wa = W0 - 2;
+      const float4* fb4 = reinterpret_cast<const float4*>(s_bias + 96);
+      int stage = 0;
+      uint32_t phase = 0, fpar = 0;
+      if (fw_ == 0) mbar_wait(wfull, 0);             // the filter tiles have landed (only the issuing warp needs to know)
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const RwItem it = rw_decode(p, item);
+        const float* xn = p.fx + (long)it.n * p.fx_img_stride;
+        const int xa = it.bx + pos;                  // column of this lane's pixel in inc.conv's output
+        for (int r0 = 0; r0 < it.rows_in; r0 += G) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          // ---- im2col rows of the four output rows
+#pragma unroll
+          for (int r = 0; r < G; ++r) {
+            const int ya = it.by + r0 + r;
+            uint32_t hi[5], lo[5];
+            const bool in = ya >= 0 && ya < Ha && xa >= 0 && xa < Wa;
+            float t[10];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) t[k] = in ? __ldg(xn + (long)(ya + k / 3) * W0 + xa + k % 3) : 0.f;
+            t[9] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(t[2 * k]), h1 = __float2bfloat16_rn(t[2 * k + 1]);
+              const float l0 = t[2 * k] - __bfloat162float(h0), l1 = t[2 * k + 1] - __bfloat162float(h1);
+              hi[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              lo[k] = pack_bf16x2(l0, l1);
+            }
+            uint8_t* th = fscr + r * 8192 + pos * 16;   // x_hi tile of row r: [2 halves][128 positions][8 taps]
+            *reinterpret_cast<uint4*>(th) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(th + 2048) = make_uint4(hi[4], 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(th + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(th + 4096 + 2048) = make_uint4(lo[4], 0u, 0u, 0u);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          tc_fence_before();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (fw_ == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int r = 0; r < G; ++r) {
+                const uint32_t d = tmem_base + (uint32_t)(kRwFrontCols + 32 * r);
+                const uint32_t xh = a_lo_c | (fscr_16 + (uint32_t)(r * 512)), xl = xh + 256u;
+                tc_mma_bf16(d, xh, desc_hi, b_lo_c | bw_16, desc_hi, idesc1, 0u);
+                tc_mma_bf16(d, xl, desc_hi, b_lo_c | bw_16, desc_hi, idesc1, 1u);
+                tc_mma_bf16(d, xh, desc_hi, b_lo_c | (bw_16 + 64u), desc_hi, idesc1, 1u);
+              }
+              tc_commit(fbar);
+            }
+            __syncwarp();
+          }
+          mbar_wait(fbar, fpar);
+          fpar ^= 1;
+          tc_fence_after();
+          // ---- bias, ReLU, bf16: the stage image [4 channel blocks][G rows][128 positions][8 channels]
+          uint8_t* sa = stage_base + (size_t)stage * stage_bytes + pos * 16;
+#pragma unroll
+          for (int r = 0; r < G; ++r) {
+            uint32_t rb[32];
+            tc_ld32(tmem_base + lane_base + (uint32_t)(kRwFrontCols + 32 * r), rb);
+            const int ya = it.by + r0 + r;
+            const bool in = ya >= 0 && ya < Ha && xa >= 0 && xa < Wa;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 b0 = fb4[2 * g], b1 = fb4[2 * g + 1];
+              uint4 o;
+              o.x = pack_bf16x2(fmaxf(__uint_as_float(rb[8 * g + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(rb[8 * g + 1]) + b0.y, 0.f));
+              o.y = pack_bf16x2(fmaxf(__uint_as_float(rb[8 * g + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(rb[8 * g + 3]) + b0.w, 0.f));
+              o.z = pack_bf16x2(fmaxf(__uint_as_float(rb[8 * g + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(rb[8 * g + 5]) + b1.y, 0.f));
+              o.w = pack_bf16x2(fmaxf(__uint_as_float(rb[8 * g + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(rb[8 * g + 7]) + b1.w, 0.f));
+              if (!in) o = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(sa + g * (G * kRwRowBytes) + r * kRwRowBytes) = o;
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
   } else {
     // =============================== epilogue ===============================
     // kSets sets x 4 TMEM lane quarters; set s finishes the output rows u with u % kSets == s.  Output row u (CTA-wide
@@ -477,18 +593,17 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         long long pb = clock64();
 #endif
         if constexpr (kRing) {
-          constexpr int gm = kGroups - 1, glog = kGroups == 16 ? 4 : 3;
-          const int r2 = u + 2;
+          const int r2 = u + 2, gu = (u + kGroups) % kGroups;
 #ifdef UNCL_PROBES
           const long long pa = clock64();
 #endif
-          mbar_wait(&rowdone[r2 & gm], (uint32_t)((r2 >> glog) & 1));   // all three contributions have landed
+          mbar_wait(&rowdone[r2 % kGroups], (uint32_t)((r2 / kGroups) & 1));   // all three contributions have landed
 #ifdef UNCL_PROBES
           pw[2] += clock64() - pa;
           pb = clock64();
 #endif
           tc_fence_after();
-          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(((kGroups - (u & gm)) & gm) * NT);
+          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(((kGroups - gu) % kGroups) * NT);
 #pragma unroll
           for (int h = 0; h < NT / 32; ++h) {
             float v[32];
@@ -502,7 +617,7 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             if (h == NT / 32 - 1) {
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&sfree[u & gm]);
+              if (lane == 0) mbar_arrive(&sfree[gu]);
             }
             if (store) finish(v, h);
           }
@@ -581,7 +696,8 @@ int rw_pick_R(int N, int nbands, int Ho, int sms) {
 }
 
 int rw_plan(RwParams& p, int N, int C_in, int H, int W, int C_out, int pad, int Wc, int derive, int sms, const char* what,
-            int* smem_bytes_out) {
+            int* smem_bytes_out, int front = 0) {
+  p.front = front; p.f_bytes = front ? kRwFrontBytes : 0;
   UNCL_REQUIRE(C_out == 32 || (C_out == 64 && !derive), "%s: C_out must be 32 (or 64 without fused skip operators), got %d", what, C_out);
   p.NT = C_out;
   p.pad = pad; p.H_in = H; p.W_in = W;
@@ -595,8 +711,8 @@ int rw_plan(RwParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
   p.nchunk = C_in / 32;
   p.w_total = p.nchunk * kRwWChunk * (C_out / 32);
   UNCL_REQUIRE(p.nchunk <= kRwMaxProg, "%s: C_in=%d too deep", what, C_in);
-  const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwRing + 1) * 8 + 16 + 128 * 4 + 256;
-  const int budget = 227 * 1024 - tail - p.w_total;
+  const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwRing + 2) * 8 + 16 + 128 * 4 + 256;
+  const int budget = 227 * 1024 - tail - p.w_total - p.f_bytes;
   // Rows per pipeline stage.  Slot variant (C_out = 32 with several K chunks per row group): a group's rows complete together,
   // and row a + G + k of the next group needs the slot of row a + G + k - 5, whose epilogue waits for row a + G + k - 3: that
   // row must belong to an earlier group, so G <= 3.  The ring variant (one-chunk layers, C_out = 64) has 16 / 8 groups of
@@ -634,7 +750,7 @@ int rw_plan(RwParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
       p.prog_kind[k] = 0; p.prog_cb[k] = (unsigned char)(4 * (cs32 + j)); p.prog_wch[k] = (unsigned char)(cs32 + j); p.prog_back[k] = 0; ++k;
     }
   }
-  int smem_bytes = p.stages * p.stage_bytes + p.w_total + tail;
+  int smem_bytes = p.stages * p.stage_bytes + p.w_total + p.f_bytes + tail;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM (each owns all 512 TMEM columns)
   *smem_bytes_out = smem_bytes;
   return UNCL_OK;
@@ -642,13 +758,17 @@ int rw_plan(RwParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
 
 int rw_launch(const void* in, long in_img_stride, const void* w_rows, const float* bias, void* out, long out_img_stride, int N,
               int C_in, int H, int W, int C_out, int pad, int Wc, int act, int emit_skip, int fuse_outc, const float* outc_w,
-              const float* outc_b, float* out_img, float* out_logit, int derive, const char* what, cudaStream_t stream) {
-  UNCL_REQUIRE(in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_rows) & 15) == 0,
-               "%s: input / weights must be 16-byte aligned", what);
+              const float* outc_b, float* out_img, float* out_logit, int derive, const char* what, cudaStream_t stream,
+              const float* fx = nullptr, long fx_img_stride = 0, const void* fw = nullptr, const float* fbias = nullptr) {
+  const int front = fx != nullptr ? 1 : 0;   // `in` is unused then: H, W are the extent of the first conv's OUTPUT
+  UNCL_REQUIRE(front || (in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0), "%s: input must be 16-byte aligned", what);
+  UNCL_REQUIRE((reinterpret_cast<uintptr_t>(w_rows) & 15) == 0 && (reinterpret_cast<uintptr_t>(fw) & 15) == 0,
+               "%s: weights must be 16-byte aligned", what);
   RwParams p{};
   int smem_bytes = 0;
   const int sms = sm_count();
-  if (int rc = rw_plan(p, N, C_in, H, W, C_out, pad, Wc, derive, sms, what, &smem_bytes)) return rc;
+  if (int rc = rw_plan(p, N, C_in, H, W, C_out, pad, Wc, derive, sms, what, &smem_bytes, front)) return rc;
+  p.fx = fx; p.fx_img_stride = fx_img_stride; p.fw = reinterpret_cast<const bf16*>(fw); p.fbias = fbias; p.H0 = H + 2; p.W0 = W + 2;
   p.w = reinterpret_cast<const bf16*>(w_rows);
   p.bias = bias; p.out = reinterpret_cast<bf16*>(out); p.out_img_stride = out_img_stride;
   p.outc_w = outc_w; p.outc_b = outc_b; p.out_img = out_img; p.out_logit = out_logit;
@@ -658,20 +778,26 @@ int rw_launch(const void* in, long in_img_stride, const void* w_rows, const floa
   if (getenv("UNCL_RW_NORING")) p.ring = 0;
   if (const char* e = getenv("UNCL_RW_PROBE")) p.probe = atoi(e);
 #endif
-  CUtensorMap tmap;
-  CUresult r = encode_blocked_bf16(&tmap, in, W, H, (derive ? C_in / 2 : C_in) / 8, N, in_img_stride, 128, p.G, 4);
-  if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
+  CUtensorMap tmap{};   // front mode: no activation tensor exists, the map is never touched
+  if (!front) {
+    CUresult r = encode_blocked_bf16(&tmap, in, W, H, (derive ? C_in / 2 : C_in) / 8, N, in_img_stride, 128, p.G, 4);
+    if (r != CUDA_SUCCESS) return uncl_set_error(UNCL_ECUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
+  }
   const int grid = p.num_items < sms ? p.num_items : sms;
   // one instantiation per (fused skip operators, rows per stage): the issuing warp's descriptor offsets are immediates
-  static thread_local int smem_ok[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, smem_dev[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
-#define RW_LAUNCH(D, GG, RING, NTT, slot_)                                                                                   \
+  static thread_local int smem_ok[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, smem_dev[10] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+#define RW_LAUNCH(D, GG, RING, NTT, slot_) RW_LAUNCH5(D, GG, RING, NTT, false, slot_)
+#define RW_LAUNCH5(D, GG, RING, NTT, FR, slot_)                                                                                   \
   do {                                                                                                                      \
-    cudaError_t e = ensure_smem(conv3x3_tc_rows_kernel<D, GG, RING, NTT>, smem_bytes, smem_ok[slot_], smem_dev[slot_]);       \
+    cudaError_t e = ensure_smem(conv3x3_tc_rows_kernel<D, GG, RING, NTT, FR>, smem_bytes, smem_ok[slot_], smem_dev[slot_]);   \
     if (e != cudaSuccess) return uncl_set_error(UNCL_ECUDA, "%s: smem attr: %s", what, cudaGetErrorString(e));               \
-    conv3x3_tc_rows_kernel<D, GG, RING, NTT><<<grid, D ? kRwThreadsDerive : kRwThreads, smem_bytes, stream>>>(tmap, p);       \
+    conv3x3_tc_rows_kernel<D, GG, RING, NTT, FR><<<grid, (D || FR) ? kRwThreadsDerive : kRwThreads, smem_bytes, stream>>>(tmap, p); \
   } while (0)
   const bool ring = !derive && (C_out == 64 || (p.nchunk == 1 && p.ring));
-  if (derive) {
+  if (front) {
+    UNCL_REQUIRE(p.G == 4 && p.nchunk == 1 && C_out == 32 && !derive, "%s: front mode needs the one-chunk C_out = 32 layer", what);
+    RW_LAUNCH5(false, 4, true, 32, true, 9);
+  } else if (derive) {
     if (p.G == 3) RW_LAUNCH(true, 3, false, 32, 0);
     else if (p.G == 2) RW_LAUNCH(true, 2, false, 32, 1);
     else return uncl_set_error(UNCL_EINVAL, "%s: no kernel for %d rows per stage", what, p.G);
@@ -688,6 +814,7 @@ int rw_launch(const void* in, long in_img_stride, const void* w_rows, const floa
     else return uncl_set_error(UNCL_EINVAL, "%s: no kernel for %d rows per stage", what, p.G);
   }
 #undef RW_LAUNCH
+#undef RW_LAUNCH5
   return uncl_check_launch(what);
 }
 
@@ -735,6 +862,23 @@ extern "C" int uncl_conv3x3_tc_rows(const void* in, long in_img_stride, const vo
   return UNCL_OK;
 }
 
+// inc.conv + inc.conv1 of the generator in ONE launch (Conv2d 1 -> 32 3x3 + ReLU, Conv2d 32 -> 32 3x3 + ReLU:
+// unet_parts.py:57-87 with in_ch = 1): the first conv's output is never written to memory - four extra warps compute it into
+// the stage ring of the row kernel (front mode, see the kernel).  x: [N][H0][W0] fp32; fw = packing.conv_first_rows(w1);
+// fbias: [32]; w_rows = packing.conv3x3_tc_rows(w9 of the second conv); out: bf16 blocked [N][4 (+ skip planes)][H0-4][W0-4][8].
+// W0 - 4 must be a whole number of 126-column bands (252 for the 256-pixel tiles of the generator).
+extern "C" int uncl_conv_first_conv3x3_tc_rows(const float* x, long x_img_stride, const void* fw, const float* fbias,
+                                               const void* w_rows, const float* bias, void* out, long out_img_stride, int N, int H0,
+                                               int W0, int act, int emit_skip, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && x != nullptr && fw != nullptr && fbias != nullptr && w_rows != nullptr && out != nullptr && H0 > 4 && W0 > 4,
+               "conv_first_conv3x3_tc_rows: bad arguments (N=%d H0=%d W0=%d)", N, H0, W0);
+  UNCL_REQUIRE(act == UNCL_ACT_RELU || act == UNCL_ACT_NONE, "conv_first_conv3x3_tc_rows: only ReLU / identity epilogues are built");
+  const int Wo = W0 - 4;
+  UNCL_REQUIRE(rw_cols(Wo) == Wo, "conv_first_conv3x3_tc_rows: %d output columns are not whole 126-column bands", Wo);
+  return rw_launch(nullptr, 0, w_rows, bias, out, out_img_stride, N, 32, H0 - 2, W0 - 2, 32, 0, Wo, act, emit_skip, 0, nullptr, nullptr,
+                   nullptr, nullptr, 0, "conv_first_conv3x3_tc_rows", stream, x, x_img_stride, fw, fbias);
+}
+
 // uncl_conv3x3_tc_skipcat (fused skip operators, `in` = [skip (C_skip) | up-sampled (C_skip)], C_out = 32) through the row
 // kernel.  w_rows / w_tail: packing.conv3x3_tc_rows / packing.conv3x3_tc of the full [9][4*C_skip][32] filter bank.
 extern "C" int uncl_conv3x3_tc_rows_skipcat(const void* in, long in_img_stride, const void* w_rows, const void* w_tail,
@@ -769,7 +913,7 @@ extern "C" int uncl_conv3x3_tc_rows_plan(int N, int C_in, int H, int W, int C_ou
   for (int i = 0; i < 16; ++i) plan[i] = 0;
   const int Wo = W + 2 * pad - 2;
   const int nchunk = C_in / 32;
-  const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwRing + 1) * 8 + 16 + 128 * 4 + 256;
+  const int tail = 128 + 128 + (2 * kRwMaxStages + 2 * kRwRing + 2) * 8 + 16 + 128 * 4 + 256;
   if (nchunk > kRwMaxProg || (derive && C_in % 128 != 0) ||
       227 * 1024 - tail - nchunk * kRwWChunk * (C_out / 32) < (derive ? 5 : 3) * 2 * 4 * kRwRowBytes)
     return UNCL_OK;   // plan[0] = 0: not eligible

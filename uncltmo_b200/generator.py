@@ -73,6 +73,9 @@ class _GeneratorBase(nn.Module):
         # bf16 inference: the narrow layers at 122..256 pixels (inc.conv1, down0.conv*, up2.conv*, up3.conv*) run in the row kernel
         # (conv_tc_rows.cu: ky taps merged into N, every input row through shared memory once).  False = the older kernels.
         self.row_kernel = True
+        # ... and inc.conv (1 -> 32) is computed inside inc.conv1's launch: its 32-channel output never reaches memory
+        # (uncl_conv_first_conv3x3_tc_rows).  False = uncl_conv_first + the row kernel.
+        self.fused_first = True
         self.to_crop = to_crop
         self.depth = depth
         self.recurrent_ch_ratio = recurrent_ch_ratio
@@ -154,6 +157,8 @@ class _GeneratorBase(nn.Module):
 
         with torch.no_grad():
             P["inc0"] = (packing.conv_first(self.inc.conv.conv.weight.detach()), self.inc.conv.conv.bias.detach().float().contiguous())
+            if tc:
+                P["inc0_rows"] = packing.conv_first_rows(self.inc.conv.conv.weight.detach())
             conv("inc1", self.inc.conv.conv1, False)
             for i in range(4):
                 blk = self.down_path[i].mpconv[1]
@@ -236,9 +241,14 @@ class _GeneratorBase(nn.Module):
         sizes = [(f, 252), (2 * f, 122), (4 * f, 57), (8 * f, 24)]
         nfused = 2 if (self.precision == "bf16" and keep is None and self.fused_skip) else 0
         cat = [buf((2 if i < nfused else 4) * c, s, s) for i, (c, s) in enumerate(sizes)]
-        a0 = buf(f, 254, 254)
-        call("uncl_conv_first", x, P["inc0"][0], P["inc0"][1], a0, st(a0), n, 256, 256, f, ACT_RELU, dt)
-        self._conv3(P, "inc1", a0, st(a0), cat[0], st(cat[0]), n, f, 254, 254, f, 0, emit_skip=0 if nfused > 0 else 1)
+        if (self.precision == "bf16" and self.row_kernel and self.fused_first and keep is None and "inc1_rows" in P
+                and "inc0_rows" in P):
+            call("uncl_conv_first_conv3x3_tc_rows", x, x.stride(0), P["inc0_rows"], P["inc0"][1], P["inc1_rows"], P["inc1"][1],
+                 cat[0], st(cat[0]), n, 256, 256, ACT_RELU, 0 if nfused > 0 else 1)
+        else:
+            a0 = buf(f, 254, 254)
+            call("uncl_conv_first", x, P["inc0"][0], P["inc0"][1], a0, st(a0), n, 256, 256, f, ACT_RELU, dt)
+            self._conv3(P, "inc1", a0, st(a0), cat[0], st(cat[0]), n, f, 254, 254, f, 0, emit_skip=0 if nfused > 0 else 1)
         state = [cat[0]]  # tensors whose first C/32 channels feed the next frame (Unet.py:229,251,264,272)
         cur, cur_c, cur_s = cat[0], f, 252
         for i in range(4):

@@ -177,6 +177,17 @@ def conv_first_layout(w):
     return w.reshape(w.shape[0], 9).t().contiguous()
 
 
+def conv_first_rows(w):
+    """Conv2d(1, 32, 3) weight [32][1][3][3] -> the B operand of the row kernel's front mode (uncl_conv_first_conv3x3_tc_rows):
+    bf16 [2 (w_hi, w_lo)][2 K halves][32 (co)][8 (tap in half)], taps 9..15 zero."""
+    w9 = w.reshape(w.shape[0], 9).t().float()                      # [9][32]
+    hi = w9.to(torch.bfloat16)
+    lo = (w9 - hi.float()).to(torch.bfloat16)
+    t = torch.zeros((2, 16, w.shape[0]), device=w.device, dtype=torch.bfloat16)
+    t[0, :9], t[1, :9] = hi, lo
+    return t.reshape(2, 2, 8, w.shape[0]).permute(0, 1, 3, 2).contiguous()
+
+
 def blocked_param(t):
     """[1][C][H][W] -> C8-blocked [C/8][H*W][8] fp32 (pos_embed)."""
     return blocked_param_layout(t).float()
