@@ -94,11 +94,11 @@ int uncl_conv3x3_tc_rows(const void* in, long in_img_stride, const void* w_rows,
 /* inconv of the generator in one launch: Conv2d(1, 32, 3) + ReLU + Conv2d(32, 32, 3) + ReLU (unet_parts.py:57-87 with in_ch = 1,
  * Unet_singleFrame.py inc).  The first conv's 32-channel output never reaches memory: four extra warps of the row kernel
  * compute it into the stage ring (im2col rows in shared memory, three-term bf16 split MMAs, bias + ReLU) while the second
- * conv consumes it.  x: [N][H0][W0] fp32, image stride x_img_stride elements; fw = packing.conv_first_rows(w1), fbias [32];
- * w_rows = packing.conv3x3_tc_rows(w9), bias [32]; out: bf16 blocked, (H0-4) x (W0-4), emit_skip as in uncl_conv3x3_tc.
+ * conv consumes it.  x: [N][H0][W0] fp32, image stride x_img_stride elements; fw = packing.conv_first_rows(w1, b1) (the
+ * bias rides on a constant-one tap); w_rows = packing.conv3x3_tc_rows(w9), bias [32]; out: bf16 blocked, (H0-4) x (W0-4), emit_skip as in uncl_conv3x3_tc.
  * W0 - 4 must be a multiple of 126 or < 126 (252 for the generator's 256-pixel tiles). */
-int uncl_conv_first_conv3x3_tc_rows(const float* x, long x_img_stride, const void* fw, const float* fbias, const void* w_rows,
-                                    const float* bias, void* out, long out_img_stride, int N, int H0, int W0, int act,
+int uncl_conv_first_conv3x3_tc_rows(const float* x, long x_img_stride, const void* fw, const void* w_rows, const float* bias,
+                                    void* out, long out_img_stride, int N, int H0, int W0, int act,
                                     int emit_skip, uncl_stream_t stream);
 
 /* uncl_conv3x3_tc_skipcat (unet_parts.py:311-332, skip operators built in shared memory, C_out = 32) through the row kernel.

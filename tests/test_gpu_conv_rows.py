@@ -183,7 +183,7 @@ def test_row_kernel_front_mode_fuses_the_first_conv(n, h0, emit):
     wt, wr = packing.conv3x3_tc(w9), packing.conv3x3_tc_rows(w9)
     _lib.call("uncl_conv3x3_tc_rows", a0, a0.stride(0), wr, wt, b, two, two.stride(0), n, 32, ha, ha, 32, 0, 1, emit, 0,
               None, None, None, None)
-    _lib.call("uncl_conv_first_conv3x3_tc_rows", x, x.stride(0), packing.conv_first_rows(w1), b1, wr, b, one, one.stride(0), n,
+    _lib.call("uncl_conv_first_conv3x3_tc_rows", x, x.stride(0), packing.conv_first_rows(w1, b1), wr, b, one, one.stride(0), n,
               h0, h0, 1, emit)
     ref0 = torch.relu(torch.nn.functional.conv2d(x, w1, b1))
     w2 = w9.reshape(3, 3, 32, 32).permute(3, 2, 0, 1).contiguous()

@@ -76,14 +76,14 @@ if len(sys.argv) <= 3:
     a0 = torch.empty((n, 4, 254, 254, 8), device=dev, dtype=torch.bfloat16)
     o0 = torch.empty((n, 4, 252, 252, 8), device=dev, dtype=torch.bfloat16)
     o1 = torch.empty_like(o0)
-    wt, wr, cf, cfr = packing.conv3x3_tc(w9), packing.conv3x3_tc_rows(w9), packing.conv_first(w1), packing.conv_first_rows(w1)
+    wt, wr, cf, cfr = packing.conv3x3_tc(w9), packing.conv3x3_tc_rows(w9), packing.conv_first(w1), packing.conv_first_rows(w1, b1)
 
     def two():
         _lib.call("uncl_conv_first", x, cf, b1, a0, a0.stride(0), n, 256, 256, 32, 1, _lib.BF16)
         _lib.call("uncl_conv3x3_tc_rows", a0, a0.stride(0), wr, wt, b, o0, o0.stride(0), n, 32, 254, 254, 32, 0, 1, 0, 0, None, None, None, None)
 
     def one():
-        _lib.call("uncl_conv_first_conv3x3_tc_rows", x, x.stride(0), cfr, b1, wr, b, o1, o1.stride(0), n, 256, 256, 1, 0)
+        _lib.call("uncl_conv_first_conv3x3_tc_rows", x, x.stride(0), cfr, wr, b, o1, o1.stride(0), n, 256, 256, 1, 0)
 
     t2, t1 = timed(two), timed(one)
     print("inc.conv + inc.conv1  %4d tiles  two launches %8.1f us  fused %8.1f us  x%.2f  rel diff %.2e"

@@ -45,7 +45,7 @@ constexpr int kRwSlots = 5;            // accumulator slots of 96 TMEM columns
 constexpr int kRwRing = 16;            // ring variant: accumulator groups of C_out TMEM columns, one per output row (16 x 32 or 8 x 64)
 constexpr int kRwMaxProg = 16;
 constexpr int kRwFrontScratch = 4 * 2 * 4096;          // front mode: x_hi / x_lo im2col tiles of the four rows of a stage
-constexpr int kRwFrontBytes = kRwFrontScratch + 2048;  // ... + the first conv's w_hi / w_lo tiles
+constexpr int kRwFrontBytes = 2 * kRwFrontScratch + 2048;  // two such buffers (the next stage is built while this one's MMAs run) + the first conv's w_hi / w_lo tiles
 constexpr int kRwFrontCols = 384;                      // front mode: TMEM columns 384..511 hold the first conv's accumulators
 constexpr int kRwRowBytes = 128 * 16;  // one row of one channel block in shared memory
 constexpr int kRwWChunk = 2 * 3 * 2 * 96 * 16;   // packed weights of 32 input channels, C_out = 32: 18432 B (x2 for C_out = 64)
@@ -69,8 +69,7 @@ struct RwParams {
   // front mode (inc.conv fused in front of inc.conv1): the stage ring is not loaded by TMA but COMPUTED by four extra warps from
   // the fp32 image - im2col rows in shared memory, three-term bf16 split MMAs (x_hi w_hi + x_lo w_hi + x_hi w_lo), bias + ReLU
   const float* fx;      // [N][H0][W0] fp32 image (1 channel)
-  const bf16* fw;       // packing.conv_first_rows: [2 (hi, lo)][2 halves][32][8] bf16
-  const float* fbias;   // [32]
+  const bf16* fw;       // packing.conv_first_rows: [2 (hi, lo)][2 halves][32][8] bf16, tap 9 = the bias
   long fx_img_stride;
   int front, H0, W0, f_bytes;
   int ring;    // one-chunk layers: ring variant of the accumulators (host switch: 1 by default)
@@ -104,6 +103,13 @@ __device__ __forceinline__ uint32_t rw_bf16x2_mul(uint32_t a, uint32_t b) {
 __device__ __forceinline__ uint32_t rw_bf16x2_sqrt_eps(uint32_t v) {
   const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
   return pack_bf16x2(fast_sqrt(lo + 1e-8f), fast_sqrt(hi + 1e-8f));
+}
+
+// two floats -> bf16x2 with ReLU (low half = first argument, like pack_bf16x2)
+__device__ __forceinline__ uint32_t rw_pack_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 
 // 32 lanes x 32 columns of zeros into TMEM (ring variant: an accumulator group is handed back cleared)
@@ -161,7 +167,7 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
   constexpr int kWChunk = kRwWChunk * (NT / 32);
   for (int i = threadIdx.x; i < 64; i += (int)blockDim.x) {
     s_bias[i] = (p.bias && i < NT) ? p.bias[i] : 0.f;
-    s_bias[64 + i] = i < 32 ? ((p.fuse_outc) ? p.outc_w[i] : 0.f) : ((kFront && p.fbias) ? p.fbias[i - 32] : 0.f);
+    s_bias[64 + i] = (p.fuse_outc && i < 32) ? p.outc_w[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -184,7 +190,7 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
       {
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
         for (int off = 0; off < p.w_total; off += kWChunk) bulk_load(wres + off, wsrc + off, kWChunk, wfull);
-        if (kFront) bulk_load(fscr + kRwFrontScratch, p.fw, 2048, wfull);
+        if (kFront) bulk_load(fscr + 2 * kRwFrontScratch, p.fw, 2048, wfull);
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -425,8 +431,8 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     // the 128 positions of a row.  Per stage (four rows of inc.conv's output): every lane gathers the 3x3 fp32 neighbourhood
     // of its pixel and writes it as two bf16 im2col rows (x_hi, x_lo: K = 9 taps padded to 16) in the K-major operand
     // layout; one elected lane issues x_hi w_hi + x_lo w_hi + x_hi w_lo (three N = 32 MMAs per row, ~2^-16 relative like the
-    // other split GEMMs) into the TMEM columns behind the ring; then each warp reads its lane quarter back, adds the bias,
-    // applies ReLU and stores the 32 bf16 channels of its pixel where the TMA box of the unfused kernel would have put them.
+    // other split GEMMs; the bias is a tenth tap whose input is the constant 1) into the TMEM columns behind the ring; then
+    // each warp reads its lane quarter back, applies ReLU inside the bf16 conversion and stores the 32 bf16 channels of its pixel where the TMA box of the unfused kernel would have put them.
     if constexpr (kFront) {
       const int fw_ = warp - kRwDeriveWarp0;        // 0..3; TMEM lane quarter = warp % 4
       const int quarter = warp & 3, pos = quarter * 32 + lane;
@@ -436,88 +442,113 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
       const uint32_t fscr_16 = smem_u32(fscr) >> 4;
       const uint32_t a_lo_c = 128u << 16;            // LBO_A: 128 positions x 16 B between the two K halves
       const uint32_t b_lo_c = 32u << 16;             // LBO_B: 32 filter rows x 16 B
-      const uint32_t bw_16 = fscr_16 + (uint32_t)(kRwFrontScratch >> 4);
+      const uint32_t bw_16 = fscr_16 + (uint32_t)(2 * kRwFrontScratch >> 4);
       const int H0 = p.H0, W0 = p.W0, Ha = H0 - 2, Wa = W0 - 2;
-      const float4* fb4 = reinterpret_cast<const float4*>(s_bias + 96);
-      int stage = 0;
+      // im2col rows (x_hi, x_lo) of the four output rows of the stage that starts at row `ya0` of image `n`, into buffer `buf`
+      auto build = [&](int n, int ya0, int xa, int buf) {
+        const float* xn = p.fx + (long)n * p.fx_img_stride;
+        // the 6 x 3 input pixels behind this lane's four output pixels, split x = x_hi + x_lo (x_hi kept as an fp32 whose low
+        // 16 bits are zero: two of them pack into a bf16x2 with one PRMT)
+        uint32_t hb[G + 2][3];
+        float lo[G + 2][3];
+        const bool xin = xa >= 0 && xa + 2 < W0;
+#pragma unroll
+        for (int j = 0; j < G + 2; ++j) {
+          const int yi = ya0 + j;
+          const bool in = xin && yi >= 0 && yi < H0;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float v = in ? __ldg(xn + (long)yi * W0 + xa + c) : 0.f;
+            const float h = __bfloat162float(__float2bfloat16_rn(v));
+            hb[j][c] = __float_as_uint(h);
+            lo[j][c] = v - h;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < G; ++r) {
+          // taps k = 3 ky + kx -> pixel (r + ky, kx); tap 9 of x_hi is the constant 1 that multiplies the bias row of the filters
+          uint8_t* th = fscr + buf * kRwFrontScratch + r * 8192 + pos * 16;   // x_hi tile of row r: [2 halves][128 positions][8 taps]
+          uint4 h0, l0;
+          h0.x = __byte_perm(hb[r][0], hb[r][1], 0x7632);     h0.y = __byte_perm(hb[r][2], hb[r + 1][0], 0x7632);
+          h0.z = __byte_perm(hb[r + 1][1], hb[r + 1][2], 0x7632); h0.w = __byte_perm(hb[r + 2][0], hb[r + 2][1], 0x7632);
+          l0.x = pack_bf16x2(lo[r][0], lo[r][1]);             l0.y = pack_bf16x2(lo[r][2], lo[r + 1][0]);
+          l0.z = pack_bf16x2(lo[r + 1][1], lo[r + 1][2]);     l0.w = pack_bf16x2(lo[r + 2][0], lo[r + 2][1]);
+          *reinterpret_cast<uint4*>(th) = h0;
+          *reinterpret_cast<uint4*>(th + 2048) = make_uint4((hb[r + 2][2] >> 16) | 0x3f800000u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(th + 4096) = l0;
+          *reinterpret_cast<uint4*>(th + 4096 + 2048) = make_uint4(pack_bf16x2(lo[r + 2][2], 0.f), 0u, 0u, 0u);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      };
+      // x_hi w_hi + x_lo w_hi + x_hi w_lo of the four rows in buffer `buf` into the front accumulators (one elected lane)
+      auto issue = [&](int buf) {
+        if (fw_ == 0) {
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int r = 0; r < G; ++r) {
+              const uint32_t d = tmem_base + (uint32_t)(kRwFrontCols + 32 * r);
+              const uint32_t xh = a_lo_c | (fscr_16 + (uint32_t)(buf * (kRwFrontScratch >> 4) + r * 512)), xl = xh + 256u;
+              tc_mma_bf16(d, xh, desc_hi, b_lo_c | bw_16, desc_hi, idesc1, 0u);
+              tc_mma_bf16(d, xl, desc_hi, b_lo_c | bw_16, desc_hi, idesc1, 1u);
+              tc_mma_bf16(d, xh, desc_hi, b_lo_c | (bw_16 + 64u), desc_hi, idesc1, 1u);
+            }
+            tc_commit(fbar);
+          }
+          __syncwarp();
+        }
+      };
+      int stage = 0, buf = 0;
       uint32_t phase = 0, fpar = 0;
       if (fw_ == 0) mbar_wait(wfull, 0);             // the filter tiles have landed (only the issuing warp needs to know)
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const RwItem it = rw_decode(p, item);
-        const float* xn = p.fx + (long)it.n * p.fx_img_stride;
-        const int xa = it.bx + pos;                  // column of this lane's pixel in inc.conv's output
-        for (int r0 = 0; r0 < it.rows_in; r0 += G) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          // ---- im2col rows of the four output rows
-#pragma unroll
-          for (int r = 0; r < G; ++r) {
-            const int ya = it.by + r0 + r;
-            uint32_t hi[5], lo[5];
-            const bool in = ya >= 0 && ya < Ha && xa >= 0 && xa < Wa;
-            float t[10];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) t[k] = in ? __ldg(xn + (long)(ya + k / 3) * W0 + xa + k % 3) : 0.f;
-            t[9] = 0.f;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(t[2 * k]), h1 = __float2bfloat16_rn(t[2 * k + 1]);
-              const float l0 = t[2 * k] - __bfloat162float(h0), l1 = t[2 * k + 1] - __bfloat162float(h1);
-              hi[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-              lo[k] = pack_bf16x2(l0, l1);
-            }
-            uint8_t* th = fscr + r * 8192 + pos * 16;   // x_hi tile of row r: [2 halves][128 positions][8 taps]
-            *reinterpret_cast<uint4*>(th) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(th + 2048) = make_uint4(hi[4], 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(th + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            *reinterpret_cast<uint4*>(th + 4096 + 2048) = make_uint4(lo[4], 0u, 0u, 0u);
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          tc_fence_before();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (fw_ == 0) {
-            tc_fence_after();
-            if (elect_one()) {
-#pragma unroll
-              for (int r = 0; r < G; ++r) {
-                const uint32_t d = tmem_base + (uint32_t)(kRwFrontCols + 32 * r);
-                const uint32_t xh = a_lo_c | (fscr_16 + (uint32_t)(r * 512)), xl = xh + 256u;
-                tc_mma_bf16(d, xh, desc_hi, b_lo_c | bw_16, desc_hi, idesc1, 0u);
-                tc_mma_bf16(d, xl, desc_hi, b_lo_c | bw_16, desc_hi, idesc1, 1u);
-                tc_mma_bf16(d, xh, desc_hi, b_lo_c | (bw_16 + 64u), desc_hi, idesc1, 1u);
-              }
-              tc_commit(fbar);
-            }
-            __syncwarp();
-          }
-          mbar_wait(fbar, fpar);
-          fpar ^= 1;
-          tc_fence_after();
-          // ---- bias, ReLU, bf16: the stage image [4 channel blocks][G rows][128 positions][8 channels]
-          uint8_t* sa = stage_base + (size_t)stage * stage_bytes + pos * 16;
-#pragma unroll
-          for (int r = 0; r < G; ++r) {
-            uint32_t rb[32];
-            tc_ld32(tmem_base + lane_base + (uint32_t)(kRwFrontCols + 32 * r), rb);
-            const int ya = it.by + r0 + r;
-            const bool in = ya >= 0 && ya < Ha && xa >= 0 && xa < Wa;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 b0 = fb4[2 * g], b1 = fb4[2 * g + 1];
-              uint4 o;
-              o.x = pack_bf16x2(fmaxf(__uint_as_float(rb[8 * g + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(rb[8 * g + 1]) + b0.y, 0.f));
-              o.y = pack_bf16x2(fmaxf(__uint_as_float(rb[8 * g + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(rb[8 * g + 3]) + b0.w, 0.f));
-              o.z = pack_bf16x2(fmaxf(__uint_as_float(rb[8 * g + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(rb[8 * g + 5]) + b1.y, 0.f));
-              o.w = pack_bf16x2(fmaxf(__uint_as_float(rb[8 * g + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(rb[8 * g + 7]) + b1.w, 0.f));
-              if (!in) o = make_uint4(0u, 0u, 0u, 0u);
-              *reinterpret_cast<uint4*>(sa + g * (G * kRwRowBytes) + r * kRwRowBytes) = o;
-            }
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full[stage]);
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+      int item = blockIdx.x, r0 = 0;
+      RwItem it = rw_decode(p, item);
+      build(it.n, it.by, it.bx + pos, 0);
+      tc_fence_before();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      issue(0);
+      while (item < num_items) {
+        // the stage after this one (same strip, or the first of the CTA's next strip): built while this one's MMAs run
+        int nitem = item, nr0 = r0 + G;
+        RwItem nit = it;
+        if (nr0 >= it.rows_in) {
+          nitem = item + (int)gridDim.x; nr0 = 0;
+          if (nitem < num_items) nit = rw_decode(p, nitem);
         }
+        const bool has_next = nitem < num_items;
+        if (has_next) build(nit.n, nit.by + nr0, nit.bx + pos, buf ^ 1);
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_wait(fbar, fpar);
+        fpar ^= 1;
+        tc_fence_after();
+        // ---- bias, ReLU, bf16: the stage image [4 channel blocks][G rows][128 positions][8 channels]
+        uint8_t* sa = stage_base + (size_t)stage * stage_bytes + pos * 16;
+        const int xa = it.bx + pos;
+#pragma unroll
+        for (int r = 0; r < G; ++r) {
+          uint32_t rb[32];
+          tc_ld32(tmem_base + lane_base + (uint32_t)(kRwFrontCols + 32 * r), rb);
+          const int ya = it.by + r0 + r;
+          const bool in = ya >= 0 && ya < Ha && xa >= 0 && xa < Wa;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {   // the bias arrived through tap 9; ReLU inside the bf16 conversion
+            uint4 o;
+            o.x = rw_pack_relu(__uint_as_float(rb[8 * g + 0]), __uint_as_float(rb[8 * g + 1]));
+            o.y = rw_pack_relu(__uint_as_float(rb[8 * g + 2]), __uint_as_float(rb[8 * g + 3]));
+            o.z = rw_pack_relu(__uint_as_float(rb[8 * g + 4]), __uint_as_float(rb[8 * g + 5]));
+            o.w = rw_pack_relu(__uint_as_float(rb[8 * g + 6]), __uint_as_float(rb[8 * g + 7]));
+            if (!in) o = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(sa + g * (G * kRwRowBytes) + r * kRwRowBytes) = o;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // every warp has read its accumulators and built its share of the next tiles
+        if (has_next) issue(buf ^ 1);
+        if (lane == 0) mbar_arrive(&full[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+        buf ^= 1;
+        item = nitem; r0 = nr0; it = nit;
       }
     }
   } else {
@@ -759,7 +790,7 @@ int rw_plan(RwParams& p, int N, int C_in, int H, int W, int C_out, int pad, int 
 int rw_launch(const void* in, long in_img_stride, const void* w_rows, const float* bias, void* out, long out_img_stride, int N,
               int C_in, int H, int W, int C_out, int pad, int Wc, int act, int emit_skip, int fuse_outc, const float* outc_w,
               const float* outc_b, float* out_img, float* out_logit, int derive, const char* what, cudaStream_t stream,
-              const float* fx = nullptr, long fx_img_stride = 0, const void* fw = nullptr, const float* fbias = nullptr) {
+              const float* fx = nullptr, long fx_img_stride = 0, const void* fw = nullptr) {
   const int front = fx != nullptr ? 1 : 0;   // `in` is unused then: H, W are the extent of the first conv's OUTPUT
   UNCL_REQUIRE(front || (in_img_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0), "%s: input must be 16-byte aligned", what);
   UNCL_REQUIRE((reinterpret_cast<uintptr_t>(w_rows) & 15) == 0 && (reinterpret_cast<uintptr_t>(fw) & 15) == 0,
@@ -768,7 +799,7 @@ int rw_launch(const void* in, long in_img_stride, const void* w_rows, const floa
   int smem_bytes = 0;
   const int sms = sm_count();
   if (int rc = rw_plan(p, N, C_in, H, W, C_out, pad, Wc, derive, sms, what, &smem_bytes, front)) return rc;
-  p.fx = fx; p.fx_img_stride = fx_img_stride; p.fw = reinterpret_cast<const bf16*>(fw); p.fbias = fbias; p.H0 = H + 2; p.W0 = W + 2;
+  p.fx = fx; p.fx_img_stride = fx_img_stride; p.fw = reinterpret_cast<const bf16*>(fw); p.H0 = H + 2; p.W0 = W + 2;
   p.w = reinterpret_cast<const bf16*>(w_rows);
   p.bias = bias; p.out = reinterpret_cast<bf16*>(out); p.out_img_stride = out_img_stride;
   p.outc_w = outc_w; p.outc_b = outc_b; p.out_img = out_img; p.out_logit = out_logit;
@@ -864,19 +895,19 @@ extern "C" int uncl_conv3x3_tc_rows(const void* in, long in_img_stride, const vo
 
 // inc.conv + inc.conv1 of the generator in ONE launch (Conv2d 1 -> 32 3x3 + ReLU, Conv2d 32 -> 32 3x3 + ReLU:
 // unet_parts.py:57-87 with in_ch = 1): the first conv's output is never written to memory - four extra warps compute it into
-// the stage ring of the row kernel (front mode, see the kernel).  x: [N][H0][W0] fp32; fw = packing.conv_first_rows(w1);
-// fbias: [32]; w_rows = packing.conv3x3_tc_rows(w9 of the second conv); out: bf16 blocked [N][4 (+ skip planes)][H0-4][W0-4][8].
+// the stage ring of the row kernel (front mode, see the kernel).  x: [N][H0][W0] fp32; fw = packing.conv_first_rows(w1, b1)
+// (the bias rides on a constant-one tap); w_rows = packing.conv3x3_tc_rows(w9 of the second conv); out: bf16 blocked [N][4 (+ skip planes)][H0-4][W0-4][8].
 // W0 - 4 must be a whole number of 126-column bands (252 for the 256-pixel tiles of the generator).
-extern "C" int uncl_conv_first_conv3x3_tc_rows(const float* x, long x_img_stride, const void* fw, const float* fbias,
-                                               const void* w_rows, const float* bias, void* out, long out_img_stride, int N, int H0,
-                                               int W0, int act, int emit_skip, cudaStream_t stream) {
-  UNCL_REQUIRE(N > 0 && x != nullptr && fw != nullptr && fbias != nullptr && w_rows != nullptr && out != nullptr && H0 > 4 && W0 > 4,
+extern "C" int uncl_conv_first_conv3x3_tc_rows(const float* x, long x_img_stride, const void* fw, const void* w_rows,
+                                               const float* bias, void* out, long out_img_stride, int N, int H0, int W0, int act,
+                                               int emit_skip, cudaStream_t stream) {
+  UNCL_REQUIRE(N > 0 && x != nullptr && fw != nullptr && w_rows != nullptr && out != nullptr && H0 > 4 && W0 > 4,
                "conv_first_conv3x3_tc_rows: bad arguments (N=%d H0=%d W0=%d)", N, H0, W0);
   UNCL_REQUIRE(act == UNCL_ACT_RELU || act == UNCL_ACT_NONE, "conv_first_conv3x3_tc_rows: only ReLU / identity epilogues are built");
   const int Wo = W0 - 4;
   UNCL_REQUIRE(rw_cols(Wo) == Wo, "conv_first_conv3x3_tc_rows: %d output columns are not whole 126-column bands", Wo);
   return rw_launch(nullptr, 0, w_rows, bias, out, out_img_stride, N, 32, H0 - 2, W0 - 2, 32, 0, Wo, act, emit_skip, 0, nullptr, nullptr,
-                   nullptr, nullptr, 0, "conv_first_conv3x3_tc_rows", stream, x, x_img_stride, fw, fbias);
+                   nullptr, nullptr, 0, "conv_first_conv3x3_tc_rows", stream, x, x_img_stride, fw);
 }
 
 // uncl_conv3x3_tc_skipcat (fused skip operators, `in` = [skip (C_skip) | up-sampled (C_skip)], C_out = 32) through the row

@@ -158,7 +158,7 @@ class _GeneratorBase(nn.Module):
         with torch.no_grad():
             P["inc0"] = (packing.conv_first(self.inc.conv.conv.weight.detach()), self.inc.conv.conv.bias.detach().float().contiguous())
             if tc:
-                P["inc0_rows"] = packing.conv_first_rows(self.inc.conv.conv.weight.detach())
+                P["inc0_rows"] = packing.conv_first_rows(self.inc.conv.conv.weight.detach(), self.inc.conv.conv.bias.detach())
             conv("inc1", self.inc.conv.conv1, False)
             for i in range(4):
                 blk = self.down_path[i].mpconv[1]
@@ -243,7 +243,7 @@ class _GeneratorBase(nn.Module):
         cat = [buf((2 if i < nfused else 4) * c, s, s) for i, (c, s) in enumerate(sizes)]
         if (self.precision == "bf16" and self.row_kernel and self.fused_first and keep is None and "inc1_rows" in P
                 and "inc0_rows" in P):
-            call("uncl_conv_first_conv3x3_tc_rows", x, x.stride(0), P["inc0_rows"], P["inc0"][1], P["inc1_rows"], P["inc1"][1],
+            call("uncl_conv_first_conv3x3_tc_rows", x, x.stride(0), P["inc0_rows"], P["inc1_rows"], P["inc1"][1],
                  cat[0], st(cat[0]), n, 256, 256, ACT_RELU, 0 if nfused > 0 else 1)
         else:
             a0 = buf(f, 254, 254)

@@ -177,14 +177,15 @@ def conv_first_layout(w):
     return w.reshape(w.shape[0], 9).t().contiguous()
 
 
-def conv_first_rows(w):
-    """Conv2d(1, 32, 3) weight [32][1][3][3] -> the B operand of the row kernel's front mode (uncl_conv_first_conv3x3_tc_rows):
-    bf16 [2 (w_hi, w_lo)][2 K halves][32 (co)][8 (tap in half)], taps 9..15 zero."""
-    w9 = w.reshape(w.shape[0], 9).t().float()                      # [9][32]
-    hi = w9.to(torch.bfloat16)
-    lo = (w9 - hi.float()).to(torch.bfloat16)
+def conv_first_rows(w, b):
+    """Conv2d(1, 32, 3) weight [32][1][3][3] + bias [32] -> the B operand of the row kernel's front mode
+    (uncl_conv_first_conv3x3_tc_rows): bf16 [2 (hi, lo)][2 K halves][32 (co)][8 (tap in half)]; tap 9 holds the bias (its
+    input is the constant 1), taps 10..15 are zero."""
+    w10 = torch.cat([w.reshape(w.shape[0], 9).t().float(), b.reshape(1, -1).float()], dim=0)     # [10][32]
+    hi = w10.to(torch.bfloat16)
+    lo = (w10 - hi.float()).to(torch.bfloat16)
     t = torch.zeros((2, 16, w.shape[0]), device=w.device, dtype=torch.bfloat16)
-    t[0, :9], t[1, :9] = hi, lo
+    t[0, :10], t[1, :10] = hi, lo
     return t.reshape(2, 2, 8, w.shape[0]).permute(0, 1, 3, 2).contiguous()
 
 
