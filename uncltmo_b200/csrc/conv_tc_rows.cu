@@ -445,23 +445,30 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
       const uint32_t bw_16 = fscr_16 + (uint32_t)(2 * kRwFrontScratch >> 4);
       const int H0 = p.H0, W0 = p.W0, Ha = H0 - 2, Wa = W0 - 2;
       // im2col rows (x_hi, x_lo) of the four output rows of the stage that starts at row `ya0` of image `n`, into buffer `buf`
-      auto build = [&](int n, int ya0, int xa, int buf) {
+      // the 6 x 3 input pixels behind this lane's four output pixels (issued early: their latency hides behind the epilogue)
+      auto fetch = [&](int n, int ya0, int xa, float (&v)[G + 2][3]) {
         const float* xn = p.fx + (long)n * p.fx_img_stride;
-        // the 6 x 3 input pixels behind this lane's four output pixels, split x = x_hi + x_lo (x_hi kept as an fp32 whose low
-        // 16 bits are zero: two of them pack into a bf16x2 with one PRMT)
-        uint32_t hb[G + 2][3];
-        float lo[G + 2][3];
         const bool xin = xa >= 0 && xa + 2 < W0;
 #pragma unroll
         for (int j = 0; j < G + 2; ++j) {
           const int yi = ya0 + j;
           const bool in = xin && yi >= 0 && yi < H0;
 #pragma unroll
+          for (int c = 0; c < 3; ++c) v[j][c] = in ? __ldg(xn + (long)yi * W0 + xa + c) : 0.f;
+        }
+      };
+      // ... split x = x_hi + x_lo (x_hi kept as an fp32 whose low 16 bits are zero: two of them pack into a bf16x2 with one PRMT)
+      // and written as the im2col rows of the four output rows
+      auto build = [&](const float (&v)[G + 2][3], int buf) {
+        uint32_t hb[G + 2][3];
+        float lo[G + 2][3];
+#pragma unroll
+        for (int j = 0; j < G + 2; ++j) {
+#pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float v = in ? __ldg(xn + (long)yi * W0 + xa + c) : 0.f;
-            const float h = __bfloat162float(__float2bfloat16_rn(v));
+            const float h = __bfloat162float(__float2bfloat16_rn(v[j][c]));
             hb[j][c] = __float_as_uint(h);
-            lo[j][c] = v - h;
+            lo[j][c] = v[j][c] - h;
           }
         }
 #pragma unroll
@@ -503,7 +510,9 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
       if (fw_ == 0) mbar_wait(wfull, 0);             // the filter tiles have landed (only the issuing warp needs to know)
       int item = blockIdx.x, r0 = 0;
       RwItem it = rw_decode(p, item);
-      build(it.n, it.by, it.bx + pos, 0);
+      float xv[G + 2][3];
+      fetch(it.n, it.by, it.bx + pos, xv);
+      build(xv, 0);
       tc_fence_before();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       issue(0);
@@ -516,7 +525,7 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
           if (nitem < num_items) nit = rw_decode(p, nitem);
         }
         const bool has_next = nitem < num_items;
-        if (has_next) build(nit.n, nit.by + nr0, nit.bx + pos, buf ^ 1);
+        if (has_next) fetch(nit.n, nit.by + nr0, nit.bx + pos, xv);
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_wait(fbar, fpar);
         fpar ^= 1;
@@ -541,6 +550,7 @@ conv3x3_tc_rows_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             *reinterpret_cast<uint4*>(sa + g * (G * kRwRowBytes) + r * kRwRowBytes) = o;
           }
         }
+        if (has_next) build(xv, buf ^ 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         asm volatile("bar.sync 1, 128;" ::: "memory");   // every warp has read its accumulators and built its share of the next tiles
