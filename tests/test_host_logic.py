@@ -380,3 +380,20 @@ def test_row_kernel_plan_and_packing():
     for ky, kx, ci, co in [(0, 0, 0, 0), (2, 1, 37, 5), (1, 2, 63, 31), (0, 2, 16, 9)]:
         chunk, ks, half, k8 = ci // 32, (ci % 32) // 16, (ci % 16) // 8, ci % 8
         assert t[chunk, ks, kx, half, ky * 32 + co, k8] == w9[ky * 3 + kx, ci, co]
+
+
+def test_conv_first_rows_packing():
+    """Filter tiles of the row kernel's front mode (inc.conv computed inside inc.conv1's launch): [hi | lo][K half][co][tap in
+    half] with the bias on tap 9 (its im2col input is the constant 1) and hi + lo reproducing the fp32 weights to 2^-16."""
+    import torch
+    from uncltmo_b200 import packing
+    g = torch.Generator().manual_seed(0)
+    w, b = torch.randn((32, 1, 3, 3), generator=g), torch.randn(32, generator=g)
+    t = packing.conv_first_rows(w, b)
+    assert tuple(t.shape) == (2, 2, 32, 8) and t.dtype == torch.bfloat16
+    full = t.float().permute(0, 1, 3, 2).reshape(2, 16, 32)            # [hi | lo][tap][co]
+    rec = full[0] + full[1]
+    want = torch.cat([w.reshape(32, 9).t(), b.reshape(1, 32)], dim=0)
+    assert (rec[:10] - want).abs().max().item() <= 2.0 ** -15 * want.abs().max().item()
+    assert (full[:, 10:] == 0).all()
+    assert torch.equal(full[0, :10], want.to(torch.bfloat16).float())
