@@ -131,3 +131,10 @@ def call(name, *args):
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, l.uncl_last_error().decode()))
     _launches += KERNELS_PER_CALL.get(name, 1)
+    if name in ("uncl_conv3x3_tc_rows", "uncl_conv3x3_tc_rows_skipcat"):
+        # the row kernel leaves the columns past the last whole 126-column band to a second launch of the older kernels
+        # (conv_tc_rows.cu:rw_cols): args[10] = W, args[12] / args[11] = pad
+        w, pad = args[10], (args[12] if name == "uncl_conv3x3_tc_rows" else args[11])
+        wo = w + 2 * pad - 2
+        if wo >= 126 and 0 < wo % 126 < 64:
+            _launches += 1
