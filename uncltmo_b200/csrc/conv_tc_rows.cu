@@ -1,18 +1,26 @@
-// 3x3 stride-1 convolution / ConvTranspose 3x3 with C_out = 32 on the tensor cores, the three ky taps (filter ROWS)
-// merged into the N dimension of one tcgen05.mma and the input streamed through shared memory ONE IMAGE ROW AT A TIME.
+// 3x3 stride-1 convolution / ConvTranspose 3x3 for the NARROW, LARGE layers of the generator (C_out = 32 / 64 at 122..256
+// pixels) on the tensor cores: the three ky taps (filter ROWS) merged into the N dimension of one tcgen05.mma, the input
+// streamed through shared memory ONE IMAGE ROW AT A TIME, accumulators rotating through TMEM.
 //
-// Why (profiles/r1_mma_probe.csv, DESIGN.md 3.1b): a kind::f16 M=128 K=16 instruction reads its 4 KB A tile at
+// Why (profiles/r1_mma_probe.csv, DESIGN.md 3.1b / 3.1c): a kind::f16 M=128 K=16 instruction reads its 4 KB A tile at
 // 128 B/cycle whatever N is, so N = C_out = 32 runs at 16/40 of the tensor peak.  conv_tc_merged.cu merges the three kx
 // taps (N' = 96: 56 cycles for three taps) but pays for it twice: its accumulator rows of one output pixel sit in
 // neighbouring TMEM LANES (a shuffle / shared-memory exchange epilogue of ~7500 warp instructions per tile) and every
 // 2-row tile reloads a 4-row halo box (2x the input through the shared-memory port the MMAs already saturate).  Here
 //     M block  = one input row of a 126-column band (128 positions, pitch 128)
-//     D_r[x][ky*32 + co] = sum_{kx, ci} X[r][x + kx][ci] * W[ky][kx][ci][co]      (3 kx x C_in/16 MMAs of N' = 96 per row;
+//     D_r[x][ky*C + co]  = sum_{kx, ci} X[r][x + kx][ci] * W[ky][kx][ci][co]      (3 kx x C_in/16 MMAs of N' = 3 C per row;
 //                                                                                  kx = descriptor start + kx*16 B)
-//     out[y][x][co]      = D_y[x][co] + D_{y+1}[x][32 + co] + D_{y+2}[x][64 + co]
-// The three terms of an output pixel are in the SAME TMEM lane of three different accumulator slots, so the epilogue is
-// three lane-aligned tcgen05.ld + 64 adds per thread, and every input row is loaded into shared memory exactly once
-// per strip (a CTA walks a strip of R output rows = R + 2 input rows; 5 accumulator slots of 96 TMEM columns rotate).
+//     out[y][x][co]      = D_y[x][co] + D_{y+1}[x][C + co] + D_{y+2}[x][2C + co]
+// The three terms of an output pixel are in the SAME TMEM lane, and every input row is loaded into shared memory exactly
+// once per strip (a CTA walks a strip of R output rows = R + 2 input rows).  Three variants behind one template:
+//   slot  (C_out = 32, several K chunks per row, incl. the fused skip operators): five accumulator slots of 96 columns, a
+//         row's MMAs are an ordinary K loop into its slot, the epilogue adds the three column groups from three slots;
+//   ring  (one-chunk layers, C_out = 64): output row u owns ONE group of C columns at position (-u) mod 16 (mod 8), the
+//         N' columns of input row r land on the adjacent groups of outputs r, r-1, r-2, every MMA accumulates, the
+//         epilogue reads one group and hands it back cleared;
+//   front (inc.conv1): ring of twelve groups; the stage ring is not loaded by TMA but COMPUTED - four extra warps build
+//         inc.conv (1 -> 32, unet_parts.py:57-87 with in_ch = 1) from the fp32 image with im2col rows and three-term
+//         bf16 split MMAs, so that layer's output never reaches memory.
 // The fused skip operators (unet_parts.py:319-322: x^2, sqrt(x + 1e-8) of the skip tensor built in shared memory) use
 // the same ring program as conv_tc_merged.cu, one row group at a time - each skip row is transformed once, not twice.
 //
@@ -20,7 +28,7 @@
 // columns past the last whole band (2 of 254, 4 of 256) to the older kernels (x0 argument), see conv_tc.cu.
 // Reference operator: models/unet_multi_filters/unet_parts.py:57-87 (double_conv), :126-141 / :183-193 (ConvTranspose
 // 3x3 pair of `up`), :311-332 (skip operators + concat), :338-345 (outconv).
-// Weights: bf16 [C_in/32][2 ksteps][3 kx][2][96 (ky, co)][8] (packing.conv3x3_tc_rows).
+// Weights: bf16 [C_in/32][2 ksteps][3 kx][2][3 C_out (ky, co)][8] (packing.conv3x3_tc_rows).
 #include <cstdio>
 #include <cstdlib>
 
@@ -36,8 +44,8 @@ using namespace tcptx;
 // the epilogue warps' instruction stream (six sets were slower than four: 344 -> 550 us on inc.conv1 - more warps only
 // dilute the issue slots).  The one-chunk layers therefore use the ring variant below (one tcgen05.ld per output row).
 constexpr int kRwSets = 4, kRwSetsDerive = 4;
-constexpr int kRwThreads = (2 + 4 * kRwSets) * 32;                 // 832
-constexpr int kRwDeriveWarp0 = 2 + 4 * kRwSetsDerive;              // warps 18-21: skip-operator warps
+constexpr int kRwThreads = (2 + 4 * kRwSets) * 32;                 // 576
+constexpr int kRwDeriveWarp0 = 2 + 4 * kRwSetsDerive;              // warps 18-21: skip-operator warps, or the first-conv warps of the front mode
 constexpr int kRwThreadsDerive = (kRwDeriveWarp0 + 4) * 32;        // 704
 constexpr int kRwDeriveWarps = 4;
 constexpr int kRwMaxStages = 8;
